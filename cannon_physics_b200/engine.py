@@ -1,0 +1,314 @@
+"""SoA-level wrapper over the C ABI (``include/cannon_cuda.h``).
+
+``DeviceWorld`` is the thin, array-oriented handle the reference-shaped classes in ``api.py`` and the
+scene generators in ``scenes.py`` sit on.  It works with any library bound by ``_ffi.bind`` — the
+package passes its own ``libcannon_cuda.so``; the parity tests also pass the CPU checker.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi as F
+
+
+@dataclass
+class SceneSpec:
+    """Plain-data description of a world: what ``World.addBody`` & co. would have built."""
+    desc: Dict = field(default_factory=dict)              # cannon_world_desc overrides
+    shapes: List[Dict] = field(default_factory=list)      # cannon_shape_desc overrides
+    bodies: Dict[str, np.ndarray] = field(default_factory=dict)  # cannon_bodies_soa arrays
+    n_bodies: int = 0
+    material_friction: Optional[np.ndarray] = None
+    material_restitution: Optional[np.ndarray] = None
+    contact_materials: List[Dict] = field(default_factory=list)
+    constraints: List[Dict] = field(default_factory=list)
+    name: str = ""
+
+
+def _check(lib, ctx, code):
+    if code != F.OK:
+        msg = lib.cannon_last_error(ctx)
+        raise F.CannonError(code, msg.decode() if msg else "")
+
+
+class Context:
+    def __init__(self, lib, device: int = 0):
+        self.lib = lib
+        self.handle = F.VP()
+        code = lib.cannon_ctx_create(device, C.byref(self.handle))
+        if code != F.OK:
+            raise F.CannonError(code, "cannon_ctx_create failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if self.handle:
+            self.lib.cannon_ctx_destroy(self.handle)
+            self.handle = F.VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_world_desc(lib, **kw) -> F.WorldDesc:
+    d = F.WorldDesc()
+    lib.cannon_world_desc_default(C.byref(d))
+    for k, v in kw.items():
+        if k == "default_contact_material":
+            for kk, vv in v.items():
+                setattr(d.default_contact_material, kk, vv)
+        elif k in ("gravity", "friction_gravity", "grid_min", "grid_max"):
+            arr = getattr(d, k)
+            vv = np.asarray(v, dtype=np.float32)
+            for i in range(3):
+                arr[i] = float(vv[i])
+        else:
+            if not hasattr(d, k):
+                raise KeyError(k)
+            setattr(d, k, v)
+    return d
+
+
+class DeviceWorld:
+    """One ``cannon_world`` handle."""
+
+    def __init__(self, lib, spec: SceneSpec, ctx: Optional[Context] = None, device: int = 0):
+        self.lib = lib
+        self.ctx = ctx or Context(lib, device)
+        self.spec = spec
+        self._keep = []  # host arrays referenced by descriptors during the calls
+        desc = make_world_desc(lib, **spec.desc)
+        self.desc = desc
+        self.handle = F.VP()
+        self._chk(lib.cannon_world_create(self.ctx.handle, C.byref(desc), C.byref(self.handle)))
+        self.n = 0
+        self.set_materials(spec.material_friction, spec.material_restitution, spec.contact_materials)
+        self.set_shapes(spec.shapes)
+        self.set_bodies(spec.bodies, spec.n_bodies)
+        if spec.constraints:
+            self.set_constraints(spec.constraints)
+
+    def _chk(self, code):
+        _check(self.lib, self.ctx.handle, code)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cannon_world_destroy(self.handle)
+            self.handle = F.VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- uploads -------------------------------------------------------------------------------
+    def set_materials(self, friction, restitution, cms: Sequence[Dict]):
+        n = 0 if friction is None else len(friction)
+        fr = None if friction is None else np.ascontiguousarray(friction, dtype=np.float64)
+        re = None if restitution is None else np.ascontiguousarray(restitution, dtype=np.float64)
+        arr = (F.ContactMaterialPOD * max(1, len(cms)))()
+        for i, cm in enumerate(cms):
+            pod = arr[i]
+            pod.friction, pod.restitution = 0.3, 0.3
+            pod.contact_equation_stiffness, pod.contact_equation_relaxation = 1e7, 3
+            pod.friction_equation_stiffness, pod.friction_equation_relaxation = 1e7, 3
+            for k, v in cm.items():
+                setattr(pod, k, v)
+        self._chk(self.lib.cannon_world_set_materials(self.handle, n, F.ptr(fr, F.c_f64), F.ptr(re, F.c_f64), len(cms), arr))
+
+    def set_shapes(self, shapes: Sequence[Dict]):
+        arr = (F.ShapeDesc * max(1, len(shapes)))()
+        keep = []
+        for i, sh in enumerate(shapes):
+            d = arr[i]
+            self.lib.cannon_shape_desc_default(C.byref(d))
+            for k, v in sh.items():
+                if k == "half_extents":
+                    vv = np.asarray(v, dtype=np.float32)
+                    for j in range(3):
+                        d.half_extents[j] = float(vv[j])
+                elif k == "vertices":
+                    a = np.ascontiguousarray(v, dtype=np.float32).reshape(-1, 3)
+                    keep.append(a)
+                    d.vertices = F.ptr(a, F.c_f32)
+                    d.n_vertices = a.shape[0]
+                elif k == "faces":
+                    offs = np.zeros(len(v) + 1, dtype=np.int32)
+                    offs[1:] = np.cumsum([len(f) for f in v])
+                    idx = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.int32) for f in v]))
+                    keep += [offs, idx]
+                    d.face_offsets, d.face_indices, d.n_faces = F.ptr(offs, F.c_i32), F.ptr(idx, F.c_i32), len(v)
+                elif k == "hf_data":
+                    a = np.ascontiguousarray(v, dtype=np.float64)
+                    assert a.ndim == 2
+                    keep.append(a)
+                    d.hf_data, d.hf_nx, d.hf_ny = F.ptr(a, F.c_f64), a.shape[0], a.shape[1]
+                else:
+                    if not hasattr(d, k):
+                        raise KeyError(k)
+                    setattr(d, k, v)
+        self._chk(self.lib.cannon_world_set_shapes(self.handle, len(shapes), arr))
+        self.n_shapes = len(shapes)
+
+    def _soa(self, arrays: Dict[str, np.ndarray], n: int, allocate: Sequence[str] = ()):
+        soa = F.BodiesSoA()
+        soa.n = n
+        held = {}
+        for name, ct, dt, k in F.BODY_FIELDS:
+            a = arrays.get(name)
+            if a is None and name in allocate:
+                a = np.zeros((n, k) if k > 1 else (n,), dtype=dt)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=dt)
+                assert a.size == n * k, f"{name}: expected {n}x{k} values, got {a.shape}"
+                held[name] = a
+                setattr(soa, name, F.ptr(a, ct))
+        return soa, held
+
+    def set_bodies(self, arrays: Dict[str, np.ndarray], n: int):
+        arrays = {k: v for k, v in arrays.items() if k not in F.DERIVED_BODY_FIELDS}
+        soa, held = self._soa(arrays, n)
+        self._chk(self.lib.cannon_world_set_bodies(self.handle, C.byref(soa)))
+        self.n = n
+
+    def set_constraints(self, cons: Sequence[Dict]):
+        arr = (F.ConstraintDesc * max(1, len(cons)))()
+        for i, c in enumerate(cons):
+            d = arr[i]
+            d.max_force = 1e6
+            d.collide_connected = 1
+            d.axis_a[0] = 1.0
+            d.axis_b[0] = 1.0
+            for k, v in c.items():
+                if k in ("pivot_a", "pivot_b", "axis_a", "axis_b"):
+                    vv = np.asarray(v, dtype=np.float32)
+                    a = getattr(d, k)
+                    for j in range(3):
+                        a[j] = float(vv[j])
+                else:
+                    setattr(d, k, v)
+        self._chk(self.lib.cannon_world_set_constraints(self.handle, len(cons), arr))
+
+    def update_bodies(self, first: int, count: int, **arrays):
+        args = []
+        for name in ("position", "quaternion", "velocity", "angular_velocity", "force", "torque"):
+            a = arrays.get(name)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                self._keep.append(a)
+            args.append(F.ptr(a, F.c_f32))
+        self._chk(self.lib.cannon_world_update_bodies(self.handle, first, count, *args))
+        self._keep.clear()
+
+    # ---- downloads -----------------------------------------------------------------------------
+    def get_bodies(self, fields: Sequence[str] = ("position", "quaternion", "velocity", "angular_velocity")) -> Dict[str, np.ndarray]:
+        soa, held = self._soa({}, self.n, allocate=fields)
+        self._chk(self.lib.cannon_world_get_bodies(self.handle, C.byref(soa)))
+        return held
+
+    def get_time(self):
+        t, s = F.c_f64(), F.c_i64()
+        self._chk(self.lib.cannon_world_get_time(self.handle, C.byref(t), C.byref(s)))
+        return t.value, s.value
+
+    def set_time(self, t: float):
+        self._chk(self.lib.cannon_world_set_time(self.handle, t))
+
+    def set_dt(self, dt: float):
+        self._chk(self.lib.cannon_world_set_dt(self.handle, dt))
+
+    # ---- staged --------------------------------------------------------------------------------
+    def apply_gravity(self):
+        self._chk(self.lib.cannon_apply_gravity(self.handle))
+
+    def broadphase_pairs(self, cap: Optional[int] = None):
+        cap = cap or max(1024, 16 * self.n)
+        while True:
+            p1 = np.empty(cap, dtype=np.int32)
+            p2 = np.empty(cap, dtype=np.int32)
+            n = F.c_i32()
+            code = self.lib.cannon_broadphase_pairs(self.handle, F.ptr(p1, F.c_i32), F.ptr(p2, F.c_i32), cap, C.byref(n))
+            if code == F.E_CAPACITY:
+                cap = n.value
+                continue
+            self._chk(code)
+            return p1[: n.value].copy(), p2[: n.value].copy()
+
+    @staticmethod
+    def _contacts_buffers(cap):
+        bufs = {
+            "body_i": np.zeros(cap, np.int32), "body_j": np.zeros(cap, np.int32),
+            "ri": np.zeros((cap, 3), np.float32), "rj": np.zeros((cap, 3), np.float32), "ni": np.zeros((cap, 3), np.float32),
+            "restitution": np.zeros(cap, np.float64), "friction": np.zeros(cap, np.float64),
+            "enabled": np.zeros(cap, np.uint8), "multiplier": np.zeros(cap, np.float64),
+        }
+        soa = F.ContactsSoA()
+        soa.capacity = cap
+        soa.body_i, soa.body_j = F.ptr(bufs["body_i"], F.c_i32), F.ptr(bufs["body_j"], F.c_i32)
+        soa.ri, soa.rj, soa.ni = F.ptr(bufs["ri"], F.c_f32), F.ptr(bufs["rj"], F.c_f32), F.ptr(bufs["ni"], F.c_f32)
+        soa.restitution, soa.friction = F.ptr(bufs["restitution"], F.c_f64), F.ptr(bufs["friction"], F.c_f64)
+        soa.enabled, soa.multiplier = F.ptr(bufs["enabled"], F.c_u8), F.ptr(bufs["multiplier"], F.c_f64)
+        return soa, bufs
+
+    def narrowphase_contacts(self, p1: np.ndarray, p2: np.ndarray, cap: Optional[int] = None):
+        p1 = np.ascontiguousarray(p1, dtype=np.int32)
+        p2 = np.ascontiguousarray(p2, dtype=np.int32)
+        np_ = len(p1)
+        cap = cap or max(1024, 8 * np_)
+        per_pair = np.zeros(max(1, np_), dtype=np.int32)
+        while True:
+            soa, bufs = self._contacts_buffers(cap)
+            n = F.c_i32()
+            code = self.lib.cannon_narrowphase_contacts(self.handle, F.ptr(p1, F.c_i32), F.ptr(p2, F.c_i32), np_, C.byref(soa),
+                                                        C.byref(n), F.ptr(per_pair, F.c_i32))
+            if code == F.E_CAPACITY:
+                cap = max(n.value, 2 * cap)
+                continue
+            self._chk(code)
+            out = {k: v[: n.value].copy() for k, v in bufs.items()}
+            out["per_pair_count"] = per_pair[:np_].copy()
+            return out
+
+    def solver_solve(self, dt: float) -> int:
+        it = F.c_i32()
+        self._chk(self.lib.cannon_solver_solve(self.handle, dt, C.byref(it)))
+        return it.value
+
+    def integrate(self, dt: float):
+        self._chk(self.lib.cannon_integrate(self.handle, dt))
+
+    # ---- fused ---------------------------------------------------------------------------------
+    def step(self, dt: float, nsteps: int = 1):
+        self._chk(self.lib.cannon_world_step(self.handle, dt, nsteps))
+
+    def profile(self) -> Dict[str, float]:
+        p = F.Profile()
+        self._chk(self.lib.cannon_world_profile(self.handle, C.byref(p)))
+        return {name: getattr(p, name) for name, _ in F.Profile._fields_}
+
+    def get_contacts(self):
+        n = F.c_i32()
+        self._chk(self.lib.cannon_world_get_contacts(self.handle, None, C.byref(n)))
+        soa, bufs = self._contacts_buffers(max(1, n.value))
+        self._chk(self.lib.cannon_world_get_contacts(self.handle, C.byref(soa), C.byref(n)))
+        return {k: v[: n.value].copy() for k, v in bufs.items()}
+
+    def get_rows(self):
+        n = F.c_i32()
+        code = self.lib.cannon_world_get_rows(self.handle, 0, C.byref(n), None, None, None, None, None, None)
+        if code not in (F.OK, F.E_CAPACITY):
+            self._chk(code)
+        cap = max(1, n.value)
+        bi, bj = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        B, invC, lam = np.zeros(cap, np.float64), np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+        lvl = np.zeros(cap, np.int32)
+        self._chk(self.lib.cannon_world_get_rows(self.handle, cap, C.byref(n), F.ptr(bi, F.c_i32), F.ptr(bj, F.c_i32),
+                                                 F.ptr(B, F.c_f64), F.ptr(invC, F.c_f64), F.ptr(lam, F.c_f64), F.ptr(lvl, F.c_i32)))
+        k = n.value
+        return {"body_i": bi[:k], "body_j": bj[:k], "B": B[:k], "invC": invC[:k], "lambda": lam[:k], "level": lvl[:k]}

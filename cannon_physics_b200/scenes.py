@@ -1,0 +1,270 @@
+"""Seeded synthetic scenes for the BASELINE.json configurations.
+
+Generator = splitmix64(seed) -> uniform f64 in [0,1) -> cast to f32 at store, so the same scene can be
+rebuilt bit-identically anywhere (the reference demos use unseeded ``math.Random()``).
+Every generator takes size parameters so the parity tests can run reduced instances of the same recipe.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _ffi as F
+from .engine import SceneSpec
+
+_MASK = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed: int):
+        self.s = seed & _MASK
+
+    def next_u64(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _MASK
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK
+        return z ^ (z >> 31)
+
+    def uniform(self, n: int) -> np.ndarray:
+        """n uniform f64 in [0,1) (vectorised: the stream is the sequential splitmix64 stream)."""
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            z = np.uint64(self.s) + idx * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        self.s = (self.s + n * 0x9E3779B97F4A7C15) & _MASK
+        return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+
+def quat_from_euler(x: float, y: float, z: float) -> np.ndarray:
+    """Quat.setFromEuler, order XYZ (lib/math/quaternion.dart:191-203), rounded to f32 at store."""
+    c1, c2, c3 = math.cos(x / 2), math.cos(y / 2), math.cos(z / 2)
+    s1, s2, s3 = math.sin(x / 2), math.sin(y / 2), math.sin(z / 2)
+    return np.array([s1 * c2 * c3 + c1 * s2 * s3, c1 * s2 * c3 - s1 * c2 * s3, c1 * c2 * s3 + s1 * s2 * c3,
+                     c1 * c2 * c3 - s1 * s2 * s3], dtype=np.float32)
+
+
+GROUND_QUAT = quat_from_euler(-math.pi / 2, 0.0, 0.0)
+
+
+def _base_bodies(n: int):
+    q = np.zeros((n, 4), np.float32)
+    q[:, 3] = 1.0
+    return {
+        "position": np.zeros((n, 3), np.float32), "quaternion": q,
+        "velocity": np.zeros((n, 3), np.float32), "angular_velocity": np.zeros((n, 3), np.float32),
+        "mass": np.zeros(n, np.float64), "shape": np.zeros(n, np.int32), "material": np.full(n, -1, np.int32),
+    }
+
+
+def _random_unit_quats(rng: SplitMix64, n: int) -> np.ndarray:
+    u = rng.uniform(3 * n).reshape(n, 3)
+    u1, u2, u3 = u[:, 0], u[:, 1], u[:, 2]
+    q = np.stack([np.sqrt(1 - u1) * np.sin(2 * np.pi * u2), np.sqrt(1 - u1) * np.cos(2 * np.pi * u2),
+                  np.sqrt(u1) * np.sin(2 * np.pi * u3), np.sqrt(u1) * np.cos(2 * np.pi * u3)], axis=1)
+    return q.astype(np.float32)
+
+
+def spheres_on_plane(nx=10, ny=10, nz=10, seed=1, radius=0.25, spacing=0.6, y0=1.0, jitter=0.05,
+                     broadphase=F.BP_NAIVE, iterations=10, solver=F.SOLVER_REFERENCE_ORDER) -> SceneSpec:
+    """config 1: nx*ny*nz spheres dropped on a plane (NaiveBroadphase + GSSolver 10 it, dt=1/60)."""
+    n = nx * ny * nz + 1
+    rng = SplitMix64(seed)
+    b = _base_bodies(n)
+    b["quaternion"][0] = GROUND_QUAT
+    b["shape"][0] = 0
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    jit = (rng.uniform(3 * (n - 1)).reshape(n - 1, 3) * 2 - 1) * jitter
+    pos = np.stack([(ii.ravel() - (nx - 1) / 2) * spacing, y0 + jj.ravel() * spacing, (kk.ravel() - (nz - 1) / 2) * spacing], axis=1) + jit
+    b["position"][1:] = pos.astype(np.float32)
+    b["mass"][1:] = 1.0
+    b["shape"][1:] = 1
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=broadphase, solver_iterations=iterations, solver_kind=solver),
+        shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_SPHERE, radius=radius)],
+        bodies=b, n_bodies=n, name=f"c1_spheres_on_plane_{nx}x{ny}x{nz}")
+
+
+def box_stacks(n_stacks=250, height=20, seed=2, he=0.5, grid=16, pitch=2.0, gap=0.02, jitter=0.01,
+               broadphase=F.BP_SAP, iterations=20, solver=F.SOLVER_REFERENCE_ORDER) -> SceneSpec:
+    """config 2: `height`-high box stacks with friction/restitution, SAPBroadphase axis x, GSSolver 20 it."""
+    n = n_stacks * height + 1
+    rng = SplitMix64(seed)
+    b = _base_bodies(n)
+    b["quaternion"][0] = GROUND_QUAT
+    b["shape"][0] = 0
+    b["material"][:] = 0
+    s = np.arange(n_stacks)
+    gx, gz = s % grid, s // grid
+    jit = (rng.uniform(2 * n_stacks * height).reshape(n_stacks, height, 2) * 2 - 1) * jitter
+    k = np.arange(height)
+    px = (gx[:, None] - (grid - 1) / 2) * pitch + jit[:, :, 0]
+    pz = (gz[:, None] - (grid - 1) / 2) * pitch + jit[:, :, 1]
+    py = np.broadcast_to(he + k[None, :] * (2 * he + gap), (n_stacks, height))
+    b["position"][1:] = np.stack([px.ravel(), py.ravel(), pz.ravel()], axis=1).astype(np.float32)
+    b["mass"][1:] = 1.0
+    b["shape"][1:] = 1
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=broadphase, sap_axis=0, solver_iterations=iterations, solver_kind=solver),
+        shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_BOX, half_extents=(he, he, he))],
+        bodies=b, n_bodies=n,
+        material_friction=np.array([-1.0]), material_restitution=np.array([-1.0]),
+        contact_materials=[dict(material_a=0, material_b=0, friction=0.3, restitution=0.2)],
+        name=f"c2_box_stacks_{n_stacks}x{height}")
+
+
+def heightfield_data(nsamp: int) -> np.ndarray:
+    """h(i,j) = cos(2*pi*i/n)*cos(2*pi*j/n)+2, border rows/cols = 3 (examples/lib/examples/heightfield.dart:46-60)."""
+    i = np.arange(nsamp, dtype=np.float64)
+    h = np.cos(2 * np.pi * i[:, None] / nsamp) * np.cos(2 * np.pi * i[None, :] / nsamp) + 2.0
+    h[0, :] = 3.0
+    h[-1, :] = 3.0
+    h[:, 0] = 3.0
+    h[:, -1] = 3.0
+    return h
+
+
+def mixed_pile_on_heightfield(nx=100, nz=100, layers=10, seed=3, hf_samples=257, pitch=2.4, layer_pitch=0.8,
+                              iterations=10, solver=F.SOLVER_COLORED, grid_cells=(128, 16, 128), with_heightfield=True,
+                              kinds=("sphere", "box", "cylinder")) -> SceneSpec:
+    """config 3: nx*nz*layers mixed sphere/box/cylinder pile on a heightfield, GridBroadphase, 10 it.
+
+    The lattice is centred over the heightfield (which spans hf_samples-1 units); pitch is shrunk when
+    the requested lattice would not fit so reduced instances keep every body above terrain.
+    """
+    n_dyn = nx * nz * layers
+    n = n_dyn + 1
+    rng = SplitMix64(seed)
+    b = _base_bodies(n)
+    size = float(hf_samples - 1)
+    hf = heightfield_data(hf_samples)
+    half = size / 2.0
+    if with_heightfield:
+        # body at (-size/2, -4, size/2), rotated -pi/2 about x (examples/lib/examples/heightfield.dart:69-74)
+        b["position"][0] = (-half, -4.0, half)
+        b["quaternion"][0] = GROUND_QUAT
+        shapes = [dict(type=F.SHAPE_HEIGHTFIELD, hf_data=hf, hf_element_size=1)]
+    else:
+        b["position"][0] = (0.0, -1.0, 0.0)
+        b["quaternion"][0] = GROUND_QUAT
+        shapes = [dict(type=F.SHAPE_PLANE)]
+    b["shape"][0] = 0
+    shape_ids = {}
+    for kname in kinds:
+        shape_ids[kname] = len(shapes)
+        if kname == "sphere":
+            shapes.append(dict(type=F.SHAPE_SPHERE, radius=0.25))
+        elif kname == "box":
+            shapes.append(dict(type=F.SHAPE_BOX, half_extents=(0.25, 0.25, 0.25)))
+        else:
+            shapes.append(dict(type=F.SHAPE_CYLINDER, radius_top=0.25, radius_bottom=0.25, height=0.5, num_segments=8))
+    pitch = min(pitch, (size - 4.0) / max(nx, nz))
+    ii, kk, ll = np.meshgrid(np.arange(nx), np.arange(nz), np.arange(layers), indexing="ij")
+    x = (ii.ravel() - (nx - 1) / 2) * pitch
+    z = (kk.ravel() - (nz - 1) / 2) * pitch
+    if with_heightfield:
+        # local heightfield coords: lx = x + half, ly = half - z (rotation -pi/2 about x maps local y -> -z)
+        lx = np.clip(np.rint(x + half).astype(int), 0, hf_samples - 1)
+        ly = np.clip(np.rint(half - z).astype(int), 0, hf_samples - 1)
+        ground = hf[lx, ly] - 4.0
+    else:
+        ground = np.full(n_dyn, -1.0)
+    y = ground + 1.0 + ll.ravel() * layer_pitch
+    jit = (rng.uniform(2 * n_dyn).reshape(n_dyn, 2) * 2 - 1) * 0.05
+    b["position"][1:] = np.stack([x + jit[:, 0], y, z + jit[:, 1]], axis=1).astype(np.float32)
+    kind_idx = np.arange(n_dyn) % len(kinds)
+    sid = np.array([shape_ids[k] for k in kinds], dtype=np.int32)[kind_idx]
+    b["shape"][1:] = sid
+    quats = _random_unit_quats(rng, n_dyn)
+    is_sphere = np.array([k == "sphere" for k in kinds])[kind_idx]
+    quats[is_sphere] = (0, 0, 0, 1)
+    b["quaternion"][1:] = quats
+    b["mass"][1:] = 1.0
+    lo = b["position"][1:].min(axis=0) - 1.0
+    hi = b["position"][1:].max(axis=0) + 1.0
+    lo[1] = min(lo[1], -6.0)
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=F.BP_GRID, grid_min=lo, grid_max=hi, grid_nx=grid_cells[0],
+                  grid_ny=grid_cells[1], grid_nz=grid_cells[2], solver_iterations=iterations, solver_kind=solver),
+        shapes=shapes, bodies=b, n_bodies=n, name=f"c3_mixed_pile_{nx}x{nz}x{layers}")
+
+
+def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver=F.SOLVER_REFERENCE_ORDER) -> SceneSpec:
+    """config 4: n_worlds independent worlds of 1 plane + chains*links boxes hanging as jointed chains.
+
+    Links are joined alternately by two corner PointToPointConstraints (examples/lib/examples/constraints.dart:135-146)
+    and a HingeConstraint (axis x); the top link of each chain has mass 0. Seed is seed + world index.
+    """
+    per = 1 + chains * links
+    n = n_worlds * per
+    b = _base_bodies(n)
+    b["world_id"] = np.repeat(np.arange(n_worlds, dtype=np.int32), per)
+    hx, hy, hz = 0.25, 0.25, 0.05
+    space = 0.1 * hy
+    cons = []
+    for w in range(n_worlds):
+        rng = SplitMix64(seed + w)
+        base = w * per
+        b["quaternion"][base] = GROUND_QUAT
+        b["shape"][base] = 0
+        anchors = (rng.uniform(2 * chains).reshape(chains, 2) * 2 - 1) * 0.5
+        for c in range(chains):
+            ax = (c - (chains - 1) / 2) * 1.5 + anchors[c, 0]
+            az = anchors[c, 1]
+            prev = -1
+            for l in range(links):
+                idx = base + 1 + c * links + l
+                b["position"][idx] = (ax, 6.0 - l * (2 * hy + 2 * space), az)
+                b["mass"][idx] = 0.0 if l == 0 else 0.3
+                b["shape"][idx] = 1
+                if l > 0:
+                    if l % 2 == 1:
+                        cons.append(dict(type=F.CONSTRAINT_POINT_TO_POINT, body_a=idx, body_b=prev,
+                                         pivot_a=(hx, hy + space, 0), pivot_b=(hx, -hy - space, 0)))
+                        cons.append(dict(type=F.CONSTRAINT_POINT_TO_POINT, body_a=idx, body_b=prev,
+                                         pivot_a=(-hx, hy + space, 0), pivot_b=(-hx, -hy - space, 0)))
+                    else:
+                        cons.append(dict(type=F.CONSTRAINT_HINGE, body_a=idx, body_b=prev,
+                                         pivot_a=(0, hy + space, 0), pivot_b=(0, -hy - space, 0),
+                                         axis_a=(1, 0, 0), axis_b=(1, 0, 0)))
+                prev = idx
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=F.BP_NAIVE, solver_iterations=iterations, solver_kind=solver,
+                  n_worlds=n_worlds),
+        shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_BOX, half_extents=(hx, hy, hz))],
+        bodies=b, n_bodies=n, constraints=cons, name=f"c4_chain_worlds_{n_worlds}x{per}")
+
+
+def sphere_container(nx=160, nz=160, ny=40, n_spheres=None, seed=5, radius=0.25, pitch=0.6, extent=100.0,
+                     iterations=10, solver=F.SOLVER_COLORED, allow_sleep=True, broadphase=F.BP_NAIVE) -> SceneSpec:
+    """config 5: granular sphere pile in a 5-plane container (floor + 4 walls, container.dart:62-100), sleeping on."""
+    n_dyn = n_spheres if n_spheres is not None else nx * ny * nz
+    n = n_dyn + 5
+    rng = SplitMix64(seed)
+    b = _base_bodies(n)
+    half = extent / 2
+    b["quaternion"][0] = GROUND_QUAT
+    b["quaternion"][1] = quat_from_euler(0, math.pi / 2, 0)
+    b["position"][1] = (-half, 0, 0)
+    b["quaternion"][2] = quat_from_euler(0, -math.pi / 2, 0)
+    b["position"][2] = (half, 0, 0)
+    b["quaternion"][3] = quat_from_euler(0, 0, 0)
+    b["position"][3] = (0, 0, -half)
+    b["quaternion"][4] = quat_from_euler(0, math.pi, 0)
+    b["position"][4] = (0, 0, half)
+    b["shape"][:5] = 0
+    site = np.arange(n_dyn)
+    ix, iz, iy = site % nx, (site // nx) % nz, site // (nx * nz)
+    jit = (rng.uniform(3 * n_dyn).reshape(n_dyn, 3) * 2 - 1) * 0.05
+    pos = np.stack([(ix - (nx - 1) / 2) * pitch, radius + 0.1 + iy * pitch, (iz - (nz - 1) / 2) * pitch], axis=1) + jit
+    b["position"][5:] = pos.astype(np.float32)
+    b["mass"][5:] = 1.0
+    b["shape"][5:] = 1
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=broadphase, solver_iterations=iterations, solver_kind=solver,
+                  allow_sleep=1 if allow_sleep else 0),
+        shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_SPHERE, radius=radius)],
+        bodies=b, n_bodies=n, name=f"c5_sphere_container_{n_dyn}")

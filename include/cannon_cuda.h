@@ -1,0 +1,275 @@
+/*
+ * cannon_cuda.h — C ABI of libcannon_cuda.so, the B200-native (sm_100a) implementation of the
+ * per-step rigid-body hot path of Knightro63/cannon_physics:
+ *
+ *     World.internalStep(dt)            lib/world/world_class.dart:433-701
+ *       broadphase.collisionPairs       lib/collision/{broadphase,naive_broadphase,sap_broadphase,grid_broadphase}.dart
+ *       narrowphase.getContacts         lib/world/narrow_phase.dart:634-721 (+ resolvers)
+ *       solver.solve                    lib/solver/gs_solver.dart:27-133
+ *       Body.integrate / sleepTick      lib/objects/rigid_body.dart:627-680, 282-300
+ *
+ * The same header is implemented twice:
+ *   - cannon_physics_b200/csrc  -> libcannon_cuda.so   (the product; CUDA kernels, no CPU fallback)
+ *   - oracle/                   -> libcannon_oracle.so (TEST INFRASTRUCTURE ONLY: a sequential CPU
+ *                                  restatement of the reference used as the parity checker)
+ * so every parity test is "same inputs, two libraries".
+ *
+ * Conventions
+ *   - every function returns an int32_t status (CANNON_OK == 0, < 0 error); nothing throws or aborts
+ *     across the boundary; cannon_last_error() gives a human-readable message (replaces the
+ *     reference's `throw '<string>'`, e.g. lib/collision/broadphase.dart:40).
+ *   - host buffers are caller-owned; device memory is library-owned; handles are opaque.
+ *   - body indices are int32_t and equal Body.index (lib/objects/rigid_body.dart:113).
+ *   - vector state is float (the reference stores Float32List vectors, lib/math/vec3.dart:2) and is
+ *     computed in double exactly like the Dart VM does; scalars the reference keeps as Dart `double`
+ *     (mass, damping, radii, SPOOK parameters, dt) are double here.
+ *   - quaternions are (x, y, z, w).
+ *   - calls on one ctx are not thread-safe and are synchronous at return.
+ *   - plain C layout, pointers + sizes only: directly bindable from dart:ffi.
+ */
+#ifndef CANNON_CUDA_H
+#define CANNON_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CANNON_ABI_VERSION 1
+
+/* ---- status codes ---- */
+#define CANNON_OK            0
+#define CANNON_E_INVALID    -1   /* bad argument                                           */
+#define CANNON_E_CUDA       -2   /* CUDA runtime error (message in cannon_last_error)      */
+#define CANNON_E_CAPACITY   -3   /* caller buffer too small; required size in the out-param */
+#define CANNON_E_UNSUPPORTED -4  /* feature outside the hot-path scope       */
+#define CANNON_E_NOGPU      -5   /* no CUDA device: there is deliberately no CPU fallback   */
+
+/* ---- enums (all int32_t on the wire) ---- */
+/* ShapeType order is the reference's, lib/rigid_body_shapes/shape.dart:6-18: it decides which
+ * shape is passed first to a resolver (lib/world/narrow_phase.dart:706-710). */
+enum {
+  CANNON_SHAPE_SPHERE = 0, CANNON_SHAPE_PLANE = 1, CANNON_SHAPE_BOX = 2, CANNON_SHAPE_CONVEX = 3,
+  CANNON_SHAPE_CYLINDER = 4, CANNON_SHAPE_HEIGHTFIELD = 8
+};
+/* BodyTypes / BodySleepStates, lib/objects/rigid_body.dart:15-16 */
+enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 2 };
+enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };
+/* World.broadphase choices: NaiveBroadphase / SAPBroadphase / GridBroadphase */
+enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
+/* World.solver choices.
+ *   REFERENCE_ORDER: GSSolver with the reference's exact equation order
+ *       (lib/world/world_class.dart:539-541,562,627-635); bit-reproducible validation mode.
+ *   COLORED: graph-coloured Gauss-Seidel (throughput mode; different row order, so only
+ *       statistical agreement with the reference). */
+enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1 };
+/* Constraint kinds, lib/constraints/{point_to_point,hinge}_constraint.dart */
+enum { CANNON_CONSTRAINT_POINT_TO_POINT = 0, CANNON_CONSTRAINT_HINGE = 1 };
+
+typedef struct cannon_ctx   cannon_ctx;
+typedef struct cannon_world cannon_world;
+
+/* ContactMaterial, lib/material/contact_material.dart:5-76 */
+typedef struct cannon_contact_material {
+  int32_t material_a;            /* Material index (ignored for the world default) */
+  int32_t material_b;
+  double  friction;                       /* default 0.3 */
+  double  restitution;                    /* default 0.3 (0.0 for the world default, world_class.dart:155-158) */
+  double  contact_equation_stiffness;     /* 1e7 */
+  double  contact_equation_relaxation;    /* 3   */
+  double  friction_equation_stiffness;    /* 1e7 */
+  double  friction_equation_relaxation;   /* 3   */
+} cannon_contact_material;
+
+/* World constructor parameters, lib/world/world_class.dart:135-162, plus the pluggable
+ * Broadphase / Solver objects flattened to POD. */
+typedef struct cannon_world_desc {
+  float   gravity[3];
+  float   friction_gravity[3];
+  int32_t has_friction_gravity;  /* World.frictionGravity != null */
+  int32_t allow_sleep;           /* World.allowSleep */
+  int32_t quat_normalize_skip;   /* World.quatNormalizeSkip */
+  int32_t quat_normalize_fast;   /* World.quatNormalizeFast */
+  int32_t solver_kind;           /* CANNON_SOLVER_* */
+  int32_t solver_iterations;     /* Solver.iterations (10) */
+  double  solver_tolerance;      /* Solver.tolerance (1e-7) */
+  int32_t broadphase_kind;       /* CANNON_BP_* */
+  int32_t use_bounding_boxes;    /* Broadphase.useBoundingBoxes */
+  int32_t sap_axis;              /* SAPBroadphase.axisIndex: 0 x, 1 y, 2 z */
+  int32_t grid_nx, grid_ny, grid_nz;      /* GridBroadphase.nx/ny/nz */
+  float   grid_min[3], grid_max[3];       /* GridBroadphase.aabbMin/aabbMax */
+  cannon_contact_material default_contact_material;  /* World.defaultContactMaterial */
+  int32_t n_worlds;              /* >1: a batch of independent worlds in one handle; bodies carry world_id.
+                                    Pairs are only formed inside a world; 0/1 = single world */
+  int32_t max_pairs;             /* capacities, 0 = library picks (grows on demand) */
+  int32_t max_contacts;
+} cannon_world_desc;
+
+/* Shape table entry (one per distinct Shape object; bodies reference it by index, the reference's
+ * demos share one Shape between many bodies, examples/lib/examples/container.dart:105). */
+typedef struct cannon_shape_desc {
+  int32_t type;                  /* CANNON_SHAPE_* */
+  int32_t collision_response;    /* Shape.collisionResponse (1) */
+  int32_t collision_filter_group;/* Shape.collisionFilterGroup (-1) */
+  int32_t collision_filter_mask; /* Shape.collisionFilterMask (-1) */
+  double  radius;                /* Sphere.radius, lib/rigid_body_shapes/sphere.dart:11 */
+  float   half_extents[3];       /* Box.halfExtents, lib/rigid_body_shapes/box.dart:14 */
+  double  radius_top, radius_bottom, height; /* Cylinder, lib/rigid_body_shapes/cylinder.dart:15 */
+  int32_t num_segments;
+  /* ConvexPolyhedron, lib/rigid_body_shapes/convex_polyhedron.dart:51 (faces CCW, CSR layout) */
+  int32_t n_vertices;
+  const float*   vertices;       /* 3*n_vertices */
+  int32_t n_faces;
+  const int32_t* face_offsets;   /* n_faces+1 */
+  const int32_t* face_indices;
+  /* Heightfield, lib/rigid_body_shapes/heightfield.dart:34: data[ix][iy] row-major [nx][ny], f64 */
+  int32_t hf_nx, hf_ny;
+  const double*  hf_data;
+  int32_t hf_element_size;       /* int in the reference (heightfield.dart:46) */
+} cannon_shape_desc;
+
+/* Body state, structure of arrays. In *_set_bodies a NULL pointer means "reference default"
+ * (lib/objects/rigid_body.dart:27-48); in *_get_bodies a NULL pointer means "not wanted".
+ * One shape per body, at the body origin (compound bodies: SURVEY.md §8f). */
+typedef struct cannon_bodies_soa {
+  int32_t  n;
+  float*   position;          /* 3n */
+  float*   quaternion;        /* 4n (x,y,z,w); default (0,0,0,1) */
+  float*   velocity;          /* 3n */
+  float*   angular_velocity;  /* 3n */
+  float*   force;             /* 3n */
+  float*   torque;            /* 3n */
+  double*  mass;              /* n; default 0 (=> static) */
+  int32_t* type;              /* n; default: mass<=0 ? STATIC : DYNAMIC */
+  int32_t* sleep_state;       /* n; default AWAKE */
+  double*  time_last_sleepy;  /* n; default 0 */
+  uint8_t* allow_sleep;       /* n; default 1 */
+  double*  sleep_speed_limit; /* n; default 0.1 */
+  double*  sleep_time_limit;  /* n; default 1 */
+  double*  linear_damping;    /* n; default 0.01 */
+  double*  angular_damping;   /* n; default 0.01 */
+  float*   linear_factor;     /* 3n; default 1,1,1 */
+  float*   angular_factor;    /* 3n; default 1,1,1 */
+  uint8_t* fixed_rotation;    /* n; default 0 */
+  int32_t* collision_filter_group; /* n; default 1 */
+  int32_t* collision_filter_mask;  /* n; default -1 */
+  uint8_t* collision_response;     /* n; default 1 */
+  uint8_t* is_trigger;        /* n; default 0 */
+  int32_t* material;          /* n; Material index or -1 (default) */
+  int32_t* shape;             /* n; index into the shape table, -1 = no shape */
+  int32_t* world_id;          /* n; batch mode only, default 0 */
+  /* derived by the library at set time (Body.updateMassProperties / updateBoundingRadius,
+   * rigid_body.dart:587-609,395-412); only written by *_get_bodies */
+  double*  inv_mass;          /* n */
+  float*   inv_inertia;       /* 3n  local diagonal */
+  float*   inv_inertia_world; /* 9n  row-major */
+  double*  bounding_radius;   /* n */
+  float*   aabb;              /* 6n  lower xyz, upper xyz */
+} cannon_bodies_soa;
+
+/* Constraint, lib/constraints/point_to_point_constraint.dart:20, hinge_constraint.dart:10 */
+typedef struct cannon_constraint_desc {
+  int32_t type;               /* CANNON_CONSTRAINT_* */
+  int32_t body_a, body_b;
+  float   pivot_a[3], pivot_b[3];
+  float   axis_a[3], axis_b[3];   /* hinge only; normalised by the library like hinge_constraint.dart:34-37 */
+  double  max_force;              /* 1e6 */
+  int32_t collide_connected;      /* Constraint.collideConnected */
+  int32_t motor_enabled;          /* hinge: RotationalMotorEquation.enabled */
+  double  motor_target_velocity;
+  double  motor_max_force;
+} cannon_constraint_desc;
+
+/* ContactEquation list produced by the narrowphase (lib/equations/contact_equation.dart). */
+typedef struct cannon_contacts_soa {
+  int32_t  capacity;          /* number of contacts the arrays can hold */
+  int32_t* body_i;            /* ContactEquation.bi (index) */
+  int32_t* body_j;            /* ContactEquation.bj */
+  float*   ri;                /* 3*capacity */
+  float*   rj;
+  float*   ni;
+  double*  restitution;       /* optional (may be NULL) */
+  double*  friction;          /* optional: mu used for the two FrictionEquations, <=0 => none */
+  uint8_t* enabled;           /* optional */
+  double*  multiplier;        /* optional: Equation.multiplier of the contact row after the last solve */
+} cannon_contacts_soa;
+
+/* Profile, lib/world/world_class.dart:27-41, in milliseconds (float here, int in the reference),
+ * plus counters of the last step. */
+typedef struct cannon_profile {
+  double solve, make_contact_constraints, broadphase, integrate, narrowphase;
+  int64_t n_pairs, n_contacts, n_rows, n_levels, iterations_done;
+  int64_t steps, contact_iters_total;  /* accumulated since world creation */
+} cannon_profile;
+
+/* ---- lifecycle ---- */
+int32_t     cannon_version(void);
+/* "cuda" for the product, "oracle" for the CPU checker */
+const char* cannon_backend(void);
+int32_t     cannon_ctx_create(int32_t device, cannon_ctx** out);
+void        cannon_ctx_destroy(cannon_ctx* ctx);
+const char* cannon_last_error(const cannon_ctx* ctx);
+/* fills the POD with the reference defaults (World(), GSSolver(), NaiveBroadphase()) */
+void        cannon_world_desc_default(cannon_world_desc* d);
+void        cannon_shape_desc_default(cannon_shape_desc* d);
+
+/* ---- world ---- */
+int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out);
+void    cannon_world_destroy(cannon_world* w);
+/* Material table (friction / restitution, -1 = unset, lib/material/material.dart:20-21) and the
+ * ContactMaterial table looked up by unordered material pair (World.addContactMaterial). */
+int32_t cannon_world_set_materials(cannon_world* w, int32_t n_materials, const double* friction,
+                                   const double* restitution, int32_t n_contact_materials,
+                                   const cannon_contact_material* cms);
+int32_t cannon_world_set_shapes(cannon_world* w, int32_t n_shapes, const cannon_shape_desc* shapes);
+/* World.addBody for all bodies at once (upload path); derives mass properties. */
+int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* bodies);
+int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* out);
+/* World.addConstraint for all constraints at once. */
+int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs);
+/* World.time (used by Body.sleepTick, world_class.dart:693) */
+int32_t cannon_world_set_time(cannon_world* w, double time);
+int32_t cannon_world_get_time(cannon_world* w, double* time, int64_t* stepnumber);
+
+/* ---- staged entry points (drop-in for World.broadphase / narrowphase / solver) ---- */
+/* Broadphase.collisionPairs(world,p1,p2), lib/collision/broadphase.dart:39, followed by the
+ * constraint-pair filter of world_class.dart:488-499. Pairs come out in the reference's order. */
+int32_t cannon_broadphase_pairs(cannon_world* w, int32_t* p1, int32_t* p2, int32_t cap, int32_t* n_pairs);
+/* Narrowphase.getContacts(p1,p2,...), lib/world/narrow_phase.dart:634. per_pair_count (np entries,
+ * may be NULL) receives the number of ContactEquations generated per pair. */
+int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const int32_t* p2, int32_t np,
+                                    cannon_contacts_soa* out, int32_t* n_contacts, int32_t* per_pair_count);
+/* World.dt used by the staged narrowphase for the SPOOK parameters (world_class.dart:434; -1 until
+ * the first step, in which case World.defaultDt = 1/60 is used) */
+int32_t cannon_world_set_dt(cannon_world* w, double dt);
+/* gravity accumulation of world_class.dart:460-471 (first thing internalStep does) */
+int32_t cannon_apply_gravity(cannon_world* w);
+/* world_class.dart:539-645: wake-up flags, Constraint.update(), equation assembly in the reference
+ * order and Solver.solve(dt, world) over the contacts of the last cannon_narrowphase_contacts call plus
+ * the world's constraints; updates velocity / angularVelocity like gs_solver.dart:111-121. Returns the
+ * iteration count like GSSolver.solve. */
+int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done);
+/* damping + Body.integrate + clearForces + sleepTick (world_class.dart:648-700) */
+int32_t cannon_integrate(cannon_world* w, double dt);
+
+/* ---- fused ---- */
+/* nsteps x World.step(dt) (fixed stepping, world_class.dart:393-399) with all state device-resident */
+int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps);
+int32_t cannon_world_profile(cannon_world* w, cannon_profile* out);
+/* World.contacts of the last step */
+int32_t cannon_world_get_contacts(cannon_world* w, cannon_contacts_soa* out, int32_t* n_contacts);
+/* solver rows of the last solve, in solve order: debug / parity only. Arrays of `cap` entries (any may be NULL) */
+int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int32_t* body_i, int32_t* body_j,
+                              double* B, double* invC, double* lambda, int32_t* level);
+
+/* user mutations between steps (Body.applyForce etc. reduce to writing these arrays on the host
+ * and re-uploading the dirty range): partial update of dynamic state for bodies [first, first+count) */
+int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count, const float* position,
+                                   const float* quaternion, const float* velocity, const float* angular_velocity,
+                                   const float* force, const float* torque);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANNON_CUDA_H */

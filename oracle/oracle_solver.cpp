@@ -1,0 +1,376 @@
+/*
+ * oracle_solver.cpp — TEST INFRASTRUCTURE ONLY (PARITY UNPINNED, see oracle_math.h).
+ * Equation assembly, Gauss-Seidel solve, integration and sleeping restated from
+ *   lib/world/world_class.dart:433-701           World.internalStep
+ *   lib/solver/gs_solver.dart:27-133             GSSolver.solve
+ *   lib/solver/solver.dart:30-34                 Solver.addEquation filter
+ *   lib/equations/equation_class.dart:53-174     SPOOK, computeGW/GiMf/GiMGt/addToWlambda
+ *   lib/equations/{contact,friction,rotational,rotational_motor}_equation.dart  computeB
+ *   lib/constraints/{point_to_point,hinge}_constraint.dart  update()
+ *   lib/objects/rigid_body.dart:263-314,627-680  sleep FSM, solve mass, integrate
+ */
+#include <cmath>
+
+#include "oracle_world.h"
+
+namespace orc {
+
+namespace {
+
+// Equation.computeGW, equation_class.dart:80-92
+double computeGW(const Eq& e, const Body& bi, const Body& bj) {
+  return (dot(bi.velocity, e.sA) + dot(bi.angularVelocity, e.rA)) + (dot(bj.velocity, e.sB) + dot(bj.angularVelocity, e.rB));
+}
+// Equation.computeGWlambda, equation_class.dart:95-105
+double computeGWlambda(const Eq& e, const Body& bi, const Body& bj) {
+  return (dot(bi.vlambda, e.sA) + dot(bi.wlambda, e.rA)) + (dot(bj.vlambda, e.sB) + dot(bj.wlambda, e.rB));
+}
+// Equation.computeGiMf, equation_class.dart:108-127
+double computeGiMf(const Eq& e, const Body& bi, const Body& bj) {
+  V3 iMfi = scale(bi.invMassSolve, bi.force);
+  V3 iMfj = scale(bj.invMassSolve, bj.force);
+  V3 invIiVmultTaui = mvmult(bi.invInertiaWorldSolve, bi.torque);
+  V3 invIjVmultTauj = mvmult(bj.invInertiaWorldSolve, bj.torque);
+  return (dot(iMfi, e.sA) + dot(invIiVmultTaui, e.rA)) + (dot(iMfj, e.sB) + dot(invIjVmultTauj, e.rB));
+}
+// Equation.computeGiMGt + computeC, equation_class.dart:130-148,172-174
+double computeC(const Eq& e, const Body& bi, const Body& bj) {
+  double result = bi.invMassSolve + bj.invMassSolve;
+  V3 tmp = mvmult(bi.invInertiaWorldSolve, e.rA);
+  result += dot(tmp, e.rA);
+  tmp = mvmult(bj.invInertiaWorldSolve, e.rB);
+  result += dot(tmp, e.rB);
+  return result + e.eps;
+}
+// Equation.addToWlambda, equation_class.dart:151-169
+void addToWlambda(const Eq& e, Body& bi, Body& bj, double dl) {
+  bi.vlambda = add_scaled(bi.vlambda, bi.invMassSolve * dl, e.sA);
+  bj.vlambda = add_scaled(bj.vlambda, bj.invMassSolve * dl, e.sB);
+  V3 temp = mvmult(bi.invInertiaWorldSolve, e.rA);
+  bi.wlambda = add_scaled(bi.wlambda, dl, temp);
+  temp = mvmult(bj.invInertiaWorldSolve, e.rB);
+  bj.wlambda = add_scaled(bj.wlambda, dl, temp);
+}
+
+double computeB(Eq& e, const Body& bi, const Body& bj, double h) {
+  switch (e.kind) {
+    case EQ_CONTACT: {  // contact_equation.dart:34-77
+      V3 rixn = cross(e.ri, e.ni);
+      V3 rjxn = cross(e.rj, e.ni);
+      e.sA = neg(e.ni);
+      e.rA = neg(rixn);
+      e.sB = e.ni;
+      e.rB = rjxn;
+      V3 pen = bj.position;
+      pen = add(pen, e.rj);
+      pen = sub(pen, bi.position);
+      pen = sub(pen, e.ri);
+      double g = dot(e.ni, pen);
+      double ePlusOne = e.restitution + 1;
+      double gw = ePlusOne * dot(bj.velocity, e.ni) - ePlusOne * dot(bi.velocity, e.ni) + dot(bj.angularVelocity, rjxn) -
+                  dot(bi.angularVelocity, rixn);
+      double giMf = computeGiMf(e, bi, bj);
+      return -g * e.a - gw * e.b - h * giMf;
+    }
+    case EQ_FRICTION: {  // friction_equation.dart:19-47
+      V3 rixt = cross(e.ri, e.ni);
+      V3 rjxt = cross(e.rj, e.ni);
+      e.sA = neg(e.ni);
+      e.rA = neg(rixt);
+      e.sB = e.ni;
+      e.rB = rjxt;
+      double gw = computeGW(e, bi, bj);
+      double giMf = computeGiMf(e, bi, bj);
+      return -gw * e.b - h * giMf;
+    }
+    case EQ_ROTATIONAL: {  // rotational_equation.dart:34-58
+      V3 nixnj = cross(e.axisA, e.axisB);
+      V3 njxni = cross(e.axisB, e.axisA);
+      e.rA = njxni;
+      e.rB = nixnj;
+      double g = std::cos(e.maxAngle) - dot(e.axisA, e.axisB);
+      double gW = computeGW(e, bi, bj);
+      double giMf = computeGiMf(e, bi, bj);
+      return -g * e.a - gW * e.b - h * giMf;
+    }
+    default: {  // rotational_motor_equation.dart:17-33
+      e.rA = e.axisA;
+      e.rB = neg(e.axisB);
+      double gw = computeGW(e, bi, bj) - e.targetVelocity;
+      double giMf = computeGiMf(e, bi, bj);
+      return -gw * e.b - h * giMf;
+    }
+  }
+}
+
+// Body.updateSolveMassProperties, rigid_body.dart:303-314
+void updateSolveMassProperties(Body& b) {
+  if (b.sleepState == CANNON_SLEEPING || b.type == CANNON_BODY_KINEMATIC) {
+    b.invMassSolve = 0;
+    b.invInertiaWorldSolve = M3{{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  } else {
+    b.invMassSolve = b.invMass;
+    b.invInertiaWorldSolve = b.invInertiaWorld;
+  }
+}
+
+// GSSolver.solve, gs_solver.dart:27-133, over `eqs` and the bodies [b0,b1)
+int gsSolve(World& w, std::vector<Eq*>& eqs, int b0, int b1, double h, std::vector<RowDebug>& dbg) {
+  int iter = 0;
+  const int maxIter = w.desc.solver_iterations;
+  const double tolSquared = w.desc.solver_tolerance * w.desc.solver_tolerance;
+  const int nEq = (int)eqs.size();
+  std::vector<Body>& bodies = w.bodies;
+  if (nEq != 0)
+    for (int i = b0; i < b1; i++) updateSolveMassProperties(bodies[i]);
+  std::vector<double> invCs(nEq), bs(nEq), lambda(nEq);
+  for (int i = 0; i != nEq; i++) {
+    Eq& c = *eqs[i];
+    lambda[i] = 0.0;
+    bs[i] = computeB(c, bodies[c.bi], bodies[c.bj], h);
+    invCs[i] = 1.0 / computeC(c, bodies[c.bi], bodies[c.bj]);
+  }
+  if (nEq != 0) {
+    for (int i = b0; i < b1; i++) {
+      bodies[i].vlambda = V3{0, 0, 0};
+      bodies[i].wlambda = V3{0, 0, 0};
+    }
+    for (iter = 0; iter != maxIter; iter++) {
+      double deltalambdaTot = 0.0;
+      for (int j = 0; j != nEq; j++) {
+        Eq& c = *eqs[j];
+        double B = bs[j], invC = invCs[j], lambdaj = lambda[j];
+        double gwlambda = computeGWlambda(c, bodies[c.bi], bodies[c.bj]);
+        double deltalambda = invC * (B - gwlambda - c.eps * lambdaj);
+        if (lambdaj + deltalambda < c.minForce) deltalambda = c.minForce - lambdaj;
+        else if (lambdaj + deltalambda > c.maxForce) deltalambda = c.maxForce - lambdaj;
+        lambda[j] = lambda[j] + deltalambda;
+        deltalambdaTot += deltalambda > 0.0 ? deltalambda : -deltalambda;
+        addToWlambda(c, bodies[c.bi], bodies[c.bj], deltalambda);
+      }
+      if (deltalambdaTot * deltalambdaTot < tolSquared) break;
+    }
+    for (int i = b0; i < b1; i++) {
+      Body& b = bodies[i];
+      b.vlambda = mulc(b.vlambda, b.linearFactor);
+      b.velocity = add(b.vlambda, b.velocity);
+      b.wlambda = mulc(b.wlambda, b.angularFactor);
+      b.angularVelocity = add(b.wlambda, b.angularVelocity);
+    }
+    double invDt = 1 / h;
+    for (int l = nEq - 1; l > -1; l--) eqs[l]->multiplier = lambda[l] * invDt;
+  }
+  for (int i = 0; i != nEq; i++) dbg.push_back(RowDebug{eqs[i]->bi, eqs[i]->bj, bs[i], invCs[i], lambda[i]});
+  return iter;
+}
+
+}  // namespace
+
+// world_class.dart:543-624: per-contact restitution override (idempotent with createContactEquation's
+// rule because shape materials are out of scope), wake-up flags, then wake flagged bodies
+void World::makeContactConstraints() {
+  for (Eq& c : contacts) {
+    Body& bi = bodies[c.bi];
+    Body& bj = bodies[c.bj];
+    if (bi.material >= 0 && bj.material >= 0) {
+      if (matRestitution[bi.material] >= 0 && matRestitution[bj.material] >= 0)
+        c.restitution = matRestitution[bi.material] * matRestitution[bj.material];
+    }
+    if (bi.allowSleep && bi.type == CANNON_BODY_DYNAMIC && bi.sleepState == CANNON_SLEEPING && bj.sleepState == CANNON_AWAKE &&
+        bj.type != CANNON_BODY_STATIC) {
+      double speedSquaredB = length2(bj.velocity) + length2(bj.angularVelocity);
+      double speedLimitSquaredB = bj.sleepSpeedLimit * bj.sleepSpeedLimit;
+      if (speedSquaredB >= speedLimitSquaredB * 2) bi.wakeUpAfterNarrowphase = true;
+    }
+    if (bj.allowSleep && bj.type == CANNON_BODY_DYNAMIC && bj.sleepState == CANNON_SLEEPING && bi.sleepState == CANNON_AWAKE &&
+        bi.type != CANNON_BODY_STATIC) {
+      double speedSquaredA = length2(bi.velocity) + length2(bi.angularVelocity);
+      double speedLimitSquaredA = bi.sleepSpeedLimit * bi.sleepSpeedLimit;
+      if (speedSquaredA >= speedLimitSquaredA * 2) bj.wakeUpAfterNarrowphase = true;
+    }
+  }
+  for (Body& b : bodies) {
+    if (b.wakeUpAfterNarrowphase) {
+      b.sleepState = CANNON_AWAKE;
+      b.wakeUpAfterNarrowphase = false;
+    }
+  }
+}
+
+int World::solve(double h) {
+  // constraints: c.update(); then their equations (world_class.dart:627-635)
+  for (Constraint& c : constraints) {
+    const Body& A = bodies[c.bodyA];
+    const Body& B = bodies[c.bodyB];
+    // PointToPointConstraint.update, point_to_point_constraint.dart:68-83
+    V3 ri = qvmult(A.quaternion, c.pivotA);
+    V3 rj = qvmult(B.quaternion, c.pivotB);
+    for (int k = 0; k < 3; k++) {
+      c.eqs[k].ri = ri;
+      c.eqs[k].rj = rj;
+    }
+    if (c.type == CANNON_CONSTRAINT_HINGE) {  // hinge_constraint.dart:79-104
+      V3 worldAxisA = qvmult(A.quaternion, c.axisA);
+      V3 worldAxisB = qvmult(B.quaternion, c.axisB);
+      tangents(worldAxisA, c.eqs[3].axisA, c.eqs[4].axisA);
+      c.eqs[3].axisB = worldAxisB;
+      c.eqs[4].axisB = worldAxisB;
+      if (c.eqs[5].enabled) {
+        c.eqs[5].axisA = qvmult(A.quaternion, c.axisA);
+        c.eqs[5].axisB = qvmult(B.quaternion, c.axisB);
+      }
+    }
+  }
+  auto accept = [&](const Eq& e) { return e.enabled && !bodies[e.bi].isTrigger && !bodies[e.bj].isTrigger; };
+  rows.clear();
+  int itersMax = 0;
+  const int nW = desc.n_worlds > 1 ? desc.n_worlds : 1;
+  if (nW == 1) {
+    std::vector<Eq*> eqs;
+    for (Eq& e : frictions) if (accept(e)) eqs.push_back(&e);
+    for (Eq& e : contacts) if (accept(e)) eqs.push_back(&e);
+    for (Constraint& c : constraints)
+      for (Eq& e : c.eqs) if (accept(e)) eqs.push_back(&e);
+    itersMax = gsSolve(*this, eqs, 0, (int)bodies.size(), h, rows);
+  } else {
+    // a batch is nW separate World objects in the reference: each solves its own equation list
+    // (own iteration loop and tolerance early-exit) over its own bodies
+    std::vector<std::vector<Eq*>> per(nW);
+    for (Eq& e : frictions) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
+    for (Eq& e : contacts) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
+    for (Constraint& c : constraints)
+      for (Eq& e : c.eqs) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
+    std::vector<int> wb0(nW, -1), wb1(nW, 0);
+    for (int i = 0; i < (int)bodies.size(); i++) {
+      int wi = bodies[i].worldId;
+      if (wb0[wi] < 0) wb0[wi] = i;
+      wb1[wi] = i + 1;
+    }
+    for (int wi = 0; wi < nW; wi++) {
+      if (wb0[wi] < 0) continue;
+      int it = gsSolve(*this, per[wi], wb0[wi], wb1[wi], h, rows);
+      if (it > itersMax) itersMax = it;
+    }
+  }
+  return itersMax;
+}
+
+void World::integrateAll(double h) {
+  // damping, world_class.dart:648-659
+  for (Body& bi : bodies) {
+    if (bi.type == CANNON_BODY_DYNAMIC) {
+      double ld = std::pow(1.0 - bi.linearDamping, h);
+      bi.velocity = scale(ld, bi.velocity);
+      double ad = std::pow(1.0 - bi.angularDamping, h);
+      bi.angularVelocity = scale(ad, bi.angularVelocity);
+    }
+  }
+  const bool quatNormalize = stepnumber % (desc.quat_normalize_skip + 1) == 0;
+  for (Body& b : bodies) {
+    // Body.integrate, rigid_body.dart:627-680
+    if (!(b.type == CANNON_BODY_DYNAMIC || b.type == CANNON_BODY_KINEMATIC) || b.sleepState == CANNON_SLEEPING) continue;
+    double iMdt = b.invMass * h;
+    b.velocity.x = (float)(D(b.velocity.x) + D(b.force.x) * iMdt * D(b.linearFactor.x));
+    b.velocity.y = (float)(D(b.velocity.y) + D(b.force.y) * iMdt * D(b.linearFactor.y));
+    b.velocity.z = (float)(D(b.velocity.z) + D(b.force.z) * iMdt * D(b.linearFactor.z));
+    const float* e = b.invInertiaWorld.e;
+    double tx = D(b.torque.x) * D(b.angularFactor.x);
+    double ty = D(b.torque.y) * D(b.angularFactor.y);
+    double tz = D(b.torque.z) * D(b.angularFactor.z);
+    b.angularVelocity.x = (float)(D(b.angularVelocity.x) + h * (D(e[0]) * tx + D(e[1]) * ty + D(e[2]) * tz));
+    b.angularVelocity.y = (float)(D(b.angularVelocity.y) + h * (D(e[3]) * tx + D(e[4]) * ty + D(e[5]) * tz));
+    b.angularVelocity.z = (float)(D(b.angularVelocity.z) + h * (D(e[6]) * tx + D(e[7]) * ty + D(e[8]) * tz));
+    b.position.x = (float)(D(b.position.x) + D(b.velocity.x) * h);
+    b.position.y = (float)(D(b.position.y) + D(b.velocity.y) * h);
+    b.position.z = (float)(D(b.position.z) + D(b.velocity.z) * h);
+    {  // Quat.integrate, quaternion.dart:93-111
+      double ax = D(b.angularVelocity.x) * D(b.angularFactor.x), ay = D(b.angularVelocity.y) * D(b.angularFactor.y),
+             az = D(b.angularVelocity.z) * D(b.angularFactor.z);
+      Q4& q = b.quaternion;
+      double bx = D(q.x), by = D(q.y), bz = D(q.z), bw = D(q.w);
+      double halfDt = h * 0.5;
+      q.x = (float)(D(q.x) + halfDt * (ax * bw + ay * bz - az * by));
+      q.y = (float)(D(q.y) + halfDt * (ay * bw + az * bx - ax * bz));
+      q.z = (float)(D(q.z) + halfDt * (az * bw + ax * by - ay * bx));
+      q.w = (float)(D(q.w) + halfDt * (-ax * bx - ay * by - az * bz));
+    }
+    if (quatNormalize) {
+      Q4& q = b.quaternion;
+      if (desc.quat_normalize_fast) {  // quaternion.dart:171-185
+        double f = (3.0 - (D(q.x) * D(q.x) + D(q.y) * D(q.y) + D(q.z) * D(q.z) + D(q.w) * D(q.w))) / 2.0;
+        if (f == 0) {
+          q = Q4{0, 0, 0, 0};
+        } else {
+          q.x = (float)(D(q.x) * f);
+          q.y = (float)(D(q.y) * f);
+          q.z = (float)(D(q.z) * f);
+          q.w = (float)(D(q.w) * f);
+        }
+      } else {  // vector_math Quaternion.normalize()
+        double l = std::sqrt((D(q.x) * D(q.x)) + (D(q.y) * D(q.y)) + (D(q.z) * D(q.z)) + (D(q.w) * D(q.w)));
+        if (l != 0.0) {
+          double d = 1.0 / l;
+          q.x = (float)(D(q.x) * d);
+          q.y = (float)(D(q.y) * d);
+          q.z = (float)(D(q.z) * d);
+          q.w = (float)(D(q.w) * d);
+        }
+      }
+    }
+    updateInertiaWorld(b, false);
+  }
+  // clearForces, world_class.dart:773-781
+  for (Body& b : bodies) {
+    b.force = V3{0, 0, 0};
+    b.torque = V3{0, 0, 0};
+  }
+  stepnumber += 1;
+  // sleepTick, world_class.dart:688-700 + rigid_body.dart:282-300 (sees `time` before this step's increment)
+  if (desc.allow_sleep) {
+    for (Body& b : bodies) {
+      if (!b.allowSleep) continue;
+      double speedSquared = length2(b.velocity) + length2(b.angularVelocity);
+      double speedLimitSquared = b.sleepSpeedLimit * b.sleepSpeedLimit;
+      if (b.sleepState == CANNON_AWAKE && speedSquared < speedLimitSquared) {
+        b.sleepState = CANNON_SLEEPY;
+        b.timeLastSleepy = time;
+      } else if (b.sleepState == CANNON_SLEEPY && speedSquared > speedLimitSquared) {
+        b.sleepState = CANNON_AWAKE;
+        b.wakeUpAfterNarrowphase = false;
+      } else if (b.sleepState == CANNON_SLEEPY && time - b.timeLastSleepy > b.sleepTimeLimit) {
+        b.sleepState = CANNON_SLEEPING;
+        b.velocity = V3{0, 0, 0};
+        b.angularVelocity = V3{0, 0, 0};
+        b.wakeUpAfterNarrowphase = false;
+      }
+    }
+  }
+}
+
+// World.internalStep + the `time += dt` of World.step, world_class.dart:392-399,433-701
+void World::internalStep(double h) {
+  dt = h;
+  const double gx = D(desc.gravity[0]), gy = D(desc.gravity[1]), gz = D(desc.gravity[2]);
+  for (Body& bi : bodies) {
+    if (bi.type == CANNON_BODY_DYNAMIC) {
+      double m = bi.mass;
+      bi.force.x = (float)(D(bi.force.x) + m * gx);
+      bi.force.y = (float)(D(bi.force.y) + m * gy);
+      bi.force.z = (float)(D(bi.force.z) + m * gz);
+    }
+  }
+  collisionPairs();
+  getContacts();
+  makeContactConstraints();
+  int iters = solve(h);
+  prof.n_pairs = (int64_t)p1.size();
+  prof.n_contacts = (int64_t)contacts.size();
+  prof.n_rows = (int64_t)rows.size();
+  prof.iterations_done = iters;
+  prof.contact_iters_total += (int64_t)contacts.size() * iters;
+  integrateAll(h);
+  prof.steps += 1;
+  time += h;
+}
+
+}  // namespace orc

@@ -1,0 +1,148 @@
+/*
+ * oracle_world.h — TEST INFRASTRUCTURE ONLY. Data model of the CPU restatement (PARITY UNPINNED, see
+ * oracle_math.h). Mirrors the reference's object graph (Body / Shape / ConvexPolyhedron / Equation /
+ * World) closely on purpose: the product uses a completely different (SoA, device) layout.
+ */
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../include/cannon_cuda.h"
+#include "oracle_math.h"
+
+namespace orc {
+
+// ConvexPolyhedron, lib/rigid_body_shapes/convex_polyhedron.dart:51
+struct Hull {
+  std::vector<V3> vertices;
+  std::vector<std::vector<int>> faces;
+  std::vector<V3> faceNormals;
+  std::vector<V3> uniqueEdges;
+  bool hasUniqueAxes = false;  // `uniqueAxes != null` (convex_polyhedron.dart:253,290)
+  double boundingSphereRadius = 0;
+  void computeNormals();
+  void computeEdges();
+  void updateBoundingSphereRadius();
+  double planeConstantOfFace(int f) const;
+};
+
+struct Shape {
+  int type = CANNON_SHAPE_SPHERE;
+  bool collisionResponse = true;
+  int group = -1, mask = -1;
+  double boundingSphereRadius = 0;
+  double radius = 1;  // sphere
+  V3 halfExtents{0, 0, 0};
+  Hull hull;  // box / cylinder / convex
+  // heightfield
+  int nx = 0, ny = 0, elementSize = 1;
+  std::vector<double> data;
+  double minValue = 0, maxValue = 0;
+  double h(int i, int j) const { return data[(size_t)i * ny + j]; }
+};
+
+struct Body {
+  V3 position{0, 0, 0}, velocity{0, 0, 0}, angularVelocity{0, 0, 0}, force{0, 0, 0}, torque{0, 0, 0};
+  Q4 quaternion{0, 0, 0, 1};
+  V3 vlambda{0, 0, 0}, wlambda{0, 0, 0};
+  double mass = 0, invMass = 0;
+  int type = CANNON_BODY_STATIC;
+  int sleepState = CANNON_AWAKE;
+  double timeLastSleepy = 0;
+  bool allowSleep = true;
+  double sleepSpeedLimit = 0.1, sleepTimeLimit = 1;
+  double linearDamping = 0.01, angularDamping = 0.01;
+  V3 linearFactor{1, 1, 1}, angularFactor{1, 1, 1};
+  bool fixedRotation = false;
+  int group = 1, mask = -1;
+  bool collisionResponse = true, isTrigger = false;
+  int material = -1;
+  int shape = -1;
+  int worldId = 0;
+  bool wakeUpAfterNarrowphase = false;
+  V3 inertia{0, 0, 0}, invInertia{0, 0, 0};
+  M3 invInertiaWorld{{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  double invMassSolve = 0;
+  M3 invInertiaWorldSolve{{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  double boundingRadius = 0;
+  V3 aabbLower{0, 0, 0}, aabbUpper{0, 0, 0};
+};
+
+enum { EQ_CONTACT = 0, EQ_FRICTION = 1, EQ_ROTATIONAL = 2, EQ_MOTOR = 3 };
+
+// Equation + subclasses, lib/equations/*.dart
+struct Eq {
+  int kind = EQ_CONTACT;
+  int bi = -1, bj = -1;
+  double minForce = -1e6, maxForce = 1e6;
+  double a = 0, b = 0, eps = 0;
+  bool enabled = true;
+  double multiplier = 0;
+  V3 ri{0, 0, 0}, rj{0, 0, 0}, ni{0, 0, 0};  // ni doubles as the friction tangent t
+  double restitution = 0;
+  V3 axisA{1, 0, 0}, axisB{0, 1, 0};
+  double maxAngle = M_PI / 2;
+  double targetVelocity = 0;
+  double friction = 0;  // contact only: mu used for its friction equations (<=0: none)
+  // jacobian elements
+  V3 sA{0, 0, 0}, rA{0, 0, 0}, sB{0, 0, 0}, rB{0, 0, 0};
+  void setSpookParams(double k, double d, double h) {  // equation_class.dart:53-60
+    a = 4.0 / (h * (1 + 4 * d));
+    b = 4.0 * d / (1 + 4 * d);
+    eps = 4.0 / (h * h * k * (1 + 4 * d));
+  }
+};
+
+struct Constraint {
+  int type = 0, bodyA = -1, bodyB = -1;
+  V3 pivotA{0, 0, 0}, pivotB{0, 0, 0}, axisA{1, 0, 0}, axisB{1, 0, 0};
+  bool collideConnected = true;
+  std::vector<Eq> eqs;  // P2P: x,y,z ; hinge: x,y,z,rot1,rot2,motor
+};
+
+struct RowDebug {
+  int bi, bj;
+  double B, invC, lambda;
+};
+
+struct World {
+  cannon_world_desc desc;
+  std::vector<Shape> shapes;
+  std::vector<Body> bodies;
+  std::vector<double> matFriction, matRestitution;
+  std::vector<cannon_contact_material> cms;
+  std::vector<int> cmTable;  // nmat*nmat -> cm index or -1
+  std::vector<Constraint> constraints;
+  double time = 0;
+  double dt = -1;
+  int64_t stepnumber = 0;
+  std::vector<int> sapAxisList;
+  // outputs of the last stages
+  std::vector<int> p1, p2;
+  std::vector<Eq> contacts;   // ContactEquations (World.contacts)
+  std::vector<Eq> frictions;  // FrictionEquations (World.frictionEquations)
+  std::vector<int> perPairCount;
+  std::vector<RowDebug> rows;
+  cannon_profile prof{};
+  std::string err;
+
+  const cannon_contact_material* contactMaterial(int ma, int mb) const;
+  void updateAABB(Body& b) const;
+  void updateMassProperties(Body& b) const;
+  void updateInertiaWorld(Body& b, bool force) const;
+  void updateBoundingRadius(Body& b) const;
+
+  void collisionPairs();            // broadphase + constraint-pair filter
+  void getContacts();               // narrowphase over p1/p2
+  void makeContactConstraints();    // restitution override + wake-up flags
+  int solve(double dt);             // GSSolver.solve over frictions ++ contacts ++ constraint rows
+  void integrateAll(double dt);     // damping, integrate, clearForces, sleepTick
+  void internalStep(double dt);
+};
+
+// shape constructors
+void make_box_hull(const V3& he, Hull& h);
+void make_cylinder_hull(double rTop, double rBottom, double height, int nSeg, Hull& h);
+void shape_world_aabb(const Shape& s, const V3& pos, const Q4& q, V3& mn, V3& mx);
+
+}  // namespace orc
