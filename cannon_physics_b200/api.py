@@ -1,0 +1,508 @@
+"""Host-side mirror of the reference's object API for the step path.
+
+Same class names, constructor arguments and defaults as the Dart library so that a program written against
+``cannon_physics`` reads the same here:
+
+    World / Body / Sphere / Plane / Box / Cylinder / ConvexPolyhedron / Heightfield / Material /
+    ContactMaterial / NaiveBroadphase / SAPBroadphase / GridBroadphase / GSSolver /
+    PointToPointConstraint / HingeConstraint
+
+(lib/world/world_class.dart:44, lib/objects/rigid_body.dart:26, lib/rigid_body_shapes/*.dart,
+lib/material/*.dart, lib/collision/*broadphase.dart, lib/solver/gs_solver.dart, lib/constraints/*.dart).
+
+The objects only hold host-side description; ``World.step`` flattens them once into the SoA upload of
+``include/cannon_cuda.h`` and afterwards steps on the device (the reference's ``CudaWorld`` fused mode,
+SURVEY.md §8b). Body vectors are float32 numpy rows, refreshed from the device after every ``step`` unless
+``sync=False``.  Errors surface as ``CannonError`` (the reference throws strings).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi as F
+from .engine import Context, DeviceWorld, SceneSpec
+
+__all__ = [
+    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron",
+    "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
+    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "World",
+    "CudaWorld", "CannonError",
+]
+
+CannonError = F.CannonError
+
+
+def Vec3(x=0.0, y=0.0, z=0.0) -> np.ndarray:
+    """vector_math Vector3: float32 storage."""
+    return np.array([x, y, z], dtype=np.float32)
+
+
+class Quaternion:
+    """Helpers of lib/math/quaternion.dart that scene set-up code uses (storage is a float32 row x,y,z,w)."""
+
+    @staticmethod
+    def identity() -> np.ndarray:
+        return np.array([0, 0, 0, 1], dtype=np.float32)
+
+    @staticmethod
+    def setFromEuler(x: float, y: float, z: float) -> np.ndarray:  # quaternion.dart:191-203 (order XYZ)
+        c1, c2, c3 = math.cos(x / 2), math.cos(y / 2), math.cos(z / 2)
+        s1, s2, s3 = math.sin(x / 2), math.sin(y / 2), math.sin(z / 2)
+        return np.array([s1 * c2 * c3 + c1 * s2 * s3, c1 * s2 * c3 - s1 * c2 * s3, c1 * c2 * s3 + s1 * s2 * c3,
+                         c1 * c2 * c3 - s1 * s2 * s3], dtype=np.float32)
+
+    @staticmethod
+    def setFromAxisAngle(axis: Sequence[float], angle: float) -> np.ndarray:  # quaternion.dart:85-91
+        s = math.sin(angle * 0.5)
+        a = np.asarray(axis, dtype=np.float32).astype(np.float64)
+        return np.array([a[0] * s, a[1] * s, a[2] * s, math.cos(angle * 0.5)], dtype=np.float32)
+
+
+class BodyTypes:
+    dynamic, static, kinematic = F.BODY_DYNAMIC, F.BODY_STATIC, F.BODY_KINEMATIC
+
+
+class BodySleepStates:
+    awake, sleepy, sleeping = F.AWAKE, F.SLEEPY, F.SLEEPING
+
+
+class Material:  # lib/material/material.dart:2
+    def __init__(self, friction: float = -1, restitution: float = -1, name: str = ""):
+        self.friction, self.restitution, self.name = friction, restitution, name
+
+
+class ContactMaterial:  # lib/material/contact_material.dart:5
+    def __init__(self, m1: Material, m2: Material, friction=0.3, restitution=0.3, contactEquationStiffness=1e7,
+                 contactEquationRelaxation=3, frictionEquationStiffness=1e7, frictionEquationRelaxation=3):
+        self.materials = [m1, m2]
+        self.friction, self.restitution = friction, restitution
+        self.contactEquationStiffness, self.contactEquationRelaxation = contactEquationStiffness, contactEquationRelaxation
+        self.frictionEquationStiffness, self.frictionEquationRelaxation = frictionEquationStiffness, frictionEquationRelaxation
+
+
+class Shape:  # lib/rigid_body_shapes/shape.dart:28
+    type = -1
+
+    def __init__(self, collisionResponse=True, collisionFilterGroup=-1, collisionFilterMask=-1):
+        self.collisionResponse = collisionResponse
+        self.collisionFilterGroup, self.collisionFilterMask = collisionFilterGroup, collisionFilterMask
+
+    def _desc(self) -> dict:
+        return dict(type=self.type, collision_response=int(self.collisionResponse), collision_filter_group=self.collisionFilterGroup,
+                    collision_filter_mask=self.collisionFilterMask)
+
+
+class Sphere(Shape):  # sphere.dart:11
+    type = F.SHAPE_SPHERE
+
+    def __init__(self, radius: float = 1.0, **kw):
+        super().__init__(**kw)
+        if radius < 0:
+            raise ValueError("The sphere radius cannot be negative.")
+        self.radius = float(radius)
+
+    def _desc(self):
+        return dict(super()._desc(), radius=self.radius)
+
+
+class Plane(Shape):  # plane.dart:11
+    type = F.SHAPE_PLANE
+
+
+class Box(Shape):  # box.dart:14
+    type = F.SHAPE_BOX
+
+    def __init__(self, halfExtents, **kw):
+        super().__init__(**kw)
+        self.halfExtents = np.asarray(halfExtents, dtype=np.float32)
+
+    def _desc(self):
+        return dict(super()._desc(), half_extents=self.halfExtents)
+
+
+class Cylinder(Shape):  # cylinder.dart:15
+    type = F.SHAPE_CYLINDER
+
+    def __init__(self, radiusTop=1.0, radiusBottom=1.0, height=1.0, numSegments=8, **kw):
+        super().__init__(**kw)
+        if radiusTop < 0:
+            raise ValueError("The cylinder radiusTop cannot be negative.")
+        if radiusBottom < 0:
+            raise ValueError("The cylinder radiusBottom cannot be negative.")
+        self.radiusTop, self.radiusBottom, self.height, self.numSegments = float(radiusTop), float(radiusBottom), float(height), int(numSegments)
+
+    def _desc(self):
+        return dict(super()._desc(), radius_top=self.radiusTop, radius_bottom=self.radiusBottom, height=self.height, num_segments=self.numSegments)
+
+
+class ConvexPolyhedron(Shape):  # convex_polyhedron.dart:51
+    type = F.SHAPE_CONVEX
+
+    def __init__(self, vertices, faces, **kw):
+        super().__init__(**kw)
+        self.vertices = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self.faces = [list(f) for f in faces]
+
+    def _desc(self):
+        return dict(super()._desc(), vertices=self.vertices, faces=self.faces)
+
+
+class Heightfield(Shape):  # heightfield.dart:34
+    type = F.SHAPE_HEIGHTFIELD
+
+    def __init__(self, data, elementSize: int = 1, **kw):
+        super().__init__(**kw)
+        self.data = np.asarray(data, dtype=np.float64)
+        self.elementSize = int(elementSize)
+
+    def _desc(self):
+        return dict(super()._desc(), hf_data=self.data, hf_element_size=self.elementSize)
+
+
+class Body:  # lib/objects/rigid_body.dart:26-86
+    def __init__(self, collisionFilterGroup=1, collisionFilterMask=-1, collisionResponse=True, position=None, velocity=None, mass=0.0,
+                 material: Optional[Material] = None, linearDamping=0.01, type=None, allowSleep=True, sleepSpeedLimit=0.1, sleepTimeLimit=1.0,
+                 quaternion=None, angularVelocity=None, fixedRotation=False, angularDamping=0.01, linearFactor=None, angularFactor=None,
+                 shape: Optional[Shape] = None, isTrigger=False):
+        f32 = lambda v, d: np.array(d if v is None else v, dtype=np.float32)
+        self.position, self.velocity = f32(position, (0, 0, 0)), f32(velocity, (0, 0, 0))
+        self.quaternion, self.angularVelocity = f32(quaternion, (0, 0, 0, 1)), f32(angularVelocity, (0, 0, 0))
+        self.force, self.torque = Vec3(), Vec3()
+        self.linearFactor, self.angularFactor = f32(linearFactor, (1, 1, 1)), f32(angularFactor, (1, 1, 1))
+        self.mass = float(mass)
+        self.type = (BodyTypes.static if self.mass <= 0 else BodyTypes.dynamic) if type is None else type
+        self.material = material
+        self.linearDamping, self.angularDamping = linearDamping, angularDamping
+        self.allowSleep, self.sleepSpeedLimit, self.sleepTimeLimit = allowSleep, sleepSpeedLimit, sleepTimeLimit
+        self.sleepState = BodySleepStates.awake
+        self.fixedRotation, self.isTrigger = fixedRotation, isTrigger
+        self.collisionFilterGroup, self.collisionFilterMask, self.collisionResponse = collisionFilterGroup, collisionFilterMask, collisionResponse
+        self.shapes: List[Shape] = []
+        self.world: Optional["World"] = None
+        self.index = -1
+        if shape is not None:
+            self.addShape(shape)
+
+    def addShape(self, shape: Shape, offset=None, orientation=None) -> "Body":  # rigid_body.dart:348-369
+        if self.shapes:
+            raise CannonError(F.E_UNSUPPORTED, "compound bodies are outside the hot-path scope (SURVEY.md §8f)")
+        if offset is not None and np.any(np.asarray(offset) != 0):
+            raise CannonError(F.E_UNSUPPORTED, "shape offsets are outside the hot-path scope (SURVEY.md §8f)")
+        if orientation is not None and np.any(np.asarray(orientation, dtype=np.float32) != np.array([0, 0, 0, 1], np.float32)):
+            raise CannonError(F.E_UNSUPPORTED, "shape orientations are outside the hot-path scope (SURVEY.md §8f)")
+        self.shapes.append(shape)
+        self._dirty()
+        return self
+
+    def _dirty(self):
+        if self.world is not None:
+            self.world._structure_dirty = True
+
+    # rigid_body.dart:263-278
+    def wakeUp(self):
+        self.sleepState = BodySleepStates.awake
+        self._dirty()
+
+    def sleep(self):
+        self.sleepState = BodySleepStates.sleeping
+        self.velocity[:] = 0
+        self.angularVelocity[:] = 0
+        self._dirty()
+
+    # rigid_body.dart:472-566 (host-side writes, uploaded before the next step)
+    def applyForce(self, force, relativePoint=None):
+        if self.type != BodyTypes.dynamic:
+            return
+        f = np.asarray(force, dtype=np.float32)
+        r = Vec3() if relativePoint is None else np.asarray(relativePoint, dtype=np.float32)
+        if self.sleepState == BodySleepStates.sleeping:
+            self.wakeUp()
+        rot = np.cross(r.astype(np.float64), f.astype(np.float64)).astype(np.float32)
+        self.force[:] = (self.force.astype(np.float64) + f).astype(np.float32)
+        self.torque[:] = (self.torque.astype(np.float64) + rot).astype(np.float32)
+        if self.world is not None:
+            self.world._state_dirty = True
+
+    def applyImpulse(self, impulse, relativePoint=None):
+        if self.type != BodyTypes.dynamic:
+            return
+        if relativePoint is not None and np.any(np.asarray(relativePoint) != 0):
+            raise CannonError(F.E_UNSUPPORTED, "off-centre impulses need the device inertia; write angularVelocity directly")
+        if self.sleepState == BodySleepStates.sleeping:
+            self.wakeUp()
+        j = np.asarray(impulse, dtype=np.float32).astype(np.float64)
+        velo = (j * (1.0 / self.mass)).astype(np.float32)
+        self.velocity[:] = (self.velocity.astype(np.float64) + velo).astype(np.float32)
+        if self.world is not None:
+            self.world._state_dirty = True
+
+
+class Broadphase:  # lib/collision/broadphase.dart:11
+    kind = F.BP_NAIVE
+
+    def __init__(self, useBoundingBoxes: bool = False):
+        self.useBoundingBoxes = useBoundingBoxes
+        self.world = None
+
+    def collisionPairs(self, world: "World"):
+        """Broadphase.collisionPairs(world, p1, p2): returns the two parallel index lists."""
+        world._ensure_uploaded()
+        return world._dev.broadphase_pairs()
+
+
+class NaiveBroadphase(Broadphase):  # naive_broadphase.dart:10
+    kind = F.BP_NAIVE
+
+
+class SAPBroadphase(Broadphase):  # sap_broadphase.dart:10
+    kind = F.BP_SAP
+
+    def __init__(self, world=None, axisIndex: int = 0, **kw):
+        super().__init__(**kw)
+        self.axisIndex = axisIndex
+
+
+class GridBroadphase(Broadphase):  # grid_broadphase.dart:12
+    kind = F.BP_GRID
+
+    def __init__(self, aabbMin=(100, 100, 100), aabbMax=(-100, -100, -100), nx=10, ny=10, nz=10, **kw):
+        super().__init__(**kw)
+        if nx * ny * nz <= 0:
+            raise ValueError("GridBroadphase: Each dimension's n must be >0")
+        self.aabbMin, self.aabbMax, self.nx, self.ny, self.nz = np.asarray(aabbMin, np.float32), np.asarray(aabbMax, np.float32), nx, ny, nz
+
+
+CudaBroadphase = NaiveBroadphase  # drop-in name used by north_star; the kind is chosen by the subclass
+
+
+class Solver:  # lib/solver/solver.dart:5
+    kind = F.SOLVER_REFERENCE_ORDER
+
+    def __init__(self, iterations: int = 10, tolerance: float = 1e-7):
+        self.iterations, self.tolerance = iterations, tolerance
+
+
+class GSSolver(Solver):  # gs_solver.dart:7 — reference equation order, bit-reproducible
+    kind = F.SOLVER_REFERENCE_ORDER
+
+
+class CudaGSSolver(Solver):  # graph-coloured throughput mode
+    kind = F.SOLVER_COLORED
+
+
+class Constraint:  # constraint_class.dart:5
+    type = -1
+
+    def __init__(self, bodyA: Body, bodyB: Body, collideConnected: bool = True):
+        self.bodyA, self.bodyB, self.collideConnected = bodyA, bodyB, collideConnected
+
+
+class PointToPointConstraint(Constraint):  # point_to_point_constraint.dart:20
+    type = F.CONSTRAINT_POINT_TO_POINT
+
+    def __init__(self, bodyA, bodyB, pivotA=None, pivotB=None, maxForce: float = 1e6):
+        super().__init__(bodyA, bodyB)
+        self.pivotA = Vec3() if pivotA is None else np.array(pivotA, dtype=np.float32)
+        self.pivotB = Vec3() if pivotB is None else np.array(pivotB, dtype=np.float32)
+        self.maxForce = maxForce
+
+    def _desc(self, idx):
+        return dict(type=self.type, body_a=idx[id(self.bodyA)], body_b=idx[id(self.bodyB)], pivot_a=self.pivotA, pivot_b=self.pivotB,
+                    max_force=self.maxForce, collide_connected=int(self.collideConnected))
+
+
+class HingeConstraint(PointToPointConstraint):  # hinge_constraint.dart:10
+    type = F.CONSTRAINT_HINGE
+
+    def __init__(self, bodyA, bodyB, pivotA=None, pivotB=None, axisA=None, axisB=None, collideConnected=None, maxForce: float = 1e6):
+        super().__init__(bodyA, bodyB, pivotA, pivotB, maxForce)
+        self.axisA = Vec3(1, 0, 0) if axisA is None else np.array(axisA, dtype=np.float32)
+        self.axisB = Vec3(1, 0, 0) if axisB is None else np.array(axisB, dtype=np.float32)
+        self.collideConnected = True if collideConnected is None else collideConnected
+        self.motorEnabled, self.motorTargetVelocity, self.motorMaxForce = False, 0.0, maxForce
+
+    def enableMotor(self):
+        self.motorEnabled = True
+
+    def disableMotor(self):
+        self.motorEnabled = False
+
+    def setMotorSpeed(self, speed: float):
+        self.motorTargetVelocity = speed
+
+    def setMotorMaxForce(self, maxForce: float):
+        self.motorMaxForce = maxForce
+
+    def _desc(self, idx):
+        return dict(super()._desc(idx), axis_a=self.axisA, axis_b=self.axisB, motor_enabled=int(self.motorEnabled),
+                    motor_target_velocity=self.motorTargetVelocity, motor_max_force=self.motorMaxForce)
+
+
+class World:  # lib/world/world_class.dart:44
+    def __init__(self, gravity=None, frictionGravity=None, allowSleep: bool = False, broadphase: Optional[Broadphase] = None,
+                 solver: Optional[Solver] = None, quatNormalizeFast: bool = False, quatNormalizeSkip: int = 0, device: int = 0, _lib=None):
+        self.gravity = Vec3() if gravity is None else np.array(gravity, dtype=np.float32)
+        self.frictionGravity = None if frictionGravity is None else np.array(frictionGravity, dtype=np.float32)
+        self.allowSleep = allowSleep
+        self.broadphase = broadphase or NaiveBroadphase()
+        self.solver = solver or GSSolver()
+        self.quatNormalizeFast, self.quatNormalizeSkip = quatNormalizeFast, quatNormalizeSkip
+        self.bodies: List[Body] = []
+        self.constraints: List[Constraint] = []
+        self.contactmaterials: List[ContactMaterial] = []
+        self.defaultMaterial = Material(name="default")
+        self.defaultContactMaterial = ContactMaterial(self.defaultMaterial, self.defaultMaterial, friction=0.3, restitution=0.0)
+        self.time, self.stepnumber, self.dt = 0.0, 0, -1.0
+        self._device = device
+        if _lib is None:
+            from . import load_library
+            _lib = load_library()
+        self._lib = _lib
+        self._dev: Optional[DeviceWorld] = None
+        self._structure_dirty = True
+        self._state_dirty = False
+
+    # world_class.dart:282-300 / 224-231 / 343-348
+    def addBody(self, body: Body):
+        if body in self.bodies:
+            return
+        body.index = len(self.bodies)
+        body.world = self
+        self.bodies.append(body)
+        self._structure_dirty = True
+
+    def addConstraint(self, c: Constraint):
+        self.constraints.append(c)
+        self._structure_dirty = True
+
+    def addContactMaterial(self, cmat: ContactMaterial):
+        self.contactmaterials.append(cmat)
+        self._structure_dirty = True
+
+    def _spec(self) -> SceneSpec:
+        n = len(self.bodies)
+        shapes, shape_ids, mats, mat_ids = [], {}, [], {}
+
+        def mat_index(m):
+            if m is None:
+                return -1
+            if id(m) not in mat_ids:
+                mat_ids[id(m)] = len(mats)
+                mats.append(m)
+            return mat_ids[id(m)]
+
+        for cm in self.contactmaterials:
+            for m in cm.materials:
+                mat_index(m)
+        b = {
+            "position": np.zeros((n, 3), np.float32), "quaternion": np.zeros((n, 4), np.float32), "velocity": np.zeros((n, 3), np.float32),
+            "angular_velocity": np.zeros((n, 3), np.float32), "force": np.zeros((n, 3), np.float32), "torque": np.zeros((n, 3), np.float32),
+            "mass": np.zeros(n), "type": np.zeros(n, np.int32), "sleep_state": np.zeros(n, np.int32), "allow_sleep": np.zeros(n, np.uint8),
+            "sleep_speed_limit": np.zeros(n), "sleep_time_limit": np.zeros(n), "linear_damping": np.zeros(n), "angular_damping": np.zeros(n),
+            "linear_factor": np.zeros((n, 3), np.float32), "angular_factor": np.zeros((n, 3), np.float32), "fixed_rotation": np.zeros(n, np.uint8),
+            "collision_filter_group": np.zeros(n, np.int32), "collision_filter_mask": np.zeros(n, np.int32),
+            "collision_response": np.zeros(n, np.uint8), "is_trigger": np.zeros(n, np.uint8), "material": np.zeros(n, np.int32),
+            "shape": np.zeros(n, np.int32),
+        }
+        for i, body in enumerate(self.bodies):
+            b["position"][i], b["quaternion"][i], b["velocity"][i] = body.position, body.quaternion, body.velocity
+            b["angular_velocity"][i], b["force"][i], b["torque"][i] = body.angularVelocity, body.force, body.torque
+            b["mass"][i], b["type"][i], b["sleep_state"][i] = body.mass, body.type, body.sleepState
+            b["allow_sleep"][i], b["sleep_speed_limit"][i], b["sleep_time_limit"][i] = body.allowSleep, body.sleepSpeedLimit, body.sleepTimeLimit
+            b["linear_damping"][i], b["angular_damping"][i] = body.linearDamping, body.angularDamping
+            b["linear_factor"][i], b["angular_factor"][i], b["fixed_rotation"][i] = body.linearFactor, body.angularFactor, body.fixedRotation
+            b["collision_filter_group"][i], b["collision_filter_mask"][i] = body.collisionFilterGroup, body.collisionFilterMask
+            b["collision_response"][i], b["is_trigger"][i] = body.collisionResponse, body.isTrigger
+            b["material"][i] = mat_index(body.material)
+            if body.shapes:
+                sh = body.shapes[0]
+                if id(sh) not in shape_ids:
+                    shape_ids[id(sh)] = len(shapes)
+                    shapes.append(sh._desc())
+                b["shape"][i] = shape_ids[id(sh)]
+            else:
+                b["shape"][i] = -1
+        bp = self.broadphase
+        desc = dict(gravity=self.gravity, allow_sleep=int(self.allowSleep), quat_normalize_skip=self.quatNormalizeSkip,
+                    quat_normalize_fast=int(self.quatNormalizeFast), solver_kind=self.solver.kind, solver_iterations=self.solver.iterations,
+                    solver_tolerance=self.solver.tolerance, broadphase_kind=bp.kind, use_bounding_boxes=int(bp.useBoundingBoxes))
+        if self.frictionGravity is not None:
+            desc.update(friction_gravity=self.frictionGravity, has_friction_gravity=1)
+        if isinstance(bp, SAPBroadphase):
+            desc["sap_axis"] = bp.axisIndex
+        if isinstance(bp, GridBroadphase):
+            desc.update(grid_min=bp.aabbMin, grid_max=bp.aabbMax, grid_nx=bp.nx, grid_ny=bp.ny, grid_nz=bp.nz)
+        d = self.defaultContactMaterial
+        desc["default_contact_material"] = dict(friction=d.friction, restitution=d.restitution, contact_equation_stiffness=d.contactEquationStiffness,
+                                                contact_equation_relaxation=d.contactEquationRelaxation,
+                                                friction_equation_stiffness=d.frictionEquationStiffness,
+                                                friction_equation_relaxation=d.frictionEquationRelaxation)
+        cms = [dict(material_a=mat_ids[id(c.materials[0])], material_b=mat_ids[id(c.materials[1])], friction=c.friction, restitution=c.restitution,
+                    contact_equation_stiffness=c.contactEquationStiffness, contact_equation_relaxation=c.contactEquationRelaxation,
+                    friction_equation_stiffness=c.frictionEquationStiffness, friction_equation_relaxation=c.frictionEquationRelaxation)
+               for c in self.contactmaterials]
+        idx = {id(body): i for i, body in enumerate(self.bodies)}
+        cons = [c._desc(idx) for c in self.constraints]
+        return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n,
+                         material_friction=np.array([m.friction for m in mats], dtype=np.float64) if mats else None,
+                         material_restitution=np.array([m.restitution for m in mats], dtype=np.float64) if mats else None,
+                         contact_materials=cms, constraints=cons, name="api_world")
+
+    def _ensure_uploaded(self):
+        if self._structure_dirty or self._dev is None:
+            if self._dev is not None:
+                self._dev.close()
+            self._dev = DeviceWorld(self._lib, self._spec(), device=self._device)
+            self._dev.set_time(self.time)
+            self._structure_dirty = False
+            self._state_dirty = False
+        elif self._state_dirty:
+            n = len(self.bodies)
+            st = lambda attr: np.stack([getattr(b, attr) for b in self.bodies]).astype(np.float32)
+            self._dev.update_bodies(0, n, position=st("position"), quaternion=st("quaternion"), velocity=st("velocity"),
+                                    angular_velocity=st("angularVelocity"), force=st("force"), torque=st("torque"))
+            self._state_dirty = False
+
+    def markDirty(self):
+        """Call after writing body vectors in place (``body.position[:] = ...``) between steps."""
+        self._state_dirty = True
+
+    def step(self, dt: float, timeSinceLastCalled: Optional[float] = None, maxSubSteps: int = 10, nsteps: int = 1, sync: bool = True):
+        """World.step(dt) in fixed-stepping mode (world_class.dart:392-399)."""
+        if timeSinceLastCalled is not None:
+            raise CannonError(F.E_UNSUPPORTED, "interpolated stepping is host-side glue outside the hot-path scope")
+        self._ensure_uploaded()
+        self._dev.step(dt, nsteps)
+        self.dt = dt
+        self.time, self.stepnumber = self._dev.get_time()
+        if sync:
+            self.sync()
+
+    def sync(self):
+        """Refresh the Body objects from device state."""
+        st = self._dev.get_bodies(("position", "quaternion", "velocity", "angular_velocity", "sleep_state"))
+        for i, body in enumerate(self.bodies):
+            body.position[:] = st["position"][i]
+            body.quaternion[:] = st["quaternion"][i]
+            body.velocity[:] = st["velocity"][i]
+            body.angularVelocity[:] = st["angular_velocity"][i]
+            body.sleepState = int(st["sleep_state"][i])
+            body.force[:] = 0
+            body.torque[:] = 0
+
+    @property
+    def contacts(self):
+        """World.contacts of the last step as SoA arrays."""
+        self._ensure_uploaded()
+        return self._dev.get_contacts()
+
+    @property
+    def profile(self):
+        self._ensure_uploaded()
+        return self._dev.profile()
+
+
+CudaWorld = World

@@ -1,0 +1,1385 @@
+// cannon_cuda.cu — libcannon_cuda.so: C ABI (include/cannon_cuda.h) + step orchestration.
+//
+// One cannon_world owns device-resident SoA state; World.internalStep (lib/world/world_class.dart:433-701) is a
+// fixed sequence of kernel launches on one stream with every data-dependent count kept on the device, so
+// nsteps steps are enqueued back to back without a host round trip. There is no CPU fallback: without a CUDA
+// device cannon_ctx_create fails with CANNON_E_NOGPU.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dmath.cuh"
+#include "k_body.cuh"
+#include "k_broadphase.cuh"
+#include "k_narrowphase.cuh"
+#include "k_solver.cuh"
+#include "world.cuh"
+
+// ---- device counters ---------------------------------------------------------------------------------
+enum {
+  CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
+  CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
+  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = CT_BUCKETCURSOR + NP_NTYPES, CT_COUNT = CT_BAR + 2
+};
+
+__global__ void k_bucket_starts(int* cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int s = 0;
+    for (int t = 0; t < NP_NTYPES; t++) { cnt[CT_BUCKETSTART + t] = s; s += cnt[CT_BUCKETCOUNT + t]; cnt[CT_BUCKETCURSOR + t] = 0; }
+  }
+}
+__global__ void k_set_int(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
+// constraint-pair filter, world_class.dart:488-499: drop pairs joined by a constraint with collideConnected == false
+__global__ void __launch_bounds__(256) k_pair_filter_flags(const int* __restrict__ p1, const int* __restrict__ p2, const int* __restrict__ nPairs,
+                                                           int cap, const unsigned long long* __restrict__ keys, int nKeys, int* __restrict__ keep) {
+  const int np = min(*nPairs, cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const unsigned a = (unsigned)min(p1[k], p2[k]), b = (unsigned)max(p1[k], p2[k]);
+    const unsigned long long key = ((unsigned long long)a << 32) | b;
+    int lo = 0, hi = nKeys;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    keep[k] = (lo < nKeys && keys[lo] == key) ? 0 : 1;
+  }
+}
+__global__ void __launch_bounds__(256) k_pair_filter_compact(const int* __restrict__ p1, const int* __restrict__ p2, const int* __restrict__ nPairs,
+                                                             int cap, const int* __restrict__ keep, const int* __restrict__ off,
+                                                             int* __restrict__ q1, int* __restrict__ q2) {
+  const int np = min(*nPairs, cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
+    if (keep[k]) { q1[off[k]] = p1[k]; q2[off[k]] = p2[k]; }
+}
+
+// Solver epilogue when the solve is invoked on its own (gs_solver.dart:111-121); the fused step folds this into k_integrate
+__global__ void __launch_bounds__(256) k_apply_lambda(BodyArrays B, int n, int nWorlds, const int* __restrict__ worldRows) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (worldRows[nWorlds > 1 ? B.world[i] : 0] <= 0) continue;
+    const f3 vl = vmulc(ld3(B.vlam[i]), ld3(B.linF[i]));
+    B.vel[i] = st3(vadd(vl, ld3(B.vel[i])));
+    const f3 wl = vmulc(ld3(B.wlam[i]), ld3(B.angF[i]));
+    B.angvel[i] = st3(vadd(wl, ld3(B.angvel[i])));
+  }
+}
+__global__ void __launch_bounds__(256) k_multipliers(ContactArrays C, RowArrays R, int contactCap, double invDt, double* __restrict__ out) {
+  const int nc = min(*C.nContacts, contactCap);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const int r = C.row[c];
+    out[c] = r >= 0 ? R.lambda[r] * invDt : 0.0;  // Equation.multiplier, gs_solver.dart:124-129
+  }
+}
+
+// ---- world -------------------------------------------------------------------------------------------
+struct HostShape {
+  int type = 0, collisionResponse = 1, group = -1, mask = -1;
+  double radius = 0, bsr = 0;
+  float he[3] = {0, 0, 0};
+  int hull = -1, hf = -1;
+};
+
+struct cannon_world {
+  cannon_ctx* ctx = nullptr;
+  cannon_world_desc desc;
+  int n = 0;
+  double time = 0, dt = -1, powDt = -1;
+  int64_t stepnumber = 0;
+  cannon_profile prof{};
+
+  // host mirrors needed for derived quantities
+  std::vector<HostShape> hShapes;
+  std::vector<HostHull> hHulls;
+  std::vector<HfDev> hHfs;
+  std::vector<double> hHfData;
+  std::vector<double> hLdamp, hAdamp;
+  std::vector<int> hBig, hBigWorldStart, hWorldStart;
+  double cell = 1.0;
+  int nBig = 0, hashSize = 1024;
+  int nMat = 0;
+
+  // device: bodies
+  DBuf<float4> pos, quat, vel, angvel, force, torque, vlam, wlam, iiw0, iiw1, iiw2, invI, linF, angF, aabbLo, aabbHi;
+  DBuf<double> mass, invMass, brad, ldamp, adamp, ldpow, adpow, sleepSpeed, sleepTime, tLastSleepy;
+  DBuf<int> type, sleep, shape, material, group, mask, world, flags;
+  // device: shape tables
+  DBuf<ShapeDev> dShapes;
+  DBuf<HullDev> dHulls;
+  DBuf<float4> dVerts, dFnormals, dEdges;
+  DBuf<double> dFplanec, dHfData, dMatFriction, dMatRestitution;
+  DBuf<int> dFvOff, dFvIdx, dFcOff, dFcIdx, dCmTable;
+  DBuf<HfDev> dHfs;
+  DBuf<cannon_contact_material> dCms;
+  // device: broadphase
+  DBuf<int4> cellc, smeta, scell;
+  DBuf<int> binLo, binHi, cellStart, cellEnd, bigList, bigWorldStart, worldStart, bpCounts, bpOffs;
+  DBuf<uint32_t> skey, sval, sapKey, sapList;
+  DBuf<float4> spos;
+  DBuf<double> srad;
+  DBuf<int> p1, p2, q1, q2, keep, keepOff;
+  DBuf<unsigned long long> filterKeys;
+  int nFilterKeys = 0;
+  bool sapInit = false;
+  int pairCap = 0;
+  // device: narrowphase
+  DBuf<int> pairTasks, pairTaskOff, taskPair, taskInfo, bucket, taskCnt, taskRaw, taskOff;
+  DBuf<int2> taskCell;
+  DBuf<float4> rawRi, rawRj, rawNi;
+  int taskCap = 0, contactCap = 0;
+  // device: contacts
+  DBuf<int> cBi, cBj, cEnabled, cRow, fricFlag, contFlag, fricOff, contOff;
+  DBuf<float4> cRi, cRj, cNi;
+  DBuf<double> cRest, cMu, cSlip, cCa, cCb, cCeps, cFb, cFeps, cMult;
+  // device: rows
+  DBuf<int> rBi, rBj, rKind, rFlags;
+  DBuf<float4> rN, rRA, rRB, rIA, rIB;
+  DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rImA, rImB, rLambda;
+  int rowCap = 0;
+  // device: joints
+  DBuf<int> jBodyA, jBodyB, jKind, jEnabled, jRowSlot, jFirst;
+  DBuf<float4> jPivotA, jPivotB, jAxisA, jAxisB, jNi;
+  DBuf<double> jMinF, jMaxF, jA, jB, jEps, jTargetVel;
+  int nJointEq = 0, nJointAccepted = 0;
+  // device: scheduler / gs
+  DBuf<unsigned long long> claim;
+  DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters;
+  DBuf<double> worldTot;
+  int maxLevels = 0;
+  // counters
+  DBuf<int> cnt;
+  int* hCnt = nullptr;  // pinned
+  ScanTmp scanTmp;
+  SortTmp sortTmp;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int coopBlocksSched = 0, coopBlocksGs = 0;
+
+  ~cannon_world() {
+    if (hCnt) cudaFreeHost(hCnt);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+};
+
+static int32_t fail(cannon_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define W_TRY(w, expr) CU_TRY((w)->ctx, expr)
+
+template <class T>
+static cudaError_t upload(DBuf<T>& d, const std::vector<T>& h, cudaStream_t s) {
+  cudaError_t e = d.reserve(h.size() ? h.size() : 1);
+  if (e != cudaSuccess) return e;
+  if (h.empty()) return cudaSuccess;
+  return cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+static BodyArrays body_arrays(cannon_world* w) {
+  BodyArrays B;
+  B.pos = w->pos.p; B.quat = w->quat.p; B.vel = w->vel.p; B.angvel = w->angvel.p; B.force = w->force.p; B.torque = w->torque.p;
+  B.vlam = w->vlam.p; B.wlam = w->wlam.p; B.iiw0 = w->iiw0.p; B.iiw1 = w->iiw1.p; B.iiw2 = w->iiw2.p;
+  B.invI = w->invI.p; B.linF = w->linF.p; B.angF = w->angF.p; B.aabbLo = w->aabbLo.p; B.aabbHi = w->aabbHi.p;
+  B.mass = w->mass.p; B.invMass = w->invMass.p; B.brad = w->brad.p; B.ldamp = w->ldamp.p; B.adamp = w->adamp.p;
+  B.ldpow = w->ldpow.p; B.adpow = w->adpow.p; B.sleepSpeed = w->sleepSpeed.p; B.sleepTime = w->sleepTime.p; B.tLastSleepy = w->tLastSleepy.p;
+  B.type = w->type.p; B.sleep = w->sleep.p; B.shape = w->shape.p; B.material = w->material.p; B.group = w->group.p; B.mask = w->mask.p;
+  B.world = w->world.p; B.flags = w->flags.p;
+  return B;
+}
+static ShapeTables shape_tables(cannon_world* w) {
+  ShapeTables T;
+  T.shapes = w->dShapes.p; T.hulls = w->dHulls.p; T.verts = w->dVerts.p; T.fnormals = w->dFnormals.p; T.fplanec = w->dFplanec.p;
+  T.fvOff = w->dFvOff.p; T.fvIdx = w->dFvIdx.p; T.fcOff = w->dFcOff.p; T.fcIdx = w->dFcIdx.p; T.edges = w->dEdges.p;
+  T.hfs = w->dHfs.p; T.hfdata = w->dHfData.p; T.cmTable = w->dCmTable.p; T.cms = w->dCms.p;
+  T.matFriction = w->dMatFriction.p; T.matRestitution = w->dMatRestitution.p; T.nMat = w->nMat;
+  return T;
+}
+static int grid_for(cannon_world* w, long long n, int threads) {
+  int g = div_up(n > 0 ? n : 1, threads);
+  int mx = w->ctx->sms * 16;
+  return g < 1 ? 1 : (g > mx ? mx : g);
+}
+
+extern "C" {
+
+int32_t cannon_version(void) { return CANNON_ABI_VERSION; }
+const char* cannon_backend(void) { return "cuda"; }
+
+int32_t cannon_ctx_create(int32_t device, cannon_ctx** out) {
+  if (!out) return CANNON_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return CANNON_E_NOGPU;
+  cannon_ctx* ctx = new (std::nothrow) cannon_ctx();
+  if (!ctx) return CANNON_E_INVALID;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CANNON_E_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CANNON_E_CUDA; }
+  *out = ctx;
+  return CANNON_OK;
+}
+void cannon_ctx_destroy(cannon_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+const char* cannon_last_error(const cannon_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+void cannon_world_desc_default(cannon_world_desc* d) {
+  memset(d, 0, sizeof(*d));
+  d->solver_kind = CANNON_SOLVER_REFERENCE_ORDER;
+  d->solver_iterations = 10;   // lib/solver/solver.dart:17
+  d->solver_tolerance = 1e-7;  // lib/solver/solver.dart:18
+  d->broadphase_kind = CANNON_BP_NAIVE;  // world_class.dart:153
+  d->grid_nx = d->grid_ny = d->grid_nz = 10;  // grid_broadphase.dart:37-41
+  for (int k = 0; k < 3; k++) { d->grid_min[k] = 100; d->grid_max[k] = -100; }
+  cannon_contact_material& cm = d->default_contact_material;  // world_class.dart:155-158, contact_material.dart:45-70
+  cm.material_a = cm.material_b = -1;
+  cm.friction = 0.3;
+  cm.restitution = 0.0;
+  cm.contact_equation_stiffness = 1e7;
+  cm.contact_equation_relaxation = 3;
+  cm.friction_equation_stiffness = 1e7;
+  cm.friction_equation_relaxation = 3;
+  d->n_worlds = 1;
+}
+void cannon_shape_desc_default(cannon_shape_desc* d) {
+  memset(d, 0, sizeof(*d));
+  d->type = CANNON_SHAPE_SPHERE;
+  d->collision_response = 1;
+  d->collision_filter_group = -1;
+  d->collision_filter_mask = -1;
+  d->radius = 1.0;
+  d->radius_top = d->radius_bottom = d->height = 1.0;
+  d->num_segments = 8;
+  d->hf_element_size = 1;
+}
+
+int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out) {
+  if (!ctx || !desc || !out) return CANNON_E_INVALID;
+  cudaSetDevice(ctx->device);
+  cannon_world* w = new (std::nothrow) cannon_world();
+  if (!w) return CANNON_E_INVALID;
+  w->ctx = ctx;
+  w->desc = *desc;
+  if (w->desc.n_worlds < 1) w->desc.n_worlds = 1;
+  if (w->desc.broadphase_kind == CANNON_BP_GRID && (desc->grid_nx > 1024 || desc->grid_ny > 1024 || desc->grid_nz > 1024 ||
+                                                    desc->grid_nx < 1 || desc->grid_ny < 1 || desc->grid_nz < 1)) {
+    delete w;
+    return fail(ctx, CANNON_E_INVALID, "GridBroadphase: each dimension's n must be in 1..1024");
+  }
+  if (w->desc.n_worlds > 1 && w->desc.broadphase_kind == CANNON_BP_SAP) {
+    delete w;
+    return fail(ctx, CANNON_E_UNSUPPORTED, "batched worlds support NaiveBroadphase / GridBroadphase only");
+  }
+  if (cudaMallocHost((void**)&w->hCnt, CT_COUNT * sizeof(int)) != cudaSuccess) { delete w; return fail(ctx, CANNON_E_CUDA, "cudaMallocHost failed"); }
+  memset(w->hCnt, 0, CT_COUNT * sizeof(int));
+  if (w->cnt.reserve(CT_COUNT) != cudaSuccess) { delete w; return fail(ctx, CANNON_E_CUDA, "cudaMalloc failed"); }
+  cudaMemsetAsync(w->cnt.p, 0, CT_COUNT * sizeof(int), ctx->stream);
+  for (auto& e : w->ev) cudaEventCreate(&e);
+  // empty tables so kernels always get valid pointers
+  std::vector<double> e0;
+  upload(w->dMatFriction, e0, ctx->stream);
+  upload(w->dMatRestitution, e0, ctx->stream);
+  w->dCmTable.reserve(1);
+  w->dCms.reserve(1);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_schedule, 256, 0);
+  w->coopBlocksSched = ctx->sms * std::max(1, std::min(occ, 4));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs, 256, 0);
+  w->coopBlocksGs = ctx->sms * std::max(1, std::min(occ, 4));
+  *out = w;
+  return CANNON_OK;
+}
+void cannon_world_destroy(cannon_world* w) {
+  if (!w) return;
+  cudaSetDevice(w->ctx->device);
+  cudaStreamSynchronize(w->ctx->stream);
+  // DBuf members are released explicitly (plain structs, no destructors)
+#define REL(x) w->x.release()
+  REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(vlam); REL(wlam); REL(iiw0); REL(iiw1); REL(iiw2);
+  REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
+  REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
+  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData);
+  REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
+  REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
+  REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
+  REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
+  REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
+  REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
+  REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rBi); REL(rBj); REL(rKind); REL(rFlags); REL(rN); REL(rRA); REL(rRB);
+  REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rImA); REL(rImB); REL(rLambda); REL(jBodyA); REL(jBodyB);
+  REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
+  REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt);
+  w->scanTmp.tiles.release();
+  w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
+#undef REL
+  delete w;
+}
+
+int32_t cannon_world_set_materials(cannon_world* w, int32_t n, const double* friction, const double* restitution, int32_t ncm,
+                                   const cannon_contact_material* cms) {
+  if (!w || n < 0 || ncm < 0) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  std::vector<double> f(n, -1.0), r(n, -1.0);
+  for (int i = 0; i < n; i++) { if (friction) f[i] = friction[i]; if (restitution) r[i] = restitution[i]; }
+  std::vector<int> table((size_t)n * n, -1);
+  std::vector<cannon_contact_material> v(cms, cms + ncm);
+  for (int k = 0; k < ncm; k++) {
+    const int a = cms[k].material_a, b = cms[k].material_b;
+    if (a < 0 || b < 0 || a >= n || b >= n) return fail(w->ctx, CANNON_E_INVALID, "contact material references unknown material");
+    table[(size_t)a * n + b] = k;  // unordered key, lib/utils/tuple_dictionary.dart:1-3
+    table[(size_t)b * n + a] = k;
+  }
+  W_TRY(w, upload(w->dMatFriction, f, s));
+  W_TRY(w, upload(w->dMatRestitution, r, s));
+  W_TRY(w, upload(w->dCmTable, table, s));
+  W_TRY(w, upload(w->dCms, v, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  w->nMat = n;
+  return CANNON_OK;
+}
+
+int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_desc* sd) {
+  if (!w || n < 0 || (n > 0 && !sd)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  w->hShapes.assign(n, HostShape());
+  w->hHulls.clear();
+  w->hHfs.clear();
+  w->hHfData.clear();
+  for (int i = 0; i < n; i++) {
+    const cannon_shape_desc& d = sd[i];
+    HostShape& h = w->hShapes[i];
+    h.type = d.type;
+    h.collisionResponse = d.collision_response != 0;
+    h.group = d.collision_filter_group;
+    h.mask = d.collision_filter_mask;
+    switch (d.type) {
+      case CANNON_SHAPE_SPHERE:
+        if (d.radius < 0) return fail(w->ctx, CANNON_E_INVALID, "The sphere radius cannot be negative.");  // sphere.dart:16-18
+        h.radius = d.radius;
+        h.bsr = d.radius;
+        break;
+      case CANNON_SHAPE_PLANE:
+        h.bsr = INFINITY;  // plane.dart:20
+        break;
+      case CANNON_SHAPE_BOX: {
+        for (int k = 0; k < 3; k++) h.he[k] = d.half_extents[k];
+        HostHull hull;
+        host_box_hull(h.he, hull);
+        h.hull = (int)w->hHulls.size();
+        w->hHulls.push_back(hull);
+        f3 e; e.x = h.he[0]; e.y = h.he[1]; e.z = h.he[2];
+        h.bsr = vlen(e);  // box.dart:124-126
+        break;
+      }
+      case CANNON_SHAPE_CYLINDER: {
+        if (d.radius_top < 0 || d.radius_bottom < 0) return fail(w->ctx, CANNON_E_INVALID, "The cylinder radius cannot be negative.");
+        if (d.num_segments < 3) return fail(w->ctx, CANNON_E_INVALID, "cylinder needs >= 3 segments");
+        HostHull hull;
+        host_cylinder_hull(d.radius_top, d.radius_bottom, d.height, d.num_segments, hull);
+        h.hull = (int)w->hHulls.size();
+        h.bsr = hull.bsr;  // after Body.addShape -> updateBoundingSphereRadius (rigid_body.dart:403)
+        w->hHulls.push_back(hull);
+        break;
+      }
+      case CANNON_SHAPE_CONVEX: {
+        if (d.n_vertices <= 0 || d.n_faces <= 0 || !d.vertices || !d.face_offsets || !d.face_indices)
+          return fail(w->ctx, CANNON_E_INVALID, "convex shape needs vertices and faces");
+        HostHull hull;
+        for (int v = 0; v < d.n_vertices; v++) { f3 p; p.x = d.vertices[3 * v]; p.y = d.vertices[3 * v + 1]; p.z = d.vertices[3 * v + 2]; hull.v.push_back(p); }
+        for (int f = 0; f < d.n_faces; f++) {
+          std::vector<int> face(d.face_indices + d.face_offsets[f], d.face_indices + d.face_offsets[f + 1]);
+          if (face.size() < 3) return fail(w->ctx, CANNON_E_INVALID, "convex face needs >= 3 vertices");
+          for (int idx : face) if (idx < 0 || idx >= d.n_vertices) return fail(w->ctx, CANNON_E_INVALID, "convex face index out of range");
+          hull.faces.push_back(face);
+        }
+        hull.hasAxes = false;  // plain ConvexPolyhedron: no `axes` => no face-normal axes
+        hull.finish();
+        h.hull = (int)w->hHulls.size();
+        h.bsr = hull.bsr;
+        w->hHulls.push_back(hull);
+        break;
+      }
+      case CANNON_SHAPE_HEIGHTFIELD: {
+        if (d.hf_nx < 2 || d.hf_ny < 2 || !d.hf_data) return fail(w->ctx, CANNON_E_INVALID, "heightfield needs >= 2x2 samples");
+        HfDev hf;
+        hf.nx = d.hf_nx; hf.ny = d.hf_ny; hf.esize = d.hf_element_size; hf.dataOff = (int)w->hHfData.size();
+        const size_t cntv = (size_t)d.hf_nx * d.hf_ny;
+        double mn = d.hf_data[0], mx = d.hf_data[0];  // updateMinValue / updateMaxValue, heightfield.dart:87-113
+        for (size_t k = 0; k < cntv; k++) { mn = d.hf_data[k] < mn ? d.hf_data[k] : mn; mx = d.hf_data[k] > mx ? d.hf_data[k] : mx; }
+        hf.minV = mn; hf.maxV = mx;
+        w->hHfData.insert(w->hHfData.end(), d.hf_data, d.hf_data + cntv);
+        h.hf = (int)w->hHfs.size();
+        w->hHfs.push_back(hf);
+        const double es = (double)hf.esize;  // updateBoundingSphereRadius, heightfield.dart:505-515
+        f3 t = mk3(hf.nx * es, hf.ny * es, fmax(fabs(mx), fabs(mn)));
+        h.bsr = vlen(t);
+        break;
+      }
+      default:
+        return fail(w->ctx, CANNON_E_UNSUPPORTED, "shape type outside the hot-path scope (SURVEY.md §8)");
+    }
+  }
+  // flatten
+  std::vector<ShapeDev> shapes(n);
+  for (int i = 0; i < n; i++) {
+    const HostShape& h = w->hShapes[i];
+    ShapeDev& d = shapes[i];
+    d.type = h.type; d.collisionResponse = h.collisionResponse; d.group = h.group; d.mask = h.mask;
+    d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.pad = 0;
+  }
+  std::vector<HullDev> hulls;
+  std::vector<float4> verts, fnormals, edges;
+  std::vector<double> fplanec;
+  std::vector<int> fvOff, fvIdx, fcOff, fcIdx;
+  int totalFaces = 0;
+  for (size_t k = 0; k < w->hHulls.size(); k++) {
+    const HostHull& h = w->hHulls[k];
+    HullDev d;
+    d.vOff = (int)verts.size(); d.nV = (int)h.v.size();
+    d.fOff = totalFaces; d.nF = (int)h.faces.size();
+    d.eOff = (int)edges.size(); d.nE = (int)h.edges.size();
+    d.hasAxes = h.hasAxes ? 1 : 0; d.pad = 0; d.bsr = h.bsr;
+    for (const f3& p : h.v) verts.push_back(st3(p));
+    for (const f3& p : h.edges) edges.push_back(st3(p));
+    for (size_t f = 0; f < h.faces.size(); f++) {
+      fnormals.push_back(st3(h.n[f]));
+      fplanec.push_back(h.planec[f]);
+      fvOff.push_back((int)fvIdx.size());
+      for (int idx : h.faces[f]) fvIdx.push_back(idx);
+      fcOff.push_back((int)fcIdx.size());
+      for (int idx : h.connected[f]) fcIdx.push_back(idx);
+    }
+    fvOff.push_back((int)fvIdx.size());  // CSR terminator per hull: segment of hull k starts at fOff + k
+    fcOff.push_back((int)fcIdx.size());
+    totalFaces += d.nF;
+    hulls.push_back(d);
+  }
+  W_TRY(w, upload(w->dShapes, shapes, s));
+  W_TRY(w, upload(w->dHulls, hulls, s));
+  W_TRY(w, upload(w->dVerts, verts, s));
+  W_TRY(w, upload(w->dFnormals, fnormals, s));
+  W_TRY(w, upload(w->dEdges, edges, s));
+  W_TRY(w, upload(w->dFplanec, fplanec, s));
+  W_TRY(w, upload(w->dFvOff, fvOff, s));
+  W_TRY(w, upload(w->dFvIdx, fvIdx, s));
+  W_TRY(w, upload(w->dFcOff, fcOff, s));
+  W_TRY(w, upload(w->dFcIdx, fcIdx, s));
+  W_TRY(w, upload(w->dHfs, w->hHfs, s));
+  W_TRY(w, upload(w->dHfData, w->hHfData, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
+// host twin of shape_aabb for the upload path (Body.updateMassProperties needs the AABB once)
+static void host_shape_aabb(const cannon_world* w, int shapeIdx, const f3& pos, const q4& q, f3& mn, f3& mx) {
+  if (shapeIdx < 0) { mn = pos; mx = pos; return; }
+  const HostShape& s = w->hShapes[shapeIdx];
+  const float inf = INFINITY;
+  switch (s.type) {
+    case CANNON_SHAPE_SPHERE: {
+      const double r = s.radius;
+      mn = mk3(W(pos.x) - r, W(pos.y) - r, W(pos.z) - r);
+      mx = mk3(W(pos.x) + r, W(pos.y) + r, W(pos.z) + r);
+      break;
+    }
+    case CANNON_SHAPE_PLANE: {
+      f3 z; z.x = 0.f; z.y = 0.f; z.z = 1.f;
+      const f3 n = qrot(q, z);
+      mn.x = mn.y = mn.z = -inf;
+      mx.x = mx.y = mx.z = inf;
+      if (n.x == 1.f) mx.x = pos.x; else if (n.x == -1.f) mn.x = pos.x;
+      if (n.y == 1.f) mx.y = pos.y; else if (n.y == -1.f) mn.y = pos.y;
+      if (n.z == 1.f) mx.z = pos.z; else if (n.z == -1.f) mn.z = pos.z;
+      break;
+    }
+    case CANNON_SHAPE_BOX: {
+      const float sx[8] = {1, -1, -1, -1, 1, 1, -1, 1}, sy[8] = {1, 1, -1, -1, -1, 1, 1, -1}, sz[8] = {1, 1, 1, -1, -1, -1, -1, 1};
+      for (int i = 0; i < 8; i++) {
+        f3 c; c.x = sx[i] * s.he[0]; c.y = sy[i] * s.he[1]; c.z = sz[i] * s.he[2];
+        const f3 p = vadd(qrot(q, c), pos);
+        if (i == 0) { mn = p; mx = p; continue; }
+        if (p.x > mx.x) mx.x = p.x;
+        if (p.y > mx.y) mx.y = p.y;
+        if (p.z > mx.z) mx.z = p.z;
+        if (p.x < mn.x) mn.x = p.x;
+        if (p.y < mn.y) mn.y = p.y;
+        if (p.z < mn.z) mn.z = p.z;
+      }
+      break;
+    }
+    case CANNON_SHAPE_CONVEX:
+    case CANNON_SHAPE_CYLINDER: {
+      const HostHull& h = w->hHulls[s.hull];
+      for (size_t i = 0; i < h.v.size(); i++) {
+        const f3 p = vadd(qrot(q, h.v[i]), pos);
+        if (i == 0) { mn = p; mx = p; continue; }
+        if (p.x < mn.x) mn.x = p.x;
+        if (p.x > mx.x) mx.x = p.x;
+        if (p.y < mn.y) mn.y = p.y;
+        if (p.y > mx.y) mx.y = p.y;
+        if (p.z < mn.z) mn.z = p.z;
+        if (p.z > mx.z) mx.z = p.z;
+      }
+      break;
+    }
+    default:
+      mn.x = mn.y = mn.z = -inf;
+      mx.x = mx.y = mx.z = inf;
+      break;
+  }
+}
+
+static int32_t ensure_capacities(cannon_world* w) {
+  const int n = w->n;
+  const int pairCap = w->desc.max_pairs > 0 ? w->desc.max_pairs : std::max(4096, 24 * n);
+  const int contactCap = w->desc.max_contacts > 0 ? w->desc.max_contacts : std::max(4096, 32 * n);
+  const int taskCap = std::max(2 * pairCap, 48 * n);
+  const int rowCap = 3 * contactCap + w->nJointAccepted + 16;
+  w->pairCap = pairCap; w->contactCap = contactCap; w->taskCap = taskCap; w->rowCap = rowCap;
+  w->maxLevels = std::min(rowCap, 1 << 20);
+#define RES(buf, cnt) W_TRY(w, w->buf.reserve((size_t)(cnt)))
+  RES(p1, pairCap); RES(p2, pairCap); RES(q1, pairCap); RES(q2, pairCap); RES(keep, pairCap); RES(keepOff, pairCap);
+  RES(pairTasks, pairCap); RES(pairTaskOff, pairCap);
+  RES(taskPair, taskCap); RES(taskInfo, taskCap); RES(taskCell, taskCap); RES(bucket, taskCap); RES(taskCnt, taskCap); RES(taskRaw, taskCap);
+  RES(taskOff, taskCap);
+  RES(rawRi, contactCap); RES(rawRj, contactCap); RES(rawNi, contactCap);
+  RES(cBi, contactCap); RES(cBj, contactCap); RES(cEnabled, contactCap); RES(cRow, contactCap); RES(fricFlag, contactCap);
+  RES(contFlag, contactCap); RES(fricOff, contactCap); RES(contOff, contactCap); RES(cRi, contactCap); RES(cRj, contactCap);
+  RES(cNi, contactCap); RES(cRest, contactCap); RES(cMu, contactCap); RES(cSlip, contactCap); RES(cCa, contactCap); RES(cCb, contactCap);
+  RES(cCeps, contactCap); RES(cFb, contactCap); RES(cFeps, contactCap); RES(cMult, contactCap);
+  RES(rBi, rowCap); RES(rBj, rowCap); RES(rKind, rowCap); RES(rFlags, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
+  RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
+  RES(rImA, rowCap); RES(rImB, rowCap); RES(rLambda, rowCap);
+  RES(unitLevel, rowCap); RES(order, rowCap); RES(act0, rowCap); RES(act1, rowCap); RES(levelStart, w->maxLevels + 2);
+  RES(claim, n + 1);
+  const int nW = w->desc.n_worlds;
+  RES(worldRows, nW + 1); RES(worldDone, nW + 2); RES(worldIters, nW + 1); RES(worldTot, nW + 1);
+#undef RES
+  return CANNON_OK;
+}
+
+int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
+  if (!w || !sb || sb->n < 0) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  const int n = sb->n;
+  const int nW = w->desc.n_worlds;
+  std::vector<float4> pos(n), quat(n), vel(n), angvel(n), force(n), torque(n), zero4(n, make_float4(0, 0, 0, 0)), iiw0(n), iiw1(n), iiw2(n),
+      invI(n), linF(n), angF(n);
+  std::vector<double> mass(n), invMass(n), brad(n), ldamp(n), adamp(n), sleepSpeed(n), sleepTime(n), tLast(n);
+  std::vector<int> type(n), sleep(n), shape(n), material(n), group(n), mask(n), world(n), flags(n);
+  auto g3 = [](const float* a, int i, float dx, float dy, float dz) {
+    return a ? make_float4(a[3 * i], a[3 * i + 1], a[3 * i + 2], 0.f) : make_float4(dx, dy, dz, 0.f);
+  };
+  double radSum = 0;
+  int radCnt = 0;
+  for (int i = 0; i < n; i++) {
+    pos[i] = g3(sb->position, i, 0, 0, 0);
+    quat[i] = sb->quaternion ? make_float4(sb->quaternion[4 * i], sb->quaternion[4 * i + 1], sb->quaternion[4 * i + 2], sb->quaternion[4 * i + 3])
+                             : make_float4(0, 0, 0, 1);
+    vel[i] = g3(sb->velocity, i, 0, 0, 0);
+    angvel[i] = g3(sb->angular_velocity, i, 0, 0, 0);
+    force[i] = g3(sb->force, i, 0, 0, 0);
+    torque[i] = g3(sb->torque, i, 0, 0, 0);
+    linF[i] = g3(sb->linear_factor, i, 1, 1, 1);
+    angF[i] = g3(sb->angular_factor, i, 1, 1, 1);
+    mass[i] = sb->mass ? sb->mass[i] : 0.0;
+    type[i] = mass[i] <= 0.0 ? CANNON_BODY_STATIC : CANNON_BODY_DYNAMIC;  // rigid_body.dart:61
+    if (sb->type && sb->type[i] >= 0) type[i] = sb->type[i];
+    sleep[i] = sb->sleep_state ? sb->sleep_state[i] : CANNON_AWAKE;
+    tLast[i] = sb->time_last_sleepy ? sb->time_last_sleepy[i] : w->time;  // world_class.dart:291
+    sleepSpeed[i] = sb->sleep_speed_limit ? sb->sleep_speed_limit[i] : 0.1;
+    sleepTime[i] = sb->sleep_time_limit ? sb->sleep_time_limit[i] : 1.0;
+    ldamp[i] = sb->linear_damping ? sb->linear_damping[i] : 0.01;
+    adamp[i] = sb->angular_damping ? sb->angular_damping[i] : 0.01;
+    group[i] = sb->collision_filter_group ? sb->collision_filter_group[i] : 1;
+    mask[i] = sb->collision_filter_mask ? sb->collision_filter_mask[i] : -1;
+    material[i] = sb->material ? sb->material[i] : -1;
+    shape[i] = sb->shape ? sb->shape[i] : -1;
+    world[i] = sb->world_id ? sb->world_id[i] : 0;
+    if (shape[i] >= (int)w->hShapes.size()) return fail(w->ctx, CANNON_E_INVALID, "body references unknown shape");
+    if (material[i] >= w->nMat) return fail(w->ctx, CANNON_E_INVALID, "body references unknown material");
+    if (world[i] < 0 || world[i] >= nW) return fail(w->ctx, CANNON_E_INVALID, "world_id out of range");
+    if (nW > 1 && i > 0 && world[i] < world[i - 1]) return fail(w->ctx, CANNON_E_INVALID, "bodies of a batched world must be contiguous (world_id ascending)");
+    int fl = 0;
+    if (!sb->allow_sleep || sb->allow_sleep[i]) fl |= BF_ALLOW_SLEEP;
+    if (!sb->collision_response || sb->collision_response[i]) fl |= BF_COLLISION_RESPONSE;
+    if (sb->is_trigger && sb->is_trigger[i]) fl |= BF_IS_TRIGGER;
+    const bool fixedRot = sb->fixed_rotation && sb->fixed_rotation[i];
+    if (fixedRot) fl |= BF_FIXED_ROTATION;
+    // Body.updateMassProperties, rigid_body.dart:587-609: inertia of the current world AABB box
+    invMass[i] = mass[i] > 0 ? 1.0 / mass[i] : 0;
+    f3 mn, mx;
+    const f3 p = ld3(pos[i]);
+    const q4 q = ldq(quat[i]);
+    host_shape_aabb(w, shape[i], p, q, mn, mx);
+    f3 he = mk3((W(mx.x) - W(mn.x)) / 2, (W(mx.y) - W(mn.y)) / 2, (W(mx.z) - W(mn.z)) / 2);
+    if (shape[i] < 0) { he.x = he.y = he.z = 0.f; }
+    const double m = mass[i], ex = W(he.x), ey = W(he.y), ez = W(he.z);
+    f3 I;  // Box.calculateInertia, box.dart:88-94
+    I.x = (float)(1.0 / 12.0 * m * (2 * ey * 2 * ey + 2 * ez * 2 * ez));
+    I.y = (float)(1.0 / 12.0 * m * (2 * ex * 2 * ex + 2 * ez * 2 * ez));
+    I.z = (float)(1.0 / 12.0 * m * (2 * ey * 2 * ey + 2 * ex * 2 * ex));
+    const f3 iI = mk3(I.x > 0 && !fixedRot ? 1.0 / W(I.x) : 0, I.y > 0 && !fixedRot ? 1.0 / W(I.y) : 0, I.z > 0 && !fixedRot ? 1.0 / W(I.z) : 0);
+    invI[i] = st3(iI);
+    inertia_world(q, iI, iiw0[i], iiw1[i], iiw2[i]);  // updateInertiaWorld(true)
+    // Body.updateBoundingRadius, rigid_body.dart:395-412 (zero shape offset)
+    brad[i] = shape[i] >= 0 ? 0.0 + w->hShapes[shape[i]].bsr : 0.0;
+    if (brad[i] < 0) brad[i] = 0;
+    if (std::isfinite(brad[i])) { radSum += brad[i]; radCnt++; }
+    flags[i] = fl;
+  }
+  // uniform-grid parameters: bodies with a non-finite or outsized bounding radius take the "big body" path
+  const double mean = radCnt ? radSum / radCnt : 0.5;
+  const double bigThreshold = std::max(8.0 * mean, 1e-3);
+  double rmax = 0;
+  w->hBig.clear();
+  for (int i = 0; i < n; i++) {
+    if (!std::isfinite(brad[i]) || brad[i] > bigThreshold) { flags[i] |= BF_BIG; w->hBig.push_back(i); }
+    else rmax = std::max(rmax, brad[i]);
+  }
+  w->nBig = (int)w->hBig.size();
+  w->cell = std::max(2.0 * rmax * 1.0001, 1e-3);
+  int H = 1024;
+  while (H < 2 * n) H <<= 1;
+  w->hashSize = H;
+  w->hBigWorldStart.assign(nW + 1, 0);
+  w->hWorldStart.assign(nW + 1, n);
+  for (int b : w->hBig) w->hBigWorldStart[world[b] + 1]++;
+  for (int k = 0; k < nW; k++) w->hBigWorldStart[k + 1] += w->hBigWorldStart[k];
+  for (int i = n - 1; i >= 0; i--) w->hWorldStart[world[i]] = i;
+  for (int k = nW - 1; k >= 0; k--) if (w->hWorldStart[k] > w->hWorldStart[k + 1]) w->hWorldStart[k] = w->hWorldStart[k + 1];
+  w->hLdamp = ldamp;
+  w->hAdamp = adamp;
+  w->powDt = -1;
+  w->n = n;
+  w->sapInit = false;
+
+  W_TRY(w, upload(w->pos, pos, s)); W_TRY(w, upload(w->quat, quat, s)); W_TRY(w, upload(w->vel, vel, s));
+  W_TRY(w, upload(w->angvel, angvel, s)); W_TRY(w, upload(w->force, force, s)); W_TRY(w, upload(w->torque, torque, s));
+  W_TRY(w, upload(w->vlam, zero4, s)); W_TRY(w, upload(w->wlam, zero4, s)); W_TRY(w, upload(w->aabbLo, zero4, s));
+  W_TRY(w, upload(w->aabbHi, zero4, s));
+  W_TRY(w, upload(w->iiw0, iiw0, s)); W_TRY(w, upload(w->iiw1, iiw1, s)); W_TRY(w, upload(w->iiw2, iiw2, s));
+  W_TRY(w, upload(w->invI, invI, s)); W_TRY(w, upload(w->linF, linF, s)); W_TRY(w, upload(w->angF, angF, s));
+  W_TRY(w, upload(w->mass, mass, s)); W_TRY(w, upload(w->invMass, invMass, s)); W_TRY(w, upload(w->brad, brad, s));
+  W_TRY(w, upload(w->ldamp, ldamp, s)); W_TRY(w, upload(w->adamp, adamp, s)); W_TRY(w, upload(w->ldpow, ldamp, s));
+  W_TRY(w, upload(w->adpow, adamp, s)); W_TRY(w, upload(w->sleepSpeed, sleepSpeed, s)); W_TRY(w, upload(w->sleepTime, sleepTime, s));
+  W_TRY(w, upload(w->tLastSleepy, tLast, s));
+  W_TRY(w, upload(w->type, type, s)); W_TRY(w, upload(w->sleep, sleep, s)); W_TRY(w, upload(w->shape, shape, s));
+  W_TRY(w, upload(w->material, material, s)); W_TRY(w, upload(w->group, group, s)); W_TRY(w, upload(w->mask, mask, s));
+  W_TRY(w, upload(w->world, world, s)); W_TRY(w, upload(w->flags, flags, s));
+  W_TRY(w, upload(w->bigList, w->hBig, s)); W_TRY(w, upload(w->bigWorldStart, w->hBigWorldStart, s));
+  W_TRY(w, upload(w->worldStart, w->hWorldStart, s));
+  const size_t nn = (size_t)std::max(n, 1);
+  W_TRY(w, w->cellc.reserve(nn)); W_TRY(w, w->smeta.reserve(nn)); W_TRY(w, w->scell.reserve(nn)); W_TRY(w, w->binLo.reserve(nn));
+  W_TRY(w, w->binHi.reserve(nn)); W_TRY(w, w->skey.reserve(nn)); W_TRY(w, w->sval.reserve(nn)); W_TRY(w, w->sapKey.reserve(nn));
+  W_TRY(w, w->sapList.reserve(nn)); W_TRY(w, w->spos.reserve(nn)); W_TRY(w, w->srad.reserve(nn)); W_TRY(w, w->bpCounts.reserve(nn));
+  W_TRY(w, w->bpOffs.reserve(nn)); W_TRY(w, w->cellStart.reserve((size_t)H + 2)); W_TRY(w, w->cellEnd.reserve((size_t)H + 2));
+  int32_t rc = ensure_capacities(w);
+  if (rc != CANNON_OK) return rc;
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
+int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs) {
+  if (!w || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  std::vector<int> bodyA, bodyB, kind, enabled, rowSlot, first;
+  std::vector<float4> pivotA, pivotB, axisA, axisB, ni;
+  std::vector<double> minF, maxF, a, b, eps, targetVel;
+  std::vector<unsigned long long> keys;
+  // trigger flags are needed for the Solver.addEquation filter (solver.dart:30-34)
+  std::vector<int> flags(w->n);
+  if (w->n) W_TRY(w, cudaMemcpy(flags.data(), w->flags.p, w->n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> wake;
+  // Equation ctor SPOOK parameters (equation_class.dart:38): k=1e7, d=4, h=1/60 — never refreshed for joints
+  const double k0 = 1e7, d0 = 4, h0 = 1.0 / 60;
+  const double sa = 4.0 / (h0 * (1 + 4 * d0)), sbv = 4.0 * d0 / (1 + 4 * d0), se = 4.0 / (h0 * h0 * k0 * (1 + 4 * d0));
+  int slot = 0;
+  for (int i = 0; i < n; i++) {
+    const cannon_constraint_desc& d = cs[i];
+    if (d.body_a < 0 || d.body_b < 0 || d.body_a >= w->n || d.body_b >= w->n) return fail(w->ctx, CANNON_E_INVALID, "constraint references unknown body");
+    if (d.type != CANNON_CONSTRAINT_POINT_TO_POINT && d.type != CANNON_CONSTRAINT_HINGE)
+      return fail(w->ctx, CANNON_E_UNSUPPORTED, "constraint type outside the hot-path scope (SURVEY.md §8f)");
+    wake.push_back(d.body_a);
+    wake.push_back(d.body_b);
+    if (!d.collide_connected) {
+      const unsigned lo = (unsigned)std::min(d.body_a, d.body_b), hi = (unsigned)std::max(d.body_a, d.body_b);
+      keys.push_back(((unsigned long long)lo << 32) | hi);
+    }
+    const bool trig = (flags[d.body_a] & BF_IS_TRIGGER) || (flags[d.body_b] & BF_IS_TRIGGER);
+    const int firstEq = (int)bodyA.size();
+    f3 axA; axA.x = d.axis_a[0]; axA.y = d.axis_a[1]; axA.z = d.axis_a[2];
+    f3 axB; axB.x = d.axis_b[0]; axB.y = d.axis_b[1]; axB.z = d.axis_b[2];
+    vnormalize(axA);  // hinge_constraint.dart:34-37
+    vnormalize(axB);
+    const int neq = d.type == CANNON_CONSTRAINT_HINGE ? 6 : 3;
+    for (int e = 0; e < neq; e++) {
+      bodyA.push_back(d.body_a);
+      bodyB.push_back(d.body_b);
+      first.push_back(firstEq);
+      pivotA.push_back(make_float4(d.pivot_a[0], d.pivot_a[1], d.pivot_a[2], 0));
+      pivotB.push_back(make_float4(d.pivot_b[0], d.pivot_b[1], d.pivot_b[2], 0));
+      axisA.push_back(st3(axA));
+      axisB.push_back(st3(axB));
+      ni.push_back(make_float4(e == 0 ? 1.f : 0.f, e == 1 ? 1.f : 0.f, e == 2 ? 1.f : 0.f, 0.f));
+      a.push_back(sa); b.push_back(sbv); eps.push_back(se);
+      int en = 1;
+      double mf = d.max_force;
+      int kd = ROW_CONTACT;
+      double tv = 0;
+      if (e == 3 || e == 4) kd = ROW_ROT;
+      if (e == 5) {
+        kd = ROW_MOTOR;
+        en = d.motor_enabled != 0;
+        mf = d.motor_max_force > 0 ? d.motor_max_force : d.max_force;
+        tv = d.motor_target_velocity;
+      }
+      kind.push_back(kd);
+      enabled.push_back(en);
+      minF.push_back(-mf);
+      maxF.push_back(mf);
+      targetVel.push_back(tv);
+      rowSlot.push_back((en && !trig) ? slot++ : -1);
+    }
+  }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  w->nFilterKeys = (int)keys.size();
+  w->nJointEq = (int)bodyA.size();
+  w->nJointAccepted = slot;
+  W_TRY(w, upload(w->jBodyA, bodyA, s)); W_TRY(w, upload(w->jBodyB, bodyB, s)); W_TRY(w, upload(w->jKind, kind, s));
+  W_TRY(w, upload(w->jEnabled, enabled, s)); W_TRY(w, upload(w->jRowSlot, rowSlot, s)); W_TRY(w, upload(w->jFirst, first, s));
+  W_TRY(w, upload(w->jPivotA, pivotA, s)); W_TRY(w, upload(w->jPivotB, pivotB, s)); W_TRY(w, upload(w->jAxisA, axisA, s));
+  W_TRY(w, upload(w->jAxisB, axisB, s)); W_TRY(w, upload(w->jNi, ni, s)); W_TRY(w, upload(w->jMinF, minF, s));
+  W_TRY(w, upload(w->jMaxF, maxF, s)); W_TRY(w, upload(w->jA, a, s)); W_TRY(w, upload(w->jB, b, s)); W_TRY(w, upload(w->jEps, eps, s));
+  W_TRY(w, upload(w->jTargetVel, targetVel, s)); W_TRY(w, upload(w->filterKeys, keys, s));
+  // Constraint ctor wakes both bodies (constraint_class.dart:26-29)
+  if (!wake.empty()) {
+    std::vector<int> sl(w->n);
+    W_TRY(w, cudaMemcpy(sl.data(), w->sleep.p, w->n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int bidx : wake) sl[bidx] = CANNON_AWAKE;
+    W_TRY(w, cudaMemcpyAsync(w->sleep.p, sl.data(), w->n * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  W_TRY(w, cudaStreamSynchronize(s));
+  return ensure_capacities(w);
+}
+
+int32_t cannon_world_set_time(cannon_world* w, double t) { if (!w) return CANNON_E_INVALID; w->time = t; return CANNON_OK; }
+int32_t cannon_world_get_time(cannon_world* w, double* t, int64_t* stepnumber) {
+  if (!w) return CANNON_E_INVALID;
+  if (t) *t = w->time;
+  if (stepnumber) *stepnumber = w->stepnumber;
+  return CANNON_OK;
+}
+int32_t cannon_world_set_dt(cannon_world* w, double dt) { if (!w) return CANNON_E_INVALID; w->dt = dt; return CANNON_OK; }
+
+}  // extern "C"
+
+// ---- stages -------------------------------------------------------------------------------------------
+static StepParams step_params(cannon_world* w, double dt) {
+  StepParams P;
+  P.dt = dt; P.time = w->time;
+  P.gx = W(w->desc.gravity[0]); P.gy = W(w->desc.gravity[1]); P.gz = W(w->desc.gravity[2]);
+  P.n = w->n;
+  P.allowSleep = w->desc.allow_sleep;
+  P.quatNormalize = (w->stepnumber % (w->desc.quat_normalize_skip + 1)) == 0;  // world_class.dart:668
+  P.quatNormalizeFast = w->desc.quat_normalize_fast;
+  P.needAABB = (w->desc.use_bounding_boxes || w->desc.broadphase_kind != CANNON_BP_NAIVE) ? 1 : 0;
+  P.nWorlds = w->desc.n_worlds;
+  return P;
+}
+
+static int32_t st_reset_counters(cannon_world* w) {
+  W_TRY(w, cudaMemsetAsync(w->cnt.p, 0, CT_COUNT * sizeof(int), w->ctx->stream));
+  return CANNON_OK;
+}
+
+static int32_t st_prestep(cannon_world* w, double dt, int doGravity, int forceAABB) {
+  StepParams P = step_params(w, dt);
+  if (forceAABB) P.needAABB = 1;
+  if (!doGravity && !P.needAABB) return CANNON_OK;
+  k_prestep<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), shape_tables(w), P, doGravity);
+  W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static BpParams bp_params(cannon_world* w) {
+  BpParams P;
+  memset(&P, 0, sizeof P);
+  const cannon_world_desc& d = w->desc;
+  P.n = w->n; P.kind = d.broadphase_kind; P.useBoxes = d.use_bounding_boxes; P.nWorlds = d.n_worlds;
+  P.hashMask = w->hashSize - 1; P.cell = w->cell; P.nBig = w->nBig;
+  P.gnx = d.grid_nx; P.gny = d.grid_ny; P.gnz = d.grid_nz;
+  // grid_broadphase.dart:72-86
+  const double xmax = W(d.grid_max[0]), ymax = W(d.grid_max[1]), zmax = W(d.grid_max[2]);
+  const double xmin = W(d.grid_min[0]), ymin = W(d.grid_min[1]), zmin = W(d.grid_min[2]);
+  P.gxmin = xmin; P.gymin = ymin; P.gzmin = zmin;
+  P.gxmult = d.grid_nx / (xmax - xmin); P.gymult = d.grid_ny / (ymax - ymin); P.gzmult = d.grid_nz / (zmax - zmin);
+  P.gbx = (xmax - xmin) / d.grid_nx; P.gby = (ymax - ymin) / d.grid_ny; P.gbz = (zmax - zmin) / d.grid_nz;
+  P.gBinRadius = sqrt(P.gbx * P.gbx + P.gby * P.gby + P.gbz * P.gbz) * 0.5;
+  P.sapAxis = d.sap_axis;
+  return P;
+}
+static BpArrays bp_arrays(cannon_world* w) {
+  BpArrays A;
+  A.cellc = w->cellc.p; A.binLo = w->binLo.p; A.binHi = w->binHi.p; A.skey = w->skey.p; A.sval = w->sval.p;
+  A.cellStart = w->cellStart.p; A.cellEnd = w->cellEnd.p; A.spos = w->spos.p; A.srad = w->srad.p; A.smeta = w->smeta.p; A.scell = w->scell.p;
+  A.bigList = w->bigList.p; A.bigWorldStart = w->bigWorldStart.p; A.worldStart = w->worldStart.p; A.counts = w->bpCounts.p; A.offs = w->bpOffs.p;
+  A.sapKey = w->sapKey.p; A.sapList = w->sapList.p;
+  return A;
+}
+
+__global__ void k_iota(uint32_t* p, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+__global__ void k_clamp_count(int* cntp, int cap) { if (threadIdx.x == 0 && blockIdx.x == 0 && *cntp > cap) *cntp = cap; }
+
+// Broadphase.collisionPairs + constraint filter; leaves pairs in w->p1/p2 and the count in cnt[CT_NPAIRS]
+static int32_t st_broadphase(cannon_world* w) {
+  cudaStream_t s = w->ctx->stream;
+  const int n = w->n;
+  BodyArrays B = body_arrays(w);
+  BpParams P = bp_params(w);
+  BpArrays A = bp_arrays(w);
+  int* cnt = w->cnt.p;
+  if (n == 0) return CANNON_OK;
+  if (P.kind == CANNON_BP_SAP) {
+    if (!w->sapInit) {  // SAPBroadphase.setWorld: axisList = bodies in insertion order (sap_broadphase.dart:114-135)
+      k_iota<<<grid_for(w, n, 256), 256, 0, s>>>(A.sapList, n);
+      w->sapInit = true;
+    }
+    // sortList (:168-189): stable sort of the persistent list by aabb.lowerBound[axis] == insertion sort result
+    k_sap_keys<<<grid_for(w, n, 256), 256, 0, s>>>(B, P, A);
+    W_TRY(w, radix_sort_pairs(A.sapKey, A.sapList, n, 32, w->sortTmp, s));
+    const int gw = grid_for(w, (long long)n * 32, 256);
+    k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+    W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
+    k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
+  } else {
+    k_bp_cells<<<grid_for(w, n, 256), 256, 0, s>>>(B, shape_tables(w), P, A);
+    int bits = 1;
+    while ((1 << bits) <= w->hashSize) bits++;
+    W_TRY(w, radix_sort_pairs(A.skey, A.sval, n, bits, w->sortTmp, s));
+    W_TRY(w, cudaMemsetAsync(A.cellStart, 0, ((size_t)w->hashSize + 2) * sizeof(int), s));
+    W_TRY(w, cudaMemsetAsync(A.cellEnd, 0, ((size_t)w->hashSize + 2) * sizeof(int), s));
+    const int nSmall = n - w->nBig;
+    if (nSmall > 0) {
+      k_bp_ranges<<<grid_for(w, nSmall, 256), 256, 0, s>>>(P, A);
+      k_bp_reorder<<<grid_for(w, nSmall, 256), 256, 0, s>>>(B, P, A);
+      k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+    }
+    if (w->nBig > 0) k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+    W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
+    if (nSmall > 0) k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
+    if (w->nBig > 0) k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
+  }
+  k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NPAIRS, w->pairCap);
+  if (w->nFilterKeys > 0) {  // world_class.dart:488-499
+    const int g = grid_for(w, w->pairCap, 256);
+    k_pair_filter_flags<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->filterKeys.p, w->nFilterKeys, w->keep.p);
+    W_TRY(w, scan_exclusive(w->keep.p, w->keepOff.p, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NPAIRS_RAW, w->scanTmp, s));
+    k_pair_filter_compact<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->keep.p, w->keepOff.p, w->q1.p, w->q2.p);
+    W_TRY(w, cudaMemcpyAsync(cnt + CT_NPAIRS, cnt + CT_NPAIRS_RAW, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    std::swap(w->p1, w->q1);
+    std::swap(w->p2, w->q2);
+  }
+  W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static NpArrays np_arrays(cannon_world* w) {
+  NpArrays A;
+  int* cnt = w->cnt.p;
+  A.p1 = w->p1.p; A.p2 = w->p2.p; A.nPairs = cnt + CT_NPAIRS;
+  A.pairTasks = w->pairTasks.p; A.pairTaskOff = w->pairTaskOff.p; A.nTasks = cnt + CT_NTASKS;
+  A.taskPair = w->taskPair.p; A.taskInfo = w->taskInfo.p; A.taskCell = w->taskCell.p;
+  A.bucket = w->bucket.p; A.bucketCount = cnt + CT_BUCKETCOUNT; A.bucketStart = cnt + CT_BUCKETSTART; A.bucketCursor = cnt + CT_BUCKETCURSOR;
+  A.taskCnt = w->taskCnt.p; A.taskRaw = w->taskRaw.p; A.taskOff = w->taskOff.p; A.rawCount = cnt + CT_RAWCOUNT;
+  A.rawRi = w->rawRi.p; A.rawRj = w->rawRj.p; A.rawNi = w->rawNi.p;
+  A.taskCap = w->taskCap; A.contactCap = w->contactCap;
+  A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS;
+  return A;
+}
+static ContactArrays contact_arrays(cannon_world* w) {
+  ContactArrays C;
+  C.nContacts = w->cnt.p + CT_NCONTACTS;
+  C.bi = w->cBi.p; C.bj = w->cBj.p; C.ri = w->cRi.p; C.rj = w->cRj.p; C.ni = w->cNi.p;
+  C.rest = w->cRest.p; C.mu = w->cMu.p; C.slip = w->cSlip.p; C.ca = w->cCa.p; C.cb = w->cCb.p; C.ceps = w->cCeps.p;
+  C.fb = w->cFb.p; C.feps = w->cFeps.p; C.enabled = w->cEnabled.p; C.row = w->cRow.p;
+  return C;
+}
+
+// Narrowphase.getContacts over the device pair list
+static int32_t st_narrowphase(cannon_world* w, double dt) {
+  cudaStream_t s = w->ctx->stream;
+  BodyArrays B = body_arrays(w);
+  ShapeTables T = shape_tables(w);
+  NpArrays A = np_arrays(w);
+  ContactArrays C = contact_arrays(w);
+  int* cnt = w->cnt.p;
+  const int gp = grid_for(w, w->pairCap, 128);
+  k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 0);
+  W_TRY(w, scan_exclusive(A.pairTasks, A.pairTaskOff, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NTASKS, w->scanTmp, s));
+  k_bucket_starts<<<1, 32, 0, s>>>(cnt);
+  k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1);
+  const int g = w->ctx->sms * 8;
+  k_np_sphere_sphere<<<g, 256, 0, s>>>(B, T, A);
+  k_np_sphere_plane<<<g, 256, 0, s>>>(B, T, A);
+  k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A);
+  k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A);
+  k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A);
+  k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP);
+  if (!w->hHfs.empty()) {
+    k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A);
+    k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP);
+  }
+  k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
+  W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s));
+  NpWorld Wd;
+  Wd.dt = dt;
+  {
+    f3 g3;
+    if (w->desc.has_friction_gravity) { g3.x = w->desc.friction_gravity[0]; g3.y = w->desc.friction_gravity[1]; g3.z = w->desc.friction_gravity[2]; }
+    else { g3.x = w->desc.gravity[0]; g3.y = w->desc.gravity[1]; g3.z = w->desc.gravity[2]; }
+    Wd.gnorm = vlen(g3);  // narrow_phase.dart:550
+  }
+  Wd.defaultCm = w->desc.default_contact_material;
+  k_np_finalize<<<grid_for(w, w->taskCap, 256), 256, 0, s>>>(B, T, A, C, Wd);
+  W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static RowArrays row_arrays(cannon_world* w) {
+  RowArrays R;
+  R.nRows = w->cnt.p + CT_NROWS;
+  R.bi = w->rBi.p; R.bj = w->rBj.p; R.kind = w->rKind.p; R.n = w->rN.p; R.rA = w->rRA.p; R.rB = w->rRB.p; R.iA = w->rIA.p; R.iB = w->rIB.p;
+  R.B = w->rB.p; R.invC = w->rInvC.p; R.eps = w->rEps.p; R.minF = w->rMinF.p; R.maxF = w->rMaxF.p; R.imA = w->rImA.p; R.imB = w->rImB.p;
+  R.lambda = w->rLambda.p; R.flags = w->rFlags.p; R.rowCap = w->rowCap;
+  return R;
+}
+static JointArrays joint_arrays(cannon_world* w) {
+  JointArrays J;
+  J.n = w->nJointEq;
+  J.bodyA = w->jBodyA.p; J.bodyB = w->jBodyB.p; J.kind = w->jKind.p; J.enabled = w->jEnabled.p; J.rowSlot = w->jRowSlot.p;
+  J.pivotA = w->jPivotA.p; J.pivotB = w->jPivotB.p; J.axisA = w->jAxisA.p; J.axisB = w->jAxisB.p; J.ni = w->jNi.p;
+  J.minF = w->jMinF.p; J.maxF = w->jMaxF.p; J.a = w->jA.p; J.b = w->jB.p; J.eps = w->jEps.p; J.targetVel = w->jTargetVel.p;
+  J.first = w->jFirst.p; J.nAccepted = w->nJointAccepted;
+  J.cosMaxAngle = cos(M_PI / 2);  // RotationalEquation.maxAngle default, rotational_equation.dart:17
+  return J;
+}
+
+// world_class.dart:539-645 without the final velocity update (k_integrate / k_apply_lambda do that)
+static int32_t st_solve(cannon_world* w, double dt) {
+  cudaStream_t s = w->ctx->stream;
+  BodyArrays B = body_arrays(w);
+  ContactArrays C = contact_arrays(w);
+  RowArrays R = row_arrays(w);
+  int* cnt = w->cnt.p;
+  const int nW = w->desc.n_worlds;
+  SolveParams P;
+  P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
+  P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
+  const int gc = grid_for(w, w->contactCap, 256);
+  k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p, w->desc.allow_sleep);
+  W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
+  W_TRY(w, scan_exclusive(w->contFlag.p, w->contOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_CONTTOTAL, w->scanTmp, s));
+  k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n);
+  W_TRY(w, cudaMemsetAsync(w->worldRows.p, 0, (nW + 1) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nW + 2) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nW + 1) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nW + 1) * sizeof(double), s));
+  k_rows_contacts<<<grid_for(w, w->contactCap, 128), 128, 0, s>>>(B, C, R, P, w->contactCap, w->fricOff.p, w->contOff.p, cnt + CT_FRICTOTAL,
+                                                                 cnt + CT_CONTTOTAL, w->worldRows.p, cnt + CT_OVF_ROWS, w->nJointAccepted,
+                                                                 cnt + CT_NCONTACTROWS);
+  if (w->nJointEq > 0)
+    k_rows_joints<<<grid_for(w, w->nJointEq, 128), 128, 0, s>>>(B, joint_arrays(w), R, P, cnt + CT_NCONTACTROWS, w->worldRows.p, cnt + CT_OVF_ROWS);
+  // dependency levels + sweeps: persistent cooperative kernels
+  SchedArrays S;
+  S.claim = w->claim.p; S.unitLevel = w->unitLevel.p; S.order = w->order.p; S.levelStart = w->levelStart.p; S.nLevels = cnt + CT_NLEVELS;
+  S.act0 = w->act0.p; S.act1 = w->act1.p; S.actCount = cnt + CT_ACT0; S.cursor = cnt + CT_CURSOR; S.bar = (unsigned*)(cnt + CT_BAR);
+  S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS; S.nUnitsFixed = -1; S.nUnitsPtr = nullptr;
+  UnitMap U;
+  U.colored = P.colored; U.taskOff = w->taskOff.p; U.taskCnt = w->taskCnt.p; U.nTasks = cnt + CT_NTASKS; U.taskCap = w->taskCap;
+  U.nContacts = cnt + CT_NCONTACTS; U.contactCap = w->contactCap;
+  W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
+  {
+    void* args[] = {&R, &S, &U};
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
+  }
+  W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, sizeof(int), s));
+  GsStats G;
+  G.worldTot = w->worldTot.p; G.worldDone = w->worldDone.p; G.worldIters = w->worldIters.p; G.itersDone = cnt + CT_ITERS;
+  {
+    void* args[] = {&R, &B, &S, &U, &P, &G};
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
+  }
+  W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static int32_t refresh_damping(cannon_world* w, double dt) {
+  if (w->powDt == dt) return CANNON_OK;
+  // world_class.dart:652,656: pow(1 - damping, dt) with the host libm (bodies mostly share a few damping values)
+  std::vector<double> lp(w->n), ap(w->n);
+  std::map<double, double> cache;
+  auto pw = [&](double d) {
+    auto it = cache.find(d);
+    if (it != cache.end()) return it->second;
+    const double v = pow(1.0 - d, dt);
+    cache[d] = v;
+    return v;
+  };
+  for (int i = 0; i < w->n; i++) { lp[i] = pw(w->hLdamp[i]); ap[i] = pw(w->hAdamp[i]); }
+  W_TRY(w, upload(w->ldpow, lp, w->ctx->stream));
+  W_TRY(w, upload(w->adpow, ap, w->ctx->stream));
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  w->powDt = dt;
+  return CANNON_OK;
+}
+
+static int32_t st_integrate(cannon_world* w, double dt, int applyLambda) {
+  StepParams P = step_params(w, dt);
+  k_integrate<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), P, w->worldRows.p, applyLambda);
+  W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static int32_t check_overflow(cannon_world* w) {
+  const int* c = w->hCnt;
+  char buf[256];
+  if (c[CT_OVF_PAIRS] > 0) { snprintf(buf, sizeof buf, "pair capacity exceeded: need %d, have %d (set cannon_world_desc.max_pairs)", c[CT_OVF_PAIRS], w->pairCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (c[CT_OVF_TASKS] > 0 || c[CT_NTASKS] > w->taskCap) { snprintf(buf, sizeof buf, "narrowphase task capacity exceeded: need %d, have %d (raise max_pairs)", std::max(c[CT_OVF_TASKS], c[CT_NTASKS]), w->taskCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (c[CT_OVF_CONTACTS] > 0 || c[CT_NCONTACTS] > w->contactCap) { snprintf(buf, sizeof buf, "contact capacity exceeded: need %d, have %d (set cannon_world_desc.max_contacts)", std::max(c[CT_OVF_CONTACTS], c[CT_NCONTACTS]), w->contactCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (c[CT_OVF_ROWS] > 0) { snprintf(buf, sizeof buf, "row capacity exceeded: need %d, have %d", c[CT_OVF_ROWS], w->rowCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (c[CT_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
+  if (c[CT_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
+  return CANNON_OK;
+}
+
+static int32_t sync_counters(cannon_world* w) {
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaMemcpyAsync(w->hCnt, w->cnt.p, CT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  return check_overflow(w);
+}
+
+extern "C" {
+
+int32_t cannon_apply_gravity(cannon_world* w) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  int32_t rc = st_prestep(w, w->dt > 0 ? w->dt : 1.0 / 60, 1, 0);
+  if (rc != CANNON_OK) return rc;
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  return CANNON_OK;
+}
+
+int32_t cannon_broadphase_pairs(cannon_world* w, int32_t* p1, int32_t* p2, int32_t cap, int32_t* n_pairs) {
+  if (!w || !n_pairs) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  int32_t rc;
+  if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
+  if ((rc = st_prestep(w, w->dt > 0 ? w->dt : 1.0 / 60, 0, 0)) != CANNON_OK) return rc;
+  if ((rc = st_broadphase(w)) != CANNON_OK) return rc;
+  if ((rc = sync_counters(w)) != CANNON_OK) { *n_pairs = w->hCnt[CT_OVF_PAIRS]; return rc; }
+  const int np = w->hCnt[CT_NPAIRS];
+  *n_pairs = np;
+  w->prof.n_pairs = np;
+  if (np > cap) return fail(w->ctx, CANNON_E_CAPACITY, "pair buffer too small");
+  if (np > 0) {
+    if (p1) W_TRY(w, cudaMemcpy(p1, w->p1.p, np * sizeof(int), cudaMemcpyDeviceToHost));
+    if (p2) W_TRY(w, cudaMemcpy(p2, w->p2.p, np * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  return CANNON_OK;
+}
+
+static int32_t export_contacts(cannon_world* w, cannon_contacts_soa* out, int32_t* n_contacts) {
+  const int nc = w->hCnt[CT_NCONTACTS];
+  if (n_contacts) *n_contacts = nc;
+  if (!out) return CANNON_OK;
+  if (out->capacity < nc) return fail(w->ctx, CANNON_E_CAPACITY, "contact buffer too small");
+  if (nc == 0) return CANNON_OK;
+  std::vector<float4> tmp(nc);
+  auto get3 = [&](float* dst, const float4* src) -> cudaError_t {
+    cudaError_t e = cudaMemcpy(tmp.data(), src, nc * sizeof(float4), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (int k = 0; k < nc; k++) { dst[3 * k] = tmp[k].x; dst[3 * k + 1] = tmp[k].y; dst[3 * k + 2] = tmp[k].z; }
+    return cudaSuccess;
+  };
+  if (out->body_i) W_TRY(w, cudaMemcpy(out->body_i, w->cBi.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out->body_j) W_TRY(w, cudaMemcpy(out->body_j, w->cBj.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out->ri) W_TRY(w, get3(out->ri, w->cRi.p));
+  if (out->rj) W_TRY(w, get3(out->rj, w->cRj.p));
+  if (out->ni) W_TRY(w, get3(out->ni, w->cNi.p));
+  if (out->restitution) W_TRY(w, cudaMemcpy(out->restitution, w->cRest.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out->friction) W_TRY(w, cudaMemcpy(out->friction, w->cMu.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out->enabled) {
+    std::vector<int> en(nc);
+    W_TRY(w, cudaMemcpy(en.data(), w->cEnabled.p, nc * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < nc; k++) out->enabled[k] = (uint8_t)en[k];
+  }
+  if (out->multiplier) {
+    const double h = w->dt > 0 ? w->dt : 1.0 / 60;
+    k_multipliers<<<grid_for(w, nc, 256), 256, 0, w->ctx->stream>>>(contact_arrays(w), row_arrays(w), w->contactCap, 1 / h, w->cMult.p);
+    W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+    W_TRY(w, cudaMemcpy(out->multiplier, w->cMult.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return CANNON_OK;
+}
+
+int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const int32_t* p2, int32_t np, cannon_contacts_soa* out,
+                                    int32_t* n_contacts, int32_t* per_pair_count) {
+  if (!w || np < 0 || (np > 0 && (!p1 || !p2))) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  if (np > w->pairCap) return fail(w->ctx, CANNON_E_CAPACITY, "more pairs than cannon_world_desc.max_pairs");
+  for (int k = 0; k < np; k++)
+    if (p1[k] < 0 || p2[k] < 0 || p1[k] >= w->n || p2[k] >= w->n) return fail(w->ctx, CANNON_E_INVALID, "pair references unknown body");
+  int32_t rc;
+  if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
+  if (np > 0) {
+    W_TRY(w, cudaMemcpyAsync(w->p1.p, p1, np * sizeof(int), cudaMemcpyHostToDevice, s));
+    W_TRY(w, cudaMemcpyAsync(w->p2.p, p2, np * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  k_set_int<<<1, 32, 0, s>>>(w->cnt.p + CT_NPAIRS, np);
+  if (w->dt < 0) w->dt = 1.0 / 60;  // World.defaultDt
+  if ((rc = st_narrowphase(w, w->dt)) != CANNON_OK) return rc;
+  if (per_pair_count && np > 0) {
+    k_np_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(np_arrays(w), w->keep.p);
+    W_TRY(w, cudaGetLastError());
+  }
+  if ((rc = sync_counters(w)) != CANNON_OK) return rc;
+  w->prof.n_pairs = np;
+  w->prof.n_contacts = w->hCnt[CT_NCONTACTS];
+  if (per_pair_count && np > 0) W_TRY(w, cudaMemcpy(per_pair_count, w->keep.p, np * sizeof(int), cudaMemcpyDeviceToHost));
+  return export_contacts(w, out, n_contacts);
+}
+
+int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  int32_t rc;
+  // keep the pair/task/contact counts of the preceding narrowphase call, clear the solver's
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 2 * sizeof(int), s));
+  if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
+  k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p);
+  W_TRY(w, cudaGetLastError());
+  const int keepPairs = w->hCnt[CT_NPAIRS], keepContacts = w->hCnt[CT_NCONTACTS];
+  if ((rc = sync_counters(w)) != CANNON_OK) return rc;
+  (void)keepPairs; (void)keepContacts;
+  w->dt = dt;
+  w->prof.n_rows = w->hCnt[CT_NROWS];
+  w->prof.n_levels = w->hCnt[CT_NLEVELS];
+  w->prof.iterations_done = w->hCnt[CT_ITERS];
+  if (iterations_done) *iterations_done = w->hCnt[CT_ITERS];
+  return CANNON_OK;
+}
+
+int32_t cannon_integrate(cannon_world* w, double dt) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  int32_t rc;
+  if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
+  if ((rc = st_integrate(w, dt, 0)) != CANNON_OK) return rc;
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  w->stepnumber += 1;
+  w->time += dt;
+  return CANNON_OK;
+}
+
+int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
+  if (!w || nsteps < 0) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  int32_t rc;
+  if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
+  w->dt = dt;
+  for (int it = 0; it < nsteps; it++) {
+    const bool last = it == nsteps - 1;
+    if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
+    if (last) cudaEventRecord(w->ev[0], s);
+    if ((rc = st_prestep(w, dt, 1, 0)) != CANNON_OK) return rc;
+    if ((rc = st_broadphase(w)) != CANNON_OK) return rc;
+    if (last) cudaEventRecord(w->ev[1], s);
+    if ((rc = st_narrowphase(w, dt)) != CANNON_OK) return rc;
+    if (last) cudaEventRecord(w->ev[2], s);
+    if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
+    if (last) cudaEventRecord(w->ev[3], s);
+    if ((rc = st_integrate(w, dt, 1)) != CANNON_OK) return rc;
+    if (last) cudaEventRecord(w->ev[4], s);
+    w->stepnumber += 1;
+    w->time += dt;  // World.step: time += dt after internalStep (world_class.dart:396-399)
+    // per-step statistics are accumulated on the host from the counters of every step: one small async copy
+    W_TRY(w, cudaMemcpyAsync(w->hCnt, w->cnt.p, CT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    W_TRY(w, cudaStreamSynchronize(s));
+    if ((rc = check_overflow(w)) != CANNON_OK) return rc;
+    w->prof.steps += 1;
+    w->prof.contact_iters_total += (int64_t)w->hCnt[CT_NCONTACTS] * w->hCnt[CT_ITERS];
+  }
+  if (nsteps > 0) {
+    float ms;
+    cannon_profile& p = w->prof;
+    if (cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]) == cudaSuccess) p.broadphase = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]) == cudaSuccess) p.narrowphase = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]) == cudaSuccess) { p.solve = ms; p.make_contact_constraints = 0; }
+    if (cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]) == cudaSuccess) p.integrate = ms;
+    p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
+    p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
+  }
+  return CANNON_OK;
+}
+
+int32_t cannon_world_profile(cannon_world* w, cannon_profile* out) {
+  if (!w || !out) return CANNON_E_INVALID;
+  *out = w->prof;
+  return CANNON_OK;
+}
+
+int32_t cannon_world_get_contacts(cannon_world* w, cannon_contacts_soa* out, int32_t* n_contacts) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  return export_contacts(w, out, n_contacts);
+}
+
+int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int32_t* body_i, int32_t* body_j, double* B, double* invC,
+                              double* lambda, int32_t* level) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  const int n = w->hCnt[CT_NROWS];
+  if (n_rows) *n_rows = n;
+  if (cap < n) return fail(w->ctx, CANNON_E_CAPACITY, "row buffer too small");
+  if (n == 0) return CANNON_OK;
+  if (body_i) W_TRY(w, cudaMemcpy(body_i, w->rBi.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (body_j) W_TRY(w, cudaMemcpy(body_j, w->rBj.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (B) W_TRY(w, cudaMemcpy(B, w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (invC) W_TRY(w, cudaMemcpy(invC, w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lambda) W_TRY(w, cudaMemcpy(lambda, w->rLambda.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (level) {
+    if (w->desc.solver_kind == CANNON_SOLVER_REFERENCE_ORDER) W_TRY(w, cudaMemcpy(level, w->unitLevel.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    else memset(level, 0, n * sizeof(int));
+  }
+  return CANNON_OK;
+}
+
+int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* o) {
+  if (!w || !o) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  const int n = w->n;
+  if (o->n < n) { o->n = n; return fail(w->ctx, CANNON_E_CAPACITY, "cannon_bodies_soa.n too small"); }
+  o->n = n;
+  if (n == 0) return CANNON_OK;
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  std::vector<float4> t4(n);
+  auto get4 = [&](float* dst, const float4* src, int comps) -> cudaError_t {
+    cudaError_t e = cudaMemcpy(t4.data(), src, n * sizeof(float4), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (int k = 0; k < n; k++) {
+      dst[comps * k] = t4[k].x; dst[comps * k + 1] = t4[k].y; dst[comps * k + 2] = t4[k].z;
+      if (comps == 4) dst[4 * k + 3] = t4[k].w;
+    }
+    return cudaSuccess;
+  };
+  if (o->position) W_TRY(w, get4(o->position, w->pos.p, 3));
+  if (o->quaternion) W_TRY(w, get4(o->quaternion, w->quat.p, 4));
+  if (o->velocity) W_TRY(w, get4(o->velocity, w->vel.p, 3));
+  if (o->angular_velocity) W_TRY(w, get4(o->angular_velocity, w->angvel.p, 3));
+  if (o->force) W_TRY(w, get4(o->force, w->force.p, 3));
+  if (o->torque) W_TRY(w, get4(o->torque, w->torque.p, 3));
+  if (o->linear_factor) W_TRY(w, get4(o->linear_factor, w->linF.p, 3));
+  if (o->angular_factor) W_TRY(w, get4(o->angular_factor, w->angF.p, 3));
+  if (o->inv_inertia) W_TRY(w, get4(o->inv_inertia, w->invI.p, 3));
+  if (o->inv_inertia_world) {
+    std::vector<float4> r0(n), r1(n), r2(n);
+    W_TRY(w, cudaMemcpy(r0.data(), w->iiw0.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(r1.data(), w->iiw1.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(r2.data(), w->iiw2.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) {
+      float* d = o->inv_inertia_world + 9 * k;
+      d[0] = r0[k].x; d[1] = r0[k].y; d[2] = r0[k].z; d[3] = r1[k].x; d[4] = r1[k].y; d[5] = r1[k].z; d[6] = r2[k].x; d[7] = r2[k].y; d[8] = r2[k].z;
+    }
+  }
+  if (o->aabb) {
+    int32_t rc = st_prestep(w, w->dt > 0 ? w->dt : 1.0 / 60, 0, 1);
+    if (rc != CANNON_OK) return rc;
+    W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+    std::vector<float4> lo(n), hi(n);
+    W_TRY(w, cudaMemcpy(lo.data(), w->aabbLo.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hi.data(), w->aabbHi.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) {
+      float* d = o->aabb + 6 * k;
+      d[0] = lo[k].x; d[1] = lo[k].y; d[2] = lo[k].z; d[3] = hi[k].x; d[4] = hi[k].y; d[5] = hi[k].z;
+    }
+  }
+#define GETA(field, buf, T) if (o->field) W_TRY(w, cudaMemcpy(o->field, w->buf.p, n * sizeof(T), cudaMemcpyDeviceToHost))
+  GETA(mass, mass, double); GETA(type, type, int); GETA(sleep_state, sleep, int); GETA(time_last_sleepy, tLastSleepy, double);
+  GETA(sleep_speed_limit, sleepSpeed, double); GETA(sleep_time_limit, sleepTime, double); GETA(linear_damping, ldamp, double);
+  GETA(angular_damping, adamp, double); GETA(collision_filter_group, group, int); GETA(collision_filter_mask, mask, int);
+  GETA(material, material, int); GETA(shape, shape, int); GETA(world_id, world, int); GETA(inv_mass, invMass, double);
+  GETA(bounding_radius, brad, double);
+#undef GETA
+  if (o->allow_sleep || o->collision_response || o->is_trigger || o->fixed_rotation) {
+    std::vector<int> fl(n);
+    W_TRY(w, cudaMemcpy(fl.data(), w->flags.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) {
+      if (o->allow_sleep) o->allow_sleep[k] = (fl[k] & BF_ALLOW_SLEEP) ? 1 : 0;
+      if (o->collision_response) o->collision_response[k] = (fl[k] & BF_COLLISION_RESPONSE) ? 1 : 0;
+      if (o->is_trigger) o->is_trigger[k] = (fl[k] & BF_IS_TRIGGER) ? 1 : 0;
+      if (o->fixed_rotation) o->fixed_rotation[k] = (fl[k] & BF_FIXED_ROTATION) ? 1 : 0;
+    }
+  }
+  return CANNON_OK;
+}
+
+__global__ void __launch_bounds__(256) k_refresh_inertia(BodyArrays B, int first, int count) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const int i = first + k;
+    const f3 I = ld3(B.invI[i]);
+    if (I.x == I.y && I.y == I.z) continue;  // updateInertiaWorld(), rigid_body.dart:450-466
+    float4 r0, r1, r2;
+    inertia_world(ldq(B.quat[i]), I, r0, r1, r2);
+    B.iiw0[i] = r0; B.iiw1[i] = r1; B.iiw2[i] = r2;
+  }
+}
+
+int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count, const float* position, const float* quaternion,
+                                   const float* velocity, const float* angular_velocity, const float* force, const float* torque) {
+  if (!w || first < 0 || count < 0 || first + count > w->n) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  if (count == 0) return CANNON_OK;
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  std::vector<float4> t4(count);
+  auto put = [&](const float* src, float4* dst, int comps) -> cudaError_t {
+    for (int k = 0; k < count; k++) t4[k] = make_float4(src[comps * k], src[comps * k + 1], src[comps * k + 2], comps == 4 ? src[4 * k + 3] : 0.f);
+    return cudaMemcpy(dst + first, t4.data(), count * sizeof(float4), cudaMemcpyHostToDevice);
+  };
+  if (position) W_TRY(w, put(position, w->pos.p, 3));
+  if (quaternion) W_TRY(w, put(quaternion, w->quat.p, 4));
+  if (velocity) W_TRY(w, put(velocity, w->vel.p, 3));
+  if (angular_velocity) W_TRY(w, put(angular_velocity, w->angvel.p, 3));
+  if (force) W_TRY(w, put(force, w->force.p, 3));
+  if (torque) W_TRY(w, put(torque, w->torque.p, 3));
+  if (quaternion) {
+    k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count);
+    W_TRY(w, cudaStreamSynchronize(s));
+  }
+  return CANNON_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,854 @@
+// k_narrowphase.cuh — contact generation (K3), lib/world/narrow_phase.dart:634-2178 for the in-scope shapes.
+//
+// Pipeline (all counts stay on the device):
+//   k_np_tasks (pass 0/1)  per pair: common prologue of getContacts (:670-716) -> number of resolver tasks
+//                          (1 for ordinary pairs, 2 per heightfield cell of the index window) -> scan -> task list
+//                          in the reference's loop order, bucketed by resolver type
+//   k_np_<resolver>        one kernel per resolver type over its bucket; contacts go to a raw pool
+//   scan(task counts)      canonical contact offsets (pair order, then the resolver's emission order)
+//   k_np_finalize          raw pool -> final contact SoA + material-derived parameters (:492-586)
+// so the final contact order equals the reference's regardless of how threads were scheduled.
+#pragma once
+#include "world.cuh"
+
+enum { NP_SS = 0, NP_SP = 1, NP_SB = 2, NP_SH = 3, NP_PH = 4, NP_HH = 5, NP_SPIL = 6, NP_HPIL = 7, NP_NTYPES = 8 };
+#define NP_MAXPOLY 40
+
+struct NpArrays {
+  const int* p1;
+  const int* p2;
+  const int* nPairs;       // device count
+  int* pairTasks;          // tasks per pair, then exclusive scan (in place into pairTaskOff)
+  int* pairTaskOff;
+  int* nTasks;
+  int* taskPair;
+  int* taskInfo;           // type | upper<<4
+  int2* taskCell;
+  int* bucket;             // [taskCap], one segment per resolver type
+  int* bucketCount;        // [NP_NTYPES] tasks per type (pass 0)
+  int* bucketStart;        // [NP_NTYPES] exclusive scan of bucketCount
+  int* bucketCursor;       // [NP_NTYPES] fill cursors (pass 1)
+  int* taskCnt;            // contacts per task
+  int* taskRaw;            // start in the raw pool
+  int* taskOff;            // exclusive scan of taskCnt
+  int* rawCount;
+  float4 *rawRi, *rawRj, *rawNi;
+  int taskCap, contactCap;
+  int* overflowTasks;
+  int* overflowContacts;
+};
+
+struct ContactArrays {
+  int* nContacts;
+  int *bi, *bj;
+  float4 *ri, *rj, *ni;
+  double *rest, *mu, *slip;            // restitution, friction coefficient, slip force mu*|g|*m_red
+  double *ca, *cb, *ceps;              // contact SPOOK
+  double *fb, *feps;                   // friction SPOOK (a is unused: g == 0)
+  int* enabled;
+  int* row;                            // solver row of the contact equation, -1 if filtered
+};
+
+struct HullView {
+  const float4* v; int nV;
+  const float4* n; const double* pc; int nF;
+  const int* fvOff; const int* fvIdx;   // fvOff[f]..fvOff[f+1]
+  const int* fcOff; const int* fcIdx;
+  const float4* e; int nE;
+  int hasAxes;
+  double bsr;
+};
+
+__device__ __forceinline__ HullView hull_view(const ShapeTables& T, int hull) {
+  const HullDev h = T.hulls[hull];
+  HullView H;
+  H.v = T.verts + h.vOff; H.nV = h.nV;
+  H.n = T.fnormals + h.fOff; H.pc = T.fplanec + h.fOff; H.nF = h.nF;
+  H.fvOff = T.fvOff + h.fOff + hull; H.fvIdx = T.fvIdx;
+  H.fcOff = T.fcOff + h.fOff + hull; H.fcIdx = T.fcIdx;
+  H.e = T.edges + h.eOff; H.nE = h.nE;
+  H.hasAxes = h.hasAxes;
+  H.bsr = h.bsr;
+  return H;
+}
+
+__device__ __forceinline__ bool is_hull_type(int t) { return t == CANNON_SHAPE_BOX || t == CANNON_SHAPE_CONVEX || t == CANNON_SHAPE_CYLINDER; }
+
+// heightfield index window: sphereHeightfield :1318-1362 / heightfieldConvex :2070-2113 (+ getRectMinMax, heightfield.dart:146-162)
+__device__ inline bool hf_window(const ShapeTables& T, const HfDev& hf, const f3& local, double radius, int& iMinX, int& iMaxX, int& iMinY,
+                                 int& iMaxY) {
+  const double wd = (double)hf.esize;
+  iMinX = (int)floor((W(local.x) - radius) / wd) - 1;
+  iMaxX = (int)ceil((W(local.x) + radius) / wd) + 1;
+  iMinY = (int)floor((W(local.y) - radius) / wd) - 1;
+  iMaxY = (int)ceil((W(local.y) + radius) / wd) + 1;
+  if (iMaxX < 0 || iMaxY < 0 || iMinX > hf.nx || iMinY > hf.ny) return false;
+  if (iMinX < 0) iMinX = 0;
+  if (iMaxX < 0) iMaxX = 0;
+  if (iMinY < 0) iMinY = 0;
+  if (iMaxY < 0) iMaxY = 0;
+  if (iMinX >= hf.nx) iMinX = hf.nx - 1;
+  if (iMaxX >= hf.nx) iMaxX = hf.nx - 1;
+  if (iMaxY >= hf.ny) iMaxY = hf.ny - 1;
+  if (iMinY >= hf.ny) iMinY = hf.ny - 1;
+  double mx = hf.minV;
+  for (int i = iMinX; i <= iMaxX; i++)
+    for (int j = iMinY; j <= iMaxY; j++) {
+      const double h = T.hfdata[hf.dataOff + (size_t)i * hf.ny + j];
+      if (h > mx) mx = h;
+    }
+  if (W(local.z) - radius > mx || W(local.z) + radius < hf.minV) return false;
+  return true;
+}
+
+// which body plays "i" for the resolver: lower ShapeType index first, equal types swapped (narrow_phase.dart:706-710)
+__device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& first, int& second) {
+  if (ta < tb) { first = a; second = b; } else { first = b; second = a; }
+}
+
+__global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass) {
+  const int np = *A.nPairs;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const int a = A.p1[k], b = A.p2[k];
+    int nt = 0, code = -1;
+    int iMinX = 0, iMaxX = 0, iMinY = 0, iMaxY = 0;
+    const int sa = B.shape[a], sb = B.shape[b];
+    if (sa >= 0 && sb >= 0) {
+      const ShapeDev si = T.shapes[sa], sj = T.shapes[sb];
+      const int tya = B.type[a], tyb = B.type[b];
+      const bool justTest = (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_STATIC) || (tya == CANNON_BODY_STATIC && tyb == CANNON_BODY_KINEMATIC) ||
+                            (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_KINEMATIC);
+      const bool maskOk = (si.mask & sj.group) != 0 && (sj.mask & si.group) != 0;
+      const f3 xi = ld3(B.pos[a]), xj = ld3(B.pos[b]);
+      if (maskOk && !justTest && !(vdist(xi, xj) > si.bsr + sj.bsr)) {
+        int lo = si.type, hi = sj.type;
+        int first = a, second = b;
+        if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
+        if (lo == CANNON_SHAPE_SPHERE) {
+          if (hi == CANNON_SHAPE_SPHERE) code = NP_SS;
+          else if (hi == CANNON_SHAPE_PLANE) code = NP_SP;
+          else if (hi == CANNON_SHAPE_BOX) code = NP_SB;
+          else if (hi == CANNON_SHAPE_CONVEX || hi == CANNON_SHAPE_CYLINDER) code = NP_SH;
+          else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_SPIL;
+        } else if (lo == CANNON_SHAPE_PLANE) {
+          if (is_hull_type(hi)) code = NP_PH;
+        } else if (is_hull_type(lo)) {
+          if (is_hull_type(hi)) code = NP_HH;
+          else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_HPIL;
+        }
+        if (code >= 0) nt = 1;
+        if (code == NP_SPIL || code == NP_HPIL) {
+          const ShapeDev s1 = T.shapes[B.shape[first]], s2 = T.shapes[B.shape[second]];
+          const HfDev hf = T.hfs[s2.hf];
+          const f3 local = to_local_point(ld3(B.pos[second]), ldq(B.quat[second]), ld3(B.pos[first]));
+          const double radius = code == NP_SPIL ? s1.radius : T.hulls[s1.hull].bsr;
+          nt = 0;
+          if (hf_window(T, hf, local, radius, iMinX, iMaxX, iMinY, iMaxY)) {
+            const int wx = iMaxX - iMinX, wy = iMaxY - iMinY;
+            if (wx > 0 && wy > 0) nt = wx * wy * 2;
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      A.pairTasks[k] = nt;
+      if (nt) atomicAdd(&A.bucketCount[code], nt);
+      continue;
+    }
+    if (nt == 0) continue;
+    const int off = A.pairTaskOff[k];
+    if (off + nt > A.taskCap) { atomicMax(A.overflowTasks, off + nt); continue; }
+    if (code == NP_SPIL || code == NP_HPIL) {
+      const int wy = iMaxY - iMinY;
+      for (int t = 0; t < nt; t++) {
+        const int cellIdx = t >> 1;
+        A.taskPair[off + t] = k;
+        A.taskInfo[off + t] = code | ((t & 1) << 4);
+        A.taskCell[off + t] = make_int2(iMinX + cellIdx / wy, iMinY + cellIdx % wy);
+      }
+      const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], nt);
+      for (int t = 0; t < nt; t++) A.bucket[slot + t] = off + t;
+    } else {
+      A.taskPair[off] = k;
+      A.taskInfo[off] = code;
+      const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], 1);
+      A.bucket[slot] = off;
+    }
+  }
+}
+
+// ---- raw contact emission ----------------------------------------------------------------------------
+struct RawOut {
+  NpArrays A;
+  int task;
+  int start;
+  int n;
+};
+__device__ __forceinline__ bool raw_alloc(RawOut& o, int m) {
+  o.n = 0;
+  o.start = 0;
+  if (m > 0) {
+    o.start = atomicAdd(o.A.rawCount, m);
+    if (o.start + m > o.A.contactCap) { atomicMax(o.A.overflowContacts, o.start + m); m = 0; o.start = 0; }
+  }
+  o.A.taskCnt[o.task] = m;
+  o.A.taskRaw[o.task] = o.start;
+  return m > 0;
+}
+// "Make relative to bodies": r.add2(x, r); r.sub2(body.position, r)
+__device__ __forceinline__ f3 rel_to_body(const f3& r, const f3& x, const f3& bodyPos) { return vsub(vadd(r, x), bodyPos); }
+__device__ __forceinline__ void raw_put(RawOut& o, const f3& ri, const f3& rj, const f3& ni) {
+  const int k = o.start + o.n++;
+  o.A.rawRi[k] = st3(ri);
+  o.A.rawRj[k] = st3(rj);
+  o.A.rawNi[k] = st3(ni);
+}
+
+struct TaskCtx {
+  int task, pair, first, second, info;
+  f3 xi, xj;   // positions of first / second (== shape world positions: single shape at the body origin)
+  q4 qi, qj;
+  ShapeDev si, sj;
+};
+__device__ __forceinline__ void load_task(const BodyArrays& B, const ShapeTables& T, const NpArrays& A, int task, TaskCtx& c) {
+  c.task = task;
+  c.pair = A.taskPair[task];
+  c.info = A.taskInfo[task];
+  const int a = A.p1[c.pair], b = A.p2[c.pair];
+  const ShapeDev sa = T.shapes[B.shape[a]], sb = T.shapes[B.shape[b]];
+  if (sa.type < sb.type) { c.first = a; c.second = b; c.si = sa; c.sj = sb; }
+  else { c.first = b; c.second = a; c.si = sb; c.sj = sa; }
+  c.xi = ld3(B.pos[c.first]); c.xj = ld3(B.pos[c.second]);
+  c.qi = ldq(B.quat[c.first]); c.qj = ldq(B.quat[c.second]);
+}
+
+#define NP_BUCKET_LOOP(TYPE)                                                     \
+  const int nb__ = (*A.nTasks <= A.taskCap) ? A.bucketCount[TYPE] : 0;          \
+  for (int u__ = blockIdx.x * blockDim.x + threadIdx.x; u__ < nb__; u__ += gridDim.x * blockDim.x)
+#define NP_TASK(TYPE) A.bucket[A.bucketStart[TYPE] + u__]
+
+// sphereSphere, narrow_phase.dart:723-765: always one contact (the prologue's bounding test is the only test)
+__global__ void __launch_bounds__(256) k_np_sphere_sphere(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_SS) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_SS), c);
+    RawOut o; o.A = A; o.task = c.task;
+    if (!raw_alloc(o, 1)) continue;
+    f3 ni = vsub(c.xj, c.xi);
+    vnormalize(ni);
+    f3 ri = vscale(c.si.radius, ni);
+    f3 rj = vscale(-c.sj.radius, ni);
+    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+  }
+}
+
+// spherePlane, narrow_phase.dart:766-815
+__global__ void __launch_bounds__(256) k_np_sphere_plane(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_SP) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_SP), c);
+    RawOut o; o.A = A; o.task = c.task;
+    f3 z; z.x = 0.f; z.y = 0.f; z.z = 1.f;
+    f3 ni = vneg(qrot(c.qj, z));
+    vnormalize(ni);
+    const double R = c.si.radius;
+    f3 ri = vscale(R, ni);
+    const f3 p2s = vsub(c.xi, c.xj);
+    const f3 ortho = vscale(vdot(ni, p2s), ni);
+    f3 rj = vsub(p2s, ortho);
+    const bool hit = -vdot(p2s, ni) <= R;
+    if (!raw_alloc(o, hit ? 1 : 0)) continue;
+    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+  }
+}
+
+// sphereBox, narrow_phase.dart:816-1038
+__global__ void __launch_bounds__(128) k_np_sphere_box(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_SB) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_SB), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const f3 xi = c.xi, xj = c.xj;
+    f3 sides[6];  // Box.getSideNormals, box.dart:99-115
+    {
+      const float hx = c.sj.hx, hy = c.sj.hy, hz = c.sj.hz;
+      f3 t;
+      t.x = hx; t.y = 0.f; t.z = 0.f; sides[0] = qrot(c.qj, t);
+      t.x = 0.f; t.y = hy; t.z = 0.f; sides[1] = qrot(c.qj, t);
+      t.x = 0.f; t.y = 0.f; t.z = hz; sides[2] = qrot(c.qj, t);
+      t.x = -hx; t.y = 0.f; t.z = 0.f; sides[3] = qrot(c.qj, t);
+      t.x = 0.f; t.y = -hy; t.z = 0.f; sides[4] = qrot(c.qj, t);
+      t.x = 0.f; t.y = 0.f; t.z = -hz; sides[5] = qrot(c.qj, t);
+    }
+    const f3 boxToSphere = vsub(xi, xj);
+    const double R = c.si.radius;
+    bool found = false;
+    f3 outRi, outRj, outNi;
+    {  // side (plane) intersections: keep the strictly smallest |dot - h - R|
+      f3 sideNs, sideNs1, sideNs2;
+      double sideH = 0, sideDot1 = 0, sideDot2 = 0, sideDistance = 0;
+      bool have = false;
+      for (int idx = 0; idx != 6; idx++) {
+        f3 ns = sides[idx];
+        const double h = vlen(ns);
+        vnormalize(ns);
+        const double dt = vdot(boxToSphere, ns);
+        if (dt < h + R && dt > 0) {
+          f3 ns1 = sides[(idx + 1) % 3], ns2 = sides[(idx + 2) % 3];
+          const double h1 = vlen(ns1), h2 = vlen(ns2);
+          vnormalize(ns1);
+          vnormalize(ns2);
+          const double dot1 = vdot(boxToSphere, ns1), dot2 = vdot(boxToSphere, ns2);
+          if (dot1 < h1 && dot1 > -h1 && dot2 < h2 && dot2 > -h2) {
+            const double dist = fabs(dt - h - R);
+            if (!have || dist < sideDistance) {
+              have = true; sideDistance = dist; sideDot1 = dot1; sideDot2 = dot2; sideH = h;
+              sideNs = ns; sideNs1 = ns1; sideNs2 = ns2;
+            }
+          }
+        }
+      }
+      if (have) {
+        found = true;
+        outRi = vscale(-R, sideNs);
+        outNi = vneg(sideNs);
+        sideNs = vscale(sideH, sideNs);
+        sideNs1 = vscale(sideDot1, sideNs1);
+        sideNs = vadd(sideNs, sideNs1);
+        sideNs2 = vscale(sideDot2, sideNs2);
+        outRj = vadd(sideNs, sideNs2);
+      }
+    }
+    // corners
+    for (int j = 0; j != 2 && !found; j++)
+      for (int k = 0; k != 2 && !found; k++)
+        for (int l = 0; l != 2 && !found; l++) {
+          f3 rj; rj.x = rj.y = rj.z = 0.f;
+          rj = j ? vadd(sides[0], rj) : vsub(rj, sides[0]);
+          rj = k ? vadd(sides[1], rj) : vsub(rj, sides[1]);
+          rj = l ? vadd(sides[2], rj) : vsub(rj, sides[2]);
+          f3 s2c = vsub(vadd(xj, rj), xi);
+          if (vlen2(s2c) < R * R) {
+            found = true;
+            outRi = s2c;
+            vnormalize(outRi);
+            outNi = outRi;
+            outRi = vscale(R, outRi);
+            outRj = rj;
+          }
+        }
+    // edges
+    for (int j = 0; j != 6 && !found; j++)
+      for (int k = 0; k != 6 && !found; k++) {
+        if (j % 3 == k % 3) continue;
+        f3 edgeTangent = vcross(sides[k], sides[j]);
+        vnormalize(edgeTangent);
+        const f3 edgeCenter = vadd(sides[j], sides[k]);
+        f3 r = vsub(vsub(xi, edgeCenter), xj);
+        const double orthonorm = vdot(r, edgeTangent);
+        const f3 orthogonal = vscale(orthonorm, edgeTangent);
+        int l = 0;
+        while (l == j % 3 || l == k % 3) l++;
+        f3 dist = vsub(vsub(vsub(xi, orthogonal), edgeCenter), xj);
+        const double tdist = fabs(orthonorm);
+        const double ndist = vlen(dist);
+        if (tdist < vlen(sides[l]) && ndist < R) {
+          found = true;
+          outRj = vadd(edgeCenter, orthogonal);
+          outNi = vneg(dist);
+          vnormalize(outNi);
+          outRi = vsub(vadd(outRj, xj), xi);
+          vnormalize(outRi);
+          outRi = vscale(R, outRi);
+        }
+      }
+    if (!raw_alloc(o, found ? 1 : 0)) continue;
+    raw_put(o, rel_to_body(outRi, xi, xi), rel_to_body(outRj, xj, xj), outNi);
+  }
+}
+
+// _pointInPolygon, narrow_phase.dart:2584-2617 over the world-space vertices of face f
+__device__ inline bool point_in_face(const HullView& H, int f, const q4& q, const f3& x, const f3& normal, const f3& p) {
+  int positive = -1;
+  const int o = H.fvOff[f], N = H.fvOff[f + 1] - o;
+  for (int i = 0; i != N; i++) {
+    const f3 v = vadd(x, qrot(q, ld3(H.v[H.fvIdx[o + i]])));
+    const f3 vn = vadd(x, qrot(q, ld3(H.v[H.fvIdx[o + (i + 1) % N]])));
+    const f3 edge = vsub(vn, v);
+    const f3 exn = vcross(edge, normal);
+    const f3 v2p = vsub(p, v);
+    const double r = vdot(exn, v2p);
+    if (positive == -1 || (r > 0 && positive == 1) || (r <= 0 && positive == 0)) {
+      if (positive == -1) positive = r > 0 ? 1 : 0;
+      continue;
+    }
+    return false;
+  }
+  return true;
+}
+
+// sphereConvex, narrow_phase.dart:1039-1257: first hit wins (vertex, then per face: inside polygon, else its edges)
+__device__ inline bool sphere_convex(const HullView& H, double R, const f3& xi, const f3& xj, const q4& qj, f3& ri, f3& rj, f3& ni) {
+  for (int i = 0; i != H.nV; i++) {
+    const f3 worldCorner = vadd(xj, qrot(qj, ld3(H.v[i])));
+    const f3 s2c = vsub(worldCorner, xi);
+    if (vlen2(s2c) < R * R) {
+      ri = s2c;
+      vnormalize(ri);
+      ni = ri;
+      ri = vscale(R, ri);
+      rj = vsub(worldCorner, xj);
+      return true;
+    }
+  }
+  for (int f = 0; f != H.nF; f++) {
+    const f3 worldNormal = qrot(qj, ld3(H.n[f]));
+    const int o = H.fvOff[f], L = H.fvOff[f + 1] - o;
+    const f3 worldPoint = vadd(qrot(qj, ld3(H.v[H.fvIdx[o]])), xj);
+    const f3 closest = vadd(xi, vscale(-R, worldNormal));
+    const f3 penVec = vsub(closest, worldPoint);
+    const double penetration = vdot(penVec, worldNormal);
+    const f3 wp2s = vsub(xi, worldPoint);
+    if (penetration < 0 && vdot(wp2s, worldNormal) > 0) {
+      if (point_in_face(H, f, qj, xj, worldNormal, xi)) {
+        ri = vscale(-R, worldNormal);
+        ni = vneg(worldNormal);
+        const f3 penVec2 = vscale(-penetration, worldNormal);
+        const f3 penSpherePoint = vscale(-R, worldNormal);
+        rj = vsub(xi, xj);
+        rj = vadd(rj, penSpherePoint);
+        rj = vadd(rj, penVec2);
+        return true;
+      }
+      for (int j = 0; j != L; j++) {
+        const f3 v1 = vadd(xj, qrot(qj, ld3(H.v[H.fvIdx[o + (j + 1) % L]])));
+        const f3 v2 = vadd(xj, qrot(qj, ld3(H.v[H.fvIdx[o + (j + 2) % L]])));
+        const f3 edge = vsub(v2, v1);
+        const f3 edgeUnit = vunit(edge);
+        const f3 v1ToXi = vsub(xi, v1);
+        const double dt = vdot(v1ToXi, edgeUnit);
+        f3 p = vadd(vscale(dt, edgeUnit), v1);
+        const f3 xiToP = vsub(p, xi);
+        if (dt > 0 && dt * dt < vlen2(edge) && vlen2(xiToP) < R * R) {
+          rj = vsub(p, xj);
+          ni = vsub(p, xi);
+          vnormalize(ni);
+          ri = vscale(R, ni);
+          return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(128) k_np_sphere_hull(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_SH) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_SH), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const HullView H = hull_view(T, c.sj.hull);
+    f3 ri, rj, ni;
+    const bool hit = sphere_convex(H, c.si.radius, c.xi, c.xj, c.qj, ri, rj, ni);
+    if (!raw_alloc(o, hit ? 1 : 0)) continue;
+    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+  }
+}
+
+// planeConvex / planeBox, narrow_phase.dart:1847-1915: every hull vertex on or behind the plane
+__global__ void __launch_bounds__(128) k_np_plane_hull(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_PH) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_PH), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const HullView H = hull_view(T, c.sj.hull);
+    f3 z; z.x = 0.f; z.y = 0.f; z.z = 1.f;
+    const f3 worldNormal = qrot(c.qi, z);
+    int m = 0;
+    for (int i = 0; i != H.nV; i++) {
+      const f3 wv = vadd(c.xj, qrot(c.qj, ld3(H.v[i])));
+      if (vdot(worldNormal, vsub(wv, c.xi)) <= 0.0) m++;
+    }
+    if (!raw_alloc(o, m)) continue;
+    for (int i = 0; i != H.nV; i++) {
+      const f3 wv = vadd(c.xj, qrot(c.qj, ld3(H.v[i])));
+      const f3 relpos = vsub(wv, c.xi);
+      const double dt = vdot(worldNormal, relpos);
+      if (dt <= 0.0) {
+        f3 projected = vscale(vdot(worldNormal, relpos), worldNormal);
+        projected = vsub(wv, projected);
+        const f3 ri = vsub(projected, c.xi);
+        const f3 rj = vsub(wv, c.xj);
+        raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), worldNormal);
+      }
+    }
+  }
+}
+
+// ConvexPolyhedron.project, convex_polyhedron.dart:843-883
+__device__ __forceinline__ void hull_project(const HullView& H, const f3& axis, const f3& pos, const q4& quat, double& mx, double& mn) {
+  const f3 localAxis = qrot(qnegw(quat), axis);
+  f3 zero; zero.x = zero.y = zero.z = 0.f;
+  const f3 localOrigin = to_local_point(pos, quat, zero);
+  const double add = vdot(localOrigin, localAxis);
+  mn = mx = vdot(ld3(H.v[0]), localAxis);
+  for (int i = 1; i < H.nV; i++) {
+    const double val = vdot(ld3(H.v[i]), localAxis);
+    if (val > mx) mx = val;
+    if (val < mn) mn = val;
+  }
+  mn -= add;
+  mx -= add;
+  if (mn > mx) { const double t = mn; mn = mx; mx = t; }
+}
+
+// testSepAxis, convex_polyhedron.dart:360-384
+__device__ __forceinline__ bool test_sep_axis(const HullView& HA, const HullView& HB, const f3& axis, const f3& posA, const q4& quatA,
+                                              const f3& posB, const q4& quatB, double& depth) {
+  double maxA, minA, maxB, minB;
+  hull_project(HA, axis, posA, quatA, maxA, minA);
+  hull_project(HB, axis, posB, quatB, maxB, minB);
+  if (maxA < minB || maxB < minA) return false;
+  const double d0 = maxA - minB, d1 = maxB - minA;
+  depth = d0 < d1 ? d0 : d1;
+  return true;
+}
+
+// findSeparatingAxis, convex_polyhedron.dart:232-356 (face normals only for hulls with `uniqueAxes`, §5.9-9)
+__device__ inline bool find_sep_axis(const HullView& HA, const HullView& HB, const f3& posA, const q4& quatA, const f3& posB, const q4& quatB,
+                                     bool onlyFace0OfA, f3& target) {
+  double dmin = INFINITY;
+  target.x = target.y = target.z = 0.f;
+  if (HA.hasAxes) {
+    const int nfa = onlyFace0OfA ? 1 : HA.nF;
+    for (int i = 0; i < nfa; i++) {
+      const f3 n = qrot(quatA, ld3(HA.n[i]));
+      double d;
+      if (!test_sep_axis(HA, HB, n, posA, quatA, posB, quatB, d)) return false;
+      if (d < dmin) { dmin = d; target = n; }
+    }
+  }
+  if (HB.hasAxes) {
+    for (int i = 0; i < HB.nF; i++) {
+      const f3 n = qrot(quatB, ld3(HB.n[i]));
+      double d;
+      if (!test_sep_axis(HA, HB, n, posA, quatA, posB, quatB, d)) return false;
+      if (d < dmin) { dmin = d; target = n; }
+    }
+  }
+  for (int e0 = 0; e0 != HA.nE; e0++) {
+    const f3 we0 = qrot(quatA, ld3(HA.e[e0]));
+    for (int e1 = 0; e1 != HB.nE; e1++) {
+      const f3 we1 = qrot(quatB, ld3(HB.e[e1]));
+      f3 c = vcross(we0, we1);
+      if (!valmost_zero(c)) {
+        vnormalize(c);
+        double d;
+        if (!test_sep_axis(HA, HB, c, posA, quatA, posB, quatB, d)) return false;
+        if (d < dmin) { dmin = d; target = c; }
+      }
+    }
+  }
+  const f3 deltaC = vsub(posB, posA);
+  if (vdot(deltaC, target) > 0.0) target = vneg(target);
+  return true;
+}
+
+// clipAgainstHull + clipFaceAgainstHull + clipFaceAgainstPlane, convex_polyhedron.dart:189-227,417-587.
+// Returns the number of kept points; pts/depth hold them; nrm = world normal of A's reference face.
+__device__ inline int clip_hulls(const HullView& HA, const f3& posA, const q4& quatA, const HullView& HB, const f3& posB, const q4& quatB,
+                                 const f3& sep, f3* pa, f3* pb, double* depthOut, f3& nrm, bool& overflow) {
+  int closestB = -1;
+  double dmax = -INFINITY;
+  for (int f = 0; f < HB.nF; f++) {
+    const double d = vdot(qrot(quatB, ld3(HB.n[f])), sep);
+    if (d > dmax) { dmax = d; closestB = f; }
+  }
+  if (closestB < 0) return 0;
+  int nIn = 0;
+  {
+    const int o = HB.fvOff[closestB], L = HB.fvOff[closestB + 1] - o;
+    for (int i = 0; i < L && nIn < NP_MAXPOLY; i++) pa[nIn++] = vadd(posB, qrot(quatB, ld3(HB.v[HB.fvIdx[o + i]])));
+    if (L > NP_MAXPOLY) overflow = true;
+  }
+  int closestA = -1;
+  double dmin = INFINITY;
+  for (int f = 0; f < HA.nF; f++) {
+    const double d = vdot(qrot(quatA, ld3(HA.n[f])), sep);
+    if (d < dmin) { dmin = d; closestA = f; }
+  }
+  if (closestA < 0) return 0;
+  const int numVerticesA = HA.fvOff[closestA + 1] - HA.fvOff[closestA];
+  const int co = HA.fcOff[closestA], nConn = HA.fcOff[closestA + 1] - co;
+  f3* in = pa;
+  f3* out = pb;
+  for (int i = 0; i < numVerticesA; i++) {
+    const int otherFace = (nConn > i) ? HA.fcIdx[co + i] : 0;
+    const f3 pn = qrot(quatA, ld3(HA.n[otherFace]));
+    const double pc = HA.pc[otherFace] - vdot(pn, posA);
+    int nOut = 0;
+    if (nIn >= 2) {  // clipFaceAgainstPlane
+      f3 firstVertex = in[nIn - 1];
+      double nDotFirst = vdot(pn, firstVertex) + pc;
+      for (int vi = 0; vi < nIn; vi++) {
+        const f3 lastVertex = in[vi];
+        const double nDotLast = vdot(pn, lastVertex) + pc;
+        if (nDotFirst < 0) {
+          if (nOut < NP_MAXPOLY) out[nOut++] = (nDotLast < 0) ? lastVertex : vlerp(firstVertex, lastVertex, nDotFirst / (nDotFirst - nDotLast));
+          else overflow = true;
+        } else if (nDotLast < 0) {
+          if (nOut + 1 < NP_MAXPOLY) {
+            out[nOut++] = vlerp(firstVertex, lastVertex, nDotFirst / (nDotFirst - nDotLast));
+            out[nOut++] = lastVertex;
+          } else overflow = true;
+        }
+        firstVertex = lastVertex;
+        nDotFirst = nDotLast;
+      }
+    }
+    f3* t = in; in = out; out = t;
+    nIn = nOut;
+  }
+  nrm = qrot(quatA, ld3(HA.n[closestA]));
+  const double planeEq = HA.pc[closestA] - vdot(nrm, posA);
+  int kept = 0;
+  for (int i = 0; i < nIn; i++) {
+    double depth = vdot(nrm, in[i]) + planeEq;
+    if (depth <= -100.0) depth = -100.0;
+    if (depth <= 100.0 && depth <= 1e-6) {
+      const f3 p = in[i];
+      out[kept] = p;  // `out` is free now; kept <= i
+      depthOut[kept] = depth;
+      kept++;
+    }
+  }
+  // results live in `out`; make the caller's pa hold them
+  if (out != pa)
+    for (int i = 0; i < kept; i++) pa[i] = out[i];
+  return kept;
+}
+
+// convexConvex, narrow_phase.dart:1981-2043 (A = first, B = second)
+__device__ inline void convex_convex_emit(RawOut& o, const HullView& HA, const HullView& HB, const f3& xi, const f3& xj, const q4& qi,
+                                          const q4& qj, const f3& bodyPosI, const f3& bodyPosJ, bool onlyFace0OfA, int* clipOverflow) {
+  f3 sep;
+  int kept = 0;
+  f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY];
+  double depth[NP_MAXPOLY];
+  f3 nrm;
+  nrm.x = nrm.y = nrm.z = 0.f;
+  if (!(vdist(xi, xj) > HA.bsr + HB.bsr) && find_sep_axis(HA, HB, xi, qi, xj, qj, onlyFace0OfA, sep)) {
+    bool ovf = false;
+    kept = clip_hulls(HA, xi, qi, HB, xj, qj, sep, pa, pb, depth, nrm, ovf);
+    if (ovf) atomicExch(clipOverflow, 1);
+  }
+  if (!raw_alloc(o, kept)) return;
+  const f3 ni = vneg(sep);
+  for (int j = 0; j < kept; j++) {
+    f3 q = vscale(depth[j], vneg(nrm));
+    f3 ri = vadd(pa[j], q);
+    f3 rj = pa[j];
+    ri = vsub(ri, xi);
+    rj = vsub(rj, xj);
+    ri = vsub(vadd(ri, xi), bodyPosI);
+    rj = vsub(vadd(rj, xj), bodyPosJ);
+    raw_put(o, ri, rj, ni);
+  }
+}
+
+__global__ void __launch_bounds__(64) k_np_hull_hull(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+  NP_BUCKET_LOOP(NP_HH) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_HH), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const HullView HA = hull_view(T, c.si.hull), HB = hull_view(T, c.sj.hull);
+    convex_convex_emit(o, HA, HB, c.xi, c.xj, c.qi, c.qj, c.xi, c.xj, false, clipOverflow);
+  }
+}
+
+// Heightfield.getConvexTrianglePillar, heightfield.dart:330-487, into thread-local storage
+struct PillarStore {
+  float4 v[6];
+  float4 n[5];
+  double pc[5];
+  float4 e[18];
+  int nE;
+  double bsr;
+};
+__constant__ int c_pillarFvOff[6] = {0, 3, 6, 10, 14, 18};
+__constant__ int c_pillarLower[18] = {0, 1, 2, 5, 4, 3, 0, 2, 5, 3, 1, 0, 3, 4, 4, 5, 2, 1};
+__constant__ int c_pillarUpper[18] = {0, 1, 2, 5, 4, 3, 2, 5, 3, 0, 3, 4, 1, 0, 1, 4, 5, 2};
+
+__device__ inline void build_pillar(const ShapeTables& T, const HfDev& hf, int xi, int yi, bool upper, PillarStore& S, f3& offset) {
+  const double es = (double)hf.esize;
+  const double* d = T.hfdata + hf.dataOff;
+  const double h00 = d[(size_t)xi * hf.ny + yi], h10 = d[(size_t)(xi + 1) * hf.ny + yi], h01 = d[(size_t)xi * hf.ny + yi + 1],
+               h11 = d[(size_t)(xi + 1) * hf.ny + yi + 1];
+  const double h = (fmin(fmin(h00, h10), fmin(h01, h11)) - hf.minV) / 2 + hf.minV;
+  f3 v[6];
+  if (!upper) {
+    offset = mk3((xi + 0.25) * es, (yi + 0.25) * es, h);
+    v[0] = mk3(-0.25 * es, -0.25 * es, h00 - h);
+    v[1] = mk3(0.75 * es, -0.25 * es, h10 - h);
+    v[2] = mk3(-0.25 * es, 0.75 * es, h01 - h);
+    v[3] = mk3(-0.25 * es, -0.25 * es, -h - 1);
+    v[4] = mk3(0.75 * es, -0.25 * es, -h - 1);
+    v[5] = mk3(-0.25 * es, 0.75 * es, -h - 1);
+  } else {
+    offset = mk3((xi + 0.75) * es, (yi + 0.75) * es, h);
+    v[0] = mk3(0.25 * es, 0.25 * es, h11 - h);
+    v[1] = mk3(-0.75 * es, 0.25 * es, h01 - h);
+    v[2] = mk3(0.25 * es, -0.75 * es, h10 - h);
+    v[3] = mk3(0.25 * es, 0.25 * es, -h - 1);
+    v[4] = mk3(-0.75 * es, 0.25 * es, -h - 1);
+    v[5] = mk3(0.25 * es, -0.75 * es, -h - 1);
+  }
+  const int* fv = upper ? c_pillarUpper : c_pillarLower;
+  double max2 = 0;
+  for (int i = 0; i < 6; i++) {
+    S.v[i] = st3(v[i]);
+    const double n2 = vlen2(v[i]);
+    if (n2 > max2) max2 = n2;
+  }
+  S.bsr = sqrt(max2);
+  S.nE = 0;
+  for (int f = 0; f < 5; f++) {
+    const int o = c_pillarFvOff[f], L = c_pillarFvOff[f + 1] - o;
+    const f3 va = v[fv[o]], vb = v[fv[o + 1]], vc = v[fv[o + 2]];
+    f3 nn = vcross(vsub(vc, vb), vsub(vb, va));
+    if (!(nn.x == 0.f && nn.y == 0.f && nn.z == 0.f)) vnormalize(nn);
+    nn = vneg(nn);
+    S.n[f] = st3(nn);
+    S.pc[f] = -vdot(nn, va);
+    for (int j = 0; j < L; j++) {
+      f3 e = vsub(v[fv[o + j]], v[fv[o + (j + 1) % L]]);
+      vnormalize(e);
+      bool found = false;
+      for (int p = 0; p < S.nE; p++)
+        if (valmost_eq(ld3(S.e[p]), e)) { found = true; break; }
+      if (!found) S.e[S.nE++] = st3(e);
+    }
+  }
+}
+__device__ __forceinline__ HullView pillar_view(const PillarStore& S, bool upper) {
+  HullView H;
+  H.v = S.v; H.nV = 6;
+  H.n = S.n; H.pc = S.pc; H.nF = 5;
+  H.fvOff = c_pillarFvOff; H.fvIdx = upper ? c_pillarUpper : c_pillarLower;
+  H.fcOff = nullptr; H.fcIdx = nullptr;  // a pillar is never the reference hull (A) of a clip
+  H.e = S.e; H.nE = S.nE;
+  H.hasAxes = 0;  // plain ConvexPolyhedron(): contributes no face-normal axes (§5.9-9)
+  H.bsr = S.bsr;
+  return H;
+}
+
+// sphereHeightfield, narrow_phase.dart:1365-1435: one task per (cell, lower/upper) pillar
+__global__ void __launch_bounds__(64) k_np_sphere_pillar(BodyArrays B, ShapeTables T, NpArrays A) {
+  NP_BUCKET_LOOP(NP_SPIL) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_SPIL), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const HfDev hf = T.hfs[c.sj.hf];
+    const int2 cell = A.taskCell[c.task];
+    const bool upper = (c.info >> 4) & 1;
+    PillarStore S;
+    f3 off;
+    build_pillar(T, hf, cell.x, cell.y, upper, S, off);
+    const f3 wpo = to_world_point(c.xj, c.qj, off);
+    bool hit = false;
+    f3 ri, rj, ni;
+    if (vdist(c.xi, wpo) < S.bsr + c.si.bsr) {
+      const HullView H = pillar_view(S, upper);
+      hit = sphere_convex(H, c.si.radius, c.xi, wpo, c.qj, ri, rj, ni);
+    }
+    if (!raw_alloc(o, hit ? 1 : 0)) continue;
+    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, wpo, c.xj), ni);
+  }
+}
+
+// heightfieldConvex / boxHeightfield, narrow_phase.dart:2116-2175: convexConvex(hull, pillar, faceListA=[0])
+__global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+  NP_BUCKET_LOOP(NP_HPIL) {
+    TaskCtx c; load_task(B, T, A, NP_TASK(NP_HPIL), c);
+    RawOut o; o.A = A; o.task = c.task;
+    const HfDev hf = T.hfs[c.sj.hf];
+    const int2 cell = A.taskCell[c.task];
+    const bool upper = (c.info >> 4) & 1;
+    PillarStore S;
+    f3 off;
+    build_pillar(T, hf, cell.x, cell.y, upper, S, off);
+    const f3 wpo = to_world_point(c.xj, c.qj, off);
+    const HullView HA = hull_view(T, c.si.hull);
+    if (vdist(c.xi, wpo) < S.bsr + HA.bsr) {
+      const HullView HB = pillar_view(S, upper);
+      convex_convex_emit(o, HA, HB, c.xi, wpo, c.qi, c.qj, c.xi, c.xj, true, clipOverflow);
+    } else {
+      raw_alloc(o, 0);
+    }
+  }
+}
+
+// raw pool -> canonical order + createContactEquation / createFrictionEquationsFromContact parameters
+struct NpWorld {
+  double dt;
+  double gnorm;   // (frictionGravity ?? gravity).length
+  cannon_contact_material defaultCm;
+};
+
+__global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T, NpArrays A, ContactArrays C, NpWorld Wd) {
+  const int nt = min(*A.nTasks, A.taskCap);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int m = A.taskCnt[t];
+    if (m == 0) continue;
+    const int dst = A.taskOff[t], src = A.taskRaw[t];
+    if (dst + m > A.contactCap) continue;
+    const int pair = A.taskPair[t];
+    const int a = A.p1[pair], b = A.p2[pair];
+    const ShapeDev sa = T.shapes[B.shape[a]], sb = T.shapes[B.shape[b]];
+    int first, second;
+    np_order(a, b, sa.type, sb.type, first, second);
+    const ShapeDev s1 = (first == a) ? sa : sb, s2 = (first == a) ? sb : sa;
+    const int matA = B.material[first], matB = B.material[second];
+    const cannon_contact_material* cm = &Wd.defaultCm;
+    if (matA >= 0 && matB >= 0) {
+      const int idx = T.cmTable[matA * T.nMat + matB];
+      if (idx >= 0) cm = &T.cms[idx];
+    }
+    const bool cr2 = (s2.type == CANNON_SHAPE_HEIGHTFIELD) ? true : (s2.collisionResponse != 0);  // pillar hulls default to true
+    const int enabled = ((B.flags[first] & BF_COLLISION_RESPONSE) && (B.flags[second] & BF_COLLISION_RESPONSE) && s1.collisionResponse && cr2) ? 1 : 0;
+    double restitution = cm->restitution;
+    double friction = cm->friction;
+    if (matA >= 0 && matB >= 0) {
+      const double ra = T.matRestitution[matA], rb = T.matRestitution[matB];
+      if (ra >= 0 && rb >= 0) restitution = ra * rb;
+      const double fa = T.matFriction[matA], fbb = T.matFriction[matB];
+      if (fa >= 0 && fbb >= 0) friction = fa * fbb;
+    }
+    const double h = Wd.dt;
+    double k = cm->contact_equation_stiffness, d = cm->contact_equation_relaxation;
+    const double ca = 4.0 / (h * (1 + 4 * d)), cb = 4.0 * d / (1 + 4 * d), ceps = 4.0 / (h * h * k * (1 + 4 * d));
+    k = cm->friction_equation_stiffness; d = cm->friction_equation_relaxation;
+    const double fb = 4.0 * d / (1 + 4 * d), feps = 4.0 / (h * h * k * (1 + 4 * d));
+    double slip = 0.0;
+    if (friction > 0) {
+      const double mug = friction * Wd.gnorm;
+      double reducedMass = B.invMass[first] + B.invMass[second];
+      if (reducedMass > 0) reducedMass = 1 / reducedMass;
+      slip = mug * reducedMass;
+    }
+    for (int q = 0; q < m; q++) {
+      const int o = dst + q;
+      C.bi[o] = first; C.bj[o] = second;
+      C.ri[o] = A.rawRi[src + q]; C.rj[o] = A.rawRj[src + q]; C.ni[o] = A.rawNi[src + q];
+      C.rest[o] = restitution; C.mu[o] = friction; C.slip[o] = slip;
+      C.ca[o] = ca; C.cb[o] = cb; C.ceps[o] = ceps; C.fb[o] = fb; C.feps[o] = feps;
+      C.enabled[o] = enabled;
+      C.row[o] = -1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_np_per_pair(NpArrays A, int* __restrict__ perPair) {
+  const int np = *A.nPairs;
+  const int nt = *A.nTasks;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const int t0 = A.pairTaskOff[k];
+    const int t1 = t0 + A.pairTasks[k];
+    int s = 0;
+    for (int t = t0; t < t1 && t < nt; t++) s += A.taskCnt[t];
+    perPair[k] = s;
+  }
+}
