@@ -38,6 +38,21 @@ __global__ void k_bucket_starts(int* cnt) {
 }
 __global__ void k_set_int(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
 
+// persistent accumulators (never reset by the per-step counter memset): statistics and sticky overflow needs
+enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_COUNT };
+__global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restrict__ acc, int taskCap, int contactCap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  acc[AC_CONTACT_ITERS] += (long long)cnt[CT_NCONTACTS] * cnt[CT_ITERS];
+  acc[AC_STEPS] += 1;
+  auto mx = [&](int slot, long long v) { if (v > acc[slot]) acc[slot] = v; };
+  mx(AC_OVF_PAIRS, cnt[CT_OVF_PAIRS]);
+  mx(AC_OVF_TASKS, cnt[CT_NTASKS] > taskCap ? cnt[CT_NTASKS] : cnt[CT_OVF_TASKS]);
+  mx(AC_OVF_CONTACTS, cnt[CT_NCONTACTS] > contactCap ? cnt[CT_NCONTACTS] : cnt[CT_OVF_CONTACTS]);
+  mx(AC_OVF_ROWS, cnt[CT_OVF_ROWS]);
+  mx(AC_OVF_LEVELS, cnt[CT_OVF_LEVELS]);
+  mx(AC_OVF_CLIP, cnt[CT_OVF_CLIP]);
+}
+
 // constraint-pair filter, world_class.dart:488-499: drop pairs joined by a constraint with collideConnected == false
 __global__ void __launch_bounds__(256) k_pair_filter_flags(const int* __restrict__ p1, const int* __restrict__ p2, const int* __restrict__ nPairs,
                                                            int cap, const unsigned long long* __restrict__ keys, int nKeys, int* __restrict__ keep) {
@@ -155,11 +170,15 @@ struct cannon_world {
   int* hCnt = nullptr;  // pinned
   ScanTmp scanTmp;
   SortTmp sortTmp;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  DBuf<long long> acc;
+  long long* hAcc = nullptr;  // pinned
+  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool recordSolveEvents = false;
   int coopBlocksSched = 0, coopBlocksGs = 0;
 
   ~cannon_world() {
     if (hCnt) cudaFreeHost(hCnt);
+    if (hAcc) cudaFreeHost(hAcc);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 };
@@ -282,6 +301,12 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   memset(w->hCnt, 0, CT_COUNT * sizeof(int));
   if (w->cnt.reserve(CT_COUNT) != cudaSuccess) { delete w; return fail(ctx, CANNON_E_CUDA, "cudaMalloc failed"); }
   cudaMemsetAsync(w->cnt.p, 0, CT_COUNT * sizeof(int), ctx->stream);
+  if (cudaMallocHost((void**)&w->hAcc, AC_COUNT * sizeof(long long)) != cudaSuccess || w->acc.reserve(AC_COUNT) != cudaSuccess) {
+    delete w;
+    return fail(ctx, CANNON_E_CUDA, "allocation failed");
+  }
+  memset(w->hAcc, 0, AC_COUNT * sizeof(long long));
+  cudaMemsetAsync(w->acc.p, 0, AC_COUNT * sizeof(long long), ctx->stream);
   for (auto& e : w->ev) cudaEventCreate(&e);
   // empty tables so kernels always get valid pointers
   std::vector<double> e0;
@@ -317,7 +342,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rImA); REL(rImB); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -811,7 +836,7 @@ static int32_t st_prestep(cannon_world* w, double dt, int doGravity, int forceAA
   StepParams P = step_params(w, dt);
   if (forceAABB) P.needAABB = 1;
   if (!doGravity && !P.needAABB) return CANNON_OK;
-  k_prestep<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), shape_tables(w), P, doGravity);
+  { g_kernel_launches++; k_prestep<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), shape_tables(w), P, doGravity); }
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }
@@ -858,18 +883,18 @@ static int32_t st_broadphase(cannon_world* w) {
   if (n == 0) return CANNON_OK;
   if (P.kind == CANNON_BP_SAP) {
     if (!w->sapInit) {  // SAPBroadphase.setWorld: axisList = bodies in insertion order (sap_broadphase.dart:114-135)
-      k_iota<<<grid_for(w, n, 256), 256, 0, s>>>(A.sapList, n);
+      { g_kernel_launches++; k_iota<<<grid_for(w, n, 256), 256, 0, s>>>(A.sapList, n); }
       w->sapInit = true;
     }
     // sortList (:168-189): stable sort of the persistent list by aabb.lowerBound[axis] == insertion sort result
-    k_sap_keys<<<grid_for(w, n, 256), 256, 0, s>>>(B, P, A);
+    { g_kernel_launches++; k_sap_keys<<<grid_for(w, n, 256), 256, 0, s>>>(B, P, A); }
     W_TRY(w, radix_sort_pairs(A.sapKey, A.sapList, n, 32, w->sortTmp, s));
     const int gw = grid_for(w, (long long)n * 32, 256);
-    k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+    { g_kernel_launches++; k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr); }
     W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
-    k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
+    { g_kernel_launches++; k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS); }
   } else {
-    k_bp_cells<<<grid_for(w, n, 256), 256, 0, s>>>(B, shape_tables(w), P, A);
+    { g_kernel_launches++; k_bp_cells<<<grid_for(w, n, 256), 256, 0, s>>>(B, shape_tables(w), P, A); }
     int bits = 1;
     while ((1 << bits) <= w->hashSize) bits++;
     W_TRY(w, radix_sort_pairs(A.skey, A.sval, n, bits, w->sortTmp, s));
@@ -877,21 +902,21 @@ static int32_t st_broadphase(cannon_world* w) {
     W_TRY(w, cudaMemsetAsync(A.cellEnd, 0, ((size_t)w->hashSize + 2) * sizeof(int), s));
     const int nSmall = n - w->nBig;
     if (nSmall > 0) {
-      k_bp_ranges<<<grid_for(w, nSmall, 256), 256, 0, s>>>(P, A);
-      k_bp_reorder<<<grid_for(w, nSmall, 256), 256, 0, s>>>(B, P, A);
-      k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+      { g_kernel_launches++; k_bp_ranges<<<grid_for(w, nSmall, 256), 256, 0, s>>>(P, A); }
+      { g_kernel_launches++; k_bp_reorder<<<grid_for(w, nSmall, 256), 256, 0, s>>>(B, P, A); }
+      { g_kernel_launches++; k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr); }
     }
-    if (w->nBig > 0) k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr);
+    if (w->nBig > 0) { g_kernel_launches++; k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr); }
     W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
-    if (nSmall > 0) k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
-    if (w->nBig > 0) k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS);
+    if (nSmall > 0) { g_kernel_launches++; k_bp_small<<<grid_for(w, nSmall, 128), 128, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS); }
+    if (w->nBig > 0) { g_kernel_launches++; k_bp_big<<<std::min(w->nBig, w->ctx->sms * 8), 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS); }
   }
-  k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NPAIRS, w->pairCap);
+  { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NPAIRS, w->pairCap); }
   if (w->nFilterKeys > 0) {  // world_class.dart:488-499
     const int g = grid_for(w, w->pairCap, 256);
-    k_pair_filter_flags<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->filterKeys.p, w->nFilterKeys, w->keep.p);
+    { g_kernel_launches++; k_pair_filter_flags<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->filterKeys.p, w->nFilterKeys, w->keep.p); }
     W_TRY(w, scan_exclusive(w->keep.p, w->keepOff.p, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NPAIRS_RAW, w->scanTmp, s));
-    k_pair_filter_compact<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->keep.p, w->keepOff.p, w->q1.p, w->q2.p);
+    { g_kernel_launches++; k_pair_filter_compact<<<g, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->keep.p, w->keepOff.p, w->q1.p, w->q2.p); }
     W_TRY(w, cudaMemcpyAsync(cnt + CT_NPAIRS, cnt + CT_NPAIRS_RAW, sizeof(int), cudaMemcpyDeviceToDevice, s));
     std::swap(w->p1, w->q1);
     std::swap(w->p2, w->q2);
@@ -931,23 +956,23 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   ContactArrays C = contact_arrays(w);
   int* cnt = w->cnt.p;
   const int gp = grid_for(w, w->pairCap, 128);
-  k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 0);
+  { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 0); }
   W_TRY(w, scan_exclusive(A.pairTasks, A.pairTaskOff, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NTASKS, w->scanTmp, s));
-  k_bucket_starts<<<1, 32, 0, s>>>(cnt);
-  k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1);
+  { g_kernel_launches++; k_bucket_starts<<<1, 32, 0, s>>>(cnt); }
+  { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1); }
   const int g = w->ctx->sms * 8;
-  k_np_sphere_sphere<<<g, 256, 0, s>>>(B, T, A);
-  k_np_sphere_plane<<<g, 256, 0, s>>>(B, T, A);
-  k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A);
-  k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A);
-  k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A);
-  k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP);
+  { g_kernel_launches++; k_np_sphere_sphere<<<g, 256, 0, s>>>(B, T, A); }
+  { g_kernel_launches++; k_np_sphere_plane<<<g, 256, 0, s>>>(B, T, A); }
+  { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
+  { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
+  { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
+  { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   if (!w->hHfs.empty()) {
-    k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A);
-    k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP);
+    { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A); }
+    { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   }
-  k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
-  W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s));
+  { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
+  W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }
   NpWorld Wd;
   Wd.dt = dt;
   {
@@ -957,7 +982,7 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
     Wd.gnorm = vlen(g3);  // narrow_phase.dart:550
   }
   Wd.defaultCm = w->desc.default_contact_material;
-  k_np_finalize<<<grid_for(w, w->taskCap, 256), 256, 0, s>>>(B, T, A, C, Wd);
+  { g_kernel_launches++; k_np_finalize<<<grid_for(w, w->taskCap, 256), 256, 0, s>>>(B, T, A, C, Wd); }
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }
@@ -993,19 +1018,19 @@ static int32_t st_solve(cannon_world* w, double dt) {
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
   P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
   const int gc = grid_for(w, w->contactCap, 256);
-  k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p, w->desc.allow_sleep);
+  { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p, w->desc.allow_sleep); }
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
   W_TRY(w, scan_exclusive(w->contFlag.p, w->contOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_CONTTOTAL, w->scanTmp, s));
-  k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n);
+  { g_kernel_launches++; k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n); }
   W_TRY(w, cudaMemsetAsync(w->worldRows.p, 0, (nW + 1) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nW + 2) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nW + 1) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nW + 1) * sizeof(double), s));
-  k_rows_contacts<<<grid_for(w, w->contactCap, 128), 128, 0, s>>>(B, C, R, P, w->contactCap, w->fricOff.p, w->contOff.p, cnt + CT_FRICTOTAL,
+  { g_kernel_launches++; k_rows_contacts<<<grid_for(w, w->contactCap, 128), 128, 0, s>>>(B, C, R, P, w->contactCap, w->fricOff.p, w->contOff.p, cnt + CT_FRICTOTAL,
                                                                  cnt + CT_CONTTOTAL, w->worldRows.p, cnt + CT_OVF_ROWS, w->nJointAccepted,
-                                                                 cnt + CT_NCONTACTROWS);
+                                                                 cnt + CT_NCONTACTROWS); }
   if (w->nJointEq > 0)
-    k_rows_joints<<<grid_for(w, w->nJointEq, 128), 128, 0, s>>>(B, joint_arrays(w), R, P, cnt + CT_NCONTACTROWS, w->worldRows.p, cnt + CT_OVF_ROWS);
+    { g_kernel_launches++; k_rows_joints<<<grid_for(w, w->nJointEq, 128), 128, 0, s>>>(B, joint_arrays(w), R, P, cnt + CT_NCONTACTROWS, w->worldRows.p, cnt + CT_OVF_ROWS); }
   // dependency levels + sweeps: persistent cooperative kernels
   SchedArrays S;
   S.claim = w->claim.p; S.unitLevel = w->unitLevel.p; S.order = w->order.p; S.levelStart = w->levelStart.p; S.nLevels = cnt + CT_NLEVELS;
@@ -1015,17 +1040,22 @@ static int32_t st_solve(cannon_world* w, double dt) {
   U.colored = P.colored; U.taskOff = w->taskOff.p; U.taskCnt = w->taskCnt.p; U.nTasks = cnt + CT_NTASKS; U.taskCap = w->taskCap;
   U.nContacts = cnt + CT_NCONTACTS; U.contactCap = w->contactCap;
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
+  if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
   {
     void* args[] = {&R, &S, &U};
+    g_kernel_launches++;
     W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
   }
+  if (w->recordSolveEvents) cudaEventRecord(w->ev[6], s);
   W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, sizeof(int), s));
   GsStats G;
   G.worldTot = w->worldTot.p; G.worldDone = w->worldDone.p; G.worldIters = w->worldIters.p; G.itersDone = cnt + CT_ITERS;
   {
     void* args[] = {&R, &B, &S, &U, &P, &G};
+    g_kernel_launches++;
     W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
   }
+  if (w->recordSolveEvents) cudaEventRecord(w->ev[7], s);
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }
@@ -1052,8 +1082,20 @@ static int32_t refresh_damping(cannon_world* w, double dt) {
 
 static int32_t st_integrate(cannon_world* w, double dt, int applyLambda) {
   StepParams P = step_params(w, dt);
-  k_integrate<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), P, w->worldRows.p, applyLambda);
+  { g_kernel_launches++; k_integrate<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), P, w->worldRows.p, applyLambda); }
   W_TRY(w, cudaGetLastError());
+  return CANNON_OK;
+}
+
+static int32_t check_overflow_acc(cannon_world* w) {
+  const long long* a = w->hAcc;
+  char buf[256];
+  if (a[AC_OVF_PAIRS] > 0) { snprintf(buf, sizeof buf, "pair capacity exceeded: need %lld, have %d (set cannon_world_desc.max_pairs)", a[AC_OVF_PAIRS], w->pairCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (a[AC_OVF_TASKS] > 0) { snprintf(buf, sizeof buf, "narrowphase task capacity exceeded: need %lld, have %d (raise max_pairs)", a[AC_OVF_TASKS], w->taskCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (a[AC_OVF_CONTACTS] > 0) { snprintf(buf, sizeof buf, "contact capacity exceeded: need %lld, have %d (set cannon_world_desc.max_contacts)", a[AC_OVF_CONTACTS], w->contactCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (a[AC_OVF_ROWS] > 0) { snprintf(buf, sizeof buf, "row capacity exceeded: need %lld, have %d", a[AC_OVF_ROWS], w->rowCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
+  if (a[AC_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
+  if (a[AC_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
   return CANNON_OK;
 }
 
@@ -1133,7 +1175,7 @@ static int32_t export_contacts(cannon_world* w, cannon_contacts_soa* out, int32_
   }
   if (out->multiplier) {
     const double h = w->dt > 0 ? w->dt : 1.0 / 60;
-    k_multipliers<<<grid_for(w, nc, 256), 256, 0, w->ctx->stream>>>(contact_arrays(w), row_arrays(w), w->contactCap, 1 / h, w->cMult.p);
+    { g_kernel_launches++; k_multipliers<<<grid_for(w, nc, 256), 256, 0, w->ctx->stream>>>(contact_arrays(w), row_arrays(w), w->contactCap, 1 / h, w->cMult.p); }
     W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
     W_TRY(w, cudaMemcpy(out->multiplier, w->cMult.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
   }
@@ -1154,11 +1196,11 @@ int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const in
     W_TRY(w, cudaMemcpyAsync(w->p1.p, p1, np * sizeof(int), cudaMemcpyHostToDevice, s));
     W_TRY(w, cudaMemcpyAsync(w->p2.p, p2, np * sizeof(int), cudaMemcpyHostToDevice, s));
   }
-  k_set_int<<<1, 32, 0, s>>>(w->cnt.p + CT_NPAIRS, np);
+  { g_kernel_launches++; k_set_int<<<1, 32, 0, s>>>(w->cnt.p + CT_NPAIRS, np); }
   if (w->dt < 0) w->dt = 1.0 / 60;  // World.defaultDt
   if ((rc = st_narrowphase(w, w->dt)) != CANNON_OK) return rc;
   if (per_pair_count && np > 0) {
-    k_np_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(np_arrays(w), w->keep.p);
+    { g_kernel_launches++; k_np_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(np_arrays(w), w->keep.p); }
     W_TRY(w, cudaGetLastError());
   }
   if ((rc = sync_counters(w)) != CANNON_OK) return rc;
@@ -1178,7 +1220,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 2 * sizeof(int), s));
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
-  k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p);
+  { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
   W_TRY(w, cudaGetLastError());
   const int keepPairs = w->hCnt[CT_NPAIRS], keepContacts = w->hCnt[CT_NCONTACTS];
   if ((rc = sync_counters(w)) != CANNON_OK) return rc;
@@ -1210,8 +1252,10 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   int32_t rc;
   if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
   w->dt = dt;
+  cudaEventRecord(w->ev[8], s);
   for (int it = 0; it < nsteps; it++) {
     const bool last = it == nsteps - 1;
+    w->recordSolveEvents = last;
     if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
     if (last) cudaEventRecord(w->ev[0], s);
     if ((rc = st_prestep(w, dt, 1, 0)) != CANNON_OK) return rc;
@@ -1223,22 +1267,29 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
     if (last) cudaEventRecord(w->ev[3], s);
     if ((rc = st_integrate(w, dt, 1)) != CANNON_OK) return rc;
     if (last) cudaEventRecord(w->ev[4], s);
+    // statistics + sticky overflow needs are folded on the device: no host round trip between steps
+    { g_kernel_launches++; k_step_epilogue<<<1, 32, 0, s>>>(w->cnt.p, w->acc.p, w->taskCap, w->contactCap); }
     w->stepnumber += 1;
     w->time += dt;  // World.step: time += dt after internalStep (world_class.dart:396-399)
-    // per-step statistics are accumulated on the host from the counters of every step: one small async copy
-    W_TRY(w, cudaMemcpyAsync(w->hCnt, w->cnt.p, CT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
-    W_TRY(w, cudaStreamSynchronize(s));
-    if ((rc = check_overflow(w)) != CANNON_OK) return rc;
-    w->prof.steps += 1;
-    w->prof.contact_iters_total += (int64_t)w->hCnt[CT_NCONTACTS] * w->hCnt[CT_ITERS];
   }
+  w->recordSolveEvents = false;
+  cudaEventRecord(w->ev[9], s);
   if (nsteps > 0) {
+    W_TRY(w, cudaMemcpyAsync(w->hCnt, w->cnt.p, CT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    W_TRY(w, cudaMemcpyAsync(w->hAcc, w->acc.p, AC_COUNT * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    W_TRY(w, cudaStreamSynchronize(s));
+    if ((rc = check_overflow_acc(w)) != CANNON_OK) return rc;
     float ms;
     cannon_profile& p = w->prof;
+    p.steps = w->hAcc[AC_STEPS];
+    p.contact_iters_total = w->hAcc[AC_CONTACT_ITERS];
     if (cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]) == cudaSuccess) p.broadphase = ms;
     if (cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]) == cudaSuccess) p.narrowphase = ms;
     if (cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]) == cudaSuccess) { p.solve = ms; p.make_contact_constraints = 0; }
     if (cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]) == cudaSuccess) p.integrate = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]) == cudaSuccess) p.schedule_ms = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[6], w->ev[7]) == cudaSuccess) p.gs_ms = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;
     p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
     p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
   }
@@ -1247,6 +1298,7 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
 
 int32_t cannon_world_profile(cannon_world* w, cannon_profile* out) {
   if (!w || !out) return CANNON_E_INVALID;
+  w->prof.kernel_launches = g_kernel_launches;
   *out = w->prof;
   return CANNON_OK;
 }
@@ -1376,7 +1428,7 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
   if (force) W_TRY(w, put(force, w->force.p, 3));
   if (torque) W_TRY(w, put(torque, w->torque.p, 3));
   if (quaternion) {
-    k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count);
+    { g_kernel_launches++; k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count); }
     W_TRY(w, cudaStreamSynchronize(s));
   }
   return CANNON_OK;

@@ -58,6 +58,9 @@ struct DBuf {
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// kernels launched by this library (reported through cannon_profile.kernel_launches)
+static long long g_kernel_launches = 0;
+
 // ---------------------------------------------------------------------------------------------------
 // exclusive scan of int32 (n read from device memory so the whole step stays asynchronous)
 // ---------------------------------------------------------------------------------------------------
@@ -170,6 +173,7 @@ static inline cudaError_t scan_exclusive(const int* in, int* out, const int* n_p
   k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, s>>>(in, n_ptr, n_fixed, tmp.tiles.p);
   k_scan_tiles<<<1, 1024, 0, s>>>(tmp.tiles.p, n_tiles, total_out);
   k_scan_apply<<<n_tiles, SCAN_THREADS, 0, s>>>(in, out, n_ptr, n_fixed, tmp.tiles.p);
+  g_kernel_launches += 3;
   return cudaGetLastError();
 }
 
@@ -256,6 +260,7 @@ static inline cudaError_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, int n
     k_rs_hist<<<n_tiles, RS_THREADS, 0, s>>>(ki, n, shift, n_tiles, t.hist.p);
     if ((e = scan_exclusive(t.hist.p, t.hist.p, nullptr, 256 * n_tiles, 256 * n_tiles, nullptr, t.scan, s)) != cudaSuccess) return e;
     k_rs_scatter<<<n_tiles, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, n_tiles, t.hist.p);
+    g_kernel_launches += 2;
     uint32_t* tk = ki; ki = ko; ko = tk;
     uint32_t* tv = vi; vi = vo; vo = tv;
   }

@@ -201,6 +201,11 @@ typedef struct cannon_profile {
   double solve, make_contact_constraints, broadphase, integrate, narrowphase;
   int64_t n_pairs, n_contacts, n_rows, n_levels, iterations_done;
   int64_t steps, contact_iters_total;  /* accumulated since world creation */
+  /* device times (CUDA events on the library's stream), milliseconds */
+  double step_call_ms;   /* whole last cannon_world_step call (all nsteps) */
+  double schedule_ms;    /* dependency-level / colouring kernel of the last step */
+  double gs_ms;          /* Gauss-Seidel sweep kernel of the last step */
+  int64_t kernel_launches; /* kernels launched by the library since world creation */
 } cannon_profile;
 
 /* ---- lifecycle ---- */
