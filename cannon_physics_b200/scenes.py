@@ -192,7 +192,7 @@ def mixed_pile_on_heightfield(nx=100, nz=100, layers=10, seed=3, hf_samples=257,
         shapes=shapes, bodies=b, n_bodies=n, name=f"c3_mixed_pile_{nx}x{nz}x{layers}")
 
 
-def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver=F.SOLVER_REFERENCE_ORDER) -> SceneSpec:
+def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver=F.SOLVER_REFERENCE_ORDER, top_y=None) -> SceneSpec:
     """config 4: n_worlds independent worlds of 1 plane + chains*links boxes hanging as jointed chains.
 
     Links are joined alternately by two corner PointToPointConstraints (examples/lib/examples/constraints.dart:135-146)
@@ -204,6 +204,9 @@ def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver
     b["world_id"] = np.repeat(np.arange(n_worlds, dtype=np.int32), per)
     hx, hy, hz = 0.25, 0.25, 0.05
     space = 0.1 * hy
+    # hang low enough that the last links of every chain rest on the ground plane (joint rows + contacts)
+    if top_y is None:
+        top_y = (links - 2) * (2 * hy + 2 * space)
     cons = []
     for w in range(n_worlds):
         rng = SplitMix64(seed + w)
@@ -217,7 +220,7 @@ def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver
             prev = -1
             for l in range(links):
                 idx = base + 1 + c * links + l
-                b["position"][idx] = (ax, 6.0 - l * (2 * hy + 2 * space), az)
+                b["position"][idx] = (ax, top_y - l * (2 * hy + 2 * space), az)
                 b["mass"][idx] = 0.0 if l == 0 else 0.3
                 b["shape"][idx] = 1
                 if l > 0:

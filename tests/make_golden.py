@@ -1,0 +1,53 @@
+"""Generates tests/golden/*.npz from the CPU oracle (the reference itself cannot run here: no Dart SDK,
+SURVEY.md §8c). The fixtures freeze the oracle's behaviour so (a) oracle regressions are caught on CPU and
+(b) the CUDA path is compared against committed vectors on the GPU box, not only against a live oracle.
+
+    python tests/make_golden.py        # rewrites the fixtures
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cannon_physics_b200 import _ffi as F  # noqa: E402
+from cannon_physics_b200 import engine, scenes  # noqa: E402
+
+REF = F.SOLVER_REFERENCE_ORDER
+CASES = {
+    "c1_small": (lambda: scenes.spheres_on_plane(4, 4, 4), 90),
+    "c2_small": (lambda: scenes.box_stacks(4, 5, grid=2), 60),
+    "c3_plane_small": (lambda: scenes.mixed_pile_on_heightfield(4, 4, 3, with_heightfield=False, solver=REF, grid_cells=(8, 4, 8)), 90),
+    "c3_hf_small": (lambda: scenes.mixed_pile_on_heightfield(4, 4, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 90),
+    "c4_small": (lambda: scenes.chain_worlds(3, chains=2, links=4), 60),
+    "c5_small": (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 120),
+}
+
+
+def run_case(lib, make_spec, steps):
+    w = engine.DeviceWorld(lib, make_spec())
+    out = {}
+    w.step(1 / 60, steps - 1)
+    # last step through the staged entry points so pair lists / contacts are part of the fixture
+    w.set_dt(1 / 60)
+    w.apply_gravity()
+    p1, p2 = w.broadphase_pairs()
+    c = w.narrowphase_contacts(p1, p2)
+    w.solver_solve(1 / 60)
+    rows = w.get_rows()
+    w.integrate(1 / 60)
+    st = w.get_bodies(("position", "quaternion", "velocity", "angular_velocity", "sleep_state"))
+    out.update(p1=p1, p2=p2, per_pair_count=c["per_pair_count"], c_bi=c["body_i"], c_bj=c["body_j"], c_ri=c["ri"], c_rj=c["rj"], c_ni=c["ni"],
+               row_B=rows["B"], row_invC=rows["invC"], row_lambda=rows["lambda"], **st)
+    return out
+
+
+if __name__ == "__main__":
+    lib = F.bind(os.path.join(ROOT, "oracle", "libcannon_oracle.so"))
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, (mk, steps) in CASES.items():
+        res = run_case(lib, mk, steps)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **res)
+        print(name, {k: v.shape for k, v in res.items() if k in ("p1", "c_bi", "row_B")})

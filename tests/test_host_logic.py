@@ -1,0 +1,118 @@
+"""CPU-only checks of the host layer: ABI export + layout, scene generators, API flattening, sharding."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cannon_physics_b200 import _ffi as F
+from cannon_physics_b200 import engine, scenes
+from cannon_physics_b200.batch import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    import re
+    text = open(os.path.join(ROOT, "include", "cannon_cuda.h")).read()
+    return sorted(set(re.findall(r"\b(cannon_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _header_symbols() == sorted(F.PROTOTYPES)
+
+
+@pytest.mark.parametrize("which", ["cuda", "oracle"])
+def test_library_exports_every_declared_symbol(which, oracle_lib):
+    path = os.path.join(ROOT, "cannon_physics_b200", "libcannon_cuda.so") if which == "cuda" else os.path.join(ROOT, "oracle", "libcannon_oracle.so")
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    missing = [s for s in F.PROTOTYPES if s not in exported]
+    assert not missing, missing
+
+
+def test_cuda_library_loads_without_gpu_and_reports_nogpu(cuda_lib):
+    # no compute calls here: loading, version and defaults must work on a CPU-only box
+    assert cuda_lib.cannon_version() == 1
+    assert cuda_lib.cannon_backend() == b"cuda"
+    import torch
+    if not torch.cuda.is_available():
+        h = F.VP()
+        assert cuda_lib.cannon_ctx_create(0, C.byref(h)) == F.E_NOGPU  # no CPU fallback, fails loudly
+
+
+@pytest.mark.parametrize("which", ["cuda", "oracle"])
+def test_struct_layouts_match_c(which, cuda_lib, oracle_lib):
+    lib = cuda_lib if which == "cuda" else oracle_lib
+    d = F.WorldDesc()
+    lib.cannon_world_desc_default(C.byref(d))
+    assert (d.solver_iterations, d.solver_tolerance, d.broadphase_kind, d.n_worlds) == (10, 1e-7, F.BP_NAIVE, 1)
+    assert (d.grid_nx, d.grid_ny, d.grid_nz) == (10, 10, 10) and list(d.grid_min) == [100.0] * 3 and list(d.grid_max) == [-100.0] * 3
+    cm = d.default_contact_material
+    assert (cm.friction, cm.restitution, cm.contact_equation_stiffness, cm.contact_equation_relaxation) == (0.3, 0.0, 1e7, 3.0)
+    assert (cm.friction_equation_stiffness, cm.friction_equation_relaxation) == (1e7, 3.0)
+    s = F.ShapeDesc()
+    lib.cannon_shape_desc_default(C.byref(s))
+    assert (s.type, s.collision_response, s.collision_filter_group, s.collision_filter_mask) == (0, 1, -1, -1)
+    assert (s.radius, s.radius_top, s.radius_bottom, s.height, s.num_segments, s.hf_element_size) == (1.0, 1.0, 1.0, 1.0, 8, 1)
+
+
+def test_splitmix64_known_values_and_vectorised_stream():
+    r = scenes.SplitMix64(0)
+    assert [r.next_u64() for _ in range(3)] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    a, b = scenes.SplitMix64(12345), scenes.SplitMix64(12345)
+    seq = np.array([(a.next_u64() >> 11) / (1 << 53) for _ in range(64)])
+    assert np.array_equal(seq, b.uniform(64)) and a.s == b.s
+
+
+def test_scene_generators_are_deterministic_and_shaped():
+    s1, s2 = scenes.spheres_on_plane(3, 3, 3), scenes.spheres_on_plane(3, 3, 3)
+    assert s1.n_bodies == 28 and np.array_equal(s1.bodies["position"], s2.bodies["position"])
+    c2 = scenes.box_stacks(4, 5, grid=2)
+    assert c2.n_bodies == 21 and c2.desc["broadphase_kind"] == F.BP_SAP and c2.contact_materials[0]["restitution"] == 0.2
+    c3 = scenes.mixed_pile_on_heightfield(4, 4, 2, hf_samples=33)
+    assert c3.n_bodies == 33 and c3.shapes[0]["hf_data"].shape == (33, 33) and c3.desc["broadphase_kind"] == F.BP_GRID
+    assert np.all(c3.shapes[0]["hf_data"][0, :] == 3.0)
+    c4 = scenes.chain_worlds(3, chains=2, links=4)
+    assert c4.n_bodies == 3 * 9 and len(c4.constraints) == 3 * 2 * (2 + 1 + 2) and np.all(np.diff(c4.bodies["world_id"]) >= 0)
+    c5 = scenes.sphere_container(n_spheres=100)
+    assert c5.n_bodies == 105 and c5.desc["allow_sleep"] == 1
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 4096):
+        for ws in (1, 2, 3, 8):
+            parts = [shard_range(n, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 4, 4)
+
+
+def test_api_world_flattens_like_the_reference_objects(oracle_lib):
+    from cannon_physics_b200 import api
+    stone = api.Material(name="stone")
+    world = api.World(gravity=(0, -10, 0), broadphase=api.SAPBroadphase(axisIndex=0), solver=api.GSSolver(), _lib=oracle_lib)
+    world.solver.iterations = 20
+    world.addContactMaterial(api.ContactMaterial(stone, stone, friction=0.3, restitution=0.2))
+    ground = api.Body(mass=0, material=stone, shape=api.Plane(), quaternion=api.Quaternion.setFromEuler(-np.pi / 2, 0, 0))
+    world.addBody(ground)
+    shape = api.Box((0.5, 0.5, 0.5))
+    boxes = [api.Body(mass=1, material=stone, shape=shape, position=(0, 0.5 + 1.02 * k, 0)) for k in range(3)]
+    for b in boxes:
+        world.addBody(b)
+    spec = world._spec()
+    assert spec.n_bodies == 4 and len(spec.shapes) == 2 and spec.desc["solver_iterations"] == 20 and spec.desc["broadphase_kind"] == F.BP_SAP
+    assert spec.bodies["type"].tolist() == [F.BODY_STATIC, 0, 0, 0] and spec.bodies["material"].tolist() == [0] * 4
+    for _ in range(30):
+        world.step(1 / 60)
+    assert world.stepnumber == 30 and abs(world.time - 0.5) < 1e-12
+    ys = [float(b.position[1]) for b in boxes]
+    assert 0.45 < ys[0] < 0.55 and ys[0] < ys[1] < ys[2]  # the stack stays a stack
+    assert len(world.contacts["body_i"]) >= 8
+    with pytest.raises(F.CannonError):
+        boxes[0].addShape(api.Sphere(1.0))  # compound bodies are outside the hot-path scope

@@ -1,0 +1,103 @@
+"""CPU-only properties of the oracle + regression against the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from cannon_physics_b200 import _ffi as F
+from cannon_physics_b200 import engine, scenes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _pairs(w):
+    p1, p2 = w.broadphase_pairs()
+    return set(zip(p1.tolist(), p2.tolist())), (p1, p2)
+
+
+def test_naive_order_is_i_major_j_ascending(oracle_lib):
+    w = engine.DeviceWorld(oracle_lib, scenes.spheres_on_plane(3, 3, 3, spacing=0.45))
+    _, (p1, p2) = _pairs(w)
+    assert len(p1) > 20 and np.all(p2 < p1)
+    key = p1.astype(np.int64) * 100000 + p2
+    assert np.all(np.diff(key) > 0)
+
+
+def test_sap_and_grid_find_the_naive_pair_set_for_spheres(oracle_lib):
+    base = scenes.spheres_on_plane(4, 4, 4, spacing=0.45)
+    ref, _ = _pairs(engine.DeviceWorld(oracle_lib, base))
+    for axis in (0, 1, 2):
+        spec = scenes.spheres_on_plane(4, 4, 4, spacing=0.45)
+        spec.desc.update(broadphase_kind=F.BP_SAP, sap_axis=axis)
+        got, _ = _pairs(engine.DeviceWorld(oracle_lib, spec))
+        assert {tuple(sorted(p)) for p in got} == {tuple(sorted(p)) for p in ref}
+    spec = scenes.spheres_on_plane(4, 4, 4, spacing=0.45)
+    lo, hi = spec.bodies["position"][1:].min(0) - 1, spec.bodies["position"][1:].max(0) + 1
+    spec.desc.update(broadphase_kind=F.BP_GRID, grid_min=lo, grid_max=hi, grid_nx=5, grid_ny=4, grid_nz=6)
+    got, (p1, p2) = _pairs(engine.DeviceWorld(oracle_lib, spec))
+    # the plane is binned by distance to bin centres, so plane pairs are a subset; sphere-sphere pairs must match
+    assert {p for p in got if 0 not in p} == {p for p in ref if 0 not in p}
+    assert got <= ref and np.all(p2 < p1)
+
+
+def test_constraint_pair_filter_removes_connected_pairs(oracle_lib):
+    spec = scenes.chain_worlds(1, chains=1, links=3)
+    w = engine.DeviceWorld(oracle_lib, spec)
+    before, _ = _pairs(w)
+    assert (3, 2) in before
+    spec2 = scenes.chain_worlds(1, chains=1, links=3)
+    for c in spec2.constraints:
+        if c["type"] == F.CONSTRAINT_HINGE:
+            c["collide_connected"] = 0
+    after, _ = _pairs(engine.DeviceWorld(oracle_lib, spec2))
+    hinge_pairs = {(max(c["body_a"], c["body_b"]), min(c["body_a"], c["body_b"])) for c in spec2.constraints if c["type"] == F.CONSTRAINT_HINGE}
+    assert hinge_pairs and hinge_pairs <= before and not (hinge_pairs & after) and after == before - hinge_pairs
+
+
+def test_batch_equals_separate_worlds(oracle_lib):
+    batch = engine.DeviceWorld(oracle_lib, scenes.chain_worlds(3, chains=2, links=4))
+    singles = [engine.DeviceWorld(oracle_lib, scenes.chain_worlds(1, chains=2, links=4, seed=4 + k)) for k in range(3)]
+    for _ in range(40):
+        batch.step(1 / 60)
+        for s in singles:
+            s.step(1 / 60)
+    b = batch.get_bodies()
+    for k, s in enumerate(singles):
+        one = s.get_bodies()
+        for f in ("position", "quaternion", "velocity", "angular_velocity"):
+            assert np.array_equal(b[f][9 * k:9 * (k + 1)], one[f]), (k, f)
+
+
+def test_pile_comes_to_rest_and_sleeps(oracle_lib):
+    w = engine.DeviceWorld(oracle_lib, scenes.sphere_container(4, 4, 2, extent=3.0, solver=F.SOLVER_REFERENCE_ORDER))
+    w.step(1 / 60, 360)
+    s = w.get_bodies(("position", "velocity", "sleep_state"))
+    assert np.all(s["position"][5:, 1] > 0.2) and np.all(s["position"][5:, 1] < 2.0)  # nobody fell through the floor
+    assert np.abs(s["velocity"]).max() < 0.2
+    assert np.count_nonzero(s["sleep_state"][5:] == F.SLEEPING) > 0  # world.allowSleep=true puts resting spheres to sleep
+
+
+def test_hinge_chain_hangs_without_drifting(oracle_lib):
+    w = engine.DeviceWorld(oracle_lib, scenes.chain_worlds(1, chains=1, links=5, top_y=6.0))
+    y0 = w.get_bodies(("position",))["position"][:, 1].copy()
+    w.step(1 / 60, 240)
+    s = w.get_bodies(("position", "velocity"))
+    assert np.all(np.isfinite(s["position"])) and np.abs(s["position"][1:, 1] - y0[1:]).max() < 0.3
+    assert np.abs(s["velocity"]).max() < 1.0
+    # default recipe: the chain is long enough for its last links to rest on the ground (joint rows + contacts)
+    w = engine.DeviceWorld(oracle_lib, scenes.chain_worlds(1, chains=1, links=5))
+    w.step(1 / 60, 240)
+    s = w.get_bodies(("position", "velocity"))
+    assert np.all(np.isfinite(s["position"])) and s["position"][1:, 1].min() > -0.1 and w.profile()["n_contacts"] > 0
+
+
+GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_matches_golden_fixture(oracle_lib, name):
+    from make_golden import CASES, run_case
+    got = run_case(oracle_lib, *CASES[name])
+    ref = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for k in ref.files:
+        assert np.array_equal(got[k], ref[k]), (name, k)
