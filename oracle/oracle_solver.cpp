@@ -236,10 +236,13 @@ int World::solve(double h) {
     // a batch is nW separate World objects in the reference: each solves its own equation list
     // (own iteration loop and tolerance early-exit) over its own bodies
     std::vector<std::vector<Eq*>> per(nW);
-    for (Eq& e : frictions) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
-    for (Eq& e : contacts) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
+    std::vector<std::vector<int>> perGlobal(nW);  // position of each equation in the batch-wide list (debug row order)
+    int gidx = 0;
+    auto put = [&](Eq& e) { per[bodies[e.bi].worldId].push_back(&e); perGlobal[bodies[e.bi].worldId].push_back(gidx++); };
+    for (Eq& e : frictions) if (accept(e)) put(e);
+    for (Eq& e : contacts) if (accept(e)) put(e);
     for (Constraint& c : constraints)
-      for (Eq& e : c.eqs) if (accept(e)) per[bodies[e.bi].worldId].push_back(&e);
+      for (Eq& e : c.eqs) if (accept(e)) put(e);
     std::vector<int> wb0(nW, -1), wb1(nW, 0);
     for (int i = 0; i < (int)bodies.size(); i++) {
       int wi = bodies[i].worldId;
@@ -248,8 +251,11 @@ int World::solve(double h) {
     }
     for (int wi = 0; wi < nW; wi++) {
       if (wb0[wi] < 0) continue;
-      int it = gsSolve(*this, per[wi], wb0[wi], wb1[wi], h, rows);
+      std::vector<RowDebug> dbg;
+      int it = gsSolve(*this, per[wi], wb0[wi], wb1[wi], h, dbg);
       if (it > itersMax) itersMax = it;
+      if ((int)rows.size() < gidx) rows.resize(gidx);
+      for (size_t k = 0; k < dbg.size(); k++) rows[perGlobal[wi][k]] = dbg[k];
     }
   }
   return itersMax;
