@@ -26,7 +26,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_NUNITS, CT_NUNITS1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = CT_BUCKETCURSOR + NP_NTYPES, CT_COUNT = CT_BAR + 2
 };
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_multipliers(ContactArrays C, RowArrays 
   const int nc = min(*C.nContacts, contactCap);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int r = C.row[c];
-    out[c] = r >= 0 ? R.lambda[r] * invDt : 0.0;  // Equation.multiplier, gs_solver.dart:124-129
+    out[c] = r >= 0 ? (R.fast ? (double)R.flambda[r] : R.lambda[r]) * invDt : 0.0;  // Equation.multiplier, gs_solver.dart:124-129
   }
 }
 
@@ -151,12 +151,18 @@ struct cannon_world {
   DBuf<float4> cRi, cRj, cNi;
   DBuf<double> cRest, cMu, cSlip, cCa, cCb, cCeps, cFb, cFeps, cMult;
   // device: rows
-  DBuf<int> rBi, rBj, rKind, rFlags;
+  DBuf<int> rKind;
   DBuf<float4> rN, rRA, rRB, rIA, rIB;
-  DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rImA, rImB, rLambda;
+  DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
+  DBuf<float4> rQ0, rQ1, rQ2, rQ3, rQ4;
+  DBuf<float> rFlambda;
   int rowCap = 0;
+  // device: solver units
+  DBuf<int> uBi, uBj, uFlags, uRows, uSrc, eBi, eBj, eFlags, eRowBase, eRows, unitRow;
+  DBuf<double> eImA, eImB;
+  int unitCap = 0;
   // device: joints
-  DBuf<int> jBodyA, jBodyB, jKind, jEnabled, jRowSlot, jFirst;
+  DBuf<int> jBodyA, jBodyB, jKind, jEnabled, jRowSlot, jFirst, jSlotEq;
   DBuf<float4> jPivotA, jPivotB, jAxisA, jAxisB, jNi;
   DBuf<double> jMinF, jMaxF, jA, jB, jEps, jTargetVel;
   int nJointEq = 0, nJointAccepted = 0;
@@ -172,9 +178,10 @@ struct cannon_world {
   SortTmp sortTmp;
   DBuf<long long> acc;
   long long* hAcc = nullptr;  // pinned
-  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long lastUnits = 0, lastLevels = 0;  // widths seen by the last synchronised call (sizes the cooperative grids)
   bool recordSolveEvents = false;
-  int coopBlocksSched = 0, coopBlocksGs = 0;
+  int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0;
 
   ~cannon_world() {
     if (hCnt) cudaFreeHost(hCnt);
@@ -319,6 +326,8 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   w->coopBlocksSched = ctx->sms * std::max(1, std::min(occ, 4));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs, 256, 0);
   w->coopBlocksGs = ctx->sms * std::max(1, std::min(occ, 4));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, 256, 0);
+  w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   *out = w;
   return CANNON_OK;
 }
@@ -338,8 +347,10 @@ void cannon_world_destroy(cannon_world* w) {
   REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
   REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
-  REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rBi); REL(rBj); REL(rKind); REL(rFlags); REL(rN); REL(rRA); REL(rRB);
-  REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rImA); REL(rImB); REL(rLambda); REL(jBodyA); REL(jBodyB);
+  REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
+  REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
+  REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rQ0); REL(rQ1); REL(rQ2); REL(rQ3); REL(rQ4); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc);
@@ -583,10 +594,18 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(contFlag, contactCap); RES(fricOff, contactCap); RES(contOff, contactCap); RES(cRi, contactCap); RES(cRj, contactCap);
   RES(cNi, contactCap); RES(cRest, contactCap); RES(cMu, contactCap); RES(cSlip, contactCap); RES(cCa, contactCap); RES(cCb, contactCap);
   RES(cCeps, contactCap); RES(cFb, contactCap); RES(cFeps, contactCap); RES(cMult, contactCap);
-  RES(rBi, rowCap); RES(rBj, rowCap); RES(rKind, rowCap); RES(rFlags, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
-  RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
-  RES(rImA, rowCap); RES(rImB, rowCap); RES(rLambda, rowCap);
-  RES(unitLevel, rowCap); RES(order, rowCap); RES(act0, rowCap); RES(act1, rowCap); RES(levelStart, w->maxLevels + 2);
+  if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
+    RES(rQ0, rowCap); RES(rQ1, rowCap); RES(rQ2, rowCap); RES(rQ3, rowCap); RES(rQ4, rowCap); RES(rFlambda, rowCap);
+  } else {
+    RES(rKind, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
+    RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
+    RES(rLambda, rowCap);
+  }
+  const int unitCap = rowCap + 2;
+  w->unitCap = unitCap;
+  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
+  RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
+  RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
   RES(worldRows, nW + 1); RES(worldDone, nW + 2); RES(worldIters, nW + 1); RES(worldTot, nW + 1);
@@ -721,7 +740,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   if (!w || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
-  std::vector<int> bodyA, bodyB, kind, enabled, rowSlot, first;
+  std::vector<int> bodyA, bodyB, kind, enabled, rowSlot, first, slotEq;
   std::vector<float4> pivotA, pivotB, axisA, axisB, ni;
   std::vector<double> minF, maxF, a, b, eps, targetVel;
   std::vector<unsigned long long> keys;
@@ -777,7 +796,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
       minF.push_back(-mf);
       maxF.push_back(mf);
       targetVel.push_back(tv);
-      rowSlot.push_back((en && !trig) ? slot++ : -1);
+      if (en && !trig) { slotEq.push_back((int)rowSlot.size()); rowSlot.push_back(slot++); } else rowSlot.push_back(-1);
     }
   }
   std::sort(keys.begin(), keys.end());
@@ -787,6 +806,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   w->nJointAccepted = slot;
   W_TRY(w, upload(w->jBodyA, bodyA, s)); W_TRY(w, upload(w->jBodyB, bodyB, s)); W_TRY(w, upload(w->jKind, kind, s));
   W_TRY(w, upload(w->jEnabled, enabled, s)); W_TRY(w, upload(w->jRowSlot, rowSlot, s)); W_TRY(w, upload(w->jFirst, first, s));
+  W_TRY(w, upload(w->jSlotEq, slotEq, s));
   W_TRY(w, upload(w->jPivotA, pivotA, s)); W_TRY(w, upload(w->jPivotB, pivotB, s)); W_TRY(w, upload(w->jAxisA, axisA, s));
   W_TRY(w, upload(w->jAxisB, axisB, s)); W_TRY(w, upload(w->jNi, ni, s)); W_TRY(w, upload(w->jMinF, minF, s));
   W_TRY(w, upload(w->jMaxF, maxF, s)); W_TRY(w, upload(w->jA, a, s)); W_TRY(w, upload(w->jB, b, s)); W_TRY(w, upload(w->jEps, eps, s));
@@ -990,20 +1010,44 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
 static RowArrays row_arrays(cannon_world* w) {
   RowArrays R;
   R.nRows = w->cnt.p + CT_NROWS;
-  R.bi = w->rBi.p; R.bj = w->rBj.p; R.kind = w->rKind.p; R.n = w->rN.p; R.rA = w->rRA.p; R.rB = w->rRB.p; R.iA = w->rIA.p; R.iB = w->rIB.p;
-  R.B = w->rB.p; R.invC = w->rInvC.p; R.eps = w->rEps.p; R.minF = w->rMinF.p; R.maxF = w->rMaxF.p; R.imA = w->rImA.p; R.imB = w->rImB.p;
-  R.lambda = w->rLambda.p; R.flags = w->rFlags.p; R.rowCap = w->rowCap;
+  R.kind = w->rKind.p; R.n = w->rN.p; R.rA = w->rRA.p; R.rB = w->rRB.p; R.iA = w->rIA.p; R.iB = w->rIB.p;
+  R.B = w->rB.p; R.invC = w->rInvC.p; R.eps = w->rEps.p; R.minF = w->rMinF.p; R.maxF = w->rMaxF.p; R.lambda = w->rLambda.p;
+  R.rowCap = w->rowCap;
+  R.fast = w->desc.solver_kind == CANNON_SOLVER_COLORED ? 1 : 0;
+  R.q0 = w->rQ0.p; R.q1 = w->rQ1.p; R.q2 = w->rQ2.p; R.q3 = w->rQ3.p; R.q4 = w->rQ4.p; R.flambda = w->rFlambda.p;
   return R;
+}
+static UnitArrays unit_arrays(cannon_world* w) {
+  UnitArrays U;
+  U.nUnits = w->cnt.p + CT_NUNITS;
+  U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p;
+  U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p;
+  U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
+  return U;
 }
 static JointArrays joint_arrays(cannon_world* w) {
   JointArrays J;
   J.n = w->nJointEq;
   J.bodyA = w->jBodyA.p; J.bodyB = w->jBodyB.p; J.kind = w->jKind.p; J.enabled = w->jEnabled.p; J.rowSlot = w->jRowSlot.p;
+  J.slotEq = w->jSlotEq.p;
   J.pivotA = w->jPivotA.p; J.pivotB = w->jPivotB.p; J.axisA = w->jAxisA.p; J.axisB = w->jAxisB.p; J.ni = w->jNi.p;
   J.minF = w->jMinF.p; J.maxF = w->jMaxF.p; J.a = w->jA.p; J.b = w->jB.p; J.eps = w->jEps.p; J.targetVel = w->jTargetVel.p;
   J.first = w->jFirst.p; J.nAccepted = w->nJointAccepted;
   J.cosMaxAngle = cos(M_PI / 2);  // RotationalEquation.maxAngle default, rotational_equation.dart:17
   return J;
+}
+
+__global__ void k_units_plus_one(int* cnt) { if (threadIdx.x == 0 && blockIdx.x == 0) cnt[CT_NUNITS1] = cnt[CT_NUNITS] + 1; }
+__global__ void __launch_bounds__(256) k_zero_tail(int* eRows, const int* nUnits, int cap) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { const int n = *nUnits; if (n <= cap) eRows[n] = 0; }
+}
+
+// cooperative grid size: enough CTAs for the widest level seen last time, never more than can be co-resident
+static int coop_blocks(cannon_world* w, int maxBlocks, long long widthEstimate) {
+  if (widthEstimate <= 0) return maxBlocks;
+  long long b = (widthEstimate + 255) / 256;
+  if (b < 1) b = 1;
+  return (int)std::min<long long>(b, maxBlocks);
 }
 
 // world_class.dart:539-645 without the final velocity update (k_integrate / k_apply_lambda do that)
@@ -1012,13 +1056,15 @@ static int32_t st_solve(cannon_world* w, double dt) {
   BodyArrays B = body_arrays(w);
   ContactArrays C = contact_arrays(w);
   RowArrays R = row_arrays(w);
+  UnitArrays U = unit_arrays(w);
+  JointArrays J = joint_arrays(w);
   int* cnt = w->cnt.p;
   const int nW = w->desc.n_worlds;
   SolveParams P;
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
   P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
   const int gc = grid_for(w, w->contactCap, 256);
-  { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p, w->desc.allow_sleep); }
+  { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p); }
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
   W_TRY(w, scan_exclusive(w->contFlag.p, w->contOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_CONTTOTAL, w->scanTmp, s));
   { g_kernel_launches++; k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n); }
@@ -1026,36 +1072,43 @@ static int32_t st_solve(cannon_world* w, double dt) {
   W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nW + 2) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nW + 1) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nW + 1) * sizeof(double), s));
-  { g_kernel_launches++; k_rows_contacts<<<grid_for(w, w->contactCap, 128), 128, 0, s>>>(B, C, R, P, w->contactCap, w->fricOff.p, w->contOff.p, cnt + CT_FRICTOTAL,
-                                                                 cnt + CT_CONTTOTAL, w->worldRows.p, cnt + CT_OVF_ROWS, w->nJointAccepted,
-                                                                 cnt + CT_NCONTACTROWS); }
-  if (w->nJointEq > 0)
-    { g_kernel_launches++; k_rows_joints<<<grid_for(w, w->nJointEq, 128), 128, 0, s>>>(B, joint_arrays(w), R, P, cnt + CT_NCONTACTROWS, w->worldRows.p, cnt + CT_OVF_ROWS); }
+  UnitSrc Us;
+  Us.colored = P.colored; Us.fricFlag = w->fricFlag.p; Us.contFlag = w->contFlag.p; Us.fricOff = w->fricOff.p; Us.contOff = w->contOff.p;
+  Us.fricTotal = cnt + CT_FRICTOTAL; Us.contTotal = cnt + CT_CONTTOTAL; Us.taskOff = w->taskOff.p; Us.taskCnt = w->taskCnt.p;
+  Us.nTasks = cnt + CT_NTASKS; Us.taskCap = w->taskCap; Us.contactCap = w->contactCap;
+  { g_kernel_launches++; k_units_build<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, C, Us, J, U, nW, w->worldRows.p, cnt + CT_OVF_ROWS); }
   // dependency levels + sweeps: persistent cooperative kernels
   SchedArrays S;
   S.claim = w->claim.p; S.unitLevel = w->unitLevel.p; S.order = w->order.p; S.levelStart = w->levelStart.p; S.nLevels = cnt + CT_NLEVELS;
   S.act0 = w->act0.p; S.act1 = w->act1.p; S.actCount = cnt + CT_ACT0; S.cursor = cnt + CT_CURSOR; S.bar = (unsigned*)(cnt + CT_BAR);
-  S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS; S.nUnitsFixed = -1; S.nUnitsPtr = nullptr;
-  UnitMap U;
-  U.colored = P.colored; U.taskOff = w->taskOff.p; U.taskCnt = w->taskCnt.p; U.nTasks = cnt + CT_NTASKS; U.taskCap = w->taskCap;
-  U.nContacts = cnt + CT_NCONTACTS; U.contactCap = w->contactCap;
+  S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS;
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
+  const long long lastUnits = w->lastUnits, lastLevels = w->lastLevels;
   if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
   {
-    void* args[] = {&R, &S, &U};
+    int colored = P.colored;
+    void* args[] = {&U, &S, &colored};
     g_kernel_launches++;
-    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(coop_blocks(w, w->coopBlocksSched, lastUnits > 0 ? lastUnits / 2 + 1 : 0)), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[6], s);
   W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, sizeof(int), s));
+  { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
+  { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NUNITS, w->unitCap); }
+  { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
+  W_TRY(w, scan_exclusive(w->eRows.p, w->eRowBase.p, cnt + CT_NUNITS1, 0, w->unitCap + 1, nullptr, w->scanTmp, s));
+  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, w->order.p, cnt + CT_OVF_ROWS); }
+  if (w->recordSolveEvents) cudaEventRecord(w->ev[7], s);
   GsStats G;
   G.worldTot = w->worldTot.p; G.worldDone = w->worldDone.p; G.worldIters = w->worldIters.p; G.itersDone = cnt + CT_ITERS;
   {
-    void* args[] = {&R, &B, &S, &U, &P, &G};
+    void* args[] = {&R, &B, &U, &S, &P, &G};
     g_kernel_launches++;
-    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
+    const long long width = (lastUnits > 0 && lastLevels > 0) ? 2 * lastUnits / lastLevels + 1 : 0;
+    if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(coop_blocks(w, w->coopBlocksGsFast, width)), dim3(256), args, 0, s));
+    else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(coop_blocks(w, w->coopBlocksGs, width)), dim3(256), args, 0, s));
   }
-  if (w->recordSolveEvents) cudaEventRecord(w->ev[7], s);
+  if (w->recordSolveEvents) cudaEventRecord(w->ev[10], s);
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }
@@ -1218,6 +1271,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   // keep the pair/task/contact counts of the preceding narrowphase call, clear the solver's
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, 2 * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 2 * sizeof(int), s));
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
   { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
@@ -1229,6 +1283,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   w->prof.n_rows = w->hCnt[CT_NROWS];
   w->prof.n_levels = w->hCnt[CT_NLEVELS];
   w->prof.iterations_done = w->hCnt[CT_ITERS];
+  w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
   if (iterations_done) *iterations_done = w->hCnt[CT_ITERS];
   return CANNON_OK;
 }
@@ -1288,10 +1343,11 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
     if (cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]) == cudaSuccess) { p.solve = ms; p.make_contact_constraints = 0; }
     if (cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]) == cudaSuccess) p.integrate = ms;
     if (cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]) == cudaSuccess) p.schedule_ms = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[6], w->ev[7]) == cudaSuccess) p.gs_ms = ms;
+    if (cudaEventElapsedTime(&ms, w->ev[7], w->ev[10]) == cudaSuccess) p.gs_ms = ms;
     if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;
     p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
     p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
+    w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
   }
   return CANNON_OK;
 }
@@ -1314,17 +1370,49 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   if (!w) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   const int n = w->hCnt[CT_NROWS];
+  const int nu = w->hCnt[CT_NUNITS];
   if (n_rows) *n_rows = n;
   if (cap < n) return fail(w->ctx, CANNON_E_CAPACITY, "row buffer too small");
   if (n == 0) return CANNON_OK;
-  if (body_i) W_TRY(w, cudaMemcpy(body_i, w->rBi.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-  if (body_j) W_TRY(w, cudaMemcpy(body_j, w->rBj.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-  if (B) W_TRY(w, cudaMemcpy(B, w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (invC) W_TRY(w, cudaMemcpy(invC, w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (lambda) W_TRY(w, cudaMemcpy(lambda, w->rLambda.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (level) {
-    if (w->desc.solver_kind == CANNON_SOLVER_REFERENCE_ORDER) W_TRY(w, cudaMemcpy(level, w->unitLevel.p, n * sizeof(int), cudaMemcpyDeviceToHost));
-    else memset(level, 0, n * sizeof(int));
+  // rows live in execution order on the device. REFERENCE_ORDER: unit id == reference row index, so the rows are
+  // returned in the reference's solve order; COLORED: returned in execution order.
+  std::vector<double> hB(n), hC(n), hL(n);
+  std::vector<int> uBi(nu), uBj(nu), uRow(nu), uLvl(nu), uRows(nu);
+  if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
+    std::vector<float4> q0(n), q1(n);
+    std::vector<float> fl(n);
+    W_TRY(w, cudaMemcpy(q0.data(), w->rQ0.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(q1.data(), w->rQ1.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(fl.data(), w->rFlambda.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) { hB[k] = q0[k].w; hC[k] = q1[k].w; hL[k] = fl[k]; }
+  } else {
+    W_TRY(w, cudaMemcpy(hB.data(), w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hC.data(), w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hL.data(), w->rLambda.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  W_TRY(w, cudaMemcpy(uBi.data(), w->uBi.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  W_TRY(w, cudaMemcpy(uBj.data(), w->uBj.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  W_TRY(w, cudaMemcpy(uRow.data(), w->unitRow.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  W_TRY(w, cudaMemcpy(uLvl.data(), w->unitLevel.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  W_TRY(w, cudaMemcpy(uRows.data(), w->uRows.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  int out = 0;
+  const bool refOrder = w->desc.solver_kind == CANNON_SOLVER_REFERENCE_ORDER;
+  std::vector<int> unitsInOrder(nu);
+  if (refOrder) { for (int u = 0; u < nu; u++) unitsInOrder[u] = u; }
+  else {
+    W_TRY(w, cudaMemcpy(unitsInOrder.data(), w->order.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  for (int k = 0; k < nu; k++) {
+    const int u = unitsInOrder[k];
+    for (int q = 0; q < uRows[u] && out < n; q++, out++) {
+      const int r = uRow[u] + q;
+      if (body_i) body_i[out] = uBi[u];
+      if (body_j) body_j[out] = uBj[u];
+      if (B) B[out] = hB[r];
+      if (invC) invC[out] = hC[r];
+      if (lambda) lambda[out] = hL[r];
+      if (level) level[out] = uLvl[u];
+    }
   }
   return CANNON_OK;
 }

@@ -4,7 +4,7 @@
 // order: all FrictionEquations, then all ContactEquations, then the constraints' equations
 // (lib/world/world_class.dart:539-541,562,627-635). Gauss-Seidel is order dependent, so:
 //
-//   REFERENCE_ORDER  rows keep the reference's order and are executed by *dependency levels*: row r gets
+//   REFERENCE_ORDER  units = single rows in the reference's order, executed by *dependency levels*: a row gets
 //                    level 1 + max(level of the previous row touching either of its movable bodies). Rows of
 //                    one level touch disjoint movable bodies, so running them concurrently performs exactly
 //                    the same floating-point operations on exactly the same operands as the sequential
@@ -13,28 +13,49 @@
 //                    rows [f1,f2,n] per contact) and hashed priorities, i.e. a randomised greedy colouring
 //                    with O(max degree) colours (statistical agreement only).
 //
-// Both run as persistent cooperative kernels (one launch per solve) with a hand-rolled grid barrier between
-// levels: launch latency would otherwise dominate (iterations x levels dependent launches).
+// Pipeline: k_units_build (who touches which bodies) -> k_schedule (levels, execution order) ->
+// scan(rows per unit in execution order) -> k_rows_build (rows written *in execution order*, so every sweep
+// streams them with coalesced 128-bit loads) -> k_gs (persistent cooperative kernel: one thread per unit keeps
+// the two bodies' lambda vectors in registers across the unit's rows; grid barrier between levels).
 #pragma once
 #include "k_narrowphase.cuh"
 #include "world.cuh"
 
-enum { ROW_CONTACT = 0, ROW_FRICTION = 1, ROW_ROT = 2, ROW_MOTOR = 3, ROW_OFF = -1 };
+enum { ROW_CONTACT = 0, ROW_FRICTION = 1, ROW_ROT = 2, ROW_MOTOR = 3 };
+enum { SRC_NORMAL = 0, SRC_FRIC1 = 1, SRC_FRIC2 = 2, SRC_JOINT = 3, SRC_TASK = 4 };
 
+// rows in execution order (SoA; float4 vectors so a row is five 128-bit + six 64-bit transactions)
 struct RowArrays {
-  int* nRows;        // rows in storage (device)
-  int *bi, *bj, *kind;
+  int* nRows;        // device count
+  int* kind;
   float4 *n;         // spatial Jacobian of body j (sB); body i gets -n (zero for rotational rows)
   float4 *rA, *rB;   // rotational Jacobians
   float4 *iA, *iB;   // invInertiaWorldSolve * rA / rB, rounded to float like the reference's temp vector
-  double *B, *invC, *eps, *minF, *maxF, *imA, *imB, *lambda;
-  int* flags;        // bit0: body i movable, bit1: body j movable
+  double *B, *invC, *eps, *minF, *maxF, *lambda;
   int rowCap;
+  // COLORED (throughput) mode: the same row packed into five float4 + one float = 84 B, solved in f32 with FMA.
+  // The row order already differs from the reference there, so only statistical agreement is claimed and the
+  // f64 emulation of the Dart VM buys nothing; B / invC are still evaluated in f64 and rounded once.
+  int fast;
+  float4 *q0, *q1, *q2, *q3, *q4;   // (n,B) (rA,invC) (rB,eps) (iA,minF) (iB,maxF)
+  float* flambda;
+};
+
+// units: by unit id (u*) before scheduling, by execution position (e*) after
+struct UnitArrays {
+  int* nUnits;       // device count
+  int *uBi, *uBj, *uFlags, *uRows, *uSrc;   // flags bit0/1: body i/j movable
+  int *eBi, *eBj, *eFlags, *eRowBase;        // eRowBase has nUnits+1 entries (exclusive scan of rows in exec order)
+  double *eImA, *eImB;                       // invMassSolve of the two bodies
+  int* eRows;                                // rows per unit in exec order (scan input)
+  int* unitRow;                              // unit id -> first execution row (debug / multipliers)
+  int unitCap;
 };
 
 struct JointArrays {  // one entry per constraint equation (P2P: 3, hinge: 6), uploaded at set_constraints
   int n;
   const int *bodyA, *bodyB, *kind, *enabled, *rowSlot;  // rowSlot: index among accepted joint rows or -1
+  const int *slotEq;                                    // accepted slot -> equation index
   const float4 *pivotA, *pivotB, *axisA, *axisB;        // local frame
   const float4 *ni;                                     // P2P rows: world x / y / z
   const double *minF, *maxF, *a, *b, *eps, *targetVel;
@@ -55,11 +76,18 @@ struct SolveParams {
 // rigid_body.dart:303-314
 __device__ __forceinline__ bool body_frozen(const BodyArrays& B, int b) { return B.sleep[b] == CANNON_SLEEPING || B.type[b] == CANNON_BODY_KINEMATIC; }
 
+// a body whose solve mass and solve inertia are all zero never changes its vlambda/wlambda: no dependency
+__device__ __forceinline__ bool body_movable(const BodyArrays& B, int b) {
+  if (body_frozen(B, b)) return false;
+  if (B.invMass[b] != 0.0) return true;
+  const float4 r0 = B.iiw0[b], r1 = B.iiw1[b], r2 = B.iiw2[b];
+  return r0.x != 0.f || r0.y != 0.f || r0.z != 0.f || r1.x != 0.f || r1.y != 0.f || r1.z != 0.f || r2.x != 0.f || r2.y != 0.f || r2.z != 0.f;
+}
+
 struct RowBody {
   f3 pos, vel, angvel, force, torque;
   float4 r0, r1, r2;  // invInertiaWorldSolve rows
   double im;          // invMassSolve
-  bool movable;
 };
 __device__ __forceinline__ void load_row_body(const BodyArrays& B, int b, RowBody& r) {
   r.pos = ld3(B.pos[b]); r.vel = ld3(B.vel[b]); r.angvel = ld3(B.angvel[b]);
@@ -71,14 +99,12 @@ __device__ __forceinline__ void load_row_body(const BodyArrays& B, int b, RowBod
     r.im = B.invMass[b];
     r.r0 = B.iiw0[b]; r.r1 = B.iiw1[b]; r.r2 = B.iiw2[b];
   }
-  r.movable = r.im != 0.0 || r.r0.x != 0.f || r.r0.y != 0.f || r.r0.z != 0.f || r.r1.x != 0.f || r.r1.y != 0.f || r.r1.z != 0.f ||
-              r.r2.x != 0.f || r.r2.y != 0.f || r.r2.z != 0.f;
 }
 
 // computeGiMf (equation_class.dart:108-127), computeC (:130-148,172-174) and row store
-__device__ inline void finish_row(const RowArrays& R, int row, int kind, int bi, int bj, const RowBody& A, const RowBody& Bd, const f3& sA,
-                                  const f3& rA, const f3& sB, const f3& rB, double gterm /* -g*a or 0 */, double gw, double b, double eps,
-                                  double minF, double maxF, double h) {
+__device__ inline void finish_row(const RowArrays& R, int row, int kind, const RowBody& A, const RowBody& Bd, const f3& sA, const f3& rA,
+                                  const f3& sB, const f3& rB, double gterm /* -g*a or 0 */, double gw, double b, double eps, double minF,
+                                  double maxF, double h) {
   const f3 iMfi = vscale(A.im, A.force), iMfj = vscale(Bd.im, Bd.force);
   const f3 iTi = mrow_mul(A.r0, A.r1, A.r2, A.torque), iTj = mrow_mul(Bd.r0, Bd.r1, Bd.r2, Bd.torque);
   const double giMf = (vdot(iMfi, sA) + vdot(iTi, rA)) + (vdot(iMfj, sB) + vdot(iTj, rB));
@@ -88,16 +114,19 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, int bi,
   c += vdot(iA, rA);
   c += vdot(iB, rB);
   c += eps;
-  R.bi[row] = bi; R.bj[row] = bj; R.kind[row] = kind;
+  if (R.fast) {
+    R.q0[row] = st3(sB, (float)Bv); R.q1[row] = st3(rA, (float)(1.0 / c)); R.q2[row] = st3(rB, (float)eps);
+    R.q3[row] = st3(iA, (float)minF); R.q4[row] = st3(iB, (float)maxF); R.flambda[row] = 0.f;
+    return;
+  }
+  R.kind[row] = kind;
   R.n[row] = st3(sB); R.rA[row] = st3(rA); R.rB[row] = st3(rB); R.iA[row] = st3(iA); R.iB[row] = st3(iB);
-  R.B[row] = Bv; R.invC[row] = 1.0 / c; R.eps[row] = eps; R.minF[row] = minF; R.maxF[row] = maxF;
-  R.imA[row] = A.im; R.imB[row] = Bd.im; R.lambda[row] = 0.0;
-  R.flags[row] = (A.movable ? 1 : 0) | (Bd.movable ? 2 : 0);
+  R.B[row] = Bv; R.invC[row] = 1.0 / c; R.eps[row] = eps; R.minF[row] = minF; R.maxF[row] = maxF; R.lambda[row] = 0.0;
 }
 
 // per contact: acceptance flags (Solver.addEquation filter, solver.dart:30-34) + wake-up flags (world_class.dart:564-590)
 __global__ void __launch_bounds__(256) k_contact_flags(BodyArrays B, ContactArrays C, int contactCap, int* __restrict__ fricFlag,
-                                                       int* __restrict__ contFlag, int allowSleepWorld) {
+                                                       int* __restrict__ contFlag) {
   const int nc = min(*C.nContacts, contactCap);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int bi = C.bi[c], bj = C.bj[c];
@@ -120,124 +149,69 @@ __global__ void __launch_bounds__(256) k_contact_flags(BodyArrays B, ContactArra
   }
 }
 
-// rows of the contacts: ContactEquation.computeB (contact_equation.dart:34-77), FrictionEquation.computeB
-// (friction_equation.dart:19-47). Row index: reference order [2*fricRank | nF2 + contRank], coloured [3c, 3c+1, 3c+2].
-__global__ void __launch_bounds__(128) k_rows_contacts(BodyArrays B, ContactArrays C, RowArrays R, SolveParams S, int contactCap,
-                                                       const int* __restrict__ fricOff, const int* __restrict__ contOff,
-                                                       const int* __restrict__ fricTotal, const int* __restrict__ contTotal,
-                                                       int* __restrict__ worldRows, int* __restrict__ rowOverflow, int nJointRows,
-                                                       int* __restrict__ nContactRows) {
-  const int nc = min(*C.nContacts, contactCap);
-  const int nF2 = 2 * (*fricTotal);
-  const int nCR = S.colored ? 3 * nc : nF2 + *contTotal;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *nContactRows = nCR;            // joint rows are appended behind by k_rows_joints
-    *R.nRows = nCR + nJointRows;
-    if (nCR + nJointRows > R.rowCap) atomicMax(rowOverflow, nCR + nJointRows);
-  }
-  if (nCR + nJointRows > R.rowCap) return;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-    const int f0 = fricOff[c], c0 = contOff[c];
-    const bool hasF = (c + 1 < nc ? fricOff[c + 1] : *fricTotal) > f0;
-    const bool hasC = (c + 1 < nc ? contOff[c + 1] : *contTotal) > c0;
-    int rowF1, rowF2, rowN;
-    if (S.colored) { rowF1 = 3 * c; rowF2 = 3 * c + 1; rowN = 3 * c + 2; }
-    else { rowF1 = 2 * f0; rowF2 = 2 * f0 + 1; rowN = nF2 + c0; }
-    if (S.colored) {
-      if (!hasF) { R.kind[rowF1] = ROW_OFF; R.kind[rowF2] = ROW_OFF; }
-      if (!hasC) R.kind[rowN] = ROW_OFF;
-    }
-    C.row[c] = hasC ? rowN : -1;
-    if (!hasC && !hasF) continue;
-    const int bi = C.bi[c], bj = C.bj[c];
-    RowBody A, Bd;
-    load_row_body(B, bi, A);
-    load_row_body(B, bj, Bd);
-    const f3 ri = ld3(C.ri[c]), rj = ld3(C.rj[c]), ni = ld3(C.ni[c]);
-    const double h = S.dt;
-    if (hasC) {
-      const f3 rixn = vcross(ri, ni), rjxn = vcross(rj, ni);
-      f3 pen = vadd(Bd.pos, rj);
-      pen = vsub(pen, A.pos);
-      pen = vsub(pen, ri);
-      const double g = vdot(ni, pen);
-      const double ePlusOne = C.rest[c] + 1;
-      const double gw = ePlusOne * vdot(Bd.vel, ni) - ePlusOne * vdot(A.vel, ni) + vdot(Bd.angvel, rjxn) - vdot(A.angvel, rixn);
-      finish_row(R, rowN, ROW_CONTACT, bi, bj, A, Bd, vneg(ni), vneg(rixn), ni, rjxn, -g * C.ca[c], gw, C.cb[c], C.ceps[c], 0.0, 1e6, h);
-      atomicAdd(&worldRows[S.nWorlds > 1 ? B.world[bi] : 0], 1);
-    }
-    if (hasF) {
-      f3 t1, t2;
-      vtangents(ni, t1, t2);
-      const double slip = C.slip[c];
-      for (int k = 0; k < 2; k++) {
-        const f3 t = k ? t2 : t1;
-        const f3 rixt = vcross(ri, t), rjxt = vcross(rj, t);
-        const f3 sA = vneg(t), rA = vneg(rixt);
-        const double gw = (vdot(A.vel, sA) + vdot(A.angvel, rA)) + (vdot(Bd.vel, t) + vdot(Bd.angvel, rjxt));
-        finish_row(R, k ? rowF2 : rowF1, ROW_FRICTION, bi, bj, A, Bd, sA, rA, t, rjxt, 0.0, gw, C.fb[c], C.feps[c], -slip, slip, h);
-      }
-      atomicAdd(&worldRows[S.nWorlds > 1 ? B.world[bi] : 0], 2);
-    }
-  }
+struct UnitSrc {  // what the units are made from
+  int colored;
+  const int* fricFlag; const int* contFlag;
+  const int* fricOff; const int* contOff;   // exclusive scans over contacts
+  const int* fricTotal; const int* contTotal;
+  const int* taskOff; const int* taskCnt; const int* nTasks; int taskCap;   // resolver tasks = manifolds
+  int contactCap;
+};
+
+__device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& B, int u, int bi, int bj, int rows, int src, int nWorlds,
+                                         int* __restrict__ worldRows) {
+  U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src;
+  U.uFlags[u] = rows > 0 ? ((body_movable(B, bi) ? 1 : 0) | (body_movable(B, bj) ? 2 : 0)) : 0;
+  if (rows > 0) atomicAdd(&worldRows[nWorlds > 1 ? B.world[bi] : 0], rows);
 }
 
-// Constraint.update() + equation rows of the joints (point_to_point_constraint.dart:68-83, hinge_constraint.dart:79-104,
-// rotational_equation.dart:34-58, rotational_motor_equation.dart:17-33). One thread per constraint equation.
-__global__ void __launch_bounds__(128) k_rows_joints(BodyArrays B, JointArrays J, RowArrays R, SolveParams S, const int* __restrict__ nContactRows, int* __restrict__ worldRows,
-                                                     int* __restrict__ rowOverflow) {
-  const int base = *nContactRows;
-  if (base + J.nAccepted > R.rowCap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(rowOverflow, base + J.nAccepted);
-    return;
-  }
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < J.n; e += gridDim.x * blockDim.x) {
-    const int slot = J.rowSlot[e];
-    if (slot < 0) continue;
-    const int row = base + slot;
-    const int bi = J.bodyA[e], bj = J.bodyB[e];
-    RowBody A, Bd;
-    load_row_body(B, bi, A);
-    load_row_body(B, bj, Bd);
-    const q4 qa = ldq(B.quat[bi]), qb = ldq(B.quat[bj]);
-    const double h = S.dt;
-    const int kind = J.kind[e];
-    f3 zero; zero.x = zero.y = zero.z = 0.f;
-    if (kind == ROW_CONTACT) {
-      const f3 ri = qrot(qa, ld3(J.pivotA[e])), rj = qrot(qb, ld3(J.pivotB[e]));
-      const f3 ni = ld3(J.ni[e]);
-      const f3 rixn = vcross(ri, ni), rjxn = vcross(rj, ni);
-      f3 pen = vadd(Bd.pos, rj);
-      pen = vsub(pen, A.pos);
-      pen = vsub(pen, ri);
-      const double g = vdot(ni, pen);
-      const double ePlusOne = 0.0 + 1;
-      const double gw = ePlusOne * vdot(Bd.vel, ni) - ePlusOne * vdot(A.vel, ni) + vdot(Bd.angvel, rjxn) - vdot(A.angvel, rixn);
-      finish_row(R, row, ROW_CONTACT, bi, bj, A, Bd, vneg(ni), vneg(rixn), ni, rjxn, -g * J.a[e], gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
-    } else if (kind == ROW_ROT) {
-      const f3 worldAxisA = qrot(qa, ld3(J.axisA[e])), worldAxisB = qrot(qb, ld3(J.axisB[e]));
-      f3 t1, t2;
-      vtangents(worldAxisA, t1, t2);
-      const f3 axA = (e - J.first[e] == 3) ? t1 : t2;  // rotationalEquation1 / rotationalEquation2
-      const f3 nixnj = vcross(axA, worldAxisB), njxni = vcross(worldAxisB, axA);
-      const double g = J.cosMaxAngle - vdot(axA, worldAxisB);
-      const double gw = (vdot(A.vel, zero) + vdot(A.angvel, njxni)) + (vdot(Bd.vel, zero) + vdot(Bd.angvel, nixnj));
-      finish_row(R, row, ROW_ROT, bi, bj, A, Bd, zero, njxni, zero, nixnj, -g * J.a[e], gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
-    } else {
-      const f3 axA = qrot(qa, ld3(J.axisA[e])), axB = qrot(qb, ld3(J.axisB[e]));
-      const f3 rB = vneg(axB);
-      const double gw = ((vdot(A.vel, zero) + vdot(A.angvel, axA)) + (vdot(Bd.vel, zero) + vdot(Bd.angvel, rB))) - J.targetVel[e];
-      finish_row(R, row, ROW_MOTOR, bi, bj, A, Bd, zero, axA, zero, rB, 0.0, gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
+// unit table. Reference order: unit id == reference row index [2*fricRank | nF2 + contRank | joints].
+// Coloured: unit id == task id (manifold) followed by the joint rows.
+__global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, UnitArrays U, int nWorlds,
+                                                     int* __restrict__ worldRows, int* __restrict__ unitOverflow) {
+  const int nc = min(*C.nContacts, S.contactCap);
+  const int nF2 = 2 * (*S.fricTotal), nC = *S.contTotal;
+  const int nt = min(*S.nTasks, S.taskCap);
+  const int jointBase = S.colored ? nt : nF2 + nC;
+  const int nUnits = jointBase + J.nAccepted;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) { *U.nUnits = nUnits; if (nUnits > U.unitCap) atomicMax(unitOverflow, nUnits); }
+  if (nUnits > U.unitCap) return;
+  if (S.colored) {
+    for (int t = tid; t < nt; t += nth) {
+      const int m = S.taskCnt[t];
+      int rows = 0, bi = 0, bj = 0;
+      if (m > 0) {
+        const int c0 = S.taskOff[t], c1 = c0 + m;
+        if (c1 <= nc) {
+          bi = C.bi[c0]; bj = C.bj[c0];
+          for (int c = c0; c < c1; c++) rows += S.contFlag[c] + 2 * S.fricFlag[c];
+        }
+      }
+      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows);
     }
-    atomicAdd(&worldRows[S.nWorlds > 1 ? B.world[bi] : 0], 1);
+  } else {
+    for (int c = tid; c < nc; c += nth) {
+      const int bi = C.bi[c], bj = C.bj[c];
+      if (S.fricFlag[c]) {
+        const int f0 = S.fricOff[c];
+        put_unit(U, B, 2 * f0, bi, bj, 1, c * 8 + SRC_FRIC1, nWorlds, worldRows);
+        put_unit(U, B, 2 * f0 + 1, bi, bj, 1, c * 8 + SRC_FRIC2, nWorlds, worldRows);
+      }
+      if (S.contFlag[c]) put_unit(U, B, nF2 + S.contOff[c], bi, bj, 1, c * 8 + SRC_NORMAL, nWorlds, worldRows);
+    }
   }
-
+  for (int s = tid; s < J.nAccepted; s += nth) {
+    const int e = J.slotEq[s];
+    put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
+  }
 }
 
 // ---- grid barrier -----------------------------------------------------------------------------------
 // Monotonic-counter barrier for cooperative (co-resident) launches. `bar` is zeroed before the launch.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
   __syncthreads();
+  if (gridDim.x == 1) return;  // single-CTA launches (small worlds) only need the block barrier
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
     __threadfence();
@@ -251,8 +225,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
 struct SchedArrays {
   unsigned long long* claim;  // per body
   int* unitLevel;             // per unit, -1 = unassigned
-  int* order;                 // units sorted by level
-  int* levelStart;            // [maxLevels+1]
+  int* order;                 // execution position -> unit id
+  int* levelStart;            // [maxLevels+1] execution positions
   int* nLevels;
   int *act0, *act1;           // active (unassigned) unit lists
   int* actCount;              // [2]
@@ -260,42 +234,15 @@ struct SchedArrays {
   unsigned* bar;
   int maxLevels;
   int* levelOverflow;
-  // units
-  int nUnitsFixed;            // <0: read from nUnitsPtr
-  const int* nUnitsPtr;
 };
-
-// unit -> its rows. reference mode: unit == row. coloured: unit == resolver task (rows 3*taskOff .. 3*(taskOff+cnt)) or a joint row.
-struct UnitMap {
-  int colored;
-  const int* taskOff;  // per task: first contact
-  const int* taskCnt;
-  const int* nTasks;
-  int taskCap;
-  const int* nContacts;
-  int contactCap;
-};
-__device__ __forceinline__ void unit_rows(const UnitMap& U, int u, int nRows, int& r0, int& r1) {
-  if (!U.colored) { r0 = u; r1 = u + 1; return; }
-  const int nt = min(*U.nTasks, U.taskCap);
-  if (u < nt) { r0 = 3 * U.taskOff[u]; r1 = r0 + 3 * U.taskCnt[u]; }
-  else { r0 = 3 * min(*U.nContacts, U.contactCap) + (u - nt); r1 = r0 + 1; }
-  if (r1 > nRows) r1 = nRows;
-}
-__device__ __forceinline__ int unit_count(const UnitMap& U, int nRows) {
-  if (!U.colored) return nRows;
-  const int nt = min(*U.nTasks, U.taskCap);
-  return nt + (nRows - 3 * min(*U.nContacts, U.contactCap));
-}
 
 // Dependency levels by repeated "claim the bodies with the smallest pending priority": a unit is released in
 // the round in which it holds the minimum on all of its movable bodies, which is exactly
 // level(u) = 1 + max(level of earlier units sharing a movable body). Keys carry the round in the high bits so
 // stale claims of earlier rounds always lose the atomicMin (no clearing pass).
-__global__ void __launch_bounds__(256) k_schedule(RowArrays R, SchedArrays S, UnitMap U) {
+__global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, int colored) {
   unsigned epoch = 0;
-  const int nRows = min(*R.nRows, R.rowCap);
-  const int nUnits = unit_count(U, nRows);
+  const int nUnits = min(*U.nUnits, U.unitCap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int u = tid; u < nUnits; u += nth) { S.act0[u] = u; S.unitLevel[u] = -1; }
   if (tid == 0) { S.actCount[0] = nUnits; S.actCount[1] = 0; *S.cursor = 0; S.levelStart[0] = 0; }
@@ -311,33 +258,21 @@ __global__ void __launch_bounds__(256) k_schedule(RowArrays R, SchedArrays S, Un
     const unsigned long long hi = (unsigned long long)(0x7fffffffu - (unsigned)round) << 32;
     for (int a = tid; a < nAct; a += nth) {
       const int u = __ldcg(&act[a]);
-      const unsigned pri = U.colored ? (unsigned)u * 2654435761u : (unsigned)u;
+      const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
       const unsigned long long key = hi | pri;
-      int r0, r1;
-      unit_rows(U, u, nRows, r0, r1);
-      for (int r = r0; r < r1; r++) {
-        if (R.kind[r] == ROW_OFF) continue;
-        const int fl = R.flags[r];
-        if (fl & 1) atomicMin(&S.claim[R.bi[r]], key);
-        if (fl & 2) atomicMin(&S.claim[R.bj[r]], key);
-        if (U.colored) break;  // all rows of a manifold share the same two bodies
-      }
+      const int fl = U.uFlags[u];
+      if (fl & 1) atomicMin(&S.claim[U.uBi[u]], key);
+      if (fl & 2) atomicMin(&S.claim[U.uBj[u]], key);
     }
     grid_barrier(S.bar, epoch);
     for (int a = tid; a < nAct; a += nth) {
       const int u = __ldcg(&act[a]);
-      const unsigned pri = U.colored ? (unsigned)u * 2654435761u : (unsigned)u;
+      const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
       const unsigned long long key = hi | pri;
-      int r0, r1;
-      unit_rows(U, u, nRows, r0, r1);
+      const int fl = U.uFlags[u];
       bool win = true;
-      for (int r = r0; r < r1; r++) {
-        if (R.kind[r] == ROW_OFF) continue;
-        const int fl = R.flags[r];
-        if ((fl & 1) && __ldcg(&S.claim[R.bi[r]]) != key) win = false;
-        if ((fl & 2) && __ldcg(&S.claim[R.bj[r]]) != key) win = false;
-        if (U.colored) break;
-      }
+      if ((fl & 1) && __ldcg(&S.claim[U.uBi[u]]) != key) win = false;
+      if ((fl & 2) && __ldcg(&S.claim[U.uBj[u]]) != key) win = false;
       if (win) {
         S.unitLevel[u] = round;
         S.order[atomicAdd(S.cursor, 1)] = u;
@@ -354,6 +289,117 @@ __global__ void __launch_bounds__(256) k_schedule(RowArrays R, SchedArrays S, Un
   if (tid == 0) *S.nLevels = round;
 }
 
+// rows per unit in execution order (input of the row-base scan) + per-unit execution data
+__global__ void __launch_bounds__(256) k_exec_units(BodyArrays B, UnitArrays U, const int* __restrict__ order) {
+  const int nUnits = min(*U.nUnits, U.unitCap);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
+    const int u = order[a];
+    const int bi = U.uBi[u], bj = U.uBj[u];
+    U.eRows[a] = U.uRows[u];
+    U.eBi[a] = bi; U.eBj[a] = bj; U.eFlags[a] = U.uFlags[u];
+    U.eImA[a] = body_frozen(B, bi) ? 0.0 : B.invMass[bi];
+    U.eImB[a] = body_frozen(B, bj) ? 0.0 : B.invMass[bj];
+  }
+}
+
+// ContactEquation.computeB (contact_equation.dart:34-77)
+__device__ __forceinline__ void build_normal_row(const RowArrays& R, int row, const RowBody& A, const RowBody& Bd, const f3& ri, const f3& rj,
+                                                 const f3& ni, double restitution, double a, double b, double eps, double minF, double maxF, double h) {
+  const f3 rixn = vcross(ri, ni), rjxn = vcross(rj, ni);
+  f3 pen = vadd(Bd.pos, rj);
+  pen = vsub(pen, A.pos);
+  pen = vsub(pen, ri);
+  const double g = vdot(ni, pen);
+  const double ePlusOne = restitution + 1;
+  const double gw = ePlusOne * vdot(Bd.vel, ni) - ePlusOne * vdot(A.vel, ni) + vdot(Bd.angvel, rjxn) - vdot(A.angvel, rixn);
+  finish_row(R, row, ROW_CONTACT, A, Bd, vneg(ni), vneg(rixn), ni, rjxn, -g * a, gw, b, eps, minF, maxF, h);
+}
+// FrictionEquation.computeB (friction_equation.dart:19-47)
+__device__ __forceinline__ void build_friction_row(const RowArrays& R, int row, const RowBody& A, const RowBody& Bd, const f3& ri, const f3& rj,
+                                                   const f3& t, double b, double eps, double slip, double h) {
+  const f3 rixt = vcross(ri, t), rjxt = vcross(rj, t);
+  const f3 sA = vneg(t), rA = vneg(rixt);
+  const double gw = (vdot(A.vel, sA) + vdot(A.angvel, rA)) + (vdot(Bd.vel, t) + vdot(Bd.angvel, rjxt));
+  finish_row(R, row, ROW_FRICTION, A, Bd, sA, rA, t, rjxt, 0.0, gw, b, eps, -slip, slip, h);
+}
+
+// Constraint.update() + joint equation rows (point_to_point_constraint.dart:68-83, hinge_constraint.dart:79-104,
+// rotational_equation.dart:34-58, rotational_motor_equation.dart:17-33)
+__device__ inline void build_joint_row(const RowArrays& R, int row, const BodyArrays& B, const JointArrays& J, int e, const RowBody& A,
+                                       const RowBody& Bd, double h) {
+  const int bi = J.bodyA[e], bj = J.bodyB[e];
+  const q4 qa = ldq(B.quat[bi]), qb = ldq(B.quat[bj]);
+  const int kind = J.kind[e];
+  f3 zero; zero.x = zero.y = zero.z = 0.f;
+  if (kind == ROW_CONTACT) {
+    const f3 ri = qrot(qa, ld3(J.pivotA[e])), rj = qrot(qb, ld3(J.pivotB[e]));
+    build_normal_row(R, row, A, Bd, ri, rj, ld3(J.ni[e]), 0.0, J.a[e], J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
+  } else if (kind == ROW_ROT) {
+    const f3 worldAxisA = qrot(qa, ld3(J.axisA[e])), worldAxisB = qrot(qb, ld3(J.axisB[e]));
+    f3 t1, t2;
+    vtangents(worldAxisA, t1, t2);
+    const f3 axA = (e - J.first[e] == 3) ? t1 : t2;  // rotationalEquation1 / rotationalEquation2
+    const f3 nixnj = vcross(axA, worldAxisB), njxni = vcross(worldAxisB, axA);
+    const double g = J.cosMaxAngle - vdot(axA, worldAxisB);
+    const double gw = (vdot(A.vel, zero) + vdot(A.angvel, njxni)) + (vdot(Bd.vel, zero) + vdot(Bd.angvel, nixnj));
+    finish_row(R, row, ROW_ROT, A, Bd, zero, njxni, zero, nixnj, -g * J.a[e], gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
+  } else {
+    const f3 axA = qrot(qa, ld3(J.axisA[e])), axB = qrot(qb, ld3(J.axisB[e]));
+    const f3 rB = vneg(axB);
+    const double gw = ((vdot(A.vel, zero) + vdot(A.angvel, axA)) + (vdot(Bd.vel, zero) + vdot(Bd.angvel, rB))) - J.targetVel[e];
+    finish_row(R, row, ROW_MOTOR, A, Bd, zero, axA, zero, rB, 0.0, gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
+  }
+}
+
+// rows, written at their execution positions: one thread per unit in execution order
+__global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, UnitArrays U, RowArrays R,
+                                                    SolveParams P, const int* __restrict__ order, int* __restrict__ rowOverflow) {
+  const int nUnits = min(*U.nUnits, U.unitCap);
+  const int nRows = U.eRowBase[nUnits];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *R.nRows = nRows; if (nRows > R.rowCap) atomicMax(rowOverflow, nRows); }
+  if (nRows > R.rowCap) return;
+  const double h = P.dt;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
+    const int u = order[a];
+    int row = U.eRowBase[a];
+    U.unitRow[u] = row;
+    if (U.eRows[a] == 0) continue;
+    const int src = U.uSrc[u], kind = src & 7, idx = src >> 3;
+    RowBody A, Bd;
+    load_row_body(B, U.eBi[a], A);
+    load_row_body(B, U.eBj[a], Bd);
+    if (kind == SRC_JOINT) {
+      build_joint_row(R, row, B, J, idx, A, Bd, h);
+    } else if (kind == SRC_TASK) {
+      const int c0 = S.taskOff[idx], c1 = c0 + S.taskCnt[idx];
+      for (int c = c0; c < c1; c++) {
+        const f3 ri = ld3(C.ri[c]), rj = ld3(C.rj[c]), ni = ld3(C.ni[c]);
+        if (S.fricFlag[c]) {
+          f3 t1, t2;
+          vtangents(ni, t1, t2);
+          build_friction_row(R, row++, A, Bd, ri, rj, t1, C.fb[c], C.feps[c], C.slip[c], h);
+          build_friction_row(R, row++, A, Bd, ri, rj, t2, C.fb[c], C.feps[c], C.slip[c], h);
+        }
+        if (S.contFlag[c]) {
+          C.row[c] = row;
+          build_normal_row(R, row++, A, Bd, ri, rj, ni, C.rest[c], C.ca[c], C.cb[c], C.ceps[c], 0.0, 1e6, h);
+        }
+      }
+    } else {
+      const int c = idx;
+      const f3 ri = ld3(C.ri[c]), rj = ld3(C.rj[c]), ni = ld3(C.ni[c]);
+      if (kind == SRC_NORMAL) {
+        C.row[c] = row;
+        build_normal_row(R, row, A, Bd, ri, rj, ni, C.rest[c], C.ca[c], C.cb[c], C.ceps[c], 0.0, 1e6, h);
+      } else {
+        f3 t1, t2;
+        vtangents(ni, t1, t2);
+        build_friction_row(R, row, A, Bd, ri, rj, kind == SRC_FRIC1 ? t1 : t2, C.fb[c], C.feps[c], C.slip[c], h);
+      }
+    }
+  }
+}
+
 struct GsStats {
   double* worldTot;     // per world: sum |delta lambda| of the current iteration
   int* worldDone;       // per world: 1 once the tolerance test passed (gs_solver.dart:105)
@@ -361,40 +407,21 @@ struct GsStats {
   int* itersDone;       // max over worlds
 };
 
-// one GS update of row r (gs_solver.dart:80-102 + equation_class.dart:95-105,151-169)
-__device__ __forceinline__ double gs_row(const RowArrays& R, const BodyArrays& B, int r) {
-  const int kind = R.kind[r];
-  const int bi = R.bi[r], bj = R.bj[r];
-  const int fl = R.flags[r];
-  const f3 n = ld3(R.n[r]), rA = ld3(R.rA[r]), rB = ld3(R.rB[r]);
-  f3 sA;
-  if (kind == ROW_ROT || kind == ROW_MOTOR) { sA.x = sA.y = sA.z = 0.f; } else sA = vneg(n);
-  f3 vA = ld3(__ldcg(&B.vlam[bi])), wA = ld3(__ldcg(&B.wlam[bi]));
-  f3 vB = ld3(__ldcg(&B.vlam[bj])), wB = ld3(__ldcg(&B.wlam[bj]));
-  const double gwlambda = (vdot(vA, sA) + vdot(wA, rA)) + (vdot(vB, n) + vdot(wB, rB));
-  const double lambdaj = R.lambda[r];
-  double dl = R.invC[r] * (R.B[r] - gwlambda - R.eps[r] * lambdaj);
-  const double minF = R.minF[r], maxF = R.maxF[r];
-  if (lambdaj + dl < minF) dl = minF - lambdaj;
-  else if (lambdaj + dl > maxF) dl = maxF - lambdaj;
-  R.lambda[r] = lambdaj + dl;
-  if (fl & 1) {
-    vA = vaddscaled(vA, R.imA[r] * dl, sA);
-    wA = vaddscaled(wA, dl, ld3(R.iA[r]));
-    B.vlam[bi] = st3(vA);
-    B.wlam[bi] = st3(wA);
-  }
-  if (fl & 2) {
-    vB = vaddscaled(vB, R.imB[r] * dl, n);
-    wB = vaddscaled(wB, dl, ld3(R.iB[r]));
-    B.vlam[bj] = st3(vB);
-    B.wlam[bj] = st3(wB);
-  }
-  return dl > 0.0 ? dl : -dl;
+struct RowData {
+  float4 n, rA, rB, iA, iB;
+  double B, invC, eps, minF, maxF, lambda;
+  int kind;
+};
+__device__ __forceinline__ void load_row(const RowArrays& R, int r, RowData& d) {
+  d.n = R.n[r]; d.rA = R.rA[r]; d.rB = R.rB[r]; d.iA = R.iA[r]; d.iB = R.iB[r];
+  d.B = R.B[r]; d.invC = R.invC[r]; d.eps = R.eps[r]; d.minF = R.minF[r]; d.maxF = R.maxF[r]; d.lambda = R.lambda[r];
+  d.kind = R.kind[r];
 }
 
-__global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, SchedArrays S, UnitMap U, SolveParams P, GsStats G) {
+// persistent cooperative kernel: all iterations x levels of GSSolver.solve (gs_solver.dart:76-108)
+__global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
   __shared__ double s_red[8];
+  __shared__ int s_any;
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -407,19 +434,48 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, SchedArra
     for (int lvl = 0; lvl < nLevels; lvl++) {
       const int a0 = S.levelStart[lvl], a1 = S.levelStart[lvl + 1];
       for (int a = a0 + tid; a < a1; a += nth) {
-        const int u = S.order[a];
-        int r0, r1;
-        unit_rows(U, u, nRows, r0, r1);
-        for (int r = r0; r < r1; r++) {
-          if (R.kind[r] == ROW_OFF) continue;
-          if (batch) {
-            const int w = B.world[R.bi[r]];
-            if (__ldcg(&G.worldDone[w])) continue;
-            atomicAdd(&G.worldTot[w], gs_row(R, B, r));
-          } else {
-            local += gs_row(R, B, r);
-          }
+        const int r0 = U.eRowBase[a], r1 = U.eRowBase[a + 1];
+        if (r0 == r1) continue;
+        const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
+        int w = 0;
+        if (batch) {
+          w = B.world[bi];
+          if (__ldcg(&G.worldDone[w])) continue;
         }
+        const double imA = U.eImA[a], imB = U.eImB[a];
+        // the two bodies' lambda vectors stay in registers across the unit's rows (gs_solver.dart:88-102,
+        // equation_class.dart:95-105,151-169); every update rounds to float exactly like the reference's stores
+        f3 vA = ld3(__ldcg(&B.vlam[bi])), wA = ld3(__ldcg(&B.wlam[bi]));
+        f3 vB = ld3(__ldcg(&B.vlam[bj])), wB = ld3(__ldcg(&B.wlam[bj]));
+        double acc = 0.0;
+        RowData d, nx;
+        load_row(R, r0, d);
+        nx = d;
+        for (int r = r0; r < r1; r++) {
+          if (r + 1 < r1) load_row(R, r + 1, nx);  // software prefetch of the next row
+          const f3 n = ld3(d.n), rA = ld3(d.rA), rB = ld3(d.rB);
+          f3 sA;
+          if (d.kind == ROW_ROT || d.kind == ROW_MOTOR) { sA.x = sA.y = sA.z = 0.f; } else sA = vneg(n);
+          const double gwlambda = (vdot(vA, sA) + vdot(wA, rA)) + (vdot(vB, n) + vdot(wB, rB));
+          double dl = d.invC * (d.B - gwlambda - d.eps * d.lambda);
+          if (d.lambda + dl < d.minF) dl = d.minF - d.lambda;
+          else if (d.lambda + dl > d.maxF) dl = d.maxF - d.lambda;
+          R.lambda[r] = d.lambda + dl;
+          if (fl & 1) {
+            vA = vaddscaled(vA, imA * dl, sA);
+            wA = vaddscaled(wA, dl, ld3(d.iA));
+          }
+          if (fl & 2) {
+            vB = vaddscaled(vB, imB * dl, n);
+            wB = vaddscaled(wB, dl, ld3(d.iB));
+          }
+          acc += dl > 0.0 ? dl : -dl;
+          d = nx;
+        }
+        if (fl & 1) { B.vlam[bi] = st3(vA); B.wlam[bi] = st3(wA); }
+        if (fl & 2) { B.vlam[bj] = st3(vB); B.wlam[bj] = st3(wB); }
+        if (batch) atomicAdd(&G.worldTot[w], acc);
+        else local += acc;
       }
       grid_barrier(S.bar, epoch);
     }
@@ -440,7 +496,6 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, SchedArra
       grid_barrier(S.bar, epoch);
       if (tid == 0) G.worldTot[0] = 0.0;
     } else {
-      __shared__ int s_any;
       if (threadIdx.x == 0) s_any = 0;
       __syncthreads();
       int anyLive = 0;
@@ -453,6 +508,105 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, SchedArra
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
       if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[P.nWorlds], 1);  // slot nWorlds: "some world still iterating"
+      grid_barrier(S.bar, epoch);
+      allDone = __ldcg(&G.worldDone[P.nWorlds]) == 0;
+      grid_barrier(S.bar, epoch);
+      if (tid == 0) G.worldDone[P.nWorlds] = 0;
+    }
+    if (allDone) break;
+  }
+  if (tid == 0) *G.itersDone = iter;
+}
+
+
+// ---- COLORED mode sweep: f32 + FMA, one thread per manifold, lambdas in registers ---------------------------
+__device__ __forceinline__ float dot3f(const float4& a, float bx, float by, float bz) { return fmaf(a.z, bz, fmaf(a.y, by, a.x * bx)); }
+
+__global__ void __launch_bounds__(256, 4) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
+  __shared__ double s_red[8];
+  __shared__ int s_any;
+  unsigned epoch = 0;
+  const int nRows = min(*R.nRows, R.rowCap);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
+  const int nLevels = *S.nLevels;
+  const bool batch = P.nWorlds > 1;
+  int iter = 0;
+  for (; iter != P.maxIter; iter++) {
+    double local = 0.0;
+    for (int lvl = 0; lvl < nLevels; lvl++) {
+      const int a0 = S.levelStart[lvl], a1 = S.levelStart[lvl + 1];
+      for (int a = a0 + tid; a < a1; a += nth) {
+        const int r0 = U.eRowBase[a], r1 = U.eRowBase[a + 1];
+        if (r0 == r1) continue;
+        const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
+        int w = 0;
+        if (batch) {
+          w = B.world[bi];
+          if (__ldcg(&G.worldDone[w])) continue;
+        }
+        const float imA = (float)U.eImA[a], imB = (float)U.eImB[a];
+        float4 vA = __ldcg(&B.vlam[bi]), wA = __ldcg(&B.wlam[bi]);
+        float4 vB = __ldcg(&B.vlam[bj]), wB = __ldcg(&B.wlam[bj]);
+        float acc = 0.f;
+        for (int r = r0; r < r1; r++) {
+          const float4 q0 = R.q0[r], q1 = R.q1[r], q2 = R.q2[r], q3 = R.q3[r], q4 = R.q4[r];
+          const float lam = R.flambda[r];
+          // G*W_lambda with G = [-n, rA, n, rB]
+          float gw = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
+          gw += dot3f(q1, wA.x, wA.y, wA.z);
+          gw += dot3f(q2, wB.x, wB.y, wB.z);
+          float dl = q1.w * (q0.w - gw - q2.w * lam);
+          if (lam + dl < q3.w) dl = q3.w - lam;
+          else if (lam + dl > q4.w) dl = q4.w - lam;
+          R.flambda[r] = lam + dl;
+          if (fl & 1) {
+            const float s = -imA * dl;
+            vA.x = fmaf(s, q0.x, vA.x); vA.y = fmaf(s, q0.y, vA.y); vA.z = fmaf(s, q0.z, vA.z);
+            wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+          }
+          if (fl & 2) {
+            const float s = imB * dl;
+            vB.x = fmaf(s, q0.x, vB.x); vB.y = fmaf(s, q0.y, vB.y); vB.z = fmaf(s, q0.z, vB.z);
+            wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+          }
+          acc += fabsf(dl);
+        }
+        if (fl & 1) { B.vlam[bi] = vA; B.wlam[bi] = wA; }
+        if (fl & 2) { B.vlam[bj] = vB; B.wlam[bj] = wB; }
+        if (batch) atomicAdd(&G.worldTot[w], (double)acc);
+        else local += (double)acc;
+      }
+      grid_barrier(S.bar, epoch);
+    }
+    bool allDone;
+    if (!batch) {
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_red[k];
+        atomicAdd(&G.worldTot[0], t);
+      }
+      grid_barrier(S.bar, epoch);
+      const double tot = __ldcg(&G.worldTot[0]);
+      allDone = tot * tot < P.tol2;
+      grid_barrier(S.bar, epoch);
+      if (tid == 0) G.worldTot[0] = 0.0;
+    } else {
+      if (threadIdx.x == 0) s_any = 0;
+      __syncthreads();
+      int anyLive = 0;
+      for (int w = tid; w < P.nWorlds; w += nth) {
+        if (G.worldDone[w]) continue;
+        const double tot = __ldcg(&G.worldTot[w]);
+        if (tot * tot < P.tol2) { G.worldDone[w] = 1; G.worldIters[w] = iter; }
+        else { anyLive = 1; G.worldTot[w] = 0.0; }
+      }
+      if (anyLive) atomicOr(&s_any, 1);
+      __syncthreads();
+      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[P.nWorlds], 1);
       grid_barrier(S.bar, epoch);
       allDone = __ldcg(&G.worldDone[P.nWorlds]) == 0;
       grid_barrier(S.bar, epoch);
