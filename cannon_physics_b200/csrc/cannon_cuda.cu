@@ -19,6 +19,7 @@
 #include "k_body.cuh"
 #include "k_broadphase.cuh"
 #include "k_narrowphase.cuh"
+#include "k_sat_warp.cuh"
 #include "k_solver.cuh"
 #include "world.cuh"
 
@@ -143,6 +144,7 @@ struct cannon_world {
   int pairCap = 0;
   // device: narrowphase
   DBuf<int> pairTasks, pairTaskOff, taskPair, taskInfo, bucket, taskCnt, taskRaw, taskOff;
+  DBuf<unsigned long long> pairMask;
   DBuf<int2> taskCell;
   DBuf<float4> rawRi, rawRj, rawNi;
   int taskCap = 0, contactCap = 0;
@@ -344,7 +346,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
   REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
-  REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
+  REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairMask); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
   REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
@@ -586,7 +588,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   w->maxLevels = std::min(rowCap, 1 << 20);
 #define RES(buf, cnt) W_TRY(w, w->buf.reserve((size_t)(cnt)))
   RES(p1, pairCap); RES(p2, pairCap); RES(q1, pairCap); RES(q2, pairCap); RES(keep, pairCap); RES(keepOff, pairCap);
-  RES(pairTasks, pairCap); RES(pairTaskOff, pairCap);
+  RES(pairTasks, pairCap); RES(pairTaskOff, pairCap); RES(pairMask, pairCap);
   RES(taskPair, taskCap); RES(taskInfo, taskCap); RES(taskCell, taskCap); RES(bucket, taskCap); RES(taskCnt, taskCap); RES(taskRaw, taskCap);
   RES(taskOff, taskCap);
   RES(rawRi, contactCap); RES(rawRj, contactCap); RES(rawNi, contactCap);
@@ -949,7 +951,7 @@ static NpArrays np_arrays(cannon_world* w) {
   NpArrays A;
   int* cnt = w->cnt.p;
   A.p1 = w->p1.p; A.p2 = w->p2.p; A.nPairs = cnt + CT_NPAIRS;
-  A.pairTasks = w->pairTasks.p; A.pairTaskOff = w->pairTaskOff.p; A.nTasks = cnt + CT_NTASKS;
+  A.pairTasks = w->pairTasks.p; A.pairTaskOff = w->pairTaskOff.p; A.pairMask = w->pairMask.p; A.nTasks = cnt + CT_NTASKS;
   A.taskPair = w->taskPair.p; A.taskInfo = w->taskInfo.p; A.taskCell = w->taskCell.p;
   A.bucket = w->bucket.p; A.bucketCount = cnt + CT_BUCKETCOUNT; A.bucketStart = cnt + CT_BUCKETSTART; A.bucketCursor = cnt + CT_BUCKETCURSOR;
   A.taskCnt = w->taskCnt.p; A.taskRaw = w->taskRaw.p; A.taskOff = w->taskOff.p; A.rawCount = cnt + CT_RAWCOUNT;
@@ -986,10 +988,10 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
-  { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  { g_kernel_launches++; k_np_hull_warp<false><<<g, SAT_WARPS * 32, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   if (!w->hHfs.empty()) {
     { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A); }
-    { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    { g_kernel_launches++; k_np_hull_warp<true><<<g, SAT_WARPS * 32, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   }
   { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
   W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }

@@ -19,6 +19,7 @@ struct NpArrays {
   const int* p2;
   const int* nPairs;       // device count
   int* pairTasks;          // tasks per pair, then exclusive scan (in place into pairTaskOff)
+  unsigned long long* pairMask;  // heightfield pairs: surviving pillars of the index window (pass 0 -> pass 1)
   int* pairTaskOff;
   int* nTasks;
   int* taskPair;
@@ -101,6 +102,83 @@ __device__ inline bool hf_window(const ShapeTables& T, const HfDev& hf, const f3
   return true;
 }
 
+// Offset and bounding-sphere radius of one triangle pillar (same arithmetic as build_pillar below): enough for the
+// `distanceTo(worldPillarOffset) < pillar.boundingSphereRadius + r` gate of narrow_phase.dart:1374-1377,2121-2124,
+// so rejected pillars never become tasks.
+__device__ inline void pillar_bounds(const ShapeTables& T, const HfDev& hf, int xi, int yi, bool upper, f3& offset, double& bsr, f3* v) {
+  const double es = (double)hf.esize;
+  const double* d = T.hfdata + hf.dataOff;
+  const double h00 = d[(size_t)xi * hf.ny + yi], h10 = d[(size_t)(xi + 1) * hf.ny + yi], h01 = d[(size_t)xi * hf.ny + yi + 1],
+               h11 = d[(size_t)(xi + 1) * hf.ny + yi + 1];
+  const double h = (fmin(fmin(h00, h10), fmin(h01, h11)) - hf.minV) / 2 + hf.minV;
+  if (!upper) {
+    offset = mk3((xi + 0.25) * es, (yi + 0.25) * es, h);
+    v[0] = mk3(-0.25 * es, -0.25 * es, h00 - h);
+    v[1] = mk3(0.75 * es, -0.25 * es, h10 - h);
+    v[2] = mk3(-0.25 * es, 0.75 * es, h01 - h);
+    v[3] = mk3(-0.25 * es, -0.25 * es, -h - 1);
+    v[4] = mk3(0.75 * es, -0.25 * es, -h - 1);
+    v[5] = mk3(-0.25 * es, 0.75 * es, -h - 1);
+  } else {
+    offset = mk3((xi + 0.75) * es, (yi + 0.75) * es, h);
+    v[0] = mk3(0.25 * es, 0.25 * es, h11 - h);
+    v[1] = mk3(-0.75 * es, 0.25 * es, h01 - h);
+    v[2] = mk3(0.25 * es, -0.75 * es, h10 - h);
+    v[3] = mk3(0.25 * es, 0.25 * es, -h - 1);
+    v[4] = mk3(-0.75 * es, 0.25 * es, -h - 1);
+    v[5] = mk3(0.25 * es, -0.75 * es, -h - 1);
+  }
+  double max2 = 0;
+  for (int i = 0; i < 6; i++) {
+    const double n2 = vlen2(v[i]);
+    if (n2 > max2) max2 = n2;
+  }
+  bsr = sqrt(max2);
+}
+
+// min/max of `nV` local vertices along a world axis, ConvexPolyhedron.project (convex_polyhedron.dart:843-883) with the
+// axis-independent local origin hoisted out
+__device__ __forceinline__ void project_verts(const float4* __restrict__ gv, const f3* __restrict__ lv, int nV, const f3& axis, const q4& quat,
+                                              const f3& localOrigin, double& mx, double& mn) {
+  const f3 localAxis = qrot(qnegw(quat), axis);
+  const double add = vdot(localOrigin, localAxis);
+  mn = mx = vdot(gv ? ld3(gv[0]) : lv[0], localAxis);
+  for (int i = 1; i < nV; i++) {
+    const double val = vdot(gv ? ld3(gv[i]) : lv[i], localAxis);
+    if (val > mx) mx = val;
+    if (val < mn) mn = val;
+  }
+  mn -= add;
+  mx -= add;
+  if (mn > mx) { const double t = mn; mn = mx; mx = t; }
+}
+
+// Exact early rejection of a hull/pillar task: convexConvex reports no contact as soon as ANY axis of its test
+// set separates the hulls (convex_polyhedron.dart:264-267,338-341). The set always contains face 0 of the hull
+// (when it has `uniqueAxes`) and cross(hull edge, pillar vertical edge (0,0,1)); testing just those with the
+// very same projection arithmetic kills most window pillars without changing a single result.
+__device__ inline bool pillar_quick_separated(const float4* hv, int nVA, const float4* hn, int hasAxes, const float4* he, int nEA,
+                                              const f3& xA, const q4& qA, const f3& oA, const f3* pv, const f3& xP, const q4& qP) {
+  f3 zero; zero.x = zero.y = zero.z = 0.f;
+  const f3 oP = to_local_point(xP, qP, zero);
+  f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
+  const f3 wz = qrot(qP, up);
+  for (int t = hasAxes ? -1 : 0; t < nEA; t++) {
+    f3 axis;
+    if (t < 0) axis = qrot(qA, ld3(hn[0]));
+    else {
+      axis = vcross(qrot(qA, ld3(he[t])), wz);
+      if (valmost_zero(axis)) continue;
+      vnormalize(axis);
+    }
+    double maxA, minA, maxB, minB;
+    project_verts(hv, nullptr, nVA, axis, qA, oA, maxA, minA);
+    project_verts(nullptr, pv, 6, axis, qP, oP, maxB, minB);
+    if (maxA < minB || maxB < minA) return true;
+  }
+  return false;
+}
+
 // which body plays "i" for the resolver: lower ShapeType index first, equal types swapped (narrow_phase.dart:706-710)
 __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& first, int& second) {
   if (ta < tb) { first = a; second = b; } else { first = b; second = a; }
@@ -144,8 +222,53 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           const double radius = code == NP_SPIL ? s1.radius : T.hulls[s1.hull].bsr;
           nt = 0;
           if (hf_window(T, hf, local, radius, iMinX, iMaxX, iMinY, iMaxY)) {
-            const int wx = iMaxX - iMinX, wy = iMaxY - iMinY;
-            if (wx > 0 && wy > 0) nt = wx * wy * 2;
+            // one task per pillar that passes the bounding-sphere gate, in the reference's loop order (i, j, lower/upper)
+            const f3 xf = ld3(B.pos[first]), xs = ld3(B.pos[second]);
+            const q4 qs = ldq(B.quat[second]);
+            const double rFirst = code == NP_SPIL ? s1.bsr : T.hulls[s1.hull].bsr;
+            const int off = pass ? A.pairTaskOff[k] : 0;
+            const bool hullTask = code == NP_HPIL;
+            HullDev hd;
+            q4 qf;
+            f3 oA;
+            if (hullTask) {
+              hd = T.hulls[s1.hull];
+              qf = ldq(B.quat[first]);
+              f3 zero; zero.x = zero.y = zero.z = 0.f;
+              oA = to_local_point(xf, qf, zero);
+            }
+            // survivors of pass 0 are cached as a bit mask (windows of up to 64 pillars) so pass 1 does not redo the tests
+            const int nPillars = (iMaxX - iMinX) * (iMaxY - iMinY) * 2;
+            const bool cached = pass && nPillars <= 64;
+            const unsigned long long cachedMask = cached ? A.pairMask[k] : 0ull;
+            unsigned long long mask = 0ull;
+            int pidx = 0;
+            for (int i = iMinX; i < iMaxX; i++)
+              for (int j = iMinY; j < iMaxY; j++)
+                for (int up = 0; up < 2; up++, pidx++) {
+                  bool alive;
+                  if (cached) alive = (cachedMask >> pidx) & 1ull;
+                  else {
+                    f3 po, pv[6];
+                    double pr;
+                    pillar_bounds(T, hf, i, j, up != 0, po, pr, pv);
+                    const f3 wpo = to_world_point(xs, qs, po);
+                    alive = vdist(xf, wpo) < pr + rFirst;
+                    if (alive && hullTask && hd.nE <= 32 && hd.nF <= 32)
+                      alive = !pillar_quick_separated(T.verts + hd.vOff, hd.nV, T.fnormals + hd.fOff, hd.hasAxes, T.edges + hd.eOff, hd.nE, xf, qf,
+                                                      oA, pv, wpo, qs);
+                    if (alive && pidx < 64) mask |= 1ull << pidx;
+                  }
+                  if (alive) {
+                    if (pass && off + nt < A.taskCap) {
+                      A.taskPair[off + nt] = k;
+                      A.taskInfo[off + nt] = code | (up << 4);
+                      A.taskCell[off + nt] = make_int2(i, j);
+                    }
+                    nt++;
+                  }
+                }
+            if (!pass) A.pairMask[k] = mask;
           }
         }
       }
@@ -159,13 +282,6 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
     const int off = A.pairTaskOff[k];
     if (off + nt > A.taskCap) { atomicMax(A.overflowTasks, off + nt); continue; }
     if (code == NP_SPIL || code == NP_HPIL) {
-      const int wy = iMaxY - iMinY;
-      for (int t = 0; t < nt; t++) {
-        const int cellIdx = t >> 1;
-        A.taskPair[off + t] = k;
-        A.taskInfo[off + t] = code | ((t & 1) << 4);
-        A.taskCell[off + t] = make_int2(iMinX + cellIdx / wy, iMinY + cellIdx % wy);
-      }
       const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], nt);
       for (int t = 0; t < nt; t++) A.bucket[slot + t] = off + t;
     } else {
@@ -673,7 +789,8 @@ __constant__ int c_pillarFvOff[6] = {0, 3, 6, 10, 14, 18};
 __constant__ int c_pillarLower[18] = {0, 1, 2, 5, 4, 3, 0, 2, 5, 3, 1, 0, 3, 4, 4, 5, 2, 1};
 __constant__ int c_pillarUpper[18] = {0, 1, 2, 5, 4, 3, 2, 5, 3, 0, 3, 4, 1, 0, 1, 4, 5, 2};
 
-__device__ inline void build_pillar(const ShapeTables& T, const HfDev& hf, int xi, int yi, bool upper, PillarStore& S, f3& offset) {
+__device__ inline void build_pillar(const ShapeTables& T, const HfDev& hf, int xi, int yi, bool upper, PillarStore& S, f3& offset,
+                                    bool needEdges = true) {
   const double es = (double)hf.esize;
   const double* d = T.hfdata + hf.dataOff;
   const double h00 = d[(size_t)xi * hf.ny + yi], h10 = d[(size_t)(xi + 1) * hf.ny + yi], h01 = d[(size_t)xi * hf.ny + yi + 1],
@@ -714,6 +831,7 @@ __device__ inline void build_pillar(const ShapeTables& T, const HfDev& hf, int x
     nn = vneg(nn);
     S.n[f] = st3(nn);
     S.pc[f] = -vdot(nn, va);
+    if (!needEdges) continue;  // sphereConvex never looks at uniqueEdges
     for (int j = 0; j < L; j++) {
       f3 e = vsub(v[fv[o + j]], v[fv[o + (j + 1) % L]]);
       vnormalize(e);
@@ -746,7 +864,7 @@ __global__ void __launch_bounds__(64) k_np_sphere_pillar(BodyArrays B, ShapeTabl
     const bool upper = (c.info >> 4) & 1;
     PillarStore S;
     f3 off;
-    build_pillar(T, hf, cell.x, cell.y, upper, S, off);
+    build_pillar(T, hf, cell.x, cell.y, upper, S, off, false);
     const f3 wpo = to_world_point(c.xj, c.qj, off);
     bool hit = false;
     f3 ri, rj, ni;
