@@ -106,7 +106,7 @@ class Profile(C.Structure):
         ("integrate", c_f64), ("narrowphase", c_f64),
         ("n_pairs", c_i64), ("n_contacts", c_i64), ("n_rows", c_i64), ("n_levels", c_i64),
         ("iterations_done", c_i64), ("steps", c_i64), ("contact_iters_total", c_i64),
-        ("step_call_ms", c_f64), ("schedule_ms", c_f64), ("gs_ms", c_f64), ("kernel_launches", c_i64),
+        ("step_call_ms", c_f64), ("schedule_ms", c_f64), ("gs_ms", c_f64), ("kernel_launches", c_i64), ("n_tasks", c_i64), ("n_tasks_by_type", c_i64 * 8),
     ]
 
 

@@ -1350,6 +1350,8 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
     p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
     p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
     w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
+    p.n_tasks = w->hCnt[CT_NTASKS];
+    for (int t = 0; t < NP_NTYPES; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];
   }
   return CANNON_OK;
 }

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
 __device__ __forceinline__ float dot3f(const float4& a, float bx, float by, float bz) { return fmaf(a.z, bz, fmaf(a.y, by, a.x * bx)); }
 
 __global__ void __launch_bounds__(256, 4) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
-  __shared__ double s_red[8];
+  __shared__ double s_red[32];
   __shared__ int s_any;
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);

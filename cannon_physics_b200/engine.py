@@ -290,7 +290,9 @@ class DeviceWorld:
     def profile(self) -> Dict[str, float]:
         p = F.Profile()
         self._chk(self.lib.cannon_world_profile(self.handle, C.byref(p)))
-        return {name: getattr(p, name) for name, _ in F.Profile._fields_}
+        out = {name: getattr(p, name) for name, _ in F.Profile._fields_}
+        out["n_tasks_by_type"] = list(p.n_tasks_by_type)
+        return out
 
     def get_contacts(self):
         n = F.c_i32()

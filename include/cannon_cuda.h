@@ -206,6 +206,8 @@ typedef struct cannon_profile {
   double schedule_ms;    /* dependency-level / colouring kernel of the last step */
   double gs_ms;          /* Gauss-Seidel sweep kernel of the last step */
   int64_t kernel_launches; /* kernels launched by the library since world creation */
+  int64_t n_tasks;         /* narrowphase resolver tasks of the last step (pairs + heightfield pillars) */
+  int64_t n_tasks_by_type[8]; /* sphere-sphere, sphere-plane, sphere-box, sphere-hull, plane-hull, hull-hull, sphere-pillar, hull-pillar */
 } cannon_profile;
 
 /* ---- lifecycle ---- */

@@ -13,7 +13,7 @@ def run(name, spec, chunks, per=20):
             p = w.profile()
             b = w.get_bodies(("position","velocity"))
             y = b["position"][:,1]
-            print(f"  steps={p['steps']} ms/step={p['step_call_ms']/per:.3f} pairs={p['n_pairs']} contacts={p['n_contacts']} rows={p['n_rows']} levels={p['n_levels']} it={p['iterations_done']} | bp={p['broadphase']:.3f} np={p['narrowphase']:.3f} solve={p['solve']:.3f} (sched={p['schedule_ms']:.3f} gs={p['gs_ms']:.3f}) int={p['integrate']:.3f} | ymin={y[1:].min():.2f} ymax={y[1:].max():.2f} vmax={np.abs(b['velocity']).max():.2f} launches={p['kernel_launches']}", flush=True)
+            print(f"  steps={p['steps']} ms/step={p['step_call_ms']/per:.3f} pairs={p['n_pairs']} contacts={p['n_contacts']} rows={p['n_rows']} levels={p['n_levels']} it={p['iterations_done']} | bp={p['broadphase']:.3f} np={p['narrowphase']:.3f} solve={p['solve']:.3f} (sched={p['schedule_ms']:.3f} gs={p['gs_ms']:.3f}) int={p['integrate']:.3f} | ymin={y[1:].min():.2f} ymax={y[1:].max():.2f} vmax={np.abs(b['velocity']).max():.2f} launches={p['kernel_launches']} tasks={p['n_tasks']} {p['n_tasks_by_type']}", flush=True)
     except Exception as e:
         print(f"FAIL {name}: {e}", flush=True)
 which = sys.argv[1] if len(sys.argv)>1 else "all"
