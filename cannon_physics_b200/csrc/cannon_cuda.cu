@@ -988,10 +988,10 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
-  { g_kernel_launches++; k_np_hull_warp<false><<<g, SAT_WARPS * 32, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   if (!w->hHfs.empty()) {
     { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A); }
-    { g_kernel_launches++; k_np_hull_warp<true><<<g, SAT_WARPS * 32, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
   }
   { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
   W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }

@@ -12,11 +12,15 @@
 // Every arithmetic expression is the one the sequential path (k_narrowphase.cuh) evaluates, so contact counts
 // and geometry stay bit-identical to the oracle; only the scheduling changed.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "k_narrowphase.cuh"
+namespace cg = cooperative_groups;
 
 #define SAT_MAXF 32
 #define SAT_MAXE 32
-#define SAT_WARPS 4
+#define SAT_GROUP 8            // lanes per task (a tile of the warp); 4 tasks share a warp
+#define SAT_TILES 8            // tiles per CTA
 
 struct SatScratch {
   f3 nA[SAT_MAXF], nB[SAT_MAXF];  // world face normals
@@ -24,6 +28,7 @@ struct SatScratch {
   f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY];
   double depth[NP_MAXPOLY];
   f3 cand[18];                    // pillar edge candidates
+  int candMask[18];               // earlier candidates each one is almostEquals to
   PillarStore pil;
   int kept, overflow, closestA;
   f3 nrm;
@@ -120,15 +125,16 @@ __device__ inline int clip_hulls_s(SatScratch& S, const HullView& HA, const f3& 
 }
 
 template <bool PILLAR>
-__global__ void __launch_bounds__(SAT_WARPS * 32) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
-  __shared__ SatScratch s_scr[SAT_WARPS];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  SatScratch& S = s_scr[wib];
+__global__ void __launch_bounds__(SAT_TILES * SAT_GROUP) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+  __shared__ SatScratch s_scr[SAT_TILES];
+  cg::thread_block_tile<SAT_GROUP> tile = cg::tiled_partition<SAT_GROUP>(cg::this_thread_block());
+  const int lane = tile.thread_rank(), tib = threadIdx.x / SAT_GROUP;
+  SatScratch& S = s_scr[tib];
   const int TYPE = PILLAR ? NP_HPIL : NP_HH;
   const int nb = (*A.nTasks <= A.taskCap) ? A.bucketCount[TYPE] : 0;
-  const int warpsPerGrid = gridDim.x * SAT_WARPS;
-  for (int u = blockIdx.x * SAT_WARPS + wib; u < nb; u += warpsPerGrid) {
-    __syncwarp();
+  const int tilesPerGrid = gridDim.x * SAT_TILES;
+  for (int u = blockIdx.x * SAT_TILES + tib; u < nb; u += tilesPerGrid) {
+    tile.sync();
     TaskCtx c;
     load_task(B, T, A, A.bucket[A.bucketStart[TYPE] + u], c);
     RawOut o; o.A = A; o.task = c.task;
@@ -140,37 +146,53 @@ __global__ void __launch_bounds__(SAT_WARPS * 32) k_np_hull_warp(BodyArrays B, S
       const HfDev hf = T.hfs[c.sj.hf];
       const int2 cell = A.taskCell[c.task];
       upper = (c.info >> 4) & 1;
-      // Heightfield.getConvexTrianglePillar (heightfield.dart:330-487): lane 0 builds vertices / normals, the 18 edge
-      // candidates are normalised by 18 lanes, lane 0 removes duplicates in order (computeEdges, convex_polyhedron.dart:110-139)
-      f3 off;
+      // Heightfield.getConvexTrianglePillar (heightfield.dart:330-487) spread over the tile: vertices by lane 0,
+      // one face normal per lane, one edge candidate per lane, duplicate removal in candidate order
+      // (computeNormals / computeEdges, convex_polyhedron.dart:110-185)
       if (lane == 0) {
-        build_pillar(T, hf, cell.x, cell.y, upper, S.pil, off, false);
+        f3 off, pv[6];
+        double bsr;
+        pillar_bounds(T, hf, cell.x, cell.y, upper, off, bsr, pv);
+        for (int i = 0; i < 6; i++) S.pil.v[i] = st3(pv[i]);
+        S.pil.bsr = bsr;
         S.nrm = off;
       }
-      __syncwarp();
-      off = S.nrm;
+      tile.sync();
+      const f3 off = S.nrm;
       const int* fv = upper ? c_pillarUpper : c_pillarLower;
-      if (lane < 18) {
-        int f = 0;
-        while (lane >= c_pillarFvOff[f + 1]) f++;
-        const int o0 = c_pillarFvOff[f], L = c_pillarFvOff[f + 1] - o0, j = lane - o0;
-        f3 e = vsub(ld3(S.pil.v[fv[o0 + j]]), ld3(S.pil.v[fv[o0 + (j + 1) % L]]));
-        vnormalize(e);
-        S.cand[lane] = e;
+      for (int f = lane; f < 5; f += SAT_GROUP) {
+        const int o0 = c_pillarFvOff[f];
+        const f3 va = ld3(S.pil.v[fv[o0]]), vb = ld3(S.pil.v[fv[o0 + 1]]), vc = ld3(S.pil.v[fv[o0 + 2]]);
+        f3 nn = vcross(vsub(vc, vb), vsub(vb, va));
+        if (!(nn.x == 0.f && nn.y == 0.f && nn.z == 0.f)) vnormalize(nn);
+        nn = vneg(nn);
+        S.pil.n[f] = st3(nn);
+        S.pil.pc[f] = -vdot(nn, va);
       }
-      __syncwarp();
+      for (int e = lane; e < 18; e += SAT_GROUP) {
+        int f = 0;
+        while (e >= c_pillarFvOff[f + 1]) f++;
+        const int o0 = c_pillarFvOff[f], L = c_pillarFvOff[f + 1] - o0, j = e - o0;
+        f3 ev = vsub(ld3(S.pil.v[fv[o0 + j]]), ld3(S.pil.v[fv[o0 + (j + 1) % L]]));
+        vnormalize(ev);
+        S.cand[e] = ev;
+      }
+      tile.sync();
+      for (int e = lane; e < 18; e += SAT_GROUP) {
+        int m = 0;
+        const f3 ev = S.cand[e];
+        for (int p = 0; p < e; p++)
+          if (valmost_eq(S.cand[p], ev)) m |= 1 << p;
+        S.candMask[e] = m;
+      }
+      tile.sync();
       if (lane == 0) {
-        int nE = 0;
-        for (int k = 0; k < 18; k++) {
-          const f3 e = S.cand[k];
-          bool found = false;
-          for (int p = 0; p < nE; p++)
-            if (valmost_eq(ld3(S.pil.e[p]), e)) { found = true; break; }
-          if (!found) S.pil.e[nE++] = st3(e);
-        }
+        int nE = 0, keep = 0;
+        for (int k = 0; k < 18; k++)
+          if ((S.candMask[k] & keep) == 0) { keep |= 1 << k; S.pil.e[nE++] = st3(S.cand[k]); }
         S.pil.nE = nE;
       }
-      __syncwarp();
+      tile.sync();
       xB = to_world_point(c.xj, c.qj, off);
       HB = pillar_view(S.pil, upper);
     } else {
@@ -187,11 +209,11 @@ __global__ void __launch_bounds__(SAT_WARPS * 32) k_np_hull_warp(BodyArrays B, S
       continue;
     }
     if (candidate) {
-      for (int i = lane; i < HA.nF; i += 32) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));
-      for (int i = lane; i < HB.nF; i += 32) S.nB[i] = qrot(c.qj, ld3(HB.n[i]));
-      for (int i = lane; i < HA.nE; i += 32) S.eA[i] = qrot(c.qi, ld3(HA.e[i]));
-      for (int i = lane; i < HB.nE; i += 32) S.eB[i] = qrot(c.qj, ld3(HB.e[i]));
-      __syncwarp();
+      for (int i = lane; i < HA.nF; i += SAT_GROUP) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));
+      for (int i = lane; i < HB.nF; i += SAT_GROUP) S.nB[i] = qrot(c.qj, ld3(HB.n[i]));
+      for (int i = lane; i < HA.nE; i += SAT_GROUP) S.eA[i] = qrot(c.qi, ld3(HA.e[i]));
+      for (int i = lane; i < HB.nE; i += SAT_GROUP) S.eB[i] = qrot(c.qj, ld3(HB.e[i]));
+      tile.sync();
       f3 zero; zero.x = zero.y = zero.z = 0.f;
       const f3 oA = to_local_point(c.xi, c.qi, zero), oB = to_local_point(xB, c.qj, zero);
       const int nfa = HA.hasAxes ? (PILLAR ? 1 : HA.nF) : 0;  // heightfieldConvex passes faceListA = [0] (:2062)
@@ -201,39 +223,51 @@ __global__ void __launch_bounds__(SAT_WARPS * 32) k_np_hull_warp(BodyArrays B, S
       int bestIdx = 0x7fffffff;
       f3 bestAxis = zero;
       bool separated = false;
-      for (int t = lane; t < nAxes; t += 32) {
-        f3 axis;
-        if (t < nfa) axis = S.nA[t];
-        else if (t < nfa + nfb) axis = S.nB[t - nfa];
-        else {
-          const int e = t - nfa - nfb;
-          axis = vcross(S.eA[e / HB.nE], S.eB[e % HB.nE]);
-          if (valmost_zero(axis)) continue;
-          vnormalize(axis);
+      // rounds of SAT_GROUP axes with a vote after each round: a separating axis ends the task early (same result
+      // as the sequential `return false`, convex_polyhedron.dart:264-267)
+      for (int base = 0; base < nAxes && !separated; base += SAT_GROUP) {
+        const int t = base + lane;
+        bool sepHere = false;
+        if (t < nAxes) {
+          f3 axis;
+          bool valid = true;
+          if (t < nfa) axis = S.nA[t];
+          else if (t < nfa + nfb) axis = S.nB[t - nfa];
+          else {
+            const int e = t - nfa - nfb;
+            axis = vcross(S.eA[e / HB.nE], S.eB[e % HB.nE]);
+            if (valmost_zero(axis)) valid = false;
+            else vnormalize(axis);
+          }
+          if (valid) {
+            double maxA, minA, maxB, minB;
+            hull_project_o(HA, axis, c.qi, oA, maxA, minA);
+            hull_project_o(HB, axis, c.qj, oB, maxB, minB);
+            if (maxA < minB || maxB < minA) sepHere = true;
+            else {
+              const double d0 = maxA - minB, d1 = maxB - minA;
+              const double d = d0 < d1 ? d0 : d1;
+              if (d < best) { best = d; bestIdx = t; bestAxis = axis; }
+            }
+          }
         }
-        double maxA, minA, maxB, minB;
-        hull_project_o(HA, axis, c.qi, oA, maxA, minA);
-        hull_project_o(HB, axis, c.qj, oB, maxB, minB);
-        if (maxA < minB || maxB < minA) { separated = true; break; }
-        const double d0 = maxA - minB, d1 = maxB - minA;
-        const double d = d0 < d1 ? d0 : d1;
-        if (d < best) { best = d; bestIdx = t; bestAxis = axis; }
+        separated = tile.any(sepHere);
       }
-      if (!__any_sync(0xffffffffu, separated)) {
+      if (!separated) {
         // lexicographic (depth, index) minimum == the sequential loop's "first strictly smaller depth"
         double rb = best;
         int ri = bestIdx;
-        for (int off = 16; off > 0; off >>= 1) {
-          const double ob = __shfl_xor_sync(0xffffffffu, rb, off);
-          const int oi = __shfl_xor_sync(0xffffffffu, ri, off);
+        for (int off = SAT_GROUP / 2; off > 0; off >>= 1) {
+          const double ob = tile.shfl_xor(rb, off);
+          const int oi = tile.shfl_xor(ri, off);
           if (ob < rb || (ob == rb && oi < ri)) { rb = ob; ri = oi; }
         }
-        const unsigned winMask = __ballot_sync(0xffffffffu, bestIdx == ri && ri != 0x7fffffff);
+        const unsigned winMask = tile.ballot(bestIdx == ri && ri != 0x7fffffff);
         if (winMask) {
           const int src = __ffs(winMask) - 1;
-          sep.x = __shfl_sync(0xffffffffu, bestAxis.x, src);
-          sep.y = __shfl_sync(0xffffffffu, bestAxis.y, src);
-          sep.z = __shfl_sync(0xffffffffu, bestAxis.z, src);
+          sep.x = tile.shfl(bestAxis.x, src);
+          sep.y = tile.shfl(bestAxis.y, src);
+          sep.z = tile.shfl(bestAxis.z, src);
         }
         const f3 deltaC = vsub(xB, c.xi);
         if (vdot(deltaC, sep) > 0.0) sep = vneg(sep);
@@ -242,23 +276,23 @@ __global__ void __launch_bounds__(SAT_WARPS * 32) k_np_hull_warp(BodyArrays B, S
           S.kept = clip_hulls_s(S, HA, c.xi, HB, xB, c.qj, sep, ovf);
           if (ovf) atomicExch(clipOverflow, 1);
         }
-        __syncwarp();
+        tile.sync();
         kept = S.kept;
       }
     }
     // emission: lane 0 reserves the block in the raw pool, lanes write one contact each
-    int start = 0;
+    tile.sync();
     if (lane == 0) {
       raw_alloc(o, kept);
       S.kept = o.A.taskCnt[o.task];  // 0 if the pool overflowed
       S.closestA = o.start;
     }
-    __syncwarp();
+    tile.sync();
     kept = S.kept;
-    start = S.closestA;
+    const int start = S.closestA;
     const f3 ni = vneg(sep);
     const f3 nrm = S.nrm;
-    for (int j = lane; j < kept; j += 32) {
+    for (int j = lane; j < kept; j += SAT_GROUP) {
       const f3 q = vscale(S.depth[j], vneg(nrm));
       f3 ri = vadd(S.pa[j], q);
       f3 rj = S.pa[j];
