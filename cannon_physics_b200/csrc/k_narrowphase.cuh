@@ -184,102 +184,133 @@ __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& firs
   if (ta < tb) { first = a; second = b; } else { first = b; second = a; }
 }
 
+// Pass 0 counts the tasks of every pair, pass 1 (after the scan) writes them. Ordinary pairs are handled by their
+// own thread. Heightfield pairs are expanded *warp-cooperatively*: the warp takes its heightfield pairs one at a time
+// and every lane tests one pillar of the index window (bounding gate + exact quick separation), a ballot gives the
+// survivor mask in the reference's loop order (i, j, lower/upper), so counts and emission order need no atomics.
 __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass) {
   const int np = *A.nPairs;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-    const int a = A.p1[k], b = A.p2[k];
+  const int lane = threadIdx.x & 31;
+  const int warpStart = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
+  const int stride = gridDim.x * blockDim.x;
+  for (int kb = warpStart; kb < np; kb += stride) {
+    const int k = kb + lane;
     int nt = 0, code = -1;
+    int first = 0, second = 0;
     int iMinX = 0, iMaxX = 0, iMinY = 0, iMaxY = 0;
-    const int sa = B.shape[a], sb = B.shape[b];
-    if (sa >= 0 && sb >= 0) {
-      const ShapeDev si = T.shapes[sa], sj = T.shapes[sb];
-      const int tya = B.type[a], tyb = B.type[b];
-      const bool justTest = (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_STATIC) || (tya == CANNON_BODY_STATIC && tyb == CANNON_BODY_KINEMATIC) ||
-                            (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_KINEMATIC);
-      const bool maskOk = (si.mask & sj.group) != 0 && (sj.mask & si.group) != 0;
-      const f3 xi = ld3(B.pos[a]), xj = ld3(B.pos[b]);
-      if (maskOk && !justTest && !(vdist(xi, xj) > si.bsr + sj.bsr)) {
-        int lo = si.type, hi = sj.type;
-        int first = a, second = b;
-        if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
-        if (lo == CANNON_SHAPE_SPHERE) {
-          if (hi == CANNON_SHAPE_SPHERE) code = NP_SS;
-          else if (hi == CANNON_SHAPE_PLANE) code = NP_SP;
-          else if (hi == CANNON_SHAPE_BOX) code = NP_SB;
-          else if (hi == CANNON_SHAPE_CONVEX || hi == CANNON_SHAPE_CYLINDER) code = NP_SH;
-          else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_SPIL;
-        } else if (lo == CANNON_SHAPE_PLANE) {
-          if (is_hull_type(hi)) code = NP_PH;
-        } else if (is_hull_type(lo)) {
-          if (is_hull_type(hi)) code = NP_HH;
-          else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_HPIL;
-        }
-        if (code >= 0) nt = 1;
-        if (code == NP_SPIL || code == NP_HPIL) {
-          const ShapeDev s1 = T.shapes[B.shape[first]], s2 = T.shapes[B.shape[second]];
-          const HfDev hf = T.hfs[s2.hf];
-          const f3 local = to_local_point(ld3(B.pos[second]), ldq(B.quat[second]), ld3(B.pos[first]));
-          const double radius = code == NP_SPIL ? s1.radius : T.hulls[s1.hull].bsr;
-          nt = 0;
-          if (hf_window(T, hf, local, radius, iMinX, iMaxX, iMinY, iMaxY)) {
-            // one task per pillar that passes the bounding-sphere gate, in the reference's loop order (i, j, lower/upper)
-            const f3 xf = ld3(B.pos[first]), xs = ld3(B.pos[second]);
-            const q4 qs = ldq(B.quat[second]);
-            const double rFirst = code == NP_SPIL ? s1.bsr : T.hulls[s1.hull].bsr;
-            const int off = pass ? A.pairTaskOff[k] : 0;
-            const bool hullTask = code == NP_HPIL;
-            HullDev hd;
-            q4 qf;
-            f3 oA;
-            if (hullTask) {
-              hd = T.hulls[s1.hull];
-              qf = ldq(B.quat[first]);
-              f3 zero; zero.x = zero.y = zero.z = 0.f;
-              oA = to_local_point(xf, qf, zero);
-            }
-            // survivors of pass 0 are cached as a bit mask (windows of up to 64 pillars) so pass 1 does not redo the tests
-            const int nPillars = (iMaxX - iMinX) * (iMaxY - iMinY) * 2;
-            const bool cached = pass && nPillars <= 64;
-            const unsigned long long cachedMask = cached ? A.pairMask[k] : 0ull;
-            unsigned long long mask = 0ull;
-            int pidx = 0;
-            for (int i = iMinX; i < iMaxX; i++)
-              for (int j = iMinY; j < iMaxY; j++)
-                for (int up = 0; up < 2; up++, pidx++) {
-                  bool alive;
-                  if (cached) alive = (cachedMask >> pidx) & 1ull;
-                  else {
-                    f3 po, pv[6];
-                    double pr;
-                    pillar_bounds(T, hf, i, j, up != 0, po, pr, pv);
-                    const f3 wpo = to_world_point(xs, qs, po);
-                    alive = vdist(xf, wpo) < pr + rFirst;
-                    if (alive && hullTask && hd.nE <= 32 && hd.nF <= 32)
-                      alive = !pillar_quick_separated(T.verts + hd.vOff, hd.nV, T.fnormals + hd.fOff, hd.hasAxes, T.edges + hd.eOff, hd.nE, xf, qf,
-                                                      oA, pv, wpo, qs);
-                    if (alive && pidx < 64) mask |= 1ull << pidx;
-                  }
-                  if (alive) {
-                    if (pass && off + nt < A.taskCap) {
-                      A.taskPair[off + nt] = k;
-                      A.taskInfo[off + nt] = code | (up << 4);
-                      A.taskCell[off + nt] = make_int2(i, j);
-                    }
-                    nt++;
-                  }
-                }
-            if (!pass) A.pairMask[k] = mask;
+    bool hfPair = false;
+    if (k < np) {
+      const int a = A.p1[k], b = A.p2[k];
+      const int sa = B.shape[a], sb = B.shape[b];
+      if (sa >= 0 && sb >= 0) {
+        const ShapeDev si = T.shapes[sa], sj = T.shapes[sb];
+        const int tya = B.type[a], tyb = B.type[b];
+        const bool justTest = (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_STATIC) || (tya == CANNON_BODY_STATIC && tyb == CANNON_BODY_KINEMATIC) ||
+                              (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_KINEMATIC);
+        const bool maskOk = (si.mask & sj.group) != 0 && (sj.mask & si.group) != 0;
+        const f3 xi = ld3(B.pos[a]), xj = ld3(B.pos[b]);
+        if (maskOk && !justTest && !(vdist(xi, xj) > si.bsr + sj.bsr)) {
+          int lo = si.type, hi = sj.type;
+          first = a; second = b;
+          if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
+          if (lo == CANNON_SHAPE_SPHERE) {
+            if (hi == CANNON_SHAPE_SPHERE) code = NP_SS;
+            else if (hi == CANNON_SHAPE_PLANE) code = NP_SP;
+            else if (hi == CANNON_SHAPE_BOX) code = NP_SB;
+            else if (hi == CANNON_SHAPE_CONVEX || hi == CANNON_SHAPE_CYLINDER) code = NP_SH;
+            else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_SPIL;
+          } else if (lo == CANNON_SHAPE_PLANE) {
+            if (is_hull_type(hi)) code = NP_PH;
+          } else if (is_hull_type(lo)) {
+            if (is_hull_type(hi)) code = NP_HH;
+            else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_HPIL;
+          }
+          if (code >= 0) nt = 1;
+          if (code == NP_SPIL || code == NP_HPIL) {
+            const ShapeDev s1 = T.shapes[B.shape[first]], s2 = T.shapes[B.shape[second]];
+            const HfDev hf = T.hfs[s2.hf];
+            const f3 local = to_local_point(ld3(B.pos[second]), ldq(B.quat[second]), ld3(B.pos[first]));
+            const double radius = code == NP_SPIL ? s1.radius : T.hulls[s1.hull].bsr;
+            nt = 0;
+            hfPair = hf_window(T, hf, local, radius, iMinX, iMaxX, iMinY, iMaxY) && iMaxX > iMinX && iMaxY > iMinY;
           }
         }
       }
     }
+    // ---- warp-cooperative expansion of the heightfield pairs of this warp ----
+    unsigned todo = __ballot_sync(0xffffffffu, hfPair);
+    const int myOff = (pass && k < np) ? A.pairTaskOff[k] : 0;
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int pFirst = __shfl_sync(0xffffffffu, first, src), pSecond = __shfl_sync(0xffffffffu, second, src);
+      const int pCode = __shfl_sync(0xffffffffu, code, src), pk = kb + src;
+      const int x0 = __shfl_sync(0xffffffffu, iMinX, src), x1 = __shfl_sync(0xffffffffu, iMaxX, src);
+      const int y0 = __shfl_sync(0xffffffffu, iMinY, src), y1 = __shfl_sync(0xffffffffu, iMaxY, src);
+      const int pOff = __shfl_sync(0xffffffffu, myOff, src);
+      const int wy = y1 - y0, nP = (x1 - x0) * wy * 2;
+      const ShapeDev s1 = T.shapes[B.shape[pFirst]], s2 = T.shapes[B.shape[pSecond]];
+      const HfDev hf = T.hfs[s2.hf];
+      const f3 xf = ld3(B.pos[pFirst]), xs = ld3(B.pos[pSecond]);
+      const q4 qs = ldq(B.quat[pSecond]);
+      const bool hullTask = pCode == NP_HPIL;
+      const double rFirst = hullTask ? T.hulls[s1.hull].bsr : s1.bsr;
+      HullDev hd;
+      q4 qf;
+      f3 oA;
+      if (hullTask) {
+        hd = T.hulls[s1.hull];
+        qf = ldq(B.quat[pFirst]);
+        f3 zero; zero.x = zero.y = zero.z = 0.f;
+        oA = to_local_point(xf, qf, zero);
+      }
+      const bool cached = pass && nP <= 64;
+      const unsigned long long cachedMask = cached ? A.pairMask[pk] : 0ull;
+      unsigned long long mask = 0ull;
+      int count = 0;
+      for (int base = 0; base < nP; base += 32) {
+        const int pidx = base + lane;
+        bool alive = false;
+        int ci = 0, cj = 0, up = 0;
+        if (pidx < nP) {
+          const int cell = pidx >> 1;
+          up = pidx & 1;
+          ci = x0 + cell / wy;
+          cj = y0 + cell % wy;
+          if (cached) alive = (cachedMask >> pidx) & 1ull;
+          else {
+            f3 po, pv[6];
+            double pr;
+            pillar_bounds(T, hf, ci, cj, up != 0, po, pr, pv);
+            const f3 wpo = to_world_point(xs, qs, po);
+            alive = vdist(xf, wpo) < pr + rFirst;
+            if (alive && hullTask && hd.nE <= 32 && hd.nF <= 32)
+              alive = !pillar_quick_separated(T.verts + hd.vOff, hd.nV, T.fnormals + hd.fOff, hd.hasAxes, T.edges + hd.eOff, hd.nE, xf, qf, oA,
+                                              pv, wpo, qs);
+          }
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, alive);
+        if (base < 64) mask |= (unsigned long long)bits << base;
+        if (pass && alive) {
+          const int t = pOff + count + __popc(bits & ((1u << lane) - 1u));
+          if (t < A.taskCap) {
+            A.taskPair[t] = pk;
+            A.taskInfo[t] = pCode | (up << 4);
+            A.taskCell[t] = make_int2(ci, cj);
+          }
+        }
+        count += __popc(bits);
+      }
+      if (lane == src) { nt = count; if (!pass) A.pairMask[pk] = mask; }
+    }
+    if (k >= np) continue;
     if (pass == 0) {
       A.pairTasks[k] = nt;
       if (nt) atomicAdd(&A.bucketCount[code], nt);
       continue;
     }
     if (nt == 0) continue;
-    const int off = A.pairTaskOff[k];
+    const int off = myOff;
     if (off + nt > A.taskCap) { atomicMax(A.overflowTasks, off + nt); continue; }
     if (code == NP_SPIL || code == NP_HPIL) {
       const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], nt);
