@@ -520,9 +520,10 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
 
 
 // ---- COLORED mode sweep: f32 + FMA, one thread per manifold, lambdas in registers ---------------------------
+#define GS_CHUNK 4
 __device__ __forceinline__ float dot3f(const float4& a, float bx, float by, float bz) { return fmaf(a.z, bz, fmaf(a.y, by, a.x * bx)); }
 
-__global__ void __launch_bounds__(256, 4) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
+__global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
   __shared__ double s_red[32];
   __shared__ int s_any;
   unsigned epoch = 0;
@@ -549,28 +550,46 @@ __global__ void __launch_bounds__(256, 4) k_gs_fast(RowArrays R, BodyArrays B, U
         float4 vA = __ldcg(&B.vlam[bi]), wA = __ldcg(&B.wlam[bi]);
         float4 vB = __ldcg(&B.vlam[bj]), wB = __ldcg(&B.wlam[bj]);
         float acc = 0.f;
-        for (int r = r0; r < r1; r++) {
-          const float4 q0 = R.q0[r], q1 = R.q1[r], q2 = R.q2[r], q3 = R.q3[r], q4 = R.q4[r];
-          const float lam = R.flambda[r];
-          // G*W_lambda with G = [-n, rA, n, rB]
-          float gw = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
-          gw += dot3f(q1, wA.x, wA.y, wA.z);
-          gw += dot3f(q2, wB.x, wB.y, wB.z);
-          float dl = q1.w * (q0.w - gw - q2.w * lam);
-          if (lam + dl < q3.w) dl = q3.w - lam;
-          else if (lam + dl > q4.w) dl = q4.w - lam;
-          R.flambda[r] = lam + dl;
-          if (fl & 1) {
-            const float s = -imA * dl;
-            vA.x = fmaf(s, q0.x, vA.x); vA.y = fmaf(s, q0.y, vA.y); vA.z = fmaf(s, q0.z, vA.z);
-            wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+        // rows are fetched in chunks of GS_CHUNK through the read-only path before any of them is solved: the
+        // manifold's sequential chain then pays one memory round trip per chunk instead of one per row
+        for (int rc = r0; rc < r1; rc += GS_CHUNK) {
+          float4 c0[GS_CHUNK], c1[GS_CHUNK], c2[GS_CHUNK], c3[GS_CHUNK], c4[GS_CHUNK];
+          float cl[GS_CHUNK];
+#pragma unroll
+          for (int k = 0; k < GS_CHUNK; k++) {
+            const int r = min(rc + k, r1 - 1);
+            c0[k] = __ldg(&R.q0[r]); c1[k] = __ldg(&R.q1[r]); c2[k] = __ldg(&R.q2[r]); c3[k] = __ldg(&R.q3[r]); c4[k] = __ldg(&R.q4[r]);
+            cl[k] = R.flambda[r];
           }
-          if (fl & 2) {
-            const float s = imB * dl;
-            vB.x = fmaf(s, q0.x, vB.x); vB.y = fmaf(s, q0.y, vB.y); vB.z = fmaf(s, q0.z, vB.z);
-            wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+#pragma unroll
+          for (int k = 0; k < GS_CHUNK; k++) {
+            const int r = rc + k;
+            if (r >= r1) break;
+            const float4 q0 = c0[k], q1 = c1[k], q2 = c2[k], q3 = c3[k], q4 = c4[k];
+            const float lam = cl[k];
+            // G*W_lambda with G = [-n, rA, n, rB]
+            float gw = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
+            gw += dot3f(q1, wA.x, wA.y, wA.z);
+            gw += dot3f(q2, wB.x, wB.y, wB.z);
+            float dl = q1.w * (q0.w - gw - q2.w * lam);
+            if (lam + dl < q3.w) dl = q3.w - lam;
+            else if (lam + dl > q4.w) dl = q4.w - lam;
+            cl[k] = lam + dl;
+            if (fl & 1) {
+              const float s = -imA * dl;
+              vA.x = fmaf(s, q0.x, vA.x); vA.y = fmaf(s, q0.y, vA.y); vA.z = fmaf(s, q0.z, vA.z);
+              wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+            }
+            if (fl & 2) {
+              const float s = imB * dl;
+              vB.x = fmaf(s, q0.x, vB.x); vB.y = fmaf(s, q0.y, vB.y); vB.z = fmaf(s, q0.z, vB.z);
+              wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+            }
+            acc += fabsf(dl);
           }
-          acc += fabsf(dl);
+#pragma unroll
+          for (int k = 0; k < GS_CHUNK; k++)
+            if (rc + k < r1) R.flambda[rc + k] = cl[k];
         }
         if (fl & 1) { B.vlam[bi] = vA; B.wlam[bi] = wA; }
         if (fl & 2) { B.vlam[bj] = vB; B.wlam[bj] = wB; }
