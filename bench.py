@@ -248,8 +248,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         n = spec.n_bodies
-        force = np.zeros((n, 3), np.float32)
-        torque = np.zeros((n, 3), np.float32)
+        # pinned host buffers for the per-step inputs (force, torque) and outputs (position, quaternion)
+        pin = lambda shape: torch.zeros(shape, dtype=torch.float32, pin_memory=True).numpy()
+        force, torque = pin((n, 3)), pin((n, 3))
+        out = {"position": pin((n, 3)), "quaternion": pin((n, 4))}
         ke = K
         if world_size > 1:
             dist.barrier()
@@ -258,7 +260,7 @@ def main():
         for _ in range(ke):
             world.update_bodies(0, n, force=force, torque=torque)
             world.step(DT, 1)
-            poses = world.get_bodies(("position", "quaternion"))
+            poses = world.get_bodies(("position", "quaternion"), out=out)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         e2e_stats = reduce_stats({"body_steps": nd * ke}, el * 1000.0, device=dev_t)

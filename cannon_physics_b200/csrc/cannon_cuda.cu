@@ -92,6 +92,20 @@ __global__ void __launch_bounds__(256) k_multipliers(ContactArrays C, RowArrays 
   }
 }
 
+// host <-> device marshalling of 3-/4-vectors: the ABI uses tightly packed float3/float4 host arrays, the device float4;
+// packing runs on the GPU so each attribute costs exactly one cudaMemcpy of the caller's buffer
+__global__ void __launch_bounds__(256) k_pack_to4(const float* __restrict__ src, float4* __restrict__ dst, int n, int comps) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    dst[i] = make_float4(src[comps * i], src[comps * i + 1], src[comps * i + 2], comps == 4 ? src[4 * i + 3] : 0.f);
+}
+__global__ void __launch_bounds__(256) k_unpack_from4(const float4* __restrict__ src, float* __restrict__ dst, int n, int comps) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[comps * i] = v.x; dst[comps * i + 1] = v.y; dst[comps * i + 2] = v.z;
+    if (comps == 4) dst[4 * i + 3] = v.w;
+  }
+}
+
 // ---- world -------------------------------------------------------------------------------------------
 struct HostShape {
   int type = 0, collisionResponse = 1, group = -1, mask = -1;
@@ -178,6 +192,7 @@ struct cannon_world {
   int* hCnt = nullptr;  // pinned
   ScanTmp scanTmp;
   SortTmp sortTmp;
+  DBuf<float> stage;  // marshalling buffer (4 floats per body)
   DBuf<long long> acc;
   long long* hAcc = nullptr;  // pinned
   cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -355,7 +370,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rQ0); REL(rQ1); REL(rQ2); REL(rQ3); REL(rQ4); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc); REL(stage);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -1429,15 +1444,14 @@ int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* o) {
   o->n = n;
   if (n == 0) return CANNON_OK;
   W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
-  std::vector<float4> t4(n);
+  W_TRY(w, w->stage.reserve((size_t)4 * n));
+  cudaStream_t gs = w->ctx->stream;
   auto get4 = [&](float* dst, const float4* src, int comps) -> cudaError_t {
-    cudaError_t e = cudaMemcpy(t4.data(), src, n * sizeof(float4), cudaMemcpyDeviceToHost);
+    g_kernel_launches++;
+    k_unpack_from4<<<grid_for(w, n, 256), 256, 0, gs>>>(src, w->stage.p, n, comps);
+    cudaError_t e = cudaMemcpyAsync(dst, w->stage.p, (size_t)comps * n * sizeof(float), cudaMemcpyDeviceToHost, gs);
     if (e != cudaSuccess) return e;
-    for (int k = 0; k < n; k++) {
-      dst[comps * k] = t4[k].x; dst[comps * k + 1] = t4[k].y; dst[comps * k + 2] = t4[k].z;
-      if (comps == 4) dst[4 * k + 3] = t4[k].w;
-    }
-    return cudaSuccess;
+    return cudaStreamSynchronize(gs);
   };
   if (o->position) W_TRY(w, get4(o->position, w->pos.p, 3));
   if (o->quaternion) W_TRY(w, get4(o->quaternion, w->quat.p, 4));
@@ -1508,10 +1522,13 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
   if (count == 0) return CANNON_OK;
   cudaStream_t s = w->ctx->stream;
   W_TRY(w, cudaStreamSynchronize(s));
-  std::vector<float4> t4(count);
+  W_TRY(w, w->stage.reserve((size_t)4 * w->n));
   auto put = [&](const float* src, float4* dst, int comps) -> cudaError_t {
-    for (int k = 0; k < count; k++) t4[k] = make_float4(src[comps * k], src[comps * k + 1], src[comps * k + 2], comps == 4 ? src[4 * k + 3] : 0.f);
-    return cudaMemcpy(dst + first, t4.data(), count * sizeof(float4), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyAsync(w->stage.p, src, (size_t)comps * count * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    g_kernel_launches++;
+    k_pack_to4<<<grid_for(w, count, 256), 256, 0, s>>>(w->stage.p, dst + first, count, comps);
+    return cudaStreamSynchronize(s);  // the caller's buffer may be reused as soon as we return
   };
   if (position) W_TRY(w, put(position, w->pos.p, 3));
   if (quaternion) W_TRY(w, put(quaternion, w->quat.p, 4));

@@ -19,7 +19,7 @@ namespace cg = cooperative_groups;
 
 #define SAT_MAXF 32
 #define SAT_MAXE 32
-#define SAT_GROUP 8            // lanes per task (a tile of the warp); 4 tasks share a warp
+#define SAT_GROUP 8  // lanes per task (a tile of the warp); 4 tasks share a warp
 #define SAT_TILES 8            // tiles per CTA
 
 struct SatScratch {

@@ -207,8 +207,10 @@ class DeviceWorld:
         self._keep.clear()
 
     # ---- downloads -----------------------------------------------------------------------------
-    def get_bodies(self, fields: Sequence[str] = ("position", "quaternion", "velocity", "angular_velocity")) -> Dict[str, np.ndarray]:
-        soa, held = self._soa({}, self.n, allocate=fields)
+    def get_bodies(self, fields: Sequence[str] = ("position", "quaternion", "velocity", "angular_velocity"),
+                   out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """Download body arrays. `out` may hold preallocated (e.g. pinned) C-contiguous arrays to fill in place."""
+        soa, held = self._soa(dict(out) if out else {}, self.n, allocate=fields)
         self._chk(self.lib.cannon_world_get_bodies(self.handle, C.byref(soa)))
         return held
 
