@@ -1061,7 +1061,9 @@ __global__ void __launch_bounds__(256) k_zero_tail(int* eRows, const int* nUnits
 
 // cooperative grid size: enough CTAs for the widest level seen last time, never more than can be co-resident
 static int coop_blocks(cannon_world* w, int maxBlocks, long long widthEstimate) {
-  if (widthEstimate <= 0) return maxBlocks;
+  // the estimate comes from the last synchronised call; inside a long multi-step call a large world can grow far
+  // beyond it, so only small worlds (where the barrier latency matters) get a reduced grid
+  if (widthEstimate <= 0 || w->n >= 16384) return maxBlocks;
   long long b = (widthEstimate + 255) / 256;
   if (b < 1) b = 1;
   return (int)std::min<long long>(b, maxBlocks);
