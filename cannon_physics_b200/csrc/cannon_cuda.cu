@@ -28,7 +28,7 @@ enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
   CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_NUNITS, CT_NUNITS1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
-  CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = CT_BUCKETCURSOR + NP_NTYPES, CT_COUNT = CT_BAR + 2
+  CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
 __global__ void k_bucket_starts(int* cnt) {
@@ -129,6 +129,7 @@ struct cannon_world {
   std::vector<double> hHfData;
   std::vector<double> hLdamp, hAdamp;
   std::vector<int> hBig, hBigWorldStart, hWorldStart;
+  bool hasOversizeHull = false;  // some hull exceeds the tile kernel's scratch: run the sequential SAT kernels for those tasks
   double cell = 1.0;
   int nBig = 0, hashSize = 1024;
   int nMat = 0;
@@ -492,6 +493,8 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.pad = 0;
   }
   std::vector<HullDev> hulls;
+  w->hasOversizeHull = false;
+  for (const HostHull& h : w->hHulls) if (h.faces.size() > 32 || h.edges.size() > 32) w->hasOversizeHull = true;
   std::vector<float4> verts, fnormals, edges;
   std::vector<double> fplanec;
   std::vector<int> fvOff, fvIdx, fcOff, fcIdx;
@@ -1004,9 +1007,11 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
   if (!w->hHfs.empty()) {
     { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A); }
     { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
   }
   { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
   W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }
@@ -1111,7 +1116,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(coop_blocks(w, w->coopBlocksSched, lastUnits > 0 ? lastUnits / 2 + 1 : 0)), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[6], s);
-  W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
   { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
   { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NUNITS, w->unitCap); }
   { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
@@ -1291,7 +1296,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, 2 * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 2 * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 64 * sizeof(int), s));
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
   { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
   W_TRY(w, cudaGetLastError());

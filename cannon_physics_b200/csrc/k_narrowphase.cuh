@@ -798,11 +798,15 @@ __device__ inline void convex_convex_emit(RawOut& o, const HullView& HA, const H
   }
 }
 
-__global__ void __launch_bounds__(64) k_np_hull_hull(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+// hulls too large for the shared-memory scratch of the tile kernel (k_sat_warp.cuh: more than 32 faces or unique edges)
+__device__ __forceinline__ bool sat_oversize(const HullView& HA, const HullView& HB) { return HA.nF > 32 || HB.nF > 32 || HA.nE > 32 || HB.nE > 32; }
+
+__global__ void __launch_bounds__(64) k_np_hull_hull(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow, int oversizeOnly) {
   NP_BUCKET_LOOP(NP_HH) {
     TaskCtx c; load_task(B, T, A, NP_TASK(NP_HH), c);
     RawOut o; o.A = A; o.task = c.task;
     const HullView HA = hull_view(T, c.si.hull), HB = hull_view(T, c.sj.hull);
+    if (oversizeOnly && !sat_oversize(HA, HB)) continue;
     convex_convex_emit(o, HA, HB, c.xi, c.xj, c.qi, c.qj, c.xi, c.xj, false, clipOverflow);
   }
 }
@@ -909,10 +913,14 @@ __global__ void __launch_bounds__(64) k_np_sphere_pillar(BodyArrays B, ShapeTabl
 }
 
 // heightfieldConvex / boxHeightfield, narrow_phase.dart:2116-2175: convexConvex(hull, pillar, faceListA=[0])
-__global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+__global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow, int oversizeOnly) {
   NP_BUCKET_LOOP(NP_HPIL) {
     TaskCtx c; load_task(B, T, A, NP_TASK(NP_HPIL), c);
     RawOut o; o.A = A; o.task = c.task;
+    if (oversizeOnly) {
+      const HullDev hd = T.hulls[c.si.hull];
+      if (!(hd.nF > 32 || hd.nE > 32)) continue;
+    }
     const HfDev hf = T.hfs[c.sj.hf];
     const int2 cell = A.taskCell[c.task];
     const bool upper = (c.info >> 4) & 1;

@@ -125,7 +125,7 @@ __device__ inline int clip_hulls_s(SatScratch& S, const HullView& HA, const f3& 
 }
 
 template <bool PILLAR>
-__global__ void __launch_bounds__(SAT_TILES * SAT_GROUP) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+__global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
   __shared__ SatScratch s_scr[SAT_TILES];
   cg::thread_block_tile<SAT_GROUP> tile = cg::tiled_partition<SAT_GROUP>(cg::this_thread_block());
   const int lane = tile.thread_rank(), tib = threadIdx.x / SAT_GROUP;
@@ -204,9 +204,7 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP) k_np_hull_warp(BodyArra
     bool candidate = PILLAR ? (vdist(c.xi, xB) < HB.bsr + HA.bsr) : true;
     if (candidate && (vdist(c.xi, xB) > HA.bsr + HB.bsr)) candidate = false;  // convexConvex's own bounding test (:1999)
     if (candidate && (HA.nF > SAT_MAXF || HB.nF > SAT_MAXF || HA.nE > SAT_MAXE || HB.nE > SAT_MAXE)) {
-      // oversized hulls: sequential path on lane 0
-      if (lane == 0) convex_convex_emit(o, HA, HB, c.xi, xB, c.qi, c.qj, c.xi, c.xj, PILLAR, clipOverflow);
-      continue;
+      continue;  // oversized hulls are left to the sequential kernels (k_np_hull_hull / k_np_hull_pillar, oversizeOnly)
     }
     if (candidate) {
       for (int i = lane; i < HA.nF; i += SAT_GROUP) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));

@@ -208,15 +208,23 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
 }
 
 // ---- grid barrier -----------------------------------------------------------------------------------
-// Monotonic-counter barrier for cooperative (co-resident) launches. `bar` is zeroed before the launch.
+// Barrier for cooperative (co-resident) launches; `bar` (64 words, zeroed before the launch) holds a monotonic
+// arrival counter in word 0 and the published generation in word 32 (its own 128-byte line). Only the arrivals
+// touch the counter (one atomic per CTA); the last arriver publishes the generation and everybody else polls that
+// second line with a short sleep, so the pollers do not fight the atomics for the same L2 line.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
   __syncthreads();
   if (gridDim.x == 1) return;  // single-CTA launches (small worlds) only need the block barrier
   if (threadIdx.x == 0) {
-    epoch += gridDim.x;
+    epoch += 1;
     __threadfence();
-    atomicAdd(bar, 1u);
-    while (*(volatile unsigned*)bar < epoch) {}
+    const unsigned arrived = atomicAdd(bar, 1u) + 1u;
+    volatile unsigned* gen = (volatile unsigned*)(bar + 32);
+    if (arrived == epoch * gridDim.x) {
+      *gen = epoch;
+    } else {
+      while (*gen < epoch) __nanosleep(20);
+    }
     __threadfence();
   }
   __syncthreads();

@@ -173,3 +173,23 @@ def test_colored_solver_statistical_agreement_and_determinism(cuda_lib):
         assert s["position"][5:, 1].min() > 0.2  # rest penetration below 0.05
     assert abs(a["position"][5:, 1].mean() - b["position"][5:, 1].mean()) < 0.05
     assert abs(np.sort(a["position"][5:, 1])[-1] - np.sort(b["position"][5:, 1])[-1]) < 0.15
+
+
+def test_oversize_hulls_take_the_sequential_sat_path(cuda_lib, oracle_lib):
+    # 40-segment cylinders have 42 faces / 41 unique edges: larger than the tile kernel's scratch (32), so these
+    # tasks run through the sequential SAT kernels; small hulls in the same scene still use the tile kernel
+    from cannon_physics_b200.engine import SceneSpec
+    n = 7
+    b = {"position": np.array([[0, 0, 0], [0, 0.6, 0], [0.2, 1.7, 0.1], [0.1, 2.9, 0], [1.3, 0.6, 0], [1.2, 1.8, 0.2], [-1.0, 0.5, 0.3]], np.float32),
+         "quaternion": np.tile(np.array([0, 0, 0, 1], np.float32), (n, 1)), "mass": np.array([0, 1, 1, 1, 1, 1, 1.0]),
+         "shape": np.array([0, 1, 2, 1, 2, 3, 4], np.int32)}
+    b["quaternion"][0] = scenes.GROUND_QUAT
+    tetra = dict(type=F.SHAPE_CONVEX, vertices=[(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], faces=[(0, 3, 2), (0, 1, 3), (0, 2, 1), (1, 2, 3)])
+    shapes = [dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_CYLINDER, radius_top=0.5, radius_bottom=0.5, height=1.0, num_segments=40),
+              dict(type=F.SHAPE_BOX, half_extents=(0.5, 0.5, 0.5)), dict(type=F.SHAPE_CYLINDER, radius_top=0.4, radius_bottom=0.5, height=1.0, num_segments=8), tetra]
+    spec = SceneSpec(desc=dict(gravity=(0, -10, 0)), shapes=shapes, bodies=b, n_bodies=n)
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    seen = 0
+    for s in range(80):
+        seen = max(seen, parity.staged_step(dev, ref, 1 / 60, f"oversize step {s}")[1])
+    assert seen > 8
