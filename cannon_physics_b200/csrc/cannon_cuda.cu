@@ -200,10 +200,16 @@ struct cannon_world {
   long long lastUnits = 0, lastLevels = 0;  // widths seen by the last synchronised call (sizes the cooperative grids)
   bool recordSolveEvents = false;
   int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0;
+  // resolver kernels of different types are independent: they run on side streams between two events
+  cudaStream_t npStream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t npFork = nullptr, npJoin[3] = {nullptr, nullptr, nullptr};
 
   ~cannon_world() {
     if (hCnt) cudaFreeHost(hCnt);
     if (hAcc) cudaFreeHost(hAcc);
+    for (auto& st : npStream) if (st) cudaStreamDestroy(st);
+    if (npFork) cudaEventDestroy(npFork);
+    for (auto& e : npJoin) if (e) cudaEventDestroy(e);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 };
@@ -333,6 +339,9 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   memset(w->hAcc, 0, AC_COUNT * sizeof(long long));
   cudaMemsetAsync(w->acc.p, 0, AC_COUNT * sizeof(long long), ctx->stream);
   for (auto& e : w->ev) cudaEventCreate(&e);
+  for (auto& st : w->npStream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&w->npFork, cudaEventDisableTiming);
+  for (auto& e : w->npJoin) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   // empty tables so kernels always get valid pointers
   std::vector<double> e0;
   upload(w->dMatFriction, e0, ctx->stream);
@@ -1001,17 +1010,32 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_bucket_starts<<<1, 32, 0, s>>>(cnt); }
   { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1); }
   const int g = w->ctx->sms * 8;
+  // fork: the heavy SAT kernels go to side streams, the cheap analytic resolvers stay on the main stream
+  cudaStream_t s1 = w->npStream[0], s2 = w->npStream[1], s3 = w->npStream[2];
+  W_TRY(w, cudaEventRecord(w->npFork, s));
+  W_TRY(w, cudaStreamWaitEvent(s1, w->npFork, 0));
+  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
+  W_TRY(w, cudaEventRecord(w->npJoin[0], s1));
+  const bool hf = !w->hHfs.empty();
+  if (hf) {
+    W_TRY(w, cudaStreamWaitEvent(s2, w->npFork, 0));
+    { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
+    W_TRY(w, cudaEventRecord(w->npJoin[1], s2));
+    W_TRY(w, cudaStreamWaitEvent(s3, w->npFork, 0));
+    { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s3>>>(B, T, A); }
+    W_TRY(w, cudaEventRecord(w->npJoin[2], s3));
+  }
   { g_kernel_launches++; k_np_sphere_sphere<<<g, 256, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_plane<<<g, 256, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
-  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
-  if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
-  if (!w->hHfs.empty()) {
-    { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s>>>(B, T, A); }
-    { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP); }
-    if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
+  W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[0], 0));
+  if (hf) {
+    W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[1], 0));
+    W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[2], 0));
   }
   { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
   W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }
