@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="c3")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named configuration's body count")
+    ap.add_argument("--solver", default="auto", choices=["auto", "colored", "reference"],
+                    help="override the solver kind of the configuration (reference = GSSolver equation order, bit-reproducible)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -203,6 +205,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev_t)
 
     spec, label = build_spec(args.config, args.scale, rank, world_size)
+    if args.solver != "auto":
+        from cannon_physics_b200 import _ffi as F
+        spec.desc["solver_kind"] = F.SOLVER_COLORED if args.solver == "colored" else F.SOLVER_REFERENCE_ORDER
+        label += f" [solver={args.solver}]"
     nd = n_dynamic(spec)
     world = engine.DeviceWorld(cp.lib, spec, device=local_rank)
 
@@ -239,7 +245,9 @@ def main():
     gs_ms = prof["gs_ms"]
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (gs_ms / 1000.0) / 1e9 if gs_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_gs", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    from cannon_physics_b200 import _ffi as _F
+    gs_kernel = "k_gs_fast" if spec.desc.get("solver_kind") == _F.SOLVER_COLORED else "k_gs"
+    roofline = {"bound": "hbm", "kernel": gs_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": gs_ms,
                 "share_of_step": gs_ms / (total_ms / K) if total_ms > 0 else None}
