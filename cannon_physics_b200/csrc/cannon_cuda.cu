@@ -6,6 +6,7 @@
 // device cannon_ctx_create fails with CANNON_E_NOGPU.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1111,6 +1112,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   SolveParams P;
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
   P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
+  P.debugSkipWork = getenv("CANNON_DEBUG_SKIP_GS_WORK") ? 1 : 0;
   const int gc = grid_for(w, w->contactCap, 256);
   { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p); }
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));

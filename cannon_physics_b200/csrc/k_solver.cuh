@@ -71,6 +71,7 @@ struct SolveParams {
   int nBodies;
   int nWorlds;
   int colored;
+  int debugSkipWork;  // profiling aid (CANNON_DEBUG_SKIP_GS_WORK=1): run only the barrier skeleton of the sweeps
 };
 
 // rigid_body.dart:303-314
@@ -433,6 +434,9 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // units of a level are dealt to the CTAs warp by warp (32 consecutive units per warp, consecutive warps on different
+  // CTAs), so a narrow level still spreads over every SM instead of filling the first few CTAs
+  const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
   const int nLevels = *S.nLevels;
   const bool batch = P.nWorlds > 1;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
     double local = 0.0;
     for (int lvl = 0; lvl < nLevels; lvl++) {
       const int a0 = S.levelStart[lvl], a1 = S.levelStart[lvl + 1];
-      for (int a = a0 + tid; a < a1; a += nth) {
+      for (int a = a0 + itid; a < a1; a += nth) {
         const int r0 = U.eRowBase[a], r1 = U.eRowBase[a + 1];
         if (r0 == r1) continue;
         const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
@@ -537,6 +541,9 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // units of a level are dealt to the CTAs warp by warp (32 consecutive units per warp, consecutive warps on different
+  // CTAs), so a narrow level still spreads over every SM instead of filling the first few CTAs
+  const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
   const int nLevels = *S.nLevels;
   const bool batch = P.nWorlds > 1;
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
     double local = 0.0;
     for (int lvl = 0; lvl < nLevels; lvl++) {
       const int a0 = S.levelStart[lvl], a1 = S.levelStart[lvl + 1];
-      for (int a = a0 + tid; a < a1; a += nth) {
+      for (int a = a0 + itid; a < (P.debugSkipWork ? a0 : a1); a += nth) {
         const int r0 = U.eRowBase[a], r1 = U.eRowBase[a + 1];
         if (r0 == r1) continue;
         const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
       grid_barrier(S.bar, epoch);
       if (tid == 0) G.worldDone[P.nWorlds] = 0;
     }
-    if (allDone) break;
+    if (allDone && !P.debugSkipWork) break;
   }
   if (tid == 0) *G.itersDone = iter;
 }
