@@ -20,7 +20,7 @@ SHAPE_SPHERE, SHAPE_PLANE, SHAPE_BOX, SHAPE_CONVEX, SHAPE_CYLINDER, SHAPE_HEIGHT
 BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC = 0, 1, 2
 AWAKE, SLEEPY, SLEEPING = 0, 1, 2
 BP_NAIVE, BP_SAP, BP_GRID = 0, 1, 2
-SOLVER_REFERENCE_ORDER, SOLVER_COLORED = 0, 1
+SOLVER_REFERENCE_ORDER, SOLVER_COLORED, SOLVER_SPLIT = 0, 1, 2
 CONSTRAINT_POINT_TO_POINT, CONSTRAINT_HINGE = 0, 1
 
 
@@ -106,7 +106,7 @@ class Profile(C.Structure):
         ("integrate", c_f64), ("narrowphase", c_f64),
         ("n_pairs", c_i64), ("n_contacts", c_i64), ("n_rows", c_i64), ("n_levels", c_i64),
         ("iterations_done", c_i64), ("steps", c_i64), ("contact_iters_total", c_i64),
-        ("step_call_ms", c_f64), ("schedule_ms", c_f64), ("gs_ms", c_f64), ("kernel_launches", c_i64), ("n_tasks", c_i64), ("n_tasks_by_type", c_i64 * 8),
+        ("step_call_ms", c_f64), ("schedule_ms", c_f64), ("gs_ms", c_f64), ("kernel_launches", c_i64), ("n_tasks", c_i64), ("n_islands", c_i64), ("n_tasks_by_type", c_i64 * 8),
     ]
 
 

@@ -28,7 +28,7 @@ from .engine import Context, DeviceWorld, SceneSpec
 __all__ = [
     "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
-    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "World",
+    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "World",
     "CudaWorld", "CannonError",
 ]
 
@@ -291,6 +291,15 @@ class GSSolver(Solver):  # gs_solver.dart:7 — reference equation order, bit-re
 
 class CudaGSSolver(Solver):  # graph-coloured throughput mode
     kind = F.SOLVER_COLORED
+
+
+class SplitSolver(Solver):  # lib/solver/split_solver.dart:32: islands + one GSSolver pass per island
+    kind = F.SOLVER_SPLIT
+
+    def __init__(self, subsolver: Optional[Solver] = None):
+        sub = subsolver or GSSolver()
+        super().__init__(iterations=sub.iterations, tolerance=sub.tolerance)
+        self.subsolver = sub
 
 
 class Constraint:  # constraint_class.dart:5

@@ -28,7 +28,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_NUNITS, CT_NUNITS1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_NUNITS, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -186,7 +186,7 @@ struct cannon_world {
   int nJointEq = 0, nJointAccepted = 0;
   // device: scheduler / gs
   DBuf<unsigned long long> claim;
-  DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters;
+  DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters, islandLabel;
   DBuf<double> worldTot;
   int maxLevels = 0;
   // counters
@@ -381,7 +381,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rQ0); REL(rQ1); REL(rQ2); REL(rQ3); REL(rQ4); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc); REL(stage);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -638,7 +638,9 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
-  RES(worldRows, nW + 1); RES(worldDone, nW + 2); RES(worldIters, nW + 1); RES(worldTot, nW + 1);
+  const int nGroupsMax = w->desc.solver_kind == CANNON_SOLVER_SPLIT ? std::max(nW, n) : nW;  // islands are labelled by body index
+  RES(worldRows, nW + 1); RES(worldDone, nGroupsMax + 2); RES(worldIters, nGroupsMax + 1); RES(worldTot, nGroupsMax + 1);
+  RES(islandLabel, n + 1);
 #undef RES
   return CANNON_OK;
 }
@@ -1118,12 +1120,14 @@ static int32_t st_solve(cannon_world* w, double dt) {
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
   W_TRY(w, scan_exclusive(w->contFlag.p, w->contOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_CONTTOTAL, w->scanTmp, s));
   { g_kernel_launches++; k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n); }
+  const bool split = w->desc.solver_kind == CANNON_SOLVER_SPLIT;
+  const int nGroups = split ? w->n : nW;
   W_TRY(w, cudaMemsetAsync(w->worldRows.p, 0, (nW + 1) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nW + 2) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nW + 1) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nW + 1) * sizeof(double), s));
+  W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nGroups + 2) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nGroups + 1) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nGroups + 1) * sizeof(double), s));
   UnitSrc Us;
-  Us.colored = P.colored; Us.fricFlag = w->fricFlag.p; Us.contFlag = w->contFlag.p; Us.fricOff = w->fricOff.p; Us.contOff = w->contOff.p;
+  Us.colored = P.colored; Us.split = split ? 1 : 0; Us.fricFlag = w->fricFlag.p; Us.contFlag = w->contFlag.p; Us.fricOff = w->fricOff.p; Us.contOff = w->contOff.p;
   Us.fricTotal = cnt + CT_FRICTOTAL; Us.contTotal = cnt + CT_CONTTOTAL; Us.taskOff = w->taskOff.p; Us.taskCnt = w->taskCnt.p;
   Us.nTasks = cnt + CT_NTASKS; Us.taskCap = w->taskCap; Us.contactCap = w->contactCap;
   { g_kernel_launches++; k_units_build<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, C, Us, J, U, nW, w->worldRows.p, cnt + CT_OVF_ROWS); }
@@ -1143,6 +1147,17 @@ static int32_t st_solve(cannon_world* w, double dt) {
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[6], s);
   W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
+  if (split) {  // island labels for the per-island tolerance exits of SplitSolver
+    int nb = w->n;
+    int* label = w->islandLabel.p;
+    int* changed = cnt + CT_ISL_CHANGED0;
+    int* nIsl = cnt + CT_NISLANDS;
+    unsigned* bar = S.bar;
+    void* args[] = {&B, &U, &nb, &label, &changed, &nIsl, &bar};
+    g_kernel_launches++;
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_islands, dim3(coop_blocks(w, w->coopBlocksSched, lastUnits > 0 ? lastUnits / 2 + 1 : 0)), dim3(256), args, 0, s));
+    W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
+  }
   { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
   { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NUNITS, w->unitCap); }
   { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
@@ -1151,6 +1166,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   if (w->recordSolveEvents) cudaEventRecord(w->ev[7], s);
   GsStats G;
   G.worldTot = w->worldTot.p; G.worldDone = w->worldDone.p; G.worldIters = w->worldIters.p; G.itersDone = cnt + CT_ITERS;
+  G.bodyGroup = split ? w->islandLabel.p : w->world.p; G.nGroups = nGroups;
   {
     void* args[] = {&R, &B, &U, &S, &P, &G};
     g_kernel_launches++;
@@ -1321,7 +1337,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   // keep the pair/task/contact counts of the preceding narrowphase call, clear the solver's
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, 2 * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, 5 * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 64 * sizeof(int), s));
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
   { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
@@ -1334,6 +1350,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   w->prof.n_levels = w->hCnt[CT_NLEVELS];
   w->prof.iterations_done = w->hCnt[CT_ITERS];
   w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
+  w->prof.n_islands = w->hCnt[CT_NISLANDS];
   if (iterations_done) *iterations_done = w->hCnt[CT_ITERS];
   return CANNON_OK;
 }
@@ -1399,6 +1416,7 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
     p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
     w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
     p.n_tasks = w->hCnt[CT_NTASKS];
+    p.n_islands = w->hCnt[CT_NISLANDS];
     for (int t = 0; t < NP_NTYPES; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];
   }
   return CANNON_OK;
@@ -1448,7 +1466,7 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   W_TRY(w, cudaMemcpy(uLvl.data(), w->unitLevel.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
   W_TRY(w, cudaMemcpy(uRows.data(), w->uRows.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
   int out = 0;
-  const bool refOrder = w->desc.solver_kind == CANNON_SOLVER_REFERENCE_ORDER;
+  const bool refOrder = w->desc.solver_kind != CANNON_SOLVER_COLORED;
   std::vector<int> unitsInOrder(nu);
   if (refOrder) { for (int u = 0; u < nu; u++) unitsInOrder[u] = u; }
   else {

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) k_contact_flags(BodyArrays B, ContactArra
 
 struct UnitSrc {  // what the units are made from
   int colored;
+  int split;   // SplitSolver order: descending creation id (joints first created, then per contact: contact, friction 1, friction 2)
   const int* fricFlag; const int* contFlag;
   const int* fricOff; const int* contOff;   // exclusive scans over contacts
   const int* fricTotal; const int* contTotal;
@@ -191,6 +192,24 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
       }
       put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows);
     }
+  } else if (S.split) {
+    // unit id = position in descending creation-id order (split_solver.dart:108,167-169)
+    const int last = nUnits - 1;
+    for (int c = tid; c < nc; c += nth) {
+      const int bi = C.bi[c], bj = C.bj[c];
+      const int asc = J.nAccepted + S.contOff[c] + 2 * S.fricOff[c];
+      const int cf = S.contFlag[c];
+      if (cf) put_unit(U, B, last - asc, bi, bj, 1, c * 8 + SRC_NORMAL, nWorlds, worldRows);
+      if (S.fricFlag[c]) {
+        put_unit(U, B, last - (asc + cf), bi, bj, 1, c * 8 + SRC_FRIC1, nWorlds, worldRows);
+        put_unit(U, B, last - (asc + cf + 1), bi, bj, 1, c * 8 + SRC_FRIC2, nWorlds, worldRows);
+      }
+    }
+    for (int s = tid; s < J.nAccepted; s += nth) {
+      const int e = J.slotEq[s];
+      put_unit(U, B, last - s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
+    }
+    return;
   } else {
     for (int c = tid; c < nc; c += nth) {
       const int bi = C.bi[c], bj = C.bj[c];
@@ -207,6 +226,11 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
     put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
   }
 }
+
+// Islands of SplitSolver (split_solver.dart:76-117): connected components of the non-static bodies under the
+// accepted equations; label = smallest body index of the component (min-label propagation + pointer jumping).
+__global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int nBodies, int* __restrict__ label, int* __restrict__ changed,
+                                                 int* __restrict__ nIslands, unsigned* bar);
 
 // ---- grid barrier -----------------------------------------------------------------------------------
 // Barrier for cooperative (co-resident) launches; `bar` (64 words, zeroed before the launch) holds a monotonic
@@ -229,6 +253,44 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
     __threadfence();
   }
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int nBodies, int* __restrict__ label, int* __restrict__ changed,
+                                                 int* __restrict__ nIslands, unsigned* bar) {
+  unsigned epoch = 0;
+  const int nUnits = min(*U.nUnits, U.unitCap);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int b = tid; b < nBodies; b += nth) label[b] = B.type[b] == CANNON_BODY_STATIC ? -1 : b;
+  if (tid == 0) { changed[0] = 0; changed[1] = 0; *nIslands = 0; }
+  grid_barrier(bar, epoch);
+  for (int round = 0;; round++) {
+    int* flag = &changed[round & 1];
+    for (int u = tid; u < nUnits; u += nth) {
+      if (U.uRows[u] == 0) continue;
+      const int bi = U.uBi[u], bj = U.uBj[u];
+      const int la = __ldcg(&label[bi]), lb = __ldcg(&label[bj]);
+      if (la < 0 || lb < 0 || la == lb) continue;  // static bodies do not merge islands
+      const int m = min(la, lb);
+      // hook the larger root label onto the smaller one
+      atomicMin(&label[max(la, lb)], m);
+      atomicMin(&label[bi], m);
+      atomicMin(&label[bj], m);
+      *flag = 1;
+    }
+    grid_barrier(bar, epoch);
+    for (int b = tid; b < nBodies; b += nth) {  // pointer jumping
+      int l = __ldcg(&label[b]);
+      if (l < 0) continue;
+      int r = __ldcg(&label[l]);
+      while (r != l) { l = r; r = __ldcg(&label[l]); }
+      label[b] = l;
+    }
+    if (tid == 0) changed[(round + 1) & 1] = 0;
+    grid_barrier(bar, epoch);
+    if (__ldcg(flag) == 0) break;
+  }
+  for (int b = tid; b < nBodies; b += nth)
+    if (label[b] == b) atomicAdd(nIslands, 1);
 }
 
 struct SchedArrays {
@@ -410,6 +472,8 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
 }
 
 struct GsStats {
+  const int* bodyGroup; // grouped early exit: world id (batches) or island label (SplitSolver); -1 = static body
+  int nGroups;          // <= 1: one group (plain GSSolver)
   double* worldTot;     // per world: sum |delta lambda| of the current iteration
   int* worldDone;       // per world: 1 once the tolerance test passed (gs_solver.dart:105)
   int* worldIters;      // per world: value of `iter` when its loop ended
@@ -439,7 +503,7 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
   const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
   const int nLevels = *S.nLevels;
-  const bool batch = P.nWorlds > 1;
+  const bool batch = G.nGroups > 1;
   int iter = 0;
   for (; iter != P.maxIter; iter++) {
     double local = 0.0;
@@ -451,8 +515,9 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
         const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
         int w = 0;
         if (batch) {
-          w = B.world[bi];
-          if (__ldcg(&G.worldDone[w])) continue;
+          w = G.bodyGroup[bi];
+          if (w < 0) w = G.bodyGroup[bj];
+          if (w < 0 || __ldcg(&G.worldDone[w])) continue;
         }
         const double imA = U.eImA[a], imB = U.eImB[a];
         // the two bodies' lambda vectors stay in registers across the unit's rows (gs_solver.dart:88-102,
@@ -511,7 +576,7 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
       if (threadIdx.x == 0) s_any = 0;
       __syncthreads();
       int anyLive = 0;
-      for (int w = tid; w < P.nWorlds; w += nth) {
+      for (int w = tid; w < G.nGroups; w += nth) {
         if (G.worldDone[w]) continue;
         const double tot = __ldcg(&G.worldTot[w]);
         if (tot * tot < P.tol2) { G.worldDone[w] = 1; G.worldIters[w] = iter; }
@@ -519,11 +584,11 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
       }
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
-      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[P.nWorlds], 1);  // slot nWorlds: "some world still iterating"
+      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);  // slot nWorlds: "some world still iterating"
       grid_barrier(S.bar, epoch);
-      allDone = __ldcg(&G.worldDone[P.nWorlds]) == 0;
+      allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
       grid_barrier(S.bar, epoch);
-      if (tid == 0) G.worldDone[P.nWorlds] = 0;
+      if (tid == 0) G.worldDone[G.nGroups] = 0;
     }
     if (allDone) break;
   }
@@ -546,7 +611,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
   const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
   const int nLevels = *S.nLevels;
-  const bool batch = P.nWorlds > 1;
+  const bool batch = G.nGroups > 1;
   int iter = 0;
   for (; iter != P.maxIter; iter++) {
     double local = 0.0;
@@ -558,8 +623,9 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
         const int bi = U.eBi[a], bj = U.eBj[a], fl = U.eFlags[a];
         int w = 0;
         if (batch) {
-          w = B.world[bi];
-          if (__ldcg(&G.worldDone[w])) continue;
+          w = G.bodyGroup[bi];
+          if (w < 0) w = G.bodyGroup[bj];
+          if (w < 0 || __ldcg(&G.worldDone[w])) continue;
         }
         const float imA = (float)U.eImA[a], imB = (float)U.eImB[a];
         float4 vA = __ldcg(&B.vlam[bi]), wA = __ldcg(&B.wlam[bi]);
@@ -632,7 +698,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
       if (threadIdx.x == 0) s_any = 0;
       __syncthreads();
       int anyLive = 0;
-      for (int w = tid; w < P.nWorlds; w += nth) {
+      for (int w = tid; w < G.nGroups; w += nth) {
         if (G.worldDone[w]) continue;
         const double tot = __ldcg(&G.worldTot[w]);
         if (tot * tot < P.tol2) { G.worldDone[w] = 1; G.worldIters[w] = iter; }
@@ -640,11 +706,11 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
       }
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
-      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[P.nWorlds], 1);
+      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);
       grid_barrier(S.bar, epoch);
-      allDone = __ldcg(&G.worldDone[P.nWorlds]) == 0;
+      allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
       grid_barrier(S.bar, epoch);
-      if (tid == 0) G.worldDone[P.nWorlds] = 0;
+      if (tid == 0) G.worldDone[G.nGroups] = 0;
     }
     if (allDone && !P.debugSkipWork) break;
   }

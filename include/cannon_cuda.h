@@ -62,8 +62,13 @@ enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
  *   REFERENCE_ORDER: GSSolver with the reference's exact equation order
  *       (lib/world/world_class.dart:539-541,562,627-635); bit-reproducible validation mode.
  *   COLORED: graph-coloured Gauss-Seidel (throughput mode; different row order, so only
- *       statistical agreement with the reference). */
-enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1 };
+ *       statistical agreement with the reference).
+ *   SPLIT: SplitSolver(GSSolver) (lib/solver/split_solver.dart:50-120): islands of non-static bodies
+ *       connected by equations, one independent GSSolver pass per island (own tolerance early-exit),
+ *       island equations in descending Equation.id order. The reference's ids depend on its object-pool
+ *       history; here ids are the history-free creation order of a pool-less step
+ *       (constraint equations first, then per contact: contact, friction 1, friction 2). */
+enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1, CANNON_SOLVER_SPLIT = 2 };
 /* Constraint kinds, lib/constraints/{point_to_point,hinge}_constraint.dart */
 enum { CANNON_CONSTRAINT_POINT_TO_POINT = 0, CANNON_CONSTRAINT_HINGE = 1 };
 
@@ -207,6 +212,7 @@ typedef struct cannon_profile {
   double gs_ms;          /* Gauss-Seidel sweep kernel of the last step */
   int64_t kernel_launches; /* kernels launched by the library since world creation */
   int64_t n_tasks;         /* narrowphase resolver tasks of the last step (pairs + heightfield pillars) */
+  int64_t n_islands;       /* SPLIT solver: islands of the last solve (SplitSolver.solve's return value) */
   int64_t n_tasks_by_type[8]; /* sphere-sphere, sphere-plane, sphere-box, sphere-hull, plane-hull, hull-hull, sphere-pillar, hull-pillar */
 } cannon_profile;
 

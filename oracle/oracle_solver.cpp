@@ -9,7 +9,10 @@
  *   lib/constraints/{point_to_point,hinge}_constraint.dart  update()
  *   lib/objects/rigid_body.dart:263-314,627-680  sleep FSM, solve mass, integrate
  */
+#include <algorithm>
 #include <cmath>
+#include <unordered_map>
+#include <utility>
 
 #include "oracle_world.h"
 
@@ -115,14 +118,14 @@ void updateSolveMassProperties(Body& b) {
 }
 
 // GSSolver.solve, gs_solver.dart:27-133, over `eqs` and the bodies [b0,b1)
-int gsSolve(World& w, std::vector<Eq*>& eqs, int b0, int b1, double h, std::vector<RowDebug>& dbg) {
+int gsSolve(World& w, std::vector<Eq*>& eqs, const std::vector<int>& bodyIdx, double h, std::vector<RowDebug>& dbg) {
   int iter = 0;
   const int maxIter = w.desc.solver_iterations;
   const double tolSquared = w.desc.solver_tolerance * w.desc.solver_tolerance;
   const int nEq = (int)eqs.size();
   std::vector<Body>& bodies = w.bodies;
   if (nEq != 0)
-    for (int i = b0; i < b1; i++) updateSolveMassProperties(bodies[i]);
+    for (int i : bodyIdx) updateSolveMassProperties(bodies[i]);
   std::vector<double> invCs(nEq), bs(nEq), lambda(nEq);
   for (int i = 0; i != nEq; i++) {
     Eq& c = *eqs[i];
@@ -131,7 +134,7 @@ int gsSolve(World& w, std::vector<Eq*>& eqs, int b0, int b1, double h, std::vect
     invCs[i] = 1.0 / computeC(c, bodies[c.bi], bodies[c.bj]);
   }
   if (nEq != 0) {
-    for (int i = b0; i < b1; i++) {
+    for (int i : bodyIdx) {
       bodies[i].vlambda = V3{0, 0, 0};
       bodies[i].wlambda = V3{0, 0, 0};
     }
@@ -150,7 +153,7 @@ int gsSolve(World& w, std::vector<Eq*>& eqs, int b0, int b1, double h, std::vect
       }
       if (deltalambdaTot * deltalambdaTot < tolSquared) break;
     }
-    for (int i = b0; i < b1; i++) {
+    for (int i : bodyIdx) {
       Body& b = bodies[i];
       b.vlambda = mulc(b.vlambda, b.linearFactor);
       b.velocity = add(b.vlambda, b.velocity);
@@ -225,13 +228,67 @@ int World::solve(double h) {
   rows.clear();
   int itersMax = 0;
   const int nW = desc.n_worlds > 1 ? desc.n_worlds : 1;
-  if (nW == 1) {
+  if (desc.solver_kind == CANNON_SOLVER_SPLIT) {
+    // SplitSolver.solve, split_solver.dart:50-120. Equation ids = creation order of a pool-less step (constraint
+    // equations are constructed with their constraint, then per contact: ContactEquation, FrictionEquation x2);
+    // each island is solved in descending id order (sortById, :167-169).
+    std::vector<Eq*> byId;
+    for (Constraint& c : constraints)
+      for (Eq& e : c.eqs) byId.push_back(&e);
+    {
+      size_t f = 0;
+      for (Eq& c : contacts) {
+        byId.push_back(&c);
+        if (c.friction > 0) { byId.push_back(&frictions[f]); byId.push_back(&frictions[f + 1]); f += 2; }
+      }
+    }
+    std::vector<Eq*> acc;
+    for (Eq* e : byId) if (accept(*e)) acc.push_back(e);
+    const int nB = (int)bodies.size();
+    // islands: non-static bodies connected through equations (static bodies are never visited, :122-131)
+    std::vector<int> parent(nB);
+    for (int i = 0; i < nB; i++) parent[i] = i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (Eq* e : acc) {
+      if (bodies[e->bi].type == CANNON_BODY_STATIC || bodies[e->bj].type == CANNON_BODY_STATIC) continue;
+      int a = find(e->bi), b = find(e->bj);
+      if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+    std::vector<std::vector<int>> islandBodies(nB);
+    std::vector<std::vector<Eq*>> islandEqs(nB);
+    for (int i = 0; i < nB; i++) if (bodies[i].type != CANNON_BODY_STATIC) islandBodies[find(i)].push_back(i);
+    for (int k = (int)acc.size() - 1; k >= 0; k--) {  // descending id
+      Eq* e = acc[k];
+      int root = bodies[e->bi].type != CANNON_BODY_STATIC ? find(e->bi) : (bodies[e->bj].type != CANNON_BODY_STATIC ? find(e->bj) : -1);
+      if (root >= 0) islandEqs[root].push_back(e);
+    }
+    // debug rows are reported in the batch-wide descending-id order
+    std::vector<int> pos(acc.size());
+    int nIslands = 0;
+    std::vector<RowDebug> all;
+    std::unordered_map<Eq*, RowDebug> tagged;
+    for (int r = 0; r < nB; r++) {
+      if (islandBodies[r].empty()) continue;
+      nIslands++;
+      std::vector<RowDebug> dbg;
+      int it = gsSolve(*this, islandEqs[r], islandBodies[r], h, dbg);
+      if (it > itersMax) itersMax = it;
+      for (size_t k = 0; k < dbg.size(); k++) tagged[islandEqs[r][k]] = dbg[k];
+    }
+    for (int k = (int)acc.size() - 1; k >= 0; k--) {
+      auto it = tagged.find(acc[k]);
+      if (it != tagged.end()) rows.push_back(it->second);
+    }
+    prof.n_islands = nIslands;
+  } else if (nW == 1) {
     std::vector<Eq*> eqs;
     for (Eq& e : frictions) if (accept(e)) eqs.push_back(&e);
     for (Eq& e : contacts) if (accept(e)) eqs.push_back(&e);
     for (Constraint& c : constraints)
       for (Eq& e : c.eqs) if (accept(e)) eqs.push_back(&e);
-    itersMax = gsSolve(*this, eqs, 0, (int)bodies.size(), h, rows);
+    std::vector<int> all(bodies.size());
+    for (size_t i = 0; i < bodies.size(); i++) all[i] = (int)i;
+    itersMax = gsSolve(*this, eqs, all, h, rows);
   } else {
     // a batch is nW separate World objects in the reference: each solves its own equation list
     // (own iteration loop and tolerance early-exit) over its own bodies
@@ -252,7 +309,9 @@ int World::solve(double h) {
     for (int wi = 0; wi < nW; wi++) {
       if (wb0[wi] < 0) continue;
       std::vector<RowDebug> dbg;
-      int it = gsSolve(*this, per[wi], wb0[wi], wb1[wi], h, dbg);
+      std::vector<int> idx;
+      for (int i = wb0[wi]; i < wb1[wi]; i++) idx.push_back(i);
+      int it = gsSolve(*this, per[wi], idx, h, dbg);
       if (it > itersMax) itersMax = it;
       if ((int)rows.size() < gidx) rows.resize(gidx);
       for (size_t k = 0; k < dbg.size(); k++) rows[perGlobal[wi][k]] = dbg[k];

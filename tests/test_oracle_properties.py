@@ -91,6 +91,27 @@ def test_hinge_chain_hangs_without_drifting(oracle_lib):
     assert np.all(np.isfinite(s["position"])) and s["position"][1:, 1].min() > -0.1 and w.profile()["n_contacts"] > 0
 
 
+def test_split_solver_islands_and_agreement_with_gssolver(oracle_lib):
+    # SplitSolver (split_solver.dart:50-120): one island per stack; per-island GS gives the same physics as one big GS
+    def run(kind):
+        spec = scenes.box_stacks(4, 3, grid=2)
+        spec.desc["solver_kind"] = kind
+        w = engine.DeviceWorld(oracle_lib, spec)
+        w.step(1 / 60, 90)
+        return w, w.get_bodies(("position", "velocity"))
+    ws, split = run(F.SOLVER_SPLIT)
+    wg, gs = run(F.SOLVER_REFERENCE_ORDER)
+    assert ws.profile()["n_islands"] == 4 and wg.profile()["n_islands"] == 0
+    assert ws.profile()["n_rows"] > 0 and abs(ws.profile()["n_rows"] - wg.profile()["n_rows"]) <= 12  # trajectories differ slightly
+    assert np.abs(split["position"] - gs["position"]).max() < 2e-2  # different equation order: statistical agreement
+    # free bodies: every non-static body is its own island, no equations
+    spec = scenes.spheres_on_plane(2, 2, 2, y0=5.0)
+    spec.desc["solver_kind"] = F.SOLVER_SPLIT
+    w = engine.DeviceWorld(oracle_lib, spec)
+    w.step(1 / 60, 2)
+    assert w.profile()["n_islands"] == 8 and w.profile()["n_rows"] == 0
+
+
 GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small"]
 
 

@@ -33,6 +33,25 @@ STAGED = {
 }
 
 
+SPLIT = {
+    "split: spheres on plane": (lambda: _with(scenes.spheres_on_plane(4, 4, 3), solver_kind=F.SOLVER_SPLIT), 80),
+    "split: box stacks SAP": (lambda: _with(scenes.box_stacks(6, 4, grid=3), solver_kind=F.SOLVER_SPLIT), 60),
+    "split: jointed chains": (lambda: _with(scenes.chain_worlds(1, chains=3, links=5), solver_kind=F.SOLVER_SPLIT), 80),
+    "split: sleeping container": (lambda: _with(scenes.sphere_container(5, 5, 3, extent=4.0, solver=REF), solver_kind=F.SOLVER_SPLIT), 150),
+}
+
+
+@pytest.mark.parametrize("name", list(SPLIT))
+def test_split_solver_parity(cuda_lib, oracle_lib, name):
+    # SplitSolver mode: islands + per-island GS in descending creation-id order; same arithmetic => bit-exact vs oracle
+    mk, steps = SPLIT[name]
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, mk())
+    for s in range(steps):
+        parity.staged_step(dev, ref, 1 / 60, f"{name} step {s}")
+        assert dev.profile()["n_islands"] == ref.profile()["n_islands"], f"{name} step {s}: island count"
+    assert dev.profile()["n_islands"] > 0
+
+
 def _with(spec, **desc):
     spec.desc.update(desc)
     return spec
