@@ -1040,8 +1040,9 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
     W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[1], 0));
     W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[2], 0));
   }
-  { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1);  // > taskCap stays visible as overflow
-  W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s)); }
+  // a task count above taskCap stays visible to the host as an overflow
+  { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NTASKS, w->taskCap + 1); }
+  W_TRY(w, scan_exclusive(A.taskCnt, A.taskOff, cnt + CT_NTASKS, 0, w->taskCap, cnt + CT_NCONTACTS, w->scanTmp, s));
   NpWorld Wd;
   Wd.dt = dt;
   {
@@ -1342,9 +1343,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
   { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
   W_TRY(w, cudaGetLastError());
-  const int keepPairs = w->hCnt[CT_NPAIRS], keepContacts = w->hCnt[CT_NCONTACTS];
   if ((rc = sync_counters(w)) != CANNON_OK) return rc;
-  (void)keepPairs; (void)keepContacts;
   w->dt = dt;
   w->prof.n_rows = w->hCnt[CT_NROWS];
   w->prof.n_levels = w->hCnt[CT_NLEVELS];
