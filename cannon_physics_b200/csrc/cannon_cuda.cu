@@ -28,7 +28,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_NCONTACTROWS, CT_NPAIRS_RAW, CT_NUNITS, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -172,7 +172,11 @@ struct cannon_world {
   DBuf<int> rKind;
   DBuf<float4> rN, rRA, rRB, rIA, rIB;
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
-  DBuf<float4> rQ0, rQ1, rQ2, rQ3, rQ4;
+  DBuf<float4> rRec;
+  DBuf<GsUnitRec> uRec;
+  DBuf<int2> gsTab;
+  DBuf<int> gsLvlTask, gsLvlWin;
+  int gsTaskCap = 0;
   DBuf<float> rFlambda;
   int rowCap = 0;
   // device: solver units
@@ -188,6 +192,7 @@ struct cannon_world {
   DBuf<unsigned long long> claim;
   DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters, islandLabel;
   DBuf<double> worldTot;
+  DBuf<long long> gsTrace;
   int maxLevels = 0;
   // counters
   DBuf<int> cnt;
@@ -200,7 +205,8 @@ struct cannon_world {
   cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long lastUnits = 0, lastLevels = 0;  // widths seen by the last synchronised call (sizes the cooperative grids)
   bool recordSolveEvents = false;
-  int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0;
+  int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0;
+  bool gsFastV1 = false;  // CANNON_GS_FAST_V1: the unstaged colored sweep, kept for A/B measurements
   // resolver kernels of different types are independent: they run on side streams between two events
   cudaStream_t npStream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t npFork = nullptr, npJoin[3] = {nullptr, nullptr, nullptr};
@@ -354,8 +360,12 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   w->coopBlocksSched = ctx->sms * std::max(1, std::min(occ, 4));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs, 256, 0);
   w->coopBlocksGs = ctx->sms * std::max(1, std::min(occ, 4));
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast_v1, 256, 0);
+  w->coopBlocksGsFastV1 = ctx->sms * std::max(1, std::min(occ, 4));
+  cudaFuncSetAttribute(k_gs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BYTES);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
+  w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
   *out = w;
   return CANNON_OK;
 }
@@ -378,10 +388,10 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rQ0); REL(rQ1); REL(rQ2); REL(rQ3); REL(rQ4); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -625,7 +635,9 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(cNi, contactCap); RES(cRest, contactCap); RES(cMu, contactCap); RES(cSlip, contactCap); RES(cCa, contactCap); RES(cCb, contactCap);
   RES(cCeps, contactCap); RES(cFb, contactCap); RES(cFeps, contactCap); RES(cMult, contactCap);
   if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
-    RES(rQ0, rowCap); RES(rQ1, rowCap); RES(rQ2, rowCap); RES(rQ3, rowCap); RES(rQ4, rowCap); RES(rFlambda, rowCap);
+    RES(rRec, (size_t)rowCap * 5); RES(rFlambda, rowCap + 32); RES(uRec, rowCap + 3);
+    w->gsTaskCap = rowCap / GS_WIN_MIN + w->maxLevels + 2;
+    RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
   } else {
     RES(rKind, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
     RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
@@ -639,7 +651,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
   const int nGroupsMax = w->desc.solver_kind == CANNON_SOLVER_SPLIT ? std::max(nW, n) : nW;  // islands are labelled by body index
-  RES(worldRows, nW + 1); RES(worldDone, nGroupsMax + 2); RES(worldIters, nGroupsMax + 1); RES(worldTot, nGroupsMax + 1);
+  RES(worldRows, nW + 1); RES(worldDone, nGroupsMax + 2); RES(worldIters, nGroupsMax + 1); RES(worldTot, nGroupsMax + 3);
   RES(islandLabel, n + 1);
 #undef RES
   return CANNON_OK;
@@ -1064,14 +1076,14 @@ static RowArrays row_arrays(cannon_world* w) {
   R.B = w->rB.p; R.invC = w->rInvC.p; R.eps = w->rEps.p; R.minF = w->rMinF.p; R.maxF = w->rMaxF.p; R.lambda = w->rLambda.p;
   R.rowCap = w->rowCap;
   R.fast = w->desc.solver_kind == CANNON_SOLVER_COLORED ? 1 : 0;
-  R.q0 = w->rQ0.p; R.q1 = w->rQ1.p; R.q2 = w->rQ2.p; R.q3 = w->rQ3.p; R.q4 = w->rQ4.p; R.flambda = w->rFlambda.p;
+  R.rec = w->rRec.p; R.flambda = w->rFlambda.p;
   return R;
 }
 static UnitArrays unit_arrays(cannon_world* w) {
   UnitArrays U;
-  U.nUnits = w->cnt.p + CT_NUNITS;
+  U.nUnits = w->cnt.p + CT_NUNITS; U.nExec = w->cnt.p + CT_NEXEC;
   U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p;
-  U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p;
+  U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
   return U;
 }
@@ -1087,7 +1099,7 @@ static JointArrays joint_arrays(cannon_world* w) {
   return J;
 }
 
-__global__ void k_units_plus_one(int* cnt) { if (threadIdx.x == 0 && blockIdx.x == 0) cnt[CT_NUNITS1] = cnt[CT_NUNITS] + 1; }
+__global__ void k_units_plus_one(int* cnt) { if (threadIdx.x == 0 && blockIdx.x == 0) cnt[CT_NUNITS1] = cnt[CT_NEXEC] + 1; }
 __global__ void __launch_bounds__(256) k_zero_tail(int* eRows, const int* nUnits, int cap) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { const int n = *nUnits; if (n <= cap) eRows[n] = 0; }
 }
@@ -1116,6 +1128,14 @@ static int32_t st_solve(cannon_world* w, double dt) {
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
   P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
   P.debugSkipWork = getenv("CANNON_DEBUG_SKIP_GS_WORK") ? 1 : 0;
+  P.trace = nullptr;
+  const char* tracePath = getenv("CANNON_GS_TRACE");
+  const size_t traceWords = (size_t)w->ctx->sms * 4 * GS_TRACE_PHASES * 2 + (size_t)w->ctx->sms * 4 * 16;
+  if (tracePath) {
+    if (w->gsTrace.reserve(traceWords) != cudaSuccess) return fail(w->ctx, CANNON_E_CUDA, "trace buffer");
+    W_TRY(w, cudaMemsetAsync(w->gsTrace.p, 0, traceWords * sizeof(long long), s));
+    P.trace = w->gsTrace.p;
+  }
   const int gc = grid_for(w, w->contactCap, 256);
   { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p); }
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
@@ -1126,7 +1146,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   W_TRY(w, cudaMemsetAsync(w->worldRows.p, 0, (nW + 1) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldDone.p, 0, (nGroups + 2) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->worldIters.p, 0, (nGroups + 1) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nGroups + 1) * sizeof(double), s));
+  W_TRY(w, cudaMemsetAsync(w->worldTot.p, 0, (nGroups + 3) * sizeof(double), s));
   UnitSrc Us;
   Us.colored = P.colored; Us.split = split ? 1 : 0; Us.fricFlag = w->fricFlag.p; Us.contFlag = w->contFlag.p; Us.fricOff = w->fricOff.p; Us.contOff = w->contOff.p;
   Us.fricTotal = cnt + CT_FRICTOTAL; Us.contTotal = cnt + CT_CONTTOTAL; Us.taskOff = w->taskOff.p; Us.taskCnt = w->taskCnt.p;
@@ -1160,23 +1180,37 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
   }
   { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
-  { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NUNITS, w->unitCap); }
+  { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NEXEC, w->unitCap); }
   { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
   W_TRY(w, scan_exclusive(w->eRows.p, w->eRowBase.p, cnt + CT_NUNITS1, 0, w->unitCap + 1, nullptr, w->scanTmp, s));
-  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, w->order.p, cnt + CT_OVF_ROWS); }
+  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, w->order.p, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
+  GsTasks T;
+  T.tab = w->gsTab.p; T.lvlTask = w->gsLvlTask.p; T.lvlWin = w->gsLvlWin.p; T.nTasks = cnt + CT_GS_NTASKS; T.taskCap = w->gsTaskCap;
+  if (P.colored && !w->gsFastV1) {
+    { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
+    { g_kernel_launches++; k_gs_task_fill<<<grid_for(w, w->gsTaskCap + 1, 256), 256, 0, s>>>(U, S, T); }
+  }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[7], s);
   GsStats G;
   G.worldTot = w->worldTot.p; G.worldDone = w->worldDone.p; G.worldIters = w->worldIters.p; G.itersDone = cnt + CT_ITERS;
   G.bodyGroup = split ? w->islandLabel.p : w->world.p; G.nGroups = nGroups;
   {
     void* args[] = {&R, &B, &U, &S, &P, &G};
+    void* argsT[] = {&R, &B, &U, &S, &T, &P, &G};
     g_kernel_launches++;
     const long long width = (lastUnits > 0 && lastLevels > 0) ? 2 * lastUnits / lastLevels + 1 : 0;
-    if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(coop_blocks(w, w->coopBlocksGsFast, width)), dim3(256), args, 0, s));
+    if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(coop_blocks(w, w->coopBlocksGsFastV1, width)), dim3(256), args, 0, s));
+    else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(coop_blocks(w, w->coopBlocksGsFast, width)), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
     else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(coop_blocks(w, w->coopBlocksGs, width)), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[10], s);
   W_TRY(w, cudaGetLastError());
+  if (tracePath) {
+    std::vector<long long> h(traceWords);
+    W_TRY(w, cudaStreamSynchronize(s));
+    W_TRY(w, cudaMemcpy(h.data(), w->gsTrace.p, traceWords * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(tracePath, "wb")) { fwrite(h.data(), sizeof(long long), traceWords, f); fclose(f); }
+  }
   return CANNON_OK;
 }
 
@@ -1337,8 +1371,8 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   int32_t rc;
   // keep the pair/task/contact counts of the preceding narrowphase call, clear the solver's
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_NCONTACTROWS + 1 - CT_FRICTOTAL) * sizeof(int), s));
-  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, 5 * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_GS_NTASKS + 1 - CT_FRICTOTAL) * sizeof(int), s));
+  W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NUNITS, 0, (CT_NISLANDS + 1 - CT_NUNITS) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_BAR, 0, 64 * sizeof(int), s));
   if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
   { g_kernel_launches++; k_apply_lambda<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), w->n, w->desc.n_worlds, w->worldRows.p); }
@@ -1448,12 +1482,11 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   std::vector<double> hB(n), hC(n), hL(n);
   std::vector<int> uBi(nu), uBj(nu), uRow(nu), uLvl(nu), uRows(nu);
   if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
-    std::vector<float4> q0(n), q1(n);
+    std::vector<float4> q((size_t)n * 5);
     std::vector<float> fl(n);
-    W_TRY(w, cudaMemcpy(q0.data(), w->rQ0.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-    W_TRY(w, cudaMemcpy(q1.data(), w->rQ1.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(q.data(), w->rRec.p, (size_t)n * 5 * sizeof(float4), cudaMemcpyDeviceToHost));
     W_TRY(w, cudaMemcpy(fl.data(), w->rFlambda.p, n * sizeof(float), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; k++) { hB[k] = q0[k].w; hC[k] = q1[k].w; hL[k] = fl[k]; }
+    for (int k = 0; k < n; k++) { hB[k] = q[(size_t)k * 5].w; hC[k] = q[(size_t)k * 5 + 1].w; hL[k] = fl[k]; }
   } else {
     W_TRY(w, cudaMemcpy(hB.data(), w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     W_TRY(w, cudaMemcpy(hC.data(), w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1466,12 +1499,13 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   W_TRY(w, cudaMemcpy(uRows.data(), w->uRows.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
   int out = 0;
   const bool refOrder = w->desc.solver_kind != CANNON_SOLVER_COLORED;
+  const int ne = refOrder ? nu : std::min(nu, w->hCnt[CT_NEXEC]);  // units without rows are not in the execution order
   std::vector<int> unitsInOrder(nu);
   if (refOrder) { for (int u = 0; u < nu; u++) unitsInOrder[u] = u; }
-  else {
-    W_TRY(w, cudaMemcpy(unitsInOrder.data(), w->order.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+  else if (ne > 0) {
+    W_TRY(w, cudaMemcpy(unitsInOrder.data(), w->order.p, ne * sizeof(int), cudaMemcpyDeviceToHost));
   }
-  for (int k = 0; k < nu; k++) {
+  for (int k = 0; k < ne; k++) {
     const int u = unitsInOrder[k];
     for (int q = 0; q < uRows[u] && out < n; q++, out++) {
       const int r = uRow[u] + q;

@@ -33,23 +33,42 @@ struct RowArrays {
   float4 *iA, *iB;   // invInertiaWorldSolve * rA / rB, rounded to float like the reference's temp vector
   double *B, *invC, *eps, *minF, *maxF, *lambda;
   int rowCap;
-  // COLORED (throughput) mode: the same row packed into five float4 + one float = 84 B, solved in f32 with FMA.
+  // COLORED (throughput) mode: the same row packed into one 80-byte record + one float = 84 B, solved in f32 with FMA.
   // The row order already differs from the reference there, so only statistical agreement is claimed and the
   // f64 emulation of the Dart VM buys nothing; B / invC are still evaluated in f64 and rounded once.
   int fast;
-  float4 *q0, *q1, *q2, *q3, *q4;   // (n,B) (rA,invC) (rB,eps) (iA,minF) (iB,maxF)
+  float4* rec;     // 5 float4 per row, contiguous (80 B): (n,B) (rA,invC) (rB,eps) (iA,minF) (iB,maxF)
   float* flambda;
 };
 
 // units: by unit id (u*) before scheduling, by execution position (e*) after
 struct UnitArrays {
   int* nUnits;       // device count
+  int* nExec;        // device count of scheduled units (units without rows never enter the execution order)
   int *uBi, *uBj, *uFlags, *uRows, *uSrc;   // flags bit0/1: body i/j movable
   int *eBi, *eBj, *eFlags, *eRowBase;        // eRowBase has nUnits+1 entries (exclusive scan of rows in exec order)
   double *eImA, *eImB;                       // invMassSolve of the two bodies
   int* eRows;                                // rows per unit in exec order (scan input)
   int* unitRow;                              // unit id -> first execution row (debug / multipliers)
   int unitCap;
+  struct GsUnitRec* rec;                     // COLORED mode: the execution record the staged sweep copies to shared memory
+};
+
+// one 32-byte record per unit in execution order (COLORED mode), bulk-copied to shared memory by k_gs_fast
+struct __align__(16) GsUnitRec {
+  int bi, bj, fl, r0;
+  int r1;
+  float imA, imB;
+  int grp;  // world id in a batch (early-exit group), 0 otherwise, -1 = no movable body
+};
+
+// warp tasks of the staged sweep: task t owns units [tab[t].x, tab[t+1].x) whose rows [tab[t].y, tab[t+1].y) are contiguous
+struct GsTasks {
+  int2* tab;
+  int* lvlTask;  // [nLevels + 1] first task of each colour
+  int* lvlWin;   // [nLevels] rows per task window of the colour
+  int* nTasks;
+  int taskCap;
 };
 
 struct JointArrays {  // one entry per constraint equation (P2P: 3, hinge: 6), uploaded at set_constraints
@@ -72,6 +91,7 @@ struct SolveParams {
   int nWorlds;
   int colored;
   int debugSkipWork;  // profiling aid (CANNON_DEBUG_SKIP_GS_WORK=1): run only the barrier skeleton of the sweeps
+  long long* trace;   // profiling aid (CANNON_GS_TRACE=<file>): per CTA and phase, cycles of work and of barrier wait
 };
 
 // rigid_body.dart:303-314
@@ -116,8 +136,9 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, const R
   c += vdot(iB, rB);
   c += eps;
   if (R.fast) {
-    R.q0[row] = st3(sB, (float)Bv); R.q1[row] = st3(rA, (float)(1.0 / c)); R.q2[row] = st3(rB, (float)eps);
-    R.q3[row] = st3(iA, (float)minF); R.q4[row] = st3(iB, (float)maxF); R.flambda[row] = 0.f;
+    float4* q = R.rec + (size_t)row * 5;
+    q[0] = st3(sB, (float)Bv); q[1] = st3(rA, (float)(1.0 / c)); q[2] = st3(rB, (float)eps);
+    q[3] = st3(iA, (float)minF); q[4] = st3(iB, (float)maxF); R.flambda[row] = 0.f;
     return;
   }
   R.kind[row] = kind;
@@ -346,7 +367,9 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       if ((fl & 2) && __ldcg(&S.claim[U.uBj[u]]) != key) win = false;
       if (win) {
         S.unitLevel[u] = round;
-        S.order[atomicAdd(S.cursor, 1)] = u;
+        // a unit without rows (a resolver task that produced no contact) is done here: it never enters the
+        // execution order, so the sweeps do not have to step over it in every iteration
+        if (U.uRows[u] > 0) S.order[atomicAdd(S.cursor, 1)] = u;
       } else {
         nxt[atomicAdd(&S.actCount[cur ^ 1], 1)] = u;
       }
@@ -357,12 +380,12 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
     cur ^= 1;
     grid_barrier(S.bar, epoch);
   }
-  if (tid == 0) *S.nLevels = round;
+  if (tid == 0) { *S.nLevels = round; *U.nExec = *(volatile int*)S.cursor; }
 }
 
 // rows per unit in execution order (input of the row-base scan) + per-unit execution data
 __global__ void __launch_bounds__(256) k_exec_units(BodyArrays B, UnitArrays U, const int* __restrict__ order) {
-  const int nUnits = min(*U.nUnits, U.unitCap);
+  const int nUnits = min(*U.nExec, U.unitCap);
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
     const int u = order[a];
     const int bi = U.uBi[u], bj = U.uBj[u];
@@ -424,8 +447,9 @@ __device__ inline void build_joint_row(const RowArrays& R, int row, const BodyAr
 
 // rows, written at their execution positions: one thread per unit in execution order
 __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, UnitArrays U, RowArrays R,
-                                                    SolveParams P, const int* __restrict__ order, int* __restrict__ rowOverflow) {
-  const int nUnits = min(*U.nUnits, U.unitCap);
+                                                    SolveParams P, const int* __restrict__ order, int* __restrict__ rowOverflow,
+                                                    const int* __restrict__ bodyGroup, int nGroups) {
+  const int nUnits = min(*U.nExec, U.unitCap);
   const int nRows = U.eRowBase[nUnits];
   if (blockIdx.x == 0 && threadIdx.x == 0) { *R.nRows = nRows; if (nRows > R.rowCap) atomicMax(rowOverflow, nRows); }
   if (nRows > R.rowCap) return;
@@ -434,6 +458,14 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
     const int u = order[a];
     int row = U.eRowBase[a];
     U.unitRow[u] = row;
+    if (R.fast) {
+      GsUnitRec rec;
+      rec.bi = U.eBi[a]; rec.bj = U.eBj[a]; rec.fl = U.eFlags[a]; rec.r0 = row; rec.r1 = U.eRowBase[a + 1];
+      rec.imA = (float)U.eImA[a]; rec.imB = (float)U.eImB[a];
+      rec.grp = 0;
+      if (nGroups > 1) { rec.grp = bodyGroup[rec.bi]; if (rec.grp < 0) rec.grp = bodyGroup[rec.bj]; }
+      U.rec[a] = rec;
+    }
     if (U.eRows[a] == 0) continue;
     const int src = U.uSrc[u], kind = src & 7, idx = src >> 3;
     RowBody A, Bd;
@@ -522,8 +554,11 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
         const double imA = U.eImA[a], imB = U.eImB[a];
         // the two bodies' lambda vectors stay in registers across the unit's rows (gs_solver.dart:88-102,
         // equation_class.dart:95-105,151-169); every update rounds to float exactly like the reference's stores
-        f3 vA = ld3(__ldcg(&B.vlam[bi])), wA = ld3(__ldcg(&B.wlam[bi]));
-        f3 vB = ld3(__ldcg(&B.vlam[bj])), wB = ld3(__ldcg(&B.wlam[bj]));
+        // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it (thousands of
+        // units resting on the same static body would otherwise all hit one L2 sector)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        f3 vA = ld3((fl & 1) ? __ldcg(&B.vlam[bi]) : z4), wA = ld3((fl & 1) ? __ldcg(&B.wlam[bi]) : z4);
+        f3 vB = ld3((fl & 2) ? __ldcg(&B.vlam[bj]) : z4), wB = ld3((fl & 2) ? __ldcg(&B.wlam[bj]) : z4);
         double acc = 0.0;
         RowData d, nx;
         load_row(R, r0, d);
@@ -600,7 +635,19 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
 #define GS_CHUNK 4
 __device__ __forceinline__ float dot3f(const float4& a, float bx, float by, float bz) { return fmaf(a.z, bz, fmaf(a.y, by, a.x * bx)); }
 
-__global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
+#define GS_TRACE_PHASES 64
+#define GS_TRACE_BEGIN() long long trS = 0, trW = 0; if (P.trace && threadIdx.x == 0) trS = clock64();
+#define GS_TRACE_WORK() if (P.trace) { __syncthreads(); if (threadIdx.x == 0) trW = clock64(); }
+#define GS_TRACE_END()                                                                          \
+  if (P.trace && threadIdx.x == 0) {                                                            \
+    const int ph = iter * nLevels + lvl;                                                        \
+    if (ph < GS_TRACE_PHASES) {                                                                 \
+      P.trace[(blockIdx.x * GS_TRACE_PHASES + ph) * 2] = trW - trS;                             \
+      P.trace[(blockIdx.x * GS_TRACE_PHASES + ph) * 2 + 1] = clock64() - trW;                   \
+    }                                                                                           \
+  }
+
+__global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G) {
   __shared__ double s_red[32];
   __shared__ int s_any;
   unsigned epoch = 0;
@@ -616,6 +663,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
   for (; iter != P.maxIter; iter++) {
     double local = 0.0;
     for (int lvl = 0; lvl < nLevels; lvl++) {
+      GS_TRACE_BEGIN();
       const int a0 = S.levelStart[lvl], a1 = S.levelStart[lvl + 1];
       for (int a = a0 + itid; a < (P.debugSkipWork ? a0 : a1); a += nth) {
         const int r0 = U.eRowBase[a], r1 = U.eRowBase[a + 1];
@@ -628,8 +676,9 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
           if (w < 0 || __ldcg(&G.worldDone[w])) continue;
         }
         const float imA = (float)U.eImA[a], imB = (float)U.eImB[a];
-        float4 vA = __ldcg(&B.vlam[bi]), wA = __ldcg(&B.wlam[bi]);
-        float4 vB = __ldcg(&B.vlam[bj]), wB = __ldcg(&B.wlam[bj]);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 vA = (fl & 1) ? __ldcg(&B.vlam[bi]) : z4, wA = (fl & 1) ? __ldcg(&B.wlam[bi]) : z4;
+        float4 vB = (fl & 2) ? __ldcg(&B.vlam[bj]) : z4, wB = (fl & 2) ? __ldcg(&B.wlam[bj]) : z4;
         float acc = 0.f;
         // rows are fetched in chunks of GS_CHUNK through the read-only path before any of them is solved: the
         // manifold's sequential chain then pays one memory round trip per chunk instead of one per row
@@ -639,7 +688,8 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
 #pragma unroll
           for (int k = 0; k < GS_CHUNK; k++) {
             const int r = min(rc + k, r1 - 1);
-            c0[k] = __ldg(&R.q0[r]); c1[k] = __ldg(&R.q1[r]); c2[k] = __ldg(&R.q2[r]); c3[k] = __ldg(&R.q3[r]); c4[k] = __ldg(&R.q4[r]);
+            const float4* q = R.rec + (size_t)r * 5;
+            c0[k] = __ldg(q); c1[k] = __ldg(q + 1); c2[k] = __ldg(q + 2); c3[k] = __ldg(q + 3); c4[k] = __ldg(q + 4);
             cl[k] = R.flambda[r];
           }
 #pragma unroll
@@ -677,7 +727,9 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
         if (batch) atomicAdd(&G.worldTot[w], (double)acc);
         else local += (double)acc;
       }
+      GS_TRACE_WORK();
       grid_barrier(S.bar, epoch);
+      GS_TRACE_END();
     }
     bool allDone;
     if (!batch) {
@@ -714,5 +766,329 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast(RowArrays R, BodyArrays B, U
     }
     if (allDone && !P.debugSkipWork) break;
   }
+  if (tid == 0) *G.itersDone = iter;
+}
+
+// ---- staged sweep: the colored solver's production kernel ---------------------------------------------------------
+// k_gs_fast_v1 gives every thread one unit and lets it fetch its own rows: 32 lanes then read 32 different places of the
+// row arrays (sector waste, one L1 wavefront per lane) and every phase pays the chain  barrier -> unit record -> rows
+// (DRAM) -> solve -> store.  Here a WARP owns a window of consecutive rows (and the 24..40 units they belong to). Unit
+// records and row records never change during a solve, so one lane copies both contiguous ranges global -> shared with
+// cp.async.bulk (TMA, completion on an mbarrier) one task ahead of the warp, across colour and iteration boundaries;
+// lambdas are prefetched and written back as coalesced lines. After a grid barrier only the body-lambda gather (L2)
+// stands before the arithmetic, and DRAM sees purely sequential streams.
+#define GS_WARPS 8
+#define GS_THREADS (GS_WARPS * 32)
+#define GS_CAP_ROWS 144
+#define GS_CAP_UNITS 48
+#define GS_WIN_MIN 96
+#define GS_WIN_MAX 112
+#define GS_LAM_REGS ((GS_CAP_ROWS + 31) / 32)
+#define GS_BUF_BYTES (GS_CAP_ROWS * 80 + GS_CAP_UNITS * 32)
+#define GS_WARP_BYTES (2 * GS_BUF_BYTES + GS_CAP_ROWS * 4)
+#define GS_SMEM_BYTES (GS_WARPS * GS_WARP_BYTES)
+#define GS_LS_MAX 1024
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(b)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+// task windows per colour: about 32 units per window, at most GS_WIN_MAX rows
+__global__ void __launch_bounds__(256) k_gs_task_levels(UnitArrays U, SchedArrays S, GsTasks T, int* __restrict__ taskOverflow) {
+  __shared__ int s_scan[256];
+  __shared__ int s_base;
+  const int nLevels = *S.nLevels;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int l0 = 0; l0 < nLevels; l0 += 256) {
+    const int l = l0 + threadIdx.x;
+    int n = 0;
+    if (l < nLevels) {
+      const int u0 = S.levelStart[l], u1 = S.levelStart[l + 1];
+      const int rows = U.eRowBase[u1] - U.eRowBase[u0], units = u1 - u0;
+      int win = GS_WIN_MIN;
+      if (rows > 0 && units > 0) win = min(GS_WIN_MAX, max(GS_WIN_MIN, (int)((32LL * rows + units - 1) / units)));
+      T.lvlWin[l] = win;
+      n = (rows + win - 1) / win;
+    }
+    s_scan[threadIdx.x] = n;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (l < nLevels) T.lvlTask[l] = s_base + s_scan[threadIdx.x] - n;
+    __syncthreads();
+    if (threadIdx.x == 255) s_base += s_scan[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    T.lvlTask[nLevels] = s_base;
+    *T.nTasks = s_base;
+    if (s_base > T.taskCap) atomicMax(taskOverflow, s_base);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gs_task_fill(UnitArrays U, SchedArrays S, GsTasks T) {
+  const int nLevels = *S.nLevels;
+  const int nTasks = min(*T.nTasks, T.taskCap);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= nTasks; t += gridDim.x * blockDim.x) {
+    if (t == nTasks) {
+      const int nu = S.levelStart[nLevels];
+      T.tab[t] = make_int2(nu, U.eRowBase[nu]);
+      continue;
+    }
+    int lo = 0, hi = nLevels;  // last colour whose first task is <= t
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (T.lvlTask[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int u0 = S.levelStart[lo], u1 = S.levelStart[lo + 1];
+    const int ws = U.eRowBase[u0] + (t - T.lvlTask[lo]) * T.lvlWin[lo];
+    int a = u0, b = u1;  // first unit of the colour whose first row is >= ws
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (U.eRowBase[mid] < ws) a = mid + 1; else b = mid;
+    }
+    T.tab[t] = make_int2(a, U.eRowBase[a]);
+  }
+}
+
+struct GsTask { int a, lvl, it; };  // a: global task index, -1 = none
+
+__device__ __forceinline__ void gs_seek(const int* lt, int nLevels, int maxIter, int gw, GsTask& t) {
+  int hops = 0;
+  while (t.a >= lt[t.lvl + 1]) {
+    if (++hops > nLevels) { t.a = -1; return; }  // the warp owns no task in any colour
+    if (++t.lvl == nLevels) { t.lvl = 0; if (++t.it >= maxIter) { t.a = -1; return; } }
+    t.a = lt[t.lvl] + gw;
+  }
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, GsTasks T, SolveParams P, GsStats G) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  __shared__ unsigned long long s_mbar[GS_WARPS][2];
+  __shared__ double s_red[32];
+  __shared__ int s_any;
+  __shared__ int s_lt[GS_LS_MAX + 2];
+  unsigned epoch = 0;
+  const int nRows = min(*R.nRows, R.rowCap);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
+  const int nLevels = *S.nLevels;
+  const bool batch = G.nGroups > 1;
+  const int* lt = T.lvlTask;
+  if (nLevels <= GS_LS_MAX) {
+    for (int k = threadIdx.x; k <= nLevels; k += blockDim.x) s_lt[k] = T.lvlTask[k];
+    lt = s_lt;
+  }
+  if (lane == 0) { mbar_init(&s_mbar[wic][0], 1); mbar_init(&s_mbar[wic][1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned char* wbase = s_dyn + (size_t)wic * GS_WARP_BYTES;
+  float* slam = (float*)(wbase + 2 * GS_BUF_BYTES);
+  // tasks of a colour are dealt to the warps CTA-interleaved so a narrow colour still spreads over every SM
+  const int gw = wic * gridDim.x + blockIdx.x, nW = gridDim.x * GS_WARPS;
+
+  // three tasks in flight per warp: t0 being solved (rows in buffer `buf`), t1 rows in flight, t2 table entry in flight
+  GsTask t0, t1, t2;
+  int2 x0, y0, x1, y1, x2, y2;  // table entries [a], [a+1] of the three tasks
+  auto table = [&](const GsTask& t, int2& x, int2& y) {
+    x = make_int2(0, 0); y = x;
+    if (t.a >= 0) { x = __ldg(&T.tab[t.a]); y = __ldg(&T.tab[t.a + 1]); }
+  };
+  auto next = [&](const GsTask& t) {
+    GsTask n = t;
+    if (n.a >= 0) { n.a += nW; gs_seek(lt, nLevels, P.maxIter, gw, n); }
+    return n;
+  };
+  auto issue = [&](const int2& x, const int2& y, int b) -> bool {  // returns whether a copy was started
+    const int nUs = min(y.x - x.x, GS_CAP_UNITS), nRs = min(y.y - x.y, GS_CAP_ROWS);
+    if (nUs <= 0) return false;
+    if (lane == 0) {
+      unsigned char* dst = wbase + (size_t)b * GS_BUF_BYTES;
+      mbar_expect_tx(&s_mbar[wic][b], (unsigned)(nUs * 32 + nRs * 80));
+      bulk_g2s(dst + GS_CAP_ROWS * 80, U.rec + x.x, (unsigned)(nUs * 32), &s_mbar[wic][b]);
+      if (nRs > 0) bulk_g2s(dst, R.rec + (size_t)x.y * 5, (unsigned)(nRs * 80), &s_mbar[wic][b]);
+    }
+    return true;
+  };
+  float lamR[GS_LAM_REGS];
+  auto lam_prefetch = [&](const int2& x, const int2& y) {
+    const int nRs = min(y.y - x.y, GS_CAP_ROWS);
+#pragma unroll
+    for (int j = 0; j < GS_LAM_REGS; j++) {
+      const int idx = j * 32 + lane;
+      lamR[j] = idx < nRs ? __ldcg(&R.flambda[x.y + idx]) : 0.f;
+    }
+  };
+
+  t0.a = lt[0] + gw; t0.lvl = 0; t0.it = 0;
+  gs_seek(lt, nLevels, P.maxIter, gw, t0);
+  t1 = next(t0);
+  table(t0, x0, y0);
+  table(t1, x1, y1);
+  int buf = 0;
+  unsigned parity = 0;  // bit b: phase parity of buffer b's mbarrier
+  bool pend0 = issue(x0, y0, 0), pend1 = false;
+  lam_prefetch(x0, y0);
+
+  int iter = 0;
+  int trN = 0;
+  for (; iter != P.maxIter; iter++) {
+    double local = 0.0;
+    for (int lvl = 0; lvl < nLevels; lvl++) {
+      GS_TRACE_BEGIN();
+      while (t0.a >= 0 && t0.lvl == lvl && t0.it == iter) {
+        pend1 = issue(x1, y1, buf ^ 1);
+        t2 = next(t1);
+        table(t2, x2, y2);
+        const int u0 = x0.x, nU = y0.x - x0.x, rBase = x0.y;
+        const int nUs = min(nU, GS_CAP_UNITS), nRs = min(y0.y - x0.y, GS_CAP_ROWS);
+        // lambdas of this task: prefetched registers -> shared
+#pragma unroll
+        for (int j = 0; j < GS_LAM_REGS; j++) {
+          const int idx = j * 32 + lane;
+          if (idx < nRs) slam[idx] = lamR[j];
+        }
+        __syncwarp();
+        const bool sameNext = t1.a == t0.a;  // one task per warp and one colour: its lambdas are not written back yet
+        if (!sameNext) lam_prefetch(x1, y1);
+        long long tk0 = 0, tk1 = 0, tk2 = 0;
+        const bool tr = P.trace && wic == 0 && iter == 1 && lvl == 0;
+        if (tr) tk0 = clock64();
+        if (pend0) { mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u); parity ^= 1u << buf; }
+        if (tr) tk1 = clock64();
+        const unsigned char* sb = wbase + (size_t)buf * GS_BUF_BYTES;
+        const float4* srows = (const float4*)sb;
+        const GsUnitRec* sunits = (const GsUnitRec*)(sb + GS_CAP_ROWS * 80);
+        int flushEnd = nRs;
+        if (!P.debugSkipWork) {
+          for (int u = lane; u < nU; u += 32) {
+            const GsUnitRec m = u < nUs ? sunits[u] : U.rec[u0 + u];
+            if (m.r1 <= m.r0) continue;
+            const bool staged = m.r1 - rBase <= nRs;
+            if (!staged) flushEnd = min(flushEnd, m.r0 - rBase);  // that unit keeps its lambdas in global memory
+            if (batch && (m.grp < 0 || __ldcg(&G.worldDone[m.grp]))) continue;
+            const float4* q = staged ? srows + (size_t)(m.r0 - rBase) * 5 : R.rec + (size_t)m.r0 * 5;
+            float* lp = staged ? slam + (m.r0 - rBase) : R.flambda + m.r0;
+            // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it (thousands
+            // of units resting on the same static body would otherwise all hit one L2 sector)
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 vA = (m.fl & 1) ? __ldcg(&B.vlam[m.bi]) : z4, wA = (m.fl & 1) ? __ldcg(&B.wlam[m.bi]) : z4;
+            float4 vB = (m.fl & 2) ? __ldcg(&B.vlam[m.bj]) : z4, wB = (m.fl & 2) ? __ldcg(&B.wlam[m.bj]) : z4;
+            float acc = 0.f;
+            for (int r = m.r0; r < m.r1; r++, q += 5, lp++) {
+              const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+              const float lam = *lp;
+              // G*W_lambda with G = [-n, rA, n, rB]
+              float gw_ = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
+              gw_ += dot3f(q1, wA.x, wA.y, wA.z);
+              gw_ += dot3f(q2, wB.x, wB.y, wB.z);
+              float dl = q1.w * (q0.w - gw_ - q2.w * lam);
+              if (lam + dl < q3.w) dl = q3.w - lam;
+              else if (lam + dl > q4.w) dl = q4.w - lam;
+              *lp = lam + dl;
+              if (m.fl & 1) {
+                const float s = -m.imA * dl;
+                vA.x = fmaf(s, q0.x, vA.x); vA.y = fmaf(s, q0.y, vA.y); vA.z = fmaf(s, q0.z, vA.z);
+                wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+              }
+              if (m.fl & 2) {
+                const float s = m.imB * dl;
+                vB.x = fmaf(s, q0.x, vB.x); vB.y = fmaf(s, q0.y, vB.y); vB.z = fmaf(s, q0.z, vB.z);
+                wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+              }
+              acc += fabsf(dl);
+            }
+            if (m.fl & 1) { B.vlam[m.bi] = vA; B.wlam[m.bi] = wA; }
+            if (m.fl & 2) { B.vlam[m.bj] = vB; B.wlam[m.bj] = wB; }
+            if (batch) atomicAdd(&G.worldTot[m.grp], (double)acc);
+            else local += (double)acc;
+          }
+        }
+        if (tr) tk2 = clock64();
+        flushEnd = __reduce_min_sync(0xffffffffu, flushEnd);
+        // lambdas of the staged units back to global as full lines
+#pragma unroll
+        for (int j = 0; j < GS_LAM_REGS; j++) {
+          const int idx = j * 32 + lane;
+          if (idx < flushEnd) R.flambda[rBase + idx] = slam[idx];
+        }
+        __syncwarp();
+        if (sameNext) lam_prefetch(x1, y1);
+        if (tr && lane == 0 && trN < 4) {
+          long long* o = P.trace + (size_t)gridDim.x * GS_TRACE_PHASES * 2 + (blockIdx.x * 4 + trN) * 4;
+          o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = clock64() - tk2; o[3] = nU * 1000 + nRs;
+          trN++;
+        }
+        t0 = t1; x0 = x1; y0 = y1; pend0 = pend1;
+        t1 = t2; x1 = x2; y1 = y2; pend1 = false;
+        buf ^= 1;
+      }
+      if (!batch && lvl == nLevels - 1) {
+        // the iteration's |delta lambda| total rides on the last colour barrier; totals rotate through three slots
+        // so a slot can be cleared a full iteration before it is used again, without an extra barrier
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) s_red[wic] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t = 0.0;
+          for (int k = 0; k < GS_WARPS; k++) t += s_red[k];
+          atomicAdd(&G.worldTot[iter % 3], t);
+        }
+      }
+      GS_TRACE_WORK();
+      grid_barrier(S.bar, epoch);
+      GS_TRACE_END();
+      if (!batch && lvl == 0 && tid == 0) G.worldTot[(iter + 2) % 3] = 0.0;  // last read before this barrier, next used in iter+2
+    }
+    bool allDone;
+    if (!batch) {
+      const double tot = __ldcg(&G.worldTot[iter % 3]);
+      allDone = tot * tot < P.tol2;
+    } else {
+      if (threadIdx.x == 0) s_any = 0;
+      __syncthreads();
+      int anyLive = 0;
+      for (int w = tid; w < G.nGroups; w += nth) {
+        if (G.worldDone[w]) continue;
+        const double tot = __ldcg(&G.worldTot[w]);
+        if (tot * tot < P.tol2) { G.worldDone[w] = 1; G.worldIters[w] = iter; }
+        else { anyLive = 1; G.worldTot[w] = 0.0; }
+      }
+      if (anyLive) atomicOr(&s_any, 1);
+      __syncthreads();
+      if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);
+      grid_barrier(S.bar, epoch);
+      allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
+      grid_barrier(S.bar, epoch);
+      if (tid == 0) G.worldDone[G.nGroups] = 0;
+    }
+    if (allDone && !P.debugSkipWork) break;
+  }
+  // a copy started for a task that will never run must land before the CTA may retire
+  if (pend0) mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u);
   if (tid == 0) *G.itersDone = iter;
 }
