@@ -1000,6 +1000,7 @@ static NpArrays np_arrays(cannon_world* w) {
   A.rawRi = w->rawRi.p; A.rawRj = w->rawRj.p; A.rawNi = w->rawNi.p;
   A.taskCap = w->taskCap; A.contactCap = w->contactCap;
   A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS;
+  { const char* e = getenv("CANNON_NP_DEBUG"); A.debug = e ? atoi(e) : 0; }
   return A;
 }
 static ContactArrays contact_arrays(cannon_world* w) {

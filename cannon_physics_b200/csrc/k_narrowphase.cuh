@@ -35,6 +35,7 @@ struct NpArrays {
   int* rawCount;
   float4 *rawRi, *rawRj, *rawNi;
   int taskCap, contactCap;
+  int debug;               // profiling aid (CANNON_NP_DEBUG): 1 skip clipping, 2 skip the axis loop, 3 skip after pillar build
   int* overflowTasks;
   int* overflowContacts;
 };
@@ -798,8 +799,13 @@ __device__ inline void convex_convex_emit(RawOut& o, const HullView& HA, const H
   }
 }
 
-// hulls too large for the shared-memory scratch of the tile kernel (k_sat_warp.cuh: more than 32 faces or unique edges)
-__device__ __forceinline__ bool sat_oversize(const HullView& HA, const HullView& HB) { return HA.nF > 32 || HB.nF > 32 || HA.nE > 32 || HB.nE > 32; }
+// hulls too large for the shared-memory scratch of the tile kernel (k_sat_warp.cuh)
+#define SAT_MAXF 32
+#define SAT_MAXE 32
+#define SAT_MAXV 24  // vertices per hull staged as doubles for the projections (box 8, 8-segment cylinder 16, pillar 6)
+__device__ __forceinline__ bool sat_oversize(const HullView& HA, const HullView& HB) {
+  return HA.nF > SAT_MAXF || HB.nF > SAT_MAXF || HA.nE > SAT_MAXE || HB.nE > SAT_MAXE || HA.nV > SAT_MAXV || HB.nV > SAT_MAXV;
+}
 
 __global__ void __launch_bounds__(64) k_np_hull_hull(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow, int oversizeOnly) {
   NP_BUCKET_LOOP(NP_HH) {

@@ -17,110 +17,171 @@
 #include "k_narrowphase.cuh"
 namespace cg = cooperative_groups;
 
-#define SAT_MAXF 32
-#define SAT_MAXE 32
 #define SAT_GROUP 8  // lanes per task (a tile of the warp); 4 tasks share a warp
 #define SAT_TILES 8            // tiles per CTA
 
 struct SatScratch {
   f3 nA[SAT_MAXF], nB[SAT_MAXF];  // world face normals
   f3 eA[SAT_MAXE], eB[SAT_MAXE];  // world unique edges
-  f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY];
-  double depth[NP_MAXPOLY];
-  f3 cand[18];                    // pillar edge candidates
-  int candMask[18];               // earlier candidates each one is almostEquals to
+  union {                          // three phases of a task that never overlap
+    struct { f3 cand[18]; int candMask[18]; } p;                                        // pillar edge candidates
+    struct { double vA[SAT_MAXV][3], vB[SAT_MAXV][3]; } v;                              // axis loop: local vertices, widened once
+    struct { f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY]; double depth[NP_MAXPOLY]; } c;          // clipping + emission
+  } u;
   PillarStore pil;
   int kept, overflow, closestA;
   f3 nrm;
 };
 
-// project with a precomputed local origin (ConvexPolyhedron.project, convex_polyhedron.dart:843-883)
-__device__ __forceinline__ void hull_project_o(const HullView& H, const f3& axis, const q4& quat, const f3& localOrigin, double& mx, double& mn) {
+// ConvexPolyhedron.project (convex_polyhedron.dart:843-883) with a precomputed local origin and the hull's local
+// vertices already widened to double in shared memory. float -> double is exact and max / min do not depend on the
+// order of the candidates, so two vertices are evaluated per trip for instruction-level parallelism.
+__device__ __forceinline__ void hull_project_w(const double (*v)[3], int nV, const f3& axis, const q4& quat, const f3& localOrigin, double& mx,
+                                               double& mn) {
   const f3 localAxis = qrot(qnegw(quat), axis);
+  const double ax = W(localAxis.x), ay = W(localAxis.y), az = W(localAxis.z);
   const double add = vdot(localOrigin, localAxis);
-  mn = mx = vdot(ld3(H.v[0]), localAxis);
-  for (int i = 1; i < H.nV; i++) {
-    const double val = vdot(ld3(H.v[i]), localAxis);
-    if (val > mx) mx = val;
-    if (val < mn) mn = val;
+  {
+    double s = v[0][0] * ax;
+    s += v[0][1] * ay;
+    s += v[0][2] * az;
+    mn = mx = s;
+  }
+  int i = 1;
+  for (; i + 1 < nV; i += 2) {
+    double s0 = v[i][0] * ax, s1 = v[i + 1][0] * ax;
+    s0 += v[i][1] * ay; s1 += v[i + 1][1] * ay;
+    s0 += v[i][2] * az; s1 += v[i + 1][2] * az;
+    mx = fmax(mx, fmax(s0, s1));
+    mn = fmin(mn, fmin(s0, s1));
+  }
+  if (i < nV) {
+    double s = v[i][0] * ax;
+    s += v[i][1] * ay;
+    s += v[i][2] * az;
+    mx = fmax(mx, s);
+    mn = fmin(mn, s);
   }
   mn -= add;
   mx -= add;
   if (mn > mx) { const double t = mn; mn = mx; mx = t; }
 }
 
-// clipFaceAgainstHull with the world normals taken from shared memory (same values as qrot(quat, n))
-__device__ inline int clip_hulls_s(SatScratch& S, const HullView& HA, const f3& posA, const HullView& HB, const f3& posB, const q4& quatB,
-                                   const f3& sep, bool& overflow) {
-  int closestB = -1;
-  double dmax = -INFINITY;
-  for (int f = 0; f < HB.nF; f++) {
+// clipAgainstHull / clipFaceAgainstHull / clipFaceAgainstPlane (convex_polyhedron.dart:189-227,417-587) by the whole
+// tile: the face searches are lexicographic reductions (first extremum wins, like the sequential scans), each
+// Sutherland-Hodgman pass gives one polygon edge to a lane and places its 0 / 1 / 2 output vertices with a prefix sum,
+// so the output polygon has the sequential order and every vertex is produced by the sequential expression.
+template <class Tile>
+__device__ inline int clip_hulls_tile(const Tile& tile, int lane, SatScratch& S, const HullView& HA, const f3& posA, const HullView& HB,
+                                      const f3& posB, const q4& quatB, const f3& sep, bool& overflow) {
+  f3* pa = S.u.c.pa;
+  f3* pb = S.u.c.pb;
+  double* nd = S.u.c.depth;
+  double bd = -INFINITY;
+  int closestB = 0x7fffffff;
+  for (int f = lane; f < HB.nF; f += SAT_GROUP) {
     const double d = vdot(S.nB[f], sep);
-    if (d > dmax) { dmax = d; closestB = f; }
+    if (d > bd) { bd = d; closestB = f; }
   }
-  if (closestB < 0) return 0;
-  f3* pa = S.pa;
-  f3* pb = S.pb;
-  int nIn = 0;
+  double ad = INFINITY;
+  int closestA = 0x7fffffff;
+  for (int f = lane; f < HA.nF; f += SAT_GROUP) {
+    const double d = vdot(S.nA[f], sep);
+    if (d < ad) { ad = d; closestA = f; }
+  }
+  for (int off = SAT_GROUP / 2; off > 0; off >>= 1) {
+    const double ob = tile.shfl_xor(bd, off), oa = tile.shfl_xor(ad, off);
+    const int ib = tile.shfl_xor(closestB, off), ia = tile.shfl_xor(closestA, off);
+    if (ib != 0x7fffffff && (closestB == 0x7fffffff || ob > bd || (ob == bd && ib < closestB))) { bd = ob; closestB = ib; }
+    if (ia != 0x7fffffff && (closestA == 0x7fffffff || oa < ad || (oa == ad && ia < closestA))) { ad = oa; closestA = ia; }
+  }
+  if (closestB == 0x7fffffff || closestA == 0x7fffffff) return 0;
+  int nIn;
   {
     const int o = HB.fvOff[closestB], L = HB.fvOff[closestB + 1] - o;
-    for (int i = 0; i < L && nIn < NP_MAXPOLY; i++) pa[nIn++] = vadd(posB, qrot(quatB, ld3(HB.v[HB.fvIdx[o + i]])));
+    nIn = min(L, NP_MAXPOLY);
+    for (int i = lane; i < nIn; i += SAT_GROUP) pa[i] = vadd(posB, qrot(quatB, ld3(HB.v[HB.fvIdx[o + i]])));
     if (L > NP_MAXPOLY) overflow = true;
   }
-  int closestA = -1;
-  double dmin = INFINITY;
-  for (int f = 0; f < HA.nF; f++) {
-    const double d = vdot(S.nA[f], sep);
-    if (d < dmin) { dmin = d; closestA = f; }
-  }
-  if (closestA < 0) return 0;
   const int numVerticesA = HA.fvOff[closestA + 1] - HA.fvOff[closestA];
   const int co = HA.fcOff[closestA], nConn = HA.fcOff[closestA + 1] - co;
   f3* in = pa;
   f3* out = pb;
+  tile.sync();
   for (int i = 0; i < numVerticesA; i++) {
     const int otherFace = (nConn > i) ? HA.fcIdx[co + i] : 0;
     const f3 pn = S.nA[otherFace];
     const double pc = HA.pc[otherFace] - vdot(pn, posA);
     int nOut = 0;
     if (nIn >= 2) {
-      f3 firstVertex = in[nIn - 1];
-      double nDotFirst = vdot(pn, firstVertex) + pc;
-      for (int vi = 0; vi < nIn; vi++) {
-        const f3 lastVertex = in[vi];
-        const double nDotLast = vdot(pn, lastVertex) + pc;
-        if (nDotFirst < 0) {
-          if (nOut < NP_MAXPOLY) out[nOut++] = (nDotLast < 0) ? lastVertex : vlerp(firstVertex, lastVertex, nDotFirst / (nDotFirst - nDotLast));
-          else overflow = true;
-        } else if (nDotLast < 0) {
-          if (nOut + 1 < NP_MAXPOLY) {
-            out[nOut++] = vlerp(firstVertex, lastVertex, nDotFirst / (nDotFirst - nDotLast));
-            out[nOut++] = lastVertex;
+      for (int v = lane; v < nIn; v += SAT_GROUP) nd[v] = vdot(pn, in[v]) + pc;
+      tile.sync();
+      for (int base = 0; base < nIn; base += SAT_GROUP) {
+        const int vi = base + lane;
+        int cnt = 0;
+        double nDotFirst = 0.0, nDotLast = 0.0;
+        if (vi < nIn) {
+          nDotFirst = nd[vi == 0 ? nIn - 1 : vi - 1];
+          nDotLast = nd[vi];
+          if (nDotFirst < 0) cnt = 1;
+          else if (nDotLast < 0) cnt = 2;
+        }
+        int incl = cnt;
+        for (int o = 1; o < SAT_GROUP; o <<= 1) {
+          const int t = tile.shfl_up(incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int pos = nOut + incl - cnt;
+        if (cnt == 1) {
+          if (pos < NP_MAXPOLY) {
+            const f3 lastVertex = in[vi];
+            out[pos] = (nDotLast < 0) ? lastVertex : vlerp(in[vi == 0 ? nIn - 1 : vi - 1], lastVertex, nDotFirst / (nDotFirst - nDotLast));
+          } else overflow = true;
+        } else if (cnt == 2) {
+          if (pos + 1 < NP_MAXPOLY) {
+            const f3 lastVertex = in[vi];
+            out[pos] = vlerp(in[vi == 0 ? nIn - 1 : vi - 1], lastVertex, nDotFirst / (nDotFirst - nDotLast));
+            out[pos + 1] = lastVertex;
           } else overflow = true;
         }
-        firstVertex = lastVertex;
-        nDotFirst = nDotLast;
+        nOut += tile.shfl(incl, SAT_GROUP - 1);
       }
+      nOut = min(nOut, NP_MAXPOLY);
     }
+    tile.sync();
     f3* t = in; in = out; out = t;
     nIn = nOut;
   }
   const f3 nrm = S.nA[closestA];
-  S.nrm = nrm;
+  if (lane == 0) S.nrm = nrm;
   const double planeEq = HA.pc[closestA] - vdot(nrm, posA);
+  // keep the points at or below the reference face (depth <= 1e-6, clamped at -100), in polygon order
   int kept = 0;
-  for (int i = 0; i < nIn; i++) {
-    double depth = vdot(nrm, in[i]) + planeEq;
-    if (depth <= -100.0) depth = -100.0;
-    if (depth <= 100.0 && depth <= 1e-6) {
-      const f3 p = in[i];
-      out[kept] = p;
-      S.depth[kept] = depth;
-      kept++;
+  for (int base = 0; base < nIn; base += SAT_GROUP) {
+    const int i = base + lane;
+    bool keep = false;
+    double depth = 0.0;
+    f3 p; p.x = p.y = p.z = 0.f;
+    if (i < nIn) {
+      p = in[i];
+      depth = vdot(nrm, p) + planeEq;
+      if (depth <= -100.0) depth = -100.0;
+      keep = depth <= 100.0 && depth <= 1e-6;
     }
+    const unsigned m = tile.ballot(keep);
+    tile.sync();  // every lane has read in[] of this chunk before out[] (which may alias earlier chunks only) is written
+    if (keep) {
+      const int pos = kept + __popc(m & ((1u << lane) - 1u));
+      out[pos] = p;
+      nd[pos] = depth;
+    }
+    kept += __popc(m);
   }
-  if (out != pa)
-    for (int i = 0; i < kept; i++) pa[i] = out[i];
+  tile.sync();
+  if (out != pa) {
+    for (int i = lane; i < kept; i += SAT_GROUP) pa[i] = out[i];
+    tile.sync();
+  }
   return kept;
 }
 
@@ -175,21 +236,21 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
         const int o0 = c_pillarFvOff[f], L = c_pillarFvOff[f + 1] - o0, j = e - o0;
         f3 ev = vsub(ld3(S.pil.v[fv[o0 + j]]), ld3(S.pil.v[fv[o0 + (j + 1) % L]]));
         vnormalize(ev);
-        S.cand[e] = ev;
+        S.u.p.cand[e] = ev;
       }
       tile.sync();
       for (int e = lane; e < 18; e += SAT_GROUP) {
         int m = 0;
-        const f3 ev = S.cand[e];
+        const f3 ev = S.u.p.cand[e];
         for (int p = 0; p < e; p++)
-          if (valmost_eq(S.cand[p], ev)) m |= 1 << p;
-        S.candMask[e] = m;
+          if (valmost_eq(S.u.p.cand[p], ev)) m |= 1 << p;
+        S.u.p.candMask[e] = m;
       }
       tile.sync();
       if (lane == 0) {
         int nE = 0, keep = 0;
         for (int k = 0; k < 18; k++)
-          if ((S.candMask[k] & keep) == 0) { keep |= 1 << k; S.pil.e[nE++] = st3(S.cand[k]); }
+          if ((S.u.p.candMask[k] & keep) == 0) { keep |= 1 << k; S.pil.e[nE++] = st3(S.u.p.cand[k]); }
         S.pil.nE = nE;
       }
       tile.sync();
@@ -203,14 +264,17 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
     f3 sep; sep.x = sep.y = sep.z = 0.f;
     bool candidate = PILLAR ? (vdist(c.xi, xB) < HB.bsr + HA.bsr) : true;
     if (candidate && (vdist(c.xi, xB) > HA.bsr + HB.bsr)) candidate = false;  // convexConvex's own bounding test (:1999)
-    if (candidate && (HA.nF > SAT_MAXF || HB.nF > SAT_MAXF || HA.nE > SAT_MAXE || HB.nE > SAT_MAXE)) {
+    if (candidate && sat_oversize(HA, HB)) {
       continue;  // oversized hulls are left to the sequential kernels (k_np_hull_hull / k_np_hull_pillar, oversizeOnly)
     }
+    if (A.debug == 3) candidate = false;
     if (candidate) {
       for (int i = lane; i < HA.nF; i += SAT_GROUP) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));
       for (int i = lane; i < HB.nF; i += SAT_GROUP) S.nB[i] = qrot(c.qj, ld3(HB.n[i]));
       for (int i = lane; i < HA.nE; i += SAT_GROUP) S.eA[i] = qrot(c.qi, ld3(HA.e[i]));
       for (int i = lane; i < HB.nE; i += SAT_GROUP) S.eB[i] = qrot(c.qj, ld3(HB.e[i]));
+      for (int i = lane; i < HA.nV; i += SAT_GROUP) { const float4 v = HA.v[i]; S.u.v.vA[i][0] = v.x; S.u.v.vA[i][1] = v.y; S.u.v.vA[i][2] = v.z; }
+      for (int i = lane; i < HB.nV; i += SAT_GROUP) { const float4 v = HB.v[i]; S.u.v.vB[i][0] = v.x; S.u.v.vB[i][1] = v.y; S.u.v.vB[i][2] = v.z; }
       tile.sync();
       f3 zero; zero.x = zero.y = zero.z = 0.f;
       const f3 oA = to_local_point(c.xi, c.qi, zero), oB = to_local_point(xB, c.qj, zero);
@@ -220,7 +284,7 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
       double best = INFINITY;
       int bestIdx = 0x7fffffff;
       f3 bestAxis = zero;
-      bool separated = false;
+      bool separated = A.debug == 2;
       // rounds of SAT_GROUP axes with a vote after each round: a separating axis ends the task early (same result
       // as the sequential `return false`, convex_polyhedron.dart:264-267)
       for (int base = 0; base < nAxes && !separated; base += SAT_GROUP) {
@@ -239,8 +303,8 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
           }
           if (valid) {
             double maxA, minA, maxB, minB;
-            hull_project_o(HA, axis, c.qi, oA, maxA, minA);
-            hull_project_o(HB, axis, c.qj, oB, maxB, minB);
+            hull_project_w(S.u.v.vA, HA.nV, axis, c.qi, oA, maxA, minA);
+            hull_project_w(S.u.v.vB, HB.nV, axis, c.qj, oB, maxB, minB);
             if (maxA < minB || maxB < minA) sepHere = true;
             else {
               const double d0 = maxA - minB, d1 = maxB - minA;
@@ -269,13 +333,12 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
         }
         const f3 deltaC = vsub(xB, c.xi);
         if (vdot(deltaC, sep) > 0.0) sep = vneg(sep);
-        if (lane == 0) {
+        tile.sync();  // the widened vertices are dead from here on: their storage becomes the clipping polygons
+        if (A.debug != 1) {
           bool ovf = false;
-          S.kept = clip_hulls_s(S, HA, c.xi, HB, xB, c.qj, sep, ovf);
+          kept = clip_hulls_tile(tile, lane, S, HA, c.xi, HB, xB, c.qj, sep, ovf);
           if (ovf) atomicExch(clipOverflow, 1);
         }
-        tile.sync();
-        kept = S.kept;
       }
     }
     // emission: lane 0 reserves the block in the raw pool, lanes write one contact each
@@ -291,9 +354,9 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
     const f3 ni = vneg(sep);
     const f3 nrm = S.nrm;
     for (int j = lane; j < kept; j += SAT_GROUP) {
-      const f3 q = vscale(S.depth[j], vneg(nrm));
-      f3 ri = vadd(S.pa[j], q);
-      f3 rj = S.pa[j];
+      const f3 q = vscale(S.u.c.depth[j], vneg(nrm));
+      f3 ri = vadd(S.u.c.pa[j], q);
+      f3 rj = S.u.c.pa[j];
       ri = vsub(ri, c.xi);
       rj = vsub(rj, xB);
       ri = vsub(vadd(ri, c.xi), c.xi);
