@@ -304,22 +304,44 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       }
       if (lane == src) { nt = count; if (!pass) A.pairMask[pk] = mask; }
     }
-    if (k >= np) continue;
+    // bucket bookkeeping: one atomic per (warp, resolver type) instead of one per pair
+    const bool valid = k < np;
+    const bool fits = valid && nt > 0 && (pass == 0 || myOff + nt <= A.taskCap);
+    if (pass && valid && nt > 0 && !fits) atomicMax(A.overflowTasks, myOff + nt);
+    const int gcode = fits ? code : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, gcode);
+    const int leader = __ffs(peers) - 1;
+    const unsigned lt = (1u << lane) - 1u;
     if (pass == 0) {
-      A.pairTasks[k] = nt;
-      if (nt) atomicAdd(&A.bucketCount[code], nt);
+      if (valid) A.pairTasks[k] = nt;
+      if (gcode >= 0) {
+        const int total = __reduce_add_sync(peers, nt);
+        if (lane == leader) atomicAdd(&A.bucketCount[gcode], total);
+      }
       continue;
     }
-    if (nt == 0) continue;
+    // exclusive prefix of nt inside the lane's type group (heightfield pairs carry several tasks each)
+    int before = 0;
+    if (gcode == NP_SPIL || gcode == NP_HPIL) {
+      for (unsigned m = peers; m; m &= m - 1) {  // the same trips for every lane of the group
+        const int src = __ffs(m) - 1;
+        const int v = __shfl_sync(peers, nt, src);
+        if (src < lane) before += v;
+      }
+    } else {
+      before = __popc(peers & lt);
+    }
+    if (gcode < 0) continue;
+    int slot = 0;
+    const int total = __reduce_add_sync(peers, nt);
+    if (lane == leader) slot = A.bucketStart[gcode] + atomicAdd(&A.bucketCursor[gcode], total);
+    slot = __shfl_sync(peers, slot, leader) + before;
     const int off = myOff;
-    if (off + nt > A.taskCap) { atomicMax(A.overflowTasks, off + nt); continue; }
-    if (code == NP_SPIL || code == NP_HPIL) {
-      const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], nt);
+    if (gcode == NP_SPIL || gcode == NP_HPIL) {
       for (int t = 0; t < nt; t++) A.bucket[slot + t] = off + t;
     } else {
       A.taskPair[off] = k;
-      A.taskInfo[off] = code;
-      const int slot = A.bucketStart[code] + atomicAdd(&A.bucketCursor[code], 1);
+      A.taskInfo[off] = gcode;
       A.bucket[slot] = off;
     }
   }

@@ -185,7 +185,13 @@ __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& 
                                          int* __restrict__ worldRows) {
   U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src;
   U.uFlags[u] = rows > 0 ? ((body_movable(B, bi) ? 1 : 0) | (body_movable(B, bj) ? 2 : 0)) : 0;
-  if (rows > 0) atomicAdd(&worldRows[nWorlds > 1 ? B.world[bi] : 0], rows);
+  if (rows > 0) {
+    // worldRows[w] > 0 <=> world w has equations this step: one plain store per (warp, world) instead of millions of
+    // atomics on the same word
+    const int wIdx = nWorlds > 1 ? B.world[bi] : 0;
+    const unsigned peers = __match_any_sync(__activemask(), wIdx);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) worldRows[wIdx] = 1;
+  }
 }
 
 // unit table. Reference order: unit id == reference row index [2*fricRank | nF2 + contRank | joints].
@@ -357,22 +363,38 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       if (fl & 2) atomicMin(&S.claim[U.uBj[u]], key);
     }
     grid_barrier(S.bar, epoch);
-    for (int a = tid; a < nAct; a += nth) {
-      const int u = __ldcg(&act[a]);
-      const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
-      const unsigned long long key = hi | pri;
-      const int fl = U.uFlags[u];
-      bool win = true;
-      if ((fl & 1) && __ldcg(&S.claim[U.uBi[u]]) != key) win = false;
-      if ((fl & 2) && __ldcg(&S.claim[U.uBj[u]]) != key) win = false;
-      if (win) {
-        S.unitLevel[u] = round;
-        // a unit without rows (a resolver task that produced no contact) is done here: it never enters the
-        // execution order, so the sweeps do not have to step over it in every iteration
-        if (U.uRows[u] > 0) S.order[atomicAdd(S.cursor, 1)] = u;
-      } else {
-        nxt[atomicAdd(&S.actCount[cur ^ 1], 1)] = u;
+    // winners go to the execution order, losers to the next round's list: one cursor atomic per warp and list
+    for (int a0 = tid - (int)(threadIdx.x & 31); a0 < nAct; a0 += nth) {
+      const int a = a0 + (int)(threadIdx.x & 31);
+      const bool active = a < nAct;
+      int u = 0;
+      bool win = false, emit = false;
+      if (active) {
+        u = __ldcg(&act[a]);
+        const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
+        const unsigned long long key = hi | pri;
+        const int fl = U.uFlags[u];
+        win = true;
+        if ((fl & 1) && __ldcg(&S.claim[U.uBi[u]]) != key) win = false;
+        if ((fl & 2) && __ldcg(&S.claim[U.uBj[u]]) != key) win = false;
+        if (win) {
+          S.unitLevel[u] = round;
+          // a unit without rows (a resolver task that produced no contact) is done here: it never enters the
+          // execution order, so the sweeps do not have to step over it in every iteration
+          emit = U.uRows[u] > 0;
+        }
       }
+      const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+      const unsigned mw = __ballot_sync(0xffffffffu, emit), ml = __ballot_sync(0xffffffffu, active && !win);
+      int bw = 0, bl = 0;
+      if ((threadIdx.x & 31) == 0) {
+        if (mw) bw = atomicAdd(S.cursor, __popc(mw));
+        if (ml) bl = atomicAdd(&S.actCount[cur ^ 1], __popc(ml));
+      }
+      bw = __shfl_sync(0xffffffffu, bw, 0);
+      bl = __shfl_sync(0xffffffffu, bl, 0);
+      if (emit) S.order[bw + __popc(mw & lt)] = u;
+      else if (active && !win) nxt[bl + __popc(ml & lt)] = u;
     }
     grid_barrier(S.bar, epoch);
     if (tid == 0) { S.levelStart[round + 1] = *(volatile int*)S.cursor; S.actCount[cur] = 0; }

@@ -18,3 +18,4 @@ for d in ("0", "1", "2", "3", "0"):
     w.step(1 / 60, 1)
     prof = w.profile()
     print(d, {k: round(prof[k], 3) for k in ("broadphase", "narrowphase", "solve", "gs_ms")}, prof["n_contacts"], flush=True)
+
