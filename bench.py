@@ -261,16 +261,23 @@ def main():
         force, torque = pin((n, 3)), pin((n, 3))
         out = {"position": pin((n, 3)), "quaternion": pin((n, 4))}
         ke = K
+        # same trajectory segment as the device-timed run: a fresh world, W untimed warm-up steps, K timed steps
+        world_e = engine.DeviceWorld(cp.lib, spec, device=local_rank)
+        for _ in range(W):
+            world_e.update_bodies(0, n, force=force, torque=torque)
+            world_e.step(DT, 1)
+            world_e.get_bodies(("position", "quaternion"), out=out)
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(ke):
-            world.update_bodies(0, n, force=force, torque=torque)
-            world.step(DT, 1)
-            poses = world.get_bodies(("position", "quaternion"), out=out)
+            world_e.update_bodies(0, n, force=force, torque=torque)
+            world_e.step(DT, 1)
+            poses = world_e.get_bodies(("position", "quaternion"), out=out)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
+        del world_e
         e2e_stats = reduce_stats({"body_steps": nd * ke}, el * 1000.0, device=dev_t)
         e2e = {"value": e2e_stats["body_steps"] / (e2e_stats["elapsed_ms"] / 1000.0), "unit": "body-steps/s",
                "h2d_bytes_per_step": int(force.nbytes + torque.nbytes), "d2h_bytes_per_step": int(poses["position"].nbytes + poses["quaternion"].nbytes),

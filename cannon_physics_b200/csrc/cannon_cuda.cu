@@ -42,8 +42,11 @@ __global__ void k_set_int(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x ==
 
 // persistent accumulators (never reset by the per-step counter memset): statistics and sticky overflow needs
 enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_COUNT };
-__global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restrict__ acc, int taskCap, int contactCap) {
+__global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restrict__ acc, int taskCap, int contactCap, long long* __restrict__ clk,
+                                double dt) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  clk[0] = __double_as_longlong(__longlong_as_double(clk[0]) + dt);  // World.step: time += dt after internalStep (world_class.dart:396-399)
+  clk[1] += 1;
   acc[AC_CONTACT_ITERS] += (long long)cnt[CT_NCONTACTS] * cnt[CT_ITERS];
   acc[AC_STEPS] += 1;
   auto mx = [&](int slot, long long v) { if (v > acc[slot]) acc[slot] = v; };
@@ -192,6 +195,8 @@ struct cannon_world {
   DBuf<unsigned long long> claim;
   DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters, islandLabel;
   DBuf<double> worldTot;
+  DBuf<long long> dClock;  // [0] bits of World.time, [1] World.stepnumber
+  long long hClock[2] = {0, 0};
   DBuf<long long> gsTrace;
   int maxLevels = 0;
   // counters
@@ -205,6 +210,14 @@ struct cannon_world {
   cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long lastUnits = 0, lastLevels = 0;  // widths seen by the last synchronised call (sizes the cooperative grids)
   bool recordSolveEvents = false;
+  // one World.step captured as a CUDA graph (all counts live on the device, so the launch sequence of a step is
+  // fixed for a given dt and capacity; the cooperative kernels size their own barrier on the device); replayed by
+  // cannon_world_step
+  cudaGraphExec_t stepGraph = nullptr;
+  double graphDt = 0.0;
+  long long graphLaunches = 0;     // kernels per replay (for cannon_profile.kernel_launches)
+  int eagerSteps = 0;              // steps run eagerly since the last (re)allocation: lazily sized scratch exists after one
+  bool graphBroken = false;        // capture failed once: stay eager
   int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0;
   bool gsFastV1 = false;  // CANNON_GS_FAST_V1: the unstaged colored sweep, kept for A/B measurements
   // resolver kernels of different types are independent: they run on side streams between two events
@@ -369,8 +382,11 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   *out = w;
   return CANNON_OK;
 }
+static void drop_step_graph(cannon_world* w);
+
 void cannon_world_destroy(cannon_world* w) {
   if (!w) return;
+  drop_step_graph(w);
   cudaSetDevice(w->ctx->device);
   cudaStreamSynchronize(w->ctx->stream);
   // DBuf members are released explicitly (plain structs, no destructors)
@@ -391,7 +407,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -400,6 +416,7 @@ void cannon_world_destroy(cannon_world* w) {
 
 int32_t cannon_world_set_materials(cannon_world* w, int32_t n, const double* friction, const double* restitution, int32_t ncm,
                                    const cannon_contact_material* cms) {
+  if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || n < 0 || ncm < 0) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
@@ -423,6 +440,7 @@ int32_t cannon_world_set_materials(cannon_world* w, int32_t n, const double* fri
 }
 
 int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_desc* sd) {
+  if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || n < 0 || (n > 0 && !sd)) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
@@ -658,6 +676,7 @@ static int32_t ensure_capacities(cannon_world* w) {
 }
 
 int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
+  if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || !sb || sb->n < 0) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
@@ -781,6 +800,7 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
 }
 
 int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs) {
+  if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
@@ -878,13 +898,21 @@ int32_t cannon_world_set_dt(cannon_world* w, double dt) { if (!w) return CANNON_
 }  // extern "C"
 
 // ---- stages -------------------------------------------------------------------------------------------
+// the host owns World.time / stepnumber between calls; every entry point that runs step kernels pushes them first
+static cudaError_t sync_clock(cannon_world* w) {
+  cudaError_t e = w->dClock.reserve(2);
+  if (e != cudaSuccess) return e;
+  memcpy(&w->hClock[0], &w->time, sizeof(double));
+  w->hClock[1] = w->stepnumber;
+  return cudaMemcpyAsync(w->dClock.p, w->hClock, sizeof w->hClock, cudaMemcpyHostToDevice, w->ctx->stream);
+}
+
 static StepParams step_params(cannon_world* w, double dt) {
   StepParams P;
-  P.dt = dt; P.time = w->time;
+  P.dt = dt; P.clk = w->dClock.p; P.quatSkip = w->desc.quat_normalize_skip;
   P.gx = W(w->desc.gravity[0]); P.gy = W(w->desc.gravity[1]); P.gz = W(w->desc.gravity[2]);
   P.n = w->n;
   P.allowSleep = w->desc.allow_sleep;
-  P.quatNormalize = (w->stepnumber % (w->desc.quat_normalize_skip + 1)) == 0;  // world_class.dart:668
   P.quatNormalizeFast = w->desc.quat_normalize_fast;
   P.needAABB = (w->desc.use_bounding_boxes || w->desc.broadphase_kind != CANNON_BP_NAIVE) ? 1 : 0;
   P.nWorlds = w->desc.n_worlds;
@@ -1105,16 +1133,6 @@ __global__ void __launch_bounds__(256) k_zero_tail(int* eRows, const int* nUnits
   if (threadIdx.x == 0 && blockIdx.x == 0) { const int n = *nUnits; if (n <= cap) eRows[n] = 0; }
 }
 
-// cooperative grid size: enough CTAs for the widest level seen last time, never more than can be co-resident
-static int coop_blocks(cannon_world* w, int maxBlocks, long long widthEstimate) {
-  // the estimate comes from the last synchronised call; inside a long multi-step call a large world can grow far
-  // beyond it, so only small worlds (where the barrier latency matters) get a reduced grid
-  if (widthEstimate <= 0 || w->n >= 16384) return maxBlocks;
-  long long b = (widthEstimate + 255) / 256;
-  if (b < 1) b = 1;
-  return (int)std::min<long long>(b, maxBlocks);
-}
-
 // world_class.dart:539-645 without the final velocity update (k_integrate / k_apply_lambda do that)
 static int32_t st_solve(cannon_world* w, double dt) {
   cudaStream_t s = w->ctx->stream;
@@ -1159,13 +1177,12 @@ static int32_t st_solve(cannon_world* w, double dt) {
   S.act0 = w->act0.p; S.act1 = w->act1.p; S.actCount = cnt + CT_ACT0; S.cursor = cnt + CT_CURSOR; S.bar = (unsigned*)(cnt + CT_BAR);
   S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS;
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
-  const long long lastUnits = w->lastUnits, lastLevels = w->lastLevels;
   if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
   {
     int colored = P.colored;
     void* args[] = {&U, &S, &colored};
     g_kernel_launches++;
-    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(coop_blocks(w, w->coopBlocksSched, lastUnits > 0 ? lastUnits / 2 + 1 : 0)), dim3(256), args, 0, s));
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_schedule, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[6], s);
   W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
@@ -1177,7 +1194,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     unsigned* bar = S.bar;
     void* args[] = {&B, &U, &nb, &label, &changed, &nIsl, &bar};
     g_kernel_launches++;
-    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_islands, dim3(coop_blocks(w, w->coopBlocksSched, lastUnits > 0 ? lastUnits / 2 + 1 : 0)), dim3(256), args, 0, s));
+    W_TRY(w, cudaLaunchCooperativeKernel((void*)k_islands, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
     W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
   }
   { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
@@ -1199,10 +1216,9 @@ static int32_t st_solve(cannon_world* w, double dt) {
     void* args[] = {&R, &B, &U, &S, &P, &G};
     void* argsT[] = {&R, &B, &U, &S, &T, &P, &G};
     g_kernel_launches++;
-    const long long width = (lastUnits > 0 && lastLevels > 0) ? 2 * lastUnits / lastLevels + 1 : 0;
-    if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(coop_blocks(w, w->coopBlocksGsFastV1, width)), dim3(256), args, 0, s));
-    else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(coop_blocks(w, w->coopBlocksGsFast, width)), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
-    else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(coop_blocks(w, w->coopBlocksGs, width)), dim3(256), args, 0, s));
+    if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
+    else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
+    else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[10], s);
   W_TRY(w, cudaGetLastError());
@@ -1278,6 +1294,7 @@ extern "C" {
 int32_t cannon_apply_gravity(cannon_world* w) {
   if (!w) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
+  W_TRY(w, sync_clock(w));
   int32_t rc = st_prestep(w, w->dt > 0 ? w->dt : 1.0 / 60, 1, 0);
   if (rc != CANNON_OK) return rc;
   W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
@@ -1287,6 +1304,7 @@ int32_t cannon_apply_gravity(cannon_world* w) {
 int32_t cannon_broadphase_pairs(cannon_world* w, int32_t* p1, int32_t* p2, int32_t cap, int32_t* n_pairs) {
   if (!w || !n_pairs) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
+  W_TRY(w, sync_clock(w));
   int32_t rc;
   if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
   if ((rc = st_prestep(w, w->dt > 0 ? w->dt : 1.0 / 60, 0, 0)) != CANNON_OK) return rc;
@@ -1341,6 +1359,7 @@ int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const in
                                     int32_t* n_contacts, int32_t* per_pair_count) {
   if (!w || np < 0 || (np > 0 && (!p1 || !p2))) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
+  W_TRY(w, sync_clock(w));
   cudaStream_t s = w->ctx->stream;
   if (np > w->pairCap) return fail(w->ctx, CANNON_E_CAPACITY, "more pairs than cannon_world_desc.max_pairs");
   for (int k = 0; k < np; k++)
@@ -1392,6 +1411,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
 int32_t cannon_integrate(cannon_world* w, double dt) {
   if (!w) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
+  W_TRY(w, sync_clock(w));
   int32_t rc;
   if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
   if ((rc = st_integrate(w, dt, 0)) != CANNON_OK) return rc;
@@ -1401,30 +1421,85 @@ int32_t cannon_integrate(cannon_world* w, double dt) {
   return CANNON_OK;
 }
 
+// everything one World.step enqueues on the library's stream(s), with the stage events of cannon_profile
+static int32_t enqueue_step(cannon_world* w, double dt) {
+  cudaStream_t s = w->ctx->stream;
+  int32_t rc;
+  w->recordSolveEvents = true;
+  if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
+  cudaEventRecord(w->ev[0], s);
+  if ((rc = st_prestep(w, dt, 1, 0)) != CANNON_OK) return rc;
+  if ((rc = st_broadphase(w)) != CANNON_OK) return rc;
+  cudaEventRecord(w->ev[1], s);
+  if ((rc = st_narrowphase(w, dt)) != CANNON_OK) return rc;
+  cudaEventRecord(w->ev[2], s);
+  if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
+  cudaEventRecord(w->ev[3], s);
+  if ((rc = st_integrate(w, dt, 1)) != CANNON_OK) return rc;
+  cudaEventRecord(w->ev[4], s);
+  // statistics + sticky overflow needs are folded on the device: no host round trip between steps
+  { g_kernel_launches++; k_step_epilogue<<<1, 32, 0, s>>>(w->cnt.p, w->acc.p, w->taskCap, w->contactCap, w->dClock.p, dt); }
+  w->recordSolveEvents = false;
+  return CANNON_OK;
+}
+
+static void drop_step_graph(cannon_world* w) {
+  if (w->stepGraph) { cudaGraphExecDestroy(w->stepGraph); w->stepGraph = nullptr; }
+  w->eagerSteps = 0;
+}
+
 int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   if (!w || nsteps < 0) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
+  W_TRY(w, sync_clock(w));
   cudaStream_t s = w->ctx->stream;
   int32_t rc;
   if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
   w->dt = dt;
+  const bool wantGraph = !w->graphBroken && !getenv("CANNON_NO_GRAPH") && !getenv("CANNON_GS_TRACE");
   cudaEventRecord(w->ev[8], s);
   for (int it = 0; it < nsteps; it++) {
-    const bool last = it == nsteps - 1;
-    w->recordSolveEvents = last;
-    if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
-    if (last) cudaEventRecord(w->ev[0], s);
-    if ((rc = st_prestep(w, dt, 1, 0)) != CANNON_OK) return rc;
-    if ((rc = st_broadphase(w)) != CANNON_OK) return rc;
-    if (last) cudaEventRecord(w->ev[1], s);
-    if ((rc = st_narrowphase(w, dt)) != CANNON_OK) return rc;
-    if (last) cudaEventRecord(w->ev[2], s);
-    if ((rc = st_solve(w, dt)) != CANNON_OK) return rc;
-    if (last) cudaEventRecord(w->ev[3], s);
-    if ((rc = st_integrate(w, dt, 1)) != CANNON_OK) return rc;
-    if (last) cudaEventRecord(w->ev[4], s);
-    // statistics + sticky overflow needs are folded on the device: no host round trip between steps
-    { g_kernel_launches++; k_step_epilogue<<<1, 32, 0, s>>>(w->cnt.p, w->acc.p, w->taskCap, w->contactCap); }
+    bool done = false;
+    // the stage events of cannon_profile only time eager launches, so a multi-step call runs its last step eagerly
+    const bool profiled = it == nsteps - 1 && nsteps > 1;
+    if (wantGraph && w->eagerSteps >= 1 && !profiled) {
+      if (w->stepGraph && w->graphDt != dt) { cudaGraphExecDestroy(w->stepGraph); w->stepGraph = nullptr; }
+      if (!w->stepGraph) {
+        const long long l0 = g_kernel_launches;
+        cudaGraph_t g = nullptr;
+        {
+          const cudaError_t stale = cudaGetLastError();
+          if (stale != cudaSuccess && getenv("CANNON_GRAPH_DEBUG")) fprintf(stderr, "[cannon] stale error before capture: %s\n", cudaGetErrorString(stale));
+        }
+        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+          rc = enqueue_step(w, dt);
+          e = cudaStreamEndCapture(s, &g);
+          if (rc == CANNON_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&w->stepGraph, g, 0);
+          else if (e == cudaSuccess) e = cudaErrorUnknown;
+          if (g) cudaGraphDestroy(g);
+        }
+        w->graphLaunches = g_kernel_launches - l0;
+        g_kernel_launches = l0;  // nothing ran yet
+        if (e != cudaSuccess || !w->stepGraph) {
+          if (getenv("CANNON_GRAPH_DEBUG")) fprintf(stderr, "[cannon] step graph capture failed: rc=%d cuda=%s last=%s\n", rc, cudaGetErrorString(e), cannon_last_error(w->ctx));
+          cudaGetLastError();
+          w->stepGraph = nullptr;
+          w->graphBroken = true;  // fall back to eager launches for good
+        } else {
+          w->graphDt = dt;
+        }
+      }
+      if (w->stepGraph) {
+        W_TRY(w, cudaGraphLaunch(w->stepGraph, s));
+        g_kernel_launches += w->graphLaunches;
+        done = true;
+      }
+    }
+    if (!done) {
+      if ((rc = enqueue_step(w, dt)) != CANNON_OK) return rc;
+      w->eagerSteps++;
+    }
     w->stepnumber += 1;
     w->time += dt;  // World.step: time += dt after internalStep (world_class.dart:396-399)
   }
@@ -1446,6 +1521,7 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
     if (cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]) == cudaSuccess) p.schedule_ms = ms;
     if (cudaEventElapsedTime(&ms, w->ev[7], w->ev[10]) == cudaSuccess) p.gs_ms = ms;
     if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;
+    cudaGetLastError();  // an event pair that was not recorded in this call is not an error of the step
     p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
     p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
     w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];

@@ -8,10 +8,12 @@
 
 struct StepParams {
   double dt;
-  double time;        // World.time before this step's increment (sleepTick sees this, world_class.dart:693)
+  const long long* clk;  // device clock: [0] bits of World.time before this step's increment (sleepTick sees this,
+                         // world_class.dart:693), [1] World.stepnumber; kept on the device so a captured step can be replayed
+  int quatSkip;          // quatNormalizeSkip
   double gx, gy, gz;  // gravity widened from float
   int n;              // bodies
-  int allowSleep, quatNormalize, quatNormalizeFast;
+  int allowSleep, quatNormalizeFast;
   int needAABB;
   int nWorlds;
 };
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, c
       q.y = (float)(by + halfDt * (ay * bw + az * bx - ax * bz));
       q.z = (float)(bz + halfDt * (az * bw + ax * by - ay * bx));
       q.w = (float)(bw + halfDt * (-ax * bx - ay * by - az * bz));
-      if (P.quatNormalize) {
+      if (P.clk[1] % (long long)(P.quatSkip + 1) == 0) {  // world_class.dart:668
         if (P.quatNormalizeFast) {  // quaternion.dart:171-185
           const double f = (3.0 - (W(q.x) * W(q.x) + W(q.y) * W(q.y) + W(q.z) * W(q.z) + W(q.w) * W(q.w))) / 2.0;
           if (f == 0) { q.x = q.y = q.z = q.w = 0.f; }
@@ -193,12 +195,12 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, c
       const double speedLimitSquared = lim * lim;
       if (sleep == CANNON_AWAKE && speedSquared < speedLimitSquared) {
         sleep = CANNON_SLEEPY;
-        B.tLastSleepy[i] = P.time;
+        B.tLastSleepy[i] = __longlong_as_double(P.clk[0]);
         B.sleep[i] = sleep;
       } else if (sleep == CANNON_SLEEPY && speedSquared > speedLimitSquared) {
         sleep = CANNON_AWAKE;
         B.sleep[i] = sleep;
-      } else if (sleep == CANNON_SLEEPY && P.time - B.tLastSleepy[i] > B.sleepTime[i]) {
+      } else if (sleep == CANNON_SLEEPY && __longlong_as_double(P.clk[0]) - B.tLastSleepy[i] > B.sleepTime[i]) {
         sleep = CANNON_SLEEPING;
         B.sleep[i] = sleep;
         v.x = v.y = v.z = 0.f;

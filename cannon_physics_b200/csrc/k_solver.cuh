@@ -264,15 +264,25 @@ __global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int
 // arrival counter in word 0 and the published generation in word 32 (its own 128-byte line). Only the arrivals
 // touch the counter (one atomic per CTA); the last arriver publishes the generation and everybody else polls that
 // second line with a short sleep, so the pollers do not fight the atomics for the same L2 line.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
+// how many CTAs of a cooperative launch take part: enough for `items` units of work per phase at `perCta` each, rounded
+// up to a power of two, never more than were launched. The rest return at once, so a small world pays for a small
+// barrier although the launch (and a captured graph of it) always has the full co-resident grid.
+__device__ __forceinline__ int coop_ctas(long long items, int perCta) {
+  long long b = (items + perCta - 1) / perCta;
+  long long q = 1;
+  while (q < b) q <<= 1;
+  return (int)(q < (long long)gridDim.x ? q : (long long)gridDim.x);
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, int nCtas) {
   __syncthreads();
-  if (gridDim.x == 1) return;  // single-CTA launches (small worlds) only need the block barrier
+  if (nCtas == 1) return;  // single-CTA launches (small worlds) only need the block barrier
   if (threadIdx.x == 0) {
     epoch += 1;
     __threadfence();
     const unsigned arrived = atomicAdd(bar, 1u) + 1u;
     volatile unsigned* gen = (volatile unsigned*)(bar + 32);
-    if (arrived == epoch * gridDim.x) {
+    if (arrived == epoch * (unsigned)nCtas) {
       *gen = epoch;
     } else {
       while (*gen < epoch) __nanosleep(20);
@@ -286,10 +296,12 @@ __global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int
                                                  int* __restrict__ nIslands, unsigned* bar) {
   unsigned epoch = 0;
   const int nUnits = min(*U.nUnits, U.unitCap);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nCtas = coop_ctas(max(nUnits / 2 + 1, nBodies / 4 + 1), 256);
+  if ((int)blockIdx.x >= nCtas) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
   for (int b = tid; b < nBodies; b += nth) label[b] = B.type[b] == CANNON_BODY_STATIC ? -1 : b;
   if (tid == 0) { changed[0] = 0; changed[1] = 0; *nIslands = 0; }
-  grid_barrier(bar, epoch);
+  grid_barrier(bar, epoch, nCtas);
   for (int round = 0;; round++) {
     int* flag = &changed[round & 1];
     for (int u = tid; u < nUnits; u += nth) {
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int
       atomicMin(&label[bj], m);
       *flag = 1;
     }
-    grid_barrier(bar, epoch);
+    grid_barrier(bar, epoch, nCtas);
     for (int b = tid; b < nBodies; b += nth) {  // pointer jumping
       int l = __ldcg(&label[b]);
       if (l < 0) continue;
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(256) k_islands(BodyArrays B, UnitArrays U, int
       label[b] = l;
     }
     if (tid == 0) changed[(round + 1) & 1] = 0;
-    grid_barrier(bar, epoch);
+    grid_barrier(bar, epoch, nCtas);
     if (__ldcg(flag) == 0) break;
   }
   for (int b = tid; b < nBodies; b += nth)
@@ -341,10 +353,12 @@ struct SchedArrays {
 __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, int colored) {
   unsigned epoch = 0;
   const int nUnits = min(*U.nUnits, U.unitCap);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nCtas = coop_ctas(nUnits / 2 + 1, 256);
+  if ((int)blockIdx.x >= nCtas) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
   for (int u = tid; u < nUnits; u += nth) { S.act0[u] = u; S.unitLevel[u] = -1; }
   if (tid == 0) { S.actCount[0] = nUnits; S.actCount[1] = 0; *S.cursor = 0; S.levelStart[0] = 0; }
-  grid_barrier(S.bar, epoch);
+  grid_barrier(S.bar, epoch, nCtas);
   int round = 0;
   int cur = 0;
   while (true) {
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       if (fl & 1) atomicMin(&S.claim[U.uBi[u]], key);
       if (fl & 2) atomicMin(&S.claim[U.uBj[u]], key);
     }
-    grid_barrier(S.bar, epoch);
+    grid_barrier(S.bar, epoch, nCtas);
     // winners go to the execution order, losers to the next round's list: one cursor atomic per warp and list
     for (int a0 = tid - (int)(threadIdx.x & 31); a0 < nAct; a0 += nth) {
       const int a = a0 + (int)(threadIdx.x & 31);
@@ -396,11 +410,11 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       if (emit) S.order[bw + __popc(mw & lt)] = u;
       else if (active && !win) nxt[bl + __popc(ml & lt)] = u;
     }
-    grid_barrier(S.bar, epoch);
+    grid_barrier(S.bar, epoch, nCtas);
     if (tid == 0) { S.levelStart[round + 1] = *(volatile int*)S.cursor; S.actCount[cur] = 0; }
     round++;
     cur ^= 1;
-    grid_barrier(S.bar, epoch);
+    grid_barrier(S.bar, epoch, nCtas);
   }
   if (tid == 0) { *S.nLevels = round; *U.nExec = *(volatile int*)S.cursor; }
 }
@@ -551,12 +565,15 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
   __shared__ int s_any;
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nLevels = *S.nLevels;
+  // CTAs for about twice the mean colour width (one unit per thread)
+  const int nCtas = coop_ctas(2LL * S.levelStart[nLevels] / max(nLevels, 1) + 1, 256);
+  if ((int)blockIdx.x >= nCtas) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
   // units of a level are dealt to the CTAs warp by warp (32 consecutive units per warp, consecutive warps on different
   // CTAs), so a narrow level still spreads over every SM instead of filling the first few CTAs
-  const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
+  const int itid = (((threadIdx.x >> 5) * nCtas + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
-  const int nLevels = *S.nLevels;
   const bool batch = G.nGroups > 1;
   int iter = 0;
   for (; iter != P.maxIter; iter++) {
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
         if (batch) atomicAdd(&G.worldTot[w], acc);
         else local += acc;
       }
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
     }
     // tolerance test (gs_solver.dart:105): the sum is order-insensitive for the comparison against tol^2
     bool allDone;
@@ -624,10 +641,10 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_red[k];
         atomicAdd(&G.worldTot[0], t);
       }
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       const double tot = __ldcg(&G.worldTot[0]);
       allDone = tot * tot < P.tol2;
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       if (tid == 0) G.worldTot[0] = 0.0;
     } else {
       if (threadIdx.x == 0) s_any = 0;
@@ -642,9 +659,9 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
       if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);  // slot nWorlds: "some world still iterating"
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       if (tid == 0) G.worldDone[G.nGroups] = 0;
     }
     if (allDone) break;
@@ -674,12 +691,15 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
   __shared__ int s_any;
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nLevels = *S.nLevels;
+  // CTAs for about twice the mean colour width (one unit per thread)
+  const int nCtas = coop_ctas(2LL * S.levelStart[nLevels] / max(nLevels, 1) + 1, 256);
+  if ((int)blockIdx.x >= nCtas) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
   // units of a level are dealt to the CTAs warp by warp (32 consecutive units per warp, consecutive warps on different
   // CTAs), so a narrow level still spreads over every SM instead of filling the first few CTAs
-  const int itid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31);
+  const int itid = (((threadIdx.x >> 5) * nCtas + blockIdx.x) << 5) | (threadIdx.x & 31);
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
-  const int nLevels = *S.nLevels;
   const bool batch = G.nGroups > 1;
   int iter = 0;
   for (; iter != P.maxIter; iter++) {
@@ -750,7 +770,7 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
         else local += (double)acc;
       }
       GS_TRACE_WORK();
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       GS_TRACE_END();
     }
     bool allDone;
@@ -763,10 +783,10 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_red[k];
         atomicAdd(&G.worldTot[0], t);
       }
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       const double tot = __ldcg(&G.worldTot[0]);
       allDone = tot * tot < P.tol2;
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       if (tid == 0) G.worldTot[0] = 0.0;
     } else {
       if (threadIdx.x == 0) s_any = 0;
@@ -781,9 +801,9 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
       if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       if (tid == 0) G.worldDone[G.nGroups] = 0;
     }
     if (allDone && !P.debugSkipWork) break;
@@ -915,10 +935,13 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   __shared__ int s_lt[GS_LS_MAX + 2];
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const int nLevels = *S.nLevels;
+  // CTAs for about twice the mean number of warp tasks per colour
+  const int nCtas = coop_ctas(2LL * min(*T.nTasks, T.taskCap) / max(nLevels, 1) + 1, GS_WARPS);
+  if ((int)blockIdx.x >= nCtas) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
-  const int nLevels = *S.nLevels;
   const bool batch = G.nGroups > 1;
   const int* lt = T.lvlTask;
   if (nLevels <= GS_LS_MAX) {
@@ -931,7 +954,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   unsigned char* wbase = s_dyn + (size_t)wic * GS_WARP_BYTES;
   float* slam = (float*)(wbase + 2 * GS_BUF_BYTES);
   // tasks of a colour are dealt to the warps CTA-interleaved so a narrow colour still spreads over every SM
-  const int gw = wic * gridDim.x + blockIdx.x, nW = gridDim.x * GS_WARPS;
+  const int gw = wic * nCtas + blockIdx.x, nW = nCtas * GS_WARPS;
 
   // three tasks in flight per warp: t0 being solved (rows in buffer `buf`), t1 rows in flight, t2 table entry in flight
   GsTask t0, t1, t2;
@@ -1082,7 +1105,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
         }
       }
       GS_TRACE_WORK();
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       GS_TRACE_END();
       if (!batch && lvl == 0 && tid == 0) G.worldTot[(iter + 2) % 3] = 0.0;  // last read before this barrier, next used in iter+2
     }
@@ -1103,9 +1126,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
       if (anyLive) atomicOr(&s_any, 1);
       __syncthreads();
       if (threadIdx.x == 0 && s_any) atomicOr(&G.worldDone[G.nGroups], 1);
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       allDone = __ldcg(&G.worldDone[G.nGroups]) == 0;
-      grid_barrier(S.bar, epoch);
+      grid_barrier(S.bar, epoch, nCtas);
       if (tid == 0) G.worldDone[G.nGroups] = 0;
     }
     if (allDone && !P.debugSkipWork) break;

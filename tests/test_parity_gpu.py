@@ -212,3 +212,31 @@ def test_oversize_hulls_take_the_sequential_sat_path(cuda_lib, oracle_lib):
     for s in range(80):
         seen = max(seen, parity.staged_step(dev, ref, 1 / 60, f"oversize step {s}")[1])
     assert seen > 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2 sap stacks", "c5 sleeping", "c4 joints", "c3 heightfield"])
+def test_graph_replay_equals_eager_launches(cuda_lib, name):
+    """cannon_world_step replays a captured CUDA graph of one step; the eager launch sequence must give the same bits
+    (time / stepnumber live on the device, cooperative kernels size their own barriers)."""
+    import os
+    mk = {"c2 sap stacks": lambda: scenes.box_stacks(6, 5, grid=3),
+          "c5 sleeping": lambda: scenes.sphere_container(6, 6, 3, extent=4.0, solver=F.SOLVER_REFERENCE_ORDER),
+          "c4 joints": lambda: scenes.chain_worlds(6, chains=2, links=5),
+          "c3 heightfield": lambda: scenes.mixed_pile_on_heightfield(6, 6, 3, solver=F.SOLVER_REFERENCE_ORDER)}[name]
+    a = engine.DeviceWorld(cuda_lib, mk())
+    b = engine.DeviceWorld(cuda_lib, mk())
+    a.step(1 / 60, 70)  # step 1 eager, 69 replays
+    a.step(1 / 60, 50)
+    os.environ["CANNON_NO_GRAPH"] = "1"
+    try:
+        b.step(1 / 60, 70)
+        b.step(1 / 60, 50)
+    finally:
+        del os.environ["CANNON_NO_GRAPH"]
+    parity.assert_same_state(a, b, name)
+    pa, pb = a.profile(), b.profile()
+    for k in ("n_pairs", "n_contacts", "n_rows", "steps", "contact_iters_total", "kernel_launches"):
+        if k != "kernel_launches":
+            assert pa[k] == pb[k], (k, pa[k], pb[k])
+    assert a.get_time() == b.get_time()

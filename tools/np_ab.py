@@ -4,6 +4,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ["CANNON_NO_GRAPH"] = "1"  # the debug switch is read per launch
 import bench  # noqa: E402
 import cannon_physics_b200 as cp  # noqa: E402
 from cannon_physics_b200 import engine  # noqa: E402
