@@ -177,6 +177,7 @@ struct cannon_world {
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
   DBuf<float4> rRec;
   DBuf<GsUnitRec> uRec;
+  DBuf<int> eLevel, orderW, worldCount, worldUnitStart;
   DBuf<int2> gsTab;
   DBuf<int> gsLvlTask, gsLvlWin;
   int gsTaskCap = 0;
@@ -376,6 +377,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast_v1, 256, 0);
   w->coopBlocksGsFastV1 = ctx->sms * std::max(1, std::min(occ, 4));
   cudaFuncSetAttribute(k_gs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BYTES);
+  cudaFuncSetAttribute(k_gs_world, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
@@ -404,7 +406,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
@@ -665,6 +667,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   w->unitCap = unitCap;
   RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
+  RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * (w->desc.n_worlds + 2)); RES(worldUnitStart, w->desc.n_worlds + 2);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
@@ -1112,7 +1115,7 @@ static UnitArrays unit_arrays(cannon_world* w) {
   UnitArrays U;
   U.nUnits = w->cnt.p + CT_NUNITS; U.nExec = w->cnt.p + CT_NEXEC;
   U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p;
-  U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p;
+  U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p; U.eLevel = w->eLevel.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
   return U;
 }
@@ -1197,14 +1200,25 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, cudaLaunchCooperativeKernel((void*)k_islands, dim3(w->coopBlocksSched), dim3(256), args, 0, s));
     W_TRY(w, cudaMemsetAsync(cnt + CT_BAR, 0, 64 * sizeof(int), s));
   }
-  { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, w->order.p); }
+  // a colored batch is swept world by world (k_gs_world): regroup the execution order by world first
+  const bool perWorld = P.colored && nW > 1 && !w->gsFastV1 && !getenv("CANNON_GS_NO_WORLD_KERNEL");
+  const int* order = w->order.p;
+  if (perWorld) {
+    int* wc = w->worldCount.p;
+    W_TRY(w, cudaMemsetAsync(wc, 0, 2 * (nW + 2) * sizeof(int), s));
+    { g_kernel_launches++; k_world_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, wc); }
+    W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nW + 1, nW + 1, nullptr, w->scanTmp, s));
+    { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, w->worldUnitStart.p, wc + nW + 2, w->orderW.p); }
+    order = w->orderW.p;
+  }
+  { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, order, w->unitLevel.p); }
   { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NEXEC, w->unitCap); }
   { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
   W_TRY(w, scan_exclusive(w->eRows.p, w->eRowBase.p, cnt + CT_NUNITS1, 0, w->unitCap + 1, nullptr, w->scanTmp, s));
-  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, w->order.p, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
+  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, order, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
   GsTasks T;
   T.tab = w->gsTab.p; T.lvlTask = w->gsLvlTask.p; T.lvlWin = w->gsLvlWin.p; T.nTasks = cnt + CT_GS_NTASKS; T.taskCap = w->gsTaskCap;
-  if (P.colored && !w->gsFastV1) {
+  if (P.colored && !w->gsFastV1 && !perWorld) {
     { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
     { g_kernel_launches++; k_gs_task_fill<<<grid_for(w, w->gsTaskCap + 1, 256), 256, 0, s>>>(U, S, T); }
   }
@@ -1216,7 +1230,11 @@ static int32_t st_solve(cannon_world* w, double dt) {
     void* args[] = {&R, &B, &U, &S, &P, &G};
     void* argsT[] = {&R, &B, &U, &S, &T, &P, &G};
     g_kernel_launches++;
-    if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
+    if (perWorld) {
+      const int* wus = w->worldUnitStart.p;
+      const int* wbs = w->worldStart.p;
+      k_gs_world<<<nW, GW_THREADS, GW_SMEM_BYTES, s>>>(R, B, U, S, P, G, wus, wbs);
+    } else if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
     else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
     else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
   }

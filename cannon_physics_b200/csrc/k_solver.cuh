@@ -52,6 +52,7 @@ struct UnitArrays {
   int* unitRow;                              // unit id -> first execution row (debug / multipliers)
   int unitCap;
   struct GsUnitRec* rec;                     // COLORED mode: the execution record the staged sweep copies to shared memory
+  int* eLevel;                               // colour of each execution position (per-world sweep of a batch)
 };
 
 // one 32-byte record per unit in execution order (COLORED mode), bulk-copied to shared memory by k_gs_fast
@@ -420,12 +421,13 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
 }
 
 // rows per unit in execution order (input of the row-base scan) + per-unit execution data
-__global__ void __launch_bounds__(256) k_exec_units(BodyArrays B, UnitArrays U, const int* __restrict__ order) {
+__global__ void __launch_bounds__(256) k_exec_units(BodyArrays B, UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel) {
   const int nUnits = min(*U.nExec, U.unitCap);
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
     const int u = order[a];
     const int bi = U.uBi[u], bj = U.uBj[u];
     U.eRows[a] = U.uRows[u];
+    U.eLevel[a] = unitLevel[u];
     U.eBi[a] = bi; U.eBj[a] = bj; U.eFlags[a] = U.uFlags[u];
     U.eImA[a] = body_frozen(B, bi) ? 0.0 : B.invMass[bi];
     U.eImB[a] = body_frozen(B, bj) ? 0.0 : B.invMass[bj];
@@ -1136,4 +1138,159 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   // a copy started for a task that will never run must land before the CTA may retire
   if (pend0) mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u);
   if (tid == 0) *G.itersDone = iter;
+}
+
+// ---- batches of small worlds: one CTA per world -------------------------------------------------------------------
+// A batch (n_worlds > 1) has no coupling between worlds, so the colored sweep does not need the grid at all: the
+// execution order is regrouped by world (k_world_count / k_world_fill), a CTA takes one world, keeps that world's
+// vlambda / wlambda in shared memory, walks the world's units colour by colour with __syncthreads() between colours
+// and leaves as soon as ITS world meets the tolerance (gs_solver.dart:105 per world, like separate World objects).
+#define GW_THREADS 128
+#define GW_MAXB 256    // bodies of a world whose lambdas fit the shared arrays (larger worlds use the global arrays)
+#define GW_MAXU 2048   // units of a world sorted by colour in shared memory (larger worlds scan their unit range per colour)
+#define GW_MAXL 256
+
+__global__ void __launch_bounds__(256) k_world_count(UnitArrays U, const int* __restrict__ order, const int* __restrict__ bodyWorld,
+                                                     int* __restrict__ worldCount) {
+  const int n = min(*U.nExec, U.unitCap);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) atomicAdd(&worldCount[bodyWorld[U.uBi[order[a]]]], 1);
+}
+
+__global__ void __launch_bounds__(256) k_world_fill(UnitArrays U, const int* __restrict__ order, const int* __restrict__ bodyWorld,
+                                                    const int* __restrict__ worldStart, int* __restrict__ worldCursor, int* __restrict__ orderW) {
+  const int n = min(*U.nExec, U.unitCap);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    const int u = order[a], wd = bodyWorld[U.uBi[u]];
+    orderW[worldStart[wd] + atomicAdd(&worldCursor[wd], 1)] = u;
+  }
+}
+
+#define GW_ROWS_CAP 576   // rows of a world staged in shared memory (80 B each)
+#define GW_UNITS_CAP 512  // unit records of a world staged in shared memory (32 B each)
+#define GW_SMEM_BYTES (GW_ROWS_CAP * 80 + GW_UNITS_CAP * 32 + GW_ROWS_CAP * 4)
+
+__global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G,
+                                                         const int* __restrict__ worldStart, const int* __restrict__ worldBody) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];  // rows | unit records | lambdas of this world
+  __shared__ float4 s_v[GW_MAXB], s_w[GW_MAXB];
+  __shared__ unsigned short s_idx[GW_MAXU];
+  __shared__ int s_start[GW_MAXL + 2], s_cur[GW_MAXL + 1];
+  __shared__ double s_red[GW_THREADS / 32];
+  __shared__ unsigned long long s_mbar;
+  __shared__ int s_flag;
+  const int wd = blockIdx.x, tid = threadIdx.x;
+  const int a0 = worldStart[wd], nU = worldStart[wd + 1] - a0;
+  if (nU <= 0) return;
+  const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
+  const int r0w = U.eRowBase[a0], nR = U.eRowBase[a0 + nU] - r0w;
+  // the whole world (rows, unit records) is copied to shared memory once with two bulk copies when it fits
+  const bool staged = nR <= GW_ROWS_CAP && nU <= GW_UNITS_CAP && nR > 0;
+  float4* const sRows = (float4*)s_dyn;
+  GsUnitRec* const sUnits = (GsUnitRec*)(s_dyn + GW_ROWS_CAP * 80);
+  float* const sLam = (float*)(s_dyn + GW_ROWS_CAP * 80 + GW_UNITS_CAP * 32);
+  if (tid == 0) { mbar_init(&s_mbar, 1); s_flag = 0; }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (staged && tid == 0) {
+    mbar_expect_tx(&s_mbar, (unsigned)(nR * 80 + nU * 32));
+    bulk_g2s(sRows, R.rec + (size_t)r0w * 5, (unsigned)(nR * 80), &s_mbar);
+    bulk_g2s(sUnits, U.rec + a0, (unsigned)(nU * 32), &s_mbar);
+  }
+  const bool sb = nB <= GW_MAXB;  // this world's vlambda / wlambda live in shared memory
+  float4* const vl = sb ? s_v : B.vlam;
+  float4* const wl = sb ? s_w : B.wlam;
+  const int boff = sb ? b0 : 0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sb) for (int i = tid; i < nB; i += GW_THREADS) { s_v[i] = z4; s_w[i] = z4; }
+  if (staged) for (int i = tid; i < nR; i += GW_THREADS) sLam[i] = 0.f;  // k_rows_build left every lambda at zero
+  for (int i = tid; i < GW_MAXL + 2; i += GW_THREADS) s_start[i] = 0;
+  __syncthreads();
+  bool sorted = nU <= GW_MAXU;
+  if (sorted)
+    for (int a = tid; a < nU; a += GW_THREADS) {
+      const int l = U.eLevel[a0 + a];
+      if (l >= GW_MAXL) s_flag = 1;
+      else atomicAdd(&s_start[l + 2], 1);
+    }
+  __syncthreads();
+  sorted = sorted && !s_flag;
+  int nLv = *S.nLevels;
+  if (sorted) {
+    if (tid == 0) {  // s_start[l + 1] = first slot of colour l, s_start[0] = number of colours of this world
+      int run = 0, last = 0;
+      for (int l = 0; l < GW_MAXL; l++) {
+        const int c = s_start[l + 2];
+        s_start[l + 1] = run;
+        s_cur[l] = run;
+        run += c;
+        if (c) last = l + 1;
+      }
+      s_start[GW_MAXL + 1] = run;
+      s_start[0] = last;
+    }
+    __syncthreads();
+    nLv = s_start[0];
+    for (int a = tid; a < nU; a += GW_THREADS) s_idx[atomicAdd(&s_cur[U.eLevel[a0 + a]], 1)] = (unsigned short)a;
+    __syncthreads();
+  }
+  if (staged) mbar_wait(&s_mbar, 0);
+  const float4* const rowBase = staged ? sRows - (size_t)r0w * 5 : R.rec;
+  float* const lamBase = staged ? sLam - r0w : R.flambda;
+  int iter = 0;
+  for (; iter != P.maxIter; iter++) {
+    double local = 0.0;
+    for (int l = 0; l < nLv; l++) {
+      const int k0 = sorted ? s_start[l + 1] : 0, k1 = sorted ? s_start[l + 2] : nU;
+      for (int k = k0 + tid; k < k1; k += GW_THREADS) {
+        int a;
+        if (sorted) a = s_idx[k];
+        else { a = k; if (U.eLevel[a0 + a] != l) continue; }
+        const GsUnitRec m = staged ? sUnits[a] : U.rec[a0 + a];
+        if (m.r1 <= m.r0) continue;
+        float4 vA = (m.fl & 1) ? vl[m.bi - boff] : z4, wA = (m.fl & 1) ? wl[m.bi - boff] : z4;
+        float4 vB = (m.fl & 2) ? vl[m.bj - boff] : z4, wB = (m.fl & 2) ? wl[m.bj - boff] : z4;
+        float acc = 0.f;
+        const float4* q = rowBase + (size_t)m.r0 * 5;
+        float* lp = lamBase + m.r0;
+        for (int r = m.r0; r < m.r1; r++, q += 5, lp++) {
+          const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+          const float lam = *lp;
+          float gw_ = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
+          gw_ += dot3f(q1, wA.x, wA.y, wA.z);
+          gw_ += dot3f(q2, wB.x, wB.y, wB.z);
+          float dl = q1.w * (q0.w - gw_ - q2.w * lam);
+          if (lam + dl < q3.w) dl = q3.w - lam;
+          else if (lam + dl > q4.w) dl = q4.w - lam;
+          *lp = lam + dl;
+          if (m.fl & 1) {
+            const float sA = -m.imA * dl;
+            vA.x = fmaf(sA, q0.x, vA.x); vA.y = fmaf(sA, q0.y, vA.y); vA.z = fmaf(sA, q0.z, vA.z);
+            wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+          }
+          if (m.fl & 2) {
+            const float sB = m.imB * dl;
+            vB.x = fmaf(sB, q0.x, vB.x); vB.y = fmaf(sB, q0.y, vB.y); vB.z = fmaf(sB, q0.z, vB.z);
+            wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+          }
+          acc += fabsf(dl);
+        }
+        if (m.fl & 1) { vl[m.bi - boff] = vA; wl[m.bi - boff] = wA; }
+        if (m.fl & 2) { vl[m.bj - boff] = vB; wl[m.bj - boff] = wB; }
+        local += (double)acc;
+      }
+      __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = local;
+    __syncthreads();
+    double tot = 0.0;
+    for (int k = 0; k < GW_THREADS / 32; k++) tot += s_red[k];
+    __syncthreads();
+    if (tot * tot < P.tol2) break;
+  }
+  if (sb)
+    for (int i = tid; i < nB; i += GW_THREADS) { B.vlam[b0 + i] = s_v[i]; B.wlam[b0 + i] = s_w[i]; }
+  if (staged)
+    for (int i = tid; i < nR; i += GW_THREADS) R.flambda[r0w + i] = sLam[i];
+  if (tid == 0) { G.worldIters[wd] = iter; atomicMax(G.itersDone, iter); }
 }

@@ -240,3 +240,29 @@ def test_graph_replay_equals_eager_launches(cuda_lib, name):
         if k != "kernel_launches":
             assert pa[k] == pb[k], (k, pa[k], pb[k])
     assert a.get_time() == b.get_time()
+
+
+@pytest.mark.gpu
+def test_batch_colored_world_kernel_equals_grid_sweep(cuda_lib):
+    """A colored batch is swept by one CTA per world (k_gs_world); the grid-wide staged sweep over the same colours must
+    give the same bits: units of one colour touch disjoint bodies, so the order inside a colour cannot matter."""
+    def mk():
+        spec = scenes.chain_worlds(40, chains=2, links=6)
+        spec.desc["solver_kind"] = F.SOLVER_COLORED
+        return spec
+    a = engine.DeviceWorld(cuda_lib, mk())
+    b = engine.DeviceWorld(cuda_lib, mk())
+    os.environ["CANNON_GS_NO_WORLD_KERNEL"] = "1"
+    os.environ["CANNON_NO_GRAPH"] = "1"
+    try:
+        b.step(1 / 60, 90)
+    finally:
+        del os.environ["CANNON_GS_NO_WORLD_KERNEL"]
+        del os.environ["CANNON_NO_GRAPH"]
+    a.step(1 / 60, 90)
+    parity.assert_same_state(a, b, "colored batch")
+    assert a.profile()["n_rows"] == b.profile()["n_rows"] > 0
+    # the colored order converges differently along a chain than the reference's list order (10 sweeps do not
+    # converge either), so only sanity is asserted against it: the chains hold together and stay near their anchors
+    pa = a.get_bodies(("position", "velocity"))
+    assert np.all(np.isfinite(pa["position"])) and np.abs(pa["position"]).max() < 20 and np.abs(pa["velocity"]).max() < 30

@@ -19,6 +19,9 @@ from cannon_physics_b200 import engine  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 config = sys.argv[2] if len(sys.argv) > 2 else "c3"
 spec, label = bench.build_spec(config, 1.0, 0, 1)
+if len(sys.argv) > 3:
+    from cannon_physics_b200 import _ffi as F
+    spec.desc["solver_kind"] = F.SOLVER_COLORED if sys.argv[3] == "colored" else F.SOLVER_REFERENCE_ORDER
 w = engine.DeviceWorld(cp.lib, spec, device=0)
 w.step(1 / 60, steps)
 prof = w.profile()
