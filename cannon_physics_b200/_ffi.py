@@ -21,7 +21,7 @@ BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC = 0, 1, 2
 AWAKE, SLEEPY, SLEEPING = 0, 1, 2
 BP_NAIVE, BP_SAP, BP_GRID = 0, 1, 2
 SOLVER_REFERENCE_ORDER, SOLVER_COLORED, SOLVER_SPLIT = 0, 1, 2
-CONSTRAINT_POINT_TO_POINT, CONSTRAINT_HINGE = 0, 1
+CONSTRAINT_POINT_TO_POINT, CONSTRAINT_HINGE, CONSTRAINT_DISTANCE, CONSTRAINT_LOCK, CONSTRAINT_CONE_TWIST = 0, 1, 2, 3, 4
 
 
 class ContactMaterialPOD(C.Structure):
@@ -89,6 +89,7 @@ class ConstraintDesc(C.Structure):
         ("pivot_a", c_f32 * 3), ("pivot_b", c_f32 * 3), ("axis_a", c_f32 * 3), ("axis_b", c_f32 * 3),
         ("max_force", c_f64), ("collide_connected", c_i32), ("motor_enabled", c_i32),
         ("motor_target_velocity", c_f64), ("motor_max_force", c_f64),
+        ("distance", c_f64), ("angle", c_f64), ("twist_angle", c_f64),
     ]
 
 

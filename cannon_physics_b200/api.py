@@ -5,7 +5,7 @@ Same class names, constructor arguments and defaults as the Dart library so that
 
     World / Body / Sphere / Plane / Box / Cylinder / ConvexPolyhedron / Heightfield / Material /
     ContactMaterial / NaiveBroadphase / SAPBroadphase / GridBroadphase / GSSolver /
-    PointToPointConstraint / HingeConstraint
+    PointToPointConstraint / HingeConstraint / DistanceConstraint / LockConstraint / ConeTwistConstraint
 
 (lib/world/world_class.dart:44, lib/objects/rigid_body.dart:26, lib/rigid_body_shapes/*.dart,
 lib/material/*.dart, lib/collision/*broadphase.dart, lib/solver/gs_solver.dart, lib/constraints/*.dart).
@@ -28,7 +28,8 @@ from .engine import Context, DeviceWorld, SceneSpec
 __all__ = [
     "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
-    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "World",
+    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint",
+    "World",
     "CudaWorld", "CannonError",
 ]
 
@@ -348,6 +349,43 @@ class HingeConstraint(PointToPointConstraint):  # hinge_constraint.dart:10
     def _desc(self, idx):
         return dict(super()._desc(idx), axis_a=self.axisA, axis_b=self.axisB, motor_enabled=int(self.motorEnabled),
                     motor_target_velocity=self.motorTargetVelocity, motor_max_force=self.motorMaxForce)
+
+
+class DistanceConstraint(Constraint):  # distance_constraint.dart:7
+    type = F.CONSTRAINT_DISTANCE
+
+    def __init__(self, bodyA, bodyB, distance: Optional[float] = None, maxForce: float = 1e6):
+        super().__init__(bodyA, bodyB)
+        self.distance = distance  # None: the distance between the bodies when the constraint reaches the world
+        self.maxForce = maxForce
+
+    def _desc(self, idx):
+        return dict(type=self.type, body_a=idx[id(self.bodyA)], body_b=idx[id(self.bodyB)], max_force=self.maxForce,
+                    collide_connected=int(self.collideConnected), distance=-1.0 if self.distance is None else float(self.distance))
+
+
+class LockConstraint(PointToPointConstraint):  # lock_constraint.dart:9
+    """The pivots and the frame vectors are taken from the bodies' poses when the constraint reaches the world
+    (lock_constraint.dart:29-43), quirks of Body.vectorToLocalFrame included."""
+    type = F.CONSTRAINT_LOCK
+
+    def __init__(self, bodyA, bodyB, maxForce: float = 1e6):
+        super().__init__(bodyA, bodyB, None, None, maxForce)
+
+
+class ConeTwistConstraint(PointToPointConstraint):  # cone_twist_constraint.dart:11
+    type = F.CONSTRAINT_CONE_TWIST
+
+    def __init__(self, bodyA, bodyB, pivotA=None, pivotB=None, axisA=None, axisB=None, angle: float = 0.0, twistAngle: float = 0.0,
+                 maxForce: float = 1e6, collideConnected: bool = False):
+        super().__init__(bodyA, bodyB, pivotA, pivotB, maxForce)
+        # the reference accepts collideConnected but never forwards it to Constraint (cone_twist_constraint.dart:38-40)
+        self.axisA = Vec3() if axisA is None else np.array(axisA, dtype=np.float32)
+        self.axisB = Vec3() if axisB is None else np.array(axisB, dtype=np.float32)
+        self.angle, self.twistAngle = angle, twistAngle
+
+    def _desc(self, idx):
+        return dict(super()._desc(idx), axis_a=self.axisA, axis_b=self.axisB, angle=float(self.angle), twist_angle=float(self.twistAngle))
 
 
 class World:  # lib/world/world_class.dart:44

@@ -190,7 +190,8 @@ struct cannon_world {
   // device: joints
   DBuf<int> jBodyA, jBodyB, jKind, jEnabled, jRowSlot, jFirst, jSlotEq;
   DBuf<float4> jPivotA, jPivotB, jAxisA, jAxisB, jNi;
-  DBuf<double> jMinF, jMaxF, jA, jB, jEps, jTargetVel;
+  DBuf<double> jMinF, jMaxF, jA, jB, jEps, jTargetVel, jCos, jParam;
+  DBuf<int> jMode;
   int nJointEq = 0, nJointAccepted = 0;
   // device: scheduler / gs
   DBuf<unsigned long long> claim;
@@ -408,7 +409,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
-  REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
+  REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
@@ -807,22 +808,29 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   if (!w || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
-  std::vector<int> bodyA, bodyB, kind, enabled, rowSlot, first, slotEq;
+  std::vector<int> bodyA, bodyB, kind, enabled, rowSlot, first, slotEq, mode;
   std::vector<float4> pivotA, pivotB, axisA, axisB, ni;
-  std::vector<double> minF, maxF, a, b, eps, targetVel;
+  std::vector<double> minF, maxF, a, b, eps, targetVel, cosv, param;
   std::vector<unsigned long long> keys;
-  // trigger flags are needed for the Solver.addEquation filter (solver.dart:30-34)
+  // trigger flags are needed for the Solver.addEquation filter (solver.dart:30-34); constructors that read body state
+  // (LockConstraint, DistanceConstraint) see the bodies as they are now
   std::vector<int> flags(w->n);
-  if (w->n) W_TRY(w, cudaMemcpy(flags.data(), w->flags.p, w->n * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<float4> hpos(w->n), hquat(w->n);
+  if (w->n) {
+    W_TRY(w, cudaMemcpy(flags.data(), w->flags.p, w->n * sizeof(int), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hpos.data(), w->pos.p, w->n * sizeof(float4), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hquat.data(), w->quat.p, w->n * sizeof(float4), cudaMemcpyDeviceToHost));
+  }
   std::vector<int> wake;
   // Equation ctor SPOOK parameters (equation_class.dart:38): k=1e7, d=4, h=1/60 — never refreshed for joints
   const double k0 = 1e7, d0 = 4, h0 = 1.0 / 60;
   const double sa = 4.0 / (h0 * (1 + 4 * d0)), sbv = 4.0 * d0 / (1 + 4 * d0), se = 4.0 / (h0 * h0 * k0 * (1 + 4 * d0));
+  const double cosHalfPi = cos(M_PI / 2);  // RotationalEquation.maxAngle default, rotational_equation.dart:17
   int slot = 0;
   for (int i = 0; i < n; i++) {
     const cannon_constraint_desc& d = cs[i];
     if (d.body_a < 0 || d.body_b < 0 || d.body_a >= w->n || d.body_b >= w->n) return fail(w->ctx, CANNON_E_INVALID, "constraint references unknown body");
-    if (d.type != CANNON_CONSTRAINT_POINT_TO_POINT && d.type != CANNON_CONSTRAINT_HINGE)
+    if (d.type < CANNON_CONSTRAINT_POINT_TO_POINT || d.type > CANNON_CONSTRAINT_CONE_TWIST)
       return fail(w->ctx, CANNON_E_UNSUPPORTED, "constraint type outside the hot-path scope (SURVEY.md §8f)");
     wake.push_back(d.body_a);
     wake.push_back(d.body_b);
@@ -832,38 +840,74 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
     }
     const bool trig = (flags[d.body_a] & BF_IS_TRIGGER) || (flags[d.body_b] & BF_IS_TRIGGER);
     const int firstEq = (int)bodyA.size();
+    const f3 xA = ld3(hpos[d.body_a]), xB = ld3(hpos[d.body_b]);
+    const q4 qA = ldq(hquat[d.body_a]), qB = ldq(hquat[d.body_b]);
+    f3 pvA, pvB;
+    pvA.x = d.pivot_a[0]; pvA.y = d.pivot_a[1]; pvA.z = d.pivot_a[2];
+    pvB.x = d.pivot_b[0]; pvB.y = d.pivot_b[1]; pvB.z = d.pivot_b[2];
     f3 axA; axA.x = d.axis_a[0]; axA.y = d.axis_a[1]; axA.z = d.axis_a[2];
     f3 axB; axB.x = d.axis_b[0]; axB.y = d.axis_b[1]; axB.z = d.axis_b[2];
-    vnormalize(axA);  // hinge_constraint.dart:34-37
-    vnormalize(axB);
-    const int neq = d.type == CANNON_CONSTRAINT_HINGE ? 6 : 3;
-    for (int e = 0; e < neq; e++) {
+    f3 zero3; zero3.x = zero3.y = zero3.z = 0.f;
+    // one equation of this constraint
+    auto push = [&](int kd, int md, const f3& eqAxisA, const f3& eqAxisB, int axisIdx, double lo, double hi, double cs_, double prm, int en, double tv) {
       bodyA.push_back(d.body_a);
       bodyB.push_back(d.body_b);
       first.push_back(firstEq);
-      pivotA.push_back(make_float4(d.pivot_a[0], d.pivot_a[1], d.pivot_a[2], 0));
-      pivotB.push_back(make_float4(d.pivot_b[0], d.pivot_b[1], d.pivot_b[2], 0));
-      axisA.push_back(st3(axA));
-      axisB.push_back(st3(axB));
-      ni.push_back(make_float4(e == 0 ? 1.f : 0.f, e == 1 ? 1.f : 0.f, e == 2 ? 1.f : 0.f, 0.f));
+      pivotA.push_back(st3(pvA));
+      pivotB.push_back(st3(pvB));
+      axisA.push_back(st3(eqAxisA));
+      axisB.push_back(st3(eqAxisB));
+      ni.push_back(make_float4(axisIdx == 0 ? 1.f : 0.f, axisIdx == 1 ? 1.f : 0.f, axisIdx == 2 ? 1.f : 0.f, 0.f));
       a.push_back(sa); b.push_back(sbv); eps.push_back(se);
-      int en = 1;
-      double mf = d.max_force;
-      int kd = ROW_CONTACT;
-      double tv = 0;
-      if (e == 3 || e == 4) kd = ROW_ROT;
-      if (e == 5) {
-        kd = ROW_MOTOR;
-        en = d.motor_enabled != 0;
-        mf = d.motor_max_force > 0 ? d.motor_max_force : d.max_force;
-        tv = d.motor_target_velocity;
-      }
       kind.push_back(kd);
+      mode.push_back(md);
       enabled.push_back(en);
-      minF.push_back(-mf);
-      maxF.push_back(mf);
+      minF.push_back(lo);
+      maxF.push_back(hi);
+      cosv.push_back(cs_);
+      param.push_back(prm);
       targetVel.push_back(tv);
       if (en && !trig) { slotEq.push_back((int)rowSlot.size()); rowSlot.push_back(slot++); } else rowSlot.push_back(-1);
+    };
+    if (d.type == CANNON_CONSTRAINT_DISTANCE) {  // distance_constraint.dart:14-23
+      double dist = d.distance;
+      if (dist < 0) dist = vdist(xA, xB);
+      push(ROW_CONTACT, JM_DISTANCE, zero3, zero3, -1, -d.max_force, d.max_force, 0.0, dist, 1, 0.0);
+      continue;
+    }
+    if (d.type == CANNON_CONSTRAINT_LOCK) {
+      // lock_constraint.dart:29-33: pivots = the halfway point in both local frames (Body.pointToLocalFrame)
+      f3 halfWay = vadd(xA, xB);
+      halfWay = vscale(0.5, halfWay);
+      pvB = qrot(qconj(qB), vsub(halfWay, xB));
+      pvA = qrot(qconj(qA), vsub(halfWay, xA));
+    }
+    for (int e = 0; e < 3; e++) push(ROW_CONTACT, JM_P2P, zero3, zero3, e, -d.max_force, d.max_force, 0.0, 0.0, 1, 0.0);
+    if (d.type == CANNON_CONSTRAINT_HINGE) {
+      vnormalize(axA);  // hinge_constraint.dart:34-37
+      vnormalize(axB);
+      push(ROW_ROT, JM_HINGE_ROT, axA, axB, -1, -d.max_force, d.max_force, cosHalfPi, 0.0, 1, 0.0);
+      push(ROW_ROT, JM_HINGE_ROT, axA, axB, -1, -d.max_force, d.max_force, cosHalfPi, 0.0, 1, 0.0);
+      const double mf = d.motor_max_force > 0 ? d.motor_max_force : d.max_force;
+      push(ROW_MOTOR, JM_MOTOR, axA, axB, -1, -mf, mf, 0.0, 0.0, d.motor_enabled != 0, d.motor_target_velocity);
+    } else if (d.type == CANNON_CONSTRAINT_LOCK) {
+      // Body.vectorToLocalFrame conjugates the body's quaternion IN PLACE before rotating (rigid_body.dart:325-329 with
+      // vector_math's mutating Quaternion.conjugate), so after the pivot call the frame vectors see q, q*, q in turn
+      // (lock_constraint.dart:38-43); four calls per body leave the quaternion where it was.
+      f3 X, Y, Z;
+      X.x = 1.f; X.y = 0.f; X.z = 0.f; Y.x = 0.f; Y.y = 1.f; Y.z = 0.f; Z.x = 0.f; Z.y = 0.f; Z.z = 1.f;
+      const f3 lxA = qrot(qA, X), lxB = qrot(qB, X), lyA = qrot(qconj(qA), Y), lyB = qrot(qconj(qB), Y), lzA = qrot(qA, Z), lzB = qrot(qB, Z);
+      push(ROW_ROT, JM_DIRECT_ROT, lxA, lyB, -1, -d.max_force, d.max_force, cosHalfPi, 0.0, 1, 0.0);  // lock_constraint.dart:79-87
+      push(ROW_ROT, JM_DIRECT_ROT, lyA, lzB, -1, -d.max_force, d.max_force, cosHalfPi, 0.0, 1, 0.0);
+      push(ROW_ROT, JM_DIRECT_ROT, lzA, lxB, -1, -d.max_force, d.max_force, cosHalfPi, 0.0, 1, 0.0);
+    } else if (d.type == CANNON_CONSTRAINT_CONE_TWIST) {
+      // cone (cone_equation.dart:34-56 == RotationalEquation.computeB with cos(angle)) and twist; both are built with
+      // maxForce 0 and then get minForce = -maxForce (cone_twist_constraint.dart:47-71)
+      push(ROW_ROT, JM_DIRECT_ROT, axA, axB, -1, -d.max_force, 0.0, cos(d.angle), 0.0, 1, 0.0);
+      f3 t1, t2a, t2b;  // axisA.tangents(twist.axisA, twist.axisA): the second tangent survives (:88-94)
+      vtangents(axA, t1, t2a);
+      vtangents(axB, t1, t2b);
+      push(ROW_ROT, JM_DIRECT_ROT, t2a, t2b, -1, -d.max_force, 0.0, cos(d.twist_angle), 0.0, 1, 0.0);
     }
   }
   std::sort(keys.begin(), keys.end());
@@ -878,6 +922,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   W_TRY(w, upload(w->jAxisB, axisB, s)); W_TRY(w, upload(w->jNi, ni, s)); W_TRY(w, upload(w->jMinF, minF, s));
   W_TRY(w, upload(w->jMaxF, maxF, s)); W_TRY(w, upload(w->jA, a, s)); W_TRY(w, upload(w->jB, b, s)); W_TRY(w, upload(w->jEps, eps, s));
   W_TRY(w, upload(w->jTargetVel, targetVel, s)); W_TRY(w, upload(w->filterKeys, keys, s));
+  W_TRY(w, upload(w->jMode, mode, s)); W_TRY(w, upload(w->jCos, cosv, s)); W_TRY(w, upload(w->jParam, param, s));
   // Constraint ctor wakes both bodies (constraint_class.dart:26-29)
   if (!wake.empty()) {
     std::vector<int> sl(w->n);
@@ -1127,7 +1172,7 @@ static JointArrays joint_arrays(cannon_world* w) {
   J.pivotA = w->jPivotA.p; J.pivotB = w->jPivotB.p; J.axisA = w->jAxisA.p; J.axisB = w->jAxisB.p; J.ni = w->jNi.p;
   J.minF = w->jMinF.p; J.maxF = w->jMaxF.p; J.a = w->jA.p; J.b = w->jB.p; J.eps = w->jEps.p; J.targetVel = w->jTargetVel.p;
   J.first = w->jFirst.p; J.nAccepted = w->nJointAccepted;
-  J.cosMaxAngle = cos(M_PI / 2);  // RotationalEquation.maxAngle default, rotational_equation.dart:17
+  J.mode = w->jMode.p; J.cosv = w->jCos.p; J.param = w->jParam.p;
   return J;
 }
 

@@ -22,6 +22,8 @@
 #include "world.cuh"
 
 enum { ROW_CONTACT = 0, ROW_FRICTION = 1, ROW_ROT = 2, ROW_MOTOR = 3 };
+// Constraint.update() flavours of a joint equation
+enum { JM_P2P = 0, JM_HINGE_ROT = 1, JM_MOTOR = 2, JM_DISTANCE = 3, JM_DIRECT_ROT = 4 };
 enum { SRC_NORMAL = 0, SRC_FRIC1 = 1, SRC_FRIC2 = 2, SRC_JOINT = 3, SRC_TASK = 4 };
 
 // rows in execution order (SoA; float4 vectors so a row is five 128-bit + six 64-bit transactions)
@@ -81,7 +83,9 @@ struct JointArrays {  // one entry per constraint equation (P2P: 3, hinge: 6), u
   const double *minF, *maxF, *a, *b, *eps, *targetVel;
   const int *first;                                     // index of the constraint's first equation (for hinge tangents)
   int nAccepted;
-  double cosMaxAngle;  // cos(RotationalEquation.maxAngle = pi/2), evaluated on the host with libm
+  const int* mode;      // JM_*: how Constraint.update() fills the equation
+  const double* cosv;   // rotational rows: cos(maxAngle) / cos(ConeEquation.angle), evaluated on the host with libm
+  const double* param;  // distance rows: DistanceConstraint.distance
 };
 
 struct SolveParams {
@@ -456,23 +460,40 @@ __device__ __forceinline__ void build_friction_row(const RowArrays& R, int row, 
 }
 
 // Constraint.update() + joint equation rows (point_to_point_constraint.dart:68-83, hinge_constraint.dart:79-104,
-// rotational_equation.dart:34-58, rotational_motor_equation.dart:17-33)
+// distance_constraint.dart:27-38, lock_constraint.dart:70-88, cone_twist_constraint.dart:77-96, rotational_equation.dart:34-58,
+// cone_equation.dart:34-56, rotational_motor_equation.dart:17-33)
 __device__ inline void build_joint_row(const RowArrays& R, int row, const BodyArrays& B, const JointArrays& J, int e, const RowBody& A,
                                        const RowBody& Bd, double h) {
   const int bi = J.bodyA[e], bj = J.bodyB[e];
   const q4 qa = ldq(B.quat[bi]), qb = ldq(B.quat[bj]);
   const int kind = J.kind[e];
   f3 zero; zero.x = zero.y = zero.z = 0.f;
-  if (kind == ROW_CONTACT) {
+  const int mode = J.mode[e];
+  if (kind == ROW_CONTACT && mode == JM_DISTANCE) {
+    // DistanceConstraint.update (distance_constraint.dart:27-38)
+    const double halfDist = J.param[e] * 0.5;
+    f3 normal = vsub(Bd.pos, A.pos);
+    vnormalize(normal);
+    const f3 ri = vscale(halfDist, normal), rj = vscale(-halfDist, normal);
+    build_normal_row(R, row, A, Bd, ri, rj, normal, 0.0, J.a[e], J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
+  } else if (kind == ROW_CONTACT) {
     const f3 ri = qrot(qa, ld3(J.pivotA[e])), rj = qrot(qb, ld3(J.pivotB[e]));
     build_normal_row(R, row, A, Bd, ri, rj, ld3(J.ni[e]), 0.0, J.a[e], J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
   } else if (kind == ROW_ROT) {
-    const f3 worldAxisA = qrot(qa, ld3(J.axisA[e])), worldAxisB = qrot(qb, ld3(J.axisB[e]));
-    f3 t1, t2;
-    vtangents(worldAxisA, t1, t2);
-    const f3 axA = (e - J.first[e] == 3) ? t1 : t2;  // rotationalEquation1 / rotationalEquation2
+    f3 axA, worldAxisB;
+    if (mode == JM_DIRECT_ROT) {
+      // lock_constraint.dart:79-87 / cone_twist_constraint.dart:84-94: body-local axes of the equation into the world frame
+      axA = qrot(qa, ld3(J.axisA[e]));
+      worldAxisB = qrot(qb, ld3(J.axisB[e]));
+    } else {
+      const f3 worldAxisA = qrot(qa, ld3(J.axisA[e]));
+      worldAxisB = qrot(qb, ld3(J.axisB[e]));
+      f3 t1, t2;
+      vtangents(worldAxisA, t1, t2);
+      axA = (e - J.first[e] == 3) ? t1 : t2;  // rotationalEquation1 / rotationalEquation2
+    }
     const f3 nixnj = vcross(axA, worldAxisB), njxni = vcross(worldAxisB, axA);
-    const double g = J.cosMaxAngle - vdot(axA, worldAxisB);
+    const double g = J.cosv[e] - vdot(axA, worldAxisB);
     const double gw = (vdot(A.vel, zero) + vdot(A.angvel, njxni)) + (vdot(Bd.vel, zero) + vdot(Bd.angvel, nixnj));
     finish_row(R, row, ROW_ROT, A, Bd, zero, njxni, zero, nixnj, -g * J.a[e], gw, J.b[e], J.eps[e], J.minF[e], J.maxF[e], h);
   } else {

@@ -185,6 +185,7 @@ class DeviceWorld:
             d.collide_connected = 1
             d.axis_a[0] = 1.0
             d.axis_b[0] = 1.0
+            d.distance = -1.0  # DistanceConstraint: current distance unless given
             for k, v in c.items():
                 if k in ("pivot_a", "pivot_b", "axis_a", "axis_b"):
                     vv = np.asarray(v, dtype=np.float32)

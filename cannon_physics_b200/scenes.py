@@ -241,6 +241,65 @@ def chain_worlds(n_worlds=4096, chains=7, links=9, seed=4, iterations=10, solver
         bodies=b, n_bodies=n, constraints=cons, name=f"c4_chain_worlds_{n_worlds}x{per}")
 
 
+def constraint_zoo(seed=7, iterations=10, solver=F.SOLVER_REFERENCE_ORDER, groups=4) -> SceneSpec:
+    """every joint type of lib/constraints over a ground plane. Each group holds
+      * a DistanceConstraint pendulum (static anchor sphere + dynamic sphere; second pendulum with the default distance),
+      * two boxes under a LockConstraint (identity poses) and two more with rotated poses (Body.vectorToLocalFrame quirk),
+      * a ragdoll-like limb: static box + three boxes joined by ConeTwistConstraints (examples/lib/examples/ragdoll.dart:310-404),
+      * a PointToPoint + Hinge pair, so the old joints run next to the new ones.
+    """
+    per = 2 + 2 + 4 + 4 + 3
+    n = 1 + groups * per
+    rng = SplitMix64(seed)
+    b = _base_bodies(n)
+    b["quaternion"][0] = GROUND_QUAT
+    b["shape"][0] = 0
+    cons = []
+    hx = 0.25
+    for g in range(groups):
+        o = 1 + g * per
+        gx = (g - (groups - 1) / 2) * 6.0
+        jit = (rng.uniform(8) * 2 - 1) * 0.1
+        # distance pendulums
+        b["position"][o] = (gx, 5.0, 0); b["shape"][o] = 2; b["mass"][o] = 0.0
+        b["position"][o + 1] = (gx + 1.5 + jit[0], 4.0, jit[1]); b["shape"][o + 1] = 2; b["mass"][o + 1] = 1.0
+        cons.append(dict(type=F.CONSTRAINT_DISTANCE, body_a=o, body_b=o + 1, distance=1.5))
+        b["position"][o + 2] = (gx, 5.0, 2.0); b["shape"][o + 2] = 2; b["mass"][o + 2] = 0.0
+        b["position"][o + 3] = (gx + 1.0, 4.5 + jit[2], 2.0); b["shape"][o + 3] = 2; b["mass"][o + 3] = 0.7
+        cons.append(dict(type=F.CONSTRAINT_DISTANCE, body_a=o + 3, body_b=o + 2, max_force=5e4))  # default distance
+        # locks: axis-aligned pair, then a pair with rotated poses
+        b["position"][o + 4] = (gx - 1.0, 1.5, -2.0); b["shape"][o + 4] = 1; b["mass"][o + 4] = 1.0
+        b["position"][o + 5] = (gx - 0.4, 1.6, -2.0); b["shape"][o + 5] = 1; b["mass"][o + 5] = 2.0
+        cons.append(dict(type=F.CONSTRAINT_LOCK, body_a=o + 4, body_b=o + 5))
+        b["position"][o + 6] = (gx + 1.0, 1.5, -2.0); b["shape"][o + 6] = 1; b["mass"][o + 6] = 1.0
+        b["quaternion"][o + 6] = quat_from_euler(0.3 + jit[3], -0.2, 0.5)
+        b["position"][o + 7] = (gx + 1.6, 1.7, -2.1); b["shape"][o + 7] = 1; b["mass"][o + 7] = 1.0
+        b["quaternion"][o + 7] = quat_from_euler(-0.4, 0.6 + jit[4], 0.1)
+        cons.append(dict(type=F.CONSTRAINT_LOCK, body_a=o + 6, body_b=o + 7, max_force=1e5))
+        # cone-twist limb hanging from a static box
+        b["position"][o + 8] = (gx, 4.0, -4.0); b["shape"][o + 8] = 1; b["mass"][o + 8] = 0.0
+        for k in range(3):
+            idx = o + 9 + k
+            b["position"][idx] = (gx + 0.05 * k + jit[5] * k, 4.0 - 0.7 * (k + 1), -4.0)
+            b["shape"][idx] = 1
+            b["mass"][idx] = 0.8
+            cons.append(dict(type=F.CONSTRAINT_CONE_TWIST, body_a=idx - 1, body_b=idx, pivot_a=(0, -0.35, 0), pivot_b=(0, 0.35, 0),
+                             axis_a=(0, 1, 0), axis_b=(0, 1, 0), angle=math.pi / 4 if k < 2 else math.pi / 8, twist_angle=math.pi / 8,
+                             collide_connected=0 if k == 1 else 1))
+        b["velocity"][o + 11] = (1.5, 0, 0.8 + jit[6])  # kick the last limb so the cone limits come into play
+        # old joints
+        b["position"][o + 12] = (gx, 3.0, 4.0); b["shape"][o + 12] = 1; b["mass"][o + 12] = 0.0
+        b["position"][o + 13] = (gx, 2.3, 4.0); b["shape"][o + 13] = 1; b["mass"][o + 13] = 0.5
+        b["position"][o + 14] = (gx, 1.6, 4.0 + jit[7]); b["shape"][o + 14] = 1; b["mass"][o + 14] = 0.5
+        cons.append(dict(type=F.CONSTRAINT_POINT_TO_POINT, body_a=o + 13, body_b=o + 12, pivot_a=(0, 0.35, 0), pivot_b=(0, -0.35, 0)))
+        cons.append(dict(type=F.CONSTRAINT_HINGE, body_a=o + 14, body_b=o + 13, pivot_a=(0, 0.35, 0), pivot_b=(0, -0.35, 0),
+                         axis_a=(1, 0, 0), axis_b=(1, 0, 0)))
+    return SceneSpec(
+        desc=dict(gravity=(0, -10, 0), broadphase_kind=F.BP_NAIVE, solver_iterations=iterations, solver_kind=solver),
+        shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_BOX, half_extents=(hx, hx, hx)), dict(type=F.SHAPE_SPHERE, radius=0.2)],
+        bodies=b, n_bodies=n, constraints=cons, name=f"constraint_zoo_{groups}")
+
+
 def sphere_container(nx=160, nz=160, ny=40, n_spheres=None, seed=5, radius=0.25, pitch=0.6, extent=100.0,
                      iterations=10, solver=F.SOLVER_COLORED, allow_sleep=True, broadphase=F.BP_NAIVE) -> SceneSpec:
     """config 5: granular sphere pile in a 5-plane container (floor + 4 walls, container.dart:62-100), sleeping on."""

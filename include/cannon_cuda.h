@@ -70,7 +70,13 @@ enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
  *       (constraint equations first, then per contact: contact, friction 1, friction 2). */
 enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1, CANNON_SOLVER_SPLIT = 2 };
 /* Constraint kinds, lib/constraints/{point_to_point,hinge}_constraint.dart */
-enum { CANNON_CONSTRAINT_POINT_TO_POINT = 0, CANNON_CONSTRAINT_HINGE = 1 };
+enum {
+  CANNON_CONSTRAINT_POINT_TO_POINT = 0, /* lib/constraints/point_to_point_constraint.dart */
+  CANNON_CONSTRAINT_HINGE = 1,          /* hinge_constraint.dart */
+  CANNON_CONSTRAINT_DISTANCE = 2,       /* distance_constraint.dart */
+  CANNON_CONSTRAINT_LOCK = 3,           /* lock_constraint.dart */
+  CANNON_CONSTRAINT_CONE_TWIST = 4      /* cone_twist_constraint.dart */
+};
 
 typedef struct cannon_ctx   cannon_ctx;
 typedef struct cannon_world cannon_world;
@@ -173,17 +179,23 @@ typedef struct cannon_bodies_soa {
   float*   aabb;              /* 6n  lower xyz, upper xyz */
 } cannon_bodies_soa;
 
-/* Constraint, lib/constraints/point_to_point_constraint.dart:20, hinge_constraint.dart:10 */
+/* Constraint, lib/constraints/point_to_point_constraint.dart:20, hinge_constraint.dart:10, distance_constraint.dart:7,
+ * lock_constraint.dart:9, cone_twist_constraint.dart:11. Constructors that read body state (LockConstraint's pivots and
+ * frame vectors, DistanceConstraint's default distance) are evaluated by cannon_world_set_constraints on the bodies'
+ * state at that moment, like `new XConstraint(bodyA, bodyB)` would. */
 typedef struct cannon_constraint_desc {
   int32_t type;               /* CANNON_CONSTRAINT_* */
   int32_t body_a, body_b;
-  float   pivot_a[3], pivot_b[3];
-  float   axis_a[3], axis_b[3];   /* hinge only; normalised by the library like hinge_constraint.dart:34-37 */
+  float   pivot_a[3], pivot_b[3]; /* point-to-point, hinge, cone-twist (lock computes its own, distance has none) */
+  float   axis_a[3], axis_b[3];   /* hinge: normalised by the library like hinge_constraint.dart:34-37; cone-twist: used as given */
   double  max_force;              /* 1e6 */
   int32_t collide_connected;      /* Constraint.collideConnected */
   int32_t motor_enabled;          /* hinge: RotationalMotorEquation.enabled */
   double  motor_target_velocity;
   double  motor_max_force;
+  double  distance;               /* distance constraint: < 0 => bodyA.position.distanceTo(bodyB.position) at set time */
+  double  angle;                  /* cone-twist: ConeEquation.angle */
+  double  twist_angle;            /* cone-twist: maxAngle of the twist RotationalEquation */
 } cannon_constraint_desc;
 
 /* ContactEquation list produced by the narrowphase (lib/equations/contact_equation.dart). */

@@ -310,6 +310,32 @@ int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_c
     // Constraint ctor wakes both bodies up (constraint_class.dart:26-29)
     w.bodies[c.bodyA].sleepState = CANNON_AWAKE;
     w.bodies[c.bodyB].sleepState = CANNON_AWAKE;
+    auto rotEq = [&](double maxAngle, double minF, double maxF) {
+      Eq e;
+      e.kind = EQ_ROTATIONAL;
+      e.bi = c.bodyA;
+      e.bj = c.bodyB;
+      e.setSpookParams(1e7, 4, 1.0 / 60);
+      e.minForce = minF;
+      e.maxForce = maxF;
+      e.maxAngle = maxAngle;
+      return e;
+    };
+    Body& A = w.bodies[c.bodyA];
+    Body& B = w.bodies[c.bodyB];
+    if (d.type == CANNON_CONSTRAINT_DISTANCE) {  // distance_constraint.dart:14-23: one bidirectional ContactEquation
+      c.distance = d.distance >= 0 ? d.distance : distance_to(A.position, B.position);
+      Eq e;
+      e.kind = EQ_CONTACT;
+      e.bi = c.bodyA;
+      e.bj = c.bodyB;
+      e.setSpookParams(1e7, 4, 1.0 / 60);
+      e.minForce = -d.max_force;
+      e.maxForce = d.max_force;
+      c.eqs.push_back(e);
+      w.constraints.push_back(c);
+      continue;
+    }
     // PointToPointConstraint ctor, point_to_point_constraint.dart:30-66: three bidirectional
     // ContactEquations with the Equation-ctor SPOOK parameters (1e7, 4, 1/60; equation_class.dart:38)
     for (int k = 0; k < 3; k++) {
@@ -329,13 +355,7 @@ int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_c
       c.axisB = V3{d.axis_b[0], d.axis_b[1], d.axis_b[2]};
       normalize(c.axisB);
       for (int k = 0; k < 2; k++) {
-        Eq e;
-        e.kind = EQ_ROTATIONAL;
-        e.bi = c.bodyA;
-        e.bj = c.bodyB;
-        e.setSpookParams(1e7, 4, 1.0 / 60);
-        e.minForce = -d.max_force;
-        e.maxForce = d.max_force;
+        Eq e = rotEq(M_PI / 2, -d.max_force, d.max_force);
         e.axisA = c.axisA;
         e.axisB = c.axisB;
         c.eqs.push_back(e);
@@ -353,6 +373,45 @@ int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_c
       m.axisA = V3{0, 0, 0};
       m.axisB = V3{0, 0, 0};
       c.eqs.push_back(m);
+    } else if (d.type == CANNON_CONSTRAINT_LOCK) {  // lock_constraint.dart:22-66
+      // pivots: the halfway point in both local frames. Body.pointToLocalFrame / vectorToLocalFrame
+      // (rigid_body.dart:317-329) conjugate the body's quaternion IN PLACE (vector_math Quaternion.conjugate mutates),
+      // so successive calls alternate between q* and q: pivot (q*, correct), x (q), y (q*), z (q); after the four calls
+      // of the constructor the body's quaternion is back where it was.
+      V3 halfWay = add(A.position, B.position);
+      halfWay = scale(0.5, halfWay);
+      c.pivotB = qvmult(qconj(B.quaternion), sub(halfWay, B.position));
+      c.pivotA = qvmult(qconj(A.quaternion), sub(halfWay, A.position));
+      const V3 X{1, 0, 0}, Y{0, 1, 0}, Z{0, 0, 1};
+      const V3 xA = qvmult(A.quaternion, X), xB = qvmult(B.quaternion, X);
+      const V3 yA = qvmult(qconj(A.quaternion), Y), yB = qvmult(qconj(B.quaternion), Y);
+      const V3 zA = qvmult(A.quaternion, Z), zB = qvmult(B.quaternion, Z);
+      // update(): r1 (xA, yB), r2 (yA, zB), r3 (zA, xB), lock_constraint.dart:79-87
+      const V3 la[3] = {xA, yA, zA}, lb[3] = {yB, zB, xB};
+      c.locA.assign(c.eqs.size(), V3{0, 0, 0});
+      c.locB.assign(c.eqs.size(), V3{0, 0, 0});
+      for (int k = 0; k < 3; k++) {
+        c.eqs.push_back(rotEq(M_PI / 2, -d.max_force, d.max_force));
+        c.locA.push_back(la[k]);
+        c.locB.push_back(lb[k]);
+      }
+    } else if (d.type == CANNON_CONSTRAINT_CONE_TWIST) {  // cone_twist_constraint.dart:26-74
+      c.axisA = V3{d.axis_a[0], d.axis_a[1], d.axis_a[2]};
+      c.axisB = V3{d.axis_b[0], d.axis_b[1], d.axis_b[2]};
+      c.locA.assign(c.eqs.size(), V3{0, 0, 0});
+      c.locB.assign(c.eqs.size(), V3{0, 0, 0});
+      // ConeEquation(maxForce: 0) then minForce = -maxForce: pushes toward the cone axis only; same for the twist
+      c.eqs.push_back(rotEq(d.angle, -d.max_force, 0.0));  // ConeEquation.computeB == RotationalEquation.computeB with cos(angle)
+      c.locA.push_back(c.axisA);
+      c.locB.push_back(c.axisB);
+      // update(): axisA.tangents(twist.axisA, twist.axisA) leaves the SECOND tangent in twist.axisA (both outputs are
+      // the same object, cross2 reads its argument before writing), then vectorToWorldFrame (:88-94)
+      V3 t1, t2a, t2b;
+      tangents(c.axisA, t1, t2a);
+      tangents(c.axisB, t1, t2b);
+      c.eqs.push_back(rotEq(d.twist_angle, -d.max_force, 0.0));
+      c.locA.push_back(t2a);
+      c.locB.push_back(t2b);
     } else if (d.type != CANNON_CONSTRAINT_POINT_TO_POINT) {
       return fail(cw->ctx, CANNON_E_UNSUPPORTED, "constraint type outside the hot-path scope");
     }

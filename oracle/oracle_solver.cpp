@@ -205,6 +205,16 @@ int World::solve(double h) {
   for (Constraint& c : constraints) {
     const Body& A = bodies[c.bodyA];
     const Body& B = bodies[c.bodyB];
+    if (c.type == CANNON_CONSTRAINT_DISTANCE) {  // DistanceConstraint.update, distance_constraint.dart:27-38
+      Eq& e = c.eqs[0];
+      const double halfDist = c.distance * 0.5;
+      V3 normal = sub(B.position, A.position);
+      normalize(normal);
+      e.ni = normal;
+      e.ri = scale(halfDist, normal);
+      e.rj = scale(-halfDist, normal);
+      continue;
+    }
     // PointToPointConstraint.update, point_to_point_constraint.dart:68-83
     V3 ri = qvmult(A.quaternion, c.pivotA);
     V3 rj = qvmult(B.quaternion, c.pivotB);
@@ -221,6 +231,12 @@ int World::solve(double h) {
       if (c.eqs[5].enabled) {
         c.eqs[5].axisA = qvmult(A.quaternion, c.axisA);
         c.eqs[5].axisB = qvmult(B.quaternion, c.axisB);
+      }
+    } else if (c.type == CANNON_CONSTRAINT_LOCK || c.type == CANNON_CONSTRAINT_CONE_TWIST) {
+      // lock_constraint.dart:79-87 / cone_twist_constraint.dart:84-94: body-local axes into the world frame
+      for (size_t k = 3; k < c.eqs.size(); k++) {
+        c.eqs[k].axisA = qvmult(A.quaternion, c.locA[k]);
+        c.eqs[k].axisB = qvmult(B.quaternion, c.locB[k]);
       }
     }
   }

@@ -97,7 +97,10 @@ struct Constraint {
   int type = 0, bodyA = -1, bodyB = -1;
   V3 pivotA{0, 0, 0}, pivotB{0, 0, 0}, axisA{1, 0, 0}, axisB{1, 0, 0};
   bool collideConnected = true;
-  std::vector<Eq> eqs;  // P2P: x,y,z ; hinge: x,y,z,rot1,rot2,motor
+  double distance = 0;  // DistanceConstraint.distance
+  // P2P: x,y,z ; hinge: x,y,z,rot1,rot2,motor ; distance: d ; lock: x,y,z,r1,r2,r3 ; cone-twist: x,y,z,cone,twist
+  std::vector<Eq> eqs;
+  std::vector<V3> locA, locB;  // body-local axes of the rotational equations that are re-oriented in update() (lock, cone-twist)
 };
 
 struct RowDebug {

@@ -23,6 +23,7 @@ CASES = {
     "c3_hf_small": (lambda: scenes.mixed_pile_on_heightfield(4, 4, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 90),
     "c4_small": (lambda: scenes.chain_worlds(3, chains=2, links=4), 60),
     "c5_small": (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 120),
+    "joints_small": (lambda: scenes.constraint_zoo(groups=2), 120),
 }
 
 

@@ -112,7 +112,82 @@ def test_split_solver_islands_and_agreement_with_gssolver(oracle_lib):
     assert w.profile()["n_islands"] == 8 and w.profile()["n_rows"] == 0
 
 
-GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small"]
+def test_distance_constraint_row_matches_closed_form_and_holds(oracle_lib):
+    # distance_constraint.dart:27-38 + contact_equation.dart:34-77 with the Equation-ctor SPOOK parameters (1e7, 4, 1/60)
+    spec = scenes.spheres_on_plane(1, 1, 2, y0=5.0)  # plane + 2 spheres
+    spec.desc["gravity"] = (0, 0, 0)
+    spec.bodies["position"][1] = (0, 5, 0)
+    spec.bodies["position"][2] = (2, 5, 0)
+    spec.constraints = [dict(type=F.CONSTRAINT_DISTANCE, body_a=1, body_b=2, distance=1.0)]
+    w = engine.DeviceWorld(oracle_lib, spec)
+    w.step(1 / 60, 1)
+    rows = w.get_rows()
+    h, k, d = 1 / 60, 1e7, 4.0
+    a, eps = 4.0 / (h * (1 + 4 * d)), 4.0 / (h * h * k * (1 + 4 * d))
+    assert len(rows["B"]) == 1
+    assert rows["B"][0] == pytest.approx(-1.0 * a, rel=1e-12)  # g = n.(xj + rj - xi - ri) = 2 - 0.5 - 0.5
+    assert rows["invC"][0] == pytest.approx(1.0 / (1.0 + 1.0 + eps), rel=1e-12)
+    w.step(1 / 60, 120)
+    p = w.get_bodies(("position",))["position"]
+    assert abs(np.linalg.norm(p[2] - p[1]) - 1.0) < 2e-3  # pulled to the target distance
+    assert np.allclose(p[1] + p[2], (2, 10, 0), atol=1e-4)  # equal masses: the midpoint does not move
+
+
+def test_lock_and_cone_twist_constraints_behave(oracle_lib):
+    w = engine.DeviceWorld(oracle_lib, scenes.constraint_zoo(groups=2))
+    p0 = w.get_bodies(("position",))["position"].copy()
+    w.step(1 / 60, 25)  # before anything reaches the ground
+    s = w.get_bodies(("position", "quaternion", "velocity"))
+    per = 15
+    for g in range(2):
+        o = 1 + g * per
+        # distance pendulums keep their length (given / default = initial distance)
+        assert abs(np.linalg.norm(s["position"][o + 1] - s["position"][o]) - 1.5) < 2e-2  # soft (SPOOK) constraint under a swinging load
+        d0 = np.linalg.norm(p0[o + 3] - p0[o + 2])
+        assert abs(np.linalg.norm(s["position"][o + 3] - s["position"][o + 2]) - d0) < 2e-2
+        # the axis-aligned locked pair falls as one rigid piece: relative position and orientation unchanged
+        assert np.allclose(s["position"][o + 5] - s["position"][o + 4], p0[o + 5] - p0[o + 4], atol=2e-3)
+        assert np.allclose(s["quaternion"][o + 4], (0, 0, 0, 1), atol=2e-3) and np.allclose(s["quaternion"][o + 5], (0, 0, 0, 1), atol=2e-3)
+        # the limb hangs from its static root: pivots stay together
+        for k in range(3):
+            a, b = o + 8 + k, o + 9 + k
+            assert np.linalg.norm(s["position"][a] - s["position"][b]) < 0.8
+    assert np.all(np.isfinite(s["position"])) and np.abs(s["velocity"]).max() < 10
+
+
+def test_cone_equation_limits_the_swing(oracle_lib):
+    # one box hanging from a static box by a ConeTwistConstraint (axis y both), pushed sideways: the angle between the
+    # two world axes stays near the cone angle while an identical PointToPoint joint lets it swing far beyond
+    def run(kind, angle):
+        spec = scenes.spheres_on_plane(1, 1, 1)
+        b = spec.bodies
+        spec.shapes = [dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_BOX, half_extents=(0.2, 0.2, 0.2))]
+        from cannon_physics_b200.scenes import _base_bodies, GROUND_QUAT
+        nb = _base_bodies(3)
+        nb["quaternion"][0] = GROUND_QUAT
+        nb["shape"][0] = 0
+        nb["position"][1] = (0, 6, 0); nb["shape"][1] = 1; nb["mass"][1] = 0.0
+        nb["position"][2] = (0, 5, 0); nb["shape"][2] = 1; nb["mass"][2] = 1.0
+        nb["velocity"][2] = (6, 0, 0)
+        spec.bodies, spec.n_bodies = nb, 3
+        spec.constraints = [dict(type=kind, body_a=1, body_b=2, pivot_a=(0, -0.5, 0), pivot_b=(0, 0.5, 0), axis_a=(0, 1, 0), axis_b=(0, 1, 0),
+                                 angle=angle, twist_angle=0.3)]
+        w = engine.DeviceWorld(oracle_lib, spec)
+        worst = 0.0
+        for _ in range(90):
+            w.step(1 / 60, 1)
+            q = w.get_bodies(("quaternion",))["quaternion"][2].astype(np.float64)
+            # world y axis of the hanging body
+            x, y, z, ww = q
+            yb = np.array([2 * (x * y - ww * z), 1 - 2 * (x * x + z * z), 2 * (y * z + ww * x)])
+            worst = max(worst, float(np.degrees(np.arccos(np.clip(yb[1], -1, 1)))))
+        return worst
+    free = run(F.CONSTRAINT_POINT_TO_POINT, 0.0)
+    cone = run(F.CONSTRAINT_CONE_TWIST, np.radians(20))
+    assert free > 60 and cone < 35, (free, cone)
+
+
+GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

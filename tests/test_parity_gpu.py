@@ -30,6 +30,7 @@ STAGED = {
     "c3 mixed pile on heightfield, Grid": (lambda: scenes.mixed_pile_on_heightfield(4, 4, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 90),
     "c4 jointed chain worlds (batch)": (lambda: scenes.chain_worlds(3, chains=2, links=5), 80),
     "c5 container with sleeping": (lambda: scenes.sphere_container(5, 5, 3, extent=4.0, solver=REF), 150),
+    "8f joints: distance, lock, cone-twist": (lambda: scenes.constraint_zoo(groups=2), 150),
 }
 
 
@@ -38,6 +39,7 @@ SPLIT = {
     "split: box stacks SAP": (lambda: _with(scenes.box_stacks(6, 4, grid=3), solver_kind=F.SOLVER_SPLIT), 60),
     "split: jointed chains": (lambda: _with(scenes.chain_worlds(1, chains=3, links=5), solver_kind=F.SOLVER_SPLIT), 80),
     "split: sleeping container": (lambda: _with(scenes.sphere_container(5, 5, 3, extent=4.0, solver=REF), solver_kind=F.SOLVER_SPLIT), 150),
+    "split: distance, lock, cone-twist": (lambda: _with(scenes.constraint_zoo(groups=2), solver_kind=F.SOLVER_SPLIT), 100),
 }
 
 
@@ -73,6 +75,7 @@ FUSED = {
     "c3 heightfield": (lambda: scenes.mixed_pile_on_heightfield(6, 6, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 120, 20),
     "c4 batch": (lambda: scenes.chain_worlds(8, chains=3, links=6), 120, 20),
     "c5 sleeping": (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 240, 40),
+    "8f joints": (lambda: scenes.constraint_zoo(groups=3), 240, 30),
 }
 
 
