@@ -246,9 +246,12 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (gs_ms / 1000.0) / 1e9 if gs_ms > 0 else 0.0
     from cannon_physics_b200 import _ffi as _F
-    gs_kernel = "k_gs_fast" if spec.desc.get("solver_kind") == _F.SOLVER_COLORED else "k_gs"
+    colored = spec.desc.get("solver_kind") == _F.SOLVER_COLORED
+    gs_kernel = ("k_gs_world" if spec.desc.get("n_worlds", 1) > 1 else "k_gs_fast") if colored else "k_gs"
+    # the ncu DRAM figure in profiles/ncu_traffic.json was captured for k_gs_fast on the default workload only
     roofline = {"bound": "hbm", "kernel": gs_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "traffic": ncu_traffic() if (gs_kernel == "k_gs_fast" and args.config == "c3" and args.scale == 1.0) else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": gs_ms,
                 "share_of_step": gs_ms / (total_ms / K) if total_ms > 0 else None}
 
