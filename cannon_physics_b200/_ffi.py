@@ -93,6 +93,13 @@ class ConstraintDesc(C.Structure):
     ]
 
 
+class SpringDesc(C.Structure):
+    _fields_ = [
+        ("body_a", c_i32), ("body_b", c_i32), ("rest_length", c_f64), ("stiffness", c_f64), ("damping", c_f64),
+        ("local_anchor_a", c_f32 * 3), ("local_anchor_b", c_f32 * 3),
+    ]
+
+
 class ContactsSoA(C.Structure):
     _fields_ = [
         ("capacity", c_i32), ("body_i", P(c_i32)), ("body_j", P(c_i32)),
@@ -129,6 +136,7 @@ PROTOTYPES = {
     "cannon_world_set_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_get_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_set_constraints": (c_i32, [VP, c_i32, P(ConstraintDesc)]),
+    "cannon_world_set_springs": (c_i32, [VP, c_i32, P(SpringDesc)]),
     "cannon_world_set_time": (c_i32, [VP, c_f64]),
     "cannon_world_get_time": (c_i32, [VP, P(c_f64), P(c_i64)]),
     "cannon_world_set_dt": (c_i32, [VP, c_f64]),

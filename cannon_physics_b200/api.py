@@ -28,7 +28,7 @@ from .engine import Context, DeviceWorld, SceneSpec
 __all__ = [
     "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
-    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint",
+    "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
     "World",
     "CudaWorld", "CannonError",
 ]
@@ -388,6 +388,21 @@ class ConeTwistConstraint(PointToPointConstraint):  # cone_twist_constraint.dart
         return dict(super()._desc(idx), axis_a=self.axisA, axis_b=self.axisB, angle=float(self.angle), twist_angle=float(self.twistAngle))
 
 
+class Spring:  # lib/objects/spring.dart:17
+    """`world.addSpring(spring)` stands for the reference idiom `world.addEventListener('postStep', (e) => spring.applyForce())`
+    (examples/lib/examples/spring.dart:90): the device applies the spring in the postStep slot of every step."""
+
+    def __init__(self, bodyA, bodyB, restLength: float = 1.0, stiffness: float = 100.0, damping: float = 1.0, localAnchorA=None, localAnchorB=None):
+        self.bodyA, self.bodyB = bodyA, bodyB
+        self.restLength, self.stiffness, self.damping = restLength, stiffness, damping
+        self.localAnchorA = Vec3() if localAnchorA is None else np.array(localAnchorA, dtype=np.float32)
+        self.localAnchorB = Vec3() if localAnchorB is None else np.array(localAnchorB, dtype=np.float32)
+
+    def _desc(self, idx):
+        return dict(body_a=idx[id(self.bodyA)], body_b=idx[id(self.bodyB)], rest_length=float(self.restLength), stiffness=float(self.stiffness),
+                    damping=float(self.damping), local_anchor_a=self.localAnchorA, local_anchor_b=self.localAnchorB)
+
+
 class World:  # lib/world/world_class.dart:44
     def __init__(self, gravity=None, frictionGravity=None, allowSleep: bool = False, broadphase: Optional[Broadphase] = None,
                  solver: Optional[Solver] = None, quatNormalizeFast: bool = False, quatNormalizeSkip: int = 0, device: int = 0, _lib=None):
@@ -399,6 +414,7 @@ class World:  # lib/world/world_class.dart:44
         self.quatNormalizeFast, self.quatNormalizeSkip = quatNormalizeFast, quatNormalizeSkip
         self.bodies: List[Body] = []
         self.constraints: List[Constraint] = []
+        self.springs: List[Spring] = []
         self.contactmaterials: List[ContactMaterial] = []
         self.defaultMaterial = Material(name="default")
         self.defaultContactMaterial = ContactMaterial(self.defaultMaterial, self.defaultMaterial, friction=0.3, restitution=0.0)
@@ -423,6 +439,10 @@ class World:  # lib/world/world_class.dart:44
 
     def addConstraint(self, c: Constraint):
         self.constraints.append(c)
+        self._structure_dirty = True
+
+    def addSpring(self, spring: Spring):
+        self.springs.append(spring)
         self._structure_dirty = True
 
     def addContactMaterial(self, cmat: ContactMaterial):
@@ -496,7 +516,7 @@ class World:  # lib/world/world_class.dart:44
         return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n,
                          material_friction=np.array([m.friction for m in mats], dtype=np.float64) if mats else None,
                          material_restitution=np.array([m.restitution for m in mats], dtype=np.float64) if mats else None,
-                         contact_materials=cms, constraints=cons, name="api_world")
+                         contact_materials=cms, constraints=cons, springs=[sp._desc(idx) for sp in self.springs], name="api_world")
 
     def _ensure_uploaded(self):
         if self._structure_dirty or self._dev is None:

@@ -197,6 +197,11 @@ struct cannon_world {
   DBuf<unsigned long long> claim;
   DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters, islandLabel;
   DBuf<double> worldTot;
+  // springs (cannon_world_set_springs)
+  int nSprings = 0;
+  DBuf<int> spBodyA, spBodyB, spOff, spIdx;
+  DBuf<double> spRest, spK, spD;
+  DBuf<float4> spAnchorA, spAnchorB;
   DBuf<long long> dClock;  // [0] bits of World.time, [1] World.stepnumber
   long long hClock[2] = {0, 0};
   DBuf<long long> gsTrace;
@@ -410,7 +415,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
-  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
+  REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(spBodyA); REL(spBodyB); REL(spOff); REL(spIdx); REL(spRest); REL(spK); REL(spD); REL(spAnchorA); REL(spAnchorB); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
   w->scanTmp.tiles.release();
   w->sortTmp.k2.release(); w->sortTmp.v2.release(); w->sortTmp.hist.release(); w->sortTmp.scan.tiles.release();
 #undef REL
@@ -934,6 +939,38 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   return ensure_capacities(w);
 }
 
+int32_t cannon_world_set_springs(cannon_world* w, int32_t n, const cannon_spring_desc* sp) {
+  if (w) drop_step_graph(w);
+  if (!w || n < 0 || (n > 0 && !sp)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  std::vector<int> a(n), b(n), off(w->n + 1, 0), idx;
+  std::vector<double> rest(n), k(n), d(n);
+  std::vector<float4> aa(n), ab(n);
+  for (int i = 0; i < n; i++) {
+    if (sp[i].body_a < 0 || sp[i].body_b < 0 || sp[i].body_a >= w->n || sp[i].body_b >= w->n) return fail(w->ctx, CANNON_E_INVALID, "spring references unknown body");
+    a[i] = sp[i].body_a; b[i] = sp[i].body_b;
+    rest[i] = sp[i].rest_length; k[i] = sp[i].stiffness; d[i] = sp[i].damping;
+    aa[i] = make_float4(sp[i].local_anchor_a[0], sp[i].local_anchor_a[1], sp[i].local_anchor_a[2], 0.f);
+    ab[i] = make_float4(sp[i].local_anchor_b[0], sp[i].local_anchor_b[1], sp[i].local_anchor_b[2], 0.f);
+    off[a[i] + 1]++;
+    if (b[i] != a[i]) off[b[i] + 1]++;
+  }
+  for (int i = 0; i < w->n; i++) off[i + 1] += off[i];
+  idx.resize(off[w->n]);
+  std::vector<int> cur(off.begin(), off.end() - 1);
+  for (int i = 0; i < n; i++) {  // ascending spring index per body
+    idx[cur[a[i]]++] = i;
+    if (b[i] != a[i]) idx[cur[b[i]]++] = i;
+  }
+  w->nSprings = n;
+  W_TRY(w, upload(w->spBodyA, a, s)); W_TRY(w, upload(w->spBodyB, b, s)); W_TRY(w, upload(w->spOff, off, s)); W_TRY(w, upload(w->spIdx, idx, s));
+  W_TRY(w, upload(w->spRest, rest, s)); W_TRY(w, upload(w->spK, k, s)); W_TRY(w, upload(w->spD, d, s));
+  W_TRY(w, upload(w->spAnchorA, aa, s)); W_TRY(w, upload(w->spAnchorB, ab, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_time(cannon_world* w, double t) { if (!w) return CANNON_E_INVALID; w->time = t; return CANNON_OK; }
 int32_t cannon_world_get_time(cannon_world* w, double* t, int64_t* stepnumber) {
   if (!w) return CANNON_E_INVALID;
@@ -1319,6 +1356,13 @@ static int32_t refresh_damping(cannon_world* w, double dt) {
 static int32_t st_integrate(cannon_world* w, double dt, int applyLambda) {
   StepParams P = step_params(w, dt);
   { g_kernel_launches++; k_integrate<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), P, w->worldRows.p, applyLambda); }
+  if (w->nSprings > 0) {  // the postStep slot (world_class.dart:685): forces for the next step
+    SpringArrays S;
+    S.n = w->nSprings; S.bodyA = w->spBodyA.p; S.bodyB = w->spBodyB.p; S.rest = w->spRest.p; S.stiffness = w->spK.p; S.damping = w->spD.p;
+    S.anchorA = w->spAnchorA.p; S.anchorB = w->spAnchorB.p; S.off = w->spOff.p; S.idx = w->spIdx.p;
+    g_kernel_launches++;
+    k_springs<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), S, w->n);
+  }
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }

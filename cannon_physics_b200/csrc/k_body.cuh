@@ -214,3 +214,43 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, c
     }
   }
 }
+
+// Spring.applyForce (lib/objects/spring.dart:108-157) in the postStep slot of the step. The reference walks the springs
+// in listener order and every body's force / torque is a float accumulated in that order; here one thread owns a body
+// and walks THAT body's springs in the same order (CSR built at cannon_world_set_springs), recomputing the spring force
+// from the (unchanged) poses and velocities, so every accumulator sees the reference's sequence of float additions.
+struct SpringArrays {
+  int n;
+  const int *bodyA, *bodyB;
+  const double *rest, *stiffness, *damping;
+  const float4 *anchorA, *anchorB;
+  const int *off, *idx;  // body -> springs touching it, ascending
+};
+
+__global__ void __launch_bounds__(256) k_springs(BodyArrays B, SpringArrays S, int nBodies) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBodies; b += gridDim.x * blockDim.x) {
+    const int s0 = S.off[b], s1 = S.off[b + 1];
+    if (s0 == s1) continue;
+    f3 force = ld3(B.force[b]), torque = ld3(B.torque[b]);
+    for (int k = s0; k < s1; k++) {
+      const int sp = S.idx[k];
+      const int a = S.bodyA[sp], c = S.bodyB[sp];
+      const f3 xa = ld3(B.pos[a]), xc = ld3(B.pos[c]);
+      const f3 worldAnchorA = to_world_point(xa, ldq(B.quat[a]), ld3(S.anchorA[sp]));  // pointToWorldFrame, rigid_body.dart:332-337
+      const f3 worldAnchorB = to_world_point(xc, ldq(B.quat[c]), ld3(S.anchorB[sp]));
+      const f3 ri = vsub(worldAnchorA, xa), rj = vsub(worldAnchorB, xc);
+      const f3 r = vsub(worldAnchorB, worldAnchorA);
+      const double rlen = vlen(r);
+      f3 rUnit = r;
+      vnormalize(rUnit);
+      f3 u = vsub(ld3(B.vel[c]), ld3(B.vel[a]));
+      u = vadd(u, vcross(ld3(B.angvel[c]), rj));
+      u = vsub(u, vcross(ld3(B.angvel[a]), ri));
+      const f3 f = vscale(-S.stiffness[sp] * (rlen - S.rest[sp]) - S.damping[sp] * vdot(u, rUnit), rUnit);
+      if (a == b) { force = vsub(force, f); torque = vsub(torque, vcross(ri, f)); }
+      if (c == b) { force = vadd(force, f); torque = vadd(torque, vcross(rj, f)); }
+    }
+    B.force[b] = st3(force);
+    B.torque[b] = st3(torque);
+  }
+}

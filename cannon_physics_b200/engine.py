@@ -26,6 +26,7 @@ class SceneSpec:
     material_restitution: Optional[np.ndarray] = None
     contact_materials: List[Dict] = field(default_factory=list)
     constraints: List[Dict] = field(default_factory=list)
+    springs: List[Dict] = field(default_factory=list)
     name: str = ""
 
 
@@ -92,6 +93,8 @@ class DeviceWorld:
         self.set_bodies(spec.bodies, spec.n_bodies)
         if spec.constraints:
             self.set_constraints(spec.constraints)
+        if spec.springs:
+            self.set_springs(spec.springs)
 
     def _chk(self, code):
         _check(self.lib, self.ctx.handle, code)
@@ -195,6 +198,22 @@ class DeviceWorld:
                 else:
                     setattr(d, k, v)
         self._chk(self.lib.cannon_world_set_constraints(self.handle, len(cons), arr))
+
+    def set_springs(self, springs: Sequence[Dict]):
+        """Spring.applyForce for these springs in every step's postStep slot (lib/objects/spring.dart)."""
+        arr = (F.SpringDesc * max(1, len(springs)))()
+        for i, sp in enumerate(springs):
+            d = arr[i]
+            d.rest_length, d.stiffness, d.damping = 1.0, 100.0, 1.0
+            for k, v in sp.items():
+                if k in ("local_anchor_a", "local_anchor_b"):
+                    vv = np.asarray(v, dtype=np.float32)
+                    a = getattr(d, k)
+                    for j in range(3):
+                        a[j] = float(vv[j])
+                else:
+                    setattr(d, k, v)
+        self._chk(self.lib.cannon_world_set_springs(self.handle, len(springs), arr))
 
     def update_bodies(self, first: int, count: int, **arrays):
         args = []

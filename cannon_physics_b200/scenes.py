@@ -246,7 +246,8 @@ def constraint_zoo(seed=7, iterations=10, solver=F.SOLVER_REFERENCE_ORDER, group
       * a DistanceConstraint pendulum (static anchor sphere + dynamic sphere; second pendulum with the default distance),
       * two boxes under a LockConstraint (identity poses) and two more with rotated poses (Body.vectorToLocalFrame quirk),
       * a ragdoll-like limb: static box + three boxes joined by ConeTwistConstraints (examples/lib/examples/ragdoll.dart:310-404),
-      * a PointToPoint + Hinge pair, so the old joints run next to the new ones.
+      * a PointToPoint + Hinge pair, so the old joints run next to the new ones,
+      * three Springs applied in the postStep slot (lib/objects/spring.dart).
     """
     per = 2 + 2 + 4 + 4 + 3
     n = 1 + groups * per
@@ -255,6 +256,7 @@ def constraint_zoo(seed=7, iterations=10, solver=F.SOLVER_REFERENCE_ORDER, group
     b["quaternion"][0] = GROUND_QUAT
     b["shape"][0] = 0
     cons = []
+    springs = []
     hx = 0.25
     for g in range(groups):
         o = 1 + g * per
@@ -294,10 +296,16 @@ def constraint_zoo(seed=7, iterations=10, solver=F.SOLVER_REFERENCE_ORDER, group
         cons.append(dict(type=F.CONSTRAINT_POINT_TO_POINT, body_a=o + 13, body_b=o + 12, pivot_a=(0, 0.35, 0), pivot_b=(0, -0.35, 0)))
         cons.append(dict(type=F.CONSTRAINT_HINGE, body_a=o + 14, body_b=o + 13, pivot_a=(0, 0.35, 0), pivot_b=(0, -0.35, 0),
                          axis_a=(1, 0, 0), axis_b=(1, 0, 0)))
+        # springs (lib/objects/spring.dart, examples/lib/examples/spring.dart): the p2p link is also tied to its anchor by an
+        # off-centre spring, the two locked pairs are tied together, and one body carries two springs (accumulation order)
+        springs.append(dict(body_a=o + 12, body_b=o + 14, rest_length=1.0, stiffness=50.0, damping=1.0, local_anchor_a=(0.25, 0, 0),
+                            local_anchor_b=(-0.25, 0.25, 0)))
+        springs.append(dict(body_a=o + 5, body_b=o + 6, rest_length=1.2, stiffness=80.0, damping=2.0, local_anchor_b=(0, 0.25, 0)))
+        springs.append(dict(body_a=o + 11, body_b=o + 6, rest_length=2.0, stiffness=20.0, damping=0.5))
     return SceneSpec(
         desc=dict(gravity=(0, -10, 0), broadphase_kind=F.BP_NAIVE, solver_iterations=iterations, solver_kind=solver),
         shapes=[dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_BOX, half_extents=(hx, hx, hx)), dict(type=F.SHAPE_SPHERE, radius=0.2)],
-        bodies=b, n_bodies=n, constraints=cons, name=f"constraint_zoo_{groups}")
+        bodies=b, n_bodies=n, constraints=cons, springs=springs, name=f"constraint_zoo_{groups}")
 
 
 def sphere_container(nx=160, nz=160, ny=40, n_spheres=None, seed=5, radius=0.25, pitch=0.6, extent=100.0,

@@ -198,6 +198,18 @@ typedef struct cannon_constraint_desc {
   double  twist_angle;            /* cone-twist: maxAngle of the twist RotationalEquation */
 } cannon_constraint_desc;
 
+/* Spring, lib/objects/spring.dart:17. The reference applies springs from user code, canonically
+ *   world.addEventListener('postStep', (e) { for (final s in springs) s.applyForce(); })
+ * (examples/lib/examples/spring.dart:90,123); the library runs exactly that in the postStep slot of every step
+ * (world_class.dart:685, after clearForces), in array order, so the forces act in the next step's integration. */
+typedef struct cannon_spring_desc {
+  int32_t body_a, body_b;
+  double  rest_length;            /* 1 */
+  double  stiffness;              /* 100 */
+  double  damping;                /* 1 */
+  float   local_anchor_a[3], local_anchor_b[3];
+} cannon_spring_desc;
+
 /* ContactEquation list produced by the narrowphase (lib/equations/contact_equation.dart). */
 typedef struct cannon_contacts_soa {
   int32_t  capacity;          /* number of contacts the arrays can hold */
@@ -253,6 +265,8 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* bodies
 int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* out);
 /* World.addConstraint for all constraints at once. */
 int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs);
+/* Springs applied in every step's postStep slot (see cannon_spring_desc); n = 0 removes them. */
+int32_t cannon_world_set_springs(cannon_world* w, int32_t n, const cannon_spring_desc* springs);
 /* World.time (used by Body.sleepTick, world_class.dart:693) */
 int32_t cannon_world_set_time(cannon_world* w, double time);
 int32_t cannon_world_get_time(cannon_world* w, double* time, int64_t* stepnumber);

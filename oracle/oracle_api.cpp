@@ -420,6 +420,26 @@ int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_c
   return CANNON_OK;
 }
 
+int32_t cannon_world_set_springs(cannon_world* cw, int32_t n, const cannon_spring_desc* sp) {
+  if (!cw || n < 0 || (n > 0 && !sp)) return CANNON_E_INVALID;
+  World& w = cw->w;
+  const int nb = (int)w.bodies.size();
+  w.springs.clear();
+  for (int i = 0; i < n; i++) {
+    if (sp[i].body_a < 0 || sp[i].body_b < 0 || sp[i].body_a >= nb || sp[i].body_b >= nb) return fail(cw->ctx, CANNON_E_INVALID, "spring references unknown body");
+    Spring s;
+    s.bodyA = sp[i].body_a;
+    s.bodyB = sp[i].body_b;
+    s.restLength = sp[i].rest_length;
+    s.stiffness = sp[i].stiffness;
+    s.damping = sp[i].damping;
+    s.localAnchorA = V3{sp[i].local_anchor_a[0], sp[i].local_anchor_a[1], sp[i].local_anchor_a[2]};
+    s.localAnchorB = V3{sp[i].local_anchor_b[0], sp[i].local_anchor_b[1], sp[i].local_anchor_b[2]};
+    w.springs.push_back(s);
+  }
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_time(cannon_world* cw, double t) {
   if (!cw) return CANNON_E_INVALID;
   cw->w.time = t;

@@ -406,6 +406,7 @@ void World::integrateAll(double h) {
     b.torque = V3{0, 0, 0};
   }
   stepnumber += 1;
+  applySprings();  // the postStep event, world_class.dart:685
   // sleepTick, world_class.dart:688-700 + rigid_body.dart:282-300 (sees `time` before this step's increment)
   if (desc.allow_sleep) {
     for (Body& b : bodies) {
@@ -425,6 +426,33 @@ void World::integrateAll(double h) {
         b.wakeUpAfterNarrowphase = false;
       }
     }
+  }
+}
+
+// Spring.applyForce, lib/objects/spring.dart:108-157, for every spring in order (every Vector3 store rounds to float)
+void World::applySprings() {
+  for (const Spring& sp : springs) {
+    Body& A = bodies[sp.bodyA];
+    Body& B = bodies[sp.bodyB];
+    const double k = sp.stiffness, d = sp.damping, l = sp.restLength;
+    const V3 worldAnchorA = add(qvmult(A.quaternion, sp.localAnchorA), A.position);  // pointToWorldFrame, rigid_body.dart:332-337
+    const V3 worldAnchorB = add(qvmult(B.quaternion, sp.localAnchorB), B.position);
+    const V3 ri = sub(worldAnchorA, A.position), rj = sub(worldAnchorB, B.position);
+    const V3 r = sub(worldAnchorB, worldAnchorA);
+    const double rlen = length(r);
+    V3 rUnit = r;
+    normalize(rUnit);
+    V3 u = sub(B.velocity, A.velocity);
+    V3 tmp = cross(B.angularVelocity, rj);
+    u = add(u, tmp);
+    tmp = cross(A.angularVelocity, ri);
+    u = sub(u, tmp);
+    const V3 f = scale(-k * (rlen - l) - d * dot(u, rUnit), rUnit);
+    A.force = sub(A.force, f);
+    B.force = add(B.force, f);
+    const V3 rixf = cross(ri, f), rjxf = cross(rj, f);
+    A.torque = sub(A.torque, rixf);
+    B.torque = add(B.torque, rjxf);
   }
 }
 

@@ -103,6 +103,12 @@ struct Constraint {
   std::vector<V3> locA, locB;  // body-local axes of the rotational equations that are re-oriented in update() (lock, cone-twist)
 };
 
+struct Spring {  // lib/objects/spring.dart
+  int bodyA = -1, bodyB = -1;
+  double restLength = 1, stiffness = 100, damping = 1;
+  V3 localAnchorA{0, 0, 0}, localAnchorB{0, 0, 0};
+};
+
 struct RowDebug {
   int bi, bj;
   double B, invC, lambda;
@@ -116,6 +122,7 @@ struct World {
   std::vector<cannon_contact_material> cms;
   std::vector<int> cmTable;  // nmat*nmat -> cm index or -1
   std::vector<Constraint> constraints;
+  std::vector<Spring> springs;  // applied in the postStep slot, in order
   double time = 0;
   double dt = -1;
   int64_t stepnumber = 0;
@@ -139,7 +146,8 @@ struct World {
   void getContacts();               // narrowphase over p1/p2
   void makeContactConstraints();    // restitution override + wake-up flags
   int solve(double dt);             // GSSolver.solve over frictions ++ contacts ++ constraint rows
-  void integrateAll(double dt);     // damping, integrate, clearForces, sleepTick
+  void integrateAll(double dt);     // damping, integrate, clearForces, postStep springs, sleepTick
+  void applySprings();              // Spring.applyForce for every spring, spring.dart:108-157
   void internalStep(double dt);
 };
 

@@ -145,14 +145,44 @@ def test_lock_and_cone_twist_constraints_behave(oracle_lib):
         assert abs(np.linalg.norm(s["position"][o + 1] - s["position"][o]) - 1.5) < 2e-2  # soft (SPOOK) constraint under a swinging load
         d0 = np.linalg.norm(p0[o + 3] - p0[o + 2])
         assert abs(np.linalg.norm(s["position"][o + 3] - s["position"][o + 2]) - d0) < 2e-2
-        # the axis-aligned locked pair falls as one rigid piece: relative position and orientation unchanged
-        assert np.allclose(s["position"][o + 5] - s["position"][o + 4], p0[o + 5] - p0[o + 4], atol=2e-3)
-        assert np.allclose(s["quaternion"][o + 4], (0, 0, 0, 1), atol=2e-3) and np.allclose(s["quaternion"][o + 5], (0, 0, 0, 1), atol=2e-3)
+        # the axis-aligned locked pair moves as one rigid piece (a spring tugs at it): same orientation, and the offset seen
+        # from body A's frame stays what it was
+        qa, qb = s["quaternion"][o + 4].astype(np.float64), s["quaternion"][o + 5].astype(np.float64)
+        assert min(np.abs(qa - qb).max(), np.abs(qa + qb).max()) < 5e-3
+        x, y, z, ww = qa
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - ww * z), 2 * (x * z + ww * y)],
+                      [2 * (x * y + ww * z), 1 - 2 * (x * x + z * z), 2 * (y * z - ww * x)],
+                      [2 * (x * z - ww * y), 2 * (y * z + ww * x), 1 - 2 * (x * x + y * y)]])
+        rel = R.T @ (s["position"][o + 5] - s["position"][o + 4]).astype(np.float64)
+        assert np.allclose(rel, p0[o + 5] - p0[o + 4], atol=5e-3)
         # the limb hangs from its static root: pivots stay together
         for k in range(3):
             a, b = o + 8 + k, o + 9 + k
             assert np.linalg.norm(s["position"][a] - s["position"][b]) < 0.8
     assert np.all(np.isfinite(s["position"])) and np.abs(s["velocity"]).max() < 10
+
+
+def test_spring_force_matches_closed_form_and_oscillates(oracle_lib):
+    # spring.dart:108-157: F = -k (|r| - L) - d (u . r^) along r^; applied in the postStep slot => it acts from the second step on
+    spec = scenes.spheres_on_plane(1, 1, 2, y0=5.0)
+    spec.desc["gravity"] = (0, 0, 0)
+    spec.bodies["position"][1] = (0, 5, 0)
+    spec.bodies["position"][2] = (3, 5, 0)
+    spec.bodies["mass"][1] = 0.0  # anchor
+    spec.springs = [dict(body_a=1, body_b=2, rest_length=1.0, stiffness=50.0, damping=0.0)]
+    w = engine.DeviceWorld(oracle_lib, spec)
+    w.step(1 / 60, 1)
+    s = w.get_bodies(("force", "velocity", "position"))
+    assert np.allclose(s["velocity"][2], 0) and np.allclose(s["force"][2], (-100.0, 0, 0))  # -k (3 - 1), waiting for the next step
+    assert np.allclose(s["force"][1], (100.0, 0, 0))
+    w.step(1 / 60, 1)
+    s = w.get_bodies(("velocity",))
+    assert s["velocity"][2][0] == pytest.approx(-100.0 / 60, rel=1e-6)  # v += f invMass dt, mass 1
+    xs = []
+    for _ in range(120):
+        w.step(1 / 60, 1)
+        xs.append(float(w.get_bodies(("position",))["position"][2][0]))
+    assert min(xs) < 0.8 and max(xs) <= 3.0 + 1e-3  # swings through the rest length (x = 1) until the spheres touch
 
 
 def test_cone_equation_limits_the_swing(oracle_lib):
