@@ -960,6 +960,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   const int nRows = min(*R.nRows, R.rowCap);
   const int nLevels = *S.nLevels;
   // CTAs for about twice the mean number of warp tasks per colour
+  if (*T.nTasks > T.taskCap) return;  // reported through the row-overflow counter by k_gs_task_levels
   const int nCtas = coop_ctas(2LL * min(*T.nTasks, T.taskCap) / max(nLevels, 1) + 1, GS_WARPS);
   if ((int)blockIdx.x >= nCtas) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nCtas * blockDim.x;
