@@ -180,6 +180,38 @@ __device__ inline bool pillar_quick_separated(const float4* hv, int nVA, const f
   return false;
 }
 
+// The axes of that test depend on the hull and on the heightfield's orientation only, not on the pillar: the warp
+// evaluates each axis, its hull projection and its image in the heightfield frame ONCE per pair (one axis per lane,
+// QsAxis in shared memory) and every lane then projects only the six vertices of its own pillar.
+struct QsAxis {
+  f3 lax;            // qrot(qnegw(qP), axis): the axis in the heightfield's local frame
+  double maxA, minA; // hull projection (ConvexPolyhedron.project of the hull on the axis)
+  int valid;
+};
+#define QS_MAX_AXES 33
+
+__device__ __forceinline__ bool pillar_quick_separated_pre(const QsAxis* __restrict__ ax, int nAx, const f3* pv, const f3& xP, const q4& qP) {
+  f3 zero; zero.x = zero.y = zero.z = 0.f;
+  const f3 oP = to_local_point(xP, qP, zero);
+  for (int t = 0; t < nAx; t++) {
+    if (!ax[t].valid) continue;
+    const f3 localAxis = ax[t].lax;
+    const double add = vdot(oP, localAxis);
+    double mn, mx;
+    mn = mx = vdot(pv[0], localAxis);
+    for (int i = 1; i < 6; i++) {
+      const double val = vdot(pv[i], localAxis);
+      if (val > mx) mx = val;
+      if (val < mn) mn = val;
+    }
+    mn -= add;
+    mx -= add;
+    if (mn > mx) { const double tt = mn; mn = mx; mx = tt; }
+    if (ax[t].maxA < mn || mx < ax[t].minA) return true;
+  }
+  return false;
+}
+
 // which body plays "i" for the resolver: lower ShapeType index first, equal types swapped (narrow_phase.dart:706-710)
 __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& first, int& second) {
   if (ta < tb) { first = a; second = b; } else { first = b; second = a; }
@@ -190,6 +222,8 @@ __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& firs
 // and every lane tests one pillar of the index window (bounding gate + exact quick separation), a ballot gives the
 // survivor mask in the reference's loop order (i, j, lower/upper), so counts and emission order need no atomics.
 __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass) {
+  __shared__ QsAxis s_qs[4][QS_MAX_AXES];
+  QsAxis* const qs_ax = s_qs[threadIdx.x >> 5];
   const int np = *A.nPairs;
   const int lane = threadIdx.x & 31;
   const int warpStart = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
@@ -267,6 +301,36 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       }
       const bool cached = pass && nP <= 64;
       const unsigned long long cachedMask = cached ? A.pairMask[pk] : 0ull;
+      // quick-separation axes of this pair (face 0 of the hull when it has uniqueAxes, then hull edge x heightfield z)
+      const bool quick = hullTask && !cached && hd.nE <= 32 && hd.nF <= 32;
+      int nAx = 0;
+      if (quick) {
+        nAx = (hd.hasAxes ? 1 : 0) + hd.nE;
+        f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
+        const f3 wz = qrot(qs, up);
+        __syncwarp();  // the previous pair's lanes are done with the scratch
+        for (int t = lane; t < nAx; t += 32) {
+          const int e = t - (hd.hasAxes ? 1 : 0);
+          f3 axis;
+          bool valid = true;
+          if (e < 0) axis = qrot(qf, ld3(T.fnormals[hd.fOff]));
+          else {
+            axis = vcross(qrot(qf, ld3(T.edges[hd.eOff + e])), wz);
+            if (valmost_zero(axis)) valid = false;
+            else vnormalize(axis);
+          }
+          QsAxis q;
+          q.valid = valid ? 1 : 0;
+          q.maxA = q.minA = 0.0;
+          q.lax = axis;
+          if (valid) {
+            project_verts(T.verts + hd.vOff, nullptr, hd.nV, axis, qf, oA, q.maxA, q.minA);
+            q.lax = qrot(qnegw(qs), axis);
+          }
+          qs_ax[t] = q;
+        }
+        __syncwarp();
+      }
       unsigned long long mask = 0ull;
       int count = 0;
       for (int base = 0; base < nP; base += 32) {
@@ -285,9 +349,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
             pillar_bounds(T, hf, ci, cj, up != 0, po, pr, pv);
             const f3 wpo = to_world_point(xs, qs, po);
             alive = vdist(xf, wpo) < pr + rFirst;
-            if (alive && hullTask && hd.nE <= 32 && hd.nF <= 32)
-              alive = !pillar_quick_separated(T.verts + hd.vOff, hd.nV, T.fnormals + hd.fOff, hd.hasAxes, T.edges + hd.eOff, hd.nE, xf, qf, oA,
-                                              pv, wpo, qs);
+            if (alive && quick) alive = !pillar_quick_separated_pre(qs_ax, nAx, pv, wpo, qs);
           }
         }
         const unsigned bits = __ballot_sync(0xffffffffu, alive);
