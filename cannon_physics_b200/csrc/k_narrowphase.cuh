@@ -158,28 +158,6 @@ __device__ __forceinline__ void project_verts(const float4* __restrict__ gv, con
 // set separates the hulls (convex_polyhedron.dart:264-267,338-341). The set always contains face 0 of the hull
 // (when it has `uniqueAxes`) and cross(hull edge, pillar vertical edge (0,0,1)); testing just those with the
 // very same projection arithmetic kills most window pillars without changing a single result.
-__device__ inline bool pillar_quick_separated(const float4* hv, int nVA, const float4* hn, int hasAxes, const float4* he, int nEA,
-                                              const f3& xA, const q4& qA, const f3& oA, const f3* pv, const f3& xP, const q4& qP) {
-  f3 zero; zero.x = zero.y = zero.z = 0.f;
-  const f3 oP = to_local_point(xP, qP, zero);
-  f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
-  const f3 wz = qrot(qP, up);
-  for (int t = hasAxes ? -1 : 0; t < nEA; t++) {
-    f3 axis;
-    if (t < 0) axis = qrot(qA, ld3(hn[0]));
-    else {
-      axis = vcross(qrot(qA, ld3(he[t])), wz);
-      if (valmost_zero(axis)) continue;
-      vnormalize(axis);
-    }
-    double maxA, minA, maxB, minB;
-    project_verts(hv, nullptr, nVA, axis, qA, oA, maxA, minA);
-    project_verts(nullptr, pv, 6, axis, qP, oP, maxB, minB);
-    if (maxA < minB || maxB < minA) return true;
-  }
-  return false;
-}
-
 // The axes of that test depend on the hull and on the heightfield's orientation only, not on the pillar: the warp
 // evaluates each axis, its hull projection and its image in the heightfield frame ONCE per pair (one axis per lane,
 // QsAxis in shared memory) and every lane then projects only the six vertices of its own pillar.
