@@ -31,7 +31,61 @@ struct SatScratch {
   PillarStore pil;
   int kept, overflow, closestA;
   f3 nrm;
+  unsigned char fA[SAT_MAXF], fB[SAT_MAXF];  // face-normal axes that are not +-copies of an earlier one
 };
+
+// Axis pruning that cannot change the result. If a world axis is numerically +-equal to an earlier axis of the same
+// loop, every expression downstream (Quaternion.vmult, cross2, normalize, project, testSepAxis; quaternion.dart:21-44,
+// convex_polyhedron.dart:360-384,843-883) is odd in the axis, IEEE rounding is symmetric under negation, and testSepAxis
+// is symmetric in (max, -min): the later axis is separated iff the earlier one is and has exactly the same depth, so
+// with findSeparatingAxis' strict `d < dmin` (convex_polyhedron.dart:266,302,328) it can never be selected. The same
+// holds for the edge loop when one of the two edges is a +-copy. A box therefore contributes 3 face axes and 3 edges
+// instead of 6 and 6, a heightfield pillar 7 edges instead of 14: box-box 48 -> 15 axes, box-pillar 90 -> 27.
+__device__ __forceinline__ bool vpm_eq(const f3& a, const f3& b) {
+  return (a.x == b.x && a.y == b.y && a.z == b.z) || (a.x == -b.x && a.y == -b.y && a.z == -b.z);
+}
+
+// order-preserving in-place compaction of the world edges of one hull; returns the number kept
+template <class Tile>
+__device__ __forceinline__ int dedup_edges_tile(const Tile& tile, int lane, f3* e, int n) {
+  int cnt = 0;
+  for (int base = 0; base < n; base += SAT_GROUP) {
+    const int i = base + lane;
+    f3 v; v.x = v.y = v.z = 0.f;
+    bool keep = false;
+    if (i < n) {
+      v = e[i];
+      keep = true;
+      for (int p = 0; p < cnt && keep; p++) if (vpm_eq(e[p], v)) keep = false;
+      for (int p = base; p < i && keep; p++) if (vpm_eq(e[p], v)) keep = false;
+    }
+    const unsigned m = tile.ballot(keep);
+    tile.sync();
+    if (keep) e[cnt + __popc(m & ((1u << lane) - 1u))] = v;
+    cnt += __popc(m);
+    tile.sync();
+  }
+  return cnt;
+}
+
+// order-preserving list of the face normals worth testing (the normals stay in place: clipping indexes them by face)
+template <class Tile>
+__device__ __forceinline__ int dedup_faces_tile(const Tile& tile, int lane, const f3* n, int nF, unsigned char* list) {
+  int cnt = 0;
+  for (int base = 0; base < nF; base += SAT_GROUP) {
+    const int i = base + lane;
+    bool keep = false;
+    if (i < nF) {
+      const f3 v = n[i];
+      keep = true;
+      for (int p = 0; p < i && keep; p++) if (vpm_eq(n[p], v)) keep = false;
+    }
+    const unsigned m = tile.ballot(keep);
+    if (keep) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
+    cnt += __popc(m);
+  }
+  return cnt;
+}
 
 // ConvexPolyhedron.project (convex_polyhedron.dart:843-883) with a precomputed local origin and the hull's local
 // vertices already widened to double in shared memory. float -> double is exact and max / min do not depend on the
@@ -276,11 +330,15 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
       for (int i = lane; i < HA.nV; i += SAT_GROUP) { const float4 v = HA.v[i]; S.u.v.vA[i][0] = v.x; S.u.v.vA[i][1] = v.y; S.u.v.vA[i][2] = v.z; }
       for (int i = lane; i < HB.nV; i += SAT_GROUP) { const float4 v = HB.v[i]; S.u.v.vB[i][0] = v.x; S.u.v.vB[i][1] = v.y; S.u.v.vB[i][2] = v.z; }
       tile.sync();
+      const int nEA = dedup_edges_tile(tile, lane, S.eA, HA.nE), nEB = dedup_edges_tile(tile, lane, S.eB, HB.nE);
+      const int nFA = PILLAR ? 1 : dedup_faces_tile(tile, lane, S.nA, HA.nF, S.fA);
+      const int nFB = dedup_faces_tile(tile, lane, S.nB, HB.nF, S.fB);
+      tile.sync();
       f3 zero; zero.x = zero.y = zero.z = 0.f;
       const f3 oA = to_local_point(c.xi, c.qi, zero), oB = to_local_point(xB, c.qj, zero);
-      const int nfa = HA.hasAxes ? (PILLAR ? 1 : HA.nF) : 0;  // heightfieldConvex passes faceListA = [0] (:2062)
-      const int nfb = HB.hasAxes ? HB.nF : 0;
-      const int nAxes = nfa + nfb + HA.nE * HB.nE;
+      const int nfa = HA.hasAxes ? nFA : 0;  // heightfieldConvex passes faceListA = [0] (:2062)
+      const int nfb = HB.hasAxes ? nFB : 0;
+      const int nAxes = nfa + nfb + nEA * nEB;
       double best = INFINITY;
       int bestIdx = 0x7fffffff;
       f3 bestAxis = zero;
@@ -293,11 +351,11 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
         if (t < nAxes) {
           f3 axis;
           bool valid = true;
-          if (t < nfa) axis = S.nA[t];
-          else if (t < nfa + nfb) axis = S.nB[t - nfa];
+          if (t < nfa) axis = S.nA[PILLAR ? 0 : S.fA[t]];
+          else if (t < nfa + nfb) axis = S.nB[S.fB[t - nfa]];
           else {
             const int e = t - nfa - nfb;
-            axis = vcross(S.eA[e / HB.nE], S.eB[e % HB.nE]);
+            axis = vcross(S.eA[e / nEB], S.eB[e % nEB]);
             if (valmost_zero(axis)) valid = false;
             else vnormalize(axis);
           }
