@@ -145,7 +145,9 @@ struct cannon_world {
   // device: shape tables
   DBuf<ShapeDev> dShapes;
   DBuf<HullDev> dHulls;
-  DBuf<float4> dVerts, dFnormals, dEdges;
+  DBuf<float4> dVerts, dFnormals, dEdges, dEdgesK;
+  DBuf<int> dFacesK;
+  DBuf<PillarRec> dPillars;
   DBuf<double> dFplanec, dHfData, dMatFriction, dMatRestitution;
   DBuf<int> dFvOff, dFvIdx, dFcOff, dFcIdx, dCmTable;
   DBuf<HfDev> dHfs;
@@ -271,6 +273,7 @@ static ShapeTables shape_tables(cannon_world* w) {
   ShapeTables T;
   T.shapes = w->dShapes.p; T.hulls = w->dHulls.p; T.verts = w->dVerts.p; T.fnormals = w->dFnormals.p; T.fplanec = w->dFplanec.p;
   T.fvOff = w->dFvOff.p; T.fvIdx = w->dFvIdx.p; T.fcOff = w->dFcOff.p; T.fcIdx = w->dFcIdx.p; T.edges = w->dEdges.p;
+  T.edgesK = w->dEdgesK.p; T.facesK = w->dFacesK.p; T.pillars = w->dPillars.p;
   T.hfs = w->dHfs.p; T.hfdata = w->dHfData.p; T.cmTable = w->dCmTable.p; T.cms = w->dCms.p;
   T.matFriction = w->dMatFriction.p; T.matRestitution = w->dMatRestitution.p; T.nMat = w->nMat;
   return T;
@@ -402,7 +405,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(vlam); REL(wlam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
-  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData);
+  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
   REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
@@ -456,6 +459,7 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   w->hHulls.clear();
   w->hHfs.clear();
   w->hHfData.clear();
+  long long nPillars = 0;
   for (int i = 0; i < n; i++) {
     const cannon_shape_desc& d = sd[i];
     HostShape& h = w->hShapes[i];
@@ -518,6 +522,8 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
         double mn = d.hf_data[0], mx = d.hf_data[0];  // updateMinValue / updateMaxValue, heightfield.dart:87-113
         for (size_t k = 0; k < cntv; k++) { mn = d.hf_data[k] < mn ? d.hf_data[k] : mn; mx = d.hf_data[k] > mx ? d.hf_data[k] : mx; }
         hf.minV = mn; hf.maxV = mx;
+        hf.pilOff = nPillars;
+        nPillars += (long long)(d.hf_nx - 1) * (d.hf_ny - 1) * 2;
         w->hHfData.insert(w->hHfData.end(), d.hf_data, d.hf_data + cntv);
         h.hf = (int)w->hHfs.size();
         w->hHfs.push_back(hf);
@@ -541,7 +547,8 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   std::vector<HullDev> hulls;
   w->hasOversizeHull = false;
   for (const HostHull& h : w->hHulls) if (h.faces.size() > 32 || h.edges.size() > 32) w->hasOversizeHull = true;
-  std::vector<float4> verts, fnormals, edges;
+  std::vector<float4> verts, fnormals, edges, edgesK;
+  std::vector<int> facesK;
   std::vector<double> fplanec;
   std::vector<int> fvOff, fvIdx, fcOff, fcIdx;
   int totalFaces = 0;
@@ -554,6 +561,23 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     d.hasAxes = h.hasAxes ? 1 : 0; d.pad = 0; d.bsr = h.bsr;
     for (const f3& p : h.v) verts.push_back(st3(p));
     for (const f3& p : h.edges) edges.push_back(st3(p));
+    // axes that are numerically +-equal in the local frame stay +-equal after Quaternion.vmult: the later one can
+    // never win findSeparatingAxis' strict `d < dmin` (k_sat_warp.cuh), so the tile kernel only walks these lists
+    auto pm_eq = [](const f3& a, const f3& b) {
+      return (a.x == b.x && a.y == b.y && a.z == b.z) || (a.x == -b.x && a.y == -b.y && a.z == -b.z);
+    };
+    d.ekOff = (int)edgesK.size(); d.nEk = 0;
+    for (size_t i = 0; i < h.edges.size(); i++) {
+      bool dup = false;
+      for (size_t p = 0; p < i && !dup; p++) dup = pm_eq(h.edges[p], h.edges[i]);
+      if (!dup) { edgesK.push_back(st3(h.edges[i])); d.nEk++; }
+    }
+    d.fkOff = (int)facesK.size(); d.nFk = 0;
+    for (size_t i = 0; i < h.faces.size(); i++) {
+      bool dup = false;
+      for (size_t p = 0; p < i && !dup; p++) dup = pm_eq(h.n[p], h.n[i]);
+      if (!dup) { facesK.push_back((int)i); d.nFk++; }
+    }
     for (size_t f = 0; f < h.faces.size(); f++) {
       fnormals.push_back(st3(h.n[f]));
       fplanec.push_back(h.planec[f]);
@@ -577,8 +601,21 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   W_TRY(w, upload(w->dFvIdx, fvIdx, s));
   W_TRY(w, upload(w->dFcOff, fcOff, s));
   W_TRY(w, upload(w->dFcIdx, fcIdx, s));
+  W_TRY(w, upload(w->dEdgesK, edgesK, s));
+  W_TRY(w, upload(w->dFacesK, facesK, s));
   W_TRY(w, upload(w->dHfs, w->hHfs, s));
   W_TRY(w, upload(w->dHfData, w->hHfData, s));
+  if (nPillars > 0) {
+    W_TRY(w, w->dPillars.reserve((size_t)nPillars));
+    const ShapeTables T = shape_tables(w);
+    for (size_t k = 0; k < w->hHfs.size(); k++) {
+      const HfDev& hf = w->hHfs[k];
+      const long long np = (long long)(hf.nx - 1) * (hf.ny - 1) * 2;
+      g_kernel_launches++;
+      k_pillars_build<<<grid_for(w, np, 128), 128, 0, s>>>(T, hf, w->dPillars.p);
+    }
+    W_TRY(w, cudaGetLastError());
+  }
   W_TRY(w, cudaStreamSynchronize(s));
   return CANNON_OK;
 }

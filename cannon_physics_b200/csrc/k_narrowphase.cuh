@@ -57,6 +57,8 @@ struct HullView {
   const int* fvOff; const int* fvIdx;   // fvOff[f]..fvOff[f+1]
   const int* fcOff; const int* fcIdx;
   const float4* e; int nE;
+  const float4* ek; int nEk;   // edges / faces left after dropping +-copies (tile SAT kernel only)
+  const int* fk; int nFk;
   int hasAxes;
   double bsr;
 };
@@ -69,6 +71,8 @@ __device__ __forceinline__ HullView hull_view(const ShapeTables& T, int hull) {
   H.fvOff = T.fvOff + h.fOff + hull; H.fvIdx = T.fvIdx;
   H.fcOff = T.fcOff + h.fOff + hull; H.fcIdx = T.fcIdx;
   H.e = T.edges + h.eOff; H.nE = h.nE;
+  H.ek = T.edgesK + h.ekOff; H.nEk = h.nEk;
+  H.fk = T.facesK + h.fkOff; H.nFk = h.nFk;
   H.hasAxes = h.hasAxes;
   H.bsr = h.bsr;
   return H;
@@ -322,9 +326,12 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           cj = y0 + cell % wy;
           if (cached) alive = (cachedMask >> pidx) & 1ull;
           else {
-            f3 po, pv[6];
-            double pr;
-            pillar_bounds(T, hf, ci, cj, up != 0, po, pr, pv);
+            // offset, bounding radius and vertices of the pillar from the table built by k_pillars_build
+            const PillarRec* R = T.pillars + hf.pilOff + (((long long)ci * (hf.ny - 1) + cj) * 2 + up);
+            f3 po = ld3(R->off), pv[6];
+            const double pr = R->bsr;
+#pragma unroll
+            for (int i = 0; i < 6; i++) pv[i] = ld3(R->v[i]);
             const f3 wpo = to_world_point(xs, qs, po);
             alive = vdist(xf, wpo) < pr + rFirst;
             if (alive && quick) alive = !pillar_quick_separated_pre(qs_ax, nAx, pv, wpo, qs);
@@ -952,8 +959,59 @@ __device__ __forceinline__ HullView pillar_view(const PillarStore& S, bool upper
   H.fvOff = c_pillarFvOff; H.fvIdx = upper ? c_pillarUpper : c_pillarLower;
   H.fcOff = nullptr; H.fcIdx = nullptr;  // a pillar is never the reference hull (A) of a clip
   H.e = S.e; H.nE = S.nE;
+  H.ek = nullptr; H.nEk = 0; H.fk = nullptr; H.nFk = 0;
   H.hasAxes = 0;  // plain ConvexPolyhedron(): contributes no face-normal axes (§5.9-9)
   H.bsr = S.bsr;
+  return H;
+}
+
+// ---- precomputed pillar table (PillarRec, world.cuh) ---------------------------------------------------
+__device__ __forceinline__ bool vpm_eq(const f3& a, const f3& b) {  // numerically a == b or a == -b
+  return (a.x == b.x && a.y == b.y && a.z == b.z) || (a.x == -b.x && a.y == -b.y && a.z == -b.z);
+}
+// one thread per (cell, lower/upper): build_pillar exactly as the per-task kernels used to, then drop the unique
+// edges that are +-copies of an earlier one (each geometric edge of the prism shows up once per adjacent face, in
+// opposite directions: 14 "unique" edges are 7 directions)
+__global__ void __launch_bounds__(128) k_pillars_build(ShapeTables T, HfDev hf, PillarRec* __restrict__ out) {
+  const long long np = (long long)(hf.nx - 1) * (hf.ny - 1) * 2;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
+    const int upper = (int)(k & 1);
+    const long long cell = k >> 1;
+    const int xi = (int)(cell / (hf.ny - 1)), yi = (int)(cell % (hf.ny - 1));
+    PillarStore S;
+    f3 off;
+    build_pillar(T, hf, xi, yi, upper != 0, S, off);
+    PillarRec& R = out[hf.pilOff + k];
+    R.off = st3(off);
+    for (int i = 0; i < 6; i++) R.v[i] = S.v[i];
+    for (int i = 0; i < 5; i++) { R.n[i] = S.n[i]; R.pc[i] = S.pc[i]; }
+    R.bsr = S.bsr;
+    int nE = 0;
+    for (int i = 0; i < S.nE; i++) {
+      const f3 e = ld3(S.e[i]);
+      bool dup = false;
+      for (int p = 0; p < i && !dup; p++) dup = vpm_eq(ld3(S.e[p]), e);
+      if (!dup && nE < 9) R.e[nE++] = S.e[i];
+    }
+    for (int i = nE; i < 9; i++) R.e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    R.nE = nE;
+    R.pad = 0;
+  }
+}
+__device__ __forceinline__ const PillarRec* pillar_rec(const ShapeTables& T, const HfDev& hf, int xi, int yi, bool upper) {
+  return T.pillars + hf.pilOff + (((long long)xi * (hf.ny - 1) + yi) * 2 + (upper ? 1 : 0));
+}
+// view of a precomputed pillar; e / nE are the pruned edges (only the tile SAT kernel may use them as the edge list)
+__device__ __forceinline__ HullView pillar_view_rec(const PillarRec* R, bool upper) {
+  HullView H;
+  H.v = R->v; H.nV = 6;
+  H.n = R->n; H.pc = R->pc; H.nF = 5;
+  H.fvOff = c_pillarFvOff; H.fvIdx = upper ? c_pillarUpper : c_pillarLower;
+  H.fcOff = nullptr; H.fcIdx = nullptr;
+  H.e = R->e; H.nE = R->nE;
+  H.ek = R->e; H.nEk = R->nE; H.fk = nullptr; H.nFk = 0;
+  H.hasAxes = 0;
+  H.bsr = R->bsr;
   return H;
 }
 
@@ -965,14 +1023,12 @@ __global__ void __launch_bounds__(64) k_np_sphere_pillar(BodyArrays B, ShapeTabl
     const HfDev hf = T.hfs[c.sj.hf];
     const int2 cell = A.taskCell[c.task];
     const bool upper = (c.info >> 4) & 1;
-    PillarStore S;
-    f3 off;
-    build_pillar(T, hf, cell.x, cell.y, upper, S, off, false);
-    const f3 wpo = to_world_point(c.xj, c.qj, off);
+    const PillarRec* R = pillar_rec(T, hf, cell.x, cell.y, upper);
+    const f3 wpo = to_world_point(c.xj, c.qj, ld3(R->off));
     bool hit = false;
     f3 ri, rj, ni;
-    if (vdist(c.xi, wpo) < S.bsr + c.si.bsr) {
-      const HullView H = pillar_view(S, upper);
+    if (vdist(c.xi, wpo) < R->bsr + c.si.bsr) {
+      const HullView H = pillar_view_rec(R, upper);  // sphereConvex never looks at the edge list
       hit = sphere_convex(H, c.si.radius, c.xi, wpo, c.qj, ri, rj, ni);
     }
     if (!raw_alloc(o, hit ? 1 : 0)) continue;

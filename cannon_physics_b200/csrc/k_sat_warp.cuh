@@ -24,14 +24,11 @@ struct SatScratch {
   f3 nA[SAT_MAXF], nB[SAT_MAXF];  // world face normals
   f3 eA[SAT_MAXE], eB[SAT_MAXE];  // world unique edges
   union {                          // three phases of a task that never overlap
-    struct { f3 cand[18]; int candMask[18]; } p;                                        // pillar edge candidates
     struct { double vA[SAT_MAXV][3], vB[SAT_MAXV][3]; } v;                              // axis loop: local vertices, widened once
     struct { f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY]; double depth[NP_MAXPOLY]; } c;          // clipping + emission
   } u;
-  PillarStore pil;
   int kept, overflow, closestA;
   f3 nrm;
-  unsigned char fA[SAT_MAXF], fB[SAT_MAXF];  // face-normal axes that are not +-copies of an earlier one
 };
 
 // Axis pruning that cannot change the result. If a world axis is numerically +-equal to an earlier axis of the same
@@ -41,51 +38,8 @@ struct SatScratch {
 // with findSeparatingAxis' strict `d < dmin` (convex_polyhedron.dart:266,302,328) it can never be selected. The same
 // holds for the edge loop when one of the two edges is a +-copy. A box therefore contributes 3 face axes and 3 edges
 // instead of 6 and 6, a heightfield pillar 7 edges instead of 14: box-box 48 -> 15 axes, box-pillar 90 -> 27.
-__device__ __forceinline__ bool vpm_eq(const f3& a, const f3& b) {
-  return (a.x == b.x && a.y == b.y && a.z == b.z) || (a.x == -b.x && a.y == -b.y && a.z == -b.z);
-}
-
-// order-preserving in-place compaction of the world edges of one hull; returns the number kept
-template <class Tile>
-__device__ __forceinline__ int dedup_edges_tile(const Tile& tile, int lane, f3* e, int n) {
-  int cnt = 0;
-  for (int base = 0; base < n; base += SAT_GROUP) {
-    const int i = base + lane;
-    f3 v; v.x = v.y = v.z = 0.f;
-    bool keep = false;
-    if (i < n) {
-      v = e[i];
-      keep = true;
-      for (int p = 0; p < cnt && keep; p++) if (vpm_eq(e[p], v)) keep = false;
-      for (int p = base; p < i && keep; p++) if (vpm_eq(e[p], v)) keep = false;
-    }
-    const unsigned m = tile.ballot(keep);
-    tile.sync();
-    if (keep) e[cnt + __popc(m & ((1u << lane) - 1u))] = v;
-    cnt += __popc(m);
-    tile.sync();
-  }
-  return cnt;
-}
-
-// order-preserving list of the face normals worth testing (the normals stay in place: clipping indexes them by face)
-template <class Tile>
-__device__ __forceinline__ int dedup_faces_tile(const Tile& tile, int lane, const f3* n, int nF, unsigned char* list) {
-  int cnt = 0;
-  for (int base = 0; base < nF; base += SAT_GROUP) {
-    const int i = base + lane;
-    bool keep = false;
-    if (i < nF) {
-      const f3 v = n[i];
-      keep = true;
-      for (int p = 0; p < i && keep; p++) if (vpm_eq(n[p], v)) keep = false;
-    }
-    const unsigned m = tile.ballot(keep);
-    if (keep) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned char)i;
-    cnt += __popc(m);
-  }
-  return cnt;
-}
+// The pruned lists are built once: per hull on the host (cannon_world_set_shapes: +-equal in the local frame implies
+// +-equal after Quaternion.vmult), per heightfield pillar by k_pillars_build.
 
 // ConvexPolyhedron.project (convex_polyhedron.dart:843-883) with a precomputed local origin and the hull's local
 // vertices already widened to double in shared memory. float -> double is exact and max / min do not depend on the
@@ -258,58 +212,13 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
     f3 xB;
     bool upper = false;
     if (PILLAR) {
+      // the pillar (vertices, face normals, plane constants, pruned unique edges) was built when the shapes were set
       const HfDev hf = T.hfs[c.sj.hf];
       const int2 cell = A.taskCell[c.task];
       upper = (c.info >> 4) & 1;
-      // Heightfield.getConvexTrianglePillar (heightfield.dart:330-487) spread over the tile: vertices by lane 0,
-      // one face normal per lane, one edge candidate per lane, duplicate removal in candidate order
-      // (computeNormals / computeEdges, convex_polyhedron.dart:110-185)
-      if (lane == 0) {
-        f3 off, pv[6];
-        double bsr;
-        pillar_bounds(T, hf, cell.x, cell.y, upper, off, bsr, pv);
-        for (int i = 0; i < 6; i++) S.pil.v[i] = st3(pv[i]);
-        S.pil.bsr = bsr;
-        S.nrm = off;
-      }
-      tile.sync();
-      const f3 off = S.nrm;
-      const int* fv = upper ? c_pillarUpper : c_pillarLower;
-      for (int f = lane; f < 5; f += SAT_GROUP) {
-        const int o0 = c_pillarFvOff[f];
-        const f3 va = ld3(S.pil.v[fv[o0]]), vb = ld3(S.pil.v[fv[o0 + 1]]), vc = ld3(S.pil.v[fv[o0 + 2]]);
-        f3 nn = vcross(vsub(vc, vb), vsub(vb, va));
-        if (!(nn.x == 0.f && nn.y == 0.f && nn.z == 0.f)) vnormalize(nn);
-        nn = vneg(nn);
-        S.pil.n[f] = st3(nn);
-        S.pil.pc[f] = -vdot(nn, va);
-      }
-      for (int e = lane; e < 18; e += SAT_GROUP) {
-        int f = 0;
-        while (e >= c_pillarFvOff[f + 1]) f++;
-        const int o0 = c_pillarFvOff[f], L = c_pillarFvOff[f + 1] - o0, j = e - o0;
-        f3 ev = vsub(ld3(S.pil.v[fv[o0 + j]]), ld3(S.pil.v[fv[o0 + (j + 1) % L]]));
-        vnormalize(ev);
-        S.u.p.cand[e] = ev;
-      }
-      tile.sync();
-      for (int e = lane; e < 18; e += SAT_GROUP) {
-        int m = 0;
-        const f3 ev = S.u.p.cand[e];
-        for (int p = 0; p < e; p++)
-          if (valmost_eq(S.u.p.cand[p], ev)) m |= 1 << p;
-        S.u.p.candMask[e] = m;
-      }
-      tile.sync();
-      if (lane == 0) {
-        int nE = 0, keep = 0;
-        for (int k = 0; k < 18; k++)
-          if ((S.u.p.candMask[k] & keep) == 0) { keep |= 1 << k; S.pil.e[nE++] = st3(S.u.p.cand[k]); }
-        S.pil.nE = nE;
-      }
-      tile.sync();
-      xB = to_world_point(c.xj, c.qj, off);
-      HB = pillar_view(S.pil, upper);
+      const PillarRec* R = pillar_rec(T, hf, cell.x, cell.y, upper);
+      xB = to_world_point(c.xj, c.qj, ld3(R->off));
+      HB = pillar_view_rec(R, upper);
     } else {
       HB = hull_view(T, c.sj.hull);
       xB = c.xj;
@@ -325,15 +234,13 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
     if (candidate) {
       for (int i = lane; i < HA.nF; i += SAT_GROUP) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));
       for (int i = lane; i < HB.nF; i += SAT_GROUP) S.nB[i] = qrot(c.qj, ld3(HB.n[i]));
-      for (int i = lane; i < HA.nE; i += SAT_GROUP) S.eA[i] = qrot(c.qi, ld3(HA.e[i]));
-      for (int i = lane; i < HB.nE; i += SAT_GROUP) S.eB[i] = qrot(c.qj, ld3(HB.e[i]));
+      for (int i = lane; i < HA.nEk; i += SAT_GROUP) S.eA[i] = qrot(c.qi, ld3(HA.ek[i]));
+      for (int i = lane; i < HB.nEk; i += SAT_GROUP) S.eB[i] = qrot(c.qj, ld3(HB.ek[i]));
       for (int i = lane; i < HA.nV; i += SAT_GROUP) { const float4 v = HA.v[i]; S.u.v.vA[i][0] = v.x; S.u.v.vA[i][1] = v.y; S.u.v.vA[i][2] = v.z; }
       for (int i = lane; i < HB.nV; i += SAT_GROUP) { const float4 v = HB.v[i]; S.u.v.vB[i][0] = v.x; S.u.v.vB[i][1] = v.y; S.u.v.vB[i][2] = v.z; }
       tile.sync();
-      const int nEA = dedup_edges_tile(tile, lane, S.eA, HA.nE), nEB = dedup_edges_tile(tile, lane, S.eB, HB.nE);
-      const int nFA = PILLAR ? 1 : dedup_faces_tile(tile, lane, S.nA, HA.nF, S.fA);
-      const int nFB = dedup_faces_tile(tile, lane, S.nB, HB.nF, S.fB);
-      tile.sync();
+      const int nEA = HA.nEk, nEB = HB.nEk;
+      const int nFA = PILLAR ? 1 : HA.nFk, nFB = HB.nFk;
       f3 zero; zero.x = zero.y = zero.z = 0.f;
       const f3 oA = to_local_point(c.xi, c.qi, zero), oB = to_local_point(xB, c.qj, zero);
       const int nfa = HA.hasAxes ? nFA : 0;  // heightfieldConvex passes faceListA = [0] (:2062)
@@ -351,8 +258,8 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
         if (t < nAxes) {
           f3 axis;
           bool valid = true;
-          if (t < nfa) axis = S.nA[PILLAR ? 0 : S.fA[t]];
-          else if (t < nfa + nfb) axis = S.nB[S.fB[t - nfa]];
+          if (t < nfa) axis = S.nA[PILLAR ? 0 : HA.fk[t]];
+          else if (t < nfa + nfb) axis = S.nB[HB.fk[t - nfa]];
           else {
             const int e = t - nfa - nfb;
             axis = vcross(S.eA[e / nEB], S.eB[e % nEB]);

@@ -47,11 +47,27 @@ struct HullDev {
   int hasAxes;        // `uniqueAxes != null` (convex_polyhedron.dart:253,290)
   int pad;
   double bsr;         // boundingSphereRadius
+  int ekOff, nEk;     // unique edges that are not +-copies of an earlier one (SAT axis pruning, k_sat_warp.cuh)
+  int fkOff, nFk;     // likewise for the face normals: list of face indices
 };
 
 struct HfDev {
   int nx, ny, esize, dataOff;
   double minV, maxV;
+  long long pilOff;   // first PillarRec of this heightfield: ((xi * (ny - 1) + yi) * 2 + upper)
+};
+
+// Heightfield.getConvexTrianglePillar (heightfield.dart:330-487) evaluated once per (cell, lower/upper) when the
+// shapes are set - the reference caches pillars too (getCachedConvexTrianglePillar, heightfield.dart:300-328); the
+// height samples are immutable through this ABI. e[] holds the unique edges minus +-copies, in their original order.
+struct PillarRec {
+  float4 off;      // pillar offset in the heightfield frame
+  float4 v[6];
+  float4 n[5];
+  float4 e[9];
+  double pc[5];
+  double bsr;
+  int nE, pad;
 };
 
 struct ShapeTables {
@@ -65,6 +81,9 @@ struct ShapeTables {
   const int* fcOff;         // per face: offset into fcIdx (connected faces, precomputed clipFaceAgainstHull :459-473)
   const int* fcIdx;
   const float4* edges;      // unique edges
+  const float4* edgesK;     // unique edges without +-copies (HullDev.ekOff)
+  const int* facesK;        // faces whose normal is not a +-copy of an earlier one (HullDev.fkOff)
+  const PillarRec* pillars; // precomputed triangle pillars of every heightfield (HfDev.pilOff)
   const HfDev* hfs;
   const double* hfdata;
   const int* cmTable;       // nMat*nMat -> contact material index or -1
