@@ -179,7 +179,7 @@ struct cannon_world {
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
   DBuf<float4> rRec;
   DBuf<GsUnitRec> uRec;
-  DBuf<int> eLevel, orderW, worldCount, worldUnitStart;
+  DBuf<int> eLevel, orderW, worldCount, worldUnitStart, lenBins;
   DBuf<int2> gsTab;
   DBuf<int> gsLvlTask, gsLvlWin;
   int gsTaskCap = 0;
@@ -229,6 +229,7 @@ struct cannon_world {
   bool graphBroken = false;        // capture failed once: stay eager
   int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0;
   bool gsFastV1 = false;  // CANNON_GS_FAST_V1: the unstaged colored sweep, kept for A/B measurements
+  bool gsNoLenSort = false;  // CANNON_GS_NO_LEN_SORT: leave the units of a colour in schedule order (A/B measurements)
   // resolver kernels of different types are independent: they run on side streams between two events
   cudaStream_t npStream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t npFork = nullptr, npJoin[3] = {nullptr, nullptr, nullptr};
@@ -390,6 +391,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
+  w->gsNoLenSort = getenv("CANNON_GS_NO_LEN_SORT") != nullptr;
   *out = w;
   return CANNON_OK;
 }
@@ -415,7 +417,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(spBodyA); REL(spBodyB); REL(spOff); REL(spIdx); REL(spRest); REL(spK); REL(spD); REL(spAnchorA); REL(spAnchorB); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
@@ -710,7 +712,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   w->unitCap = unitCap;
   RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
-  RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * (w->desc.n_worlds + 2)); RES(worldUnitStart, w->desc.n_worlds + 2);
+  RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * (w->desc.n_worlds + 2)); RES(worldUnitStart, w->desc.n_worlds + 2);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
@@ -1330,6 +1332,13 @@ static int32_t st_solve(cannon_world* w, double dt) {
     { g_kernel_launches++; k_world_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, wc); }
     W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nW + 1, nW + 1, nullptr, w->scanTmp, s));
     { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, w->worldUnitStart.p, wc + nW + 2, w->orderW.p); }
+    order = w->orderW.p;
+  } else if (P.colored && !w->gsFastV1 && !w->gsNoLenSort) {
+    // homogeneous windows for k_gs_fast: units of a colour ordered by row count (k_solver.cuh, k_len_*)
+    W_TRY(w, cudaMemsetAsync(w->lenBins.p, 0, LEN_BINS * sizeof(int), s));
+    { g_kernel_launches++; k_len_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->lenBins.p); }
+    { g_kernel_launches++; k_len_starts<<<1, LEN_BINS, 0, s>>>(w->levelStart.p, cnt + CT_NLEVELS, w->lenBins.p); }
+    { g_kernel_launches++; k_len_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->lenBins.p, w->orderW.p); }
     order = w->orderW.p;
   }
   { g_kernel_launches++; k_exec_units<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, U, order, w->unitLevel.p); }

@@ -855,6 +855,17 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
 #define GS_LS_MAX 1024
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f1(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f1(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
@@ -1044,7 +1055,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
         __syncwarp();
         const bool sameNext = t1.a == t0.a;  // one task per warp and one colour: its lambdas are not written back yet
         if (!sameNext) lam_prefetch(x1, y1);
-        long long tk0 = 0, tk1 = 0, tk2 = 0;
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tkg = 0;
         const bool tr = P.trace && wic == 0 && iter == 1 && lvl == 0;
         if (tr) tk0 = clock64();
         if (pend0) { mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u); parity ^= 1u << buf; }
@@ -1060,37 +1071,69 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
             const bool staged = m.r1 - rBase <= nRs;
             if (!staged) flushEnd = min(flushEnd, m.r0 - rBase);  // that unit keeps its lambdas in global memory
             if (batch && (m.grp < 0 || __ldcg(&G.worldDone[m.grp]))) continue;
-            const float4* q = staged ? srows + (size_t)(m.r0 - rBase) * 5 : R.rec + (size_t)m.r0 * 5;
-            float* lp = staged ? slam + (m.r0 - rBase) : R.flambda + m.r0;
             // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it (thousands
             // of units resting on the same static body would otherwise all hit one L2 sector)
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 vA = (m.fl & 1) ? __ldcg(&B.vlam[m.bi]) : z4, wA = (m.fl & 1) ? __ldcg(&B.wlam[m.bi]) : z4;
             float4 vB = (m.fl & 2) ? __ldcg(&B.vlam[m.bj]) : z4, wB = (m.fl & 2) ? __ldcg(&B.wlam[m.bj]) : z4;
             float acc = 0.f;
-            for (int r = m.r0; r < m.r1; r++, q += 5, lp++) {
-              const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
-              const float lam = *lp;
-              // G*W_lambda with G = [-n, rA, n, rB]
-              float gw_ = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
-              gw_ += dot3f(q1, wA.x, wA.y, wA.z);
-              gw_ += dot3f(q2, wB.x, wB.y, wB.z);
-              float dl = q1.w * (q0.w - gw_ - q2.w * lam);
-              if (lam + dl < q3.w) dl = q3.w - lam;
-              else if (lam + dl > q4.w) dl = q4.w - lam;
-              *lp = lam + dl;
-              if (m.fl & 1) {
-                const float s = -m.imA * dl;
-                vA.x = fmaf(s, q0.x, vA.x); vA.y = fmaf(s, q0.y, vA.y); vA.z = fmaf(s, q0.z, vA.z);
-                wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
-              }
-              if (m.fl & 2) {
-                const float s = m.imB * dl;
-                vB.x = fmaf(s, q0.x, vB.x); vB.y = fmaf(s, q0.y, vB.y); vB.z = fmaf(s, q0.z, vB.z);
-                wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
-              }
-              acc += fabsf(dl);
+            if (tr && tkg == 0) {  // trace only: when did the body lambdas of this lane arrive?
+              asm volatile("" ::"f"(vA.x), "f"(wA.x), "f"(vB.x), "f"(wB.x));
+              tkg = clock64();
             }
+            // one projected Gauss-Seidel row update: G*W_lambda with G = [-n, rA, n, rB], clamp, body deltas
+#define GS_ROW_UPDATE(q0, q1, q2, q3, q4, lam, dl)                                                                   \
+            {                                                                                                        \
+              float gw_ = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);                                          \
+              gw_ += dot3f(q1, wA.x, wA.y, wA.z);                                                                    \
+              gw_ += dot3f(q2, wB.x, wB.y, wB.z);                                                                    \
+              dl = q1.w * (q0.w - gw_ - q2.w * lam);                                                                 \
+              if (lam + dl < q3.w) dl = q3.w - lam;                                                                  \
+              else if (lam + dl > q4.w) dl = q4.w - lam;                                                             \
+              if (m.fl & 1) {                                                                                        \
+                const float s_ = -m.imA * dl;                                                                        \
+                vA.x = fmaf(s_, q0.x, vA.x); vA.y = fmaf(s_, q0.y, vA.y); vA.z = fmaf(s_, q0.z, vA.z);               \
+                wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);               \
+              }                                                                                                      \
+              if (m.fl & 2) {                                                                                        \
+                const float s_ = m.imB * dl;                                                                         \
+                vB.x = fmaf(s_, q0.x, vB.x); vB.y = fmaf(s_, q0.y, vB.y); vB.z = fmaf(s_, q0.z, vB.z);               \
+                wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);               \
+              }                                                                                                      \
+              acc += fabsf(dl);                                                                                      \
+            }
+            if (staged) {
+              // rows and lambdas of the window live in shared memory: explicit ld.shared / st.shared (a pointer that may
+              // also be global compiles to generic loads) and the next row is fetched before the current one is solved
+              unsigned qa = smem_u32(srows) + (unsigned)(m.r0 - rBase) * 80u, la = smem_u32(slam) + (unsigned)(m.r0 - rBase) * 4u;
+              const int nr = m.r1 - m.r0;
+              float4 n0 = lds_f4(qa), n1 = lds_f4(qa + 16), n2 = lds_f4(qa + 32), n3 = lds_f4(qa + 48), n4 = lds_f4(qa + 64);
+              float nl = lds_f1(la);
+              for (int r = 0; r < nr; r++) {
+                const float4 q0 = n0, q1 = n1, q2 = n2, q3 = n3, q4 = n4;
+                const float lam = nl;
+                if (r + 1 < nr) {
+                  qa += 80u;
+                  n0 = lds_f4(qa); n1 = lds_f4(qa + 16); n2 = lds_f4(qa + 32); n3 = lds_f4(qa + 48); n4 = lds_f4(qa + 64);
+                  nl = lds_f1(la + 4u);
+                }
+                float dl;
+                GS_ROW_UPDATE(q0, q1, q2, q3, q4, lam, dl);
+                sts_f1(la, lam + dl);
+                la += 4u;
+              }
+            } else {
+              const float4* q = R.rec + (size_t)m.r0 * 5;
+              float* lp = R.flambda + m.r0;
+              for (int r = m.r0; r < m.r1; r++, q += 5, lp++) {
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+                const float lam = *lp;
+                float dl;
+                GS_ROW_UPDATE(q0, q1, q2, q3, q4, lam, dl);
+                *lp = lam + dl;
+              }
+            }
+#undef GS_ROW_UPDATE
             if (m.fl & 1) { B.vlam[m.bi] = vA; B.wlam[m.bi] = wA; }
             if (m.fl & 2) { B.vlam[m.bj] = vB; B.wlam[m.bj] = wB; }
             if (batch) atomicAdd(&G.worldTot[m.grp], (double)acc);
@@ -1109,7 +1152,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
         if (sameNext) lam_prefetch(x1, y1);
         if (tr && lane == 0 && trN < 4) {
           long long* o = P.trace + (size_t)gridDim.x * GS_TRACE_PHASES * 2 + (blockIdx.x * 4 + trN) * 4;
-          o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = clock64() - tk2; o[3] = nU * 1000 + nRs;
+          o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tkg - tk1; o[3] = nU * 1000 + nRs;
           trN++;
         }
         t0 = t1; x0 = x1; y0 = y1; pend0 = pend1;
@@ -1184,6 +1227,66 @@ __global__ void __launch_bounds__(256) k_world_fill(UnitArrays U, const int* __r
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
     const int u = order[a], wd = bodyWorld[U.uBi[u]];
     orderW[worldStart[wd] + atomicAdd(&worldCursor[wd], 1)] = u;
+  }
+}
+
+// ---- colored sweep: units of a colour ordered by row count ----------------------------------------------------------
+// A warp of k_gs_fast owns a window of consecutive units, one unit per lane, and its time is the longest unit of the
+// window (units have 3, 6, ... 24+ rows). Units of one colour are independent, so their order is free: a counting sort
+// by (colour, row-count class descending) makes the windows homogeneous - a few windows of long units, many windows of
+// 3-row units that finish after three rows. Colours beyond LEN_LEVELS keep their order.
+#define LEN_LEVELS 64
+#define LEN_CLASSES 8
+#define LEN_BINS (LEN_LEVELS * LEN_CLASSES)
+__device__ __forceinline__ int len_bin(int level, int rows) {
+  const int cls = min(LEN_CLASSES - 1, max(rows - 1, 0) / 3);
+  return level * LEN_CLASSES + (LEN_CLASSES - 1 - cls);
+}
+__global__ void __launch_bounds__(256) k_len_count(UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel,
+                                                   int* __restrict__ bins) {
+  const int n = min(*U.nExec, U.unitCap);
+  const int lane = threadIdx.x & 31;
+  for (int a0 = blockIdx.x * blockDim.x + threadIdx.x - lane; a0 < n; a0 += gridDim.x * blockDim.x) {
+    const int a = a0 + lane;
+    int bin = -1;
+    if (a < n) {
+      const int u = order[a], l = unitLevel[u];
+      if (l < LEN_LEVELS) bin = len_bin(l, U.uRows[u]);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&bins[bin], __popc(peers));
+  }
+}
+// bins[0..LEN_BINS): counts -> bins[LEN_BINS..2*LEN_BINS): first execution position of the bin; cursors cleared
+__global__ void __launch_bounds__(LEN_BINS) k_len_starts(const int* __restrict__ levelStart, const int* __restrict__ nLevels, int* __restrict__ bins) {
+  const int b = threadIdx.x, l = b / LEN_CLASSES;
+  int start = 0;
+  if (l < *nLevels) {
+    start = levelStart[l];
+    for (int k = l * LEN_CLASSES; k < b; k++) start += bins[k];
+  }
+  bins[LEN_BINS + b] = start;
+  bins[2 * LEN_BINS + b] = 0;
+}
+__global__ void __launch_bounds__(256) k_len_fill(UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel,
+                                                  int* __restrict__ bins, int* __restrict__ orderL) {
+  const int n = min(*U.nExec, U.unitCap);
+  const int lane = threadIdx.x & 31;
+  for (int a0 = blockIdx.x * blockDim.x + threadIdx.x - lane; a0 < n; a0 += gridDim.x * blockDim.x) {
+    const int a = a0 + lane;
+    int bin = -1, u = 0;
+    if (a < n) {
+      u = order[a];
+      const int l = unitLevel[u];
+      if (l < LEN_LEVELS) bin = len_bin(l, U.uRows[u]);
+      else orderL[a] = u;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (bin >= 0 && lane == leader) base = atomicAdd(&bins[2 * LEN_BINS + bin], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    if (bin >= 0) orderL[bins[LEN_BINS + bin] + base + __popc(peers & ((1u << lane) - 1u))] = u;
   }
 }
 

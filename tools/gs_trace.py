@@ -52,6 +52,6 @@ print("rows per unit histogram", np.bincount(sizes).tolist())
 
 ncta = t.shape[0]
 tk = raw[ncta * 64 * 2: ncta * 64 * 2 + ncta * 16].reshape(ncta, 4, 4)
-print("warp 0 of the first CTAs, iteration 1 colour 0: per task (wait us, solve us, flush us, units*1000+rows)")
+print("warp 0 of the first CTAs, iteration 1 colour 0: per task (wait us, solve us, of which body-lambda gather us, units*1000+rows)")
 for c in range(0, min(ncta, 148), 12):
     print(c, [(round(a / ghz / 1e3, 2), round(b / ghz / 1e3, 2), round(cc / ghz / 1e3, 2), int(d)) for a, b, cc, d in tk[c] if d > 0])
