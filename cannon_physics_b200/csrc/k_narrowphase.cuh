@@ -172,6 +172,17 @@ struct QsAxis {
 };
 #define QS_MAX_AXES 33
 
+// what k_np_tasks needs about one heightfield pair, fetched by the pair's own lane and read by the whole warp
+struct HfPairCtx {
+  f3 xf, xs, oA;
+  q4 qs, qf;
+  double rFirst;
+  unsigned long long mask;  // survivor mask cached by pass 0 (windows of <= 64 pillars)
+  HfDev hf;
+  HullDev hd;
+  int hullTask;
+};
+
 __device__ __forceinline__ bool pillar_quick_separated_pre(const QsAxis* __restrict__ ax, int nAx, const f3* pv, const f3& xP, const q4& qP) {
   f3 zero; zero.x = zero.y = zero.z = 0.f;
   const f3 oP = to_local_point(xP, qP, zero);
@@ -205,6 +216,7 @@ __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& firs
 // survivor mask in the reference's loop order (i, j, lower/upper), so counts and emission order need no atomics.
 __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass) {
   __shared__ QsAxis s_qs[4][QS_MAX_AXES];
+  __shared__ HfPairCtx s_ctx[4][32];
   QsAxis* const qs_ax = s_qs[threadIdx.x >> 5];
   const int np = *A.nPairs;
   const int lane = threadIdx.x & 31;
@@ -255,39 +267,59 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       }
     }
     // ---- warp-cooperative expansion of the heightfield pairs of this warp ----
+    // every heightfield pair's own lane fetches what the warp will need (all lanes in parallel: one round of memory
+    // latency per batch instead of one per pair); pass 1 only needs the survivor mask cached by pass 0
+    HfPairCtx* const ctxs = s_ctx[threadIdx.x >> 5];
+    __syncwarp();  // the previous batch is done with the scratch
+    if (hfPair) {
+      HfPairCtx& X = ctxs[lane];
+      const bool cachedOwn = pass && (iMaxX - iMinX) * (iMaxY - iMinY) * 2 <= 64;
+      X.mask = cachedOwn ? A.pairMask[k] : 0ull;
+      if (!cachedOwn) {
+        const ShapeDev s1 = T.shapes[B.shape[first]], s2 = T.shapes[B.shape[second]];
+        X.hf = T.hfs[s2.hf];
+        X.xf = ld3(B.pos[first]); X.xs = ld3(B.pos[second]);
+        X.qs = ldq(B.quat[second]);
+        X.hullTask = code == NP_HPIL;
+        if (X.hullTask) {
+          X.hd = T.hulls[s1.hull];
+          X.qf = ldq(B.quat[first]);
+          f3 zero; zero.x = zero.y = zero.z = 0.f;
+          X.oA = to_local_point(X.xf, X.qf, zero);
+          X.rFirst = X.hd.bsr;
+        } else {
+          X.rFirst = s1.bsr;
+        }
+      }
+    }
+    __syncwarp();
     unsigned todo = __ballot_sync(0xffffffffu, hfPair);
     const int myOff = (pass && k < np) ? A.pairTaskOff[k] : 0;
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int pFirst = __shfl_sync(0xffffffffu, first, src), pSecond = __shfl_sync(0xffffffffu, second, src);
       const int pCode = __shfl_sync(0xffffffffu, code, src), pk = kb + src;
       const int x0 = __shfl_sync(0xffffffffu, iMinX, src), x1 = __shfl_sync(0xffffffffu, iMaxX, src);
       const int y0 = __shfl_sync(0xffffffffu, iMinY, src), y1 = __shfl_sync(0xffffffffu, iMaxY, src);
       const int pOff = __shfl_sync(0xffffffffu, myOff, src);
       const int wy = y1 - y0, nP = (x1 - x0) * wy * 2;
-      const ShapeDev s1 = T.shapes[B.shape[pFirst]], s2 = T.shapes[B.shape[pSecond]];
-      const HfDev hf = T.hfs[s2.hf];
-      const f3 xf = ld3(B.pos[pFirst]), xs = ld3(B.pos[pSecond]);
-      const q4 qs = ldq(B.quat[pSecond]);
+      const HfPairCtx& X = ctxs[src];
+      const HfDev hf = X.hf;
+      const f3 xf = X.xf, xs = X.xs;
+      const q4 qs = X.qs;
       const bool hullTask = pCode == NP_HPIL;
-      const double rFirst = hullTask ? T.hulls[s1.hull].bsr : s1.bsr;
+      const double rFirst = X.rFirst;
       HullDev hd;
       q4 qf;
       f3 oA;
-      if (hullTask) {
-        hd = T.hulls[s1.hull];
-        qf = ldq(B.quat[pFirst]);
-        f3 zero; zero.x = zero.y = zero.z = 0.f;
-        oA = to_local_point(xf, qf, zero);
-      }
+      if (hullTask) { hd = X.hd; qf = X.qf; oA = X.oA; }
       const bool cached = pass && nP <= 64;
-      const unsigned long long cachedMask = cached ? A.pairMask[pk] : 0ull;
+      const unsigned long long cachedMask = X.mask;
       // quick-separation axes of this pair (face 0 of the hull when it has uniqueAxes, then hull edge x heightfield z)
       const bool quick = hullTask && !cached && hd.nE <= 32 && hd.nF <= 32;
       int nAx = 0;
       if (quick) {
-        nAx = (hd.hasAxes ? 1 : 0) + hd.nE;
+        nAx = (hd.hasAxes ? 1 : 0) + hd.nEk;  // +-copies of an edge separate exactly when the first copy does
         f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
         const f3 wz = qrot(qs, up);
         __syncwarp();  // the previous pair's lanes are done with the scratch
@@ -297,7 +329,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           bool valid = true;
           if (e < 0) axis = qrot(qf, ld3(T.fnormals[hd.fOff]));
           else {
-            axis = vcross(qrot(qf, ld3(T.edges[hd.eOff + e])), wz);
+            axis = vcross(qrot(qf, ld3(T.edgesK[hd.ekOff + e])), wz);
             if (valmost_zero(axis)) valid = false;
             else vnormalize(axis);
           }
