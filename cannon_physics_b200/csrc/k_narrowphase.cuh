@@ -181,7 +181,27 @@ struct HfPairCtx {
   HfDev hf;
   HullDev hd;
   int hullTask;
+  f3 lc;          // sphere tasks: the sphere centre in the heightfield frame
+  double margin;  // and the slack of sphere_pillar_far
 };
+
+// Conservative rejection of a sphere / pillar task. sphereConvex (narrow_phase.dart:1039-1257) reports a contact only when
+// a vertex, a face point or an edge point of the pillar lies within the sphere radius of the centre, i.e. when the
+// centre is closer than R to the pillar; the pillar lies inside the box [x0,x1] x [y0,y1] x (-inf, top] of its triangle
+// in the heightfield frame. A centre farther than R + margin from that box cannot produce a contact; the margin
+// (1 % of the cell plus 1e-4 of the coordinate magnitudes) is three orders of magnitude above the f32 rounding of the
+// reference's world-frame arithmetic, so no reachable contact is ever dropped and the surviving tasks run the
+// unchanged resolver. Rejected pillars never become tasks (nine tenths of a resting sphere's window).
+__device__ __forceinline__ bool sphere_pillar_far(const f3& lc, double R, double margin, const f3& po, const f3* pv) {
+  const double ox = W(po.x), oy = W(po.y), oz = W(po.z);
+  const double x0 = fmin(fmin(W(pv[0].x), W(pv[1].x)), W(pv[2].x)) + ox, x1 = fmax(fmax(W(pv[0].x), W(pv[1].x)), W(pv[2].x)) + ox;
+  const double y0 = fmin(fmin(W(pv[0].y), W(pv[1].y)), W(pv[2].y)) + oy, y1 = fmax(fmax(W(pv[0].y), W(pv[1].y)), W(pv[2].y)) + oy;
+  const double zt = fmax(fmax(W(pv[0].z), W(pv[1].z)), W(pv[2].z)) + oz;
+  const double cx = W(lc.x), cy = W(lc.y), cz = W(lc.z);
+  const double dx = fmax(0.0, fmax(x0 - cx, cx - x1)), dy = fmax(0.0, fmax(y0 - cy, cy - y1)), dz = fmax(0.0, cz - zt);
+  const double r = R + margin;
+  return dx * dx + dy * dy + dz * dz > r * r;
+}
 
 __device__ __forceinline__ bool pillar_quick_separated_pre(const QsAxis* __restrict__ ax, int nAx, const f3* pv, const f3& xP, const q4& qP) {
   f3 zero; zero.x = zero.y = zero.z = 0.f;
@@ -289,6 +309,9 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           X.rFirst = X.hd.bsr;
         } else {
           X.rFirst = s1.bsr;
+          X.lc = to_local_point(X.xs, X.qs, X.xf);
+          X.margin = fmax(0.0, s1.radius - s1.bsr) + 0.01 * (double)X.hf.esize + 1e-4 * (fabs(W(X.xf.x)) + fabs(W(X.xf.y)) + fabs(W(X.xf.z)) + fabs(W(X.xs.x)) + fabs(W(X.xs.y)) +
+                                                         fabs(W(X.xs.z)) + fabs(W(X.lc.x)) + fabs(W(X.lc.y)) + fabs(W(X.lc.z)));
         }
       }
     }
@@ -366,6 +389,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
             for (int i = 0; i < 6; i++) pv[i] = ld3(R->v[i]);
             const f3 wpo = to_world_point(xs, qs, po);
             alive = vdist(xf, wpo) < pr + rFirst;
+            if (alive && !hullTask) alive = !sphere_pillar_far(X.lc, rFirst, X.margin, po, pv);
             if (alive && quick) alive = !pillar_quick_separated_pre(qs_ax, nAx, pv, wpo, qs);
           }
         }
