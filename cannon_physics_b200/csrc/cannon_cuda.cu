@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(256) k_pair_filter_compact(const int* __restri
 __global__ void __launch_bounds__(256) k_apply_lambda(BodyArrays B, int n, int nWorlds, const int* __restrict__ worldRows) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (worldRows[nWorlds > 1 ? B.world[i] : 0] <= 0) continue;
-    const f3 vl = vmulc(ld3(B.vlam[i]), ld3(B.linF[i]));
+    const f3 vl = vmulc(ld3(B.vlam[2 * i]), ld3(B.linF[i]));
     B.vel[i] = st3(vadd(vl, ld3(B.vel[i])));
-    const f3 wl = vmulc(ld3(B.wlam[i]), ld3(B.angF[i]));
+    const f3 wl = vmulc(ld3(B.wlam[2 * i]), ld3(B.angF[i]));
     B.angvel[i] = st3(vadd(wl, ld3(B.angvel[i])));
   }
 }
@@ -139,7 +139,7 @@ struct cannon_world {
   int nMat = 0;
 
   // device: bodies
-  DBuf<float4> pos, quat, vel, angvel, force, torque, vlam, wlam, iiw0, iiw1, iiw2, invI, linF, angF, aabbLo, aabbHi;
+  DBuf<float4> pos, quat, vel, angvel, force, torque, lam, iiw0, iiw1, iiw2, invI, linF, angF, aabbLo, aabbHi;
   DBuf<double> mass, invMass, brad, ldamp, adamp, ldpow, adpow, sleepSpeed, sleepTime, tLastSleepy;
   DBuf<int> type, sleep, shape, material, group, mask, world, flags;
   // device: shape tables
@@ -262,7 +262,7 @@ static cudaError_t upload(DBuf<T>& d, const std::vector<T>& h, cudaStream_t s) {
 static BodyArrays body_arrays(cannon_world* w) {
   BodyArrays B;
   B.pos = w->pos.p; B.quat = w->quat.p; B.vel = w->vel.p; B.angvel = w->angvel.p; B.force = w->force.p; B.torque = w->torque.p;
-  B.vlam = w->vlam.p; B.wlam = w->wlam.p; B.iiw0 = w->iiw0.p; B.iiw1 = w->iiw1.p; B.iiw2 = w->iiw2.p;
+  B.vlam = w->lam.p; B.wlam = w->lam.p ? w->lam.p + 1 : nullptr; /* interleaved: one 32-byte record per body */ B.iiw0 = w->iiw0.p; B.iiw1 = w->iiw1.p; B.iiw2 = w->iiw2.p;
   B.invI = w->invI.p; B.linF = w->linF.p; B.angF = w->angF.p; B.aabbLo = w->aabbLo.p; B.aabbHi = w->aabbHi.p;
   B.mass = w->mass.p; B.invMass = w->invMass.p; B.brad = w->brad.p; B.ldamp = w->ldamp.p; B.adamp = w->adamp.p;
   B.ldpow = w->ldpow.p; B.adpow = w->adpow.p; B.sleepSpeed = w->sleepSpeed.p; B.sleepTime = w->sleepTime.p; B.tLastSleepy = w->tLastSleepy.p;
@@ -404,7 +404,7 @@ void cannon_world_destroy(cannon_world* w) {
   cudaStreamSynchronize(w->ctx->stream);
   // DBuf members are released explicitly (plain structs, no destructors)
 #define REL(x) w->x.release()
-  REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(vlam); REL(wlam); REL(iiw0); REL(iiw1); REL(iiw2);
+  REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(lam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
   REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars);
@@ -823,7 +823,7 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
 
   W_TRY(w, upload(w->pos, pos, s)); W_TRY(w, upload(w->quat, quat, s)); W_TRY(w, upload(w->vel, vel, s));
   W_TRY(w, upload(w->angvel, angvel, s)); W_TRY(w, upload(w->force, force, s)); W_TRY(w, upload(w->torque, torque, s));
-  W_TRY(w, upload(w->vlam, zero4, s)); W_TRY(w, upload(w->wlam, zero4, s)); W_TRY(w, upload(w->aabbLo, zero4, s));
+  { std::vector<float4> zero8(2 * zero4.size(), make_float4(0.f, 0.f, 0.f, 0.f)); W_TRY(w, upload(w->lam, zero8, s)); W_TRY(w, cudaStreamSynchronize(s)); } W_TRY(w, upload(w->aabbLo, zero4, s));
   W_TRY(w, upload(w->aabbHi, zero4, s));
   W_TRY(w, upload(w->iiw0, iiw0, s)); W_TRY(w, upload(w->iiw1, iiw1, s)); W_TRY(w, upload(w->iiw2, iiw2, s));
   W_TRY(w, upload(w->invI, invI, s)); W_TRY(w, upload(w->linF, linF, s)); W_TRY(w, upload(w->angF, angF, s));

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256) k_presolve(BodyArrays B, int n) {
       B.sleep[i] = CANNON_AWAKE;  // Body.wakeUp, rigid_body.dart:263-270
       B.flags[i] = fl & ~BF_WAKE;
     }
-    B.vlam[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    B.wlam[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.vlam[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.wlam[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, c
 
     // gs_solver.dart:111-121 — only when the (body's) world had equations this step
     if (applyLambda && worldRows[P.nWorlds > 1 ? B.world[i] : 0] > 0) {
-      f3 vl = vmulc(ld3(B.vlam[i]), linF);
+      f3 vl = vmulc(ld3(B.vlam[2 * i]), linF);
       v = vadd(vl, v);
-      f3 wl = vmulc(ld3(B.wlam[i]), angF);
+      f3 wl = vmulc(ld3(B.wlam[2 * i]), angF);
       w = vadd(wl, w);
       dirtyVel = true;
     }

@@ -619,8 +619,8 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
         // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it (thousands of
         // units resting on the same static body would otherwise all hit one L2 sector)
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        f3 vA = ld3((fl & 1) ? __ldcg(&B.vlam[bi]) : z4), wA = ld3((fl & 1) ? __ldcg(&B.wlam[bi]) : z4);
-        f3 vB = ld3((fl & 2) ? __ldcg(&B.vlam[bj]) : z4), wB = ld3((fl & 2) ? __ldcg(&B.wlam[bj]) : z4);
+        f3 vA = ld3((fl & 1) ? __ldcg(&B.vlam[2 * bi]) : z4), wA = ld3((fl & 1) ? __ldcg(&B.wlam[2 * bi]) : z4);
+        f3 vB = ld3((fl & 2) ? __ldcg(&B.vlam[2 * bj]) : z4), wB = ld3((fl & 2) ? __ldcg(&B.wlam[2 * bj]) : z4);
         double acc = 0.0;
         RowData d, nx;
         load_row(R, r0, d);
@@ -646,8 +646,8 @@ __global__ void __launch_bounds__(256) k_gs(RowArrays R, BodyArrays B, UnitArray
           acc += dl > 0.0 ? dl : -dl;
           d = nx;
         }
-        if (fl & 1) { B.vlam[bi] = st3(vA); B.wlam[bi] = st3(wA); }
-        if (fl & 2) { B.vlam[bj] = st3(vB); B.wlam[bj] = st3(wB); }
+        if (fl & 1) { B.vlam[2 * bi] = st3(vA); B.wlam[2 * bi] = st3(wA); }
+        if (fl & 2) { B.vlam[2 * bj] = st3(vB); B.wlam[2 * bj] = st3(wB); }
         if (batch) atomicAdd(&G.worldTot[w], acc);
         else local += acc;
       }
@@ -742,8 +742,8 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
         }
         const float imA = (float)U.eImA[a], imB = (float)U.eImB[a];
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 vA = (fl & 1) ? __ldcg(&B.vlam[bi]) : z4, wA = (fl & 1) ? __ldcg(&B.wlam[bi]) : z4;
-        float4 vB = (fl & 2) ? __ldcg(&B.vlam[bj]) : z4, wB = (fl & 2) ? __ldcg(&B.wlam[bj]) : z4;
+        float4 vA = (fl & 1) ? __ldcg(&B.vlam[2 * bi]) : z4, wA = (fl & 1) ? __ldcg(&B.wlam[2 * bi]) : z4;
+        float4 vB = (fl & 2) ? __ldcg(&B.vlam[2 * bj]) : z4, wB = (fl & 2) ? __ldcg(&B.wlam[2 * bj]) : z4;
         float acc = 0.f;
         // rows are fetched in chunks of GS_CHUNK through the read-only path before any of them is solved: the
         // manifold's sequential chain then pays one memory round trip per chunk instead of one per row
@@ -787,8 +787,8 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
           for (int k = 0; k < GS_CHUNK; k++)
             if (rc + k < r1) R.flambda[rc + k] = cl[k];
         }
-        if (fl & 1) { B.vlam[bi] = vA; B.wlam[bi] = wA; }
-        if (fl & 2) { B.vlam[bj] = vB; B.wlam[bj] = wB; }
+        if (fl & 1) { B.vlam[2 * bi] = vA; B.wlam[2 * bi] = wA; }
+        if (fl & 2) { B.vlam[2 * bj] = vB; B.wlam[2 * bj] = wB; }
         if (batch) atomicAdd(&G.worldTot[w], (double)acc);
         else local += (double)acc;
       }
@@ -855,6 +855,18 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
 #define GS_LS_MAX 1024
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// 256-bit L2 access (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): both halves of a 32-byte body record at once
+__device__ __forceinline__ void ldcg_f8(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_f8(float4* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z),
+               "f"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ float4 lds_f4(unsigned a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
@@ -1074,8 +1086,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
             // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it (thousands
             // of units resting on the same static body would otherwise all hit one L2 sector)
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 vA = (m.fl & 1) ? __ldcg(&B.vlam[m.bi]) : z4, wA = (m.fl & 1) ? __ldcg(&B.wlam[m.bi]) : z4;
-            float4 vB = (m.fl & 2) ? __ldcg(&B.vlam[m.bj]) : z4, wB = (m.fl & 2) ? __ldcg(&B.wlam[m.bj]) : z4;
+            // vlambda and wlambda of a body are one 32-byte record: one 256-bit L2 access (one sector) per body
+            float4 vA = z4, wA = z4, vB = z4, wB = z4;
+            if (m.fl & 1) ldcg_f8(&B.vlam[2 * m.bi], vA, wA);
+            if (m.fl & 2) ldcg_f8(&B.vlam[2 * m.bj], vB, wB);
             float acc = 0.f;
             if (tr && tkg == 0) {  // trace only: when did the body lambdas of this lane arrive?
               asm volatile("" ::"f"(vA.x), "f"(wA.x), "f"(vB.x), "f"(wB.x));
@@ -1134,8 +1148,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
               }
             }
 #undef GS_ROW_UPDATE
-            if (m.fl & 1) { B.vlam[m.bi] = vA; B.wlam[m.bi] = wA; }
-            if (m.fl & 2) { B.vlam[m.bj] = vB; B.wlam[m.bj] = wB; }
+            if (m.fl & 1) st_f8(&B.vlam[2 * m.bi], vA, wA);
+            if (m.fl & 2) st_f8(&B.vlam[2 * m.bj], vB, wB);
             if (batch) atomicAdd(&G.worldTot[m.grp], (double)acc);
             else local += (double)acc;
           }
@@ -1322,8 +1336,9 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
     bulk_g2s(sUnits, U.rec + a0, (unsigned)(nU * 32), &s_mbar);
   }
   const bool sb = nB <= GW_MAXB;  // this world's vlambda / wlambda live in shared memory
-  float4* const vl = sb ? s_v : B.vlam;
+  float4* const vl = sb ? s_v : B.vlam;  // global records are interleaved (stride 2), the shared arrays are not
   float4* const wl = sb ? s_w : B.wlam;
+  const int ls = sb ? 1 : 2;
   const int boff = sb ? b0 : 0;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (sb) for (int i = tid; i < nB; i += GW_THREADS) { s_v[i] = z4; s_w[i] = z4; }
@@ -1372,8 +1387,8 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
         else { a = k; if (U.eLevel[a0 + a] != l) continue; }
         const GsUnitRec m = staged ? sUnits[a] : U.rec[a0 + a];
         if (m.r1 <= m.r0) continue;
-        float4 vA = (m.fl & 1) ? vl[m.bi - boff] : z4, wA = (m.fl & 1) ? wl[m.bi - boff] : z4;
-        float4 vB = (m.fl & 2) ? vl[m.bj - boff] : z4, wB = (m.fl & 2) ? wl[m.bj - boff] : z4;
+        float4 vA = (m.fl & 1) ? vl[ls * (m.bi - boff)] : z4, wA = (m.fl & 1) ? wl[ls * (m.bi - boff)] : z4;
+        float4 vB = (m.fl & 2) ? vl[ls * (m.bj - boff)] : z4, wB = (m.fl & 2) ? wl[ls * (m.bj - boff)] : z4;
         float acc = 0.f;
         const float4* q = rowBase + (size_t)m.r0 * 5;
         float* lp = lamBase + m.r0;
@@ -1399,8 +1414,8 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
           }
           acc += fabsf(dl);
         }
-        if (m.fl & 1) { vl[m.bi - boff] = vA; wl[m.bi - boff] = wA; }
-        if (m.fl & 2) { vl[m.bj - boff] = vB; wl[m.bj - boff] = wB; }
+        if (m.fl & 1) { vl[ls * (m.bi - boff)] = vA; wl[ls * (m.bi - boff)] = wA; }
+        if (m.fl & 2) { vl[ls * (m.bj - boff)] = vB; wl[ls * (m.bj - boff)] = wB; }
         local += (double)acc;
       }
       __syncthreads();
@@ -1414,7 +1429,7 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
     if (tot * tot < P.tol2) break;
   }
   if (sb)
-    for (int i = tid; i < nB; i += GW_THREADS) { B.vlam[b0 + i] = s_v[i]; B.wlam[b0 + i] = s_w[i]; }
+    for (int i = tid; i < nB; i += GW_THREADS) { B.vlam[2 * (b0 + i)] = s_v[i]; B.wlam[2 * (b0 + i)] = s_w[i]; }
   if (staged)
     for (int i = tid; i < nR; i += GW_THREADS) R.flambda[r0w + i] = sLam[i];
   if (tid == 0) { G.worldIters[wd] = iter; atomicMax(G.itersDone, iter); }

@@ -73,7 +73,11 @@ FUSED = {
     "c1 600 steps": (lambda: scenes.spheres_on_plane(5, 5, 5), 600, 50),
     "c2 stacks": (lambda: scenes.box_stacks(9, 6, grid=3), 120, 20),
     "c3 heightfield": (lambda: scenes.mixed_pile_on_heightfield(6, 6, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 120, 20),
-XX: (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 240, 40),
+    # 768 bodies settling on the terrain: every sphere / box / cylinder meets several pillars (pruned SAT axes, pillar
+    # table, conservative sphere-pillar rejection: all must leave pairs, contacts, rows and state bit-identical)
+    "c3 heightfield, 768 bodies": (lambda: scenes.mixed_pile_on_heightfield(16, 16, 3, hf_samples=65, solver=REF, grid_cells=(16, 4, 16)), 150, 50),
+    "c4 batch": (lambda: scenes.chain_worlds(8, chains=3, links=6), 120, 20),
+    "c5 sleeping": (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 240, 40),
     "8f joints": (lambda: scenes.constraint_zoo(groups=3), 240, 30),
 }
 
