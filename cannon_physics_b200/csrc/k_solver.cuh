@@ -279,20 +279,19 @@ __device__ __forceinline__ int coop_ctas(long long items, int perCta) {
   return (int)(q < (long long)gridDim.x ? q : (long long)gridDim.x);
 }
 
+// Monotonic-counter grid barrier: one release atomic to arrive, acquire loads of the same counter to wait (no separate
+// generation word, no stand-alone fences: the release / acquire pair at gpu scope is cumulative over the CTA's writes
+// ordered before it by the block barrier). The counter is cleared by the host before every cooperative launch.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, int nCtas) {
   __syncthreads();
   if (nCtas == 1) return;  // single-CTA launches (small worlds) only need the block barrier
   if (threadIdx.x == 0) {
     epoch += 1;
-    __threadfence();
-    const unsigned arrived = atomicAdd(bar, 1u) + 1u;
-    volatile unsigned* gen = (volatile unsigned*)(bar + 32);
-    if (arrived == epoch * (unsigned)nCtas) {
-      *gen = epoch;
-    } else {
-      while (*gen < epoch) __nanosleep(20);
-    }
-    __threadfence();
+    const unsigned target = epoch * (unsigned)nCtas;
+    unsigned v;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(bar) : "memory");
+    v += 1u;
+    while (v < target) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
   }
   __syncthreads();
 }
@@ -849,8 +848,10 @@ __global__ void __launch_bounds__(256, 2) k_gs_fast_v1(RowArrays R, BodyArrays B
 #define GS_WIN_MIN 96
 #define GS_WIN_MAX 112
 #define GS_LAM_REGS ((GS_CAP_ROWS + 31) / 32)
-#define GS_BUF_BYTES (GS_CAP_ROWS * 80 + GS_CAP_UNITS * 32)
-#define GS_WARP_BYTES (2 * GS_BUF_BYTES + GS_CAP_ROWS * 4)
+#define GS_LAM_OFF (GS_CAP_ROWS * 80 + GS_CAP_UNITS * 32)
+#define GS_LAM_BYTES ((GS_CAP_ROWS + 8) * 4)  // the lambda range is copied from a 16-byte aligned start: up to 3 + 3 floats of slack
+#define GS_BUF_BYTES (GS_LAM_OFF + GS_LAM_BYTES)
+#define GS_WARP_BYTES (2 * GS_BUF_BYTES)
 #define GS_SMEM_BYTES (GS_WARPS * GS_WARP_BYTES)
 #define GS_LS_MAX 1024
 
@@ -999,7 +1000,6 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   unsigned char* wbase = s_dyn + (size_t)wic * GS_WARP_BYTES;
-  float* slam = (float*)(wbase + 2 * GS_BUF_BYTES);
   // tasks of a colour are dealt to the warps CTA-interleaved so a narrow colour still spreads over every SM
   const int gw = wic * nCtas + blockIdx.x, nW = nCtas * GS_WARPS;
 
@@ -1015,25 +1015,25 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
     if (n.a >= 0) { n.a += nW; gs_seek(lt, nLevels, P.maxIter, gw, n); }
     return n;
   };
-  auto issue = [&](const int2& x, const int2& y, int b) -> bool {  // returns whether a copy was started
+  // unit records, rows and (withLam) the rows' lambdas of a task: three bulk copies on one mbarrier. The lambda range
+  // starts at the 16-byte boundary below the first row (bulk copies need 16-byte alignment); no register ever waits
+  // for it, so nothing of the prefetch can stall the warp before the data is used.
+  auto issue = [&](const int2& x, const int2& y, int b, bool withLam) -> bool {  // returns whether a copy was started
     const int nUs = min(y.x - x.x, GS_CAP_UNITS), nRs = min(y.y - x.y, GS_CAP_ROWS);
     if (nUs <= 0) return false;
     if (lane == 0) {
       unsigned char* dst = wbase + (size_t)b * GS_BUF_BYTES;
-      mbar_expect_tx(&s_mbar[wic][b], (unsigned)(nUs * 32 + nRs * 80));
+      // the buffer was last written with ordinary shared stores (lambdas of an earlier task): order them before the
+      // async-proxy writes of the bulk copies
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int a0 = x.y & ~3;
+      const unsigned lamBytes = (withLam && nRs > 0) ? (unsigned)(((x.y + nRs - a0 + 3) & ~3) * 4) : 0u;
+      mbar_expect_tx(&s_mbar[wic][b], (unsigned)(nUs * 32 + nRs * 80) + lamBytes);
       bulk_g2s(dst + GS_CAP_ROWS * 80, U.rec + x.x, (unsigned)(nUs * 32), &s_mbar[wic][b]);
       if (nRs > 0) bulk_g2s(dst, R.rec + (size_t)x.y * 5, (unsigned)(nRs * 80), &s_mbar[wic][b]);
+      if (lamBytes) bulk_g2s(dst + GS_LAM_OFF, R.flambda + a0, lamBytes, &s_mbar[wic][b]);
     }
     return true;
-  };
-  float lamR[GS_LAM_REGS];
-  auto lam_prefetch = [&](const int2& x, const int2& y) {
-    const int nRs = min(y.y - x.y, GS_CAP_ROWS);
-#pragma unroll
-    for (int j = 0; j < GS_LAM_REGS; j++) {
-      const int idx = j * 32 + lane;
-      lamR[j] = idx < nRs ? __ldcg(&R.flambda[x.y + idx]) : 0.f;
-    }
   };
 
   t0.a = lt[0] + gw; t0.lvl = 0; t0.it = 0;
@@ -1043,8 +1043,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
   table(t1, x1, y1);
   int buf = 0;
   unsigned parity = 0;  // bit b: phase parity of buffer b's mbarrier
-  bool pend0 = issue(x0, y0, 0), pend1 = false;
-  lam_prefetch(x0, y0);
+  bool pend0 = issue(x0, y0, 0, true), pend1 = false;
 
   int iter = 0;
   int trN = 0;
@@ -1053,20 +1052,14 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
     for (int lvl = 0; lvl < nLevels; lvl++) {
       GS_TRACE_BEGIN();
       while (t0.a >= 0 && t0.lvl == lvl && t0.it == iter) {
-        pend1 = issue(x1, y1, buf ^ 1);
+        // one task per warp and one colour: the next task is this one again, its lambdas are not written back yet
+        // (they are handed over shared -> shared after the solve instead of being fetched)
+        const bool sameNext = t1.a == t0.a;
+        pend1 = issue(x1, y1, buf ^ 1, !sameNext);
         t2 = next(t1);
         table(t2, x2, y2);
         const int u0 = x0.x, nU = y0.x - x0.x, rBase = x0.y;
         const int nUs = min(nU, GS_CAP_UNITS), nRs = min(y0.y - x0.y, GS_CAP_ROWS);
-        // lambdas of this task: prefetched registers -> shared
-#pragma unroll
-        for (int j = 0; j < GS_LAM_REGS; j++) {
-          const int idx = j * 32 + lane;
-          if (idx < nRs) slam[idx] = lamR[j];
-        }
-        __syncwarp();
-        const bool sameNext = t1.a == t0.a;  // one task per warp and one colour: its lambdas are not written back yet
-        if (!sameNext) lam_prefetch(x1, y1);
         long long tk0 = 0, tk1 = 0, tk2 = 0, tkg = 0;
         const bool tr = P.trace && wic == 0 && iter == 1 && lvl == 0;
         if (tr) tk0 = clock64();
@@ -1075,6 +1068,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
         const unsigned char* sb = wbase + (size_t)buf * GS_BUF_BYTES;
         const float4* srows = (const float4*)sb;
         const GsUnitRec* sunits = (const GsUnitRec*)(sb + GS_CAP_ROWS * 80);
+        float* const slam = (float*)(wbase + (size_t)buf * GS_BUF_BYTES + GS_LAM_OFF) + (rBase & 3);
         int flushEnd = nRs;
         if (!P.debugSkipWork) {
           for (int u = lane; u < nU; u += 32) {
@@ -1162,8 +1156,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
           const int idx = j * 32 + lane;
           if (idx < flushEnd) R.flambda[rBase + idx] = slam[idx];
         }
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // a later bulk copy (async proxy) reads these lambdas back
+        if (sameNext) {
+          float* const nlam = (float*)(wbase + (size_t)(buf ^ 1) * GS_BUF_BYTES + GS_LAM_OFF) + (rBase & 3);
+#pragma unroll
+          for (int j = 0; j < GS_LAM_REGS; j++) {
+            const int idx = j * 32 + lane;
+            if (idx < nRs) nlam[idx] = slam[idx];
+          }
+        }
         __syncwarp();
-        if (sameNext) lam_prefetch(x1, y1);
         if (tr && lane == 0 && trN < 4) {
           long long* o = P.trace + (size_t)gridDim.x * GS_TRACE_PHASES * 2 + (blockIdx.x * 4 + trN) * 4;
           o[0] = tk1 - tk0; o[1] = tk2 - tk1; o[2] = tkg - tk1; o[3] = nU * 1000 + nRs;
