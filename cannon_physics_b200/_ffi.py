@@ -148,6 +148,8 @@ PROTOTYPES = {
     "cannon_world_step": (c_i32, [VP, c_f64, c_i32]),
     "cannon_world_profile": (c_i32, [VP, P(Profile)]),
     "cannon_world_get_contacts": (c_i32, [VP, P(ContactsSoA), P(c_i32)]),
+    "cannon_world_enable_contact_events": (c_i32, [VP, c_i32]),
+    "cannon_world_get_contact_events": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32)]),
     "cannon_world_get_rows": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_i32), P(c_f64), P(c_f64), P(c_f64), P(c_i32)]),
     "cannon_world_update_bodies": (c_i32, [VP, c_i32, c_i32, P(c_f32), P(c_f32), P(c_f32), P(c_f32), P(c_f32), P(c_f32)]),
 }

@@ -427,6 +427,8 @@ class World:  # lib/world/world_class.dart:44
         self._dev: Optional[DeviceWorld] = None
         self._structure_dirty = True
         self._state_dirty = False
+        self._listeners = {}
+        self._events_on = False
 
     # world_class.dart:282-300 / 224-231 / 343-348
     def addBody(self, body: Body):
@@ -524,6 +526,8 @@ class World:  # lib/world/world_class.dart:44
                 self._dev.close()
             self._dev = DeviceWorld(self._lib, self._spec(), device=self._device)
             self._dev.set_time(self.time)
+            if self._events_on:
+                self._dev.enable_contact_events(True)
             self._structure_dirty = False
             self._state_dirty = False
         elif self._state_dirty:
@@ -532,6 +536,33 @@ class World:  # lib/world/world_class.dart:44
             self._dev.update_bodies(0, n, position=st("position"), quaternion=st("quaternion"), velocity=st("velocity"),
                                     angular_velocity=st("angularVelocity"), force=st("force"), torque=st("torque"))
             self._state_dirty = False
+
+    # EventTarget (lib/utils/event_target.dart) for the world-level contact events of world_class.dart:703-730
+    def addEventListener(self, type: str, listener):
+        """``beginContact`` / ``endContact``: ``listener(event)`` with ``event = {"type", "bodyA", "bodyB"}`` (bodyA is
+        the body with the smaller index, like OverlapKeeper's unpacked key), dispatched after the step that changed the
+        contact state. Listening switches the device-side pair-set tracking on from the next step."""
+        if type not in ("beginContact", "endContact"):
+            raise CannonError(F.E_UNSUPPORTED, f"event '{type}' is outside the hot-path scope (world-level contact events only)")
+        self._listeners.setdefault(type, []).append(listener)
+        if self._dev is not None and not self._events_on:
+            self._dev.enable_contact_events(True)
+        self._events_on = True
+
+    def hasAnyEventListener(self, type: str) -> bool:
+        return bool(self._listeners.get(type))
+
+    def removeEventListener(self, type: str, listener):
+        if listener in self._listeners.get(type, []):
+            self._listeners[type].remove(listener)
+
+    def _emit_contact_events(self):
+        begin, end = self._dev.get_contact_events()
+        for type, pairs in (("beginContact", begin), ("endContact", end)):  # additions first (world_class.dart:710-727)
+            for a, b in pairs:
+                ev = {"type": type, "bodyA": self.bodies[int(a)], "bodyB": self.bodies[int(b)]}
+                for fn in list(self._listeners.get(type, [])):
+                    fn(ev)
 
     def markDirty(self):
         """Call after writing body vectors in place (``body.position[:] = ...``) between steps."""
@@ -542,7 +573,14 @@ class World:  # lib/world/world_class.dart:44
         if timeSinceLastCalled is not None:
             raise CannonError(F.E_UNSUPPORTED, "interpolated stepping is host-side glue outside the hot-path scope")
         self._ensure_uploaded()
-        self._dev.step(dt, nsteps)
+        if self._events_on and nsteps > 1:  # listeners hear every step, like the reference's synchronous dispatch
+            for _ in range(nsteps):
+                self._dev.step(dt, 1)
+                self._emit_contact_events()
+        else:
+            self._dev.step(dt, nsteps)
+            if self._events_on:
+                self._emit_contact_events()
         self.dt = dt
         self.time, self.stepnumber = self._dev.get_time()
         if sync:

@@ -179,6 +179,12 @@ struct cannon_world {
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
   DBuf<float4> rRec;
   DBuf<GsUnitRec> uRec;
+  // contact events (opt-in)
+  bool evEnabled = false;
+  int evCap = 0;
+  unsigned evMask = 0;
+  DBuf<unsigned long long> evKeysCur, evKeysPrev, evTabCur, evTabPrev, evBegin, evEnd;
+  DBuf<int> evCnt;
   DBuf<int> eLevel, orderW, worldCount, worldUnitStart, lenBins;
   DBuf<int2> gsTab;
   DBuf<int> gsLvlTask, gsLvlWin;
@@ -417,7 +423,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(spBodyA); REL(spBodyB); REL(spOff); REL(spIdx); REL(spRest); REL(spK); REL(spD); REL(spAnchorA); REL(spAnchorB); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
@@ -1257,6 +1263,43 @@ __global__ void __launch_bounds__(256) k_zero_tail(int* eRows, const int* nUnits
   if (threadIdx.x == 0 && blockIdx.x == 0) { const int n = *nUnits; if (n <= cap) eRows[n] = 0; }
 }
 
+static EvArrays ev_arrays(cannon_world* w) {
+  EvArrays E;
+  E.keysCur = w->evKeysCur.p; E.keysPrev = w->evKeysPrev.p; E.tabCur = w->evTabCur.p; E.tabPrev = w->evTabPrev.p;
+  E.begin = w->evBegin.p; E.end = w->evEnd.p; E.cnt = w->evCnt.p; E.mask = w->evMask; E.cap = w->evCap;
+  return E;
+}
+// (re)allocates the event buffers for the current pair capacity and starts from an empty previous set
+static int32_t ensure_events(cannon_world* w) {
+  if (!w->evEnabled || (w->evCap == w->pairCap && w->evCap > 0)) return CANNON_OK;
+  if (w->pairCap <= 0) return CANNON_OK;  // no bodies yet: allocated on the first step
+  drop_step_graph(w);
+  cudaStream_t s = w->ctx->stream;
+  const size_t cap = (size_t)w->pairCap;
+  size_t tab = 1024;
+  while (tab < 2 * cap) tab <<= 1;
+  W_TRY(w, w->evKeysCur.reserve(cap)); W_TRY(w, w->evKeysPrev.reserve(cap)); W_TRY(w, w->evBegin.reserve(cap)); W_TRY(w, w->evEnd.reserve(cap));
+  W_TRY(w, w->evTabCur.reserve(tab)); W_TRY(w, w->evTabPrev.reserve(tab)); W_TRY(w, w->evCnt.reserve(8));
+  w->evCap = (int)cap; w->evMask = (unsigned)(tab - 1);
+  W_TRY(w, cudaMemsetAsync(w->evTabPrev.p, 0xff, tab * sizeof(unsigned long long), s));
+  W_TRY(w, cudaMemsetAsync(w->evCnt.p, 0, 8 * sizeof(int), s));
+  return CANNON_OK;
+}
+// World.emitContactEvents (world_class.dart:610,703-730) from the pairs that own contacts after the narrowphase
+static int32_t st_contact_events(cannon_world* w) {
+  if (!w->evEnabled || w->evCap <= 0) return CANNON_OK;
+  cudaStream_t s = w->ctx->stream;
+  const EvArrays E = ev_arrays(w);
+  const size_t tabBytes = ((size_t)w->evMask + 1) * sizeof(unsigned long long);
+  W_TRY(w, cudaMemsetAsync(E.tabCur, 0xff, tabBytes, s));
+  { g_kernel_launches++; k_ev_begin<<<1, 32, 0, s>>>(E); }
+  { g_kernel_launches++; k_ev_collect<<<grid_for(w, w->pairCap, 256), 256, 0, s>>>(np_arrays(w), E); }
+  { g_kernel_launches++; k_ev_diff<<<grid_for(w, 2LL * w->pairCap, 256), 256, 0, s>>>(E); }
+  { g_kernel_launches++; k_ev_roll<<<grid_for(w, w->pairCap, 256), 256, 0, s>>>(E); }
+  W_TRY(w, cudaMemcpyAsync(E.tabPrev, E.tabCur, tabBytes, cudaMemcpyDeviceToDevice, s));
+  return CANNON_OK;
+}
+
 // world_class.dart:539-645 without the final velocity update (k_integrate / k_apply_lambda do that)
 static int32_t st_solve(cannon_world* w, double dt) {
   cudaStream_t s = w->ctx->stream;
@@ -1267,6 +1310,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   JointArrays J = joint_arrays(w);
   int* cnt = w->cnt.p;
   const int nW = w->desc.n_worlds;
+  { const int32_t rcEv = st_contact_events(w); if (rcEv != CANNON_OK) return rcEv; }
   SolveParams P;
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
   P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
@@ -1544,6 +1588,7 @@ int32_t cannon_solver_solve(cannon_world* w, double dt, int32_t* iterations_done
   cudaSetDevice(w->ctx->device);
   cudaStream_t s = w->ctx->stream;
   int32_t rc;
+  if ((rc = ensure_events(w)) != CANNON_OK) return rc;
   // keep the pair/task/contact counts of the preceding narrowphase call, clear the solver's
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_NROWS, 0, sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->cnt.p + CT_FRICTOTAL, 0, (CT_GS_NTASKS + 1 - CT_FRICTOTAL) * sizeof(int), s));
@@ -1610,6 +1655,7 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   cudaStream_t s = w->ctx->stream;
   int32_t rc;
   if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
+  if ((rc = ensure_events(w)) != CANNON_OK) return rc;
   w->dt = dt;
   const bool wantGraph = !w->graphBroken && !getenv("CANNON_NO_GRAPH") && !getenv("CANNON_GS_TRACE");
   cudaEventRecord(w->ev[8], s);
@@ -1691,6 +1737,38 @@ int32_t cannon_world_profile(cannon_world* w, cannon_profile* out) {
   if (!w || !out) return CANNON_E_INVALID;
   w->prof.kernel_launches = g_kernel_launches;
   *out = w->prof;
+  return CANNON_OK;
+}
+
+int32_t cannon_world_enable_contact_events(cannon_world* w, int32_t enable) {
+  if (!w) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  drop_step_graph(w);  // the captured step does or does not contain the event kernels
+  w->evEnabled = enable != 0;
+  w->evCap = 0;        // (re)start from an empty previous set
+  return ensure_events(w);
+}
+
+int32_t cannon_world_get_contact_events(cannon_world* w, int32_t cap, int32_t* n_begin, int32_t* begin_a, int32_t* begin_b, int32_t* n_end,
+                                        int32_t* end_a, int32_t* end_b) {
+  if (!w || cap < 0 || !n_begin || !n_end) return CANNON_E_INVALID;
+  if (!w->evEnabled) return fail(w->ctx, CANNON_E_INVALID, "contact events are not enabled");
+  cudaSetDevice(w->ctx->device);
+  *n_begin = 0; *n_end = 0;
+  if (w->evCap <= 0) return CANNON_OK;
+  int c[8];
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  W_TRY(w, cudaMemcpy(c, w->evCnt.p, sizeof c, cudaMemcpyDeviceToHost));
+  if (c[0] > w->evCap || c[2] > w->evCap || c[3] > w->evCap) return fail(w->ctx, CANNON_E_CAPACITY, "contact pair capacity exceeded (set cannon_world_desc.max_pairs)");
+  *n_begin = c[2]; *n_end = c[3];
+  if (c[2] > cap || c[3] > cap) return fail(w->ctx, CANNON_E_CAPACITY, "contact event arrays too small");
+  std::vector<unsigned long long> kb(c[2]), ke(c[3]);
+  if (c[2]) W_TRY(w, cudaMemcpy(kb.data(), w->evBegin.p, kb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (c[3]) W_TRY(w, cudaMemcpy(ke.data(), w->evEnd.p, ke.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::sort(kb.begin(), kb.end());  // OverlapKeeper.getDiff walks its sorted key lists
+  std::sort(ke.begin(), ke.end());
+  for (int k = 0; k < c[2]; k++) { if (begin_a) begin_a[k] = (int32_t)(kb[k] >> 32); if (begin_b) begin_b[k] = (int32_t)(kb[k] & 0xffffffffull); }
+  for (int k = 0; k < c[3]; k++) { if (end_a) end_a[k] = (int32_t)(ke[k] >> 32); if (end_b) end_b[k] = (int32_t)(ke[k] & 0xffffffffull); }
   return CANNON_OK;
 }
 

@@ -1189,3 +1189,66 @@ __global__ void __launch_bounds__(256) k_np_per_pair(NpArrays A, int* __restrict
     perPair[k] = s;
   }
 }
+
+// ---- contact events ---------------------------------------------------------------------
+// bodyOverlapKeeper (overlap_keeper.dart) as two open-addressing hash sets of 64-bit body-pair keys: the pairs that own
+// at least one ContactEquation this step (world_class.dart:606) are inserted into the current set, the difference
+// against the previous step's set in both directions gives beginContact / endContact (getDiff, overlap_keeper.dart:48-82).
+// The lists leave the device unordered; cannon_world_get_contact_events sorts the few events by key on the host.
+#define EV_EMPTY 0xffffffffffffffffull
+struct EvArrays {
+  unsigned long long *keysCur, *keysPrev, *tabCur, *tabPrev, *begin, *end;
+  int* cnt;  // [0] pairs in contact now, [1] in the previous step, [2] begin events, [3] end events
+  unsigned mask;
+  int cap;
+};
+__device__ __forceinline__ unsigned ev_hash(unsigned long long k, unsigned mask) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+  return (unsigned)k & mask;
+}
+__device__ __forceinline__ bool ev_find(const unsigned long long* __restrict__ tab, unsigned mask, unsigned long long key) {
+  for (unsigned h = ev_hash(key, mask);; h = (h + 1) & mask) {
+    const unsigned long long v = tab[h];
+    if (v == key) return true;
+    if (v == EV_EMPTY) return false;
+  }
+}
+__global__ void k_ev_begin(EvArrays E) { if (threadIdx.x == 0) { E.cnt[0] = 0; E.cnt[2] = 0; E.cnt[3] = 0; } }
+__global__ void __launch_bounds__(256) k_ev_collect(NpArrays A, EvArrays E) {
+  const int np = *A.nPairs, nt = min(*A.nTasks, A.taskCap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const int t0 = A.pairTaskOff[k], t1 = min(t0 + A.pairTasks[k], nt);
+    bool any = false;
+    for (int t = t0; t < t1 && !any; t++) any = A.taskCnt[t] > 0;
+    if (!any) continue;
+    const int a = A.p1[k], b = A.p2[k];
+    const unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned long long)(unsigned)max(a, b);
+    for (unsigned h = ev_hash(key, E.mask);; h = (h + 1) & E.mask) {
+      const unsigned long long prev = atomicCAS(&E.tabCur[h], EV_EMPTY, key);
+      if (prev == EV_EMPTY) {  // first insertion of this pair (OverlapKeeper.set ignores duplicates)
+        const int idx = atomicAdd(&E.cnt[0], 1);
+        if (idx < E.cap) E.keysCur[idx] = key;
+        break;
+      }
+      if (prev == key) break;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_ev_diff(EvArrays E) {
+  const int nCur = min(E.cnt[0], E.cap), nPrev = min(E.cnt[1], E.cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nCur + nPrev; i += gridDim.x * blockDim.x) {
+    if (i < nCur) {
+      const unsigned long long key = E.keysCur[i];
+      if (!ev_find(E.tabPrev, E.mask, key)) { const int o = atomicAdd(&E.cnt[2], 1); if (o < E.cap) E.begin[o] = key; }
+    } else {
+      const unsigned long long key = E.keysPrev[i - nCur];
+      if (!ev_find(E.tabCur, E.mask, key)) { const int o = atomicAdd(&E.cnt[3], 1); if (o < E.cap) E.end[o] = key; }
+    }
+  }
+}
+// OverlapKeeper.tick for the next step: current becomes previous (the tables are copied by the host code)
+__global__ void __launch_bounds__(256) k_ev_roll(EvArrays E) {
+  const int nCur = min(E.cnt[0], E.cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nCur; i += gridDim.x * blockDim.x) E.keysPrev[i] = E.keysCur[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) E.cnt[1] = nCur;
+}

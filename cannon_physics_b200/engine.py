@@ -323,6 +323,26 @@ class DeviceWorld:
         self._chk(self.lib.cannon_world_get_contacts(self.handle, C.byref(soa), C.byref(n)))
         return {k: v[: n.value].copy() for k, v in bufs.items()}
 
+    # ---- contact events (world_class.dart:703-730 over overlap_keeper.dart) -------------------------
+    def enable_contact_events(self, enable: bool = True):
+        self._chk(self.lib.cannon_world_enable_contact_events(self.handle, 1 if enable else 0))
+
+    def get_contact_events(self):
+        """(begin, end): int32 arrays of shape (n, 2) with the body pairs (a < b, ascending) whose contact began /
+        ended in the last step."""
+        nb, ne = F.c_i32(), F.c_i32()
+        cap = 256
+        while True:
+            ba, bb = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            ea, eb = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+            code = self.lib.cannon_world_get_contact_events(self.handle, cap, C.byref(nb), F.ptr(ba, F.c_i32), F.ptr(bb, F.c_i32),
+                                                            C.byref(ne), F.ptr(ea, F.c_i32), F.ptr(eb, F.c_i32))
+            if code == F.E_CAPACITY and max(nb.value, ne.value) > cap:
+                cap = max(nb.value, ne.value)
+                continue
+            self._chk(code)
+            return (np.stack([ba[: nb.value], bb[: nb.value]], axis=1), np.stack([ea[: ne.value], eb[: ne.value]], axis=1))
+
     def get_rows(self):
         n = F.c_i32()
         code = self.lib.cannon_world_get_rows(self.handle, 0, C.byref(n), None, None, None, None, None, None)

@@ -298,6 +298,19 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps);
 int32_t cannon_world_profile(cannon_world* w, cannon_profile* out);
 /* World.contacts of the last step */
 int32_t cannon_world_get_contacts(cannon_world* w, cannon_contacts_soa* out, int32_t* n_contacts);
+/* Contact events of the last step: World.emitContactEvents (lib/world/world_class.dart:703-730)
+ * over bodyOverlapKeeper (lib/collision/overlap_keeper.dart:20-96, filled per contact at world_class.dart:606, ticked at
+ * :219). Tracking is off until enabled; enabling starts from an empty "previous" set, like a new World. After a step,
+ * begin_* lists the body pairs that have a ContactEquation now and had none in the previous step (`beginContact`),
+ * end_* the pairs that lost theirs (`endContact`); a < b inside a pair and pairs ascend by (a, b) - the order of
+ * OverlapKeeper.getDiff, whose key (i << 16) | j is injective below 65536 bodies (64-bit keys are used here).
+ * With one shape per body `beginShapeContact` / `endShapeContact` (:732-769) are the same lists. The reference's
+ * `collide` event fires for every contact of every step as written (collisionMatrixPrevious aliases collisionMatrix,
+ * world_class.dart:213-217,595): it is cannon_world_get_contacts. A multi-step call keeps the events of its last step.
+ * cap = capacity of each of the four arrays; CANNON_E_CAPACITY reports the needed size through n_begin / n_end. */
+int32_t cannon_world_enable_contact_events(cannon_world* w, int32_t enable);
+int32_t cannon_world_get_contact_events(cannon_world* w, int32_t cap, int32_t* n_begin, int32_t* begin_a, int32_t* begin_b,
+                                        int32_t* n_end, int32_t* end_a, int32_t* end_b);
 /* solver rows of the last solve, in solve order: debug / parity only. Arrays of `cap` entries (any may be NULL) */
 int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int32_t* body_i, int32_t* body_j,
                               double* B, double* invC, double* lambda, int32_t* level);

@@ -555,6 +555,27 @@ int32_t cannon_world_get_contacts(cannon_world* cw, cannon_contacts_soa* out, in
   return export_contacts(cw, out, n_contacts);
 }
 
+int32_t cannon_world_enable_contact_events(cannon_world* cw, int32_t enable) {
+  if (!cw) return CANNON_E_INVALID;
+  World& w = cw->w;
+  w.trackOverlaps = enable != 0;
+  w.overlapCurrent.clear(); w.overlapPrevious.clear(); w.additions.clear(); w.removals.clear();
+  return CANNON_OK;
+}
+
+int32_t cannon_world_get_contact_events(cannon_world* cw, int32_t cap, int32_t* n_begin, int32_t* begin_a, int32_t* begin_b, int32_t* n_end,
+                                        int32_t* end_a, int32_t* end_b) {
+  if (!cw || cap < 0 || !n_begin || !n_end) return CANNON_E_INVALID;
+  const World& w = cw->w;
+  if (!w.trackOverlaps) return fail(cw->ctx, CANNON_E_INVALID, "contact events are not enabled");
+  const int nb = (int)w.additions.size() / 2, ne = (int)w.removals.size() / 2;
+  *n_begin = nb; *n_end = ne;
+  if (nb > cap || ne > cap) return fail(cw->ctx, CANNON_E_CAPACITY, "contact event arrays too small");
+  for (int k = 0; k < nb; k++) { if (begin_a) begin_a[k] = w.additions[2 * k]; if (begin_b) begin_b[k] = w.additions[2 * k + 1]; }
+  for (int k = 0; k < ne; k++) { if (end_a) end_a[k] = w.removals[2 * k]; if (end_b) end_b[k] = w.removals[2 * k + 1]; }
+  return CANNON_OK;
+}
+
 int32_t cannon_world_get_rows(cannon_world* cw, int32_t cap, int32_t* n_rows, int32_t* body_i, int32_t* body_j, double* B, double* invC,
                               double* lambda, int32_t* level) {
   if (!cw) return CANNON_E_INVALID;

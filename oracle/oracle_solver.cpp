@@ -171,10 +171,47 @@ int gsSolve(World& w, std::vector<Eq*>& eqs, const std::vector<int>& bodyIdx, do
 
 // world_class.dart:543-624: per-contact restitution override (idempotent with createContactEquation's
 // rule because shape materials are out of scope), wake-up flags, then wake flagged bodies
+// OverlapKeeper.set (overlap_keeper.dart:20-37): insertion into the sorted key list, duplicates ignored. The reference
+// key is (i << 16) | j with i < j; 32 bits per id keep it injective beyond 65535 bodies with the same order below.
+void World::overlapSet(int i, int j) {
+  if (j < i) { const int t = j; j = i; i = t; }
+  const int64_t key = ((int64_t)i << 32) | (int64_t)j;
+  size_t index = 0;
+  while (index < overlapCurrent.size() && key > overlapCurrent[index]) index++;
+  if (index < overlapCurrent.size() && key == overlapCurrent[index]) return;
+  overlapCurrent.insert(overlapCurrent.begin() + (long)index, key);
+}
+
+// OverlapKeeper.getDiff (overlap_keeper.dart:48-82): keys of this step missing from the previous one, then the reverse
+void World::emitContactEvents() {
+  additions.clear();
+  removals.clear();
+  const std::vector<int64_t>&a = overlapCurrent, &b = overlapPrevious;
+  size_t j = 0;
+  for (size_t i = 0; i < a.size(); i++) {
+    const int64_t keyA = a[i];
+    while (j < b.size() && keyA > b[j]) j++;
+    const bool found = j < b.size() && keyA == b[j];
+    if (!found) { additions.push_back((int)(keyA >> 32)); additions.push_back((int)(keyA & 0xffffffffll)); }
+  }
+  j = 0;
+  for (size_t i = 0; i < b.size(); i++) {
+    const int64_t keyB = b[i];
+    while (j < a.size() && keyB > a[j]) j++;
+    const bool found = j < a.size() && a[j] == keyB;
+    if (!found) { removals.push_back((int)(keyB >> 32)); removals.push_back((int)(keyB & 0xffffffffll)); }
+  }
+}
+
 void World::makeContactConstraints() {
+  if (trackOverlaps) {  // collisionMatrixTick, world_class.dart:219 (bodyOverlapKeeper.tick, overlap_keeper.dart:40-45)
+    overlapCurrent.swap(overlapPrevious);
+    overlapCurrent.clear();
+  }
   for (Eq& c : contacts) {
     Body& bi = bodies[c.bi];
     Body& bj = bodies[c.bj];
+    if (trackOverlaps) overlapSet(c.bi, c.bj);  // world_class.dart:606
     if (bi.material >= 0 && bj.material >= 0) {
       if (matRestitution[bi.material] >= 0 && matRestitution[bj.material] >= 0)
         c.restitution = matRestitution[bi.material] * matRestitution[bj.material];
@@ -192,6 +229,7 @@ void World::makeContactConstraints() {
       if (speedSquaredA >= speedLimitSquaredA * 2) bj.wakeUpAfterNarrowphase = true;
     }
   }
+  if (trackOverlaps) emitContactEvents();  // world_class.dart:610
   for (Body& b : bodies) {
     if (b.wakeUpAfterNarrowphase) {
       b.sleepState = CANNON_AWAKE;

@@ -135,6 +135,12 @@ struct World {
   std::vector<RowDebug> rows;
   cannon_profile prof{};
   std::string err;
+  // OverlapKeeper of body ids (overlap_keeper.dart): sorted key lists of this and the previous step + the last diff
+  bool trackOverlaps = false;
+  std::vector<int64_t> overlapCurrent, overlapPrevious;
+  std::vector<int> additions, removals;  // flat (a, b) pairs, a < b, like OverlapKeeper._unpackAndPush
+  void overlapSet(int i, int j);         // OverlapKeeper.set, overlap_keeper.dart:20-37
+  void emitContactEvents();              // OverlapKeeper.getDiff, overlap_keeper.dart:48-82 (world_class.dart:703-708)
 
   const cannon_contact_material* contactMaterial(int ma, int mb) const;
   void updateAABB(Body& b) const;

@@ -120,3 +120,42 @@ def test_box_box_stack_contacts(oracle_lib):
     c = w.narrowphase_contacts(p1, p2)
     assert c["per_pair_count"].tolist() == [4]
     assert np.all(np.abs(c["ni"][:, 1]) == 1.0)
+
+
+def _events_world(lib):
+    """Two spheres over a plane: body 0 = plane, 1 = sphere resting just above it, 2 = sphere dropped on sphere 1."""
+    from cannon_physics_b200.scenes import GROUND_QUAT
+    b = {"position": np.array([[0, 0, 0], [0, 0.6, 0], [0, 2.5, 0]], np.float32),
+         "quaternion": np.array([GROUND_QUAT, [0, 0, 0, 1], [0, 0, 0, 1]], np.float32),
+         "mass": np.array([0.0, 1.0, 1.0]), "shape": np.array([0, 1, 1], np.int32),
+         "type": np.array([F.BODY_STATIC, F.BODY_DYNAMIC, F.BODY_DYNAMIC], np.int32)}
+    shapes = [dict(type=F.SHAPE_PLANE), dict(type=F.SHAPE_SPHERE, radius=0.5)]
+    return engine.DeviceWorld(lib, SceneSpec(desc=dict(gravity=(0, -10, 0)), shapes=shapes, bodies=b, n_bodies=3))
+
+
+def test_contact_events_follow_overlap_keeper(oracle_lib):
+    # world_class.dart:606,703-730 + overlap_keeper.dart: a pair is announced once when its first ContactEquation
+    # appears, stays silent while it keeps one, and is announced again (endContact) in the step that has none
+    w = _events_world(oracle_lib)
+    w.enable_contact_events(True)
+    seen_begin, seen_end, in_contact = [], [], set()
+    for step in range(90):
+        w.step(1 / 60)
+        begin, end = w.get_contact_events()
+        c = w.get_contacts()
+        now = {(min(int(a), int(b)), max(int(a), int(b))) for a, b in zip(c["body_i"], c["body_j"])}
+        assert {tuple(p) for p in begin.tolist()} == now - in_contact, step
+        assert {tuple(p) for p in end.tolist()} == in_contact - now, step
+        assert begin.tolist() == sorted(begin.tolist()) and end.tolist() == sorted(end.tolist())
+        assert all(a < b for a, b in begin.tolist() + end.tolist())
+        in_contact = now
+        seen_begin += [tuple(p) for p in begin.tolist()]
+        seen_end += [tuple(p) for p in end.tolist()]
+    assert (0, 1) in seen_begin and (1, 2) in seen_begin  # sphere 1 lands on the plane, sphere 2 lands on sphere 1
+    # re-enabling starts from an empty previous set: everything in contact is announced again
+    w.enable_contact_events(True)
+    w.step(1 / 60)
+    begin, end = w.get_contact_events()
+    assert {tuple(p) for p in begin.tolist()} == {(min(int(a), int(b)), max(int(a), int(b))) for a, b in
+                                                   zip(w.get_contacts()["body_i"], w.get_contacts()["body_j"])}
+    assert len(end) == 0

@@ -272,3 +272,47 @@ def test_batch_colored_world_kernel_equals_grid_sweep(cuda_lib):
     # converge either), so only sanity is asserted against it: the chains hold together and stay near their anchors
     pa = a.get_bodies(("position", "velocity"))
     assert np.all(np.isfinite(pa["position"])) and np.abs(pa["position"]).max() < 20 and np.abs(pa["velocity"]).max() < 30
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["spheres bouncing on a plane", "mixed pile on heightfield", "jointed chains (batch)"])
+def test_contact_events_match_the_overlap_keeper(cuda_lib, oracle_lib, name):
+    """beginContact / endContact lists (world_class.dart:703-730, overlap_keeper.dart) from the device
+    pair sets equal the oracle's sorted-list OverlapKeeper, step by step, in the same order."""
+    mk = {"spheres bouncing on a plane": lambda: _with(scenes.spheres_on_plane(5, 5, 4, spacing=0.55), default_contact_material=dict(restitution=0.6)),
+          "mixed pile on heightfield": lambda: scenes.mixed_pile_on_heightfield(8, 8, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)),
+          "jointed chains (batch)": lambda: scenes.chain_worlds(4, chains=3, links=6)}[name]
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, mk())
+    dev.enable_contact_events(True)
+    ref.enable_contact_events(True)
+    n_begin = n_end = 0
+    for s in range(150):
+        dev.step(1 / 60)
+        ref.step(1 / 60)
+        (ba, ea), (bb, eb) = dev.get_contact_events(), ref.get_contact_events()
+        assert np.array_equal(ba, bb) and np.array_equal(ea, eb), f"{name}: events differ at step {s}"
+        n_begin += len(ba)
+        n_end += len(ea)
+    assert n_begin > 0 and n_end > 0, (n_begin, n_end)
+    parity.assert_same_state(dev, ref, name)
+    # a multi-step call keeps the events of its last step
+    dev.step(1 / 60, 3)
+    ref.step(1 / 60, 3)
+    (ba, ea), (bb, eb) = dev.get_contact_events(), ref.get_contact_events()
+    assert np.array_equal(ba, bb) and np.array_equal(ea, eb)
+
+
+@pytest.mark.gpu
+def test_world_api_dispatches_contact_events(cuda_lib):
+    from cannon_physics_b200 import api
+    world = api.World(gravity=(0, -10, 0), _lib=cuda_lib)
+    ground = api.Body(mass=0, shape=api.Plane())
+    ground.quaternion[:] = scenes.GROUND_QUAT
+    ball = api.Body(mass=1, shape=api.Sphere(0.5), position=(0, 1.0, 0))
+    world.addBody(ground)
+    world.addBody(ball)
+    heard = []
+    world.addEventListener("beginContact", lambda e: heard.append((e["type"], e["bodyA"] is ground, e["bodyB"] is ball)))
+    for _ in range(60):
+        world.step(1 / 60)
+    assert heard and heard[0] == ("beginContact", True, True)
