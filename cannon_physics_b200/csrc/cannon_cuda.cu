@@ -28,7 +28,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -235,6 +235,7 @@ struct cannon_world {
   bool graphBroken = false;        // capture failed once: stay eager
   int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0;
   bool gsFastV1 = false;  // CANNON_GS_FAST_V1: the unstaged colored sweep, kept for A/B measurements
+  bool gwNoRing = false;     // CANNON_GW_NO_RING: batches always take the staged CTA-per-world kernel (A/B measurements)
   bool gsNoLenSort = false;  // CANNON_GS_NO_LEN_SORT: leave the units of a colour in schedule order (A/B measurements)
   // resolver kernels of different types are independent: they run on side streams between two events
   cudaStream_t npStream[3] = {nullptr, nullptr, nullptr};
@@ -398,6 +399,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
   w->gsNoLenSort = getenv("CANNON_GS_NO_LEN_SORT") != nullptr;
+  w->gwNoRing = getenv("CANNON_GW_NO_RING") != nullptr;
   *out = w;
   return CANNON_OK;
 }
@@ -718,7 +720,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   w->unitCap = unitCap;
   RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
-  RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * (w->desc.n_worlds + 2)); RES(worldUnitStart, w->desc.n_worlds + 2);
+  RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * ((size_t)w->desc.n_worlds * GR_LV + 4)); RES(worldUnitStart, (size_t)w->desc.n_worlds * GR_LV + 4);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
   RES(claim, n + 1);
   const int nW = w->desc.n_worlds;
@@ -1371,11 +1373,13 @@ static int32_t st_solve(cannon_world* w, double dt) {
   const bool perWorld = P.colored && nW > 1 && !w->gsFastV1 && !getenv("CANNON_GS_NO_WORLD_KERNEL");
   const int* order = w->order.p;
   if (perWorld) {
+    // (world, colour) bins: units - hence rows - of a world are contiguous colour by colour
+    const int nBins = nW * GR_LV + 1;
     int* wc = w->worldCount.p;
-    W_TRY(w, cudaMemsetAsync(wc, 0, 2 * (nW + 2) * sizeof(int), s));
-    { g_kernel_launches++; k_world_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, wc); }
-    W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nW + 1, nW + 1, nullptr, w->scanTmp, s));
-    { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->world.p, w->worldUnitStart.p, wc + nW + 2, w->orderW.p); }
+    W_TRY(w, cudaMemsetAsync(wc, 0, 2 * (size_t)(nBins + 1) * sizeof(int), s));
+    { g_kernel_launches++; k_world_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->world.p, wc); }
+    W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nBins, nBins, nullptr, w->scanTmp, s));
+    { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->world.p, w->worldUnitStart.p, wc + nBins + 1, w->orderW.p); }
     order = w->orderW.p;
   } else if (P.colored && !w->gsFastV1 && !w->gsNoLenSort) {
     // homogeneous windows for k_gs_fast: units of a colour ordered by row count (k_solver.cuh, k_len_*)
@@ -1407,7 +1411,15 @@ static int32_t st_solve(cannon_world* w, double dt) {
     if (perWorld) {
       const int* wus = w->worldUnitStart.p;
       const int* wbs = w->worldStart.p;
-      k_gs_world<<<nW, GW_THREADS, GW_SMEM_BYTES, s>>>(R, B, U, S, P, G, wus, wbs);
+      // small worlds (the RL / parameter-sweep case) take the warp-per-world ring kernel; if one world of the batch
+      // does not fit its shared tables the staged CTA-per-world kernel does the whole batch (decided on the device)
+      int* ringOk = cnt + CT_RING_OK;
+      { g_kernel_launches++; k_set_int<<<1, 32, 0, s>>>(ringOk, w->gwNoRing ? 0 : 1); }
+      if (!w->gwNoRing) {
+        { g_kernel_launches++; k_world_ring_check<<<grid_for(w, nW, 256), 256, 0, s>>>(U, wus, wbs, nW, cnt + CT_NLEVELS, ringOk); }
+        { g_kernel_launches++; k_gs_world_ring<<<nW, 32, 0, s>>>(R, B, U, P, G, wus, wbs, ringOk); }
+      }
+      k_gs_world<<<nW, GW_THREADS, GW_SMEM_BYTES, s>>>(R, B, U, S, P, G, wus, wbs, ringOk);
     } else if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
     else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
     else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));

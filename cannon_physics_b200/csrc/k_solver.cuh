@@ -24,7 +24,7 @@
 enum { ROW_CONTACT = 0, ROW_FRICTION = 1, ROW_ROT = 2, ROW_MOTOR = 3 };
 // Constraint.update() flavours of a joint equation
 enum { JM_P2P = 0, JM_HINGE_ROT = 1, JM_MOTOR = 2, JM_DISTANCE = 3, JM_DIRECT_ROT = 4 };
-enum { SRC_NORMAL = 0, SRC_FRIC1 = 1, SRC_FRIC2 = 2, SRC_JOINT = 3, SRC_TASK = 4 };
+enum { SRC_NORMAL = 0, SRC_FRIC1 = 1, SRC_FRIC2 = 2, SRC_JOINT = 3, SRC_TASK = 4, SRC_JOINTS = 5 };
 
 // rows in execution order (SoA; float4 vectors so a row is five 128-bit + six 64-bit transactions)
 struct RowArrays {
@@ -255,7 +255,18 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
   }
   for (int s = tid; s < J.nAccepted; s += nth) {
     const int e = J.slotEq[s];
-    put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
+    if (S.colored) {
+      // all accepted equations of one constraint (3 for a point-to-point joint, 5-6 for a hinge ...) act on the same two
+      // bodies: one unit at the first of them, swept row after row like a contact manifold - a joint costs one colour
+      // instead of one per equation. The other slots keep their unit ids but own no rows (they leave the schedule).
+      const int f = J.first[e];
+      const bool head = s == 0 || J.first[J.slotEq[s - 1]] != f;
+      int rows = 0;
+      if (head) { rows = 1; while (s + rows < J.nAccepted && J.first[J.slotEq[s + rows]] == f) rows++; }
+      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], rows, s * 8 + SRC_JOINTS, nWorlds, worldRows);
+    } else {
+      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
+    }
   }
 }
 
@@ -531,6 +542,8 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
     load_row_body(B, U.eBj[a], Bd);
     if (kind == SRC_JOINT) {
       build_joint_row(R, row, B, J, idx, A, Bd, h);
+    } else if (kind == SRC_JOINTS) {  // COLORED: the accepted equations of one constraint, slots idx .. idx + rows - 1
+      for (int k = 0; k < U.eRows[a]; k++) build_joint_row(R, row + k, B, J, J.slotEq[idx + k], A, Bd, h);
     } else if (kind == SRC_TASK) {
       const int c0 = S.taskOff[idx], c1 = c0 + S.taskCnt[idx];
       for (int c = c0; c < c1; c++) {
@@ -1231,18 +1244,25 @@ __global__ void __launch_bounds__(GS_THREADS, 1) k_gs_fast(RowArrays R, BodyArra
 #define GW_MAXU 2048   // units of a world sorted by colour in shared memory (larger worlds scan their unit range per colour)
 #define GW_MAXL 256
 
-__global__ void __launch_bounds__(256) k_world_count(UnitArrays U, const int* __restrict__ order, const int* __restrict__ bodyWorld,
-                                                     int* __restrict__ worldCount) {
-  const int n = min(*U.nExec, U.unitCap);
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) atomicAdd(&worldCount[bodyWorld[U.uBi[order[a]]]], 1);
-}
-
-__global__ void __launch_bounds__(256) k_world_fill(UnitArrays U, const int* __restrict__ order, const int* __restrict__ bodyWorld,
-                                                    const int* __restrict__ worldStart, int* __restrict__ worldCursor, int* __restrict__ orderW) {
+// Execution order of a colored batch: grouped by world, by colour inside a world (counting sort over nW * GR_LV bins), so
+// a world's units - and, because rows are built in execution order, its rows - are contiguous colour by colour.
+#define GR_LV 32  // colours with their own bin; a batch with more colours takes the staged kernel, which re-sorts by colour
+__global__ void __launch_bounds__(256) k_world_count(UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel,
+                                                     const int* __restrict__ bodyWorld, int* __restrict__ binCount) {
   const int n = min(*U.nExec, U.unitCap);
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-    const int u = order[a], wd = bodyWorld[U.uBi[u]];
-    orderW[worldStart[wd] + atomicAdd(&worldCursor[wd], 1)] = u;
+    const int u = order[a];
+    atomicAdd(&binCount[bodyWorld[U.uBi[u]] * GR_LV + min(unitLevel[u], GR_LV - 1)], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_world_fill(UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel,
+                                                    const int* __restrict__ bodyWorld, const int* __restrict__ binStart, int* __restrict__ binCursor,
+                                                    int* __restrict__ orderW) {
+  const int n = min(*U.nExec, U.unitCap);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    const int u = order[a], bin = bodyWorld[U.uBi[u]] * GR_LV + min(unitLevel[u], GR_LV - 1);
+    orderW[binStart[bin] + atomicAdd(&binCursor[bin], 1)] = u;
   }
 }
 
@@ -1311,7 +1331,7 @@ __global__ void __launch_bounds__(256) k_len_fill(UnitArrays U, const int* __res
 #define GW_SMEM_BYTES (GW_ROWS_CAP * 80 + GW_UNITS_CAP * 32 + GW_ROWS_CAP * 4)
 
 __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G,
-                                                         const int* __restrict__ worldStart, const int* __restrict__ worldBody) {
+                                                         const int* __restrict__ worldStart, const int* __restrict__ worldBody, const int* __restrict__ ringOk) {
   extern __shared__ __align__(128) unsigned char s_dyn[];  // rows | unit records | lambdas of this world
   __shared__ float4 s_v[GW_MAXB], s_w[GW_MAXB];
   __shared__ unsigned short s_idx[GW_MAXU];
@@ -1319,8 +1339,9 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
   __shared__ double s_red[GW_THREADS / 32];
   __shared__ unsigned long long s_mbar;
   __shared__ int s_flag;
+  if (ringOk && *ringOk) return;  // every world fits k_gs_world_ring: that kernel does the batch
   const int wd = blockIdx.x, tid = threadIdx.x;
-  const int a0 = worldStart[wd], nU = worldStart[wd + 1] - a0;
+  const int a0 = worldStart[(size_t)wd * GR_LV], nU = worldStart[(size_t)(wd + 1) * GR_LV] - a0;
   if (nU <= 0) return;
   const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
   const int r0w = U.eRowBase[a0], nR = U.eRowBase[a0 + nU] - r0w;
@@ -1435,4 +1456,152 @@ __global__ void __launch_bounds__(GW_THREADS) k_gs_world(RowArrays R, BodyArrays
   if (staged)
     for (int i = tid; i < nR; i += GW_THREADS) R.flambda[r0w + i] = sLam[i];
   if (tid == 0) { G.worldIters[wd] = iter; atomicMax(G.itersDone, iter); }
+}
+
+// ---- batches of small worlds, ring variant: one WARP per world, rows streamed colour by colour ----------------------
+// The staged kernel keeps a whole world's rows in shared memory (2 worlds per SM) and is bound by the serial chain of a
+// world: 180 colour phases x the longest unit, 14 waves of worlds. Here only what is reused lives in shared memory for
+// the whole solve (unit records, row lambdas, body lambdas: ~11 KB); the rows of one colour are contiguous (the order
+// above), so the warp copies them global -> shared with cp.async three colours ahead of the sweep into a four-slot
+// ring. 9 worlds share an SM, the copies hide the DRAM latency, a phase costs only its own arithmetic.
+#define GR_MAXB 96
+#define GR_MAXU 160
+#define GR_MAXR 704
+#define GR_SLOTS 4
+#define GR_SLOT_ROWS 40
+#define GR_MAXSEG 96  // segments (runs of units of one colour that fit a ring slot) per world
+#define GR_AHEAD (GR_SLOTS - 1)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// ringOk = every world of the batch fits the shared tables of k_gs_world_ring
+__global__ void __launch_bounds__(256) k_world_ring_check(UnitArrays U, const int* __restrict__ binStart, const int* __restrict__ worldBody, int nW,
+                                                          const int* __restrict__ nLevels, int* __restrict__ ringOk) {
+  if (*nLevels > GR_LV && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(ringOk, 0);
+  for (int wd = blockIdx.x * blockDim.x + threadIdx.x; wd < nW; wd += gridDim.x * blockDim.x) {
+    const int* bs = binStart + (size_t)wd * GR_LV;
+    const int a0 = bs[0], nU = bs[GR_LV] - a0;
+    bool ok = nU <= GR_MAXU && worldBody[wd + 1] - worldBody[wd] <= GR_MAXB && U.eRowBase[a0 + nU] - U.eRowBase[a0] <= GR_MAXR;
+    // the segmentation k_gs_world_ring will build: runs of units of one colour with at most GR_SLOT_ROWS rows
+    int ns = 0;
+    for (int l = 0, u = a0; l < GR_LV && ok; l++) {
+      const int ue = bs[l + 1];
+      while (u < ue && ok) {
+        const int rows0 = U.eRowBase[u];
+        if (U.eRowBase[u + 1] - rows0 > GR_SLOT_ROWS) ok = false;  // a single unit larger than a ring slot
+        while (u < ue && U.eRowBase[u + 1] - rows0 <= GR_SLOT_ROWS) u++;
+        ns++;
+      }
+    }
+    if (!ok || ns > GR_MAXSEG) atomicExch(ringOk, 0);
+  }
+}
+
+__global__ void __launch_bounds__(32) k_gs_world_ring(RowArrays R, BodyArrays B, UnitArrays U, SolveParams P, GsStats G,
+                                                      const int* __restrict__ binStart, const int* __restrict__ worldBody,
+                                                      const int* __restrict__ ringOk) {
+  if (!*ringOk) return;
+  __shared__ __align__(16) float4 s_vw[GR_MAXB * 2];
+  __shared__ __align__(16) GsUnitRec s_units[GR_MAXU];
+  __shared__ __align__(16) float4 s_ring[GR_SLOTS][GR_SLOT_ROWS * 5];
+  __shared__ float s_lam[GR_MAXR];
+  __shared__ int s_cs[GR_LV + 1];
+  __shared__ unsigned char s_seg[GR_MAXSEG + 1];  // first unit of every segment (GR_MAXU <= 255)
+  const int wd = blockIdx.x, lane = threadIdx.x;
+  const int* bs = binStart + (size_t)wd * GR_LV;
+  const int a0 = bs[0], nU = bs[GR_LV] - a0;
+  if (nU <= 0) return;
+  const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
+  const int r0w = U.eRowBase[a0], nR = U.eRowBase[a0 + nU] - r0w;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i <= GR_LV; i += 32) s_cs[i] = bs[i] - a0;
+  for (int i = lane; i < 2 * nB; i += 32) s_vw[i] = z4;
+  for (int i = lane; i < nR; i += 32) s_lam[i] = 0.f;  // k_rows_build left every lambda at zero
+  for (int i = lane; i < nU; i += 32) s_units[i] = U.rec[a0 + i];
+  __syncwarp();
+  // segments: runs of consecutive units of one colour whose rows fit a ring slot (units of a colour are independent,
+  // and a single warp walks the segments in order, so colour boundaries need no more than the per-segment __syncwarp)
+  if (lane == 0) {
+    int ns = 0;
+    for (int l = 0, u = 0; l < GR_LV; l++) {
+      const int ue = s_cs[l + 1];
+      while (u < ue) {
+        const int rows0 = s_units[u].r0;
+        s_seg[ns++] = (unsigned char)u;
+        while (u < ue && s_units[u].r1 - rows0 <= GR_SLOT_ROWS) u++;
+      }
+    }
+    s_seg[ns] = (unsigned char)nU;
+    s_cs[0] = ns;  // s_cs is not needed any more
+  }
+  __syncwarp();
+  const int nSeg = s_cs[0];
+  const int nPhases = nSeg * P.maxIter;
+  auto issue = [&](int p) {  // rows of phase p's segment -> ring slot p % GR_SLOTS (an empty group keeps the count uniform)
+    if (p < nPhases) {
+      const int k = p % nSeg;
+      const int rlo = s_units[s_seg[k]].r0, rhi = s_units[s_seg[k + 1] - 1].r1;
+      const float4* src = R.rec + (size_t)rlo * 5;
+      float4* dst = s_ring[p % GR_SLOTS];
+      const int n16 = (rhi - rlo) * 5;
+      for (int i = lane; i < n16; i += 32) cp_async16(dst + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int p = 0; p < GR_AHEAD; p++) issue(p);
+  int iter = 0, p = 0;
+  for (; iter != P.maxIter; iter++) {
+    float local = 0.f;
+    for (int k = 0; k < nSeg; k++, p++) {
+      issue(p + GR_AHEAD);
+      asm volatile("cp.async.wait_group %0;" ::"n"(GR_AHEAD) : "memory");
+      __syncwarp();
+      const float4* rows = s_ring[p % GR_SLOTS];
+      const int u0 = s_seg[k], u1 = s_seg[k + 1];
+      const int rlo = s_units[u0].r0;
+      for (int u = u0 + lane; u < u1; u += 32) {
+        const GsUnitRec m = s_units[u];
+        if (m.r1 <= m.r0) continue;
+        const int ia = 2 * (m.bi - b0), ib = 2 * (m.bj - b0);
+        float4 vA = (m.fl & 1) ? s_vw[ia] : z4, wA = (m.fl & 1) ? s_vw[ia + 1] : z4;
+        float4 vB = (m.fl & 2) ? s_vw[ib] : z4, wB = (m.fl & 2) ? s_vw[ib + 1] : z4;
+        const float4* q = rows + (size_t)(m.r0 - rlo) * 5;
+        float* lp = s_lam + (m.r0 - r0w);
+        float acc = 0.f;
+        for (int r = m.r0; r < m.r1; r++, q += 5, lp++) {
+          const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+          const float lam = *lp;
+          float gw_ = dot3f(q0, vB.x - vA.x, vB.y - vA.y, vB.z - vA.z);
+          gw_ += dot3f(q1, wA.x, wA.y, wA.z);
+          gw_ += dot3f(q2, wB.x, wB.y, wB.z);
+          float dl = q1.w * (q0.w - gw_ - q2.w * lam);
+          if (lam + dl < q3.w) dl = q3.w - lam;
+          else if (lam + dl > q4.w) dl = q4.w - lam;
+          *lp = lam + dl;
+          if (m.fl & 1) {
+            const float sA = -m.imA * dl;
+            vA.x = fmaf(sA, q0.x, vA.x); vA.y = fmaf(sA, q0.y, vA.y); vA.z = fmaf(sA, q0.z, vA.z);
+            wA.x = fmaf(dl, q3.x, wA.x); wA.y = fmaf(dl, q3.y, wA.y); wA.z = fmaf(dl, q3.z, wA.z);
+          }
+          if (m.fl & 2) {
+            const float sB = m.imB * dl;
+            vB.x = fmaf(sB, q0.x, vB.x); vB.y = fmaf(sB, q0.y, vB.y); vB.z = fmaf(sB, q0.z, vB.z);
+            wB.x = fmaf(dl, q4.x, wB.x); wB.y = fmaf(dl, q4.y, wB.y); wB.z = fmaf(dl, q4.z, wB.z);
+          }
+          acc += fabsf(dl);
+        }
+        if (m.fl & 1) { s_vw[ia] = vA; s_vw[ia + 1] = wA; }
+        if (m.fl & 2) { s_vw[ib] = vB; s_vw[ib + 1] = wB; }
+        local += acc;
+      }
+      __syncwarp();
+    }
+    double tot = (double)local;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (tot * tot < P.tol2) break;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  for (int i = lane; i < 2 * nB; i += 32) B.vlam[2 * b0 + i] = s_vw[i];
+  for (int i = lane; i < nR; i += 32) R.flambda[r0w + i] = s_lam[i];
+  if (lane == 0) { G.worldIters[wd] = iter; atomicMax(G.itersDone, iter); }
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-1 result table: one bench line per BASELINE configuration (run on the GPU box through gpurun).
 set -x
-OUT=gpurun_out/table_r1.jsonl
+OUT=gpurun_out/${1:-table_r1}.jsonl
 : > $OUT
 python bench.py --config c1 --solver reference --steps 600 --warmup 20 --no-e2e | tail -1 >> $OUT
 python bench.py --config c1 --solver colored --steps 600 --warmup 20 --no-e2e --no-cpu-baseline | tail -1 >> $OUT
