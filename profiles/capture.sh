@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 python bench.py --steps 200 --warmup 20 > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err
-ncu --metrics gpu__time_duration.sum --clock-control none -s 15300 -c 150 --csv --log-file gpurun_out/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 15900 -c 160 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_gs_fast --launch-skip 215 --launch-count 1 -f -o gpurun_out/${TAG}_k_gs_fast \
     python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_gs.log 2>&1
