@@ -82,6 +82,10 @@ typedef _PairsC = Int32 Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, 
 typedef _PairsD = int Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, int, Pointer<Int32>);
 typedef _ContactsC = Int32 Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, Int32, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>);
 typedef _ContactsD = int Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, int, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>);
+typedef _EventsEnableC = Int32 Function(Pointer<Void>, Int32);
+typedef _EventsEnableD = int Function(Pointer<Void>, int);
+typedef _EventsGetC = Int32 Function(Pointer<Void>, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>);
+typedef _EventsGetD = int Function(Pointer<Void>, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>);
 typedef _SolveC = Int32 Function(Pointer<Void>, Double, Pointer<Int32>);
 typedef _SolveD = int Function(Pointer<Void>, double, Pointer<Int32>);
 
@@ -97,6 +101,8 @@ class CannonCuda {
   late final _PairsD broadphasePairs = lib.lookupFunction<_PairsC, _PairsD>('cannon_broadphase_pairs');
   late final _ContactsD narrowphaseContacts = lib.lookupFunction<_ContactsC, _ContactsD>('cannon_narrowphase_contacts');
   late final _SolveD solverSolve = lib.lookupFunction<_SolveC, _SolveD>('cannon_solver_solve');
+  late final _EventsEnableD enableContactEvents = lib.lookupFunction<_EventsEnableC, _EventsEnableD>('cannon_world_enable_contact_events');
+  late final _EventsGetD getContactEvents = lib.lookupFunction<_EventsGetC, _EventsGetD>('cannon_world_get_contact_events');
   late final Pointer<Utf8> Function(Pointer<Void>) lastError =
       lib.lookupFunction<Pointer<Utf8> Function(Pointer<Void>), Pointer<Utf8> Function(Pointer<Void>)>('cannon_last_error');
   CannonCuda([String path = 'libcannon_cuda.so']) : lib = DynamicLibrary.open(path);

@@ -27,6 +27,32 @@ class CudaWorld extends World {
     if (rc != 0) throw cuda.lastError(_ctx).toDartString(); // the reference throws strings
     // poses are downloaded lazily: cannon_world_get_bodies fills position/quaternion views on demand
     stepnumber += 1;
+    if (hasAnyEventListener('beginContact') || hasAnyEventListener('endContact')) _emitContactEvents();
+  }
+
+  // World.emitContactEvents (world_class.dart:703-730) from the device-side pair-set difference instead of OverlapKeeper
+  bool _eventsOn = false;
+  void _emitContactEvents() {
+    if (!_eventsOn) { cuda.enableContactEvents(_world, 1); _eventsOn = true; return; } // tracking starts with the next step
+    final cap = 4096;
+    final nb = calloc<Int32>(), ne = calloc<Int32>();
+    final ba = calloc<Int32>(cap), bb = calloc<Int32>(cap), ea = calloc<Int32>(cap), eb = calloc<Int32>(cap);
+    try {
+      final rc = cuda.getContactEvents(_world, cap, nb, ba, bb, ne, ea, eb);
+      if (rc != 0) throw cuda.lastError(_ctx).toDartString();
+      for (var k = 0; k < nb.value; k++) {
+        beginContactEvent.bodyA = bodies[ba[k]];
+        beginContactEvent.bodyB = bodies[bb[k]];
+        dispatchEvent(beginContactEvent);
+      }
+      for (var k = 0; k < ne.value; k++) {
+        endContactEvent.bodyA = bodies[ea[k]];
+        endContactEvent.bodyB = bodies[eb[k]];
+        dispatchEvent(endContactEvent);
+      }
+    } finally {
+      for (final p in [nb, ne, ba, bb, ea, eb]) { calloc.free(p); }
+    }
   }
 }
 
