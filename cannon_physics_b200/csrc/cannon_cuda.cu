@@ -154,6 +154,7 @@ struct cannon_world {
   DBuf<cannon_contact_material> dCms;
   // device: broadphase
   DBuf<int4> cellc, smeta, scell;
+  DBuf<int> nbCache;
   DBuf<int> binLo, binHi, cellStart, cellEnd, bigList, bigWorldStart, worldStart, bpCounts, bpOffs;
   DBuf<uint32_t> skey, sval, sapKey, sapList;
   DBuf<float4> spos;
@@ -417,7 +418,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
   REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
-  REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
+  REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
   REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairMask); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
   REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
@@ -845,7 +846,7 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   W_TRY(w, upload(w->bigList, w->hBig, s)); W_TRY(w, upload(w->bigWorldStart, w->hBigWorldStart, s));
   W_TRY(w, upload(w->worldStart, w->hWorldStart, s));
   const size_t nn = (size_t)std::max(n, 1);
-  W_TRY(w, w->cellc.reserve(nn)); W_TRY(w, w->smeta.reserve(nn)); W_TRY(w, w->scell.reserve(nn)); W_TRY(w, w->binLo.reserve(nn));
+  W_TRY(w, w->nbCache.reserve((size_t)nn * BP_CACHE + 4)); W_TRY(w, w->cellc.reserve(nn)); W_TRY(w, w->smeta.reserve(nn)); W_TRY(w, w->scell.reserve(nn)); W_TRY(w, w->binLo.reserve(nn));
   W_TRY(w, w->binHi.reserve(nn)); W_TRY(w, w->skey.reserve(nn)); W_TRY(w, w->sval.reserve(nn)); W_TRY(w, w->sapKey.reserve(nn));
   W_TRY(w, w->sapList.reserve(nn)); W_TRY(w, w->spos.reserve(nn)); W_TRY(w, w->srad.reserve(nn)); W_TRY(w, w->bpCounts.reserve(nn));
   W_TRY(w, w->bpOffs.reserve(nn)); W_TRY(w, w->cellStart.reserve((size_t)H + 2)); W_TRY(w, w->cellEnd.reserve((size_t)H + 2));
@@ -1084,6 +1085,7 @@ static BpParams bp_params(cannon_world* w) {
 }
 static BpArrays bp_arrays(cannon_world* w) {
   BpArrays A;
+  A.nbCache = getenv("CANNON_BP_NO_CACHE") ? nullptr : w->nbCache.p;
   A.cellc = w->cellc.p; A.binLo = w->binLo.p; A.binHi = w->binHi.p; A.skey = w->skey.p; A.sval = w->sval.p;
   A.cellStart = w->cellStart.p; A.cellEnd = w->cellEnd.p; A.spos = w->spos.p; A.srad = w->srad.p; A.smeta = w->smeta.p; A.scell = w->scell.p;
   A.bigList = w->bigList.p; A.bigWorldStart = w->bigWorldStart.p; A.worldStart = w->worldStart.p; A.counts = w->bpCounts.p; A.offs = w->bpOffs.p;

@@ -31,6 +31,7 @@ struct BpParams {
 };
 
 struct BpArrays {
+  int* nbCache;         // [n * BP_CACHE] partners found by the counting pass of k_bp_small, indexed by bucket position
   // per body
   int4* cellc;          // (cx,cy,cz,world) of small bodies
   int* binLo;           // packed 10:10:10 GridBroadphase bin range
@@ -200,14 +201,17 @@ __device__ __forceinline__ bool bp_test(const BodyArrays& B, const BpParams& P, 
   return true;
 }
 
+#define BP_CACHE 16  // partners remembered by the counting pass (per body, global scratch): the emit pass of a body with
+                     // at most this many partners sorts and writes them without walking its 27 cells again
 struct NbState {
-  int mode;   // 0 count, 1 collect into buf, 2 select the smallest j > last
+  int mode;   // 0 count, 1 collect into buf, 2 select the smallest j > last, 3 count + remember the first BP_CACHE
   int count;
   int last, best;
   int* buf;
 };
 __device__ __forceinline__ void nb_accept(NbState& S, int j) {
   if (S.mode == 0) S.count++;
+  else if (S.mode == 3) { if (S.count < BP_CACHE) S.buf[S.count] = j; S.count++; }
   else if (S.mode == 1) { if (S.count < BP_MAXNB) S.buf[S.count] = j; S.count++; }
   else if (j > S.last && j < S.best) S.best = j;
 }
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(128) k_bp_small(BodyArrays B, BpParams P, BpAr
     const int4 c = A.scell[k];
     NbState S;
     if (pass == 0) {
-      S.mode = 0; S.count = 0; S.buf = nullptr;
+      S.mode = A.nbCache ? 3 : 0; S.count = 0; S.buf = A.nbCache ? A.nbCache + (size_t)k * BP_CACHE : nullptr;
       bp_enum_small(B, P, A, s, c, S);
       A.counts[i] = S.count;
       continue;
@@ -269,7 +273,25 @@ __global__ void __launch_bounds__(128) k_bp_small(BodyArrays B, BpParams P, BpAr
     if (cnt == 0) continue;
     const int off = A.offs[i];
     if (off + cnt > cap) { atomicMax(overflow, off + cnt); continue; }
-    if (cnt <= BP_MAXNB) {
+    if (cnt <= BP_CACHE && A.nbCache) {
+      int buf[BP_CACHE];
+      const int4* src = (const int4*)(A.nbCache + (size_t)k * BP_CACHE);
+#pragma unroll
+      for (int q = 0; q < BP_CACHE / 4; q++) {
+        const int4 v = src[q];
+        buf[4 * q] = v.x; buf[4 * q + 1] = v.y; buf[4 * q + 2] = v.z; buf[4 * q + 3] = v.w;
+      }
+      // rank sort by j (partners are distinct): no data-dependent indexing, the buffer stays in registers
+#pragma unroll
+      for (int a = 0; a < BP_CACHE; a++) {
+        if (a < cnt) {
+          int rank = 0;
+#pragma unroll
+          for (int b = 0; b < BP_CACHE; b++) rank += (b < cnt && buf[b] < buf[a]) ? 1 : 0;
+          p1[off + rank] = i; p2[off + rank] = buf[a];
+        }
+      }
+    } else if (cnt <= BP_MAXNB) {
       int buf[BP_MAXNB];
       S.mode = 1; S.count = 0; S.buf = buf;
       bp_enum_small(B, P, A, s, c, S);
