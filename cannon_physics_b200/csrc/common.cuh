@@ -252,8 +252,7 @@ static inline cudaError_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, int n
   if ((e = t.k2.reserve(n)) != cudaSuccess) return e;
   if ((e = t.v2.reserve(n)) != cudaSuccess) return e;
   if ((e = t.hist.reserve((size_t)256 * n_tiles)) != cudaSuccess) return e;
-  int passes = (bits + 7) / 8;
-  if (passes & 1) passes++;  // even number of passes so the result lands in the caller's buffers
+  const int passes = (bits + 7) / 8;  // an odd number of passes ends in the scratch buffers: copied back below
   uint32_t *ki = keys, *vi = vals, *ko = t.k2.p, *vo = t.v2.p;
   for (int p = 0; p < passes; p++) {
     const int shift = 8 * p;
@@ -263,6 +262,10 @@ static inline cudaError_t radix_sort_pairs(uint32_t* keys, uint32_t* vals, int n
     g_kernel_launches += 2;
     uint32_t* tk = ki; ki = ko; ko = tk;
     uint32_t* tv = vi; vi = vo; vo = tv;
+  }
+  if (passes & 1) {  // two small device copies are cheaper than a fourth pass (five launches)
+    if ((e = cudaMemcpyAsync(keys, ki, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(vals, vi, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }
