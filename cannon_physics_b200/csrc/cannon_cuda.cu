@@ -378,7 +378,13 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   memset(w->hAcc, 0, AC_COUNT * sizeof(long long));
   cudaMemsetAsync(w->acc.p, 0, AC_COUNT * sizeof(long long), ctx->stream);
   for (auto& e : w->ev) cudaEventCreate(&e);
-  for (auto& st : w->npStream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  {
+    // the hull / heightfield-pillar SAT kernel (npStream[1]) is the longest resolver: its CTAs get the SMs first, the
+    // shorter resolvers on the other streams fill in behind it
+    int prLo = 0, prHi = 0;
+    cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    for (int k = 0; k < 3; k++) cudaStreamCreateWithPriority(&w->npStream[k], cudaStreamNonBlocking, k == 1 ? prHi : prLo);
+  }
   cudaEventCreateWithFlags(&w->npFork, cudaEventDisableTiming);
   for (auto& e : w->npJoin) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   // empty tables so kernels always get valid pointers
@@ -1191,16 +1197,18 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   // fork: the heavy SAT kernels go to side streams, the cheap analytic resolvers stay on the main stream
   cudaStream_t s1 = w->npStream[0], s2 = w->npStream[1], s3 = w->npStream[2];
   W_TRY(w, cudaEventRecord(w->npFork, s));
-  W_TRY(w, cudaStreamWaitEvent(s1, w->npFork, 0));
-  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
-  if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
-  W_TRY(w, cudaEventRecord(w->npJoin[0], s1));
   const bool hf = !w->hHfs.empty();
   if (hf) {
     W_TRY(w, cudaStreamWaitEvent(s2, w->npFork, 0));
     { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP); }
     if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
     W_TRY(w, cudaEventRecord(w->npJoin[1], s2));
+  }
+  W_TRY(w, cudaStreamWaitEvent(s1, w->npFork, 0));
+  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
+  W_TRY(w, cudaEventRecord(w->npJoin[0], s1));
+  if (hf) {
     W_TRY(w, cudaStreamWaitEvent(s3, w->npFork, 0));
     { g_kernel_launches++; k_np_sphere_pillar<<<g * 2, 64, 0, s3>>>(B, T, A); }
     W_TRY(w, cudaEventRecord(w->npJoin[2], s3));
