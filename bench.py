@@ -247,7 +247,7 @@ def main():
     achieved = alg_bytes / (gs_ms / 1000.0) / 1e9 if gs_ms > 0 else 0.0
     from cannon_physics_b200 import _ffi as _F
     colored = spec.desc.get("solver_kind") == _F.SOLVER_COLORED
-    gs_kernel = ("k_gs_world" if spec.desc.get("n_worlds", 1) > 1 else "k_gs_fast") if colored else "k_gs"
+    gs_kernel = ("k_gs_world_ring" if spec.desc.get("n_worlds", 1) > 1 else "k_gs_fast") if colored else "k_gs"
     # the ncu DRAM figure in profiles/ncu_traffic.json was captured for k_gs_fast on the default workload only
     roofline = {"bound": "hbm", "kernel": gs_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic() if (gs_kernel == "k_gs_fast" and args.config == "c3" and args.scale == 1.0) else None,

@@ -1551,7 +1551,7 @@ __global__ void __launch_bounds__(32) k_gs_world_ring(RowArrays R, BodyArrays B,
   for (int p = 0; p < GR_AHEAD; p++) issue(p);
   int iter = 0, p = 0;
   for (; iter != P.maxIter; iter++) {
-    float local = 0.f;
+    double local = 0.0;  // same accumulation as k_gs_world: float inside a unit, double across units
     for (int k = 0; k < nSeg; k++, p++) {
       issue(p + GR_AHEAD);
       asm volatile("cp.async.wait_group %0;" ::"n"(GR_AHEAD) : "memory");
@@ -1592,11 +1592,11 @@ __global__ void __launch_bounds__(32) k_gs_world_ring(RowArrays R, BodyArrays B,
         }
         if (m.fl & 1) { s_vw[ia] = vA; s_vw[ia + 1] = wA; }
         if (m.fl & 2) { s_vw[ib] = vB; s_vw[ib + 1] = wB; }
-        local += acc;
+        local += (double)acc;
       }
       __syncwarp();
     }
-    double tot = (double)local;
+    double tot = local;
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (tot * tot < P.tol2) break;
   }
