@@ -249,14 +249,22 @@ def test_graph_replay_equals_eager_launches(cuda_lib, name):
 
 
 @pytest.mark.gpu
-def test_batch_colored_world_kernel_equals_grid_sweep(cuda_lib):
-    """A colored batch is swept by one CTA per world (k_gs_world); the grid-wide staged sweep over the same colours must
-    give the same bits: units of one colour touch disjoint bodies, so the order inside a colour cannot matter."""
+@pytest.mark.parametrize("variant", ["ring (warp per world)", "staged (CANNON_GW_NO_RING)", "staged fallback: a world too big for the ring"])
+def test_batch_colored_world_kernel_equals_grid_sweep(cuda_lib, variant):
+    """A colored batch is swept world by world (k_gs_world_ring: one warp per world, or k_gs_world: one CTA per world when
+    the device-side check finds a world that does not fit the ring's tables); the grid-wide staged sweep over the same
+    colours must give the same bits: units of one colour touch disjoint bodies, so the order inside a colour cannot matter."""
+    big = variant.startswith("staged fallback")
     def mk():
-        spec = scenes.chain_worlds(40, chains=2, links=6)
+        spec = scenes.chain_worlds(6, chains=12, links=9) if big else scenes.chain_worlds(40, chains=2, links=6)  # 109 > 96 bodies
         spec.desc["solver_kind"] = F.SOLVER_COLORED
         return spec
-    a = engine.DeviceWorld(cuda_lib, mk())
+    if "NO_RING" in variant:
+        os.environ["CANNON_GW_NO_RING"] = "1"  # read when the world is created
+    try:
+        a = engine.DeviceWorld(cuda_lib, mk())
+    finally:
+        os.environ.pop("CANNON_GW_NO_RING", None)
     b = engine.DeviceWorld(cuda_lib, mk())
     os.environ["CANNON_GS_NO_WORLD_KERNEL"] = "1"
     os.environ["CANNON_NO_GRAPH"] = "1"
