@@ -401,6 +401,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast_v1, 256, 0);
   w->coopBlocksGsFastV1 = ctx->sms * std::max(1, std::min(occ, 4));
   cudaFuncSetAttribute(k_gs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_SMEM_BYTES);
+  cudaFuncSetAttribute(k_np_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 32 * QS_HOIST_AXES * sizeof(QsAxis)));
   cudaFuncSetAttribute(k_gs_world, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
@@ -1189,10 +1190,11 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   ContactArrays C = contact_arrays(w);
   int* cnt = w->cnt.p;
   const int gp = grid_for(w, w->pairCap, 128);
-  { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 0); }
+  const int hoistBytes = (int)(4 * 32 * QS_HOIST_AXES * sizeof(QsAxis));  // pass 0 only
+  { g_kernel_launches++; k_np_tasks<<<gp, 128, hoistBytes, s>>>(B, T, A, 0, hoistBytes); }
   W_TRY(w, scan_exclusive(A.pairTasks, A.pairTaskOff, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NTASKS, w->scanTmp, s));
   { g_kernel_launches++; k_bucket_starts<<<1, 32, 0, s>>>(cnt); }
-  { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1); }
+  { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1, 0); }
   const int g = w->ctx->sms * 8;
   // fork: the heavy SAT kernels go to side streams, the cheap analytic resolvers stay on the main stream
   cudaStream_t s1 = w->npStream[0], s2 = w->npStream[1], s3 = w->npStream[2];

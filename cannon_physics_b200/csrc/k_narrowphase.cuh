@@ -225,6 +225,31 @@ __device__ __forceinline__ bool pillar_quick_separated_pre(const QsAxis* __restr
   return false;
 }
 
+// one quick-separation axis of a hull / heightfield pair: face 0 of the hull (t == 0 when it has uniqueAxes) or
+// cross(hull edge, heightfield z), its hull projection and its image in the heightfield frame
+__device__ __forceinline__ QsAxis qs_axis(const ShapeTables& T, const HullDev& hd, const q4& qf, const f3& oA, const q4& qs, int t) {
+  f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
+  const int e = t - (hd.hasAxes ? 1 : 0);
+  f3 axis;
+  bool valid = true;
+  if (e < 0) axis = qrot(qf, ld3(T.fnormals[hd.fOff]));
+  else {
+    axis = vcross(qrot(qf, ld3(T.edgesK[hd.ekOff + e])), qrot(qs, up));
+    if (valmost_zero(axis)) valid = false;
+    else vnormalize(axis);
+  }
+  QsAxis q;
+  q.valid = valid ? 1 : 0;
+  q.maxA = q.minA = 0.0;
+  q.lax = axis;
+  if (valid) {
+    project_verts(T.verts + hd.vOff, nullptr, hd.nV, axis, qf, oA, q.maxA, q.minA);
+    q.lax = qrot(qnegw(qs), axis);
+  }
+  return q;
+}
+#define QS_HOIST_AXES 8  // pairs with at most this many quick axes (box 4, 8-segment cylinder 6) get them computed up front
+
 // which body plays "i" for the resolver: lower ShapeType index first, equal types swapped (narrow_phase.dart:706-710)
 __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& first, int& second) {
   if (ta < tb) { first = a; second = b; } else { first = b; second = a; }
@@ -234,9 +259,12 @@ __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& firs
 // own thread. Heightfield pairs are expanded *warp-cooperatively*: the warp takes its heightfield pairs one at a time
 // and every lane tests one pillar of the index window (bounding gate + exact quick separation), a ballot gives the
 // survivor mask in the reference's loop order (i, j, lower/upper), so counts and emission order need no atomics.
-__global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass) {
+__global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, NpArrays A, int pass, int hoistBytes) {
   __shared__ QsAxis s_qs[4][QS_MAX_AXES];
   __shared__ HfPairCtx s_ctx[4][32];
+  __shared__ int s_hoistOff[4 * 33];
+  extern __shared__ __align__(16) unsigned char s_dynTasks[];  // pass 0: QsAxis[4][32][QS_HOIST_AXES]
+  QsAxis* const s_hoist = hoistBytes ? (QsAxis*)s_dynTasks : nullptr;
   QsAxis* const qs_ax = s_qs[threadIdx.x >> 5];
   const int np = *A.nPairs;
   const int lane = threadIdx.x & 31;
@@ -316,6 +344,31 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       }
     }
     __syncwarp();
+    // quick-separation axes of ALL hull / heightfield pairs of the batch, one (pair, axis) item per lane: the serial
+    // loop below then starts with its axes ready instead of computing 4-6 of them with 4-6 lanes per pair
+    const bool hoisted = pass == 0 && s_hoist != nullptr;
+    if (hoisted) {
+      int myAx = 0;
+      if (hfPair && code == NP_HPIL) {
+        const HullDev& h = ctxs[lane].hd;
+        if (h.nE <= 32 && h.nF <= 32) { myAx = (h.hasAxes ? 1 : 0) + h.nEk; if (myAx > QS_HOIST_AXES) myAx = 0; }
+      }
+      int incl = myAx;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int* const ex = s_hoistOff + (threadIdx.x >> 5) * 33;
+      ex[lane] = incl - myAx;
+      if (lane == 31) ex[32] = total;
+      __syncwarp();
+      for (int item = lane; item < total; item += 32) {
+        int lo = 0, hi = 32;  // last pair slot whose first item is <= item (slots without axes have empty ranges)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ex[mid] <= item) lo = mid; else hi = mid; }
+        while (ex[lo + 1] <= item) lo++;  // skip empty slots that share the offset
+        const HfPairCtx& X = ctxs[lo];
+        s_hoist[((size_t)(threadIdx.x >> 5) * 32 + lo) * QS_HOIST_AXES + (item - ex[lo])] = qs_axis(T, X.hd, X.qf, X.oA, X.qs, item - ex[lo]);
+      }
+      __syncwarp();
+    }
     unsigned todo = __ballot_sync(0xffffffffu, hfPair);
     const int myOff = (pass && k < np) ? A.pairTaskOff[k] : 0;
     while (todo) {
@@ -341,32 +394,16 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       // quick-separation axes of this pair (face 0 of the hull when it has uniqueAxes, then hull edge x heightfield z)
       const bool quick = hullTask && !cached && hd.nE <= 32 && hd.nF <= 32;
       int nAx = 0;
+      const QsAxis* qs_use = qs_ax;
       if (quick) {
         nAx = (hd.hasAxes ? 1 : 0) + hd.nEk;  // +-copies of an edge separate exactly when the first copy does
-        f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
-        const f3 wz = qrot(qs, up);
-        __syncwarp();  // the previous pair's lanes are done with the scratch
-        for (int t = lane; t < nAx; t += 32) {
-          const int e = t - (hd.hasAxes ? 1 : 0);
-          f3 axis;
-          bool valid = true;
-          if (e < 0) axis = qrot(qf, ld3(T.fnormals[hd.fOff]));
-          else {
-            axis = vcross(qrot(qf, ld3(T.edgesK[hd.ekOff + e])), wz);
-            if (valmost_zero(axis)) valid = false;
-            else vnormalize(axis);
-          }
-          QsAxis q;
-          q.valid = valid ? 1 : 0;
-          q.maxA = q.minA = 0.0;
-          q.lax = axis;
-          if (valid) {
-            project_verts(T.verts + hd.vOff, nullptr, hd.nV, axis, qf, oA, q.maxA, q.minA);
-            q.lax = qrot(qnegw(qs), axis);
-          }
-          qs_ax[t] = q;
+        if (hoisted && nAx <= QS_HOIST_AXES) {
+          qs_use = s_hoist + ((size_t)(threadIdx.x >> 5) * 32 + src) * QS_HOIST_AXES;  // computed before the loop
+        } else {
+          __syncwarp();  // the previous pair's lanes are done with the scratch
+          for (int t = lane; t < nAx; t += 32) qs_ax[t] = qs_axis(T, hd, qf, oA, qs, t);
+          __syncwarp();
         }
-        __syncwarp();
       }
       unsigned long long mask = 0ull;
       int count = 0;
@@ -390,7 +427,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
             const f3 wpo = to_world_point(xs, qs, po);
             alive = vdist(xf, wpo) < pr + rFirst;
             if (alive && !hullTask) alive = !sphere_pillar_far(X.lc, rFirst, X.margin, po, pv);
-            if (alive && quick) alive = !pillar_quick_separated_pre(qs_ax, nAx, pv, wpo, qs);
+            if (alive && quick) alive = !pillar_quick_separated_pre(qs_use, nAx, pv, wpo, qs);
           }
         }
         const unsigned bits = __ballot_sync(0xffffffffu, alive);
