@@ -28,7 +28,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -154,7 +154,8 @@ struct cannon_world {
   DBuf<cannon_contact_material> dCms;
   // device: broadphase
   DBuf<int4> cellc, smeta, scell;
-  DBuf<int> nbCache;
+  DBuf<int> nbCache, clipList;
+  DBuf<float4> taskSep;
   DBuf<int> binLo, binHi, cellStart, cellEnd, bigList, bigWorldStart, worldStart, bpCounts, bpOffs;
   DBuf<uint32_t> skey, sval, sapKey, sapList;
   DBuf<float4> spos;
@@ -425,7 +426,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
   REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
-  REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
+  REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
   REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairMask); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
   REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
@@ -1170,6 +1171,7 @@ static NpArrays np_arrays(cannon_world* w) {
   A.taskCap = w->taskCap; A.contactCap = w->contactCap;
   A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS;
   { const char* e = getenv("CANNON_NP_DEBUG"); A.debug = e ? atoi(e) : 0; }
+  A.clipList = w->clipList.p; A.nClip = cnt + CT_NCLIP0; A.taskSep = w->taskSep.p;
   return A;
 }
 static ContactArrays contact_arrays(cannon_world* w) {
@@ -1202,12 +1204,14 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   const bool hf = !w->hHfs.empty();
   if (hf) {
     W_TRY(w, cudaStreamWaitEvent(s2, w->npFork, 0));
-    { g_kernel_launches++; k_np_hull_warp<true><<<g * 2, SAT_TILES * SAT_GROUP, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    { g_kernel_launches++; k_np_hull_warp<true, 0><<<g * 2, SAT_TILES * SAT_GROUP, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP); }
+    { g_kernel_launches++; k_np_hull_warp<true, 1><<<g * 2, SAT_TILES * SAT_GROUP, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP); }
     if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_pillar<<<g * 2, 64, 0, s2>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
     W_TRY(w, cudaEventRecord(w->npJoin[1], s2));
   }
   W_TRY(w, cudaStreamWaitEvent(s1, w->npFork, 0));
-  { g_kernel_launches++; k_np_hull_warp<false><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  { g_kernel_launches++; k_np_hull_warp<false, 0><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
+  { g_kernel_launches++; k_np_hull_warp<false, 1><<<g * 2, SAT_TILES * SAT_GROUP, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP); }
   if (w->hasOversizeHull) { g_kernel_launches++; k_np_hull_hull<<<g * 2, 64, 0, s1>>>(B, T, A, cnt + CT_OVF_CLIP, 1); }
   W_TRY(w, cudaEventRecord(w->npJoin[0], s1));
   if (hf) {
@@ -1282,6 +1286,15 @@ static EvArrays ev_arrays(cannon_world* w) {
   E.keysCur = w->evKeysCur.p; E.keysPrev = w->evKeysPrev.p; E.tabCur = w->evTabCur.p; E.tabPrev = w->evTabPrev.p;
   E.begin = w->evBegin.p; E.end = w->evEnd.p; E.cnt = w->evCnt.p; E.mask = w->evMask; E.cap = w->evCap;
   return E;
+}
+// queue of the tile SAT kernel's clipping launch: only worlds with hull shapes (box / convex / cylinder) need it
+static int32_t ensure_clip_buffers(cannon_world* w) {
+  if (w->hHulls.empty() || w->taskCap <= 0) return CANNON_OK;
+  if (w->clipList.cap >= 2 * (size_t)w->taskCap && w->taskSep.cap >= (size_t)w->taskCap) return CANNON_OK;
+  drop_step_graph(w);
+  W_TRY(w, w->clipList.reserve(2 * (size_t)w->taskCap));
+  W_TRY(w, w->taskSep.reserve((size_t)w->taskCap));
+  return CANNON_OK;
 }
 // (re)allocates the event buffers for the current pair capacity and starts from an empty previous set
 static int32_t ensure_events(cannon_world* w) {
@@ -1588,6 +1601,7 @@ int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const in
   for (int k = 0; k < np; k++)
     if (p1[k] < 0 || p2[k] < 0 || p1[k] >= w->n || p2[k] >= w->n) return fail(w->ctx, CANNON_E_INVALID, "pair references unknown body");
   int32_t rc;
+  if ((rc = ensure_clip_buffers(w)) != CANNON_OK) return rc;
   if ((rc = st_reset_counters(w)) != CANNON_OK) return rc;
   if (np > 0) {
     W_TRY(w, cudaMemcpyAsync(w->p1.p, p1, np * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1680,6 +1694,7 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   int32_t rc;
   if ((rc = refresh_damping(w, dt)) != CANNON_OK) return rc;
   if ((rc = ensure_events(w)) != CANNON_OK) return rc;
+  if ((rc = ensure_clip_buffers(w)) != CANNON_OK) return rc;
   w->dt = dt;
   const bool wantGraph = !w->graphBroken && !getenv("CANNON_NO_GRAPH") && !getenv("CANNON_GS_TRACE");
   cudaEventRecord(w->ev[8], s);

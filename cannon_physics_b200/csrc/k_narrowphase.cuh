@@ -38,6 +38,10 @@ struct NpArrays {
   int debug;               // profiling aid (CANNON_NP_DEBUG): 1 skip clipping, 2 skip the axis loop, 3 skip after pillar build
   int* overflowTasks;
   int* overflowContacts;
+  // tile SAT kernel (k_sat_warp.cuh): tasks that passed the separating-axis test, queued for the clipping launch
+  int* clipList;           // [2][taskCap]: hull/hull, hull/pillar
+  int* nClip;              // [2]
+  float4* taskSep;         // separating axis of a queued task
 };
 
 struct ContactArrays {

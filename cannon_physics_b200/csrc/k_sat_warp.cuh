@@ -193,19 +193,25 @@ __device__ inline int clip_hulls_tile(const Tile& tile, int lane, SatScratch& S,
   return kept;
 }
 
-template <bool PILLAR>
+// Two launches per task type. PHASE 0 runs the separating-axis test of every task and either closes the task (no contact)
+// or queues it with its separating axis; PHASE 1 clips and emits the queued tasks. One fused kernel was ~53 KB of code
+// walked by four divergent tiles per warp - far beyond the 32 KB L1.5 instruction cache (`no_instruction` was the second
+// largest stall); each phase fits, and phase 1 only sees tasks that all take the same path.
+template <bool PILLAR, int PHASE>
 __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
   __shared__ SatScratch s_scr[SAT_TILES];
   cg::thread_block_tile<SAT_GROUP> tile = cg::tiled_partition<SAT_GROUP>(cg::this_thread_block());
   const int lane = tile.thread_rank(), tib = threadIdx.x / SAT_GROUP;
   SatScratch& S = s_scr[tib];
   const int TYPE = PILLAR ? NP_HPIL : NP_HH;
-  const int nb = (*A.nTasks <= A.taskCap) ? A.bucketCount[TYPE] : 0;
+  const int* const clipList = A.clipList + (size_t)(PILLAR ? 1 : 0) * A.taskCap;
+  int* const nClip = A.nClip + (PILLAR ? 1 : 0);
+  const int nb = (*A.nTasks <= A.taskCap) ? (PHASE == 0 ? A.bucketCount[TYPE] : min(*nClip, A.taskCap)) : 0;
   const int tilesPerGrid = gridDim.x * SAT_TILES;
   for (int u = blockIdx.x * SAT_TILES + tib; u < nb; u += tilesPerGrid) {
     tile.sync();
     TaskCtx c;
-    load_task(B, T, A, A.bucket[A.bucketStart[TYPE] + u], c);
+    load_task(B, T, A, PHASE == 0 ? A.bucket[A.bucketStart[TYPE] + u] : clipList[u], c);
     RawOut o; o.A = A; o.task = c.task;
     const HullView HA = hull_view(T, c.si.hull);
     HullView HB;
@@ -225,6 +231,19 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
     }
     int kept = 0;
     f3 sep; sep.x = sep.y = sep.z = 0.f;
+    if (PHASE == 1) {
+      // a queued task: its separating axis is known, clipping needs the world face normals of both hulls
+      sep = ld3(A.taskSep[c.task]);
+      for (int i = lane; i < HA.nF; i += SAT_GROUP) S.nA[i] = qrot(c.qi, ld3(HA.n[i]));
+      for (int i = lane; i < HB.nF; i += SAT_GROUP) S.nB[i] = qrot(c.qj, ld3(HB.n[i]));
+      tile.sync();
+      if (A.debug != 1) {
+        bool ovf = false;
+        kept = clip_hulls_tile(tile, lane, S, HA, c.xi, HB, xB, c.qj, sep, ovf);
+        if (ovf) atomicExch(clipOverflow, 1);
+      }
+    } else {
+    bool needClip = false;
     bool candidate = PILLAR ? (vdist(c.xi, xB) < HB.bsr + HA.bsr) : true;
     if (candidate && (vdist(c.xi, xB) > HA.bsr + HB.bsr)) candidate = false;  // convexConvex's own bounding test (:1999)
     if (candidate && sat_oversize(HA, HB)) {
@@ -298,13 +317,19 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
         }
         const f3 deltaC = vsub(xB, c.xi);
         if (vdot(deltaC, sep) > 0.0) sep = vneg(sep);
-        tile.sync();  // the widened vertices are dead from here on: their storage becomes the clipping polygons
-        if (A.debug != 1) {
-          bool ovf = false;
-          kept = clip_hulls_tile(tile, lane, S, HA, c.xi, HB, xB, c.qj, sep, ovf);
-          if (ovf) atomicExch(clipOverflow, 1);
-        }
+        needClip = true;
       }
+    }
+    if (lane == 0) {
+      if (needClip) {  // queue for the clipping launch
+        const int q = atomicAdd(nClip, 1);
+        if (q < A.taskCap) A.clipList[(size_t)(PILLAR ? 1 : 0) * A.taskCap + q] = c.task;
+        A.taskSep[c.task] = st3(sep);
+      } else {
+        raw_alloc(o, 0);  // separated (or outside the bounding test): the task is closed without contacts
+      }
+    }
+    continue;
     }
     // emission: lane 0 reserves the block in the raw pool, lanes write one contact each
     tile.sync();
