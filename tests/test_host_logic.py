@@ -116,3 +116,30 @@ def test_api_world_flattens_like_the_reference_objects(oracle_lib):
     assert len(world.contacts["body_i"]) >= 8
     with pytest.raises(F.CannonError):
         boxes[0].addShape(api.Sphere(1.0))  # compound bodies are outside the hot-path scope
+
+
+def test_world_api_contact_event_listeners(oracle_lib):
+    """Host mirror of EventTarget for the world-level contact events (world_class.dart:703-730), driven by the checker
+    library on the CPU: begin once when the ball lands, nothing while it rests, `endContact` when it is lifted away."""
+    from cannon_physics_b200 import api, scenes
+    world = api.World(gravity=(0, -10, 0), _lib=oracle_lib)
+    ground = api.Body(mass=0, shape=api.Plane())
+    ground.quaternion[:] = scenes.GROUND_QUAT
+    ball = api.Body(mass=1, shape=api.Sphere(0.5), position=(0, 0.8, 0))
+    world.addBody(ground)
+    world.addBody(ball)
+    heard = []
+    world.addEventListener("beginContact", lambda e: heard.append(("begin", e["bodyA"] is ground, e["bodyB"] is ball)))
+    world.addEventListener("endContact", lambda e: heard.append(("end", e["bodyA"] is ground, e["bodyB"] is ball)))
+    assert world.hasAnyEventListener("beginContact") and not world.hasAnyEventListener("collide")
+    for _ in range(60):
+        world.step(1 / 60)
+    assert heard == [("begin", True, True)]
+    ball.position[:] = (0, 5, 0)
+    ball.velocity[:] = 0
+    world.markDirty()
+    world.step(1 / 60, nsteps=2)  # listeners hear every step of a multi-step call
+    assert heard == [("begin", True, True), ("end", True, True)]
+    import pytest
+    with pytest.raises(api.CannonError):
+        world.addEventListener("collide", lambda e: None)
