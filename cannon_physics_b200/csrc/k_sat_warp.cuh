@@ -1,14 +1,16 @@
-// k_sat_warp.cuh — warp-per-task separating-axis test + clipping for hull/hull and hull/heightfield-pillar tasks.
+// k_sat_warp.cuh — tile-per-task separating-axis test + clipping for hull/hull and hull/heightfield-pillar tasks.
 //
 // The reference's convexConvex (lib/world/narrow_phase.dart:1981-2043) is a long sequential loop: up to
-// |facesA| + |facesB| + |edgesA|*|edgesB| axis tests (48 for box-box, 85 for box-pillar, 120 for two 8-segment
-// cylinders; lib/rigid_body_shapes/convex_polyhedron.dart:232-356), each projecting both hulls. Here one warp
-// owns one task:
-//   1. lanes rotate the face normals / unique edges of both hulls into shared memory once,
-//   2. the axis list is dealt round-robin to the lanes; every lane keeps its own (depth, axis index) minimum,
-//   3. a warp vote detects a separating axis, a lexicographic (depth, index) shuffle reduction reproduces the
-//      sequential "first strictly smaller depth wins" rule bit for bit,
-//   4. lane 0 clips the incident face (Sutherland-Hodgman, polygons in shared memory), lanes emit the contacts.
+// |facesA| + |facesB| + |edgesA|*|edgesB| axis tests (48 for box-box, 85 for box-pillar, 141 for cylinder-pillar;
+// lib/rigid_body_shapes/convex_polyhedron.dart:232-356), each projecting both hulls. Here an 8-lane tile owns one
+// task (four tasks per warp) and the work is two launches per task type (k_np_hull_warp<PILLAR, PHASE>):
+//   PHASE 0  lanes rotate the face normals / pruned unique edges of both hulls into shared memory and widen the
+//            vertices to f64 once; the pruned axis list (+- copies removed, see below) is taken in rounds of 8 with a
+//            vote after each round (a separating axis closes the task); a lexicographic (depth, index) shuffle
+//            reduction reproduces the sequential "first strictly smaller depth wins" rule bit for bit; surviving
+//            tasks are queued with their axis,
+//   PHASE 1  the queued tasks are clipped by the whole tile (Sutherland-Hodgman with a prefix sum per pass, polygons
+//            in shared memory) and the lanes emit the contacts.
 // Every arithmetic expression is the one the sequential path (k_narrowphase.cuh) evaluates, so contact counts
 // and geometry stay bit-identical to the oracle; only the scheduling changed.
 #pragma once
