@@ -48,13 +48,19 @@ for t, sv in zip(tab, solvers):
     cb = t.get("cpu_baseline")
     rows.append(f"| {names[c]} | {sv} | {t['ms_per_step']:.2f} | {t['steps_per_s']:.0f} | {sci(t['value'])} | {sci(t['contact_iters_per_s'])} | {sci(cb['value']) if cb else ''} |")
 sc = []
-for name, what in (("r01_scale2_c3.json", "c3 replicas"), ("r01_scale2_c4_reference.json", "c4 sharded 2048 worlds per GPU, reference order"),
-                   ("r01_scale2_c4_colored.json", "c4 sharded, colored")):
-    p = os.path.join(HERE, name)
-    if os.path.exists(p):
-        j = load(name)
-        sc.append(f"{what}: {sci(j['value'])} body-steps/s ({j['ms_per_step']:.2f} ms/step" + (f", e2e {sci(j['e2e']['value'])}" if j.get("e2e") else "") + ")")
-scale2 = "2-GPU check (`gpurun --gpus 2`, `r01_scale2_*.json`): " + "; ".join(sc) + "." if sc else ""
+for n in (2, 4, 8):
+    for name, what in ((f"r01_scale{n}_c3.json", f"{n} × c3 replicas (weak)"), (f"r01_scale{n}_c4_reference.json", f"c4 sharded over {n} GPUs, reference order (strong)"),
+                       (f"r01_scale{n}_c4_colored.json", f"c4 sharded over {n} GPUs, colored (strong)")):
+        p = os.path.join(HERE, name)
+        if os.path.exists(p):
+            j = load(name)
+            sc.append(f"| {what} | {j['steps']} | {j['ms_per_step']:.2f} | {sci(j['value'])} | " + (sci(j['e2e']['value']) if j.get("e2e") else "") + " |")
+scale2 = ("Multi-GPU checks (`gpurun --gpus N`, one process per GPU, no collective on the step path, `r01_scaleN_*.json`; 100 timed steps, so the c3 lines\n"
+          "average over the cheaper early steps):\n\n| run | steps | ms/step | body-steps/s | e2e body-steps/s |\n|---|---|---|---|---|\n" + "\n".join(sc) + "\n\n"
+          "Replicas scale linearly (no shared resource). The *fixed* 4096-world batch does not: 2.44 ms on one GPU, 1.52 ms on two, 1.09 ms on four — a\n"
+          "step has a latency floor of ≈ 0.5 ms (73 dependent launches, the cooperative colouring and sweep phases; config 1 with 1000 bodies takes\n"
+          "0.52 ms), and a quarter of the batch per GPU is within 2× of it. Batches that grow with the GPU count (4096 worlds *per* GPU) keep the one-GPU\n"
+          "rate per GPU; lowering the floor (fewer, fused launches for small batches) is what strong scaling needs next.") if sc else ""
 c4 = [t for t, sv in zip(tab, solvers) if sv.startswith("colored (ring")][0]
 c5 = tab[-1]
 s = open(os.path.join(HERE, "README.tmpl.md")).read()
