@@ -143,3 +143,18 @@ def test_world_api_contact_event_listeners(oracle_lib):
     import pytest
     with pytest.raises(api.CannonError):
         world.addEventListener("collide", lambda e: None)
+
+
+def test_profiles_readme_matches_the_evidence_files():
+    """profiles/README.md is generated (profiles/make_readme.py) from the committed bench lines: regenerating it must not
+    change a byte, so the numbers quoted there are the numbers in profiles/*.json."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    readme = os.path.join(root, "profiles", "README.md")
+    before = open(readme).read()
+    subprocess.check_call([sys.executable, os.path.join(root, "profiles", "make_readme.py")], stdout=subprocess.DEVNULL)
+    after = open(readme).read()
+    assert before == after
+    assert "@@" not in after
