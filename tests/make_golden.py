@@ -45,6 +45,32 @@ def run_case(lib, make_spec, steps):
     return out
 
 
+def _bouncing():
+    spec = scenes.spheres_on_plane(5, 5, 4, spacing=0.55)
+    spec.desc["default_contact_material"] = dict(restitution=0.6)
+    return spec
+
+
+# world-level contact events (world_class.dart:703-730): per step, the beginContact / endContact pair lists
+EVENT_CASES = {
+    "events_bouncing": (_bouncing, 120),
+    "events_heightfield": (lambda: scenes.mixed_pile_on_heightfield(6, 6, 3, hf_samples=33, solver=REF, grid_cells=(8, 4, 8)), 120),
+}
+
+
+def run_events(lib, make_spec, steps):
+    """(step, a, b) rows of every beginContact / endContact event of the run, in dispatch order."""
+    w = engine.DeviceWorld(lib, make_spec())
+    w.enable_contact_events(True)
+    begin, end = [], []
+    for s in range(steps):
+        w.step(1 / 60)
+        b, e = w.get_contact_events()
+        begin += [(s, int(x), int(y)) for x, y in b]
+        end += [(s, int(x), int(y)) for x, y in e]
+    return {"begin": np.array(begin, np.int32).reshape(-1, 3), "end": np.array(end, np.int32).reshape(-1, 3)}
+
+
 if __name__ == "__main__":
     lib = F.bind(os.path.join(ROOT, "oracle", "libcannon_oracle.so"))
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
@@ -52,3 +78,7 @@ if __name__ == "__main__":
         res = run_case(lib, mk, steps)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **res)
         print(name, {k: v.shape for k, v in res.items() if k in ("p1", "c_bi", "row_B")})
+    for name, (mk, steps) in EVENT_CASES.items():
+        res = run_events(lib, mk, steps)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **res)
+        print(name, {k: v.shape for k, v in res.items()})

@@ -227,3 +227,13 @@ def test_oracle_matches_golden_fixture(oracle_lib, name):
     ref = np.load(os.path.join(GOLDEN, name + ".npz"))
     for k in ref.files:
         assert np.array_equal(got[k], ref[k]), (name, k)
+
+
+@pytest.mark.parametrize("name", ["events_bouncing", "events_heightfield"])
+def test_oracle_contact_events_match_golden_fixture(oracle_lib, name):
+    from make_golden import EVENT_CASES, run_events
+    got = run_events(oracle_lib, *EVENT_CASES[name])
+    ref = np.load(os.path.join(GOLDEN, name + ".npz"))
+    assert len(ref["begin"]) > 0 and len(ref["end"]) > 0
+    for k in ref.files:
+        assert np.array_equal(got[k], ref[k]), f"{name}: {k} differs from the fixture"

@@ -324,3 +324,13 @@ def test_world_api_dispatches_contact_events(cuda_lib):
     for _ in range(60):
         world.step(1 / 60)
     assert heard and heard[0] == ("beginContact", True, True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["events_bouncing", "events_heightfield"])
+def test_cuda_contact_events_match_golden_fixture(cuda_lib, name):
+    from make_golden import EVENT_CASES, run_events
+    got = run_events(cuda_lib, *EVENT_CASES[name])
+    ref = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for k in ref.files:
+        assert np.array_equal(got[k], ref[k]), f"{name}: {k} differs from the fixture"
