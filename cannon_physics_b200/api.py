@@ -429,19 +429,53 @@ class World:  # lib/world/world_class.dart:44
         self._state_dirty = False
         self._listeners = {}
         self._events_on = False
+        self._host_current = True  # the Body objects hold the device state (False after a step with sync=False)
 
     # world_class.dart:282-300 / 224-231 / 343-348
+    def _pull(self):
+        """Before a structural change rebuilds the device world: make the Body objects current."""
+        if self._dev is not None and not self._structure_dirty and not self._host_current:
+            self.sync()
+
     def addBody(self, body: Body):
         if body in self.bodies:
             return
+        self._pull()
         body.index = len(self.bodies)
         body.world = self
         self.bodies.append(body)
         self._structure_dirty = True
 
+    def removeBody(self, body: Body):
+        """World.removeBody (world_class.dart:303-320): the remaining bodies are re-indexed; the device world is rebuilt
+        from the current body state before the next step (constraints that still reference the body must be removed
+        first, the upload refuses dangling references)."""
+        if body not in self.bodies:
+            return
+        self._pull()  # the Body objects carry the state the rebuilt device world starts from
+        self.bodies.remove(body)
+        body.world = None
+        body.index = -1
+        for i, b in enumerate(self.bodies):
+            b.index = i
+        self._structure_dirty = True
+
     def addConstraint(self, c: Constraint):
+        self._pull()
         self.constraints.append(c)
         self._structure_dirty = True
+
+    def removeConstraint(self, c: Constraint):  # world_class.dart:234-236
+        if c in self.constraints:
+            self._pull()
+            self.constraints.remove(c)
+            self._structure_dirty = True
+
+    def clearForces(self):  # world_class.dart:773-781
+        for b in self.bodies:
+            b.force[:] = 0
+            b.torque[:] = 0
+        self._state_dirty = True
 
     def addSpring(self, spring: Spring):
         self.springs.append(spring)
@@ -514,6 +548,9 @@ class World:  # lib/world/world_class.dart:44
                     friction_equation_stiffness=c.frictionEquationStiffness, friction_equation_relaxation=c.frictionEquationRelaxation)
                for c in self.contactmaterials]
         idx = {id(body): i for i, body in enumerate(self.bodies)}
+        for c in list(self.constraints) + list(self.springs):
+            if id(c.bodyA) not in idx or id(c.bodyB) not in idx:
+                raise CannonError(F.E_INVALID, "a constraint or spring references a body that is not in the world (remove it first)")
         cons = [c._desc(idx) for c in self.constraints]
         return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n,
                          material_friction=np.array([m.friction for m in mats], dtype=np.float64) if mats else None,
@@ -522,9 +559,10 @@ class World:  # lib/world/world_class.dart:44
 
     def _ensure_uploaded(self):
         if self._structure_dirty or self._dev is None:
+            spec = self._spec()  # may refuse (dangling constraint): the old device world stays usable
             if self._dev is not None:
                 self._dev.close()
-            self._dev = DeviceWorld(self._lib, self._spec(), device=self._device)
+            self._dev = DeviceWorld(self._lib, spec, device=self._device)
             self._dev.set_time(self.time)
             if self._events_on:
                 self._dev.enable_contact_events(True)
@@ -583,6 +621,7 @@ class World:  # lib/world/world_class.dart:44
                 self._emit_contact_events()
         self.dt = dt
         self.time, self.stepnumber = self._dev.get_time()
+        self._host_current = False
         if sync:
             self.sync()
 
@@ -597,6 +636,7 @@ class World:  # lib/world/world_class.dart:44
             body.sleepState = int(st["sleep_state"][i])
             body.force[:] = 0
             body.torque[:] = 0
+        self._host_current = True
 
     @property
     def contacts(self):

@@ -158,3 +158,44 @@ def test_profiles_readme_matches_the_evidence_files():
     after = open(readme).read()
     assert before == after
     assert "@@" not in after
+
+
+def test_world_api_remove_body_and_constraint(oracle_lib):
+    """World.removeBody / removeConstraint / clearForces (world_class.dart:234-236,303-320,773-781) in the host mirror: a
+    structural change rebuilds the device world from the current body state, the remaining bodies are re-indexed and keep
+    moving as if nothing else had happened."""
+    import pytest
+    from cannon_physics_b200 import api, scenes
+
+    def build(with_extra):
+        w = api.World(gravity=(0, -10, 0), _lib=oracle_lib)
+        g = api.Body(mass=0, shape=api.Plane())
+        g.quaternion[:] = scenes.GROUND_QUAT
+        a = api.Body(mass=1, shape=api.Sphere(0.5), position=(0, 3, 0))
+        b = api.Body(mass=1, shape=api.Sphere(0.5), position=(5, 4, 0))   # far away: never touches `a`
+        c = api.Body(mass=1, shape=api.Box((0.25, 0.25, 0.25)), position=(5, 6, 0))
+        for body in (g, a) + ((b, c) if with_extra else ()):
+            w.addBody(body)
+        return w, g, a, b, c
+
+    w, g, a, b, c = build(True)
+    joint = api.DistanceConstraint(b, c)
+    w.addConstraint(joint)
+    for _ in range(30):
+        w.step(1 / 60, sync=False)   # the Body objects are stale until a structural change pulls the state
+    with pytest.raises(api.CannonError):
+        w.removeBody(c)
+        w.step(1 / 60)               # the joint still references `c`
+    w.addBody(c)
+    w.removeConstraint(joint)
+    w.removeBody(b)
+    w.removeBody(c)
+    assert [body.index for body in w.bodies] == [0, 1] and b.index == -1 and b.world is None
+    w.clearForces()
+    for _ in range(60):
+        w.step(1 / 60)
+    ref, _, a_ref, _, _ = build(False)
+    for _ in range(90):
+        ref.step(1 / 60)
+    # `a` never interacted with the removed bodies: same trajectory as in a world that never had them
+    assert np.array_equal(a.position, a_ref.position) and np.array_equal(a.velocity, a_ref.velocity)
