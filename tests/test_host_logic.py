@@ -199,3 +199,20 @@ def test_world_api_remove_body_and_constraint(oracle_lib):
         ref.step(1 / 60)
     # `a` never interacted with the removed bodies: same trajectory as in a world that never had them
     assert np.array_equal(a.position, a_ref.position) and np.array_equal(a.velocity, a_ref.velocity)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU: one JSON line with the
+    same metric / unit / config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e record."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                                  stderr=subprocess.DEVNULL, text=True)
+    j = json.loads(out.strip().splitlines()[-1])
+    assert j["impl"] == "reference" and j["metric"] == "body-steps/s" and j["unit"] == "body-steps/s" and j["higher_is_better"] is True
+    assert j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 1 and j["value"] > 0
+    assert j["config"]["workload"].startswith("c3") and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
