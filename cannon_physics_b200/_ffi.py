@@ -20,7 +20,7 @@ SHAPE_SPHERE, SHAPE_PLANE, SHAPE_BOX, SHAPE_CONVEX, SHAPE_CYLINDER, SHAPE_HEIGHT
 BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC = 0, 1, 2
 AWAKE, SLEEPY, SLEEPING = 0, 1, 2
 BP_NAIVE, BP_SAP, BP_GRID = 0, 1, 2
-SOLVER_REFERENCE_ORDER, SOLVER_COLORED, SOLVER_SPLIT = 0, 1, 2
+SOLVER_REFERENCE_ORDER, SOLVER_COLORED, SOLVER_SPLIT, SOLVER_COLORED_F32 = 0, 1, 2, 3
 CONSTRAINT_POINT_TO_POINT, CONSTRAINT_HINGE, CONSTRAINT_DISTANCE, CONSTRAINT_LOCK, CONSTRAINT_CONE_TWIST = 0, 1, 2, 3, 4
 
 
@@ -115,6 +115,8 @@ class Profile(C.Structure):
         ("n_pairs", c_i64), ("n_contacts", c_i64), ("n_rows", c_i64), ("n_levels", c_i64),
         ("iterations_done", c_i64), ("steps", c_i64), ("contact_iters_total", c_i64),
         ("step_call_ms", c_f64), ("schedule_ms", c_f64), ("gs_ms", c_f64), ("kernel_launches", c_i64), ("n_tasks", c_i64), ("n_islands", c_i64), ("n_tasks_by_type", c_i64 * 8),
+        ("sum_steps", c_i64), ("sum_step_ms", c_f64), ("sum_broadphase", c_f64), ("sum_narrowphase", c_f64), ("sum_solve", c_f64),
+        ("sum_integrate", c_f64), ("sum_schedule", c_f64), ("sum_gs", c_f64),
     ]
 
 
@@ -147,6 +149,9 @@ PROTOTYPES = {
     "cannon_integrate": (c_i32, [VP, c_f64]),
     "cannon_world_step": (c_i32, [VP, c_f64, c_i32]),
     "cannon_world_profile": (c_i32, [VP, P(Profile)]),
+    "cannon_world_step_profiled": (c_i32, [VP, c_f64, c_i32]),
+    "cannon_world_step_async": (c_i32, [VP, c_f64, c_i32]),
+    "cannon_ctx_sync": (c_i32, [VP]),
     "cannon_world_get_contacts": (c_i32, [VP, P(ContactsSoA), P(c_i32)]),
     "cannon_world_enable_contact_events": (c_i32, [VP, c_i32]),
     "cannon_world_get_contact_events": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32)]),

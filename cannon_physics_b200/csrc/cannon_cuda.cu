@@ -194,7 +194,7 @@ struct cannon_world {
   DBuf<float> rFlambda;
   int rowCap = 0;
   // device: solver units
-  DBuf<int> uBi, uBj, uFlags, uRows, uSrc, eBi, eBj, eFlags, eRowBase, eRows, unitRow;
+  DBuf<int> uBi, uBj, uFlags, uRows, uSrc, uKey, eBi, eBj, eFlags, eRowBase, eRows, unitRow;
   DBuf<double> eImA, eImB;
   int unitCap = 0;
   // device: joints
@@ -227,6 +227,8 @@ struct cannon_world {
   cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   long long lastUnits = 0, lastLevels = 0;  // widths seen by the last synchronised call (sizes the cooperative grids)
   bool recordSolveEvents = false;
+  bool stepPending = false;             // cannon_world_step_async enqueued work that cannon_ctx_sync has not collected yet
+  std::vector<cudaEvent_t> profPool;    // cannon_world_step_profiled: PROF_EV events per step
   // one World.step captured as a CUDA graph (all counts live on the device, so the launch sequence of a step is
   // fixed for a given dt and capacity; the cooperative kernels size their own barrier on the device); replayed by
   // cannon_world_step
@@ -250,8 +252,14 @@ struct cannon_world {
     if (npFork) cudaEventDestroy(npFork);
     for (auto& e : npJoin) if (e) cudaEventDestroy(e);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : profPool) if (e) cudaEventDestroy(e);
   }
 };
+
+// COLORED sweeps the colour order with the reference arithmetic (f64, bit-exact against the oracle's restatement of the same
+// order); COLORED_F32 packs the rows to f32 and sweeps with FMA (reduced precision, opt-in)
+static inline bool kind_colored(const cannon_world* w) { return w->desc.solver_kind == CANNON_SOLVER_COLORED || w->desc.solver_kind == CANNON_SOLVER_COLORED_F32; }
+static inline bool kind_fast(const cannon_world* w) { return w->desc.solver_kind == CANNON_SOLVER_COLORED_F32; }
 
 static int32_t fail(cannon_ctx* ctx, int32_t code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -415,6 +423,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
 static void drop_step_graph(cannon_world* w);
 
 void cannon_world_destroy(cannon_world* w) {
+  if (w && w->ctx) { auto& pv = w->ctx->pending; pv.erase(std::remove(pv.begin(), pv.end(), w), pv.end()); }
   if (!w) return;
   drop_step_graph(w);
   cudaSetDevice(w->ctx->device);
@@ -433,7 +442,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
-  REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
+  REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(uKey); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
@@ -716,7 +725,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(contFlag, contactCap); RES(fricOff, contactCap); RES(contOff, contactCap); RES(cRi, contactCap); RES(cRj, contactCap);
   RES(cNi, contactCap); RES(cRest, contactCap); RES(cMu, contactCap); RES(cSlip, contactCap); RES(cCa, contactCap); RES(cCb, contactCap);
   RES(cCeps, contactCap); RES(cFb, contactCap); RES(cFeps, contactCap); RES(cMult, contactCap);
-  if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
+  if (kind_fast(w)) {
     RES(rRec, (size_t)rowCap * 5); RES(rFlambda, rowCap + 32); RES(uRec, rowCap + 3);
     w->gsTaskCap = rowCap / GS_WIN_MIN + w->maxLevels + 2;
     RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
@@ -727,7 +736,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   }
   const int unitCap = rowCap + 2;
   w->unitCap = unitCap;
-  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
+  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(uKey, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
   RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * ((size_t)w->desc.n_worlds * GR_LV + 4)); RES(worldUnitStart, (size_t)w->desc.n_worlds * GR_LV + 4);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
@@ -1252,14 +1261,14 @@ static RowArrays row_arrays(cannon_world* w) {
   R.kind = w->rKind.p; R.n = w->rN.p; R.rA = w->rRA.p; R.rB = w->rRB.p; R.iA = w->rIA.p; R.iB = w->rIB.p;
   R.B = w->rB.p; R.invC = w->rInvC.p; R.eps = w->rEps.p; R.minF = w->rMinF.p; R.maxF = w->rMaxF.p; R.lambda = w->rLambda.p;
   R.rowCap = w->rowCap;
-  R.fast = w->desc.solver_kind == CANNON_SOLVER_COLORED ? 1 : 0;
+  R.fast = kind_fast(w) ? 1 : 0;
   R.rec = w->rRec.p; R.flambda = w->rFlambda.p;
   return R;
 }
 static UnitArrays unit_arrays(cannon_world* w) {
   UnitArrays U;
   U.nUnits = w->cnt.p + CT_NUNITS; U.nExec = w->cnt.p + CT_NEXEC;
-  U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p;
+  U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p; U.uKey = w->uKey.p;
   U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p; U.eLevel = w->eLevel.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
   return U;
@@ -1340,7 +1349,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   { const int32_t rcEv = st_contact_events(w); if (rcEv != CANNON_OK) return rcEv; }
   SolveParams P;
   P.dt = dt; P.tol2 = w->desc.solver_tolerance * w->desc.solver_tolerance; P.maxIter = w->desc.solver_iterations;
-  P.nBodies = w->n; P.nWorlds = nW; P.colored = w->desc.solver_kind == CANNON_SOLVER_COLORED;
+  P.nBodies = w->n; P.nWorlds = nW; P.colored = kind_colored(w);
   P.debugSkipWork = getenv("CANNON_DEBUG_SKIP_GS_WORK") ? 1 : 0;
   P.trace = nullptr;
   const char* tracePath = getenv("CANNON_GS_TRACE");
@@ -1395,7 +1404,8 @@ static int32_t st_solve(cannon_world* w, double dt) {
   // a colored batch is swept world by world (k_gs_world): regroup the execution order by world first
   // (measured: the same per-world scheme for the f64 reference-order rows is slower than the grid-wide k_gs, 4.7 vs 4.2 ms
   // on c4 — its phases are two dependent global loads long and only 15 worlds fit an SM — so it is not in the tree)
-  const bool perWorld = P.colored && nW > 1 && !w->gsFastV1 && !getenv("CANNON_GS_NO_WORLD_KERNEL");
+  const bool fast = kind_fast(w);
+  const bool perWorld = fast && nW > 1 && !w->gsFastV1 && !getenv("CANNON_GS_NO_WORLD_KERNEL");
   const int* order = w->order.p;
   if (perWorld) {
     // (world, colour) bins: units - hence rows - of a world are contiguous colour by colour
@@ -1406,7 +1416,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nBins, nBins, nullptr, w->scanTmp, s));
     { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->world.p, w->worldUnitStart.p, wc + nBins + 1, w->orderW.p); }
     order = w->orderW.p;
-  } else if (P.colored && !w->gsFastV1 && !w->gsNoLenSort) {
+  } else if (fast && !w->gsFastV1 && !w->gsNoLenSort) {
     // homogeneous windows for k_gs_fast: units of a colour ordered by row count (k_solver.cuh, k_len_*)
     W_TRY(w, cudaMemsetAsync(w->lenBins.p, 0, LEN_BINS * sizeof(int), s));
     { g_kernel_launches++; k_len_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->lenBins.p); }
@@ -1421,7 +1431,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, order, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
   GsTasks T;
   T.tab = w->gsTab.p; T.lvlTask = w->gsLvlTask.p; T.lvlWin = w->gsLvlWin.p; T.nTasks = cnt + CT_GS_NTASKS; T.taskCap = w->gsTaskCap;
-  if (P.colored && !w->gsFastV1 && !perWorld) {
+  if (fast && !w->gsFastV1 && !perWorld) {
     { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
     { g_kernel_launches++; k_gs_task_fill<<<grid_for(w, w->gsTaskCap + 1, 256), 256, 0, s>>>(U, S, T); }
   }
@@ -1445,8 +1455,8 @@ static int32_t st_solve(cannon_world* w, double dt) {
         { g_kernel_launches++; k_gs_world_ring<<<nW, 32, 0, s>>>(R, B, U, P, G, wus, wbs, ringOk); }
       }
       k_gs_world<<<nW, GW_THREADS, GW_SMEM_BYTES, s>>>(R, B, U, S, P, G, wus, wbs, ringOk);
-    } else if (P.colored && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
-    else if (P.colored) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
+    } else if (fast && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
+    else if (fast) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
     else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
   }
   if (w->recordSolveEvents) cudaEventRecord(w->ev[10], s);
@@ -1686,8 +1696,13 @@ static void drop_step_graph(cannon_world* w) {
   w->eagerSteps = 0;
 }
 
-int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
-  if (!w || nsteps < 0) return CANNON_E_INVALID;
+// stage events of one eager step, in enqueue_step's order: start, after broadphase / narrowphase / solve / integrate,
+// schedule begin / end, sweep begin, -, -, sweep end (indices into cannon_world::ev)
+#define PROF_EV 11
+
+// enqueues nsteps steps and the asynchronous read-back of the counters; no host synchronisation.
+// profiled: every step runs eagerly with its own set of stage events (cannon_world_step_profiled)
+static int32_t step_enqueue(cannon_world* w, double dt, int32_t nsteps, bool profiled) {
   cudaSetDevice(w->ctx->device);
   W_TRY(w, sync_clock(w));
   cudaStream_t s = w->ctx->stream;
@@ -1696,13 +1711,23 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   if ((rc = ensure_events(w)) != CANNON_OK) return rc;
   if ((rc = ensure_clip_buffers(w)) != CANNON_OK) return rc;
   w->dt = dt;
-  const bool wantGraph = !w->graphBroken && !getenv("CANNON_NO_GRAPH") && !getenv("CANNON_GS_TRACE");
-  cudaEventRecord(w->ev[8], s);
+  const bool wantGraph = !profiled && !w->graphBroken && !getenv("CANNON_NO_GRAPH") && !getenv("CANNON_GS_TRACE");
+  if (profiled) {
+    const size_t need = (size_t)nsteps * PROF_EV;
+    while (w->profPool.size() < need) {
+      cudaEvent_t e;
+      W_TRY(w, cudaEventCreate(&e));
+      w->profPool.push_back(e);
+    }
+  }
+  cudaEvent_t keep[PROF_EV];
+  for (int k = 0; k < PROF_EV; k++) keep[k] = w->ev[k];
+  cudaEventRecord(keep[8], s);
   for (int it = 0; it < nsteps; it++) {
     bool done = false;
     // the stage events of cannon_profile only time eager launches, so a multi-step call runs its last step eagerly
-    const bool profiled = it == nsteps - 1 && nsteps > 1;
-    if (wantGraph && w->eagerSteps >= 1 && !profiled) {
+    const bool lastEager = it == nsteps - 1 && nsteps > 1;
+    if (wantGraph && w->eagerSteps >= 1 && !lastEager) {
       if (w->stepGraph && w->graphDt != dt) { cudaGraphExecDestroy(w->stepGraph); w->stepGraph = nullptr; }
       if (!w->stepGraph) {
         const long long l0 = g_kernel_launches;
@@ -1737,7 +1762,12 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
       }
     }
     if (!done) {
-      if ((rc = enqueue_step(w, dt)) != CANNON_OK) return rc;
+      if (profiled)
+        for (int k = 0; k < PROF_EV; k++)
+          if (k != 8 && k != 9) w->ev[k] = w->profPool[(size_t)it * PROF_EV + k];
+      rc = enqueue_step(w, dt);
+      if (profiled) for (int k = 0; k < PROF_EV; k++) w->ev[k] = keep[k];
+      if (rc != CANNON_OK) return rc;
       w->eagerSteps++;
     }
     w->stepnumber += 1;
@@ -1748,28 +1778,92 @@ int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
   if (nsteps > 0) {
     W_TRY(w, cudaMemcpyAsync(w->hCnt, w->cnt.p, CT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
     W_TRY(w, cudaMemcpyAsync(w->hAcc, w->acc.p, AC_COUNT * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    W_TRY(w, cudaStreamSynchronize(s));
-    if ((rc = check_overflow_acc(w)) != CANNON_OK) return rc;
-    float ms;
-    cannon_profile& p = w->prof;
-    p.steps = w->hAcc[AC_STEPS];
-    p.contact_iters_total = w->hAcc[AC_CONTACT_ITERS];
-    if (cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]) == cudaSuccess) p.broadphase = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]) == cudaSuccess) p.narrowphase = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]) == cudaSuccess) { p.solve = ms; p.make_contact_constraints = 0; }
-    if (cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]) == cudaSuccess) p.integrate = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[5], w->ev[6]) == cudaSuccess) p.schedule_ms = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[7], w->ev[10]) == cudaSuccess) p.gs_ms = ms;
-    if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;
-    cudaGetLastError();  // an event pair that was not recorded in this call is not an error of the step
-    p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
-    p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
-    w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
-    p.n_tasks = w->hCnt[CT_NTASKS];
-    p.n_islands = w->hCnt[CT_NISLANDS];
-    for (int t = 0; t < NP_NTYPES; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];
   }
   return CANNON_OK;
+}
+
+// after the stream has been synchronised: overflow check + cannon_profile of the call
+static int32_t step_finish(cannon_world* w, int32_t nsteps, bool profiled) {
+  w->stepPending = false;
+  if (nsteps <= 0) return CANNON_OK;
+  int32_t rc;
+  if ((rc = check_overflow_acc(w)) != CANNON_OK) return rc;
+  float ms;
+  cannon_profile& p = w->prof;
+  p.steps = w->hAcc[AC_STEPS];
+  p.contact_iters_total = w->hAcc[AC_CONTACT_ITERS];
+  auto stage = [&](cudaEvent_t* ev) {
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) p.broadphase = ms;
+    if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) p.narrowphase = ms;
+    if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) { p.solve = ms; p.make_contact_constraints = 0; }
+    if (cudaEventElapsedTime(&ms, ev[3], ev[4]) == cudaSuccess) p.integrate = ms;
+    if (cudaEventElapsedTime(&ms, ev[5], ev[6]) == cudaSuccess) p.schedule_ms = ms;
+    if (cudaEventElapsedTime(&ms, ev[7], ev[10]) == cudaSuccess) p.gs_ms = ms;
+  };
+  if (profiled) {
+    p.sum_steps = 0; p.sum_step_ms = p.sum_broadphase = p.sum_narrowphase = p.sum_solve = p.sum_integrate = p.sum_schedule = p.sum_gs = 0;
+    for (int it = 0; it < nsteps; it++) {
+      cudaEvent_t* ev = &w->profPool[(size_t)it * PROF_EV];
+      stage(ev);
+      p.sum_broadphase += p.broadphase; p.sum_narrowphase += p.narrowphase; p.sum_solve += p.solve; p.sum_integrate += p.integrate;
+      p.sum_schedule += p.schedule_ms; p.sum_gs += p.gs_ms;
+      if (cudaEventElapsedTime(&ms, ev[0], ev[4]) == cudaSuccess) p.sum_step_ms += ms;
+      p.sum_steps += 1;
+    }
+  } else {
+    stage(w->ev);
+  }
+  if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;
+  cudaGetLastError();  // an event pair that was not recorded in this call is not an error of the step
+  p.n_pairs = w->hCnt[CT_NPAIRS]; p.n_contacts = w->hCnt[CT_NCONTACTS]; p.n_rows = w->hCnt[CT_NROWS];
+  p.n_levels = w->hCnt[CT_NLEVELS]; p.iterations_done = w->hCnt[CT_ITERS];
+  w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
+  p.n_tasks = w->hCnt[CT_NTASKS];
+  p.n_islands = w->hCnt[CT_NISLANDS];
+  for (int t = 0; t < NP_NTYPES; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];
+  return CANNON_OK;
+}
+
+int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps) {
+  if (!w || nsteps < 0) return CANNON_E_INVALID;
+  int32_t rc;
+  if ((rc = step_enqueue(w, dt, nsteps, false)) != CANNON_OK) return rc;
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  return step_finish(w, nsteps, false);
+}
+
+// every step eager and bracketed by its own stage events: cannon_profile.sum_* hold the per-stage device time summed over
+// the nsteps steps of this call (what bench.py reports as the sweep kernel's average launch duration)
+int32_t cannon_world_step_profiled(cannon_world* w, double dt, int32_t nsteps) {
+  if (!w || nsteps < 0 || nsteps > 4096) return CANNON_E_INVALID;
+  int32_t rc;
+  if ((rc = step_enqueue(w, dt, nsteps, true)) != CANNON_OK) return rc;
+  W_TRY(w, cudaStreamSynchronize(w->ctx->stream));
+  return step_finish(w, nsteps, true);
+}
+
+// World.step without waiting for the device: the call returns once the work is enqueued on the ctx's stream, so one host
+// thread (one Dart isolate) can keep several GPUs busy; cannon_ctx_sync collects the result
+int32_t cannon_world_step_async(cannon_world* w, double dt, int32_t nsteps) {
+  if (!w || nsteps < 0) return CANNON_E_INVALID;
+  int32_t rc;
+  if ((rc = step_enqueue(w, dt, nsteps, false)) != CANNON_OK) return rc;
+  if (nsteps > 0 && !w->stepPending) { w->stepPending = true; w->ctx->pending.push_back(w); }
+  return CANNON_OK;
+}
+
+int32_t cannon_ctx_sync(cannon_ctx* ctx) {
+  if (!ctx) return CANNON_E_INVALID;
+  cudaSetDevice(ctx->device);
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int32_t first = CANNON_OK;
+  std::vector<cannon_world*> pend;
+  pend.swap(ctx->pending);
+  for (cannon_world* w : pend) {
+    const int32_t rc = step_finish(w, 1, false);
+    if (rc != CANNON_OK && first == CANNON_OK) first = rc;
+  }
+  return first;
 }
 
 int32_t cannon_world_profile(cannon_world* w, cannon_profile* out) {
@@ -1830,7 +1924,7 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   // returned in the reference's solve order; COLORED: returned in execution order.
   std::vector<double> hB(n), hC(n), hL(n);
   std::vector<int> uBi(nu), uBj(nu), uRow(nu), uLvl(nu), uRows(nu);
-  if (w->desc.solver_kind == CANNON_SOLVER_COLORED) {
+  if (kind_fast(w)) {
     std::vector<float4> q((size_t)n * 5);
     std::vector<float> fl(n);
     W_TRY(w, cudaMemcpy(q.data(), w->rRec.p, (size_t)n * 5 * sizeof(float4), cudaMemcpyDeviceToHost));
@@ -1847,12 +1941,17 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   W_TRY(w, cudaMemcpy(uLvl.data(), w->unitLevel.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
   W_TRY(w, cudaMemcpy(uRows.data(), w->uRows.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
   int out = 0;
-  const bool refOrder = w->desc.solver_kind != CANNON_SOLVER_COLORED;
+  const bool refOrder = !kind_colored(w);
   const int ne = refOrder ? nu : std::min(nu, w->hCnt[CT_NEXEC]);  // units without rows are not in the execution order
   std::vector<int> unitsInOrder(nu);
   if (refOrder) { for (int u = 0; u < nu; u++) unitsInOrder[u] = u; }
   else if (ne > 0) {
+    // the schedule appends the units of a colour in arrival order: report them by (colour, unit key), the canonical order
+    // of include/cannon_cuda.h (units of one colour are independent, so any order inside a colour is the same solve)
     W_TRY(w, cudaMemcpy(unitsInOrder.data(), w->order.p, ne * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> uKey(nu);
+    W_TRY(w, cudaMemcpy(uKey.data(), w->uKey.p, nu * sizeof(int), cudaMemcpyDeviceToHost));
+    std::sort(unitsInOrder.begin(), unitsInOrder.begin() + ne, [&](int a, int b) { return uLvl[a] != uLvl[b] ? uLvl[a] < uLvl[b] : uKey[a] < uKey[b]; });
   }
   for (int k = 0; k < ne; k++) {
     const int u = unitsInOrder[k];

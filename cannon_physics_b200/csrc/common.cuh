@@ -15,6 +15,7 @@ struct cannon_ctx {
   int sms = 148;
   cudaStream_t stream = nullptr;
   std::string err;
+  std::vector<struct cannon_world*> pending;  // worlds with a cannon_world_step_async call that cannon_ctx_sync has not collected
 };
 
 #define CU_TRY(ctx, expr)                                                                         \

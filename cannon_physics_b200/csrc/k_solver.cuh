@@ -48,6 +48,7 @@ struct UnitArrays {
   int* nUnits;       // device count
   int* nExec;        // device count of scheduled units (units without rows never enter the execution order)
   int *uBi, *uBj, *uFlags, *uRows, *uSrc;   // flags bit0/1: body i/j movable
+  int* uKey;                                 // COLORED: canonical unit key (first contact index / nContacts + joint slot)
   int *eBi, *eBj, *eFlags, *eRowBase;        // eRowBase has nUnits+1 entries (exclusive scan of rows in exec order)
   double *eImA, *eImB;                       // invMassSolve of the two bodies
   int* eRows;                                // rows per unit in exec order (scan input)
@@ -187,8 +188,8 @@ struct UnitSrc {  // what the units are made from
 };
 
 __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& B, int u, int bi, int bj, int rows, int src, int nWorlds,
-                                         int* __restrict__ worldRows) {
-  U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src;
+                                         int* __restrict__ worldRows, int key = 0) {
+  U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src; U.uKey[u] = key;
   U.uFlags[u] = rows > 0 ? ((body_movable(B, bi) ? 1 : 0) | (body_movable(B, bj) ? 2 : 0)) : 0;
   if (rows > 0) {
     // worldRows[w] > 0 <=> world w has equations this step: one plain store per (warp, world) instead of millions of
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
           for (int c = c0; c < c1; c++) rows += S.contFlag[c] + 2 * S.fricFlag[c];
         }
       }
-      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows);
+      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows, m > 0 ? S.taskOff[t] : 0);
     }
   } else if (S.split) {
     // unit id = position in descending creation-id order (split_solver.dart:108,167-169)
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
       const bool head = s == 0 || J.first[J.slotEq[s - 1]] != f;
       int rows = 0;
       if (head) { rows = 1; while (s + rows < J.nAccepted && J.first[J.slotEq[s + rows]] == f) rows++; }
-      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], rows, s * 8 + SRC_JOINTS, nWorlds, worldRows);
+      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], rows, s * 8 + SRC_JOINTS, nWorlds, worldRows, nc + s);
     } else {
       put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
     }
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
     const unsigned long long hi = (unsigned long long)(0x7fffffffu - (unsigned)round) << 32;
     for (int a = tid; a < nAct; a += nth) {
       const int u = __ldcg(&act[a]);
-      const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
+      const unsigned pri = colored ? (unsigned)U.uKey[u] * 2654435761u : (unsigned)u;
       const unsigned long long key = hi | pri;
       const int fl = U.uFlags[u];
       if (fl & 1) atomicMin(&S.claim[U.uBi[u]], key);
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       bool win = false, emit = false;
       if (active) {
         u = __ldcg(&act[a]);
-        const unsigned pri = colored ? (unsigned)u * 2654435761u : (unsigned)u;
+        const unsigned pri = colored ? (unsigned)U.uKey[u] * 2654435761u : (unsigned)u;
         const unsigned long long key = hi | pri;
         const int fl = U.uFlags[u];
         win = true;

@@ -44,6 +44,10 @@ class Context:
         if code != F.OK:
             raise F.CannonError(code, "cannon_ctx_create failed (no CUDA device? there is no CPU fallback)")
 
+    def sync(self):
+        """cannon_ctx_sync: wait for the asynchronous steps of every world of this ctx and collect their status."""
+        _check(self.lib, self.handle, self.lib.cannon_ctx_sync(self.handle))
+
     def close(self):
         if self.handle:
             self.lib.cannon_ctx_destroy(self.handle)
@@ -308,6 +312,14 @@ class DeviceWorld:
     # ---- fused ---------------------------------------------------------------------------------
     def step(self, dt: float, nsteps: int = 1):
         self._chk(self.lib.cannon_world_step(self.handle, dt, nsteps))
+
+    def step_profiled(self, dt: float, nsteps: int = 1):
+        """nsteps eager steps, each between its own stage events: profile()['sum_*'] = device ms per stage over the call."""
+        self._chk(self.lib.cannon_world_step_profiled(self.handle, dt, nsteps))
+
+    def step_async(self, dt: float, nsteps: int = 1):
+        """World.step enqueued on the ctx's stream; collect with Context.sync() (one host thread can drive several GPUs)."""
+        self._chk(self.lib.cannon_world_step_async(self.handle, dt, nsteps))
 
     def profile(self) -> Dict[str, float]:
         p = F.Profile()

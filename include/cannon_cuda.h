@@ -61,14 +61,23 @@ enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
 /* World.solver choices.
  *   REFERENCE_ORDER: GSSolver with the reference's exact equation order
  *       (lib/world/world_class.dart:539-541,562,627-635); bit-reproducible validation mode.
- *   COLORED: graph-coloured Gauss-Seidel (throughput mode; different row order, so only
- *       statistical agreement with the reference).
+ *   COLORED: graph-coloured Gauss-Seidel, the throughput mode. Same per-row arithmetic as GSSolver (f64 on
+ *       f32-stored operands, no FMA, every Vector3 store rounds to float), different - but fully specified -
+ *       row order: units = contact manifolds (the ContactEquations of one resolver call, rows [f1,f2,n] per
+ *       contact) followed by one unit per constraint; unit key = index of its first ContactEquation in
+ *       World.contacts (constraints: n_contacts + ordinal of its first accepted equation); priority =
+ *       key * 2654435761 mod 2^32; colour(u) = round in which u holds the smallest pending priority on all of
+ *       its movable bodies. Colours are swept in ascending order, units of a colour are independent. The oracle
+ *       restates exactly this order sequentially, so COLORED is bit-exact against it; agreement
+ *       with the reference's own insertion order is statistical (Gauss-Seidel is order dependent).
+ *   COLORED_F32: the same colour order with rows packed to f32 and swept with FMA (reduced precision; opt-in,
+ *       never used for a headline number).
  *   SPLIT: SplitSolver(GSSolver) (lib/solver/split_solver.dart:50-120): islands of non-static bodies
  *       connected by equations, one independent GSSolver pass per island (own tolerance early-exit),
  *       island equations in descending Equation.id order. The reference's ids depend on its object-pool
  *       history; here ids are the history-free creation order of a pool-less step
  *       (constraint equations first, then per contact: contact, friction 1, friction 2). */
-enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1, CANNON_SOLVER_SPLIT = 2 };
+enum { CANNON_SOLVER_REFERENCE_ORDER = 0, CANNON_SOLVER_COLORED = 1, CANNON_SOLVER_SPLIT = 2, CANNON_SOLVER_COLORED_F32 = 3 };
 /* Constraint kinds, lib/constraints/{point_to_point,hinge}_constraint.dart */
 enum {
   CANNON_CONSTRAINT_POINT_TO_POINT = 0, /* lib/constraints/point_to_point_constraint.dart */
@@ -238,6 +247,9 @@ typedef struct cannon_profile {
   int64_t n_tasks;         /* narrowphase resolver tasks of the last step (pairs + heightfield pillars) */
   int64_t n_islands;       /* SPLIT solver: islands of the last solve (SplitSolver.solve's return value) */
   int64_t n_tasks_by_type[8]; /* sphere-sphere, sphere-plane, sphere-box, sphere-hull, plane-hull, hull-hull, sphere-pillar, hull-pillar */
+  /* cannon_world_step_profiled: device time per stage summed over the sum_steps steps of that call, milliseconds */
+  int64_t sum_steps;
+  double sum_step_ms, sum_broadphase, sum_narrowphase, sum_solve, sum_integrate, sum_schedule, sum_gs;
 } cannon_profile;
 
 /* ---- lifecycle ---- */
@@ -296,6 +308,15 @@ int32_t cannon_integrate(cannon_world* w, double dt);
 /* nsteps x World.step(dt) (fixed stepping, world_class.dart:393-399) with all state device-resident */
 int32_t cannon_world_step(cannon_world* w, double dt, int32_t nsteps);
 int32_t cannon_world_profile(cannon_world* w, cannon_profile* out);
+/* the same nsteps steps, every one launched eagerly between its own stage events: cannon_profile.sum_* then hold the
+ * device time of every stage summed over the call (World.profile of lib/world/world_class.dart:27-41 accumulated) */
+int32_t cannon_world_step_profiled(cannon_world* w, double dt, int32_t nsteps);
+/* World.step without waiting for the device (SURVEY.md 8b `_async` + cannon_ctx_sync): returns once the steps are
+ * enqueued on the ctx's stream, so one host thread / Dart isolate can drive one ctx per GPU concurrently. Counters,
+ * capacity errors and cannon_world_profile of the call become valid after cannon_ctx_sync(ctx), which returns the first
+ * error of the collected calls. Any synchronous entry point on the same ctx also completes the pending work first. */
+int32_t cannon_world_step_async(cannon_world* w, double dt, int32_t nsteps);
+int32_t cannon_ctx_sync(cannon_ctx* ctx);
 /* World.contacts of the last step */
 int32_t cannon_world_get_contacts(cannon_world* w, cannon_contacts_soa* out, int32_t* n_contacts);
 /* Contact events of the last step: World.emitContactEvents (lib/world/world_class.dart:703-730)

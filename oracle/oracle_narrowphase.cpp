@@ -22,6 +22,7 @@ namespace {
 struct NP {
   World& w;
   const cannon_contact_material* cm = nullptr;  // currentContactMaterial
+  int manifold = 0;  // ordinal of the current resolver call (one sphereConvex / convexConvex call per heightfield pillar)
   explicit NP(World& w_) : w(w_) {}
 
   // createContactEquation, narrow_phase.dart:492-528. `crA/crB` are the collisionResponse flags of the
@@ -54,6 +55,7 @@ struct NP {
       friction = w.matFriction[matA] * w.matFriction[matB];
     c.friction = friction;
     w.contacts.push_back(c);
+    w.contactManifold.push_back(manifold);
     if (friction > 0) {
       V3 g = w.desc.has_friction_gravity ? V3{w.desc.friction_gravity[0], w.desc.friction_gravity[1], w.desc.friction_gravity[2]}
                                          : V3{w.desc.gravity[0], w.desc.gravity[1], w.desc.gravity[2]};
@@ -616,8 +618,10 @@ struct NP {
         for (int up = 0; up < 2; up++) {
           pillar(sj, i, j, up != 0, pc, po);
           V3 worldPillarOffset = point_to_world_frame(xj, qj, po);
-          if (distance_to(xi, worldPillarOffset) < pc.boundingSphereRadius + si.boundingSphereRadius)
+          if (distance_to(xi, worldPillarOffset) < pc.boundingSphereRadius + si.boundingSphereRadius) {
+            manifold++;
             sphereConvex(si, pc, true, xi, worldPillarOffset, qj, bi, bj);
+          }
         }
         if (w.contacts.size() - numContactsBefore > 2) return;
       }
@@ -637,8 +641,10 @@ struct NP {
         for (int up = 0; up < 2; up++) {
           pillar(sj, i, j, up != 0, pc, po);
           V3 worldPillarOffset = point_to_world_frame(xj, qj, po);
-          if (distance_to(xi, worldPillarOffset) < pc.boundingSphereRadius + si.boundingSphereRadius)
+          if (distance_to(xi, worldPillarOffset) < pc.boundingSphereRadius + si.boundingSphereRadius) {
+            manifold++;
             convexConvex(si, pc, crA, true, xi, worldPillarOffset, qi, qj, bi, bj, faceList, 1);
+          }
         }
   }
 
@@ -648,6 +654,7 @@ struct NP {
   // (sa,xa,qa,ba) has the lower ShapeType index; equal types arrive swapped (narrow_phase.dart:706-710).
   void resolve(const Shape& sa, const Shape& sb, V3 xa, V3 xb, Q4 qa, Q4 qb, int ba, int bb) {
     const int ta = sa.type, tb = sb.type;
+    manifold++;
     if (ta == CANNON_SHAPE_SPHERE) {
       if (tb == CANNON_SHAPE_SPHERE) sphereSphere(sa, sb, xa, xb, ba, bb);
       else if (tb == CANNON_SHAPE_PLANE) spherePlane(sa, sb, xa, xb, qb, ba, bb);
@@ -679,6 +686,7 @@ const cannon_contact_material* World::contactMaterial(int ma, int mb) const {
 void World::getContacts() {
   contacts.clear();
   frictions.clear();
+  contactManifold.clear();
   perPairCount.assign(p1.size(), 0);
   NP np(*this);
   for (size_t k = 0; k != p1.size(); k++) {

@@ -334,6 +334,97 @@ int World::solve(double h) {
       if (it != tagged.end()) rows.push_back(it->second);
     }
     prof.n_islands = nIslands;
+  } else if (desc.solver_kind == CANNON_SOLVER_COLORED || desc.solver_kind == CANNON_SOLVER_COLORED_F32) {
+    // COLORED order (include/cannon_cuda.h): GSSolver's arithmetic over a different, fully specified equation order.
+    // Units = contact manifolds (the ContactEquations of one resolver call; rows [f1, f2, n] per contact) and one unit per
+    // constraint; colour(u) = round in which u holds the smallest pending priority on all of its movable bodies; colours
+    // ascend, units of a colour are independent (ordered by key here). Sequential GS over that list is the coloured sweep.
+    struct CUnit { int bi, bj, key, level; unsigned pri; std::vector<Eq*> eqs; };
+    std::vector<CUnit> units;
+    auto movable = [&](int b) {
+      const Body& B = bodies[b];
+      if (B.sleepState == CANNON_SLEEPING || B.type == CANNON_BODY_KINEMATIC) return false;
+      if (B.invMass != 0.0) return true;
+      for (int k = 0; k < 9; k++) if (B.invInertiaWorld.e[k] != 0.f) return true;
+      return false;
+    };
+    {
+      size_t f = 0;
+      for (size_t c = 0; c < contacts.size();) {
+        size_t e = c;
+        while (e < contacts.size() && contactManifold[e] == contactManifold[c]) e++;
+        CUnit u{contacts[c].bi, contacts[c].bj, (int)c, -1, 0u, {}};
+        for (size_t k = c; k < e; k++) {
+          if (contacts[k].friction > 0) {
+            if (accept(frictions[f])) { u.eqs.push_back(&frictions[f]); u.eqs.push_back(&frictions[f + 1]); }
+            f += 2;
+          }
+          if (accept(contacts[k])) u.eqs.push_back(&contacts[k]);
+        }
+        if (!u.eqs.empty()) units.push_back(u);
+        c = e;
+      }
+      int slot = 0;
+      for (Constraint& c : constraints) {
+        CUnit u{-1, -1, 0, -1, 0u, {}};
+        for (Eq& e : c.eqs)
+          if (accept(e)) {
+            if (u.eqs.empty()) { u.bi = e.bi; u.bj = e.bj; u.key = (int)contacts.size() + slot; }
+            u.eqs.push_back(&e);
+            slot++;
+          }
+        if (!u.eqs.empty()) units.push_back(u);
+      }
+    }
+    int nLevels = 0;
+    {
+      std::vector<unsigned> claim(bodies.size(), 0xffffffffu);
+      std::vector<int> active(units.size()), next;
+      for (size_t k = 0; k < units.size(); k++) { active[k] = (int)k; units[k].pri = (unsigned)units[k].key * 2654435761u; }
+      while (!active.empty()) {
+        for (int k : active) {
+          const CUnit& u = units[k];
+          if (movable(u.bi) && u.pri < claim[u.bi]) claim[u.bi] = u.pri;
+          if (movable(u.bj) && u.pri < claim[u.bj]) claim[u.bj] = u.pri;
+        }
+        next.clear();
+        for (int k : active) {
+          CUnit& u = units[k];
+          const bool win = (!movable(u.bi) || claim[u.bi] == u.pri) && (!movable(u.bj) || claim[u.bj] == u.pri);
+          if (win) u.level = nLevels; else next.push_back(k);
+        }
+        for (int k : active) { claim[units[k].bi] = 0xffffffffu; claim[units[k].bj] = 0xffffffffu; }
+        active.swap(next);
+        nLevels++;
+      }
+    }
+    std::vector<int> ord(units.size());
+    for (size_t k = 0; k < units.size(); k++) ord[k] = (int)k;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+      return units[a].level != units[b].level ? units[a].level < units[b].level : units[a].key < units[b].key;
+    });
+    prof.n_levels = nLevels;
+    std::vector<std::vector<Eq*>> per(nW);
+    for (int k : ord) {
+      const int wi = nW > 1 ? bodies[units[k].bi].worldId : 0;
+      for (Eq* e : units[k].eqs) per[wi].push_back(e);
+    }
+    std::vector<std::vector<int>> wbodies(nW);
+    for (int i = 0; i < (int)bodies.size(); i++) wbodies[nW > 1 ? bodies[i].worldId : 0].push_back(i);
+    std::unordered_map<Eq*, RowDebug> tagged;
+    for (int wi = 0; wi < nW; wi++) {
+      if (wbodies[wi].empty()) continue;
+      std::vector<RowDebug> dbg;
+      int it = gsSolve(*this, per[wi], wbodies[wi], h, dbg);
+      if (it > itersMax) itersMax = it;
+      for (size_t k = 0; k < dbg.size(); k++) tagged[per[wi][k]] = dbg[k];
+    }
+    for (int k : ord)
+      for (Eq* e : units[k].eqs) {
+        RowDebug r = tagged[e];
+        r.level = units[k].level;
+        rows.push_back(r);
+      }
   } else if (nW == 1) {
     std::vector<Eq*> eqs;
     for (Eq& e : frictions) if (accept(e)) eqs.push_back(&e);

@@ -112,6 +112,7 @@ struct Spring {  // lib/objects/spring.dart
 struct RowDebug {
   int bi, bj;
   double B, invC, lambda;
+  int level = 0;  // COLORED: colour of the row's unit
 };
 
 struct World {
@@ -132,6 +133,7 @@ struct World {
   std::vector<Eq> contacts;   // ContactEquations (World.contacts)
   std::vector<Eq> frictions;  // FrictionEquations (World.frictionEquations)
   std::vector<int> perPairCount;
+  std::vector<int> contactManifold;  // per ContactEquation: ordinal of the resolver call that created it (COLORED solver units)
   std::vector<RowDebug> rows;
   cannon_profile prof{};
   std::string err;

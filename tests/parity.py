@@ -27,7 +27,7 @@ def assert_same_contacts(ca, cb, what=""):
             raise AssertionError(f"{what}: contacts.{k} differs at {i}: cuda={ca[k][i]} oracle={cb[k][i]} ({len(bad)} differ)")
 
 
-def staged_step(dev, ref, dt, what=""):
+def staged_step(dev, ref, dt, what="", compare_levels=False):
     """One World.internalStep through the staged entry points, comparing after every stage."""
     for w in (dev, ref):
         w.set_dt(dt)
@@ -41,7 +41,8 @@ def staged_step(dev, ref, dt, what=""):
     ia, ib = dev.solver_solve(dt), ref.solver_solve(dt)
     ra, rb = dev.get_rows(), ref.get_rows()
     assert len(ra["B"]) == len(rb["B"]), f"{what}: row count {len(ra['B'])} vs {len(rb['B'])}"
-    for k in ("body_i", "body_j", "B", "invC", "lambda"):
+    keys = ("body_i", "body_j", "B", "invC", "lambda") + (("level",) if compare_levels else ())
+    for k in keys:
         if not np.array_equal(ra[k], rb[k]):
             bad = np.argwhere(ra[k] != rb[k])
             i = bad[0][0]

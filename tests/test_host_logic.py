@@ -203,16 +203,39 @@ def test_world_api_remove_body_and_constraint(oracle_lib):
 
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU: one JSON line with the
-    same metric / unit / config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e record."""
+    same metric / unit / config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e record.
+    (Run at 1/16 of the bodies here to keep the CPU suite short; the default is the full 100 001-body settled state.)"""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                                  stderr=subprocess.DEVNULL, text=True)
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                                   "--scale", "0.0625"], stderr=subprocess.DEVNULL, text=True)
     j = json.loads(out.strip().splitlines()[-1])
     assert j["impl"] == "reference" and j["metric"] == "body-steps/s" and j["unit"] == "body-steps/s" and j["higher_is_better"] is True
     assert j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 1 and j["value"] > 0
     assert j["config"]["workload"].startswith("c3") and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
+    assert j["config"]["same_config"] is True and j["dtype"] == "f64"
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_uses_the_settled_state_and_never_maps_the_cuda_library():
+    """Both bench arms start config 3 from the committed settled snapshot (same 100 001 bodies), and the reference arm gets
+    its host modules without running the package __init__, so libcannon_cuda.so is never mapped into that process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import bench\n"
+        "spec, label, state = bench.build_spec('c3', 1.0, 0, 1, solver='reference')\n"
+        "st = np.load(bench.SETTLED)\n"
+        "assert spec.n_bodies == 100001 and 'settled' in state and np.array_equal(spec.bodies['position'], st['position'])\n"
+        "assert np.array_equal(spec.bodies['velocity'], st['velocity']) and float(np.abs(st['velocity']).max()) > 0\n"
+        "lib = bench.oracle_lib(); assert lib.cannon_backend() == b'oracle'\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libcannon_oracle.so' in maps and 'libcannon_cuda' not in maps, 'reference arm mapped the product library'\n"
+        "print('ok')\n" % root)
+    out = subprocess.check_output([sys.executable, "-c", code], text=True)
+    assert out.strip().endswith("ok")
