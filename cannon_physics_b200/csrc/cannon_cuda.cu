@@ -22,13 +22,14 @@
 #include "k_narrowphase.cuh"
 #include "k_sat_warp.cuh"
 #include "k_solver.cuh"
+#include "k_gs_exact.cuh"
 #include "world.cuh"
 
 // ---- device counters ---------------------------------------------------------------------------------
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -41,7 +42,7 @@ __global__ void k_bucket_starts(int* cnt) {
 __global__ void k_set_int(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
 
 // persistent accumulators (never reset by the per-step counter memset): statistics and sticky overflow needs
-enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_COUNT };
+enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_GS_ABORT, AC_COUNT };
 __global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restrict__ acc, int taskCap, int contactCap, long long* __restrict__ clk,
                                 double dt) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -56,6 +57,7 @@ __global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restri
   mx(AC_OVF_ROWS, cnt[CT_OVF_ROWS]);
   mx(AC_OVF_LEVELS, cnt[CT_OVF_LEVELS]);
   mx(AC_OVF_CLIP, cnt[CT_OVF_CLIP]);
+  mx(AC_GS_ABORT, cnt[CT_GS_ABORT]);
 }
 
 // constraint-pair filter, world_class.dart:488-499: drop pairs joined by a constraint with collideConnected == false
@@ -181,6 +183,9 @@ struct cannon_world {
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
   DBuf<float4> rRec;
   DBuf<GsUnitRec> uRec;
+  DBuf<GxRow> rXrec;      // COLORED (exact), single world: packed rows / unit records of k_gs_exact
+  DBuf<GxUnit> uXrec;
+  DBuf<int> unitSeq, gxBody;  // per unit: ranks on its two bodies; per body: [0, n) scheduled units, [n, 2n) progress counters
   // contact events (opt-in)
   bool evEnabled = false;
   int evCap = 0;
@@ -237,7 +242,8 @@ struct cannon_world {
   long long graphLaunches = 0;     // kernels per replay (for cannon_profile.kernel_launches)
   int eagerSteps = 0;              // steps run eagerly since the last (re)allocation: lazily sized scratch exists after one
   bool graphBroken = false;        // capture failed once: stay eager
-  int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0;
+  int coopBlocksSched = 0, coopBlocksGs = 0, coopBlocksGsFast = 0, coopBlocksGsFastV1 = 0, coopBlocksGx = 0;
+  bool gxOff = false;     // CANNON_GS_NO_DATAFLOW: COLORED falls back to the unstaged level-by-level sweep k_gs (A/B measurements)
   bool gsFastV1 = false;  // CANNON_GS_FAST_V1: the unstaged colored sweep, kept for A/B measurements
   bool gwNoRing = false;     // CANNON_GW_NO_RING: batches always take the staged CTA-per-world kernel (A/B measurements)
   bool gsNoLenSort = false;  // CANNON_GS_NO_LEN_SORT: leave the units of a colour in schedule order (A/B measurements)
@@ -260,6 +266,8 @@ struct cannon_world {
 // order); COLORED_F32 packs the rows to f32 and sweeps with FMA (reduced precision, opt-in)
 static inline bool kind_colored(const cannon_world* w) { return w->desc.solver_kind == CANNON_SOLVER_COLORED || w->desc.solver_kind == CANNON_SOLVER_COLORED_F32; }
 static inline bool kind_fast(const cannon_world* w) { return w->desc.solver_kind == CANNON_SOLVER_COLORED_F32; }
+// the exact colour sweep of a single world runs as the staged dataflow kernel k_gs_exact over packed 96-byte rows
+static inline bool kind_packed(const cannon_world* w) { return w->desc.solver_kind == CANNON_SOLVER_COLORED && w->desc.n_worlds <= 1 && !w->gxOff; }
 
 static int32_t fail(cannon_ctx* ctx, int32_t code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -414,6 +422,10 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   cudaFuncSetAttribute(k_gs_world, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
+  cudaFuncSetAttribute(k_gs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_exact, GX_THREADS, GX_SMEM_BYTES);
+  w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, 2));
+  w->gxOff = getenv("CANNON_GS_NO_DATAFLOW") != nullptr;
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
   w->gsNoLenSort = getenv("CANNON_GS_NO_LEN_SORT") != nullptr;
   w->gwNoRing = getenv("CANNON_GW_NO_RING") != nullptr;
@@ -443,7 +455,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(uKey); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(rXrec); REL(uXrec); REL(unitSeq); REL(gxBody); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(spBodyA); REL(spBodyB); REL(spOff); REL(spIdx); REL(spRest); REL(spK); REL(spD); REL(spAnchorA); REL(spAnchorB); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
@@ -729,6 +741,11 @@ static int32_t ensure_capacities(cannon_world* w) {
     RES(rRec, (size_t)rowCap * 5); RES(rFlambda, rowCap + 32); RES(uRec, rowCap + 3);
     w->gsTaskCap = rowCap / GS_WIN_MIN + w->maxLevels + 2;
     RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
+  } else if (kind_packed(w)) {
+    RES(rXrec, rowCap + 1); RES(uXrec, rowCap + 3); RES(rMinF, rowCap); RES(rMaxF, rowCap); RES(rLambda, rowCap + 4);
+    w->gsTaskCap = rowCap / GX_WIN_MIN + w->maxLevels + 2;
+    RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
+    RES(unitSeq, 2 * ((size_t)rowCap + 2)); RES(gxBody, 2 * (size_t)n + 2);
   } else {
     RES(rKind, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
     RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
@@ -1263,6 +1280,7 @@ static RowArrays row_arrays(cannon_world* w) {
   R.rowCap = w->rowCap;
   R.fast = kind_fast(w) ? 1 : 0;
   R.rec = w->rRec.p; R.flambda = w->rFlambda.p;
+  R.xrec = kind_packed(w) ? w->rXrec.p : nullptr;
   return R;
 }
 static UnitArrays unit_arrays(cannon_world* w) {
@@ -1271,6 +1289,8 @@ static UnitArrays unit_arrays(cannon_world* w) {
   U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p; U.uKey = w->uKey.p;
   U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p; U.eLevel = w->eLevel.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
+  const bool packed = kind_packed(w);
+  U.xrec = packed ? w->uXrec.p : nullptr; U.unitSeq = packed ? w->unitSeq.p : nullptr; U.bodyCnt = packed ? w->gxBody.p : nullptr;
   return U;
 }
 static JointArrays joint_arrays(cannon_world* w) {
@@ -1380,6 +1400,9 @@ static int32_t st_solve(cannon_world* w, double dt) {
   S.claim = w->claim.p; S.unitLevel = w->unitLevel.p; S.order = w->order.p; S.levelStart = w->levelStart.p; S.nLevels = cnt + CT_NLEVELS;
   S.act0 = w->act0.p; S.act1 = w->act1.p; S.actCount = cnt + CT_ACT0; S.cursor = cnt + CT_CURSOR; S.bar = (unsigned*)(cnt + CT_BAR);
   S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS;
+  const bool packed = kind_packed(w);
+  S.unitSeq = packed ? w->unitSeq.p : nullptr; S.bodyCnt = packed ? w->gxBody.p : nullptr;
+  if (packed) W_TRY(w, cudaMemsetAsync(w->gxBody.p, 0, (2 * (size_t)w->n + 2) * sizeof(int), s));
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
   if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
   {
@@ -1416,7 +1439,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, scan_exclusive(wc, w->worldUnitStart.p, nullptr, nBins, nBins, nullptr, w->scanTmp, s));
     { g_kernel_launches++; k_world_fill<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->world.p, w->worldUnitStart.p, wc + nBins + 1, w->orderW.p); }
     order = w->orderW.p;
-  } else if (fast && !w->gsFastV1 && !w->gsNoLenSort) {
+  } else if (((fast && !w->gsFastV1) || packed) && !w->gsNoLenSort) {
     // homogeneous windows for k_gs_fast: units of a colour ordered by row count (k_solver.cuh, k_len_*)
     W_TRY(w, cudaMemsetAsync(w->lenBins.p, 0, LEN_BINS * sizeof(int), s));
     { g_kernel_launches++; k_len_count<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(U, w->order.p, w->unitLevel.p, w->lenBins.p); }
@@ -1431,7 +1454,8 @@ static int32_t st_solve(cannon_world* w, double dt) {
   { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, order, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
   GsTasks T;
   T.tab = w->gsTab.p; T.lvlTask = w->gsLvlTask.p; T.lvlWin = w->gsLvlWin.p; T.nTasks = cnt + CT_GS_NTASKS; T.taskCap = w->gsTaskCap;
-  if (fast && !w->gsFastV1 && !perWorld) {
+  T.winMin = packed ? GX_WIN_MIN : GS_WIN_MIN; T.winMax = packed ? GX_WIN_MAX : GS_WIN_MAX;
+  if ((fast && !w->gsFastV1 && !perWorld) || packed) {
     { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
     { g_kernel_launches++; k_gs_task_fill<<<grid_for(w, w->gsTaskCap + 1, 256), 256, 0, s>>>(U, S, T); }
   }
@@ -1456,6 +1480,12 @@ static int32_t st_solve(cannon_world* w, double dt) {
       }
       k_gs_world<<<nW, GW_THREADS, GW_SMEM_BYTES, s>>>(R, B, U, S, P, G, wus, wbs, ringOk);
     } else if (fast && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
+    else if (packed) {
+      GxState X;
+      X.done = w->gxBody.p + w->n; X.abort = cnt + CT_GS_ABORT;
+      void* argsX[] = {&R, &B, &U, &S, &T, &P, &G, &X};
+      W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_exact, dim3(w->coopBlocksGx), dim3(GX_THREADS), argsX, GX_SMEM_BYTES, s));
+    }
     else if (fast) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
     else W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs, dim3(w->coopBlocksGs), dim3(256), args, 0, s));
   }
@@ -1513,6 +1543,7 @@ static int32_t check_overflow_acc(cannon_world* w) {
   if (a[AC_OVF_ROWS] > 0) { snprintf(buf, sizeof buf, "row capacity exceeded: need %lld, have %d", a[AC_OVF_ROWS], w->rowCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
   if (a[AC_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
   if (a[AC_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
+  if (a[AC_GS_ABORT] > 0) return fail(w->ctx, CANNON_E_CUDA, "k_gs_exact: a dependency wait ran out (solver aborted instead of hanging)");
   return CANNON_OK;
 }
 
@@ -1525,6 +1556,7 @@ static int32_t check_overflow(cannon_world* w) {
   if (c[CT_OVF_ROWS] > 0) { snprintf(buf, sizeof buf, "row capacity exceeded: need %d, have %d", c[CT_OVF_ROWS], w->rowCap); return fail(w->ctx, CANNON_E_CAPACITY, buf); }
   if (c[CT_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
   if (c[CT_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
+  if (c[CT_GS_ABORT] > 0) return fail(w->ctx, CANNON_E_CUDA, "k_gs_exact: a dependency wait ran out (solver aborted instead of hanging)");
   return CANNON_OK;
 }
 
@@ -1930,6 +1962,11 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
     W_TRY(w, cudaMemcpy(q.data(), w->rRec.p, (size_t)n * 5 * sizeof(float4), cudaMemcpyDeviceToHost));
     W_TRY(w, cudaMemcpy(fl.data(), w->rFlambda.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; k++) { hB[k] = q[(size_t)k * 5].w; hC[k] = q[(size_t)k * 5 + 1].w; hL[k] = fl[k]; }
+  } else if (kind_packed(w)) {
+    std::vector<GxRow> q(n);
+    W_TRY(w, cudaMemcpy(q.data(), w->rXrec.p, (size_t)n * sizeof(GxRow), cudaMemcpyDeviceToHost));
+    W_TRY(w, cudaMemcpy(hL.data(), w->rLambda.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) { hB[k] = q[k].B; hC[k] = q[k].invC; }
   } else {
     W_TRY(w, cudaMemcpy(hB.data(), w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     W_TRY(w, cudaMemcpy(hC.data(), w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -41,7 +41,22 @@ struct RowArrays {
   int fast;
   float4* rec;     // 5 float4 per row, contiguous (80 B): (n,B) (rA,invC) (rB,eps) (iA,minF) (iB,maxF)
   float* flambda;
+  // COLORED (exact) single-world mode: the row as one 96-byte record the staged sweep k_gs_exact bulk-copies to shared
+  // memory - the f32-stored Jacobian exactly as the reference keeps it, the f64 scalars as f64 (lambda stays in `lambda`)
+  struct GxRow* xrec;
 };
+
+// bound codes of a packed exact row: [0, bound] (contact), [-bound, bound] (friction, joints), [-bound, 0] (cone / twist),
+// anything else keeps its bounds in RowArrays.minF / maxF
+enum { GXB_POS = 0, GXB_SYM = 1, GXB_NEG = 2, GXB_GENERAL = 3 };
+struct __align__(16) GxRow {
+  float nx, ny, nz; int code;      // code bit 0: rotational row (sA = 0 instead of -n); bits 2-3: GXB_*
+  float rAx, rAy, rAz, iAx;
+  float rBx, rBy, rBz, iAy;
+  float iBx, iBy, iBz, iAz;
+  double B, invC, eps, bound;
+};
+static_assert(sizeof(GxRow) == 96, "GxRow is bulk-copied as 96-byte records");
 
 // units: by unit id (u*) before scheduling, by execution position (e*) after
 struct UnitArrays {
@@ -54,9 +69,22 @@ struct UnitArrays {
   int* eRows;                                // rows per unit in exec order (scan input)
   int* unitRow;                              // unit id -> first execution row (debug / multipliers)
   int unitCap;
-  struct GsUnitRec* rec;                     // COLORED mode: the execution record the staged sweep copies to shared memory
+  struct GsUnitRec* rec;                     // COLORED_F32 mode: the execution record the staged sweep copies to shared memory
   int* eLevel;                               // colour of each execution position (per-world sweep of a batch)
+  struct GxUnit* xrec;                       // COLORED (exact) mode: execution record of k_gs_exact
+  const int* unitSeq;                        // per unit id: rank of the unit among the units of body i / body j (colour order)
+  const int* bodyCnt;                        // per body: number of scheduled units that move it
 };
+
+// one 64-byte record per unit in execution order (exact staged sweep). seqA / degA: the unit is the seqA-th of the degA
+// units that move body i (in colour order), so in iteration `it` it may run once done[bi] == it * degA + seqA.
+struct __align__(16) GxUnit {
+  int bi, bj, fl, r0;
+  int r1, seqA, degA, seqB;
+  int degB, pad0, pad1, pad2;
+  double imA, imB;
+};
+static_assert(sizeof(GxUnit) == 64, "GxUnit is bulk-copied as 64-byte records");
 
 // one 32-byte record per unit in execution order (COLORED mode), bulk-copied to shared memory by k_gs_fast
 struct __align__(16) GsUnitRec {
@@ -73,6 +101,7 @@ struct GsTasks {
   int* lvlWin;   // [nLevels] rows per task window of the colour
   int* nTasks;
   int taskCap;
+  int winMin, winMax;  // rows per task window (GS_WIN_* for the f32 sweep, GX_WIN_* for the exact one)
 };
 
 struct JointArrays {  // one entry per constraint equation (P2P: 3, hinge: 6), uploaded at set_constraints
@@ -145,6 +174,24 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, const R
     float4* q = R.rec + (size_t)row * 5;
     q[0] = st3(sB, (float)Bv); q[1] = st3(rA, (float)(1.0 / c)); q[2] = st3(rB, (float)eps);
     q[3] = st3(iA, (float)minF); q[4] = st3(iB, (float)maxF); R.flambda[row] = 0.f;
+    return;
+  }
+  if (R.xrec) {
+    GxRow q;
+    q.nx = sB.x; q.ny = sB.y; q.nz = sB.z;
+    q.rAx = rA.x; q.rAy = rA.y; q.rAz = rA.z; q.rBx = rB.x; q.rBy = rB.y; q.rBz = rB.z;
+    q.iAx = iA.x; q.iAy = iA.y; q.iAz = iA.z; q.iBx = iB.x; q.iBy = iB.y; q.iBz = iB.z;
+    q.B = Bv; q.invC = 1.0 / c; q.eps = eps;
+    int bc = GXB_GENERAL;
+    q.bound = maxF;
+    const long long mn = __double_as_longlong(minF), mx = __double_as_longlong(maxF);
+    if (mn == 0LL) bc = GXB_POS;
+    else if (mn == __double_as_longlong(-maxF)) bc = GXB_SYM;
+    else if (mx == 0LL) { bc = GXB_NEG; q.bound = -minF; }
+    else { R.minF[row] = minF; R.maxF[row] = maxF; }
+    q.code = ((kind == ROW_ROT || kind == ROW_MOTOR) ? 1 : 0) | (bc << 2);
+    R.xrec[row] = q;
+    R.lambda[row] = 0.0;
     return;
   }
   R.kind[row] = kind;
@@ -360,6 +407,8 @@ struct SchedArrays {
   unsigned* bar;
   int maxLevels;
   int* levelOverflow;
+  int* unitSeq;   // exact staged sweep: [2 * unit] rank of the unit among the units moving body i / body j, or null
+  int* bodyCnt;   // per body: units scheduled so far that move it
 };
 
 // Dependency levels by repeated "claim the bodies with the smallest pending priority": a unit is released in
@@ -412,6 +461,11 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
           // a unit without rows (a resolver task that produced no contact) is done here: it never enters the
           // execution order, so the sweeps do not have to step over it in every iteration
           emit = U.uRows[u] > 0;
+          // at most one unit wins a body per round, so the rank of a unit on its body follows the colour order
+          if (emit && S.unitSeq) {
+            S.unitSeq[2 * u] = (fl & 1) ? atomicAdd(&S.bodyCnt[U.uBi[u]], 1) : 0;
+            S.unitSeq[2 * u + 1] = (fl & 2) ? atomicAdd(&S.bodyCnt[U.uBj[u]], 1) : 0;
+          }
         }
       }
       const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
@@ -535,6 +589,15 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
       rec.grp = 0;
       if (nGroups > 1) { rec.grp = bodyGroup[rec.bi]; if (rec.grp < 0) rec.grp = bodyGroup[rec.bj]; }
       U.rec[a] = rec;
+    }
+    if (U.xrec) {
+      GxUnit x;
+      x.bi = U.eBi[a]; x.bj = U.eBj[a]; x.fl = U.eFlags[a]; x.r0 = row; x.r1 = U.eRowBase[a + 1];
+      x.seqA = U.unitSeq[2 * u]; x.seqB = U.unitSeq[2 * u + 1];
+      x.degA = (x.fl & 1) ? U.bodyCnt[x.bi] : 0; x.degB = (x.fl & 2) ? U.bodyCnt[x.bj] : 0;
+      x.pad0 = x.pad1 = x.pad2 = 0;
+      x.imA = U.eImA[a]; x.imB = U.eImB[a];
+      U.xrec[a] = x;
     }
     if (U.eRows[a] == 0) continue;
     const int src = U.uSrc[u], kind = src & 7, idx = src >> 3;
@@ -927,8 +990,8 @@ __global__ void __launch_bounds__(256) k_gs_task_levels(UnitArrays U, SchedArray
     if (l < nLevels) {
       const int u0 = S.levelStart[l], u1 = S.levelStart[l + 1];
       const int rows = U.eRowBase[u1] - U.eRowBase[u0], units = u1 - u0;
-      int win = GS_WIN_MIN;
-      if (rows > 0 && units > 0) win = min(GS_WIN_MAX, max(GS_WIN_MIN, (int)((32LL * rows + units - 1) / units)));
+      int win = T.winMin;
+      if (rows > 0 && units > 0) win = min(T.winMax, max(T.winMin, (int)((32LL * rows + units - 1) / units)));
       T.lvlWin[l] = win;
       n = (rows + win - 1) / win;
     }

@@ -24,7 +24,19 @@ CASES = {
     "c4_small": (lambda: scenes.chain_worlds(3, chains=2, links=4), 60),
     "c5_small": (lambda: scenes.sphere_container(6, 6, 4, extent=5.0, solver=REF), 120),
     "joints_small": (lambda: scenes.constraint_zoo(groups=2), 120),
+    # COLORED (the throughput solver bench.py times): GSSolver's arithmetic in the colour order of include/cannon_cuda.h
+    "c2_colored_small": (lambda: _with(scenes.box_stacks(4, 5, grid=2), solver_kind=F.SOLVER_COLORED), 60),
+    "c3_hf_colored_small": (lambda: scenes.mixed_pile_on_heightfield(4, 4, 3, hf_samples=33, solver=F.SOLVER_COLORED, grid_cells=(8, 4, 8)), 90),
+    "c4_colored_small": (lambda: _with(scenes.chain_worlds(3, chains=2, links=4), solver_kind=F.SOLVER_COLORED), 60),
+    # World(quatNormalizeFast: true, quatNormalizeSkip: 2, frictionGravity: ...) (world_class.dart:135-144,668; quaternion.dart:171-185)
+    "c2_quatfast_small": (lambda: _with(scenes.mixed_pile_on_heightfield(4, 4, 3, with_heightfield=False, solver=REF, grid_cells=(8, 4, 8)),
+                                        quat_normalize_fast=1, quat_normalize_skip=2, has_friction_gravity=1, friction_gravity=(0, -3, 0)), 90),
 }
+
+
+def _with(spec, **desc):
+    spec.desc.update(desc)
+    return spec
 
 
 def run_case(lib, make_spec, steps):

@@ -217,7 +217,8 @@ def test_cone_equation_limits_the_swing(oracle_lib):
     assert free > 60 and cone < 35, (free, cone)
 
 
-GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small"]
+GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small",
+                "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

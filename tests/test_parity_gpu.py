@@ -126,7 +126,52 @@ def test_colored_solver_fused_step_parity(cuda_lib, oracle_lib, name):
                (pb["n_pairs"], pb["n_contacts"], pb["n_rows"], pb["iterations_done"], pb["n_levels"])
 
 
-@pytest.mark.parametrize("name", ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small"])
+# BASELINE configurations at their stated sizes (c3 at 1/16 of the lattice on the full 257-sample field: the oracle needs
+# ~7 s per step at 100k bodies). REF = the reference's insertion order, COLORED = the solver bench.py times.
+FULL = {
+    "c1 full: 1000 spheres on a plane, Naive, 600 steps": (lambda: scenes.spheres_on_plane(10, 10, 10), 600, 100),
+    "c2 full: 250 x 20 box stacks, SAP, 20 it, 30 steps": (lambda: scenes.box_stacks(250, 20), 30, 10),
+    "c3: 6250 bodies on the 257-sample heightfield, Grid 128x16x128, 150 steps": (lambda: scenes.mixed_pile_on_heightfield(25, 25, 10, solver=REF), 150, 50),
+    "c4: 64 worlds x 64 bodies, P2P + hinge chains, 120 steps": (lambda: scenes.chain_worlds(64), 120, 40),
+}
+
+
+@pytest.mark.parametrize("kind", ["reference", "colored"])
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_size_configs_fused_parity(cuda_lib, oracle_lib, name, kind):
+    mk, steps, chunk = FULL[name]
+    spec = _with(mk(), solver_kind=REF if kind == "reference" else F.SOLVER_COLORED)
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    most = 0
+    for s in range(0, steps, chunk):
+        dev.step(1 / 60, chunk)
+        ref.step(1 / 60, chunk)
+        parity.assert_same_state(dev, ref, f"{name} [{kind}] after {s + chunk} steps")
+        pa, pb = dev.profile(), ref.profile()
+        assert (pa["n_pairs"], pa["n_contacts"], pa["n_rows"], pa["iterations_done"]) == (pb["n_pairs"], pb["n_contacts"], pb["n_rows"], pb["iterations_done"])
+        most = max(most, pa["n_contacts"])
+    assert most > 0
+    # the refitted AABBs themselves (Body.updateAABB, rigid_body.dart:415-447), not only the pair lists they lead to
+    a, b = dev.get_bodies(("aabb",)), ref.get_bodies(("aabb",))
+    assert np.array_equal(a["aabb"], b["aabb"]), f"{name}: AABB arrays differ"
+
+
+@pytest.mark.parametrize("opts", [dict(quat_normalize_fast=1), dict(quat_normalize_skip=3), dict(quat_normalize_fast=1, quat_normalize_skip=1),
+                                  dict(has_friction_gravity=1, friction_gravity=(0, -2, 0)), dict(has_friction_gravity=1, friction_gravity=(3, 0, -4))])
+def test_world_options_quat_normalize_and_friction_gravity(cuda_lib, oracle_lib, opts):
+    # World(quatNormalizeFast / quatNormalizeSkip / frictionGravity): world_class.dart:135-144,668, quaternion.dart:171-185,
+    # narrow_phase.dart:547-550
+    spec = _with(scenes.mixed_pile_on_heightfield(5, 5, 3, with_heightfield=False, solver=REF, grid_cells=(8, 4, 8)), **opts)
+    spec.bodies["angular_velocity"][1:] = (0.7, -1.3, 0.4)  # tumbling boxes and cylinders: the normalisation branch matters
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    for s in range(90):
+        parity.staged_step(dev, ref, 1 / 60, f"{opts} step {s}")
+    a, b = dev.get_bodies(("aabb",)), ref.get_bodies(("aabb",))
+    assert np.array_equal(a["aabb"], b["aabb"])
+
+
+@pytest.mark.parametrize("name", ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small",
+                                  "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small"])
 def test_cuda_matches_golden_fixture(cuda_lib, name):
     from make_golden import CASES, run_case
     got = run_case(cuda_lib, *CASES[name])
