@@ -29,7 +29,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NROWS_PAD, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -183,7 +183,9 @@ struct cannon_world {
   DBuf<double> rB, rInvC, rEps, rMinF, rMaxF, rLambda;
   DBuf<float4> rRec;
   DBuf<GsUnitRec> uRec;
-  DBuf<GxRow> rXrec;      // COLORED (exact), single world: packed rows / unit records of k_gs_exact
+  DBuf<float4> rXblk;     // COLORED (exact), single world: window-interleaved row blocks / unit records of k_gs_exact
+  DBuf<int> gxWinRows, gxWinBase;  // row slots per window (32 x longest unit) and their exclusive scan
+  int gxWinCap = 0;
   DBuf<GxUnit> uXrec;
   DBuf<int> unitSeq, gxBody;  // per unit: ranks on its two bodies; per body: [0, n) scheduled units, [n, 2n) progress counters
   // contact events (opt-in)
@@ -424,7 +426,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   cudaFuncSetAttribute(k_gs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_exact, GX_THREADS, GX_SMEM_BYTES);
-  w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, 2));
+  w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, GX_CTAS_PER_SM));
   w->gxOff = getenv("CANNON_GS_NO_DATAFLOW") != nullptr;
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
   w->gsNoLenSort = getenv("CANNON_GS_NO_LEN_SORT") != nullptr;
@@ -455,7 +457,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
   REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(uKey); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
-  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(rXrec); REL(uXrec); REL(unitSeq); REL(gxBody); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
+  REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(rXblk); REL(gxWinRows); REL(gxWinBase); REL(uXrec); REL(unitSeq); REL(gxBody); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
   REL(worldRows); REL(worldDone); REL(worldIters); REL(worldTot); REL(dClock); REL(spBodyA); REL(spBodyB); REL(spOff); REL(spIdx); REL(spRest); REL(spK); REL(spD); REL(spAnchorA); REL(spAnchorB); REL(gsTrace); REL(cnt); REL(acc); REL(stage); REL(islandLabel);
@@ -742,10 +744,11 @@ static int32_t ensure_capacities(cannon_world* w) {
     w->gsTaskCap = rowCap / GS_WIN_MIN + w->maxLevels + 2;
     RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
   } else if (kind_packed(w)) {
-    RES(rXrec, rowCap + 1); RES(uXrec, rowCap + 3); RES(rMinF, rowCap); RES(rMaxF, rowCap); RES(rLambda, rowCap + 4);
-    w->gsTaskCap = rowCap / GX_WIN_MIN + w->maxLevels + 2;
-    RES(gsTab, w->gsTaskCap + 2); RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
-    RES(unitSeq, 2 * ((size_t)rowCap + 2)); RES(gxBody, 2 * (size_t)n + 2);
+    RES(rXblk, ((size_t)rowCap / 32 + 2) * GX_CHUNKS * 32); RES(uXrec, rowCap + 3); RES(rMinF, rowCap + 32); RES(rMaxF, rowCap + 32); RES(rLambda, rowCap + 64);
+    w->gxWinCap = rowCap / 32 + w->maxLevels + 2;
+    RES(gxWinRows, w->gxWinCap + 1); RES(gxWinBase, w->gxWinCap + 1);
+    w->gsTaskCap = 0x7fffffff;
+    RES(gsLvlTask, w->maxLevels + 2);
   } else {
     RES(rKind, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
     RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
@@ -1280,7 +1283,7 @@ static RowArrays row_arrays(cannon_world* w) {
   R.rowCap = w->rowCap;
   R.fast = kind_fast(w) ? 1 : 0;
   R.rec = w->rRec.p; R.flambda = w->rFlambda.p;
-  R.xrec = kind_packed(w) ? w->rXrec.p : nullptr;
+  R.xblk = kind_packed(w) ? w->rXblk.p : nullptr;
   return R;
 }
 static UnitArrays unit_arrays(cannon_world* w) {
@@ -1290,7 +1293,8 @@ static UnitArrays unit_arrays(cannon_world* w) {
   U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p; U.eLevel = w->eLevel.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
   const bool packed = kind_packed(w);
-  U.xrec = packed ? w->uXrec.p : nullptr; U.unitSeq = packed ? w->unitSeq.p : nullptr; U.bodyCnt = packed ? w->gxBody.p : nullptr;
+  U.xrec = packed ? w->uXrec.p : nullptr; U.unitSeq = nullptr; U.bodyCnt = nullptr;
+  U.winBase = w->gxWinBase.p; U.lvlWin = w->gsLvlTask.p; U.levelStart = w->levelStart.p; U.padTotal = w->cnt.p + CT_NROWS_PAD;
   return U;
 }
 static JointArrays joint_arrays(cannon_world* w) {
@@ -1401,8 +1405,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   S.act0 = w->act0.p; S.act1 = w->act1.p; S.actCount = cnt + CT_ACT0; S.cursor = cnt + CT_CURSOR; S.bar = (unsigned*)(cnt + CT_BAR);
   S.maxLevels = w->maxLevels; S.levelOverflow = cnt + CT_OVF_LEVELS;
   const bool packed = kind_packed(w);
-  S.unitSeq = packed ? w->unitSeq.p : nullptr; S.bodyCnt = packed ? w->gxBody.p : nullptr;
-  if (packed) W_TRY(w, cudaMemsetAsync(w->gxBody.p, 0, (2 * (size_t)w->n + 2) * sizeof(int), s));
+  S.unitSeq = nullptr; S.bodyCnt = nullptr;
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
   if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
   {
@@ -1451,11 +1454,18 @@ static int32_t st_solve(cannon_world* w, double dt) {
   { g_kernel_launches++; k_zero_tail<<<1, 32, 0, s>>>(w->eRows.p, cnt + CT_NEXEC, w->unitCap); }
   { g_kernel_launches++; k_units_plus_one<<<1, 32, 0, s>>>(cnt); }
   W_TRY(w, scan_exclusive(w->eRows.p, w->eRowBase.p, cnt + CT_NUNITS1, 0, w->unitCap + 1, nullptr, w->scanTmp, s));
-  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, order, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
   GsTasks T;
   T.tab = w->gsTab.p; T.lvlTask = w->gsLvlTask.p; T.lvlWin = w->gsLvlWin.p; T.nTasks = cnt + CT_GS_NTASKS; T.taskCap = w->gsTaskCap;
-  T.winMin = packed ? GX_WIN_MIN : GS_WIN_MIN; T.winMax = packed ? GX_WIN_MAX : GS_WIN_MAX;
-  if ((fast && !w->gsFastV1 && !perWorld) || packed) {
+  T.winMin = packed ? 0 : GS_WIN_MIN; T.winMax = packed ? 0 : GS_WIN_MAX;
+  if (packed) {
+    // windows of 32 units per colour, their row slots (32 x longest unit of the window), then the rows at those slots
+    { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
+    { g_kernel_launches++; k_gx_windows<<<grid_for(w, 32LL * w->gxWinCap, 256), 256, 0, s>>>(U, w->levelStart.p, cnt + CT_NLEVELS, w->gsLvlTask.p, w->gxWinRows.p, w->gxWinCap, cnt + CT_OVF_ROWS); }
+    W_TRY(w, scan_exclusive(w->gxWinRows.p, w->gxWinBase.p, nullptr, w->gxWinCap, w->gxWinCap, cnt + CT_NROWS_PAD, w->scanTmp, s));
+  }
+  { g_kernel_launches++; k_rows_build<<<grid_for(w, w->unitCap, 128), 128, 0, s>>>(B, C, Us, J, U, R, P, order, cnt + CT_OVF_ROWS, split ? w->islandLabel.p : w->world.p, nGroups); }
+  if (packed) {
+  } else if (fast && !w->gsFastV1 && !perWorld) {
     { g_kernel_launches++; k_gs_task_levels<<<1, 256, 0, s>>>(U, S, T, cnt + CT_OVF_ROWS); }
     { g_kernel_launches++; k_gs_task_fill<<<grid_for(w, w->gsTaskCap + 1, 256), 256, 0, s>>>(U, S, T); }
   }
@@ -1482,8 +1492,8 @@ static int32_t st_solve(cannon_world* w, double dt) {
     } else if (fast && w->gsFastV1) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast_v1, dim3(w->coopBlocksGsFastV1), dim3(256), args, 0, s));
     else if (packed) {
       GxState X;
-      X.done = w->gxBody.p + w->n; X.abort = cnt + CT_GS_ABORT;
-      void* argsX[] = {&R, &B, &U, &S, &T, &P, &G, &X};
+      X.lvlTask = w->gsLvlTask.p;
+      void* argsX[] = {&R, &B, &U, &S, &P, &G, &X};
       W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_exact, dim3(w->coopBlocksGx), dim3(GX_THREADS), argsX, GX_SMEM_BYTES, s));
     }
     else if (fast) W_TRY(w, cudaLaunchCooperativeKernel((void*)k_gs_fast, dim3(w->coopBlocksGsFast), dim3(GS_THREADS), argsT, GS_SMEM_BYTES, s));
@@ -1963,10 +1973,16 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
     W_TRY(w, cudaMemcpy(fl.data(), w->rFlambda.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     for (int k = 0; k < n; k++) { hB[k] = q[(size_t)k * 5].w; hC[k] = q[(size_t)k * 5 + 1].w; hL[k] = fl[k]; }
   } else if (kind_packed(w)) {
-    std::vector<GxRow> q(n);
-    W_TRY(w, cudaMemcpy(q.data(), w->rXrec.p, (size_t)n * sizeof(GxRow), cudaMemcpyDeviceToHost));
-    W_TRY(w, cudaMemcpy(hL.data(), w->rLambda.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < n; k++) { hB[k] = q[k].B; hC[k] = q[k].invC; }
+    // slot index = block * 32 + lane; B / invC are chunk 4 of the block (k_solver.cuh, GxRow)
+    const int nSlots = std::max(n, w->hCnt[CT_NROWS_PAD]);
+    std::vector<float4> q(((size_t)nSlots / 32 + 1) * GX_CHUNKS * 32);
+    W_TRY(w, cudaMemcpy(q.data(), w->rXblk.p, q.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    hB.assign(nSlots + 32, 0.0); hC.assign(nSlots + 32, 0.0); hL.assign(nSlots + 32, 0.0);
+    W_TRY(w, cudaMemcpy(hL.data(), w->rLambda.p, nSlots * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < nSlots; k++) {
+      const double* d = (const double*)&q[((size_t)(k >> 5) * GX_CHUNKS + 4) * 32 + (k & 31)];
+      hB[k] = d[0]; hC[k] = d[1];
+    }
   } else {
     W_TRY(w, cudaMemcpy(hB.data(), w->rB.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     W_TRY(w, cudaMemcpy(hC.data(), w->rInvC.p, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1992,8 +2008,9 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
   }
   for (int k = 0; k < ne; k++) {
     const int u = unitsInOrder[k];
+    const int rstride = kind_packed(w) ? 32 : 1;  // consecutive rows of a unit sit in consecutive blocks of its window
     for (int q = 0; q < uRows[u] && out < n; q++, out++) {
-      const int r = uRow[u] + q;
+      const int r = uRow[u] + q * rstride;
       if (body_i) body_i[out] = uBi[u];
       if (body_j) body_j[out] = uBj[u];
       if (B) B[out] = hB[r];

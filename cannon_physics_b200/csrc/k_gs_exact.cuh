@@ -1,319 +1,275 @@
 // k_gs_exact.cuh — the COLORED solver's production sweep: GSSolver's arithmetic (gs_solver.dart:76-108, f64 on f32-stored
-// operands, no FMA, every Vector3 store rounds to float) over the colour order of include/cannon_cuda.h, as a staged
-// DATAFLOW kernel.
+// operands, no FMA, every Vector3 store rounds to float) over the colour order of include/cannon_cuda.h.
 //
-// Two units conflict only if they move the same body; the colouring puts the units of a body into distinct colours, so per
-// body there is a fixed sequence of units (ascending colour). Executing every unit after its predecessor ON EACH OF ITS TWO
-// BODIES performs exactly the floating-point operations of the colour-by-colour sweep on exactly the same operands - no
-// matter how the units of different bodies interleave. The kernel therefore has no grid barrier between colours:
-//   * k_schedule hands every unit its rank seq among the deg units of each of its movable bodies;
-//   * done[b] counts the units that have updated body b in this solve; a unit of iteration `it` runs when
-//     done[b] == it * deg + seq on both bodies, then publishes done[b] + 1 (fence + flag store / acquire load);
-//   * a warp owns a window of consecutive units of one colour (one unit per lane) and walks its windows in (iteration,
-//     colour) order. That order is a topological order of the dependencies and all warps are co-resident (cooperative
-//     launch), so the globally first unfinished window can always run: no deadlock. Every spin is bounded anyway and
-//     raises `abort` (reported as an error) instead of hanging the device.
-// The only grid barrier left is the one per iteration that the tolerance test of gs_solver.dart:105 needs.
-// Rows (96-byte GxRow records, built in execution order), unit records and the rows' multipliers are bulk-copied global ->
-// shared with cp.async.bulk one window ahead of the warp, across colour and iteration boundaries (rows never change during
-// a solve), exactly like the f32 sweep k_gs_fast.
+// Persistent cooperative kernel, one grid barrier per colour phase (units of a colour touch disjoint movable bodies, so a
+// phase is embarrassingly parallel and the result does not depend on how its units are spread over lanes and warps).
+//   * A window = 32 consecutive units of one colour, one unit per lane. Units of a colour are ordered by row count
+//     (k_len_*), so the lanes of a window carry equal work; windows are dealt to the warps round robin with a per-colour
+//     rotation (the long windows of every colour land on different warps).
+//   * Rows are stored window-interleaved (k_solver.cuh, GxRow): block r of a window holds row r of each of its 32 units,
+//     chunk by chunk, so one row step of a warp reads 3 KB of contiguous memory with coalesced 16-byte accesses. Every lane
+//     streams ITS rows global -> shared with cp.async into a private four-slot ring (three rows in flight while one is
+//     solved): the L2 latency of a row hides behind the f64 dependency chain of the previous ones, without spending
+//     registers on it; the window's remaining blocks are prefetched into L2 one phase ahead.
+//   * The unit records and the first rows of a warp's NEXT window are requested before the grid barrier (rows never change
+//     during a solve), so after the barrier only the body-lambda gather (L2) stands before the arithmetic.
+//   * 16 warps per SM (two CTAs) hide the latency of the f64 chains (~16 dependent DP operations per row).
+// History on the settled 100k pile of config 3 (1.36e6 rows, 10 colours, 10 iterations; profiles/README.md):
+//   unstaged level sweep k_gs 3.43 ms -> TMA-staged per-warp row windows with per-body dataflow counters 1.74 ms (8 warps
+//   per SM, 12 of 32 lanes busy: instruction-latency bound) -> 32-unit windows, dynamic claiming, dataflow 2.32 ms (every
+//   iteration drains at the tolerance barrier; a window waits for the slowest of its 64 predecessors, i.e. dataflow
+//   degenerates to one barrier per colour plus polling traffic) -> this kernel.
 #pragma once
 #include "k_solver.cuh"
 
 #define GX_WARPS 8
 #define GX_THREADS (GX_WARPS * 32)
-#define GX_CAP_ROWS 104
-#define GX_CAP_UNITS 40
-#define GX_WIN_MIN 72
-#define GX_WIN_MAX 80
-#define GX_ROW_BYTES 96
-#define GX_UNIT_BYTES 64
-#define GX_LAM_REGS ((GX_CAP_ROWS + 31) / 32)
-#define GX_UNIT_OFF (GX_CAP_ROWS * GX_ROW_BYTES)
-#define GX_LAM_OFF (GX_UNIT_OFF + GX_CAP_UNITS * GX_UNIT_BYTES)
-#define GX_LAM_BYTES ((GX_CAP_ROWS + 2) * 8)  // the multiplier range is copied from a 16-byte aligned start: one double of slack each side
-#define GX_BUF_BYTES (GX_LAM_OFF + GX_LAM_BYTES)
-#define GX_WARP_BYTES (2 * GX_BUF_BYTES)
-#define GX_SMEM_BYTES (GX_WARPS * GX_WARP_BYTES)
+#define GX_CTAS_PER_SM 2
 #define GX_LS_MAX 1024
-#define GX_SPIN_LIMIT (1 << 20)
+#define GX_SLOTS 4                       // ring slots per lane: GX_SLOTS - 1 rows in flight
+#define GX_SLOT_BYTES (GX_CHUNKS * 32 * 16 + 32 * 8)  // six 16-byte chunks + the row's multiplier (8 bytes) per lane
+#define GX_WARP_BYTES (GX_SLOTS * GX_SLOT_BYTES)
+#define GX_SMEM_BYTES (GX_WARPS * GX_WARP_BYTES)
 
+__device__ __forceinline__ int4 ldnc_i4(const void* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void ldnc_d2(const void* p, double& a, double& b) { asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p)); }
+__device__ __forceinline__ double ldcg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stcg_f64(double* p, double v) { asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ double lds_f64(unsigned a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_i32(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_i32(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-// grid barrier that gives up when another CTA raised `abort` (a dependency wait timed out): nobody is left spinning
-__device__ __forceinline__ bool grid_barrier_abortable(unsigned* bar, unsigned& epoch, int nCtas, const int* abortFlag) {
-  __shared__ int s_ab;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int ab = 0;
-    if (nCtas > 1) {
-      epoch += 1;
-      const unsigned target = epoch * (unsigned)nCtas;
-      unsigned v;
-      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(bar) : "memory");
-      v += 1u;
-      int spins = 0;
-      while (v < target) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        if ((++spins & 255) == 0 && ld_acquire_i32(abortFlag)) { ab = 1; break; }
-        if (spins > GX_SPIN_LIMIT) { ab = 1; break; }
-      }
-    }
-    if (!ab) ab = ld_acquire_i32(abortFlag);
-    s_ab = ab;
-  }
-  __syncthreads();
-  return s_ab != 0;
-}
+__device__ __forceinline__ void lds_d2(unsigned a, double& x, double& y) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory"); }
+__device__ __forceinline__ void cp_async8_s(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async16_s(unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
 struct GxState {
-  int* done;    // [nBodies] units that have updated the body in this solve (zeroed before the launch)
-  int* abort;   // raised when a bounded wait ran out (reported by the host as an error)
+  const int* lvlTask;  // [nLevels + 1] first window of each colour (k_gs_task_levels, windows of 32 units)
 };
 
-__global__ void __launch_bounds__(GX_THREADS, 1) k_gs_exact(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, GsTasks T, SolveParams P, GsStats G,
-                                                            GxState X) {
+struct GxWin { int a, lvl, it; };  // a: window index inside the iteration, -1 = none
+
+__global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G,
+                                                                         GxState X) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
-  __shared__ unsigned long long s_mbar[GX_WARPS][2];
   __shared__ double s_red[GX_WARPS];
   __shared__ int s_lt[GX_LS_MAX + 2];
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
   const int nLevels = *S.nLevels;
-  if (*T.nTasks > T.taskCap) return;  // reported through the row-overflow counter by k_gs_task_levels
-  // the dataflow needs parallel slack, not one CTA per colour width: every resident CTA takes part unless the solve is tiny
-  const int nCtas = coop_ctas(4LL * min(*T.nTasks, T.taskCap) + 1, GX_WARPS);
+  const int nTasks = X.lvlTask[nLevels];  // windows per iteration
+  // CTAs for about twice the mean number of windows per colour
+  const int nCtas = coop_ctas(2LL * nTasks / max(nLevels, 1) + 1, GX_WARPS);
   if ((int)blockIdx.x >= nCtas) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  if (nRows == 0) { if (tid == 0) *G.itersDone = 0; return; }
-  const int* lt = T.lvlTask;
+  if (nRows == 0 || nTasks == 0) { if (tid == 0) *G.itersDone = 0; return; }
+  const int* lt = X.lvlTask;
   if (nLevels <= GX_LS_MAX) {
-    for (int k = threadIdx.x; k <= nLevels; k += blockDim.x) s_lt[k] = T.lvlTask[k];
+    for (int k = threadIdx.x; k <= nLevels; k += blockDim.x) s_lt[k] = X.lvlTask[k];
     lt = s_lt;
   }
-  if (lane == 0) { mbar_init(&s_mbar[wic][0], 1); mbar_init(&s_mbar[wic][1], 1); }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  unsigned char* wbase = s_dyn + (size_t)wic * GX_WARP_BYTES;
-  // windows of a colour are dealt to the warps CTA-interleaved so a narrow colour still spreads over every SM
+  const float4* const xblk = R.xblk;
+  // this lane's ring: slot s, chunk c at ring + s * GX_SLOT_BYTES + c * 512 (lanes interleaved by 16 B: conflict-free
+  // LDS.128); the row's multiplier at ringL + s * GX_SLOT_BYTES (lanes interleaved by 8 B)
+  const unsigned ring = smem_u32(s_dyn) + (unsigned)wic * GX_WARP_BYTES + (unsigned)lane * 16u;
+  const unsigned ringL = smem_u32(s_dyn) + (unsigned)wic * GX_WARP_BYTES + GX_CHUNKS * 512u + (unsigned)lane * 8u;
+  // windows of a colour are dealt to the warps CTA-interleaved, rotated per colour
   const int gw = wic * nCtas + blockIdx.x, nW = nCtas * GX_WARPS;
 
-  GsTask t0, t1, t2;
-  int2 x0, y0, x1, y1, x2, y2;  // table entries [a], [a+1] of the three tasks: (first unit, first row)
-  auto table = [&](const GsTask& t, int2& x, int2& y) {
-    x = make_int2(0, 0); y = x;
-    if (t.a >= 0) { x = __ldg(&T.tab[t.a]); y = __ldg(&T.tab[t.a + 1]); }
-  };
-  auto next = [&](const GsTask& t) {
-    GsTask n = t;
-    if (n.a >= 0) { n.a += nW; gs_seek(lt, nLevels, P.maxIter, gw, n); }
-    return n;
-  };
-  // unit records, rows and (withLam) the rows' multipliers of a window: three bulk copies on one mbarrier
-  auto issue = [&](const int2& x, const int2& y, int b, bool withLam) -> bool {
-    const int nUs = min(y.x - x.x, GX_CAP_UNITS), nRs = min(y.y - x.y, GX_CAP_ROWS);
-    if (nUs <= 0) return false;
-    if (lane == 0) {
-      unsigned char* dst = wbase + (size_t)b * GX_BUF_BYTES;
-      // the buffer was last written with ordinary shared stores (multipliers of an earlier window): order them before the
-      // async-proxy writes of the bulk copies
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const int a0 = x.y & ~1;
-      const unsigned lamBytes = (withLam && nRs > 0) ? (unsigned)(((x.y + nRs - a0 + 1) & ~1) * 8) : 0u;
-      mbar_expect_tx(&s_mbar[wic][b], (unsigned)(nUs * GX_UNIT_BYTES + nRs * GX_ROW_BYTES) + lamBytes);
-      bulk_g2s(dst + GX_UNIT_OFF, U.xrec + x.x, (unsigned)(nUs * GX_UNIT_BYTES), &s_mbar[wic][b]);
-      if (nRs > 0) bulk_g2s(dst, R.xrec + x.y, (unsigned)(nRs * GX_ROW_BYTES), &s_mbar[wic][b]);
-      if (lamBytes) bulk_g2s(dst + GX_LAM_OFF, R.lambda + a0, lamBytes, &s_mbar[wic][b]);
+  // Window j of a colour goes to warp slot (j * 1223 + colour * 61) mod nW inside each round of nW windows: windows are
+  // sorted by length, so neighbours in j are equally long - the multiplier scatters the long ones over all SM sub-partitions.
+  int gwInv = 0;
+  {  // inverse of x -> x * 1223 mod nW (1223 is prime and does not divide nW = 8 * nCtas for any grid used here)
+    long long a = 1223 % nW, b = nW, x0 = 1, x1 = 0;
+    while (b) { const long long q = a / b, t2 = a - q * b; a = b; b = t2; const long long t3 = x0 - q * x1; x0 = x1; x1 = t3; }
+    gwInv = (int)(((x0 % nW) + nW) % nW);  // a == gcd == 1
+  }
+  auto first_in = [&](int lvl) { return lt[lvl] + (int)(((long long)((gw - (lvl * 61) % nW + nW) % nW) * gwInv) % nW); };
+  auto seek = [&](GxWin& t) {  // t.a is a candidate inside colour t.lvl: move on to the warp's next window
+    int hops = 0;
+    while (t.a >= lt[t.lvl + 1]) {
+      if (++hops > nLevels) { t.a = -1; return; }  // the warp owns no window in any colour
+      if (++t.lvl == nLevels) { t.lvl = 0; if (++t.it >= P.maxIter) { t.a = -1; return; } }
+      t.a = first_in(t.lvl);
     }
-    return true;
   };
 
-  t0.a = lt[0] + gw; t0.lvl = 0; t0.it = 0;
-  gs_seek(lt, nLevels, P.maxIter, gw, t0);
-  t1 = next(t0);
-  table(t0, x0, y0);
-  table(t1, x1, y1);
-  int buf = 0;
-  unsigned parity = 0;  // bit b: phase parity of buffer b's mbarrier
-  bool pend0 = issue(x0, y0, 0, true), pend1 = false;
-  bool aborted = false;
+  GxUnit m;         // unit of this lane in the warp's current window
+  bool act = false; // the lane has a unit with rows
+  // unit record of window t into registers + the first GX_SLOTS - 1 rows into the ring (GX_SLOTS - 1 groups committed)
+  auto prime = [&](const GxWin& t) {
+    act = false;
+    m.fl = 0; m.r0 = m.r1 = 0; m.bi = m.bj = 0; m.imA = m.imB = 0.0;
+    if (t.a >= 0) {
+      const int a0 = S.levelStart[t.lvl], a1 = S.levelStart[t.lvl + 1];
+      const int u = a0 + 32 * (t.a - lt[t.lvl]) + lane;
+      if (u < a1) {
+        const int4* up = (const int4*)(U.xrec + u);
+        const int4 a = ldnc_i4(up), b = ldnc_i4(up + 1);
+        m.bi = a.x; m.bj = a.y; m.fl = a.z; m.r0 = a.w; m.r1 = b.x;
+        ldnc_d2(up + 3, m.imA, m.imB);
+        act = m.r1 > m.r0;
+      }
+    }
+    const int nr = act ? (m.r1 - m.r0) >> 5 : 0;
+    // The ring keeps three rows in flight per lane, which hides L2 latency but not DRAM latency (a lane walks its rows one
+    // after the other). So the rest of the window's blocks are pulled into L2 right away - this runs before the grid
+    // barrier of the previous phase, i.e. the DRAM time of a phase's rows overlaps the phase before it.
+    int nrMax = nr, blk0 = act ? m.r0 >> 5 : 0;
+    for (int o = 16; o > 0; o >>= 1) { nrMax = max(nrMax, __shfl_xor_sync(0xffffffffu, nrMax, o)); blk0 = max(blk0, __shfl_xor_sync(0xffffffffu, blk0, o)); }
+    {
+      const unsigned char* q = (const unsigned char*)(xblk + (size_t)blk0 * (GX_CHUNKS * 32));
+      const int nb = nrMax * GX_CHUNKS * 512;
+      for (int o = (GX_SLOTS - 1) * GX_CHUNKS * 512 + lane * 128; o < nb; o += 32 * 128) prefetch_l2(q + o);
+      const unsigned char* ql = (const unsigned char*)(R.lambda + (size_t)blk0 * 32);  // the rows' multipliers: 256 B per block
+      for (int o = lane * 128; o < nrMax * 256; o += 32 * 128) prefetch_l2(ql + o);
+    }
+#pragma unroll
+    for (int r = 0; r < GX_SLOTS - 1; r++) {
+      if (r < nr) {
+        const float4* q = xblk + (size_t)((m.r0 >> 5) + r) * (GX_CHUNKS * 32) + lane;
+        const unsigned d = ring + (unsigned)(r * GX_SLOT_BYTES);
+#pragma unroll
+        for (int c = 0; c < GX_CHUNKS; c++) cp_async16_s(d + c * 512, q + c * 32);
+        cp_async8_s(ringL + (unsigned)(r * GX_SLOT_BYTES), R.lambda + m.r0 + 32 * r);
+      }
+      cp_async_commit();
+    }
+  };
+
+  GxWin t;
+  t.lvl = 0; t.it = 0; t.a = first_in(0);
+  seek(t);
+  prime(t);
 
   int iter = 0;
-  for (; iter != P.maxIter && !aborted; iter++) {
+  int trN = 0;
+  for (; iter != P.maxIter; iter++) {
     double local = 0.0;
-    while (t0.a >= 0 && t0.it == iter) {
-      // the warp's next window is this one again (it owns a single window per iteration): its multipliers are handed over
-      // shared -> shared after the solve instead of being fetched
-      const bool sameNext = t1.a == t0.a;
-      pend1 = issue(x1, y1, buf ^ 1, !sameNext);
-      t2 = next(t1);
-      table(t2, x2, y2);
-      const int u0 = x0.x, nU = y0.x - x0.x, rBase = x0.y;
-      const int nUs = min(nU, GX_CAP_UNITS), nRs = min(y0.y - x0.y, GX_CAP_ROWS);
-      if (pend0) { mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u); parity ^= 1u << buf; pend0 = false; }
-      const unsigned char* sb = wbase + (size_t)buf * GX_BUF_BYTES;
-      const GxUnit* sunits = (const GxUnit*)(sb + GX_UNIT_OFF);
-      double* const slam = (double*)(wbase + (size_t)buf * GX_BUF_BYTES + GX_LAM_OFF) + (rBase & 1);
-      int flushEnd = nRs;
-      for (int ub = 0; ub < nU && !aborted; ub += 32) {
-        const int u = ub + lane;
-        const bool have = u < nU;
-        GxUnit m;
-        m.fl = 0; m.r0 = m.r1 = 0; m.bi = m.bj = 0; m.seqA = m.seqB = m.degA = m.degB = 0; m.imA = m.imB = 0.0;
-        if (have) m = u < nUs ? sunits[u] : U.xrec[u0 + u];
-        const bool work = have && m.r1 > m.r0;
-        const bool staged = work && m.r1 - rBase <= nRs;
-        if (work && !staged) flushEnd = min(flushEnd, m.r0 - rBase);  // that unit keeps its multipliers in global memory
-        // ---- wait for the predecessors of this unit on both of its movable bodies ----
-        const int expA = iter * m.degA + m.seqA, expB = iter * m.degB + m.seqB;
-        {
-          bool rdy = !work;
-          int spins = 0;
-          while (true) {
-            if (!rdy) {
-              const int a = (m.fl & 1) ? ld_acquire_i32(X.done + m.bi) : expA;
-              const int b = (m.fl & 2) ? ld_acquire_i32(X.done + m.bj) : expB;
-              rdy = a == expA && b == expB;
-            }
-            if (__all_sync(0xffffffffu, rdy)) break;
-            __nanosleep(40);
-            if ((++spins & 63) == 0) {
-              int ab = 0;
-              if (lane == 0) ab = ld_acquire_i32(X.abort);
-              if (spins > GX_SPIN_LIMIT) ab = 1;
-              ab = __any_sync(0xffffffffu, ab);
-              if (ab) { if (lane == 0) atomicExch(X.abort, 1); aborted = true; break; }
-            }
-          }
-        }
-        if (aborted) break;
-        if (work) {
-          // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: do not fetch it
+    for (int lvl = 0; lvl < nLevels; lvl++) {
+      GS_TRACE_BEGIN();
+      while (t.a >= 0 && t.lvl == lvl && t.it == iter) {
+        const bool tr = P.trace && wic == 0 && iter == 1 && lvl == 0 && trN < 4;
+        long long tk0 = 0, tk1 = 0, tk2 = 0;
+        if (tr) tk0 = clock64();
+        if (act) {
+          // a body that is not movable keeps vlambda = wlambda = 0 for the whole solve: it is never fetched
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           float4 vA4 = z4, wA4 = z4, vB4 = z4, wB4 = z4;
           if (m.fl & 1) ldcg_f8(&B.vlam[2 * m.bi], vA4, wA4);
           if (m.fl & 2) ldcg_f8(&B.vlam[2 * m.bj], vB4, wB4);
+          double* lp = R.lambda + m.r0;  // slot of row r: m.r0 + 32 r
+          if (tr) { asm volatile("" ::"f"(vA4.x), "f"(wA4.x), "f"(vB4.x), "f"(wB4.x)); tk2 = clock64() - tk0; tk1 = 0; }
           f3 vA = ld3(vA4), wA = ld3(wA4), vB = ld3(vB4), wB = ld3(wB4);
           double acc = 0.0;
-          // one projected Gauss-Seidel row update (gs_solver.dart:88-102, equation_class.dart:95-105,151-169)
-#define GX_ROW_UPDATE(q0, q1, q2, q3, Bv, invC, eps, bound, lam, lamNew, rowIdx)                                             \
-          {                                                                                                                  \
-            const int code_ = __float_as_int(q0.w);                                                                         \
-            f3 n_, rA_, rB_, iA_, iB_, sA_;                                                                                  \
-            n_.x = q0.x; n_.y = q0.y; n_.z = q0.z; rA_.x = q1.x; rA_.y = q1.y; rA_.z = q1.z;                                 \
-            rB_.x = q2.x; rB_.y = q2.y; rB_.z = q2.z; iB_.x = q3.x; iB_.y = q3.y; iB_.z = q3.z;                              \
-            iA_.x = q1.w; iA_.y = q2.w; iA_.z = q3.w;                                                                        \
-            if (code_ & 1) { sA_.x = sA_.y = sA_.z = 0.f; } else sA_ = vneg(n_);                                             \
-            const double gwl_ = (vdot(vA, sA_) + vdot(wA, rA_)) + (vdot(vB, n_) + vdot(wB, rB_));                            \
-            double dl_ = invC * (Bv - gwl_ - eps * lam);                                                                     \
-            double mn_, mx_;                                                                                                 \
-            const int bc_ = code_ >> 2;                                                                                      \
-            if (bc_ == GXB_POS) { mn_ = 0.0; mx_ = bound; }                                                                  \
-            else if (bc_ == GXB_SYM) { mn_ = -bound; mx_ = bound; }                                                          \
-            else if (bc_ == GXB_NEG) { mn_ = -bound; mx_ = 0.0; }                                                            \
-            else { mn_ = R.minF[rowIdx]; mx_ = R.maxF[rowIdx]; }                                                             \
-            if (lam + dl_ < mn_) dl_ = mn_ - lam;                                                                            \
-            else if (lam + dl_ > mx_) dl_ = mx_ - lam;                                                                       \
-            lamNew = lam + dl_;                                                                                              \
-            if (m.fl & 1) { vA = vaddscaled(vA, m.imA * dl_, sA_); wA = vaddscaled(wA, dl_, iA_); }                          \
-            if (m.fl & 2) { vB = vaddscaled(vB, m.imB * dl_, n_); wB = vaddscaled(wB, dl_, iB_); }                           \
-            acc += dl_ > 0.0 ? dl_ : -dl_;                                                                                   \
-          }
-          if (staged) {
-            // rows and multipliers of the window live in shared memory; the next row is fetched before the current one is solved
-            unsigned qa = smem_u32(sb) + (unsigned)(m.r0 - rBase) * GX_ROW_BYTES, la = smem_u32(slam) + (unsigned)(m.r0 - rBase) * 8u;
-            const int nr = m.r1 - m.r0;
-            float4 n0 = lds_f4(qa), n1 = lds_f4(qa + 16), n2 = lds_f4(qa + 32), n3 = lds_f4(qa + 48);
-            double nB = lds_f64(qa + 64), nC = lds_f64(qa + 72), nE = lds_f64(qa + 80), nBd = lds_f64(qa + 88);
-            double nl = lds_f64(la);
-            for (int r = 0; r < nr; r++) {
-              const float4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-              const double Bv = nB, invC = nC, eps = nE, bound = nBd, lam = nl;
-              if (r + 1 < nr) {
-                qa += GX_ROW_BYTES;
-                n0 = lds_f4(qa); n1 = lds_f4(qa + 16); n2 = lds_f4(qa + 32); n3 = lds_f4(qa + 48);
-                nB = lds_f64(qa + 64); nC = lds_f64(qa + 72); nE = lds_f64(qa + 80); nBd = lds_f64(qa + 88);
-                nl = lds_f64(la + 8u);
-              }
-              double lamNew;
-              GX_ROW_UPDATE(q0, q1, q2, q3, Bv, invC, eps, bound, lam, lamNew, m.r0 + r);
-              sts_f64(la, lamNew);
-              la += 8u;
+          const int nr = (m.r1 - m.r0) >> 5;
+          for (int r = 0; r < nr; r++) {
+            long long tw0 = 0;
+            if (tr) tw0 = clock64();
+            asm volatile("cp.async.wait_group %0;" ::"n"(GX_SLOTS - 2) : "memory");  // row r has landed
+            if (tr) tk1 += clock64() - tw0;  // trace: cycles spent waiting for rows
+            const unsigned so = (unsigned)((r % GX_SLOTS) * GX_SLOT_BYTES), sa = ring + so;
+            const float4 q0 = lds_f4(sa), q1 = lds_f4(sa + 512), q2 = lds_f4(sa + 1024), q3 = lds_f4(sa + 1536);
+            double Bv, invC, eps, bound;
+            lds_d2(sa + 2048, Bv, invC);
+            lds_d2(sa + 2560, eps, bound);
+            const double lam = lds_f64(ringL + so);
+            // request row r + GX_SLOTS - 1 (and its multiplier) into the slot row r - 1 was read from (its values were
+            // consumed by the previous update)
+            if (r + GX_SLOTS - 1 < nr) {
+              const float4* q = xblk + (size_t)((m.r0 >> 5) + r + GX_SLOTS - 1) * (GX_CHUNKS * 32) + lane;
+              const unsigned dso = (unsigned)(((r + GX_SLOTS - 1) % GX_SLOTS) * GX_SLOT_BYTES), d = ring + dso;
+#pragma unroll
+              for (int c = 0; c < GX_CHUNKS; c++) cp_async16_s(d + c * 512, q + c * 32);
+              cp_async8_s(ringL + dso, lp + 32 * (GX_SLOTS - 1));
             }
-          } else {
-            for (int r = m.r0; r < m.r1; r++) {
-              const float4* q = (const float4*)(R.xrec + r);
-              const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-              const double* d = (const double*)(q + 4);
-              const double Bv = d[0], invC = d[1], eps = d[2], bound = d[3], lam = R.lambda[r];
-              double lamNew;
-              GX_ROW_UPDATE(q0, q1, q2, q3, Bv, invC, eps, bound, lam, lamNew, r);
-              R.lambda[r] = lamNew;
-            }
+            cp_async_commit();
+            // one projected Gauss-Seidel row update (gs_solver.dart:88-102, equation_class.dart:95-105,151-169)
+            const int code = __float_as_int(q0.w);
+            f3 n, rA, rB, iA, iB, sA;
+            n.x = q0.x; n.y = q0.y; n.z = q0.z; rA.x = q1.x; rA.y = q1.y; rA.z = q1.z;
+            rB.x = q2.x; rB.y = q2.y; rB.z = q2.z; iB.x = q3.x; iB.y = q3.y; iB.z = q3.z;
+            iA.x = q1.w; iA.y = q2.w; iA.z = q3.w;
+            if (code & 1) { sA.x = sA.y = sA.z = 0.f; } else sA = vneg(n);
+            const double gwl = (vdot(vA, sA) + vdot(wA, rA)) + (vdot(vB, n) + vdot(wB, rB));
+            double dl = invC * (Bv - gwl - eps * lam);
+            double mn, mx;
+            const int bc = code >> 2;
+            if (bc == GXB_POS) { mn = 0.0; mx = bound; }
+            else if (bc == GXB_SYM) { mn = -bound; mx = bound; }
+            else if (bc == GXB_NEG) { mn = -bound; mx = 0.0; }
+            else { mn = R.minF[m.r0 + 32 * r]; mx = R.maxF[m.r0 + 32 * r]; }
+            if (lam + dl < mn) dl = mn - lam;
+            else if (lam + dl > mx) dl = mx - lam;
+            *lp = lam + dl;  // plain store: the same lane reads it back through L1 (cp.async.ca) one iteration later
+            lp += 32;
+            if (m.fl & 1) { vA = vaddscaled(vA, m.imA * dl, sA); wA = vaddscaled(wA, dl, iA); }
+            if (m.fl & 2) { vB = vaddscaled(vB, m.imB * dl, n); wB = vaddscaled(wB, dl, iB); }
+            acc += dl > 0.0 ? dl : -dl;
           }
-#undef GX_ROW_UPDATE
           if (m.fl & 1) st_f8(&B.vlam[2 * m.bi], st3(vA), st3(wA));
           if (m.fl & 2) st_f8(&B.vlam[2 * m.bj], st3(vB), st3(wB));
-          // publish: the body records above become visible before the counters (fence + relaxed store = release)
-          __threadfence();
-          if (m.fl & 1) st_relaxed_i32(X.done + m.bi, expA + 1);
-          if (m.fl & 2) st_relaxed_i32(X.done + m.bj, expB + 1);
           local += acc;
         }
-      }
-      if (aborted) break;
-      flushEnd = __reduce_min_sync(0xffffffffu, flushEnd);
-      __syncwarp();
-      // multipliers of the staged units back to global as full lines
-#pragma unroll
-      for (int j = 0; j < GX_LAM_REGS; j++) {
-        const int idx = j * 32 + lane;
-        if (idx < flushEnd) R.lambda[rBase + idx] = slam[idx];
-      }
-      asm volatile("fence.proxy.async.global;" ::: "memory");  // a later bulk copy (async proxy) reads these multipliers back
-      if (sameNext) {
-        double* const nlam = (double*)(wbase + (size_t)(buf ^ 1) * GX_BUF_BYTES + GX_LAM_OFF) + (rBase & 1);
-#pragma unroll
-        for (int j = 0; j < GX_LAM_REGS; j++) {
-          const int idx = j * 32 + lane;
-          if (idx < nRs) nlam[idx] = slam[idx];
+        __syncwarp();
+        if (tr) {
+          const long long tend = clock64();
+          int nrm = act ? (m.r1 - m.r0) >> 5 : 0;
+          for (int o = 16; o > 0; o >>= 1) {
+            nrm = max(nrm, __shfl_xor_sync(0xffffffffu, nrm, o)); tk1 = max(tk1, __shfl_xor_sync(0xffffffffu, tk1, o));
+            tk2 = max(tk2, __shfl_xor_sync(0xffffffffu, tk2, o));
+          }
+          if (lane == 0) {  // (body gather, whole window, of which waiting for rows, 32000 + rows)
+            long long* o = P.trace + (size_t)gridDim.x * GS_TRACE_PHASES * 2 + (blockIdx.x * 4 + trN) * 4;
+            o[0] = tk2; o[1] = tend - tk0; o[2] = tk1; o[3] = 32 * 1000 + nrm;
+          }
+          trN++;
+        }
+        // the warp's next window (same colour, a later colour or the next iteration): its unit records and first rows are
+        // requested now, i.e. before the barrier when it belongs to a later phase
+        t.a += nW;
+        seek(t);
+        prime(t);
+        {  // unit records of the window after that one towards L2 (32 x 64 B = 16 lines)
+          GxWin t2 = t;
+          if (t2.a >= 0) { t2.a += nW; seek(t2); }
+          if (t2.a >= 0 && lane < 16) prefetch_l2((const unsigned char*)(U.xrec + S.levelStart[t2.lvl] + 32 * (t2.a - lt[t2.lvl])) + lane * 128);
         }
       }
-      __syncwarp();
-      t0 = t1; x0 = x1; y0 = y1; pend0 = pend1;
-      t1 = t2; x1 = x2; y1 = y2; pend1 = false;
-      buf ^= 1;
+      if (lvl == nLevels - 1) {
+        // the iteration's |delta lambda| total rides on the last colour barrier; totals rotate through three slots so a slot
+        // can be cleared a full iteration before it is used again, without an extra barrier
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) s_red[wic] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double tt = 0.0;
+          for (int w = 0; w < GX_WARPS; w++) tt += s_red[w];
+          atomicAdd(&G.worldTot[iter % 3], tt);
+        }
+      }
+      GS_TRACE_WORK();
+      grid_barrier(S.bar, epoch, nCtas);
+      GS_TRACE_END();
+      if (lvl == 0 && tid == 0) G.worldTot[(iter + 2) % 3] = 0.0;  // last read before this barrier, next used in iter + 2
     }
-    if (aborted) break;
-    // tolerance test (gs_solver.dart:99-107): the iteration's sum of |delta lambda| over all rows; totals rotate through
-    // three slots so a slot can be cleared a full iteration before it is used again
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if (lane == 0) s_red[wic] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int k = 0; k < GX_WARPS; k++) t += s_red[k];
-      atomicAdd(&G.worldTot[iter % 3], t);
-      if (blockIdx.x == 0) G.worldTot[(iter + 1) % 3] = 0.0;  // last read two barriers ago, next used in iter + 1
-    }
-    if (grid_barrier_abortable(S.bar, epoch, nCtas, X.abort)) { aborted = true; break; }
+    // tolerance test (gs_solver.dart:99-107)
     const double tot = __ldcg(&G.worldTot[iter % 3]);
     if (tot * tot < P.tol2) break;
   }
-  // a copy started for a window that will never run must land before the CTA may retire
-  if (pend0) mbar_wait(&s_mbar[wic][buf], (parity >> buf) & 1u);
-  if (pend1) mbar_wait(&s_mbar[wic][buf ^ 1], (parity >> (buf ^ 1)) & 1u);
+  asm volatile("cp.async.wait_all;" ::: "memory");  // rows requested for a window that will never run must land before the CTA retires
   if (tid == 0) *G.itersDone = iter;
 }

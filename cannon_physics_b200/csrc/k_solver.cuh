@@ -41,9 +41,12 @@ struct RowArrays {
   int fast;
   float4* rec;     // 5 float4 per row, contiguous (80 B): (n,B) (rA,invC) (rB,eps) (iA,minF) (iB,maxF)
   float* flambda;
-  // COLORED (exact) single-world mode: the row as one 96-byte record the staged sweep k_gs_exact bulk-copies to shared
-  // memory - the f32-stored Jacobian exactly as the reference keeps it, the f64 scalars as f64 (lambda stays in `lambda`)
-  struct GxRow* xrec;
+  // COLORED (exact) single-world mode: rows packed for k_gs_exact - the f32-stored Jacobian exactly as the reference keeps
+  // it, the f64 scalars as f64 - in BLOCKS of 32 row slots, chunk-interleaved (see GxRow / gx_store_row): a window of the
+  // sweep (32 units, one per lane) owns consecutive blocks, block r holds row r of every unit of the window, so a warp's
+  // row step reads 3 KB of contiguous memory with fully coalesced 16-byte accesses. `lambda`, `minF`, `maxF` use the same
+  // slot index (block * 32 + lane).
+  float4* xblk;
 };
 
 // bound codes of a packed exact row: [0, bound] (contact), [-bound, bound] (friction, joints), [-bound, 0] (cone / twist),
@@ -56,7 +59,8 @@ struct __align__(16) GxRow {
   float iBx, iBy, iBz, iAz;
   double B, invC, eps, bound;
 };
-static_assert(sizeof(GxRow) == 96, "GxRow is bulk-copied as 96-byte records");
+static_assert(sizeof(GxRow) == 96, "a GxRow is six 16-byte chunks");
+#define GX_CHUNKS 6
 
 // units: by unit id (u*) before scheduling, by execution position (e*) after
 struct UnitArrays {
@@ -74,6 +78,12 @@ struct UnitArrays {
   struct GxUnit* xrec;                       // COLORED (exact) mode: execution record of k_gs_exact
   const int* unitSeq;                        // per unit id: rank of the unit among the units of body i / body j (colour order)
   const int* bodyCnt;                        // per body: number of scheduled units that move it
+  // exact staged sweep: windows of 32 units per colour; winBase[w] = first row slot of window w (multiple of 32),
+  // lvlWin[l] = first window of colour l
+  const int* winBase;
+  const int* lvlWin;
+  const int* levelStart;
+  const int* padTotal;  // row slots in use including the padding of the windows
 };
 
 // one 64-byte record per unit in execution order (exact staged sweep). seqA / degA: the unit is the seqA-th of the degA
@@ -176,7 +186,7 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, const R
     q[3] = st3(iA, (float)minF); q[4] = st3(iB, (float)maxF); R.flambda[row] = 0.f;
     return;
   }
-  if (R.xrec) {
+  if (R.xblk) {
     GxRow q;
     q.nx = sB.x; q.ny = sB.y; q.nz = sB.z;
     q.rAx = rA.x; q.rAy = rA.y; q.rAz = rA.z; q.rBx = rB.x; q.rBy = rB.y; q.rBz = rB.z;
@@ -190,7 +200,11 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, const R
     else if (mx == 0LL) { bc = GXB_NEG; q.bound = -minF; }
     else { R.minF[row] = minF; R.maxF[row] = maxF; }
     q.code = ((kind == ROW_ROT || kind == ROW_MOTOR) ? 1 : 0) | (bc << 2);
-    R.xrec[row] = q;
+    // slot `row` = block * 32 + lane; chunk c of the block sits at float4 index (block * 6 + c) * 32 + lane
+    float4* d = R.xblk + (size_t)(row >> 5) * (GX_CHUNKS * 32) + (row & 31);
+    const float4* src = (const float4*)&q;
+#pragma unroll
+    for (int c = 0; c < GX_CHUNKS; c++) d[c * 32] = src[c];
     R.lambda[row] = 0.0;
     return;
   }
@@ -575,12 +589,20 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
                                                     const int* __restrict__ bodyGroup, int nGroups) {
   const int nUnits = min(*U.nExec, U.unitCap);
   const int nRows = U.eRowBase[nUnits];
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *R.nRows = nRows; if (nRows > R.rowCap) atomicMax(rowOverflow, nRows); }
-  if (nRows > R.rowCap) return;
+  const int nSlots = R.xblk ? max(nRows, *U.padTotal) : nRows;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *R.nRows = nRows; if (nSlots > R.rowCap) atomicMax(rowOverflow, nSlots); }
+  if (nSlots > R.rowCap) return;
   const double h = P.dt;
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
     const int u = order[a];
     int row = U.eRowBase[a];
+    int rs = 1;  // distance between consecutive rows of a unit
+    if (R.xblk) {
+      // window-interleaved slots: unit = lane (a - a0) % 32 of window (a - a0) / 32 of its colour, row r in block r of the window
+      const int l = U.eLevel[a], a0 = U.levelStart[l];
+      row = U.winBase[U.lvlWin[l] + ((a - a0) >> 5)] + ((a - a0) & 31);
+      rs = 32;
+    }
     U.unitRow[u] = row;
     if (R.fast) {
       GsUnitRec rec;
@@ -592,9 +614,12 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
     }
     if (U.xrec) {
       GxUnit x;
-      x.bi = U.eBi[a]; x.bj = U.eBj[a]; x.fl = U.eFlags[a]; x.r0 = row; x.r1 = U.eRowBase[a + 1];
-      x.seqA = U.unitSeq[2 * u]; x.seqB = U.unitSeq[2 * u + 1];
-      x.degA = (x.fl & 1) ? U.bodyCnt[x.bi] : 0; x.degB = (x.fl & 2) ? U.bodyCnt[x.bj] : 0;
+      x.bi = U.eBi[a]; x.bj = U.eBj[a]; x.fl = U.eFlags[a]; x.r0 = row; x.r1 = row + 32 * U.eRows[a];  // row r of the unit = slot r0 + 32 r
+      x.seqA = x.seqB = x.degA = x.degB = 0;
+      if (U.unitSeq) {  // dataflow bookkeeping (see the history note in k_gs_exact.cuh): rank of the unit on its two bodies
+        x.seqA = U.unitSeq[2 * u]; x.seqB = U.unitSeq[2 * u + 1];
+        x.degA = (x.fl & 1) ? U.bodyCnt[x.bi] : 0; x.degB = (x.fl & 2) ? U.bodyCnt[x.bj] : 0;
+      }
       x.pad0 = x.pad1 = x.pad2 = 0;
       x.imA = U.eImA[a]; x.imB = U.eImB[a];
       U.xrec[a] = x;
@@ -607,7 +632,7 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
     if (kind == SRC_JOINT) {
       build_joint_row(R, row, B, J, idx, A, Bd, h);
     } else if (kind == SRC_JOINTS) {  // COLORED: the accepted equations of one constraint, slots idx .. idx + rows - 1
-      for (int k = 0; k < U.eRows[a]; k++) build_joint_row(R, row + k, B, J, J.slotEq[idx + k], A, Bd, h);
+      for (int k = 0; k < U.eRows[a]; k++) build_joint_row(R, row + k * rs, B, J, J.slotEq[idx + k], A, Bd, h);
     } else if (kind == SRC_TASK) {
       const int c0 = S.taskOff[idx], c1 = c0 + S.taskCnt[idx];
       for (int c = c0; c < c1; c++) {
@@ -615,12 +640,14 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
         if (S.fricFlag[c]) {
           f3 t1, t2;
           vtangents(ni, t1, t2);
-          build_friction_row(R, row++, A, Bd, ri, rj, t1, C.fb[c], C.feps[c], C.slip[c], h);
-          build_friction_row(R, row++, A, Bd, ri, rj, t2, C.fb[c], C.feps[c], C.slip[c], h);
+          build_friction_row(R, row, A, Bd, ri, rj, t1, C.fb[c], C.feps[c], C.slip[c], h);
+          build_friction_row(R, row + rs, A, Bd, ri, rj, t2, C.fb[c], C.feps[c], C.slip[c], h);
+          row += 2 * rs;
         }
         if (S.contFlag[c]) {
           C.row[c] = row;
-          build_normal_row(R, row++, A, Bd, ri, rj, ni, C.rest[c], C.ca[c], C.cb[c], C.ceps[c], 0.0, 1e6, h);
+          build_normal_row(R, row, A, Bd, ri, rj, ni, C.rest[c], C.ca[c], C.cb[c], C.ceps[c], 0.0, 1e6, h);
+          row += rs;
         }
       }
     } else {
@@ -635,6 +662,29 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
         build_friction_row(R, row, A, Bd, ri, rj, kind == SRC_FRIC1 ? t1 : t2, C.fb[c], C.feps[c], C.slip[c], h);
       }
     }
+  }
+}
+
+// exact staged sweep: rows per window = 32 x the longest unit of the window (units of a colour are sorted by row count, so
+// the padding is small); one warp per window
+__global__ void __launch_bounds__(256) k_gx_windows(UnitArrays U, const int* __restrict__ levelStart, const int* __restrict__ nLevels,
+                                                    const int* __restrict__ lvlWin, int* __restrict__ winRows, int winCap, int* __restrict__ overflow) {
+  const int nl = *nLevels, nWin = lvlWin[nl];
+  if (nWin > winCap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(overflow, nWin); return; }
+  const int lane = threadIdx.x & 31;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < winCap; w += (gridDim.x * blockDim.x) >> 5) {
+    int m = 0;
+    if (w < nWin) {
+      int lo = 0, hi = nl;  // last colour whose first window is <= w
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (lvlWin[mid] <= w) lo = mid; else hi = mid;
+      }
+      const int a = levelStart[lo] + 32 * (w - lvlWin[lo]) + lane;
+      if (a < levelStart[lo + 1]) m = U.eRows[a];
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (lane == 0) winRows[w] = 32 * m;  // windows beyond nWin contribute nothing to the scan
   }
 }
 
@@ -990,10 +1040,14 @@ __global__ void __launch_bounds__(256) k_gs_task_levels(UnitArrays U, SchedArray
     if (l < nLevels) {
       const int u0 = S.levelStart[l], u1 = S.levelStart[l + 1];
       const int rows = U.eRowBase[u1] - U.eRowBase[u0], units = u1 - u0;
-      int win = T.winMin;
-      if (rows > 0 && units > 0) win = min(T.winMax, max(T.winMin, (int)((32LL * rows + units - 1) / units)));
-      T.lvlWin[l] = win;
-      n = (rows + win - 1) / win;
+      if (T.winMax == 0) {  // k_gs_exact: windows of 32 units, whatever their rows
+        n = (units + 31) / 32;
+      } else {
+        int win = T.winMin;
+        if (rows > 0 && units > 0) win = min(T.winMax, max(T.winMin, (int)((32LL * rows + units - 1) / units)));
+        T.lvlWin[l] = win;
+        n = (rows + win - 1) / win;
+      }
     }
     s_scan[threadIdx.x] = n;
     __syncthreads();

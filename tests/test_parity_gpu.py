@@ -415,3 +415,32 @@ def test_cuda_contact_events_match_golden_fixture(cuda_lib, name):
     ref = np.load(os.path.join(GOLDEN, name + ".npz"))
     for k in ref.files:
         assert np.array_equal(got[k], ref[k]), f"{name}: {k} differs from the fixture"
+
+
+@pytest.mark.gpu
+def test_dataflow_sweep_equals_level_sweep_on_the_100k_pile(cuda_lib):
+    """The COLORED solver's production kernel (k_gs_exact: per-body progress counters, no grid barrier between colours)
+    against the plain level-by-level sweep of the same colours (k_gs, CANNON_GS_NO_DATAFLOW) on the full bench workload -
+    the settled 100 001-body pile of config 3 (~4.4e5 contacts, 1.3e6 rows), a size the oracle needs 10 s per step for.
+    Units of one colour touch disjoint bodies and every unit runs after its predecessors on both bodies, so the two must
+    agree bit for bit; any missed dependency or stale read in the dataflow would show up here."""
+    import bench
+    spec, _, state = bench.build_spec("c3", 1.0, 0, 1)
+    assert "settled" in state
+    a = engine.DeviceWorld(cuda_lib, spec)
+    os.environ["CANNON_GS_NO_DATAFLOW"] = "1"  # read when the world is created
+    try:
+        b = engine.DeviceWorld(cuda_lib, spec)
+    finally:
+        del os.environ["CANNON_GS_NO_DATAFLOW"]
+    for s in range(3):
+        a.step(1 / 60, 4)
+        b.step(1 / 60, 4)
+        parity.assert_same_state(a, b, f"100k pile after {4 * (s + 1)} steps")
+        pa, pb = a.profile(), b.profile()
+        assert (pa["n_pairs"], pa["n_contacts"], pa["n_rows"], pa["n_levels"], pa["iterations_done"]) == \
+               (pb["n_pairs"], pb["n_contacts"], pb["n_rows"], pb["n_levels"], pb["iterations_done"])
+    assert pa["n_contacts"] > 300000
+    ra, rb = a.get_rows(), b.get_rows()
+    for k in ("body_i", "body_j", "B", "invC", "lambda", "level"):
+        assert np.array_equal(ra[k], rb[k]), k

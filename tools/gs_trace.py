@@ -18,10 +18,7 @@ from cannon_physics_b200 import engine  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 config = sys.argv[2] if len(sys.argv) > 2 else "c3"
-spec, label = bench.build_spec(config, 1.0, 0, 1)
-if len(sys.argv) > 3:
-    from cannon_physics_b200 import _ffi as F
-    spec.desc["solver_kind"] = F.SOLVER_COLORED if sys.argv[3] == "colored" else F.SOLVER_REFERENCE_ORDER
+spec, label, state = bench.build_spec(config, 1.0, 0, 1, solver=sys.argv[3] if len(sys.argv) > 3 else "auto")
 w = engine.DeviceWorld(cp.lib, spec, device=0)
 w.step(1 / 60, steps)
 prof = w.profile()
@@ -29,8 +26,10 @@ print({k: prof[k] for k in ("n_contacts", "n_rows", "n_levels", "iterations_done
 raw = np.fromfile(path, dtype=np.int64)
 nsm = (len(raw)) // (4 * 64 * 2 + 64)
 t = raw[: nsm * 4 * 64 * 2].reshape(-1, 64, 2)
-grid = 148 if not os.environ.get('CANNON_GS_FAST_V1') else 296
+raw_tail_base = None
+grid = int(os.environ.get('GS_TRACE_CTAS', '296'))
 t = t[:grid]
+raw_tail_base = grid * 64 * 2
 print("CTAs", t.shape[0])
 nph = min(64, prof["n_levels"] * prof["iterations_done"])
 ghz = 1.9
@@ -51,7 +50,7 @@ sizes = np.diff(np.flatnonzero(np.append(newunit, True)))
 print("rows per unit histogram", np.bincount(sizes).tolist())
 
 ncta = t.shape[0]
-tk = raw[ncta * 64 * 2: ncta * 64 * 2 + ncta * 16].reshape(ncta, 4, 4)
+tk = raw[raw_tail_base: raw_tail_base + ncta * 16].reshape(ncta, 4, 4)
 print("warp 0 of the first CTAs, iteration 1 colour 0: per task (wait us, solve us, of which body-lambda gather us, units*1000+rows)")
 for c in range(0, min(ncta, 148), 12):
     print(c, [(round(a / ghz / 1e3, 2), round(b / ghz / 1e3, 2), round(cc / ghz / 1e3, 2), int(d)) for a, b, cc, d in tk[c] if d > 0])
