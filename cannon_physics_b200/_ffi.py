@@ -157,6 +157,10 @@ PROTOTYPES = {
     "cannon_world_get_contact_events": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32), P(c_i32)]),
     "cannon_world_get_rows": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_i32), P(c_f64), P(c_f64), P(c_f64), P(c_i32)]),
     "cannon_world_update_bodies": (c_i32, [VP, c_i32, c_i32, P(c_f32), P(c_f32), P(c_f32), P(c_f32), P(c_f32), P(c_f32)]),
+    "cannon_world_set_inv_inertia": (c_i32, [VP, c_i32, c_i32, P(c_f32)]),
+    "cannon_world_set_stepnumber": (c_i32, [VP, c_i64]),
+    "cannon_world_update_sleep_states": (c_i32, [VP, c_i32, c_i32, P(c_i32)]),
+    "cannon_world_set_hinge_motor": (c_i32, [VP, c_i32, c_i32, c_f64, c_f64]),
 }
 
 

@@ -184,6 +184,8 @@ class Body:  # lib/objects/rigid_body.dart:26-86
         self.shapes: List[Shape] = []
         self.world: Optional["World"] = None
         self.index = -1
+        self.timeLastSleepy = 0.0      # rigid_body.dart:130; World.addBody sets it to world.time (world_class.dart:291)
+        self._invInertia = None        # Body.invInertia as the device derived it at the first upload (rigid_body.dart:587-609)
         if shape is not None:
             self.addShape(shape)
 
@@ -194,29 +196,40 @@ class Body:  # lib/objects/rigid_body.dart:26-86
             raise CannonError(F.E_UNSUPPORTED, "shape offsets are outside the hot-path scope (SURVEY.md §8f)")
         if orientation is not None and np.any(np.asarray(orientation, dtype=np.float32) != np.array([0, 0, 0, 1], np.float32)):
             raise CannonError(F.E_UNSUPPORTED, "shape orientations are outside the hot-path scope (SURVEY.md §8f)")
+        self._before_write()
         self.shapes.append(shape)
-        self._dirty()
-        return self
-
-    def _dirty(self):
+        self._invInertia = None  # addShape recomputes the mass properties (rigid_body.dart:362)
         if self.world is not None:
             self.world._structure_dirty = True
+        return self
 
-    # rigid_body.dart:263-278
+    def _before_write(self):
+        """Every mutator starts here: after World.step(sync=False) the device holds the newer state, so it is pulled into
+        the Body objects BEFORE the write - otherwise the next upload would roll the world back to stale host values."""
+        if self.world is not None:
+            self.world._pull()
+
+    # rigid_body.dart:263-278: sleepState (and for sleep() the velocities) only - no rebuild of the device world
     def wakeUp(self):
+        self._before_write()
         self.sleepState = BodySleepStates.awake
-        self._dirty()
+        if self.world is not None:
+            self.world._sleep_dirty = True
 
     def sleep(self):
+        self._before_write()
         self.sleepState = BodySleepStates.sleeping
         self.velocity[:] = 0
         self.angularVelocity[:] = 0
-        self._dirty()
+        if self.world is not None:
+            self.world._sleep_dirty = True
+            self.world._state_dirty = True
 
     # rigid_body.dart:472-566 (host-side writes, uploaded before the next step)
     def applyForce(self, force, relativePoint=None):
         if self.type != BodyTypes.dynamic:
             return
+        self._before_write()
         f = np.asarray(force, dtype=np.float32)
         r = Vec3() if relativePoint is None else np.asarray(relativePoint, dtype=np.float32)
         if self.sleepState == BodySleepStates.sleeping:
@@ -232,6 +245,7 @@ class Body:  # lib/objects/rigid_body.dart:26-86
             return
         if relativePoint is not None and np.any(np.asarray(relativePoint) != 0):
             raise CannonError(F.E_UNSUPPORTED, "off-centre impulses need the device inertia; write angularVelocity directly")
+        self._before_write()
         if self.sleepState == BodySleepStates.sleeping:
             self.wakeUp()
         j = np.asarray(impulse, dtype=np.float32).astype(np.float64)
@@ -308,6 +322,7 @@ class Constraint:  # constraint_class.dart:5
 
     def __init__(self, bodyA: Body, bodyB: Body, collideConnected: bool = True):
         self.bodyA, self.bodyB, self.collideConnected = bodyA, bodyB, collideConnected
+        self.world: Optional["World"] = None  # set by World.addConstraint
 
 
 class PointToPointConstraint(Constraint):  # point_to_point_constraint.dart:20
@@ -334,17 +349,27 @@ class HingeConstraint(PointToPointConstraint):  # hinge_constraint.dart:10
         self.collideConnected = True if collideConnected is None else collideConnected
         self.motorEnabled, self.motorTargetVelocity, self.motorMaxForce = False, 0.0, maxForce
 
+    # hinge_constraint.dart:56-76: the motor equation's fields, effective from the next step. On a live device world they go
+    # through cannon_world_set_hinge_motor (no rebuild, nothing else changes).
+    def _motor_changed(self):
+        if self.world is not None:
+            self.world._motor_dirty.add(id(self))
+
     def enableMotor(self):
         self.motorEnabled = True
+        self._motor_changed()
 
     def disableMotor(self):
         self.motorEnabled = False
+        self._motor_changed()
 
     def setMotorSpeed(self, speed: float):
         self.motorTargetVelocity = speed
+        self._motor_changed()
 
     def setMotorMaxForce(self, maxForce: float):
         self.motorMaxForce = maxForce
+        self._motor_changed()
 
     def _desc(self, idx):
         return dict(super()._desc(idx), axis_a=self.axisA, axis_b=self.axisB, motor_enabled=int(self.motorEnabled),
@@ -356,7 +381,10 @@ class DistanceConstraint(Constraint):  # distance_constraint.dart:7
 
     def __init__(self, bodyA, bodyB, distance: Optional[float] = None, maxForce: float = 1e6):
         super().__init__(bodyA, bodyB)
-        self.distance = distance  # None: the distance between the bodies when the constraint reaches the world
+        # distance_constraint.dart:14-18: the default is the bodies' distance when the constraint is constructed; here the
+        # value is frozen when the constraint reaches the world (World.addConstraint), so later rebuilds of the device world
+        # keep it
+        self.distance = distance
         self.maxForce = maxForce
 
     def _desc(self, idx):
@@ -427,14 +455,17 @@ class World:  # lib/world/world_class.dart:44
         self._dev: Optional[DeviceWorld] = None
         self._structure_dirty = True
         self._state_dirty = False
+        self._sleep_dirty = False        # Body.sleep / wakeUp since the last upload
+        self._motor_dirty = set()        # ids of HingeConstraints whose motor fields changed since the last upload
         self._listeners = {}
         self._events_on = False
         self._host_current = True  # the Body objects hold the device state (False after a step with sync=False)
 
     # world_class.dart:282-300 / 224-231 / 343-348
     def _pull(self):
-        """Before a structural change rebuilds the device world: make the Body objects current."""
-        if self._dev is not None and not self._structure_dirty and not self._host_current:
+        """Before any host-side write (structural or not): make the Body objects current. The body list cannot have changed
+        since the device world was built while the host is stale, because every mutator pulls before it writes."""
+        if self._dev is not None and not self._host_current:
             self.sync()
 
     def addBody(self, body: Body):
@@ -443,6 +474,7 @@ class World:  # lib/world/world_class.dart:44
         self._pull()
         body.index = len(self.bodies)
         body.world = self
+        body.timeLastSleepy = self.time  # world_class.dart:291
         self.bodies.append(body)
         self._structure_dirty = True
 
@@ -462,6 +494,11 @@ class World:  # lib/world/world_class.dart:44
 
     def addConstraint(self, c: Constraint):
         self._pull()
+        c.world = self
+        if isinstance(c, DistanceConstraint) and c.distance is None:
+            # Vector3.distanceTo on the f32-stored positions, evaluated in double (distance_constraint.dart:16)
+            d = c.bodyA.position.astype(np.float64) - c.bodyB.position.astype(np.float64)
+            c.distance = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
         self.constraints.append(c)
         self._structure_dirty = True
 
@@ -472,16 +509,19 @@ class World:  # lib/world/world_class.dart:44
             self._structure_dirty = True
 
     def clearForces(self):  # world_class.dart:773-781
+        self._pull()
         for b in self.bodies:
             b.force[:] = 0
             b.torque[:] = 0
         self._state_dirty = True
 
     def addSpring(self, spring: Spring):
+        self._pull()
         self.springs.append(spring)
         self._structure_dirty = True
 
     def addContactMaterial(self, cmat: ContactMaterial):
+        self._pull()
         self.contactmaterials.append(cmat)
         self._structure_dirty = True
 
@@ -508,7 +548,7 @@ class World:  # lib/world/world_class.dart:44
             "linear_factor": np.zeros((n, 3), np.float32), "angular_factor": np.zeros((n, 3), np.float32), "fixed_rotation": np.zeros(n, np.uint8),
             "collision_filter_group": np.zeros(n, np.int32), "collision_filter_mask": np.zeros(n, np.int32),
             "collision_response": np.zeros(n, np.uint8), "is_trigger": np.zeros(n, np.uint8), "material": np.zeros(n, np.int32),
-            "shape": np.zeros(n, np.int32),
+            "shape": np.zeros(n, np.int32), "time_last_sleepy": np.zeros(n),
         }
         for i, body in enumerate(self.bodies):
             b["position"][i], b["quaternion"][i], b["velocity"][i] = body.position, body.quaternion, body.velocity
@@ -520,6 +560,7 @@ class World:  # lib/world/world_class.dart:44
             b["collision_filter_group"][i], b["collision_filter_mask"][i] = body.collisionFilterGroup, body.collisionFilterMask
             b["collision_response"][i], b["is_trigger"][i] = body.collisionResponse, body.isTrigger
             b["material"][i] = mat_index(body.material)
+            b["time_last_sleepy"][i] = body.timeLastSleepy
             if body.shapes:
                 sh = body.shapes[0]
                 if id(sh) not in shape_ids:
@@ -563,17 +604,46 @@ class World:  # lib/world/world_class.dart:44
             if self._dev is not None:
                 self._dev.close()
             self._dev = DeviceWorld(self._lib, spec, device=self._device)
+            # what a rebuild must not lose: World.time / stepnumber (the quatNormalizeSkip phase) and every body's
+            # invInertia, which the reference computes once at construction (rigid_body.dart:85,362), not from the pose
+            # the body happens to have when the device world is rebuilt
             self._dev.set_time(self.time)
+            self._dev.set_stepnumber(self.stepnumber)
+            n = len(self.bodies)
+            if n:
+                inv = self._dev.get_bodies(("inv_inertia",))["inv_inertia"].reshape(n, 3)
+                carried = False
+                for i, body in enumerate(self.bodies):
+                    if body._invInertia is None:
+                        body._invInertia = inv[i].copy()
+                    elif not np.array_equal(body._invInertia, inv[i]):
+                        inv[i] = body._invInertia
+                        carried = True
+                if carried:
+                    self._dev.set_inv_inertia(0, inv)
             if self._events_on:
                 self._dev.enable_contact_events(True)
             self._structure_dirty = False
             self._state_dirty = False
-        elif self._state_dirty:
+            self._sleep_dirty = False
+            self._motor_dirty.clear()
+            return
+        # Only ever reached with the Body objects current (every mutator pulls first), so no stale pose can be uploaded.
+        assert self._host_current or not (self._state_dirty or self._sleep_dirty)
+        if self._state_dirty:
             n = len(self.bodies)
             st = lambda attr: np.stack([getattr(b, attr) for b in self.bodies]).astype(np.float32)
             self._dev.update_bodies(0, n, position=st("position"), quaternion=st("quaternion"), velocity=st("velocity"),
                                     angular_velocity=st("angularVelocity"), force=st("force"), torque=st("torque"))
             self._state_dirty = False
+        if self._sleep_dirty:
+            self._dev.update_sleep_states(0, np.array([b.sleepState for b in self.bodies], dtype=np.int32))
+            self._sleep_dirty = False
+        if self._motor_dirty:
+            for k, c in enumerate(self.constraints):
+                if id(c) in self._motor_dirty:
+                    self._dev.set_hinge_motor(k, c.motorEnabled, c.motorTargetVelocity, c.motorMaxForce)
+            self._motor_dirty.clear()
 
     # EventTarget (lib/utils/event_target.dart) for the world-level contact events of world_class.dart:703-730
     def addEventListener(self, type: str, listener):
@@ -603,7 +673,11 @@ class World:  # lib/world/world_class.dart:44
                     fn(ev)
 
     def markDirty(self):
-        """Call after writing body vectors in place (``body.position[:] = ...``) between steps."""
+        """Call after writing body vectors in place (``body.position[:] = ...``) between steps. After ``step(sync=False)``
+        the Body objects are stale: call ``world.sync()`` BEFORE editing them - an in-place edit of stale vectors cannot be
+        told apart from the stale values around it, so this refuses instead of rolling the world back."""
+        if self._dev is not None and not self._host_current:
+            raise CannonError(F.E_INVALID, "the Body objects are stale after step(sync=False): call world.sync() before editing them")
         self._state_dirty = True
 
     def step(self, dt: float, timeSinceLastCalled: Optional[float] = None, maxSubSteps: int = 10, nsteps: int = 1, sync: bool = True):
@@ -627,8 +701,9 @@ class World:  # lib/world/world_class.dart:44
 
     def sync(self):
         """Refresh the Body objects from device state."""
-        st = self._dev.get_bodies(("position", "quaternion", "velocity", "angular_velocity", "sleep_state"))
+        st = self._dev.get_bodies(("position", "quaternion", "velocity", "angular_velocity", "sleep_state", "time_last_sleepy"))
         for i, body in enumerate(self.bodies):
+            body.timeLastSleepy = float(st["time_last_sleepy"][i])
             body.position[:] = st["position"][i]
             body.quaternion[:] = st["quaternion"][i]
             body.velocity[:] = st["velocity"][i]

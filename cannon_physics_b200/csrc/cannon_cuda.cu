@@ -210,6 +210,7 @@ struct cannon_world {
   DBuf<double> jMinF, jMaxF, jA, jB, jEps, jTargetVel, jCos, jParam;
   DBuf<int> jMode;
   int nJointEq = 0, nJointAccepted = 0;
+  std::vector<int> hConFirst, hConType, hJEnabled, hJTrig;  // host mirror for cannon_world_set_hinge_motor: first equation / type per constraint, flags per equation
   // device: scheduler / gs
   DBuf<unsigned long long> claim;
   DBuf<int> unitLevel, order, levelStart, act0, act1, worldRows, worldDone, worldIters, islandLabel;
@@ -426,7 +427,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
   cudaFuncSetAttribute(k_gs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_exact, GX_THREADS, GX_SMEM_BYTES);
-  w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, GX_CTAS_PER_SM));
+  w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, 1));
   w->gxOff = getenv("CANNON_GS_NO_DATAFLOW") != nullptr;
   w->gsFastV1 = getenv("CANNON_GS_FAST_V1") != nullptr;
   w->gsNoLenSort = getenv("CANNON_GS_NO_LEN_SORT") != nullptr;
@@ -748,7 +749,7 @@ static int32_t ensure_capacities(cannon_world* w) {
     w->gxWinCap = rowCap / 32 + w->maxLevels + 2;
     RES(gxWinRows, w->gxWinCap + 1); RES(gxWinBase, w->gxWinCap + 1);
     w->gsTaskCap = 0x7fffffff;
-    RES(gsLvlTask, w->maxLevels + 2);
+    RES(gsLvlTask, w->maxLevels + 2); RES(gsLvlWin, w->maxLevels + 2);
   } else {
     RES(rKind, rowCap); RES(rN, rowCap); RES(rRA, rowCap); RES(rRB, rowCap);
     RES(rIA, rowCap); RES(rIB, rowCap); RES(rB, rowCap); RES(rInvC, rowCap); RES(rEps, rowCap); RES(rMinF, rowCap); RES(rMaxF, rowCap);
@@ -912,6 +913,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
     W_TRY(w, cudaMemcpy(hquat.data(), w->quat.p, w->n * sizeof(float4), cudaMemcpyDeviceToHost));
   }
   std::vector<int> wake;
+  w->hConFirst.clear(); w->hConType.clear(); w->hJTrig.clear();
   // Equation ctor SPOOK parameters (equation_class.dart:38): k=1e7, d=4, h=1/60 — never refreshed for joints
   const double k0 = 1e7, d0 = 4, h0 = 1.0 / 60;
   const double sa = 4.0 / (h0 * (1 + 4 * d0)), sbv = 4.0 * d0 / (1 + 4 * d0), se = 4.0 / (h0 * h0 * k0 * (1 + 4 * d0));
@@ -958,7 +960,10 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
       param.push_back(prm);
       targetVel.push_back(tv);
       if (en && !trig) { slotEq.push_back((int)rowSlot.size()); rowSlot.push_back(slot++); } else rowSlot.push_back(-1);
+      w->hJTrig.push_back(trig ? 1 : 0);
     };
+    w->hConFirst.push_back(firstEq);
+    w->hConType.push_back(d.type);
     if (d.type == CANNON_CONSTRAINT_DISTANCE) {  // distance_constraint.dart:14-23
       double dist = d.distance;
       if (dist < 0) dist = vdist(xA, xB);
@@ -1005,6 +1010,7 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
   w->nFilterKeys = (int)keys.size();
   w->nJointEq = (int)bodyA.size();
   w->nJointAccepted = slot;
+  w->hJEnabled = enabled;
   W_TRY(w, upload(w->jBodyA, bodyA, s)); W_TRY(w, upload(w->jBodyB, bodyB, s)); W_TRY(w, upload(w->jKind, kind, s));
   W_TRY(w, upload(w->jEnabled, enabled, s)); W_TRY(w, upload(w->jRowSlot, rowSlot, s)); W_TRY(w, upload(w->jFirst, first, s));
   W_TRY(w, upload(w->jSlotEq, slotEq, s));
@@ -1063,6 +1069,7 @@ int32_t cannon_world_get_time(cannon_world* w, double* t, int64_t* stepnumber) {
   if (stepnumber) *stepnumber = w->stepnumber;
   return CANNON_OK;
 }
+int32_t cannon_world_set_stepnumber(cannon_world* w, int64_t n) { if (!w || n < 0) return CANNON_E_INVALID; w->stepnumber = n; return CANNON_OK; }
 int32_t cannon_world_set_dt(cannon_world* w, double dt) { if (!w) return CANNON_E_INVALID; w->dt = dt; return CANNON_OK; }
 
 }  // extern "C"
@@ -2090,11 +2097,11 @@ int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* o) {
   return CANNON_OK;
 }
 
-__global__ void __launch_bounds__(256) k_refresh_inertia(BodyArrays B, int first, int count) {
+__global__ void __launch_bounds__(256) k_refresh_inertia(BodyArrays B, int first, int count, int force) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
     const int i = first + k;
     const f3 I = ld3(B.invI[i]);
-    if (I.x == I.y && I.y == I.z) continue;  // updateInertiaWorld(), rigid_body.dart:450-466
+    if (I.x == I.y && I.y == I.z && !force) continue;  // updateInertiaWorld(force), rigid_body.dart:450-466
     float4 r0, r1, r2;
     inertia_world(ldq(B.quat[i]), I, r0, r1, r2);
     B.iiw0[i] = r0; B.iiw1[i] = r1; B.iiw2[i] = r2;
@@ -2123,10 +2130,65 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
   if (force) W_TRY(w, put(force, w->force.p, 3));
   if (torque) W_TRY(w, put(torque, w->torque.p, 3));
   if (quaternion) {
-    { g_kernel_launches++; k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count); }
+    { g_kernel_launches++; k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count, 0); }
     W_TRY(w, cudaStreamSynchronize(s));
   }
   return CANNON_OK;
+}
+
+int32_t cannon_world_set_inv_inertia(cannon_world* w, int32_t first, int32_t count, const float* inv_inertia) {
+  if (!w || first < 0 || count < 0 || first + count > w->n || (count > 0 && !inv_inertia)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  if (count == 0) return CANNON_OK;
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  W_TRY(w, w->stage.reserve((size_t)4 * w->n));
+  W_TRY(w, cudaMemcpyAsync(w->stage.p, inv_inertia, (size_t)3 * count * sizeof(float), cudaMemcpyHostToDevice, s));
+  { g_kernel_launches++; k_pack_to4<<<grid_for(w, count, 256), 256, 0, s>>>(w->stage.p, w->invI.p + first, count, 3); }
+  { g_kernel_launches++; k_refresh_inertia<<<grid_for(w, count, 256), 256, 0, s>>>(body_arrays(w), first, count, 1); }
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
+int32_t cannon_world_update_sleep_states(cannon_world* w, int32_t first, int32_t count, const int32_t* sleep_state) {
+  if (!w || first < 0 || count < 0 || first + count > w->n || (count > 0 && !sleep_state)) return CANNON_E_INVALID;
+  for (int k = 0; k < count; k++)
+    if (sleep_state[k] < CANNON_AWAKE || sleep_state[k] > CANNON_SLEEPING) return fail(w->ctx, CANNON_E_INVALID, "sleep state out of range");
+  cudaSetDevice(w->ctx->device);
+  if (count == 0) return CANNON_OK;
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  W_TRY(w, cudaMemcpyAsync(w->sleep.p + first, sleep_state, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
+int32_t cannon_world_set_hinge_motor(cannon_world* w, int32_t constraint, int32_t enabled, double target_velocity, double max_force) {
+  if (!w || constraint < 0 || constraint >= (int)w->hConType.size()) return CANNON_E_INVALID;
+  if (w->hConType[constraint] != CANNON_CONSTRAINT_HINGE) return fail(w->ctx, CANNON_E_INVALID, "constraint is not a HingeConstraint");
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  const int eq = w->hConFirst[constraint] + 5;  // x, y, z, rotational1, rotational2, motor (hinge_constraint.dart:50)
+  const bool wasOn = w->hJEnabled[eq] != 0, on = enabled != 0;
+  const double mn = -max_force;
+  W_TRY(w, cudaMemcpyAsync(w->jTargetVel.p + eq, &target_velocity, sizeof(double), cudaMemcpyHostToDevice, s));
+  W_TRY(w, cudaMemcpyAsync(w->jMaxF.p + eq, &max_force, sizeof(double), cudaMemcpyHostToDevice, s));
+  W_TRY(w, cudaMemcpyAsync(w->jMinF.p + eq, &mn, sizeof(double), cudaMemcpyHostToDevice, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  if (wasOn == on) return CANNON_OK;
+  // the set of accepted equations changes (Solver.addEquation skips disabled ones, world_class.dart:627-633): new row slots
+  drop_step_graph(w);
+  w->hJEnabled[eq] = on ? 1 : 0;
+  std::vector<int> rowSlot(w->nJointEq), slotEq;
+  int slot = 0;
+  for (int e = 0; e < w->nJointEq; e++) {
+    if (w->hJEnabled[e] && !w->hJTrig[e]) { slotEq.push_back(e); rowSlot[e] = slot++; } else rowSlot[e] = -1;
+  }
+  w->nJointAccepted = slot;
+  W_TRY(w, upload(w->jEnabled, w->hJEnabled, s)); W_TRY(w, upload(w->jRowSlot, rowSlot, s)); W_TRY(w, upload(w->jSlotEq, slotEq, s));
+  W_TRY(w, cudaStreamSynchronize(s));
+  return ensure_capacities(w);
 }
 
 }  // extern "C"

@@ -22,9 +22,10 @@
 #pragma once
 #include "k_solver.cuh"
 
-#define GX_WARPS 8
+#define GX_WARPS 16
 #define GX_THREADS (GX_WARPS * 32)
-#define GX_CTAS_PER_SM 2
+#define GX_CTAS_PER_SM 1
+#define GX_TAIL_WINS GX_WARPS            // colours from which on at most this many windows remain run on CTA 0 only
 #define GX_LS_MAX 1024
 #define GX_SLOTS 4                       // ring slots per lane: GX_SLOTS - 1 rows in flight
 #define GX_SLOT_BYTES (GX_CHUNKS * 32 * 16 + 32 * 8)  // six 16-byte chunks + the row's multiplier (8 bytes) per lane
@@ -54,23 +55,51 @@ __device__ __forceinline__ void cp_async16_s(unsigned dst, const void* src) { as
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
+// Grid barrier for one CTA per SM, split into ARRIVE and WAIT so the requests for the next phase's rows can be issued in
+// between: a release has to wait for the thread's outstanding loads, and a warp that has just asked for 10 KB of rows from
+// DRAM would sit on its arrival for microseconds (measured: 10 - 17 us per phase when all CTAs arrive together with their
+// prefetches in flight, 1 us when they do not). Arrivals go to one counter; the last arriver publishes the phase number on a
+// second line and everybody else polls that line with relaxed loads (nobody writes it until the phase is over, so the
+// arrival atomics never queue behind the pollers), then fences once.
+__device__ __forceinline__ bool gx_arrive(unsigned* bar, unsigned& epoch, int nCtas) {  // one thread per CTA; true: this CTA was the last
+  epoch += 1;
+  unsigned v;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(bar) : "memory");
+  const bool last = v + 1u == epoch * (unsigned)nCtas;
+  if (last) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 32), "r"(epoch) : "memory");
+  return last;
+}
+__device__ __forceinline__ void gx_wait(unsigned* bar, unsigned epoch, bool last) {
+  if (last) return;
+  unsigned g;
+  while (true) {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 32) : "memory");
+    if (g >= epoch) break;
+    __nanosleep(20);
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 struct GxState {
   const int* lvlTask;  // [nLevels + 1] first window of each colour (k_gs_task_levels, windows of 32 units)
 };
 
-struct GxWin { int a, lvl, it; };  // a: window index inside the iteration, -1 = none
+struct GxWin { int a, lvl, it, k; };  // a: window index inside the iteration, -1 = none; k: the warp's k-th window of colour lvl
 
 __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArrays R, BodyArrays B, UnitArrays U, SchedArrays S, SolveParams P, GsStats G,
                                                                          GxState X) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ double s_red[GX_WARPS];
   __shared__ int s_lt[GX_LS_MAX + 2];
+  __shared__ int s_trc[2];  // trace: windows and row steps this CTA has swept so far
+  int trcW = 0, trcR = 0;
+  if (threadIdx.x == 0) s_trc[0] = s_trc[1] = 0;
   unsigned epoch = 0;
   const int nRows = min(*R.nRows, R.rowCap);
   const int nLevels = *S.nLevels;
   const int nTasks = X.lvlTask[nLevels];  // windows per iteration
   // CTAs for about twice the mean number of windows per colour
-  const int nCtas = coop_ctas(2LL * nTasks / max(nLevels, 1) + 1, GX_WARPS);
+  const int nCtas = coop_ctas(4LL * nTasks / max(nLevels, 1) + 1, GX_WARPS);
   if ((int)blockIdx.x >= nCtas) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -86,24 +115,36 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
   // LDS.128); the row's multiplier at ringL + s * GX_SLOT_BYTES (lanes interleaved by 8 B)
   const unsigned ring = smem_u32(s_dyn) + (unsigned)wic * GX_WARP_BYTES + (unsigned)lane * 16u;
   const unsigned ringL = smem_u32(s_dyn) + (unsigned)wic * GX_WARP_BYTES + GX_CHUNKS * 512u + (unsigned)lane * 8u;
-  // windows of a colour are dealt to the warps CTA-interleaved, rotated per colour
-  const int gw = wic * nCtas + blockIdx.x, nW = nCtas * GX_WARPS;
-
-  // Window j of a colour goes to warp slot (j * 1223 + colour * 61) mod nW inside each round of nW windows: windows are
-  // sorted by length, so neighbours in j are equally long - the multiplier scatters the long ones over all SM sub-partitions.
-  int gwInv = 0;
-  {  // inverse of x -> x * 1223 mod nW (1223 is prime and does not divide nW = 8 * nCtas for any grid used here)
-    long long a = 1223 % nW, b = nW, x0 = 1, x1 = 0;
-    while (b) { const long long q = a / b, t2 = a - q * b; a = b; b = t2; const long long t3 = x0 - q * x1; x0 = x1; x1 = t3; }
-    gwInv = (int)(((x0 % nW) + nW) % nW);  // a == gcd == 1
-  }
-  auto first_in = [&](int lvl) { return lt[lvl] + (int)(((long long)((gw - (lvl * 61) % nW + nW) % nW) * gwInv) % nW); };
-  auto seek = [&](GxWin& t) {  // t.a is a candidate inside colour t.lvl: move on to the warp's next window
+  // colours [tailStart, nLevels) hold at most GX_TAIL_WINS windows together (the last colours of a greedy colouring are a
+  // handful of units): CTA 0 sweeps them alone with block barriers in between - a grid barrier costs more than their work
+  int tailStart = nLevels;
+  while (tailStart > 0 && nTasks - lt[tailStart - 1] <= GX_TAIL_WINS) tailStart--;
+  if (nCtas == 1) tailStart = 0;
+  // Dealing the windows of a wide colour. Warps w, w + 4, w + 8, w + 12 of a CTA share an SM sub-partition (issue port, F2F
+  // and FP64 pipes): the unit of balance is the sub-partition, nS of them. The windows of a colour are sorted longest
+  // first and dealt in rounds of nS, forwards in even rounds and backwards in odd ones (sub-partition s gets windows s,
+  // 2 nS - 1 - s, 2 nS + s, ...: every sub-partition receives nearly the same number of rows), the start rotated per colour.
+  // Round rho of a sub-partition is taken by its warp rho % 4. Consecutive positions lie on different SMs.
+  const int nS = nCtas * 4, sid = (wic & 3) * nCtas + (int)blockIdx.x, sv = wic >> 2;
+  auto win_of = [&](int lvl, int k) -> int {  // the warp's k-th window of colour lvl, -1 past the end
+    const int n = lt[lvl + 1] - lt[lvl];
+    int j;
+    if (lvl >= tailStart) {
+      if (blockIdx.x != 0) return -1;
+      j = wic + GX_WARPS * k;
+    } else {
+      const int rho = sv + 4 * k;
+      const int s = (sid + nS - (lvl * 61) % nS) % nS;
+      j = rho * nS + ((rho & 1) ? nS - 1 - s : s);
+    }
+    return j < n ? lt[lvl] + j : -1;
+  };
+  auto seek = [&](GxWin& t) {  // (t.lvl, t.it, t.k) is a candidate: move on to the warp's next existing window
     int hops = 0;
-    while (t.a >= lt[t.lvl + 1]) {
-      if (++hops > nLevels) { t.a = -1; return; }  // the warp owns no window in any colour
-      if (++t.lvl == nLevels) { t.lvl = 0; if (++t.it >= P.maxIter) { t.a = -1; return; } }
-      t.a = first_in(t.lvl);
+    while ((t.a = win_of(t.lvl, t.k)) < 0) {
+      if (++hops > nLevels) return;  // the warp owns no window in any colour
+      t.k = 0;
+      if (++t.lvl == nLevels) { t.lvl = 0; if (++t.it >= P.maxIter) return; }
     }
   };
 
@@ -150,10 +191,18 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
     }
   };
 
+  auto prime_all = [&](const GxWin& t) {
+    prime(t);
+    // unit records of the window after that one towards L2 (32 x 64 B = 16 lines)
+    GxWin t2 = t;
+    if (t2.a >= 0) { t2.k++; seek(t2); }
+    if (t2.a >= 0 && lane < 16) prefetch_l2((const unsigned char*)(U.xrec + S.levelStart[t2.lvl] + 32 * (t2.a - lt[t2.lvl])) + lane * 128);
+  };
   GxWin t;
-  t.lvl = 0; t.it = 0; t.a = first_in(0);
+  t.lvl = 0; t.it = 0; t.k = 0; t.a = -1;
   seek(t);
   prime(t);
+  bool pend = false;  // the next window's rows are still to be requested
 
   int iter = 0;
   int trN = 0;
@@ -225,29 +274,24 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
           local += acc;
         }
         __syncwarp();
-        if (tr) {
+        if (P.trace) {
           const long long tend = clock64();
           int nrm = act ? (m.r1 - m.r0) >> 5 : 0;
           for (int o = 16; o > 0; o >>= 1) {
             nrm = max(nrm, __shfl_xor_sync(0xffffffffu, nrm, o)); tk1 = max(tk1, __shfl_xor_sync(0xffffffffu, tk1, o));
             tk2 = max(tk2, __shfl_xor_sync(0xffffffffu, tk2, o));
           }
-          if (lane == 0) {  // (body gather, whole window, of which waiting for rows, 32000 + rows)
+          if (lane == 0) { atomicAdd(&s_trc[0], 1); atomicAdd(&s_trc[1], nrm); }
+          if (lane == 0 && tr) {  // (body gather, whole window, of which waiting for rows, 32000 + rows)
             long long* o = P.trace + (size_t)gridDim.x * GS_TRACE_PHASES * 2 + (blockIdx.x * 4 + trN) * 4;
             o[0] = tk2; o[1] = tend - tk0; o[2] = tk1; o[3] = 32 * 1000 + nrm;
           }
-          trN++;
+          if (tr) trN++;
         }
-        // the warp's next window (same colour, a later colour or the next iteration): its unit records and first rows are
-        // requested now, i.e. before the barrier when it belongs to a later phase
-        t.a += nW;
+        // the warp's next window: requested right away if it belongs to this phase, else after the arrival at the barrier
+        t.k++;
         seek(t);
-        prime(t);
-        {  // unit records of the window after that one towards L2 (32 x 64 B = 16 lines)
-          GxWin t2 = t;
-          if (t2.a >= 0) { t2.a += nW; seek(t2); }
-          if (t2.a >= 0 && lane < 16) prefetch_l2((const unsigned char*)(U.xrec + S.levelStart[t2.lvl] + 32 * (t2.a - lt[t2.lvl])) + lane * 128);
-        }
+        if (t.a >= 0 && t.lvl == lvl && t.it == iter) prime_all(t); else pend = true;
       }
       if (lvl == nLevels - 1) {
         // the iteration's |delta lambda| total rides on the last colour barrier; totals rotate through three slots so a slot
@@ -262,8 +306,25 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
         }
       }
       GS_TRACE_WORK();
-      grid_barrier(S.bar, epoch, nCtas);
-      GS_TRACE_END();
+      // wide colours end with a grid barrier; inside the tail only CTA 0 works, a block barrier separates its colours
+      const bool grid = nCtas > 1 && (lvl < tailStart || lvl == nLevels - 1);
+      __syncthreads();
+      bool last = false;
+      if (grid && threadIdx.x == 0) last = gx_arrive(S.bar, epoch, nCtas);
+      if (pend) { prime_all(t); pend = false; }
+      if (grid) {
+        if (threadIdx.x == 0) gx_wait(S.bar, epoch, last);
+        __syncthreads();
+      }
+      if (P.trace && threadIdx.x == 0) {
+        const int ph = iter * nLevels + lvl;
+        if (ph < GS_TRACE_PHASES) {  // low words: cycles of work / of barrier wait; high words: windows / row steps of this CTA in the phase
+          const int cw = s_trc[0], cr = s_trc[1];
+          P.trace[(blockIdx.x * GS_TRACE_PHASES + ph) * 2] = ((trW - trS) & 0xffffffffLL) | ((long long)(cw - trcW) << 32);
+          P.trace[(blockIdx.x * GS_TRACE_PHASES + ph) * 2 + 1] = ((clock64() - trW) & 0xffffffffLL) | ((long long)(cr - trcR) << 32);
+          trcW = cw; trcR = cr;
+        }
+      }
       if (lvl == 0 && tid == 0) G.worldTot[(iter + 2) % 3] = 0.0;  // last read before this barrier, next used in iter + 2
     }
     // tolerance test (gs_solver.dart:99-107)

@@ -1063,6 +1063,11 @@ __global__ void __launch_bounds__(256) k_gs_task_levels(UnitArrays U, SchedArray
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    if (T.winMax == 0) {  // k_gs_exact: lvlWin holds the first 8-unit task of each colour
+      int q = 0;
+      for (int l = 0; l < nLevels; l++) { T.lvlWin[l] = q; q += (S.levelStart[l + 1] - S.levelStart[l] + 7) / 8; }
+      T.lvlWin[nLevels] = q;
+    }
     T.lvlTask[nLevels] = s_base;
     *T.nTasks = s_base;
     if (s_base > T.taskCap) atomicMax(taskOverflow, s_base);

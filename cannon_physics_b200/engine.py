@@ -230,6 +230,20 @@ class DeviceWorld:
         self._chk(self.lib.cannon_world_update_bodies(self.handle, first, count, *args))
         self._keep.clear()
 
+    def set_inv_inertia(self, first: int, inv_inertia):
+        a = np.ascontiguousarray(inv_inertia, dtype=np.float32)
+        self._chk(self.lib.cannon_world_set_inv_inertia(self.handle, first, a.size // 3, F.ptr(a, F.c_f32)))
+
+    def set_stepnumber(self, n: int):
+        self._chk(self.lib.cannon_world_set_stepnumber(self.handle, int(n)))
+
+    def update_sleep_states(self, first: int, sleep_state):
+        a = np.ascontiguousarray(sleep_state, dtype=np.int32)
+        self._chk(self.lib.cannon_world_update_sleep_states(self.handle, first, len(a), F.ptr(a, F.c_i32)))
+
+    def set_hinge_motor(self, constraint: int, enabled: bool, target_velocity: float, max_force: float):
+        self._chk(self.lib.cannon_world_set_hinge_motor(self.handle, constraint, int(enabled), float(target_velocity), float(max_force)))
+
     # ---- downloads -----------------------------------------------------------------------------
     def get_bodies(self, fields: Sequence[str] = ("position", "quaternion", "velocity", "angular_velocity"),
                    out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:

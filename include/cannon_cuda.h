@@ -282,6 +282,9 @@ int32_t cannon_world_set_springs(cannon_world* w, int32_t n, const cannon_spring
 /* World.time (used by Body.sleepTick, world_class.dart:693) */
 int32_t cannon_world_set_time(cannon_world* w, double time);
 int32_t cannon_world_get_time(cannon_world* w, double* time, int64_t* stepnumber);
+/* World.stepnumber (world_class.dart:696; the phase of quatNormalizeSkip, rigid_body.dart:637): restores it when a world
+ * is rebuilt from a checkpoint (cannon_world_get_bodies / set_bodies round trip) */
+int32_t cannon_world_set_stepnumber(cannon_world* w, int64_t stepnumber);
 
 /* ---- staged entry points (drop-in for World.broadphase / narrowphase / solver) ---- */
 /* Broadphase.collisionPairs(world,p1,p2), lib/collision/broadphase.dart:39, followed by the
@@ -341,6 +344,21 @@ int32_t cannon_world_get_rows(cannon_world* w, int32_t cap, int32_t* n_rows, int
 int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count, const float* position,
                                    const float* quaternion, const float* velocity, const float* angular_velocity,
                                    const float* force, const float* torque);
+
+/* Body.sleep() / Body.wakeUp() (lib/objects/rigid_body.dart:263-278) for bodies [first, first+count): only sleepState is
+ * written (Body.sleep also zeroes the velocities: send those through cannon_world_update_bodies). No other per-body
+ * state - sleep timers, mass properties, the contact-event sets - is touched. */
+int32_t cannon_world_update_sleep_states(cannon_world* w, int32_t first, int32_t count, const int32_t* sleep_state);
+/* Body.invInertia (local diagonal, 3 floats per body) for bodies [first, first+count), replacing what
+ * cannon_world_set_bodies derived from the pose at upload time: the reference computes it once, in the Body constructor /
+ * addShape (rigid_body.dart:85,362,587-609), so a world rebuilt from a checkpoint carries the original values over.
+ * invInertiaWorld is refreshed from the current orientation (rigid_body.dart:450-466). */
+int32_t cannon_world_set_inv_inertia(cannon_world* w, int32_t first, int32_t count, const float* inv_inertia);
+/* HingeConstraint.enableMotor / disableMotor / setMotorSpeed / setMotorMaxForce (lib/constraints/hinge_constraint.dart:
+ * 56-76) for constraint `constraint` (its index in the array given to cannon_world_set_constraints): the motor equation's
+ * enabled flag, targetVelocity and maxForce = -minForce are replaced; takes effect at the next step like in the
+ * reference, and nothing else (body state, the other constraints' frozen parameters) changes. */
+int32_t cannon_world_set_hinge_motor(cannon_world* w, int32_t constraint, int32_t enabled, double target_velocity, double max_force);
 
 #ifdef __cplusplus
 }

@@ -292,6 +292,36 @@ int32_t cannon_world_update_bodies(cannon_world* cw, int32_t first, int32_t coun
   return CANNON_OK;
 }
 
+int32_t cannon_world_set_inv_inertia(cannon_world* cw, int32_t first, int32_t count, const float* inv_inertia) {
+  if (!cw || first < 0 || count < 0 || first + count > (int)cw->w.bodies.size() || (count > 0 && !inv_inertia)) return CANNON_E_INVALID;
+  for (int k = 0; k < count; k++) {
+    Body& b = cw->w.bodies[first + k];
+    GETF3(b.invInertia, inv_inertia, k);
+    cw->w.updateInertiaWorld(b, true);  // rigid_body.dart:450-466
+  }
+  return CANNON_OK;
+}
+
+int32_t cannon_world_update_sleep_states(cannon_world* cw, int32_t first, int32_t count, const int32_t* sleep_state) {
+  if (!cw || first < 0 || count < 0 || first + count > (int)cw->w.bodies.size() || (count > 0 && !sleep_state)) return CANNON_E_INVALID;
+  for (int k = 0; k < count; k++)
+    if (sleep_state[k] < CANNON_AWAKE || sleep_state[k] > CANNON_SLEEPING) return fail(cw->ctx, CANNON_E_INVALID, "sleep state out of range");
+  for (int k = 0; k < count; k++) cw->w.bodies[first + k].sleepState = sleep_state[k];  // rigid_body.dart:263-278
+  return CANNON_OK;
+}
+
+int32_t cannon_world_set_hinge_motor(cannon_world* cw, int32_t constraint, int32_t enabled, double target_velocity, double max_force) {
+  if (!cw || constraint < 0 || constraint >= (int)cw->w.constraints.size()) return CANNON_E_INVALID;
+  Constraint& c = cw->w.constraints[constraint];
+  if (c.type != CANNON_CONSTRAINT_HINGE) return fail(cw->ctx, CANNON_E_INVALID, "constraint is not a HingeConstraint");
+  Eq& m = c.eqs[5];  // hinge_constraint.dart:50,56-76
+  m.enabled = enabled != 0;
+  m.targetVelocity = target_velocity;
+  m.maxForce = max_force;
+  m.minForce = -max_force;
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_constraint_desc* cs) {
   if (!cw || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
   World& w = cw->w;
@@ -449,6 +479,11 @@ int32_t cannon_world_get_time(cannon_world* cw, double* t, int64_t* stepnumber) 
   if (!cw) return CANNON_E_INVALID;
   if (t) *t = cw->w.time;
   if (stepnumber) *stepnumber = cw->w.stepnumber;
+  return CANNON_OK;
+}
+int32_t cannon_world_set_stepnumber(cannon_world* cw, int64_t n) {
+  if (!cw || n < 0) return CANNON_E_INVALID;
+  cw->w.stepnumber = n;
   return CANNON_OK;
 }
 int32_t cannon_world_set_dt(cannon_world* cw, double dt) {

@@ -201,6 +201,133 @@ def test_world_api_remove_body_and_constraint(oracle_lib):
     assert np.array_equal(a.position, a_ref.position) and np.array_equal(a.velocity, a_ref.velocity)
 
 
+def test_world_api_mutators_after_unsynced_steps_do_not_roll_the_world_back(oracle_lib):
+    """After step(sync=False) the device is ahead of the Body objects. Every mutator (applyForce, applyImpulse, wakeUp,
+    sleep, clearForces) pulls the device state before it writes, so the next upload can never restore a stale pose;
+    markDirty() - whose in-place edits have already happened - refuses instead."""
+    from cannon_physics_b200 import api
+
+    def build():
+        w = api.World(gravity=(0, -10, 0), _lib=oracle_lib)
+        a = api.Body(mass=1, shape=api.Sphere(0.5), position=(0, 10, 0))
+        b = api.Body(mass=2, shape=api.Box((0.3, 0.2, 0.1)), position=(3, 10, 0), angularVelocity=(1, 2, 3))
+        w.addBody(a)
+        w.addBody(b)
+        return w, a, b
+
+    ref, ra, rb = build()
+    for _ in range(11):
+        ref.step(1 / 60)
+    for mutate in ("applyForce", "applyImpulse", "wakeUp", "clearForces", "addContactMaterial"):
+        w, a, b = build()
+        for _ in range(10):
+            w.step(1 / 60, sync=False)
+        if mutate == "applyForce":
+            a.applyForce((0, 0, 0))
+        elif mutate == "applyImpulse":
+            a.applyImpulse((0, 0, 0))
+        elif mutate == "wakeUp":
+            a.wakeUp()
+        elif mutate == "clearForces":
+            w.clearForces()
+        else:
+            w.addContactMaterial(api.ContactMaterial(api.Material(), api.Material(), friction=0.1))
+        w.step(1 / 60)
+        assert w.stepnumber == 11, mutate
+        for x, y in ((a, ra), (b, rb)):
+            assert np.array_equal(x.position, y.position) and np.array_equal(x.velocity, y.velocity), mutate
+            assert np.array_equal(x.quaternion, y.quaternion) and np.array_equal(x.angularVelocity, y.angularVelocity), mutate
+    w, a, b = build()
+    w.step(1 / 60, sync=False)
+    with pytest.raises(api.CannonError):
+        w.markDirty()
+    w.sync()
+    a.position[1] = 20.0
+    w.markDirty()
+    w.step(1 / 60)
+    assert a.position[1] > 19.9
+
+
+def test_world_api_rebuild_keeps_stepnumber_inertia_and_sleep_timers(oracle_lib):
+    """A structural change (addBody far away) rebuilds the device world. What the reference would not touch stays put:
+    stepnumber (the quatNormalizeSkip phase), the tumbling box's invInertia (computed once at construction,
+    rigid_body.dart:85,362 - not from the pose at rebuild time) and timeLastSleepy; body.sleep() / wakeUp() do not rebuild."""
+    from cannon_physics_b200 import api
+
+    def build():
+        w = api.World(gravity=(0, 0, 0), quatNormalizeSkip=3, allowSleep=True, _lib=oracle_lib)
+        box = api.Body(mass=2, shape=api.Box((0.5, 0.2, 0.1)), position=(0, 0, 0), angularVelocity=(1, 2, 3), angularDamping=0.0)
+        w.addBody(box)
+        return w, box
+
+    ref, rbox = build()
+    for _ in range(60):
+        ref.step(1 / 60)
+    w, box = build()
+    for _ in range(20):
+        w.step(1 / 60, sync=False)
+    w.addBody(api.Body(mass=1, shape=api.Sphere(0.5), position=(100, 0, 0)))
+    dev_before = None
+    for k in range(40):
+        w.step(1 / 60, sync=False)
+        if k == 0:
+            dev_before = w._dev
+            assert w.stepnumber == 21
+    w.sync()
+    assert w.stepnumber == 60
+    assert np.array_equal(box.quaternion, rbox.quaternion) and np.array_equal(box.angularVelocity, rbox.angularVelocity)
+    box.sleep()
+    w.step(1 / 60)
+    assert w._dev is dev_before and box.sleepState == api.BodySleepStates.sleeping and not box.angularVelocity.any()
+    box.wakeUp()
+    w.step(1 / 60)
+    assert w._dev is dev_before and box.sleepState != api.BodySleepStates.sleeping  # at rest: awake -> sleepy (rigid_body.dart:290)
+
+
+def test_world_api_hinge_motor_setters_reach_a_live_world(oracle_lib):
+    """HingeConstraint.enableMotor / setMotorSpeed / setMotorMaxForce / disableMotor (hinge_constraint.dart:56-76) after the
+    first step: effective from the next step, without a rebuild, identical to a world that was built with the motor on."""
+    from cannon_physics_b200 import api
+
+    def build(motor_from_start):
+        w = api.World(gravity=(0, 0, 0), _lib=oracle_lib)
+        base = api.Body(mass=0, shape=api.Box((0.5, 0.5, 0.5)), position=(0, 0, 0))
+        wheel = api.Body(mass=1, shape=api.Sphere(0.5), position=(2, 0, 0), angularDamping=0.0)
+        w.addBody(base)
+        w.addBody(wheel)
+        h = api.HingeConstraint(base, wheel, pivotA=(2, 0, 0), pivotB=(0, 0, 0), axisA=(0, 0, 1), axisB=(0, 0, 1))
+        if motor_from_start:
+            h.enableMotor()
+            h.setMotorSpeed(2.0)
+            h.setMotorMaxForce(50.0)
+        w.addConstraint(h)
+        return w, wheel, h
+
+    a, wa, ha = build(False)
+    a.step(1 / 60)            # the motor is off: the wheel stays (numerically almost) at rest
+    assert np.abs(wa.angularVelocity).max() < 1e-9
+    dev = a._dev
+    ha.enableMotor()
+    ha.setMotorSpeed(2.0)
+    ha.setMotorMaxForce(50.0)
+    # the same history, but the motor fields reach the device through a full rebuild of the world (descriptor path)
+    b, wb, hb = build(False)
+    b.step(1 / 60)
+    hb.motorEnabled, hb.motorTargetVelocity, hb.motorMaxForce = True, 2.0, 50.0
+    b._structure_dirty = True
+    for _ in range(30):
+        a.step(1 / 60)
+        b.step(1 / 60)
+    assert a._dev is dev
+    assert abs(wa.angularVelocity[2]) > 1.0
+    assert np.array_equal(wa.angularVelocity, wb.angularVelocity) and np.array_equal(wa.quaternion, wb.quaternion)
+    ha.disableMotor()
+    before = wa.angularVelocity.copy()
+    for _ in range(10):
+        a.step(1 / 60)
+    assert a._dev is dev and np.allclose(wa.angularVelocity, before, atol=1e-5)  # free spinning again
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU: one JSON line with the
     same metric / unit / config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e record.

@@ -33,10 +33,12 @@ raw_tail_base = grid * 64 * 2
 print("CTAs", t.shape[0])
 nph = min(64, prof["n_levels"] * prof["iterations_done"])
 ghz = 1.9
-print("phase  work(us): mean   max | wait(us): min  mean | phase total(us) of CTA0")
+cntw, cntr = t[:, :, 0] >> 32, t[:, :, 1] >> 32  # windows / row steps per CTA and phase (k_gs_exact)
+t = t & 0xffffffff
+print("phase  work(us): mean   max | wait(us): min  mean | phase total(us) of CTA0 | windows: sum max/CTA | row steps: sum max/CTA")
 for ph in range(nph):
     wk, wt = t[:, ph, 0] / ghz / 1e3, t[:, ph, 1] / ghz / 1e3
-    print(f"{ph:4d}  {wk.mean():8.2f} {wk.max():8.2f} | {wt.min():8.2f} {wt.mean():8.2f} | {wk[0] + wt[0]:8.2f}")
+    print(f"{ph:4d}  {wk.mean():8.2f} {wk.max():8.2f} | {wt.min():8.2f} {wt.mean():8.2f} | {wk[0] + wt[0]:8.2f} | {cntw[:, ph].sum():6d} {cntw[:, ph].max():4d} | {cntr[:, ph].sum():7d} {cntr[:, ph].max():5d}")
 tot = (t[:, :nph, 0] + t[:, :nph, 1]).sum(1) / ghz / 1e3
 print("sum over traced phases (us): CTA mean", tot.mean(), " => per phase", tot.mean() / nph)
 rows = w.get_rows()
