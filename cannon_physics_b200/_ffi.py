@@ -120,6 +120,18 @@ class Profile(C.Structure):
     ]
 
 
+BATCH_MAX_GPUS = 16
+
+
+class BatchStats(C.Structure):
+    _fields_ = [
+        ("n_gpus", c_i32), ("n_worlds", c_i32), ("bodies_per_world", c_i32), ("pad0", c_i32),
+        ("n_pairs", c_i64), ("n_contacts", c_i64), ("n_rows", c_i64), ("iterations_done", c_i64), ("steps", c_i64),
+        ("contact_iters_total", c_i64), ("step_call_ms_max", c_f64), ("gpu_step_call_ms", c_f64 * BATCH_MAX_GPUS),
+        ("gpu_worlds", c_i32 * BATCH_MAX_GPUS),
+    ]
+
+
 VP = C.c_void_p
 
 # every symbol include/cannon_cuda.h declares: name -> (restype, argtypes)
@@ -161,6 +173,17 @@ PROTOTYPES = {
     "cannon_world_set_stepnumber": (c_i32, [VP, c_i64]),
     "cannon_world_update_sleep_states": (c_i32, [VP, c_i32, c_i32, P(c_i32)]),
     "cannon_world_set_hinge_motor": (c_i32, [VP, c_i32, c_i32, c_f64, c_f64]),
+    "cannon_batch_create": (c_i32, [P(c_i32), c_i32, P(WorldDesc), c_i32, c_i32, P(VP)]),
+    "cannon_batch_destroy": (None, [VP]),
+    "cannon_batch_last_error": (C.c_char_p, [VP]),
+    "cannon_batch_set_materials": (c_i32, [VP, c_i32, P(c_f64), P(c_f64), c_i32, P(ContactMaterialPOD)]),
+    "cannon_batch_set_shapes": (c_i32, [VP, c_i32, P(ShapeDesc)]),
+    "cannon_batch_set_bodies": (c_i32, [VP, P(BodiesSoA)]),
+    "cannon_batch_set_constraints": (c_i32, [VP, c_i32, P(ConstraintDesc)]),
+    "cannon_batch_step": (c_i32, [VP, c_f64, c_i32]),
+    "cannon_batch_stats": (c_i32, [VP, P(BatchStats)]),
+    "cannon_batch_get_bodies": (c_i32, [VP, P(BodiesSoA)]),
+    "cannon_batch_shard": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(VP)]),
 }
 
 

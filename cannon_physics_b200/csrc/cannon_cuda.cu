@@ -1093,6 +1093,7 @@ static StepParams step_params(cannon_world* w, double dt) {
   P.quatNormalizeFast = w->desc.quat_normalize_fast;
   P.needAABB = (w->desc.use_bounding_boxes || w->desc.broadphase_kind != CANNON_BP_NAIVE) ? 1 : 0;
   P.nWorlds = w->desc.n_worlds;
+  P.deferSleepTick = w->nSprings > 0 ? 1 : 0;
   return P;
 }
 
@@ -1546,6 +1547,7 @@ static int32_t st_integrate(cannon_world* w, double dt, int applyLambda) {
     S.anchorA = w->spAnchorA.p; S.anchorB = w->spAnchorB.p; S.off = w->spOff.p; S.idx = w->spIdx.p;
     g_kernel_launches++;
     k_springs<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), S, w->n);
+    if (P.allowSleep) { g_kernel_launches++; k_sleep_tick<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), P); }
   }
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
@@ -2192,3 +2194,6 @@ int32_t cannon_world_set_hinge_motor(cannon_world* w, int32_t constraint, int32_
 }
 
 }  // extern "C"
+
+// cannon_batch_*: host glue over the entry points above, shared by both libraries
+#include "batch_impl.inc"

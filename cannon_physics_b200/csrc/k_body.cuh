@@ -16,6 +16,7 @@ struct StepParams {
   int allowSleep, quatNormalizeFast;
   int needAABB;
   int nWorlds;
+  int deferSleepTick;  // springs in the world: sleepTick runs after the postStep slot (k_sleep_tick)
 };
 
 // Shape.calculateWorldAABB for the in-scope shapes
@@ -111,6 +112,25 @@ __global__ void __launch_bounds__(256) k_presolve(BodyArrays B, int n) {
 }
 
 // Algorithmic HBM bytes per body: see the K1 table; every array is touched once.
+// Body.sleepTick (rigid_body.dart:282-300); true when the velocities were zeroed
+__device__ __forceinline__ bool sleep_tick(const BodyArrays& B, const StepParams& P, int i, int sleep, f3& v, f3& w) {
+  const double speedSquared = vlen2(v) + vlen2(w);
+  const double lim = B.sleepSpeed[i];
+  const double speedLimitSquared = lim * lim;
+  if (sleep == CANNON_AWAKE && speedSquared < speedLimitSquared) {
+    B.tLastSleepy[i] = __longlong_as_double(P.clk[0]);
+    B.sleep[i] = CANNON_SLEEPY;
+  } else if (sleep == CANNON_SLEEPY && speedSquared > speedLimitSquared) {
+    B.sleep[i] = CANNON_AWAKE;
+  } else if (sleep == CANNON_SLEEPY && __longlong_as_double(P.clk[0]) - B.tLastSleepy[i] > B.sleepTime[i]) {
+    B.sleep[i] = CANNON_SLEEPING;
+    v.x = v.y = v.z = 0.f;
+    w.x = w.y = w.z = 0.f;
+    return true;
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, const int* __restrict__ worldRows, int applyLambda) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
     const int type = B.type[i];
@@ -188,26 +208,9 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepParams P, c
     // clearForces, world_class.dart:773-781
     B.force[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     B.torque[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // sleepTick, rigid_body.dart:282-300
-    if (P.allowSleep && (flags & BF_ALLOW_SLEEP)) {
-      const double speedSquared = vlen2(v) + vlen2(w);
-      const double lim = B.sleepSpeed[i];
-      const double speedLimitSquared = lim * lim;
-      if (sleep == CANNON_AWAKE && speedSquared < speedLimitSquared) {
-        sleep = CANNON_SLEEPY;
-        B.tLastSleepy[i] = __longlong_as_double(P.clk[0]);
-        B.sleep[i] = sleep;
-      } else if (sleep == CANNON_SLEEPY && speedSquared > speedLimitSquared) {
-        sleep = CANNON_AWAKE;
-        B.sleep[i] = sleep;
-      } else if (sleep == CANNON_SLEEPY && __longlong_as_double(P.clk[0]) - B.tLastSleepy[i] > B.sleepTime[i]) {
-        sleep = CANNON_SLEEPING;
-        B.sleep[i] = sleep;
-        v.x = v.y = v.z = 0.f;
-        w.x = w.y = w.z = 0.f;
-        dirtyVel = true;
-      }
-    }
+    // sleepTick, rigid_body.dart:282-300 - after the postStep slot (world_class.dart:685-699): with springs in the world it
+    // runs in k_sleep_tick, behind k_springs, so Spring.applyForce still sees the velocities of a body that falls asleep now
+    if (P.allowSleep && !P.deferSleepTick && (flags & BF_ALLOW_SLEEP)) dirtyVel |= sleep_tick(B, P, i, sleep, v, w);
     if (dirtyVel) {
       B.vel[i] = st3(v);
       B.angvel[i] = st3(w);
@@ -226,6 +229,15 @@ struct SpringArrays {
   const float4 *anchorA, *anchorB;
   const int *off, *idx;  // body -> springs touching it, ascending
 };
+
+// the deferred sleepTick of a world with springs (world_class.dart:691-699 comes after the postStep event of :685)
+__global__ void __launch_bounds__(256) k_sleep_tick(BodyArrays B, StepParams P) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
+    if (!(B.flags[i] & BF_ALLOW_SLEEP)) continue;
+    f3 v = ld3(B.vel[i]), w = ld3(B.angvel[i]);
+    if (sleep_tick(B, P, i, B.sleep[i], v, w)) { B.vel[i] = st3(v); B.angvel[i] = st3(w); }
+  }
+}
 
 __global__ void __launch_bounds__(256) k_springs(BodyArrays B, SpringArrays S, int nBodies) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBodies; b += gridDim.x * blockDim.x) {

@@ -4,21 +4,32 @@
 // Persistent cooperative kernel, one grid barrier per colour phase (units of a colour touch disjoint movable bodies, so a
 // phase is embarrassingly parallel and the result does not depend on how its units are spread over lanes and warps).
 //   * A window = 32 consecutive units of one colour, one unit per lane. Units of a colour are ordered by row count
-//     (k_len_*), so the lanes of a window carry equal work; windows are dealt to the warps round robin with a per-colour
-//     rotation (the long windows of every colour land on different warps).
+//     (k_len_*), so the lanes of a window carry equal work. The unit of balance is the SM sub-partition (its warps share
+//     one conversion pipe): the windows of a colour, longest first, are dealt to the sub-partitions in rounds, forwards
+//     and backwards alternately, rotated per colour.
 //   * Rows are stored window-interleaved (k_solver.cuh, GxRow): block r of a window holds row r of each of its 32 units,
 //     chunk by chunk, so one row step of a warp reads 3 KB of contiguous memory with coalesced 16-byte accesses. Every lane
-//     streams ITS rows global -> shared with cp.async into a private four-slot ring (three rows in flight while one is
-//     solved): the L2 latency of a row hides behind the f64 dependency chain of the previous ones, without spending
-//     registers on it; the window's remaining blocks are prefetched into L2 one phase ahead.
-//   * The unit records and the first rows of a warp's NEXT window are requested before the grid barrier (rows never change
-//     during a solve), so after the barrier only the body-lambda gather (L2) stands before the arithmetic.
-//   * 16 warps per SM (two CTAs) hide the latency of the f64 chains (~16 dependent DP operations per row).
+//     streams ITS rows global -> shared with cp.async into a private four-slot ring; the window's remaining blocks are
+//     prefetched into L2 one phase ahead.
+//   * The row loop is software-pipelined: the record of row r + 1 is read from the ring and widened while the dependent
+//     chain of row r runs, and the loop body is kept one basic block (no movable-body branches: an immovable body's
+//     deltas stay +0 by arithmetic) so the compiler can interleave the two.
+//   * One CTA of 16 warps per SM. The grid barrier is split into arrive / wait and the requests for the next phase's rows
+//     are issued in between (a release waits for the thread's outstanding loads); arrivals and the phase flag live on
+//     different lines, pollers use relaxed loads + one fence. The sparse last colours run on CTA 0 with block barriers.
+// What bounds it (tools/ubench/row_step.cu, cvt_rate.cu on a B200): a row update is 27 f32->f64 widenings, 12 f64->f32
+// roundings and ~60 FP64 operations per lane. F2F.F64.F32 retires ~3 lanes / clk / sub-partition, so a warp row step costs
+// ~350 clk of conversion pipe however many lanes are active (measured: 545 clk for a lone warp, 1412 clk with four warps
+// per sub-partition; replacing the conversions by integer or add-magic forms is exact but not faster). The solve is
+// therefore conversion-bound at ~0.13 ms for this scene if perfectly packed; the rest of the time is the longest unit of
+// every colour phase (up to 30 rows on one lane) and ~3 us of barrier + prologue per phase (100 phases).
 // History on the settled 100k pile of config 3 (1.36e6 rows, 10 colours, 10 iterations; profiles/README.md):
 //   unstaged level sweep k_gs 3.43 ms -> TMA-staged per-warp row windows with per-body dataflow counters 1.74 ms (8 warps
 //   per SM, 12 of 32 lanes busy: instruction-latency bound) -> 32-unit windows, dynamic claiming, dataflow 2.32 ms (every
 //   iteration drains at the tolerance barrier; a window waits for the slowest of its 64 predecessors, i.e. dataflow
-//   degenerates to one barrier per colour plus polling traffic) -> this kernel.
+//   degenerates to one barrier per colour plus polling traffic) -> barrier per colour, window-interleaved rows, cp.async
+//   rings 1.55 ms -> four lanes per unit (quarter of the chain, but 3x the warp instructions: 2.4 ms, rejected) -> split
+//   barrier, balanced dealing, tail colours on one CTA, pipelined row loop 1.28 ms.
 #pragma once
 #include "k_solver.cuh"
 
@@ -80,6 +91,46 @@ __device__ __forceinline__ void gx_wait(unsigned* bar, unsigned epoch, bool last
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
+// a row of the ring, widened: everything the update of one row needs besides the body deltas
+struct GxJ {
+  double nx, ny, nz, sAx, sAy, sAz, rAx, rAy, rAz, rBx, rBy, rBz, iAx, iAy, iAz, iBx, iBy, iBz;
+  double Bv, invC, eps, lam, mn, mx;
+  bool general;  // bounds in RowArrays.minF / maxF
+};
+__device__ __forceinline__ void gx_read_row(unsigned sa, unsigned sl, GxJ& j) {
+  const float4 q0 = lds_f4(sa), q1 = lds_f4(sa + 512), q2 = lds_f4(sa + 1024), q3 = lds_f4(sa + 1536);
+  double bound;
+  lds_d2(sa + 2048, j.Bv, j.invC);
+  lds_d2(sa + 2560, j.eps, bound);
+  j.lam = lds_f64(sl);
+  const int code = __float_as_int(q0.w);
+  j.nx = (double)q0.x; j.ny = (double)q0.y; j.nz = (double)q0.z;
+  // sA = -n, or 0 for a rotational row (equation_class.dart:95-105 with the Jacobian of rotational_equation.dart)
+  const bool rot = code & 1;
+  j.sAx = rot ? 0.0 : -j.nx; j.sAy = rot ? 0.0 : -j.ny; j.sAz = rot ? 0.0 : -j.nz;
+  j.rAx = (double)q1.x; j.rAy = (double)q1.y; j.rAz = (double)q1.z;
+  j.rBx = (double)q2.x; j.rBy = (double)q2.y; j.rBz = (double)q2.z;
+  j.iBx = (double)q3.x; j.iBy = (double)q3.y; j.iBz = (double)q3.z;
+  j.iAx = (double)q1.w; j.iAy = (double)q2.w; j.iAz = (double)q3.w;
+  const int bc = code >> 2;
+  j.general = bc == GXB_GENERAL;
+  j.mn = bc == GXB_POS ? 0.0 : -bound;
+  j.mx = bc == GXB_NEG ? 0.0 : bound;
+}
+// Vector3.dot of an f32-stored vector with a widened one, left to right (vec3.dart:62)
+__device__ __forceinline__ double gx_dot(const f3& a, double bx, double by, double bz) {
+  double s = (double)a.x * bx;
+  s += (double)a.y * by;
+  s += (double)a.z * bz;
+  return s;
+}
+// Vector3.addScaledVector into an f32-stored vector (vec3.dart:140): a + s * b, every component rounded to float
+__device__ __forceinline__ f3 gx_axpy(const f3& a, double s, double bx, double by, double bz) {
+  f3 r;
+  r.x = (float)((double)a.x + s * bx); r.y = (float)((double)a.y + s * by); r.z = (float)((double)a.z + s * bz);
+  return r;
+}
+
 struct GxState {
   const int* lvlTask;  // [nLevels + 1] first window of each colour (k_gs_task_levels, windows of 32 units)
 };
@@ -120,11 +171,11 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
   int tailStart = nLevels;
   while (tailStart > 0 && nTasks - lt[tailStart - 1] <= GX_TAIL_WINS) tailStart--;
   if (nCtas == 1) tailStart = 0;
-  // Dealing the windows of a wide colour. Warps w, w + 4, w + 8, w + 12 of a CTA share an SM sub-partition (issue port, F2F
+  // Dealing the windows of a wide colour. Warps w, w + 4, ... of a CTA share an SM sub-partition (issue port, F2F
   // and FP64 pipes): the unit of balance is the sub-partition, nS of them. The windows of a colour are sorted longest
   // first and dealt in rounds of nS, forwards in even rounds and backwards in odd ones (sub-partition s gets windows s,
   // 2 nS - 1 - s, 2 nS + s, ...: every sub-partition receives nearly the same number of rows), the start rotated per colour.
-  // Round rho of a sub-partition is taken by its warp rho % 4. Consecutive positions lie on different SMs.
+  // Round rho of a sub-partition is taken by its warp rho % (GX_WARPS / 4). Consecutive positions lie on different SMs.
   const int nS = nCtas * 4, sid = (wic & 3) * nCtas + (int)blockIdx.x, sv = wic >> 2;
   auto win_of = [&](int lvl, int k) -> int {  // the warp's k-th window of colour lvl, -1 past the end
     const int n = lt[lvl + 1] - lt[lvl];
@@ -133,7 +184,7 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
       if (blockIdx.x != 0) return -1;
       j = wic + GX_WARPS * k;
     } else {
-      const int rho = sv + 4 * k;
+      const int rho = sv + (GX_WARPS / 4) * k;
       const int s = (sid + nS - (lvl * 61) % nS) % nS;
       j = rho * nS + ((rho & 1) ? nS - 1 - s : s);
     }
@@ -191,6 +242,21 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
     }
   };
 
+  // row r of the lane's current unit (and its multiplier) into ring slot r % GX_SLOTS; commits a group either way
+  // row r of the lane's current unit (and its multiplier) into ring slot r % GX_SLOTS; commits a group either way.
+  // (Measured: a branch-free form - copies with a source size of zero past the last row - is 10 % slower than this branch;
+  // three MORE uniform branches in the row loop doubled the sweep's time: the loop lives on the compiler interleaving the
+  // next row's loads and widenings with the current row's dependent chain inside one basic block.)
+  auto gx_request = [&](int r) {
+    if (r < ((m.r1 - m.r0) >> 5)) {
+      const float4* q = xblk + (size_t)((m.r0 >> 5) + r) * (GX_CHUNKS * 32) + lane;
+      const unsigned dso = (unsigned)((r % GX_SLOTS) * GX_SLOT_BYTES), d = ring + dso;
+#pragma unroll
+      for (int c = 0; c < GX_CHUNKS; c++) cp_async16_s(d + c * 512, q + c * 32);
+      cp_async8_s(ringL + dso, R.lambda + m.r0 + 32 * r);
+    }
+    cp_async_commit();
+  };
   auto prime_all = [&](const GxWin& t) {
     prime(t);
     // unit records of the window after that one towards L2 (32 x 64 B = 16 lines)
@@ -225,49 +291,36 @@ __global__ void __launch_bounds__(GX_THREADS, GX_CTAS_PER_SM) k_gs_exact(RowArra
           f3 vA = ld3(vA4), wA = ld3(wA4), vB = ld3(vB4), wB = ld3(wB4);
           double acc = 0.0;
           const int nr = (m.r1 - m.r0) >> 5;
+          const double imA = m.imA, imB = m.imB;
+          // Software pipeline over the rows of the unit. The dependent chain of a row update (widen the body deltas, four dot
+          // products, delta lambda, clamp, four axpys, round) is ~20 f64 / conversion operations long; the 15 widenings of
+          // the row's own Jacobian and its shared-memory reads do not depend on the previous row, so the NEXT row's record
+          // is read and widened in the shadow of this row's chain (measured with tools/ubench/row_step: a lone warp needs
+          // 545 cycles per row when everything sits on the chain; what a colour phase costs is its longest unit).
+          // An immovable body has invMassSolve = 0 and I^-1 r = 0, so its (never stored) deltas stay +0 without a branch.
+          GxJ cur, nxt;
+          asm volatile("cp.async.wait_group %0;" ::"n"(GX_SLOTS - 2) : "memory");  // row 0 has landed
+          gx_read_row(ring, ringL, cur);
+          gx_request(3);  // rows 0 .. GX_SLOTS - 2 were requested with the unit record (prime)
           for (int r = 0; r < nr; r++) {
-            long long tw0 = 0;
-            if (tr) tw0 = clock64();
-            asm volatile("cp.async.wait_group %0;" ::"n"(GX_SLOTS - 2) : "memory");  // row r has landed
-            if (tr) tk1 += clock64() - tw0;  // trace: cycles spent waiting for rows
-            const unsigned so = (unsigned)((r % GX_SLOTS) * GX_SLOT_BYTES), sa = ring + so;
-            const float4 q0 = lds_f4(sa), q1 = lds_f4(sa + 512), q2 = lds_f4(sa + 1024), q3 = lds_f4(sa + 1536);
-            double Bv, invC, eps, bound;
-            lds_d2(sa + 2048, Bv, invC);
-            lds_d2(sa + 2560, eps, bound);
-            const double lam = lds_f64(ringL + so);
-            // request row r + GX_SLOTS - 1 (and its multiplier) into the slot row r - 1 was read from (its values were
-            // consumed by the previous update)
-            if (r + GX_SLOTS - 1 < nr) {
-              const float4* q = xblk + (size_t)((m.r0 >> 5) + r + GX_SLOTS - 1) * (GX_CHUNKS * 32) + lane;
-              const unsigned dso = (unsigned)(((r + GX_SLOTS - 1) % GX_SLOTS) * GX_SLOT_BYTES), d = ring + dso;
-#pragma unroll
-              for (int c = 0; c < GX_CHUNKS; c++) cp_async16_s(d + c * 512, q + c * 32);
-              cp_async8_s(ringL + dso, lp + 32 * (GX_SLOTS - 1));
-            }
-            cp_async_commit();
+            asm volatile("cp.async.wait_group %0;" ::"n"(GX_SLOTS - 2) : "memory");  // row r + 1 has landed (garbage past the end: never used)
+            const unsigned so = (unsigned)(((r + 1) % GX_SLOTS) * GX_SLOT_BYTES);
+            gx_read_row(ring + so, ringL + so, nxt);
+            gx_request(r + GX_SLOTS);  // into the slot of row r, which was read one step ago
             // one projected Gauss-Seidel row update (gs_solver.dart:88-102, equation_class.dart:95-105,151-169)
-            const int code = __float_as_int(q0.w);
-            f3 n, rA, rB, iA, iB, sA;
-            n.x = q0.x; n.y = q0.y; n.z = q0.z; rA.x = q1.x; rA.y = q1.y; rA.z = q1.z;
-            rB.x = q2.x; rB.y = q2.y; rB.z = q2.z; iB.x = q3.x; iB.y = q3.y; iB.z = q3.z;
-            iA.x = q1.w; iA.y = q2.w; iA.z = q3.w;
-            if (code & 1) { sA.x = sA.y = sA.z = 0.f; } else sA = vneg(n);
-            const double gwl = (vdot(vA, sA) + vdot(wA, rA)) + (vdot(vB, n) + vdot(wB, rB));
-            double dl = invC * (Bv - gwl - eps * lam);
-            double mn, mx;
-            const int bc = code >> 2;
-            if (bc == GXB_POS) { mn = 0.0; mx = bound; }
-            else if (bc == GXB_SYM) { mn = -bound; mx = bound; }
-            else if (bc == GXB_NEG) { mn = -bound; mx = 0.0; }
-            else { mn = R.minF[m.r0 + 32 * r]; mx = R.maxF[m.r0 + 32 * r]; }
-            if (lam + dl < mn) dl = mn - lam;
-            else if (lam + dl > mx) dl = mx - lam;
-            *lp = lam + dl;  // plain store: the same lane reads it back through L1 (cp.async.ca) one iteration later
-            lp += 32;
-            if (m.fl & 1) { vA = vaddscaled(vA, m.imA * dl, sA); wA = vaddscaled(wA, dl, iA); }
-            if (m.fl & 2) { vB = vaddscaled(vB, m.imB * dl, n); wB = vaddscaled(wB, dl, iB); }
+            const double gwl = (gx_dot(vA, cur.sAx, cur.sAy, cur.sAz) + gx_dot(wA, cur.rAx, cur.rAy, cur.rAz)) +
+                               (gx_dot(vB, cur.nx, cur.ny, cur.nz) + gx_dot(wB, cur.rBx, cur.rBy, cur.rBz));
+            double dl = cur.invC * (cur.Bv - gwl - cur.eps * cur.lam);
+            double mn = cur.mn, mx = cur.mx;
+            if (cur.general) { mn = R.minF[m.r0 + 32 * r]; mx = R.maxF[m.r0 + 32 * r]; }
+            if (cur.lam + dl < mn) dl = mn - cur.lam;
+            else if (cur.lam + dl > mx) dl = mx - cur.lam;
+            lp[32 * r] = cur.lam + dl;  // plain store: the same lane reads it back through L1 (cp.async.ca) one iteration later
+            const double dA = imA * dl, dB = imB * dl;
+            vA = gx_axpy(vA, dA, cur.sAx, cur.sAy, cur.sAz); wA = gx_axpy(wA, dl, cur.iAx, cur.iAy, cur.iAz);
+            vB = gx_axpy(vB, dB, cur.nx, cur.ny, cur.nz); wB = gx_axpy(wB, dl, cur.iBx, cur.iBy, cur.iBz);
             acc += dl > 0.0 ? dl : -dl;
+            cur = nxt;
           }
           if (m.fl & 1) st_f8(&B.vlam[2 * m.bi], st3(vA), st3(wA));
           if (m.fl & 2) st_f8(&B.vlam[2 * m.bj], st3(vB), st3(wB));

@@ -382,3 +382,75 @@ class DeviceWorld:
                                                  F.ptr(B, F.c_f64), F.ptr(invC, F.c_f64), F.ptr(lam, F.c_f64), F.ptr(lvl, F.c_i32)))
         k = n.value
         return {"body_i": bi[:k], "body_j": bj[:k], "B": B[:k], "invC": invC[:k], "lambda": lam[:k], "level": lvl[:k]}
+
+
+class _BatchCalls:
+    """The upload / download entry points DeviceWorld's marshalling code calls, mapped onto their cannon_batch_* twins."""
+    _MAP = {"cannon_world_set_materials": "cannon_batch_set_materials", "cannon_world_set_shapes": "cannon_batch_set_shapes",
+            "cannon_world_set_bodies": "cannon_batch_set_bodies", "cannon_world_set_constraints": "cannon_batch_set_constraints",
+            "cannon_world_get_bodies": "cannon_batch_get_bodies", "cannon_world_step": "cannon_batch_step"}
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        if name.startswith("cannon_world_") and name not in self._MAP:
+            raise AttributeError(f"{name} has no batch form: use DeviceBatch.shard(g) for the per-world entry points")
+        return getattr(self._lib, self._MAP.get(name, name))
+
+
+class DeviceBatch(DeviceWorld):
+    """One ``cannon_batch`` handle (include/cannon_cuda.h): the worlds of a batch spec sharded over ``devices``, all driven
+    from this one host thread. ``spec`` is a batch scene (desc.n_worlds worlds of n_bodies / n_worlds bodies each, world-major,
+    like scenes.chain_worlds)."""
+
+    def __init__(self, lib, spec: SceneSpec, devices: Sequence[int] = (0,)):
+        self.lib = _BatchCalls(lib)
+        self._raw = lib
+        self.ctx = None
+        self.spec = spec
+        self._keep = []
+        n_worlds = int(spec.desc.get("n_worlds", 1))
+        if spec.n_bodies % n_worlds:
+            raise ValueError("a batch needs the same number of bodies in every world")
+        if spec.springs:
+            raise F.CannonError(F.E_UNSUPPORTED, "springs have no batch entry point")
+        desc = make_world_desc(lib, **spec.desc)
+        self.desc = desc
+        self.handle = F.VP()
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        code = lib.cannon_batch_create(F.ptr(dev, F.c_i32), len(dev), C.byref(desc), n_worlds, spec.n_bodies // n_worlds, C.byref(self.handle))
+        if code != F.OK:
+            raise F.CannonError(code, "cannon_batch_create failed")
+        self.n = 0
+        self.set_materials(spec.material_friction, spec.material_restitution, spec.contact_materials)
+        self.set_shapes(spec.shapes)
+        self.set_bodies({k: v for k, v in spec.bodies.items() if k != "world_id"}, spec.n_bodies)
+        if spec.constraints:
+            self.set_constraints(spec.constraints)
+
+    def _chk(self, code):
+        if code != F.OK:
+            msg = self._raw.cannon_batch_last_error(self.handle)
+            raise F.CannonError(code, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._raw.cannon_batch_destroy(self.handle)
+            self.handle = F.VP()
+
+    def step(self, dt: float, nsteps: int = 1):
+        self._chk(self._raw.cannon_batch_step(self.handle, dt, nsteps))
+
+    def stats(self) -> Dict:
+        st = F.BatchStats()
+        self._chk(self._raw.cannon_batch_stats(self.handle, C.byref(st)))
+        out = {k: getattr(st, k) for k, _ in F.BatchStats._fields_ if not k.startswith("gpu_") and k != "pad0"}
+        out["gpu_step_call_ms"] = list(st.gpu_step_call_ms)[: st.n_gpus]
+        out["gpu_worlds"] = list(st.gpu_worlds)[: st.n_gpus]
+        return out
+
+    def shard(self, g: int):
+        first, n, h = F.c_i32(), F.c_i32(), F.VP()
+        self._chk(self._raw.cannon_batch_shard(self.handle, g, C.byref(first), C.byref(n), C.byref(h)))
+        return first.value, n.value, h

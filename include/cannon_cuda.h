@@ -345,6 +345,41 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
                                    const float* quaternion, const float* velocity, const float* angular_velocity,
                                    const float* force, const float* torque);
 
+/* ---- batches of independent worlds over the GPUs of one box ----
+ * n_worlds worlds of bodies_per_world bodies each (config 4: the RL / parameter-sweep case; the reference equivalent is a
+ * Dart program holding n_worlds World objects and calling World.step on each, lib/world/world_class.dart:392-431).
+ * Worlds are split into ngpu contiguous shards, one cannon_world (desc.n_worlds = its share) on its own cannon_ctx per
+ * device; body arrays are world-major (body b of world w = index w * bodies_per_world + b) and constraints use these
+ * global indices. cannon_batch_step enqueues every shard's steps without waiting (cannon_world_step_async) and then
+ * synchronises all of them (cannon_ctx_sync): one host thread / Dart isolate keeps all GPUs busy, with no cross-GPU
+ * traffic on the step path. A world's results do not depend on ngpu. */
+typedef struct cannon_batch cannon_batch;
+#define CANNON_BATCH_MAX_GPUS 16
+typedef struct cannon_batch_statistics {
+  int32_t n_gpus, n_worlds, bodies_per_world, pad0;
+  int64_t n_pairs, n_contacts, n_rows;   /* last step, summed over the shards */
+  int64_t iterations_done;               /* last step, max over the shards */
+  int64_t steps;                         /* steps taken since creation */
+  int64_t contact_iters_total;           /* accumulated, summed over the shards */
+  double  step_call_ms_max;              /* device time of the last cannon_batch_step call: max over the shards */
+  double  gpu_step_call_ms[CANNON_BATCH_MAX_GPUS];
+  int32_t gpu_worlds[CANNON_BATCH_MAX_GPUS];
+} cannon_batch_statistics;
+int32_t     cannon_batch_create(const int32_t* devices, int32_t ngpu, const cannon_world_desc* desc, int32_t n_worlds,
+                                int32_t bodies_per_world, cannon_batch** out);
+void        cannon_batch_destroy(cannon_batch* b);
+const char* cannon_batch_last_error(const cannon_batch* b);
+int32_t     cannon_batch_set_materials(cannon_batch* b, int32_t n_materials, const double* friction, const double* restitution,
+                                       int32_t n_contact_materials, const cannon_contact_material* cms);
+int32_t     cannon_batch_set_shapes(cannon_batch* b, int32_t n_shapes, const cannon_shape_desc* shapes);
+int32_t     cannon_batch_set_bodies(cannon_batch* b, const cannon_bodies_soa* bodies);   /* world_id is derived, not read */
+int32_t     cannon_batch_set_constraints(cannon_batch* b, int32_t n, const cannon_constraint_desc* cs);
+int32_t     cannon_batch_step(cannon_batch* b, double dt, int32_t nsteps);
+int32_t     cannon_batch_stats(cannon_batch* b, cannon_batch_statistics* out);
+int32_t     cannon_batch_get_bodies(cannon_batch* b, cannon_bodies_soa* out);           /* out->n = n_worlds * bodies_per_world */
+/* the shard of GPU `gpu`: its first world, its world count and its cannon_world (for the per-world entry points) */
+int32_t     cannon_batch_shard(cannon_batch* b, int32_t gpu, int32_t* first_world, int32_t* n_worlds, cannon_world** world);
+
 /* Body.sleep() / Body.wakeUp() (lib/objects/rigid_body.dart:263-278) for bodies [first, first+count): only sleepState is
  * written (Body.sleep also zeroes the velocities: send those through cannon_world_update_bodies). No other per-body
  * state - sleep timers, mass properties, the contact-event sets - is touched. */

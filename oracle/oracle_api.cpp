@@ -639,3 +639,6 @@ int32_t cannon_world_get_rows(cannon_world* cw, int32_t cap, int32_t* n_rows, in
 }
 
 }  // extern "C"
+
+// cannon_batch_*: host glue over the entry points above, shared by both libraries
+#include "../cannon_physics_b200/csrc/batch_impl.inc"

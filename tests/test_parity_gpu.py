@@ -31,7 +31,19 @@ STAGED = {
     "c4 jointed chain worlds (batch)": (lambda: scenes.chain_worlds(3, chains=2, links=5), 80),
     "c5 container with sleeping": (lambda: scenes.sphere_container(5, 5, 3, extent=4.0, solver=REF), 150),
     "8f joints: distance, lock, cone-twist": (lambda: scenes.constraint_zoo(groups=2), 150),
+    # bodies fall asleep while their springs still see a relative velocity: sleepTick must come after the postStep slot
+    # (world_class.dart:685-699), or the spring forces of the next step differ
+    "springs + sleeping (sleepTick after postStep)": (lambda: _sleepy(scenes.constraint_zoo(groups=2)), 120),
 }
+
+
+def _sleepy(spec):
+    spec.desc.update(allow_sleep=1)
+    n = spec.n_bodies
+    spec.bodies["allow_sleep"] = np.ones(n, np.uint8)
+    spec.bodies["sleep_speed_limit"] = np.full(n, 1.5)
+    spec.bodies["sleep_time_limit"] = np.full(n, 0.1)
+    return spec
 
 
 SPLIT = {
@@ -232,6 +244,45 @@ def test_hinge_motor_and_collide_connected(cuda_lib, oracle_lib):
     dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
     for s in range(60):
         parity.staged_step(dev, ref, 1 / 60, f"motor step {s}")
+
+
+@pytest.mark.parametrize("kind", ["reference", "colored"])
+def test_live_setters_hinge_motor_sleep_state_inertia_stepnumber(cuda_lib, oracle_lib, kind):
+    """The between-step setters a live world offers without a rebuild: HingeConstraint motor fields
+    (hinge_constraint.dart:56-76; switching the motor on or off changes the set of accepted equations), Body.sleep / wakeUp
+    (rigid_body.dart:263-278), Body.invInertia and World.stepnumber. Same calls on both libraries, bit-exact afterwards."""
+    spec = _with(scenes.chain_worlds(2, chains=2, links=4), allow_sleep=1, quat_normalize_skip=2,
+                 solver_kind=REF if kind == "reference" else F.SOLVER_COLORED)
+    hinges = [k for k, c in enumerate(spec.constraints) if c["type"] == F.CONSTRAINT_HINGE]
+    assert len(hinges) >= 2
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    n = spec.n_bodies
+    for s in range(50):
+        if s == 10:
+            for w in (dev, ref):
+                w.set_hinge_motor(hinges[0], True, 2.0, 5.0)
+                w.set_hinge_motor(hinges[1], True, -1.0, 50.0)
+        if s == 20:
+            inv = dev.get_bodies(("inv_inertia",))["inv_inertia"].reshape(n, 3).copy()
+            inv[3] = (0.5, 2.0, 1.0)
+            inv[4] = (1.0, 1.0, 1.0)   # isotropic: the world inertia is still refreshed (forced update)
+            sl = dev.get_bodies(("sleep_state",))["sleep_state"].copy()
+            sl[5] = F.SLEEPING if hasattr(F, "SLEEPING") else 2
+            for w in (dev, ref):
+                w.set_inv_inertia(3, inv[3:5])
+                w.update_sleep_states(0, sl)
+                w.set_stepnumber(7)
+        if s == 30:
+            for w in (dev, ref):
+                w.set_hinge_motor(hinges[0], False, 0.0, 5.0)
+                w.update_sleep_states(5, np.zeros(1, np.int32))
+        for w in (dev, ref):
+            w.step(1 / 60, 1)
+        parity.assert_same_state(dev, ref, f"setters step {s}")
+        if s == 20:
+            a, b = dev.get_bodies(("inv_inertia", "inv_inertia_world")), ref.get_bodies(("inv_inertia", "inv_inertia_world"))
+            assert np.array_equal(a["inv_inertia"], b["inv_inertia"]) and np.array_equal(a["inv_inertia_world"], b["inv_inertia_world"])
+    assert dev.get_time() == ref.get_time() and dev.get_time()[1] == 7 + 30
 
 
 def test_large_pair_set_equals_brute_force_and_is_deterministic(cuda_lib):
