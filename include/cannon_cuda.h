@@ -348,7 +348,7 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
 /* ---- batches of independent worlds over the GPUs of one box ----
  * n_worlds worlds of bodies_per_world bodies each (config 4: the RL / parameter-sweep case; the reference equivalent is a
  * Dart program holding n_worlds World objects and calling World.step on each, lib/world/world_class.dart:392-431).
- * Worlds are split into ngpu contiguous shards, one cannon_world (desc.n_worlds = its share) on its own cannon_ctx per
+ * Worlds are split into ngpu contiguous shards, one cannon_world handle with desc.n_worlds = its share, on its own cannon_ctx per
  * device; body arrays are world-major (body b of world w = index w * bodies_per_world + b) and constraints use these
  * global indices. cannon_batch_step enqueues every shard's steps without waiting (cannon_world_step_async) and then
  * synchronises all of them (cannon_ctx_sync): one host thread / Dart isolate keeps all GPUs busy, with no cross-GPU
@@ -377,7 +377,7 @@ int32_t     cannon_batch_set_constraints(cannon_batch* b, int32_t n, const canno
 int32_t     cannon_batch_step(cannon_batch* b, double dt, int32_t nsteps);
 int32_t     cannon_batch_stats(cannon_batch* b, cannon_batch_statistics* out);
 int32_t     cannon_batch_get_bodies(cannon_batch* b, cannon_bodies_soa* out);           /* out->n = n_worlds * bodies_per_world */
-/* the shard of GPU `gpu`: its first world, its world count and its cannon_world (for the per-world entry points) */
+/* the shard of GPU `gpu`: its first world, its world count and the cannon_world handle that serves the per-world entry points */
 int32_t     cannon_batch_shard(cannon_batch* b, int32_t gpu, int32_t* first_world, int32_t* n_worlds, cannon_world** world);
 
 /* Body.sleep() / Body.wakeUp() (lib/objects/rigid_body.dart:263-278) for bodies [first, first+count): only sleepState is

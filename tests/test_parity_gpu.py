@@ -495,3 +495,26 @@ def test_dataflow_sweep_equals_level_sweep_on_the_100k_pile(cuda_lib):
     ra, rb = a.get_rows(), b.get_rows()
     for k in ("body_i", "body_j", "B", "invC", "lambda", "level"):
         assert np.array_equal(ra[k], rb[k]), k
+
+
+@pytest.mark.gpu
+def test_cannon_batch_two_contexts_one_host_thread(cuda_lib, oracle_lib):
+    """cannon_batch_* on the device: the batch split into two shards, each on its own context / stream (both on GPU 0 here;
+    one per GPU on a multi-GPU box), stepped concurrently from this one thread (step_async on every shard, then ctx_sync).
+    Per-world results equal the unsharded batch and the oracle bit for bit; the statistics add up."""
+    import torch
+    spec = _with(scenes.chain_worlds(12, chains=3, links=6), solver_kind=F.SOLVER_COLORED)
+    whole, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    devices = (0, 1) if torch.cuda.device_count() > 1 else (0, 0)
+    b = engine.DeviceBatch(cuda_lib, spec, devices=devices)
+    for _ in range(3):
+        whole.step(1 / 60, 20)
+        ref.step(1 / 60, 20)
+        b.step(1 / 60, 20)
+        got, want = b.get_bodies(parity.STATE), ref.get_bodies(parity.STATE)
+        for k in parity.STATE:
+            assert np.array_equal(got[k], want[k]), k
+        parity.assert_same_state(whole, ref, "unsharded batch")
+    st = b.stats()
+    assert st["steps"] == 60 and st["n_contacts"] == whole.profile()["n_contacts"] and st["step_call_ms_max"] > 0
+    b.close()
