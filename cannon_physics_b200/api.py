@@ -392,6 +392,20 @@ class DistanceConstraint(Constraint):  # distance_constraint.dart:7
                     collide_connected=int(self.collideConnected), distance=-1.0 if self.distance is None else float(self.distance))
 
 
+class SpringConstraint(DistanceConstraint):  # spring_constraint.dart:7-56
+    """One bidirectional ContactEquation that holds the bodies at the distance they have when the constraint is made, its
+    force bounded by +-stiffness (spring_constraint.dart:34-41); update() is DistanceConstraint's (:44-55). `damping` is
+    stored and never read, like in the reference. On the device it is a distance row with max_force = stiffness."""
+
+    def __init__(self, bodyA, bodyB, stiffness: float = 1.0, damping: float = 1.0):
+        super().__init__(bodyA, bodyB, None, stiffness)
+        self.stiffness, self.damping = stiffness, damping
+
+    def _desc(self, idx):
+        self.maxForce = self.stiffness
+        return super()._desc(idx)
+
+
 class LockConstraint(PointToPointConstraint):  # lock_constraint.dart:9
     """The pivots and the frame vectors are taken from the bodies' poses when the constraint reaches the world
     (lock_constraint.dart:29-43), quirks of Body.vectorToLocalFrame included."""

@@ -1,12 +1,23 @@
-// cannon_cuda_bindings.dart — dart:ffi binding of libcannon_cuda.so (include/cannon_cuda.h).
+// cannon_cuda_bindings.dart — dart:ffi binding of libcannon_cuda.so: EVERY struct and symbol of include/cannon_cuda.h.
 //
-// NOT compiled in the build container (no Dart SDK there); kept thin and mechanical so a maintainer of
-// cannon_physics can drop it into lib/cuda/ next to the reference's Broadphase / Narrowphase / Solver classes.
-// Every native symbol below is exported by the library and exercised through the identical ctypes binding in
-// cannon_physics_b200/_ffi.py.
+// NOT compiled in the build container (no Dart SDK there; SURVEY.md 8b caveat). It is kept mechanical: one Struct per
+// C struct with the fields in declaration order, one lookupFunction per symbol with the C signature next to it. The same
+// table exists as ctypes prototypes in cannon_physics_b200/_ffi.py, where tests/test_host_logic.py checks it against the
+// header symbol by symbol and against both libraries' export tables; a maintainer who changes the header changes the
+// three places together. Drop the file into lib/cuda/ of cannon_physics next to cuda_world.dart.
+// ignore_for_file: non_constant_identifier_names, camel_case_types
 import 'dart:ffi';
 import 'package:ffi/ffi.dart';
 
+// ---- enums of the header -------------------------------------------------------------------------------------------
+const cannonOk = 0, cannonEInvalid = -1, cannonECuda = -2, cannonECapacity = -3, cannonEUnsupported = -4, cannonENoGpu = -5;
+const shapeSphere = 0, shapePlane = 1, shapeBox = 2, shapeConvex = 3, shapeCylinder = 4, shapeHeightfield = 8; // ShapeType.index
+const bpNaive = 0, bpSap = 1, bpGrid = 2;
+const solverReferenceOrder = 0, solverColored = 1, solverSplit = 2, solverColoredF32 = 3;
+const constraintPointToPoint = 0, constraintHinge = 1, constraintDistance = 2, constraintLock = 3, constraintConeTwist = 4;
+const cannonBatchMaxGpus = 16;
+
+// ---- structs ---------------------------------------------------------------------------------------------------------
 final class CannonContactMaterial extends Struct {
   @Int32() external int materialA;
   @Int32() external int materialB;
@@ -25,10 +36,10 @@ final class CannonWorldDesc extends Struct {
   @Int32() external int allowSleep;
   @Int32() external int quatNormalizeSkip;
   @Int32() external int quatNormalizeFast;
-  @Int32() external int solverKind;        // 0 reference order (bit-reproducible), 1 colored (throughput)
+  @Int32() external int solverKind;
   @Int32() external int solverIterations;
   @Double() external double solverTolerance;
-  @Int32() external int broadphaseKind;    // 0 Naive, 1 SAP, 2 Grid
+  @Int32() external int broadphaseKind;
   @Int32() external int useBoundingBoxes;
   @Int32() external int sapAxis;
   @Int32() external int gridNx;
@@ -42,68 +53,259 @@ final class CannonWorldDesc extends Struct {
   @Int32() external int maxContacts;
 }
 
+final class CannonShapeDesc extends Struct {
+  @Int32() external int type;
+  @Int32() external int collisionResponse;
+  @Int32() external int collisionFilterGroup;
+  @Int32() external int collisionFilterMask;
+  @Double() external double radius;
+  @Array(3) external Array<Float> halfExtents;
+  @Double() external double radiusTop;
+  @Double() external double radiusBottom;
+  @Double() external double height;
+  @Int32() external int numSegments;
+  @Int32() external int nVertices;
+  external Pointer<Float> vertices;
+  @Int32() external int nFaces;
+  external Pointer<Int32> faceOffsets;
+  external Pointer<Int32> faceIndices;
+  @Int32() external int hfNx;
+  @Int32() external int hfNy;
+  external Pointer<Double> hfData;
+  @Int32() external int hfElementSize;
+}
+
 final class CannonBodiesSoa extends Struct {
   @Int32() external int n;
-  external Pointer<Float> position, quaternion, velocity, angularVelocity, force, torque;
+  external Pointer<Float> position;
+  external Pointer<Float> quaternion;
+  external Pointer<Float> velocity;
+  external Pointer<Float> angularVelocity;
+  external Pointer<Float> force;
+  external Pointer<Float> torque;
   external Pointer<Double> mass;
-  external Pointer<Int32> type, sleepState;
+  external Pointer<Int32> type;
+  external Pointer<Int32> sleepState;
   external Pointer<Double> timeLastSleepy;
   external Pointer<Uint8> allowSleep;
-  external Pointer<Double> sleepSpeedLimit, sleepTimeLimit, linearDamping, angularDamping;
-  external Pointer<Float> linearFactor, angularFactor;
+  external Pointer<Double> sleepSpeedLimit;
+  external Pointer<Double> sleepTimeLimit;
+  external Pointer<Double> linearDamping;
+  external Pointer<Double> angularDamping;
+  external Pointer<Float> linearFactor;
+  external Pointer<Float> angularFactor;
   external Pointer<Uint8> fixedRotation;
-  external Pointer<Int32> collisionFilterGroup, collisionFilterMask;
-  external Pointer<Uint8> collisionResponse, isTrigger;
-  external Pointer<Int32> material, shape, worldId;
+  external Pointer<Int32> collisionFilterGroup;
+  external Pointer<Int32> collisionFilterMask;
+  external Pointer<Uint8> collisionResponse;
+  external Pointer<Uint8> isTrigger;
+  external Pointer<Int32> material;
+  external Pointer<Int32> shape;
+  external Pointer<Int32> worldId;
   external Pointer<Double> invMass;
-  external Pointer<Float> invInertia, invInertiaWorld;
+  external Pointer<Float> invInertia;
+  external Pointer<Float> invInertiaWorld;
   external Pointer<Double> boundingRadius;
   external Pointer<Float> aabb;
 }
 
+final class CannonConstraintDesc extends Struct {
+  @Int32() external int type;
+  @Int32() external int bodyA;
+  @Int32() external int bodyB;
+  @Array(3) external Array<Float> pivotA;
+  @Array(3) external Array<Float> pivotB;
+  @Array(3) external Array<Float> axisA;
+  @Array(3) external Array<Float> axisB;
+  @Double() external double maxForce;
+  @Int32() external int collideConnected;
+  @Int32() external int motorEnabled;
+  @Double() external double motorTargetVelocity;
+  @Double() external double motorMaxForce;
+  @Double() external double distance;
+  @Double() external double angle;
+  @Double() external double twistAngle;
+}
+
+final class CannonSpringDesc extends Struct {
+  @Int32() external int bodyA;
+  @Int32() external int bodyB;
+  @Double() external double restLength;
+  @Double() external double stiffness;
+  @Double() external double damping;
+  @Array(3) external Array<Float> localAnchorA;
+  @Array(3) external Array<Float> localAnchorB;
+}
+
 final class CannonContactsSoa extends Struct {
   @Int32() external int capacity;
-  external Pointer<Int32> bodyI, bodyJ;
-  external Pointer<Float> ri, rj, ni;
-  external Pointer<Double> restitution, friction;
+  external Pointer<Int32> bodyI;
+  external Pointer<Int32> bodyJ;
+  external Pointer<Float> ri;
+  external Pointer<Float> rj;
+  external Pointer<Float> ni;
+  external Pointer<Double> restitution;
+  external Pointer<Double> friction;
   external Pointer<Uint8> enabled;
   external Pointer<Double> multiplier;
 }
 
-typedef _CtxCreateC = Int32 Function(Int32, Pointer<Pointer<Void>>);
-typedef _CtxCreateD = int Function(int, Pointer<Pointer<Void>>);
-typedef _WorldCreateC = Int32 Function(Pointer<Void>, Pointer<CannonWorldDesc>, Pointer<Pointer<Void>>);
-typedef _WorldCreateD = int Function(Pointer<Void>, Pointer<CannonWorldDesc>, Pointer<Pointer<Void>>);
-typedef _SetBodiesC = Int32 Function(Pointer<Void>, Pointer<CannonBodiesSoa>);
-typedef _SetBodiesD = int Function(Pointer<Void>, Pointer<CannonBodiesSoa>);
-typedef _StepC = Int32 Function(Pointer<Void>, Double, Int32);
-typedef _StepD = int Function(Pointer<Void>, double, int);
-typedef _PairsC = Int32 Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, Int32, Pointer<Int32>);
-typedef _PairsD = int Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, int, Pointer<Int32>);
-typedef _ContactsC = Int32 Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, Int32, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>);
-typedef _ContactsD = int Function(Pointer<Void>, Pointer<Int32>, Pointer<Int32>, int, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>);
-typedef _EventsEnableC = Int32 Function(Pointer<Void>, Int32);
-typedef _EventsEnableD = int Function(Pointer<Void>, int);
-typedef _EventsGetC = Int32 Function(Pointer<Void>, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>);
-typedef _EventsGetD = int Function(Pointer<Void>, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>);
-typedef _SolveC = Int32 Function(Pointer<Void>, Double, Pointer<Int32>);
-typedef _SolveD = int Function(Pointer<Void>, double, Pointer<Int32>);
+final class CannonProfile extends Struct {
+  @Double() external double solve;
+  @Double() external double makeContactConstraints;
+  @Double() external double broadphase;
+  @Double() external double integrate;
+  @Double() external double narrowphase;
+  @Int64() external int nPairs;
+  @Int64() external int nContacts;
+  @Int64() external int nRows;
+  @Int64() external int nLevels;
+  @Int64() external int iterationsDone;
+  @Int64() external int steps;
+  @Int64() external int contactItersTotal;
+  @Double() external double stepCallMs;
+  @Double() external double scheduleMs;
+  @Double() external double gsMs;
+  @Int64() external int kernelLaunches;
+  @Int64() external int nTasks;
+  @Int64() external int nIslands;
+  @Array(8) external Array<Int64> nTasksByType;
+  @Int64() external int sumSteps;
+  @Double() external double sumStepMs;
+  @Double() external double sumBroadphase;
+  @Double() external double sumNarrowphase;
+  @Double() external double sumSolve;
+  @Double() external double sumIntegrate;
+  @Double() external double sumSchedule;
+  @Double() external double sumGs;
+}
 
+final class CannonBatchStatistics extends Struct {
+  @Int32() external int nGpus;
+  @Int32() external int nWorlds;
+  @Int32() external int bodiesPerWorld;
+  @Int32() external int pad0;
+  @Int64() external int nPairs;
+  @Int64() external int nContacts;
+  @Int64() external int nRows;
+  @Int64() external int iterationsDone;
+  @Int64() external int steps;
+  @Int64() external int contactItersTotal;
+  @Double() external double stepCallMsMax;
+  @Array(16) external Array<Double> gpuStepCallMs;
+  @Array(16) external Array<Int32> gpuWorlds;
+}
+
+typedef H = Pointer<Void>; // opaque cannon_ctx* / cannon_world* / cannon_batch*
+
+// ---- symbols ---------------------------------------------------------------------------------------------------------
 class CannonCuda {
   final DynamicLibrary lib;
-  late final _CtxCreateD ctxCreate = lib.lookupFunction<_CtxCreateC, _CtxCreateD>('cannon_ctx_create');
+  CannonCuda([String path = 'libcannon_cuda.so']) : lib = DynamicLibrary.open(path);
+
+  // lifecycle
+  late final int Function() version = lib.lookupFunction<Int32 Function(), int Function()>('cannon_version');
+  late final Pointer<Utf8> Function() backend = lib.lookupFunction<Pointer<Utf8> Function(), Pointer<Utf8> Function()>('cannon_backend');
+  late final int Function(int, Pointer<H>) ctxCreate =
+      lib.lookupFunction<Int32 Function(Int32, Pointer<H>), int Function(int, Pointer<H>)>('cannon_ctx_create');
+  late final void Function(H) ctxDestroy = lib.lookupFunction<Void Function(H), void Function(H)>('cannon_ctx_destroy');
+  late final Pointer<Utf8> Function(H) lastError = lib.lookupFunction<Pointer<Utf8> Function(H), Pointer<Utf8> Function(H)>('cannon_last_error');
   late final void Function(Pointer<CannonWorldDesc>) worldDescDefault =
       lib.lookupFunction<Void Function(Pointer<CannonWorldDesc>), void Function(Pointer<CannonWorldDesc>)>('cannon_world_desc_default');
-  late final _WorldCreateD worldCreate = lib.lookupFunction<_WorldCreateC, _WorldCreateD>('cannon_world_create');
-  late final _SetBodiesD worldSetBodies = lib.lookupFunction<_SetBodiesC, _SetBodiesD>('cannon_world_set_bodies');
-  late final _SetBodiesD worldGetBodies = lib.lookupFunction<_SetBodiesC, _SetBodiesD>('cannon_world_get_bodies');
-  late final _StepD worldStep = lib.lookupFunction<_StepC, _StepD>('cannon_world_step');
-  late final _PairsD broadphasePairs = lib.lookupFunction<_PairsC, _PairsD>('cannon_broadphase_pairs');
-  late final _ContactsD narrowphaseContacts = lib.lookupFunction<_ContactsC, _ContactsD>('cannon_narrowphase_contacts');
-  late final _SolveD solverSolve = lib.lookupFunction<_SolveC, _SolveD>('cannon_solver_solve');
-  late final _EventsEnableD enableContactEvents = lib.lookupFunction<_EventsEnableC, _EventsEnableD>('cannon_world_enable_contact_events');
-  late final _EventsGetD getContactEvents = lib.lookupFunction<_EventsGetC, _EventsGetD>('cannon_world_get_contact_events');
-  late final Pointer<Utf8> Function(Pointer<Void>) lastError =
-      lib.lookupFunction<Pointer<Utf8> Function(Pointer<Void>), Pointer<Utf8> Function(Pointer<Void>)>('cannon_last_error');
-  CannonCuda([String path = 'libcannon_cuda.so']) : lib = DynamicLibrary.open(path);
+  late final void Function(Pointer<CannonShapeDesc>) shapeDescDefault =
+      lib.lookupFunction<Void Function(Pointer<CannonShapeDesc>), void Function(Pointer<CannonShapeDesc>)>('cannon_shape_desc_default');
+
+  // world
+  late final int Function(H, Pointer<CannonWorldDesc>, Pointer<H>) worldCreate = lib.lookupFunction<
+      Int32 Function(H, Pointer<CannonWorldDesc>, Pointer<H>), int Function(H, Pointer<CannonWorldDesc>, Pointer<H>)>('cannon_world_create');
+  late final void Function(H) worldDestroy = lib.lookupFunction<Void Function(H), void Function(H)>('cannon_world_destroy');
+  late final int Function(H, int, Pointer<Double>, Pointer<Double>, int, Pointer<CannonContactMaterial>) worldSetMaterials = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<Double>, Pointer<Double>, Int32, Pointer<CannonContactMaterial>),
+      int Function(H, int, Pointer<Double>, Pointer<Double>, int, Pointer<CannonContactMaterial>)>('cannon_world_set_materials');
+  late final int Function(H, int, Pointer<CannonShapeDesc>) worldSetShapes =
+      lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonShapeDesc>), int Function(H, int, Pointer<CannonShapeDesc>)>('cannon_world_set_shapes');
+  late final int Function(H, Pointer<CannonBodiesSoa>) worldSetBodies =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_world_set_bodies');
+  late final int Function(H, Pointer<CannonBodiesSoa>) worldGetBodies =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_world_get_bodies');
+  late final int Function(H, int, Pointer<CannonConstraintDesc>) worldSetConstraints = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<CannonConstraintDesc>), int Function(H, int, Pointer<CannonConstraintDesc>)>('cannon_world_set_constraints');
+  late final int Function(H, int, Pointer<CannonSpringDesc>) worldSetSprings =
+      lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonSpringDesc>), int Function(H, int, Pointer<CannonSpringDesc>)>('cannon_world_set_springs');
+  late final int Function(H, double) worldSetTime = lib.lookupFunction<Int32 Function(H, Double), int Function(H, double)>('cannon_world_set_time');
+  late final int Function(H, Pointer<Double>, Pointer<Int64>) worldGetTime =
+      lib.lookupFunction<Int32 Function(H, Pointer<Double>, Pointer<Int64>), int Function(H, Pointer<Double>, Pointer<Int64>)>('cannon_world_get_time');
+  late final int Function(H, int) worldSetStepnumber = lib.lookupFunction<Int32 Function(H, Int64), int Function(H, int)>('cannon_world_set_stepnumber');
+  late final int Function(H, double) worldSetDt = lib.lookupFunction<Int32 Function(H, Double), int Function(H, double)>('cannon_world_set_dt');
+
+  // staged entry points
+  late final int Function(H) applyGravity = lib.lookupFunction<Int32 Function(H), int Function(H)>('cannon_apply_gravity');
+  late final int Function(H, Pointer<Int32>, Pointer<Int32>, int, Pointer<Int32>) broadphasePairs = lib.lookupFunction<
+      Int32 Function(H, Pointer<Int32>, Pointer<Int32>, Int32, Pointer<Int32>),
+      int Function(H, Pointer<Int32>, Pointer<Int32>, int, Pointer<Int32>)>('cannon_broadphase_pairs');
+  late final int Function(H, Pointer<Int32>, Pointer<Int32>, int, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>) narrowphaseContacts =
+      lib.lookupFunction<Int32 Function(H, Pointer<Int32>, Pointer<Int32>, Int32, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>),
+          int Function(H, Pointer<Int32>, Pointer<Int32>, int, Pointer<CannonContactsSoa>, Pointer<Int32>, Pointer<Int32>)>('cannon_narrowphase_contacts');
+  late final int Function(H, double, Pointer<Int32>) solverSolve =
+      lib.lookupFunction<Int32 Function(H, Double, Pointer<Int32>), int Function(H, double, Pointer<Int32>)>('cannon_solver_solve');
+  late final int Function(H, double) integrate = lib.lookupFunction<Int32 Function(H, Double), int Function(H, double)>('cannon_integrate');
+
+  // fused
+  late final int Function(H, double, int) worldStep = lib.lookupFunction<Int32 Function(H, Double, Int32), int Function(H, double, int)>('cannon_world_step');
+  late final int Function(H, double, int) worldStepProfiled =
+      lib.lookupFunction<Int32 Function(H, Double, Int32), int Function(H, double, int)>('cannon_world_step_profiled');
+  late final int Function(H, double, int) worldStepAsync =
+      lib.lookupFunction<Int32 Function(H, Double, Int32), int Function(H, double, int)>('cannon_world_step_async');
+  late final int Function(H) ctxSync = lib.lookupFunction<Int32 Function(H), int Function(H)>('cannon_ctx_sync');
+  late final int Function(H, Pointer<CannonProfile>) worldProfile =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonProfile>), int Function(H, Pointer<CannonProfile>)>('cannon_world_profile');
+  late final int Function(H, Pointer<CannonContactsSoa>, Pointer<Int32>) worldGetContacts = lib.lookupFunction<
+      Int32 Function(H, Pointer<CannonContactsSoa>, Pointer<Int32>), int Function(H, Pointer<CannonContactsSoa>, Pointer<Int32>)>('cannon_world_get_contacts');
+  late final int Function(H, int) enableContactEvents =
+      lib.lookupFunction<Int32 Function(H, Int32), int Function(H, int)>('cannon_world_enable_contact_events');
+  late final int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>) getContactEvents =
+      lib.lookupFunction<Int32 Function(H, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>),
+          int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>)>(
+          'cannon_world_get_contact_events');
+  late final int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Double>, Pointer<Double>, Pointer<Double>, Pointer<Int32>) worldGetRows =
+      lib.lookupFunction<
+          Int32 Function(H, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Double>, Pointer<Double>, Pointer<Double>, Pointer<Int32>),
+          int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Int32>, Pointer<Double>, Pointer<Double>, Pointer<Double>, Pointer<Int32>)>(
+          'cannon_world_get_rows');
+
+  // user mutations between steps
+  late final int Function(H, int, int, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>) worldUpdateBodies =
+      lib.lookupFunction<Int32 Function(H, Int32, Int32, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>),
+          int Function(H, int, int, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>, Pointer<Float>)>(
+          'cannon_world_update_bodies');
+  late final int Function(H, int, int, Pointer<Float>) worldSetInvInertia =
+      lib.lookupFunction<Int32 Function(H, Int32, Int32, Pointer<Float>), int Function(H, int, int, Pointer<Float>)>('cannon_world_set_inv_inertia');
+  late final int Function(H, int, int, Pointer<Int32>) worldUpdateSleepStates =
+      lib.lookupFunction<Int32 Function(H, Int32, Int32, Pointer<Int32>), int Function(H, int, int, Pointer<Int32>)>('cannon_world_update_sleep_states');
+  late final int Function(H, int, int, double, double) worldSetHingeMotor =
+      lib.lookupFunction<Int32 Function(H, Int32, Int32, Double, Double), int Function(H, int, int, double, double)>('cannon_world_set_hinge_motor');
+
+  // batches of independent worlds over the GPUs of one box
+  late final int Function(Pointer<Int32>, int, Pointer<CannonWorldDesc>, int, int, Pointer<H>) batchCreate = lib.lookupFunction<
+      Int32 Function(Pointer<Int32>, Int32, Pointer<CannonWorldDesc>, Int32, Int32, Pointer<H>),
+      int Function(Pointer<Int32>, int, Pointer<CannonWorldDesc>, int, int, Pointer<H>)>('cannon_batch_create');
+  late final void Function(H) batchDestroy = lib.lookupFunction<Void Function(H), void Function(H)>('cannon_batch_destroy');
+  late final Pointer<Utf8> Function(H) batchLastError =
+      lib.lookupFunction<Pointer<Utf8> Function(H), Pointer<Utf8> Function(H)>('cannon_batch_last_error');
+  late final int Function(H, int, Pointer<Double>, Pointer<Double>, int, Pointer<CannonContactMaterial>) batchSetMaterials = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<Double>, Pointer<Double>, Int32, Pointer<CannonContactMaterial>),
+      int Function(H, int, Pointer<Double>, Pointer<Double>, int, Pointer<CannonContactMaterial>)>('cannon_batch_set_materials');
+  late final int Function(H, int, Pointer<CannonShapeDesc>) batchSetShapes =
+      lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonShapeDesc>), int Function(H, int, Pointer<CannonShapeDesc>)>('cannon_batch_set_shapes');
+  late final int Function(H, Pointer<CannonBodiesSoa>) batchSetBodies =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_batch_set_bodies');
+  late final int Function(H, int, Pointer<CannonConstraintDesc>) batchSetConstraints = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<CannonConstraintDesc>), int Function(H, int, Pointer<CannonConstraintDesc>)>('cannon_batch_set_constraints');
+  late final int Function(H, double, int) batchStep = lib.lookupFunction<Int32 Function(H, Double, Int32), int Function(H, double, int)>('cannon_batch_step');
+  late final int Function(H, Pointer<CannonBatchStatistics>) batchStats =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonBatchStatistics>), int Function(H, Pointer<CannonBatchStatistics>)>('cannon_batch_stats');
+  late final int Function(H, Pointer<CannonBodiesSoa>) batchGetBodies =
+      lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_batch_get_bodies');
+  late final int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<H>) batchShard = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<H>), int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<H>)>('cannon_batch_shard');
 }

@@ -328,6 +328,31 @@ def test_world_api_hinge_motor_setters_reach_a_live_world(oracle_lib):
     assert a._dev is dev and np.allclose(wa.angularVelocity, before, atol=1e-5)  # free spinning again
 
 
+def test_world_api_spring_constraint_is_a_bounded_distance_row(oracle_lib):
+    """SpringConstraint (spring_constraint.dart:7-56): rest length = the distance at construction, one bidirectional
+    equation with |force| <= stiffness. A stiff one holds a pendulum like a DistanceConstraint of that length; a soft one
+    (bound below the bob's weight) lets it sag."""
+    from cannon_physics_b200 import api
+
+    def run(make):
+        w = api.World(gravity=(0, -10, 0), _lib=oracle_lib)
+        anchor = api.Body(mass=0, shape=api.Sphere(0.1), position=(0, 5, 0))
+        bob = api.Body(mass=1, shape=api.Sphere(0.1), position=(0, 3, 0), linearDamping=0.0)
+        w.addBody(anchor)
+        w.addBody(bob)
+        w.addConstraint(make(anchor, bob))
+        for _ in range(60):
+            w.step(1 / 60)
+        return bob.position.copy()
+
+    stiff = run(lambda a, b: api.SpringConstraint(a, b, stiffness=1e6))
+    dist = run(lambda a, b: api.DistanceConstraint(a, b, 2.0, 1e6))
+    soft = run(lambda a, b: api.SpringConstraint(a, b, stiffness=0.05))
+    assert np.array_equal(stiff, dist) and abs(stiff[1] - 3.0) < 0.05
+    # the bound acts on the multiplier, an impulse per step (gs_solver.dart:88-98): 0.05 N s per 1/60 s = 3 N against a
+    # 10 N weight - the bob falls, only slowed down
+    assert soft[1] < 2.0
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm) needs no GPU: one JSON line with the
     same metric / unit / config keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e record.
