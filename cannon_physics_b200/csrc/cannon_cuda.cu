@@ -201,7 +201,7 @@ struct cannon_world {
   DBuf<float> rFlambda;
   int rowCap = 0;
   // device: solver units
-  DBuf<int> uBi, uBj, uFlags, uRows, uSrc, uKey, eBi, eBj, eFlags, eRowBase, eRows, unitRow;
+  DBuf<int> uBi, uBj, uFlags, uRows, uSrc, uKey, uPri, worldKeys, eBi, eBj, eFlags, eRowBase, eRows, unitRow;
   DBuf<double> eImA, eImB;
   int unitCap = 0;
   // device: joints
@@ -457,7 +457,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
-  REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(uKey); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
+  REL(uBi); REL(uBj); REL(uFlags); REL(uRows); REL(uSrc); REL(uKey); REL(uPri); REL(worldKeys); REL(eBi); REL(eBj); REL(eFlags); REL(eRowBase); REL(eRows); REL(unitRow);
   REL(eImA); REL(eImB); REL(jSlotEq); REL(rRec); REL(uRec); REL(rXblk); REL(gxWinRows); REL(gxWinBase); REL(uXrec); REL(unitSeq); REL(gxBody); REL(eLevel); REL(evKeysCur); REL(evKeysPrev); REL(evTabCur); REL(evTabPrev); REL(evBegin); REL(evEnd); REL(evCnt); REL(orderW); REL(worldCount); REL(lenBins); REL(worldUnitStart); REL(gsTab); REL(gsLvlTask); REL(gsLvlWin); REL(rFlambda);
   REL(jKind); REL(jEnabled); REL(jRowSlot); REL(jFirst); REL(jPivotA); REL(jPivotB); REL(jAxisA); REL(jAxisB); REL(jNi); REL(jMinF);
   REL(jMaxF); REL(jA); REL(jB); REL(jEps); REL(jTargetVel); REL(jCos); REL(jParam); REL(jMode); REL(claim); REL(unitLevel); REL(order); REL(levelStart); REL(act0); REL(act1);
@@ -757,7 +757,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   }
   const int unitCap = rowCap + 2;
   w->unitCap = unitCap;
-  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(uKey, unitCap); RES(eBi, unitCap); RES(eBj, unitCap);
+  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(uKey, unitCap); RES(uPri, unitCap); RES(worldKeys, 3 * (size_t)std::max(1, w->desc.n_worlds) + 1); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
   RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * ((size_t)w->desc.n_worlds * GR_LV + 4)); RES(worldUnitStart, (size_t)w->desc.n_worlds * GR_LV + 4);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
@@ -1297,7 +1297,7 @@ static RowArrays row_arrays(cannon_world* w) {
 static UnitArrays unit_arrays(cannon_world* w) {
   UnitArrays U;
   U.nUnits = w->cnt.p + CT_NUNITS; U.nExec = w->cnt.p + CT_NEXEC;
-  U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p; U.uKey = w->uKey.p;
+  U.uBi = w->uBi.p; U.uBj = w->uBj.p; U.uFlags = w->uFlags.p; U.uRows = w->uRows.p; U.uSrc = w->uSrc.p; U.uKey = w->uKey.p; U.uPri = w->uPri.p;
   U.eBi = w->eBi.p; U.eBj = w->eBj.p; U.eFlags = w->eFlags.p; U.eRowBase = w->eRowBase.p; U.eImA = w->eImA.p; U.eImB = w->eImB.p; U.rec = w->uRec.p; U.eLevel = w->eLevel.p;
   U.eRows = w->eRows.p; U.unitRow = w->unitRow.p; U.unitCap = w->unitCap;
   const bool packed = kind_packed(w);
@@ -1406,7 +1406,11 @@ static int32_t st_solve(cannon_world* w, double dt) {
   Us.colored = P.colored; Us.split = split ? 1 : 0; Us.fricFlag = w->fricFlag.p; Us.contFlag = w->contFlag.p; Us.fricOff = w->fricOff.p; Us.contOff = w->contOff.p;
   Us.fricTotal = cnt + CT_FRICTOTAL; Us.contTotal = cnt + CT_CONTTOTAL; Us.taskOff = w->taskOff.p; Us.taskCnt = w->taskCnt.p;
   Us.nTasks = cnt + CT_NTASKS; Us.taskCap = w->taskCap; Us.contactCap = w->contactCap;
-  { g_kernel_launches++; k_units_build<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, C, Us, J, U, nW, w->worldRows.p, cnt + CT_OVF_ROWS); }
+  if (P.colored && nW > 1) {  // world-local keys for the colouring of a batch
+    { g_kernel_launches++; k_world_keys_init<<<grid_for(w, 3 * nW, 256), 256, 0, s>>>(w->worldKeys.p, nW); }
+    { g_kernel_launches++; k_world_keys<<<grid_for(w, w->taskCap, 256), 256, 0, s>>>(B, C, Us, J, nW, w->worldKeys.p); }
+  }
+  { g_kernel_launches++; k_units_build<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, C, Us, J, U, nW, w->worldRows.p, cnt + CT_OVF_ROWS, w->worldKeys.p); }
   // dependency levels + sweeps: persistent cooperative kernels
   SchedArrays S;
   S.claim = w->claim.p; S.unitLevel = w->unitLevel.p; S.order = w->order.p; S.levelStart = w->levelStart.p; S.nLevels = cnt + CT_NLEVELS;

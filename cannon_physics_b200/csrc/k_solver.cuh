@@ -68,6 +68,7 @@ struct UnitArrays {
   int* nExec;        // device count of scheduled units (units without rows never enter the execution order)
   int *uBi, *uBj, *uFlags, *uRows, *uSrc;   // flags bit0/1: body i/j movable
   int* uKey;                                 // COLORED: canonical unit key (first contact index / nContacts + joint slot)
+  int* uPri;                                 // COLORED: the key counted inside the unit's world (== uKey for a single world): what the colouring hashes
   int *eBi, *eBj, *eFlags, *eRowBase;        // eRowBase has nUnits+1 entries (exclusive scan of rows in exec order)
   double *eImA, *eImB;                       // invMassSolve of the two bodies
   int* eRows;                                // rows per unit in exec order (scan input)
@@ -249,8 +250,8 @@ struct UnitSrc {  // what the units are made from
 };
 
 __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& B, int u, int bi, int bj, int rows, int src, int nWorlds,
-                                         int* __restrict__ worldRows, int key = 0) {
-  U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src; U.uKey[u] = key;
+                                         int* __restrict__ worldRows, int key = 0, int priKey = 0) {
+  U.uBi[u] = bi; U.uBj[u] = bj; U.uRows[u] = rows; U.uSrc[u] = src; U.uKey[u] = key; U.uPri[u] = priKey;
   U.uFlags[u] = rows > 0 ? ((body_movable(B, bi) ? 1 : 0) | (body_movable(B, bj) ? 2 : 0)) : 0;
   if (rows > 0) {
     // worldRows[w] > 0 <=> world w has equations this step: one plain store per (warp, world) instead of millions of
@@ -261,10 +262,31 @@ __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& 
   }
 }
 
+// COLORED batches: the colouring hashes a unit's key, and a world's colours must not depend on which other worlds share
+// the handle (a batch may be sharded over GPUs in any way). So the hashed key is counted inside the world:
+// contacts from the world's first ContactEquation, constraints from the world's contact count. wk[w] = first contact
+// index, wk[nW + w] = contacts, wk[2 nW + w] = first accepted joint slot of world w.
+__global__ void __launch_bounds__(256) k_world_keys_init(int* __restrict__ wk, int nWorlds) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * nWorlds; i += gridDim.x * blockDim.x) wk[i] = (i >= nWorlds && i < 2 * nWorlds) ? 0 : 0x7fffffff;
+}
+__global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, int nWorlds, int* __restrict__ wk) {
+  const int nc = min(*C.nContacts, S.contactCap);
+  const int nt = min(*S.nTasks, S.taskCap);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int t = tid; t < nt; t += nth) {
+    const int m = S.taskCnt[t], c0 = S.taskOff[t];
+    if (m <= 0 || c0 + m > nc) continue;
+    const int w = B.world[C.bi[c0]];
+    atomicMin(&wk[w], c0);
+    atomicAdd(&wk[nWorlds + w], m);
+  }
+  for (int s2 = tid; s2 < J.nAccepted; s2 += nth) atomicMin(&wk[2 * nWorlds + B.world[J.bodyA[J.slotEq[s2]]]], s2);
+}
+
 // unit table. Reference order: unit id == reference row index [2*fricRank | nF2 + contRank | joints].
 // Coloured: unit id == task id (manifold) followed by the joint rows.
 __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, UnitArrays U, int nWorlds,
-                                                     int* __restrict__ worldRows, int* __restrict__ unitOverflow) {
+                                                     int* __restrict__ worldRows, int* __restrict__ unitOverflow, const int* __restrict__ wk) {
   const int nc = min(*C.nContacts, S.contactCap);
   const int nF2 = 2 * (*S.fricTotal), nC = *S.contTotal;
   const int nt = min(*S.nTasks, S.taskCap);
@@ -284,7 +306,8 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
           for (int c = c0; c < c1; c++) rows += S.contFlag[c] + 2 * S.fricFlag[c];
         }
       }
-      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows, m > 0 ? S.taskOff[t] : 0);
+      const int key = m > 0 ? S.taskOff[t] : 0;
+      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows, key, (nWorlds > 1 && rows > 0) ? key - wk[B.world[bi]] : key);
     }
   } else if (S.split) {
     // unit id = position in descending creation-id order (split_solver.dart:108,167-169)
@@ -325,7 +348,9 @@ __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays
       const bool head = s == 0 || J.first[J.slotEq[s - 1]] != f;
       int rows = 0;
       if (head) { rows = 1; while (s + rows < J.nAccepted && J.first[J.slotEq[s + rows]] == f) rows++; }
-      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], rows, s * 8 + SRC_JOINTS, nWorlds, worldRows, nc + s);
+      int pk = nc + s;
+      if (nWorlds > 1) { const int w = B.world[J.bodyA[e]]; pk = wk[nWorlds + w] + (s - wk[2 * nWorlds + w]); }
+      put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], rows, s * 8 + SRC_JOINTS, nWorlds, worldRows, nc + s, pk);
     } else {
       put_unit(U, B, jointBase + s, J.bodyA[e], J.bodyB[e], 1, e * 8 + SRC_JOINT, nWorlds, worldRows);
     }
@@ -449,7 +474,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
     const unsigned long long hi = (unsigned long long)(0x7fffffffu - (unsigned)round) << 32;
     for (int a = tid; a < nAct; a += nth) {
       const int u = __ldcg(&act[a]);
-      const unsigned pri = colored ? (unsigned)U.uKey[u] * 2654435761u : (unsigned)u;
+      const unsigned pri = colored ? (unsigned)U.uPri[u] * 2654435761u : (unsigned)u;
       const unsigned long long key = hi | pri;
       const int fl = U.uFlags[u];
       if (fl & 1) atomicMin(&S.claim[U.uBi[u]], key);
@@ -464,7 +489,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
       bool win = false, emit = false;
       if (active) {
         u = __ldcg(&act[a]);
-        const unsigned pri = colored ? (unsigned)U.uKey[u] * 2654435761u : (unsigned)u;
+        const unsigned pri = colored ? (unsigned)U.uPri[u] * 2654435761u : (unsigned)u;
         const unsigned long long key = hi | pri;
         const int fl = U.uFlags[u];
         win = true;

@@ -65,7 +65,9 @@ enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
  *       f32-stored operands, no FMA, every Vector3 store rounds to float), different - but fully specified -
  *       row order: units = contact manifolds (the ContactEquations of one resolver call, rows [f1,f2,n] per
  *       contact) followed by one unit per constraint; unit key = index of its first ContactEquation in
- *       World.contacts (constraints: n_contacts + ordinal of its first accepted equation); priority =
+ *       World.contacts (constraints: n_contacts + ordinal of its first accepted equation), counted inside the
+ *       unit's world for a batch (n_worlds > 1: contacts from the world's first ContactEquation, constraints
+ *       from the world's contact count), so a world's result does not depend on the rest of the batch; priority =
  *       key * 2654435761 mod 2^32; colour(u) = round in which u holds the smallest pending priority on all of
  *       its movable bodies. Colours are swept in ascending order, units of a colour are independent. The oracle
  *       restates exactly this order sequentially, so COLORED is bit-exact against it; agreement

@@ -339,7 +339,17 @@ int World::solve(double h) {
     // Units = contact manifolds (the ContactEquations of one resolver call; rows [f1, f2, n] per contact) and one unit per
     // constraint; colour(u) = round in which u holds the smallest pending priority on all of its movable bodies; colours
     // ascend, units of a colour are independent (ordered by key here). Sequential GS over that list is the coloured sweep.
-    struct CUnit { int bi, bj, key, level; unsigned pri; std::vector<Eq*> eqs; };
+    // In a batch the hashed key is counted inside the unit's world (contacts from the world's first ContactEquation,
+    // constraints from the world's contact count), so a world's colours do not depend on the rest of the batch.
+    struct CUnit { int bi, bj, key, level; unsigned pri; std::vector<Eq*> eqs; int priKey; };
+    const int nWk = std::max(1, desc.n_worlds);
+    std::vector<int> wFirstC(nWk, 0x7fffffff), wCountC(nWk, 0), wFirstSlot(nWk, 0x7fffffff);
+    auto worldOf = [&](int b) { return nWk > 1 ? bodies[b].worldId : 0; };
+    for (size_t c = 0; c < contacts.size(); c++) {
+      const int wi = worldOf(contacts[c].bi);
+      wFirstC[wi] = std::min(wFirstC[wi], (int)c);
+      wCountC[wi]++;
+    }
     std::vector<CUnit> units;
     auto movable = [&](int b) {
       const Body& B = bodies[b];
@@ -353,7 +363,7 @@ int World::solve(double h) {
       for (size_t c = 0; c < contacts.size();) {
         size_t e = c;
         while (e < contacts.size() && contactManifold[e] == contactManifold[c]) e++;
-        CUnit u{contacts[c].bi, contacts[c].bj, (int)c, -1, 0u, {}};
+        CUnit u{contacts[c].bi, contacts[c].bj, (int)c, -1, 0u, {}, (int)c - (nWk > 1 ? wFirstC[worldOf(contacts[c].bi)] : 0)};
         for (size_t k = c; k < e; k++) {
           if (contacts[k].friction > 0) {
             if (accept(frictions[f])) { u.eqs.push_back(&frictions[f]); u.eqs.push_back(&frictions[f + 1]); }
@@ -366,10 +376,15 @@ int World::solve(double h) {
       }
       int slot = 0;
       for (Constraint& c : constraints) {
-        CUnit u{-1, -1, 0, -1, 0u, {}};
+        CUnit u{-1, -1, 0, -1, 0u, {}, 0};
         for (Eq& e : c.eqs)
           if (accept(e)) {
-            if (u.eqs.empty()) { u.bi = e.bi; u.bj = e.bj; u.key = (int)contacts.size() + slot; }
+            if (u.eqs.empty()) {
+              u.bi = e.bi; u.bj = e.bj; u.key = (int)contacts.size() + slot;
+              const int wi = worldOf(e.bi);
+              wFirstSlot[wi] = std::min(wFirstSlot[wi], slot);  // constraints are visited in slot order
+              u.priKey = nWk > 1 ? wCountC[wi] + (slot - wFirstSlot[wi]) : u.key;
+            }
             u.eqs.push_back(&e);
             slot++;
           }
@@ -380,7 +395,7 @@ int World::solve(double h) {
     {
       std::vector<unsigned> claim(bodies.size(), 0xffffffffu);
       std::vector<int> active(units.size()), next;
-      for (size_t k = 0; k < units.size(); k++) { active[k] = (int)k; units[k].pri = (unsigned)units[k].key * 2654435761u; }
+      for (size_t k = 0; k < units.size(); k++) { active[k] = (int)k; units[k].pri = (unsigned)units[k].priKey * 2654435761u; }
       while (!active.empty()) {
         for (int k : active) {
           const CUnit& u = units[k];

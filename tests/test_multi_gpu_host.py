@@ -58,24 +58,25 @@ def test_cannon_batch_abi_shards_from_one_thread(oracle_lib):
     constraints (global -> shard-local indices), stepping, gathered download, statistics. Per-world results must be
     bit-identical for every shard count, and equal to one cannon_world holding the whole batch."""
     from cannon_physics_b200 import _ffi as F, engine, scenes
-    spec = scenes.chain_worlds(7, chains=2, links=4)
-    whole = engine.DeviceWorld(oracle_lib, spec)
-    whole.step(1 / 60, 25)
     fields = ("position", "quaternion", "velocity", "angular_velocity", "sleep_state", "world_id")
-    ref = whole.get_bodies(fields)
-    for devices in ((0,), (0, 0), (0, 0, 0)):
-        b = engine.DeviceBatch(oracle_lib, spec, devices=devices)
-        b.step(1 / 60, 20)
-        b.step(1 / 60, 5)
-        got = b.get_bodies(fields)
-        for k in fields:
-            assert np.array_equal(got[k], ref[k]), (devices, k)
-        st = b.stats()
-        assert (st["n_gpus"], st["n_worlds"], st["steps"]) == (len(devices), 7, 25) and sum(st["gpu_worlds"]) == 7
-        assert st["n_contacts"] == whole.profile()["n_contacts"] and st["n_rows"] == whole.profile()["n_rows"]
-        first, n, h = b.shard(len(devices) - 1)
-        assert first + n == 7 and h.value
-        b.close()
+    for solver in (F.SOLVER_REFERENCE_ORDER, F.SOLVER_COLORED):  # COLORED hashes world-local unit keys: shard-independent too
+      spec = scenes.chain_worlds(7, chains=2, links=4, solver=solver)
+      whole = engine.DeviceWorld(oracle_lib, spec)
+      whole.step(1 / 60, 25)
+      ref = whole.get_bodies(fields)
+      for devices in ((0,), (0, 0), (0, 0, 0)):
+          b = engine.DeviceBatch(oracle_lib, spec, devices=devices)
+          b.step(1 / 60, 20)
+          b.step(1 / 60, 5)
+          got = b.get_bodies(fields)
+          for k in fields:
+              assert np.array_equal(got[k], ref[k]), (devices, k)
+          st = b.stats()
+          assert (st["n_gpus"], st["n_worlds"], st["steps"]) == (len(devices), 7, 25) and sum(st["gpu_worlds"]) == 7
+          assert st["n_contacts"] == whole.profile()["n_contacts"] and st["n_rows"] == whole.profile()["n_rows"]
+          first, n, h = b.shard(len(devices) - 1)
+          assert first + n == 7 and h.value
+          b.close()
     # a constraint across two worlds cannot be sharded
     bad = scenes.chain_worlds(2, chains=2, links=4)
     bad.constraints[0] = dict(bad.constraints[0], body_b=bad.n_bodies - 1)
