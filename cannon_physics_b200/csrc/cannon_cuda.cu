@@ -23,6 +23,7 @@
 #include "k_sat_warp.cuh"
 #include "k_solver.cuh"
 #include "k_gs_exact.cuh"
+#include "k_gs_world_exact.cuh"
 #include "world.cuh"
 
 // ---- device counters ---------------------------------------------------------------------------------
@@ -425,6 +426,7 @@ int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cann
   cudaFuncSetAttribute(k_gs_world, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_fast, GS_THREADS, GS_SMEM_BYTES);
   w->coopBlocksGsFast = ctx->sms * std::max(1, std::min(occ, 4));
+  cudaFuncSetAttribute(k_gs_world_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, GWX_SMEM_BYTES);
   cudaFuncSetAttribute(k_gs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gs_exact, GX_THREADS, GX_SMEM_BYTES);
   w->coopBlocksGx = ctx->sms * std::max(1, std::min(occ, 1));
@@ -1444,8 +1446,10 @@ static int32_t st_solve(cannon_world* w, double dt) {
   // on c4 — its phases are two dependent global loads long and only 15 worlds fit an SM — so it is not in the tree)
   const bool fast = kind_fast(w);
   const bool perWorld = fast && nW > 1 && !w->gsFastV1 && !getenv("CANNON_GS_NO_WORLD_KERNEL");
+  // exact COLORED batches: eight lanes per world (k_gs_world_exact) over the same (world, colour) grouping
+  const bool perWorldX = P.colored && !fast && !split && nW > 1 && !w->gxOff;
   const int* order = w->order.p;
-  if (perWorld) {
+  if (perWorld || perWorldX) {
     // (world, colour) bins: units - hence rows - of a world are contiguous colour by colour
     const int nBins = nW * GR_LV + 1;
     int* wc = w->worldCount.p;
@@ -1489,7 +1493,9 @@ static int32_t st_solve(cannon_world* w, double dt) {
     void* args[] = {&R, &B, &U, &S, &P, &G};
     void* argsT[] = {&R, &B, &U, &S, &T, &P, &G};
     g_kernel_launches++;
-    if (perWorld) {
+    if (perWorldX) {
+      k_gs_world_exact<<<nW, 32, GWX_SMEM_BYTES, s>>>(R, B, U, P, G, w->worldUnitStart.p, w->worldStart.p, cnt + CT_NLEVELS);
+    } else if (perWorld) {
       const int* wus = w->worldUnitStart.p;
       const int* wbs = w->worldStart.p;
       // small worlds (the RL / parameter-sweep case) take the warp-per-world ring kernel; if one world of the batch
