@@ -120,6 +120,19 @@ class Profile(C.Structure):
     ]
 
 
+RAY_CLOSEST, RAY_ANY, RAY_ALL = 1, 2, 4
+
+
+class RayOptions(C.Structure):
+    _fields_ = [("mode", c_i32), ("skip_backfaces", c_i32), ("collision_filter_mask", c_i32), ("collision_filter_group", c_i32),
+                ("check_collision_response", c_i32)]
+
+
+class RayHitsSoA(C.Structure):
+    _fields_ = [("capacity", c_i32), ("ray", P(c_i32)), ("body", P(c_i32)), ("hit_face_index", P(c_i32)), ("distance", P(c_f64)),
+                ("hit_point_world", P(c_f32)), ("hit_normal_world", P(c_f32))]
+
+
 BATCH_MAX_GPUS = 16
 
 
@@ -173,6 +186,9 @@ PROTOTYPES = {
     "cannon_world_set_stepnumber": (c_i32, [VP, c_i64]),
     "cannon_world_update_sleep_states": (c_i32, [VP, c_i32, c_i32, P(c_i32)]),
     "cannon_world_set_hinge_motor": (c_i32, [VP, c_i32, c_i32, c_f64, c_f64]),
+    "cannon_ray_options_default": (None, [P(RayOptions)]),
+    "cannon_world_raycast": (c_i32, [VP, c_i32, P(c_f32), P(c_f32), P(RayOptions), P(c_u8), P(RayHitsSoA), P(c_i32)]),
+    "cannon_world_aabb_query": (c_i32, [VP, P(c_f32), P(c_f32), P(c_i32), c_i32, P(c_i32)]),
     "cannon_batch_create": (c_i32, [P(c_i32), c_i32, P(WorldDesc), c_i32, c_i32, P(VP)]),
     "cannon_batch_destroy": (None, [VP]),
     "cannon_batch_last_error": (C.c_char_p, [VP]),

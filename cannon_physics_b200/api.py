@@ -445,6 +445,17 @@ class Spring:  # lib/objects/spring.dart:17
                     damping=float(self.damping), local_anchor_a=self.localAnchorA, local_anchor_b=self.localAnchorB)
 
 
+class RaycastResult:  # lib/collision/raycast_result.dart:6
+    def __init__(self):
+        self.rayFromWorld, self.rayToWorld, self.hitNormalWorld, self.hitPointWorld = Vec3(), Vec3(), Vec3(), Vec3()
+        self.reset()
+
+    def reset(self):
+        for v in (self.rayFromWorld, self.rayToWorld, self.hitNormalWorld, self.hitPointWorld):
+            v[:] = 0
+        self.hasHit, self.shape, self.body, self.hitFaceIndex, self.distance, self.shouldStop = False, None, None, -1, -1.0, False
+
+
 class World:  # lib/world/world_class.dart:44
     def __init__(self, gravity=None, frictionGravity=None, allowSleep: bool = False, broadphase: Optional[Broadphase] = None,
                  solver: Optional[Solver] = None, quatNormalizeFast: bool = False, quatNormalizeSkip: int = 0, device: int = 0, _lib=None):
@@ -726,6 +737,53 @@ class World:  # lib/world/world_class.dart:44
             body.force[:] = 0
             body.torque[:] = 0
         self._host_current = True
+
+    # ---- ray casts (world_class.dart:248-277) ------------------------------------------------------
+    def _raycast(self, mode, from_, to, options, result):
+        self._ensure_uploaded()
+        o = options or {}
+        r = self._dev.raycast([from_], [to], mode=mode, skip_backfaces=o.get("skipBackfaces", True),
+                              collision_filter_mask=o.get("collisionFilterMask", -1), collision_filter_group=o.get("collisionFilterGroup", -1),
+                              check_collision_response=o.get("checkCollisionResponse", True))
+        return r
+
+    def _fill(self, result: "RaycastResult", r, k, from_, to):
+        result.rayFromWorld[:], result.rayToWorld[:] = from_, to
+        result.hasHit = True
+        result.body = self.bodies[int(r["body"][k])]
+        result.shape = result.body.shapes[0]
+        result.hitFaceIndex, result.distance = int(r["hit_face_index"][k]), float(r["distance"][k])
+        result.hitPointWorld[:], result.hitNormalWorld[:] = r["hit_point_world"][k], r["hit_normal_world"][k]
+
+    def raycastClosest(self, from_, to, options=None, result: Optional["RaycastResult"] = None) -> bool:
+        result = result if result is not None else RaycastResult()
+        result.reset()
+        r = self._raycast(F.RAY_CLOSEST, from_, to, options, result)
+        if r["has_hit"][0]:
+            self._fill(result, r, 0, from_, to)
+        return bool(r["has_hit"][0])
+
+    def raycastAny(self, from_, to, options=None, result: Optional["RaycastResult"] = None) -> bool:
+        result = result if result is not None else RaycastResult()
+        result.reset()
+        r = self._raycast(F.RAY_ANY, from_, to, options, result)
+        if r["has_hit"][0]:
+            self._fill(result, r, 0, from_, to)
+        return bool(r["has_hit"][0])
+
+    def raycastAll(self, from_, to, options=None, callback=None) -> bool:
+        r = self._raycast(F.RAY_ALL, from_, to, options, None)
+        for k in range(r["n_hits"]):
+            res = RaycastResult()
+            self._fill(res, r, k, from_, to)
+            if callback is not None:
+                callback(res)
+        return bool(r["has_hit"][0])
+
+    def aabbQuery(self, lower, upper) -> List[Body]:
+        """Broadphase.aabbQuery(world, aabb) (naive_broadphase.dart:39-56): the bodies whose AABB overlaps [lower, upper]."""
+        self._ensure_uploaded()
+        return [self.bodies[int(i)] for i in self._dev.aabb_query(lower, upper)]
 
     @property
     def contacts(self):

@@ -24,6 +24,7 @@
 #include "k_solver.cuh"
 #include "k_gs_exact.cuh"
 #include "k_gs_world_exact.cuh"
+#include "k_raycast.cuh"
 #include "world.cuh"
 
 // ---- device counters ---------------------------------------------------------------------------------
@@ -2201,6 +2202,134 @@ int32_t cannon_world_set_hinge_motor(cannon_world* w, int32_t constraint, int32_
   W_TRY(w, upload(w->jEnabled, w->hJEnabled, s)); W_TRY(w, upload(w->jRowSlot, rowSlot, s)); W_TRY(w, upload(w->jSlotEq, slotEq, s));
   W_TRY(w, cudaStreamSynchronize(s));
   return ensure_capacities(w);
+}
+
+}  // extern "C"
+
+// ---- ray casts / AABB query ---------------------------------------------------------------
+extern "C" {
+
+void cannon_ray_options_default(cannon_ray_options* o) {
+  if (!o) return;
+  o->mode = CANNON_RAY_CLOSEST; o->skip_backfaces = 1; o->collision_filter_mask = -1; o->collision_filter_group = -1; o->check_collision_response = 1;
+}
+
+int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from, const float* to, const cannon_ray_options* opt, uint8_t* has_hit,
+                             cannon_ray_hits_soa* hits, int32_t* n_hits) {
+  if (!w || n_rays < 0 || !opt || !hits || !n_hits || (n_rays > 0 && (!from || !to))) return CANNON_E_INVALID;
+  if (opt->mode != CANNON_RAY_CLOSEST && opt->mode != CANNON_RAY_ANY && opt->mode != CANNON_RAY_ALL) return fail(w->ctx, CANNON_E_INVALID, "ray mode");
+  if (!w->hHfs.empty()) return fail(w->ctx, CANNON_E_UNSUPPORTED, "heightfield rays are outside the hot-path scope (SURVEY.md 8f)");
+  const bool all = opt->mode == CANNON_RAY_ALL;
+  if (!all && hits->capacity < n_rays) { *n_hits = n_rays; return fail(w->ctx, CANNON_E_CAPACITY, "hit arrays smaller than n_rays"); }
+  *n_hits = 0;
+  if (n_rays == 0) return CANNON_OK;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  const size_t n = (size_t)n_rays;
+  const int allCap = all ? std::max(hits->capacity, 1) : 1;
+  DBuf<float> dFrom, dTo;
+  DBuf<unsigned char> dHas;
+  DBuf<int> dBody, dFace, dCount, aRay, aBody, aFace;
+  DBuf<double> dDist, aDist;
+  DBuf<float4> dPoint, dNormal, aPoint, aNormal;
+  DBuf<unsigned long long> aKey;
+  int32_t rc = CANNON_OK;
+  auto done = [&](int32_t code) {
+    dFrom.release(); dTo.release(); dHas.release(); dBody.release(); dFace.release(); dCount.release(); aRay.release(); aBody.release(); aFace.release();
+    dDist.release(); aDist.release(); dPoint.release(); dNormal.release(); aPoint.release(); aNormal.release(); aKey.release();
+    return code;
+  };
+#define R_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(w->ctx, CANNON_E_CUDA, cudaGetErrorString(e_)); return done(CANNON_E_CUDA); } } while (0)
+  R_TRY(dFrom.reserve(3 * n)); R_TRY(dTo.reserve(3 * n)); R_TRY(dHas.reserve(n)); R_TRY(dBody.reserve(n)); R_TRY(dFace.reserve(n)); R_TRY(dCount.reserve(1));
+  R_TRY(dDist.reserve(n)); R_TRY(dPoint.reserve(n)); R_TRY(dNormal.reserve(n));
+  R_TRY(aRay.reserve(allCap)); R_TRY(aBody.reserve(allCap)); R_TRY(aFace.reserve(allCap)); R_TRY(aKey.reserve(allCap)); R_TRY(aDist.reserve(allCap));
+  R_TRY(aPoint.reserve(allCap)); R_TRY(aNormal.reserve(allCap));
+  R_TRY(cudaMemcpyAsync(dFrom.p, from, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  R_TRY(cudaMemcpyAsync(dTo.p, to, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  R_TRY(cudaMemsetAsync(dCount.p, 0, sizeof(int), s));
+  RayArgs A;
+  A.nRays = n_rays; A.nBodies = w->n; A.from = dFrom.p; A.to = dTo.p;
+  A.mode = opt->mode; A.skipBackfaces = opt->skip_backfaces; A.mask = opt->collision_filter_mask; A.group = opt->collision_filter_group;
+  A.checkCollisionResponse = opt->check_collision_response;
+  A.hasHit = dHas.p; A.body = dBody.p; A.face = dFace.p; A.dist = dDist.p; A.point = dPoint.p; A.normal = dNormal.p;
+  A.allCount = dCount.p; A.allCap = all ? hits->capacity : 0; A.allRay = aRay.p; A.allBody = aBody.p; A.allFace = aFace.p; A.allKey = aKey.p; A.allDist = aDist.p;
+  A.allPoint = aPoint.p; A.allNormal = aNormal.p;
+  { g_kernel_launches++; k_raycast<<<grid_for(w, 32LL * n_rays, 128), 128, 0, s>>>(body_arrays(w), shape_tables(w), A); }
+  R_TRY(cudaGetLastError());
+  std::vector<unsigned char> hHas(n);
+  std::vector<int> hBody(n), hFace(n);
+  std::vector<double> hDist(n);
+  std::vector<float4> hPoint(n), hNormal(n);
+  int count = 0;
+  R_TRY(cudaMemcpyAsync(hHas.data(), dHas.p, n, cudaMemcpyDeviceToHost, s));
+  R_TRY(cudaMemcpyAsync(&count, dCount.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (!all) {
+    R_TRY(cudaMemcpyAsync(hBody.data(), dBody.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    R_TRY(cudaMemcpyAsync(hFace.data(), dFace.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    R_TRY(cudaMemcpyAsync(hDist.data(), dDist.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    R_TRY(cudaMemcpyAsync(hPoint.data(), dPoint.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    R_TRY(cudaMemcpyAsync(hNormal.data(), dNormal.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  }
+  R_TRY(cudaStreamSynchronize(s));
+  if (has_hit) memcpy(has_hit, hHas.data(), n);
+  auto put = [&](int k, int ray, int body, int face, double dist, const float4& p, const float4& nn) {
+    if (hits->ray) hits->ray[k] = ray;
+    if (hits->body) hits->body[k] = body;
+    if (hits->hit_face_index) hits->hit_face_index[k] = face;
+    if (hits->distance) hits->distance[k] = dist;
+    if (hits->hit_point_world) { hits->hit_point_world[3 * k] = p.x; hits->hit_point_world[3 * k + 1] = p.y; hits->hit_point_world[3 * k + 2] = p.z; }
+    if (hits->hit_normal_world) { hits->hit_normal_world[3 * k] = nn.x; hits->hit_normal_world[3 * k + 1] = nn.y; hits->hit_normal_world[3 * k + 2] = nn.z; }
+  };
+  if (!all) {
+    int nh = 0;
+    for (int r = 0; r < n_rays; r++) { put(r, r, hBody[r], hFace[r], hDist[r], hPoint[r], hNormal[r]); nh += hHas[r] ? 1 : 0; }
+    *n_hits = nh;
+  } else {
+    *n_hits = count;
+    if (count > hits->capacity) { fail(w->ctx, CANNON_E_CAPACITY, "hit arrays too small"); return done(CANNON_E_CAPACITY); }
+    const size_t m = (size_t)count;
+    std::vector<int> r(m), bd(m), fc(m);
+    std::vector<unsigned long long> key(m);
+    std::vector<double> ds(m);
+    std::vector<float4> pt(m), nm(m);
+    if (m) {
+      R_TRY(cudaMemcpy(r.data(), aRay.p, m * sizeof(int), cudaMemcpyDeviceToHost)); R_TRY(cudaMemcpy(bd.data(), aBody.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+      R_TRY(cudaMemcpy(fc.data(), aFace.p, m * sizeof(int), cudaMemcpyDeviceToHost)); R_TRY(cudaMemcpy(key.data(), aKey.p, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      R_TRY(cudaMemcpy(ds.data(), aDist.p, m * sizeof(double), cudaMemcpyDeviceToHost)); R_TRY(cudaMemcpy(pt.data(), aPoint.p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+      R_TRY(cudaMemcpy(nm.data(), aNormal.p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int> ord(m);
+    for (size_t k = 0; k < m; k++) ord[k] = (int)k;
+    // the reference's callback sequence: ray by ray, bodies ascending, reports of a body in the order they were made
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return r[a] != r[b] ? r[a] < r[b] : key[a] < key[b]; });
+    for (size_t k = 0; k < m; k++) { const int i = ord[k]; put((int)k, r[i], bd[i], fc[i], ds[i], pt[i], nm[i]); }
+  }
+#undef R_TRY
+  return done(rc);
+}
+
+int32_t cannon_world_aabb_query(cannon_world* w, const float* lower, const float* upper, int32_t* bodies, int32_t cap, int32_t* n) {
+  if (!w || !lower || !upper || !n || cap < 0 || (cap > 0 && !bodies)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  *n = 0;
+  if (w->n == 0) return CANNON_OK;
+  DBuf<int> flag;
+  if (flag.reserve(w->n) != cudaSuccess) return fail(w->ctx, CANNON_E_CUDA, "cudaMalloc failed");
+  f3 lo, hi;
+  lo.x = lower[0]; lo.y = lower[1]; lo.z = lower[2]; hi.x = upper[0]; hi.y = upper[1]; hi.z = upper[2];
+  { g_kernel_launches++; k_aabb_query<<<grid_for(w, w->n, 256), 256, 0, s>>>(body_arrays(w), shape_tables(w), w->n, lo, hi, flag.p); }
+  std::vector<int> h(w->n);
+  cudaError_t e = cudaMemcpyAsync(h.data(), flag.p, (size_t)w->n * sizeof(int), cudaMemcpyDeviceToHost, s);  // the ctx stream does not
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);                                                              // synchronise with the legacy stream
+  flag.release();
+  if (e != cudaSuccess) return fail(w->ctx, CANNON_E_CUDA, cudaGetErrorString(e));
+  int cnt = 0;
+  for (int b = 0; b < w->n; b++) if (h[b]) { if (cnt < cap) bodies[cnt] = b; cnt++; }
+  *n = cnt;
+  return cnt > cap ? fail(w->ctx, CANNON_E_CAPACITY, "body array too small") : CANNON_OK;
 }
 
 }  // extern "C"

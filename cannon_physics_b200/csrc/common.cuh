@@ -66,7 +66,7 @@ static long long g_kernel_launches = 0;
 // exclusive scan of int32 (n read from device memory so the whole step stays asynchronous)
 // ---------------------------------------------------------------------------------------------------
 #define SCAN_THREADS 512
-#define SCAN_ITEMS 8
+#define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
@@ -108,6 +108,7 @@ struct ScanTmp {
 // tiles before it are known; a tile only ever waits for tiles with a smaller ticket, and tickets are handed out in start
 // order, so the wait always ends. One read and one write of the data, one launch (+ one memset of the tile states) instead
 // of the three launches of the tile-sums / scan-of-sums / apply form - the step runs ~9 scans, this was 28 of its 73 launches.
+#define SCAN_RESIDENT_BLOCKS 148  // one 512-thread block per SM is always resident on a B200
 #define SCAN_FLAG_A 1ull  // aggregate of the tile
 #define SCAN_FLAG_P 2ull  // inclusive prefix up to and including the tile
 __device__ __forceinline__ void scan_publish(unsigned long long* p, unsigned long long flag, int v) {
@@ -123,7 +124,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(const int* __rest
                                                                unsigned long long* __restrict__ state, int* __restrict__ ticket,
                                                                int* __restrict__ total_out) {
   __shared__ int s_tile, s_prefix;
-  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  // tiles in start order: the block index when the whole grid is resident anyway (every block runs from the start, no block
+  // can wait for one that has not been scheduled), a ticket otherwise
+  if (gridDim.x <= SCAN_RESIDENT_BLOCKS) {
+    if (threadIdx.x == 0) s_tile = blockIdx.x;
+  } else if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
   __syncthreads();
   const int tile = s_tile;
   const int n = n_ptr ? *n_ptr : n_fixed;

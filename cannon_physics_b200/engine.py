@@ -244,6 +244,46 @@ class DeviceWorld:
     def set_hinge_motor(self, constraint: int, enabled: bool, target_velocity: float, max_force: float):
         self._chk(self.lib.cannon_world_set_hinge_motor(self.handle, constraint, int(enabled), float(target_velocity), float(max_force)))
 
+    # ---- ray casts / AABB query ----------------------------------------------
+    def raycast(self, from_, to, mode: int = F.RAY_CLOSEST, skip_backfaces: bool = True, collision_filter_mask: int = -1,
+                collision_filter_group: int = -1, check_collision_response: bool = True) -> Dict[str, np.ndarray]:
+        """World.raycastClosest / raycastAny / raycastAll for a batch of rays (from_, to: (n, 3) float32). Returns has_hit (n)
+        and the hit arrays: one RaycastResult per ray for CLOSEST / ANY, the callback sequence (with `ray`) for ALL."""
+        a = np.ascontiguousarray(from_, dtype=np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(to, dtype=np.float32).reshape(-1, 3)
+        n = len(a)
+        opt = F.RayOptions()
+        self.lib.cannon_ray_options_default(C.byref(opt))
+        opt.mode, opt.skip_backfaces, opt.collision_filter_mask = mode, int(skip_backfaces), collision_filter_mask
+        opt.collision_filter_group, opt.check_collision_response = collision_filter_group, int(check_collision_response)
+        has = np.zeros(n, np.uint8)
+        cap = max(n, 1) if mode != F.RAY_ALL else max(4 * n, 64)
+        while True:
+            out = dict(ray=np.zeros(cap, np.int32), body=np.zeros(cap, np.int32), hit_face_index=np.zeros(cap, np.int32), distance=np.zeros(cap),
+                       hit_point_world=np.zeros((cap, 3), np.float32), hit_normal_world=np.zeros((cap, 3), np.float32))
+            soa = F.RayHitsSoA(capacity=cap, ray=F.ptr(out["ray"], F.c_i32), body=F.ptr(out["body"], F.c_i32),
+                               hit_face_index=F.ptr(out["hit_face_index"], F.c_i32), distance=F.ptr(out["distance"], F.c_f64),
+                               hit_point_world=F.ptr(out["hit_point_world"], F.c_f32), hit_normal_world=F.ptr(out["hit_normal_world"], F.c_f32))
+            nh = F.c_i32()
+            code = self.lib.cannon_world_raycast(self.handle, n, F.ptr(a, F.c_f32), F.ptr(b, F.c_f32), C.byref(opt), F.ptr(has, F.c_u8), C.byref(soa), C.byref(nh))
+            if code == F.E_CAPACITY and nh.value > cap:
+                cap = nh.value
+                continue
+            self._chk(code)
+            k = nh.value if mode == F.RAY_ALL else n
+            res = {name: arr[:k] for name, arr in out.items()}
+            res["has_hit"] = has.astype(bool)
+            res["n_hits"] = nh.value
+            return res
+
+    def aabb_query(self, lower, upper) -> np.ndarray:
+        lo, hi = np.ascontiguousarray(lower, dtype=np.float32), np.ascontiguousarray(upper, dtype=np.float32)
+        cap = max(self.n, 1)
+        out = np.zeros(cap, np.int32)
+        n = F.c_i32()
+        self._chk(self.lib.cannon_world_aabb_query(self.handle, F.ptr(lo, F.c_f32), F.ptr(hi, F.c_f32), F.ptr(out, F.c_i32), cap, C.byref(n)))
+        return out[: n.value].copy()
+
     # ---- downloads -----------------------------------------------------------------------------
     def get_bodies(self, fields: Sequence[str] = ("position", "quaternion", "velocity", "angular_velocity"),
                    out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:

@@ -16,6 +16,7 @@ const bpNaive = 0, bpSap = 1, bpGrid = 2;
 const solverReferenceOrder = 0, solverColored = 1, solverSplit = 2, solverColoredF32 = 3;
 const constraintPointToPoint = 0, constraintHinge = 1, constraintDistance = 2, constraintLock = 3, constraintConeTwist = 4;
 const cannonBatchMaxGpus = 16;
+const rayClosest = 1, rayAny = 2, rayAll = 4; // RayMode
 
 // ---- structs ---------------------------------------------------------------------------------------------------------
 final class CannonContactMaterial extends Struct {
@@ -180,6 +181,24 @@ final class CannonProfile extends Struct {
   @Double() external double sumGs;
 }
 
+final class CannonRayOptions extends Struct {
+  @Int32() external int mode;
+  @Int32() external int skipBackfaces;
+  @Int32() external int collisionFilterMask;
+  @Int32() external int collisionFilterGroup;
+  @Int32() external int checkCollisionResponse;
+}
+
+final class CannonRayHitsSoa extends Struct {
+  @Int32() external int capacity;
+  external Pointer<Int32> ray;
+  external Pointer<Int32> body;
+  external Pointer<Int32> hitFaceIndex;
+  external Pointer<Double> distance;
+  external Pointer<Float> hitPointWorld;
+  external Pointer<Float> hitNormalWorld;
+}
+
 final class CannonBatchStatistics extends Struct {
   @Int32() external int nGpus;
   @Int32() external int nWorlds;
@@ -284,6 +303,18 @@ class CannonCuda {
       lib.lookupFunction<Int32 Function(H, Int32, Int32, Pointer<Int32>), int Function(H, int, int, Pointer<Int32>)>('cannon_world_update_sleep_states');
   late final int Function(H, int, int, double, double) worldSetHingeMotor =
       lib.lookupFunction<Int32 Function(H, Int32, Int32, Double, Double), int Function(H, int, int, double, double)>('cannon_world_set_hinge_motor');
+
+  // ray casts and AABB queries
+  late final void Function(Pointer<CannonRayOptions>) rayOptionsDefault =
+      lib.lookupFunction<Void Function(Pointer<CannonRayOptions>), void Function(Pointer<CannonRayOptions>)>('cannon_ray_options_default');
+  late final int Function(H, int, Pointer<Float>, Pointer<Float>, Pointer<CannonRayOptions>, Pointer<Uint8>, Pointer<CannonRayHitsSoa>, Pointer<Int32>) worldRaycast =
+      lib.lookupFunction<
+          Int32 Function(H, Int32, Pointer<Float>, Pointer<Float>, Pointer<CannonRayOptions>, Pointer<Uint8>, Pointer<CannonRayHitsSoa>, Pointer<Int32>),
+          int Function(H, int, Pointer<Float>, Pointer<Float>, Pointer<CannonRayOptions>, Pointer<Uint8>, Pointer<CannonRayHitsSoa>, Pointer<Int32>)>(
+          'cannon_world_raycast');
+  late final int Function(H, Pointer<Float>, Pointer<Float>, Pointer<Int32>, int, Pointer<Int32>) worldAabbQuery = lib.lookupFunction<
+      Int32 Function(H, Pointer<Float>, Pointer<Float>, Pointer<Int32>, Int32, Pointer<Int32>),
+      int Function(H, Pointer<Float>, Pointer<Float>, Pointer<Int32>, int, Pointer<Int32>)>('cannon_world_aabb_query');
 
   // batches of independent worlds over the GPUs of one box
   late final int Function(Pointer<Int32>, int, Pointer<CannonWorldDesc>, int, int, Pointer<H>) batchCreate = lib.lookupFunction<

@@ -297,6 +297,41 @@ class CudaWorld extends World {
     if (hasAnyEventListener('beginContact') || hasAnyEventListener('endContact')) _emitContactEvents();
   }
 
+  /// World.raycastClosest (world_class.dart:269-277) against the device-resident poses.
+  @override
+  bool raycastClosest([Vector3? from, Vector3? to, RayOptions? options, RaycastResult? result]) {
+    session.ensureUploaded(solverKind: solverKind);
+    if (hostDirty) { session.pushState(); hostDirty = false; }
+    final f = from ?? Vector3.zero(), t = to ?? Vector3.zero();
+    return using((Arena a) {
+      final pf = a<Float>(3), pt = a<Float>(3);
+      for (var k = 0; k < 3; k++) { pf[k] = f[k]; pt[k] = t[k]; }
+      final opt = a<CannonRayOptions>();
+      cuda.rayOptionsDefault(opt);
+      opt.ref.mode = rayClosest;
+      opt.ref.skipBackfaces = (options?.skipBackfaces ?? true) ? 1 : 0;
+      opt.ref.collisionFilterMask = options?.collisionFilterMask ?? -1;
+      opt.ref.collisionFilterGroup = options?.collisionFilterGroup ?? -1;
+      opt.ref.checkCollisionResponse = (options?.checkCollisionResponse ?? true) ? 1 : 0;
+      final hits = a<CannonRayHitsSoa>();
+      hits.ref.capacity = 1;
+      hits.ref.ray = a<Int32>(); hits.ref.body = a<Int32>(); hits.ref.hitFaceIndex = a<Int32>(); hits.ref.distance = a<Double>();
+      hits.ref.hitPointWorld = a<Float>(3); hits.ref.hitNormalWorld = a<Float>(3);
+      final has = a<Uint8>(), n = a<Int32>();
+      session.check(cuda.worldRaycast(session.handle, 1, pf, pt, opt, has, hits, n), 'cannon_world_raycast');
+      final r = result ?? RaycastResult();
+      r.reset();
+      if (has.value != 0) {
+        final b = bodies[hits.ref.body.value];
+        final hp = hits.ref.hitPointWorld, hn = hits.ref.hitNormalWorld;
+        r.set(f, t, Vector3(hn[0], hn[1], hn[2]), Vector3(hp[0], hp[1], hp[2]), b.shapes[0], b, hits.ref.distance.value);
+        r.hasHit = true;
+        r.hitFaceIndex = hits.ref.hitFaceIndex.value;
+      }
+      return has.value != 0;
+    });
+  }
+
   // World.emitContactEvents (world_class.dart:703-730) from the device-side pair-set difference instead of OverlapKeeper
   void _emitContactEvents() {
     if (!_eventsOn) { session.check(cuda.enableContactEvents(session.handle, 1), 'cannon_world_enable_contact_events'); _eventsOn = true; return; }

@@ -347,6 +347,45 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
                                    const float* quaternion, const float* velocity, const float* angular_velocity,
                                    const float* force, const float* torque);
 
+/* ---- ray casts and AABB queries ----
+ * World.raycastClosest / raycastAny / raycastAll (lib/world/world_class.dart:248-277) = Ray.intersectWorld
+ * (lib/collision/ray_class.dart:175-199) for n_rays rays at once against the bodies' CURRENT poses: the ray's AABB against
+ * every body's AABB (NaiveBroadphase.aabbQuery, naive_broadphase.dart:39-56), the collision filters of Ray.intersectBody
+ * (:201-225), the bounding-sphere rejection of _intersectShape (:270-283), then _intersectSphere / _intersectPlane /
+ * _intersectBox / _intersectConvex (:285-326,411-553) in the reference's arithmetic.
+ *   CLOSEST / ANY: entry r of the hit arrays is ray r's RaycastResult (body -1 and distance -1 without a hit; hit_face_index
+ *     is the face of the LAST reported intersection in CLOSEST mode, as ray_class.dart:664 writes it before looking at the
+ *     mode); *n_hits = rays that hit; capacity >= n_rays.
+ *   ALL: the hit arrays receive the callback sequence of ray 0, then ray 1, ... (`ray` tells which); *n_hits = their number;
+ *     CANNON_E_CAPACITY reports the needed capacity through *n_hits.
+ * has_hit (n_rays entries, may be NULL) is intersectWorld's return value per ray.
+ * Candidates are visited in body-index order for every broadphase kind (SAPBroadphase.aabbQuery would walk its axis list,
+ * GridBroadphase has none: broadphase.dart:151-154) - it decides ties between equidistant hits and the sequence of ALL.
+ * Worlds with a Heightfield shape are refused (CANNON_E_UNSUPPORTED; ray_class.dart:344-409 is outside the scope). */
+enum { CANNON_RAY_CLOSEST = 1, CANNON_RAY_ANY = 2, CANNON_RAY_ALL = 4 };  /* RayMode, ray_class.dart:9-21 */
+typedef struct cannon_ray_options {
+  int32_t mode;                     /* CANNON_RAY_* */
+  int32_t skip_backfaces;           /* 1: RayOptions.skipBackfaces ?? true (ray_class.dart:178) */
+  int32_t collision_filter_mask;    /* -1 */
+  int32_t collision_filter_group;   /* -1 */
+  int32_t check_collision_response; /* 1 */
+} cannon_ray_options;
+typedef struct cannon_ray_hits_soa {
+  int32_t  capacity;
+  int32_t* ray;               /* ALL: index of the ray; CLOSEST / ANY: r */
+  int32_t* body;              /* RaycastResult.body (index) or -1 */
+  int32_t* hit_face_index;    /* RaycastResult.hitFaceIndex */
+  double*  distance;          /* RaycastResult.distance */
+  float*   hit_point_world;   /* 3 per entry */
+  float*   hit_normal_world;  /* 3 per entry */
+} cannon_ray_hits_soa;
+void    cannon_ray_options_default(cannon_ray_options* o);
+int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from, const float* to, const cannon_ray_options* opt,
+                             uint8_t* has_hit, cannon_ray_hits_soa* hits, int32_t* n_hits);
+/* Broadphase.aabbQuery (naive_broadphase.dart:39-56): indices of the bodies whose current AABB overlaps [lower, upper],
+ * ascending; CANNON_E_CAPACITY reports the needed size through *n. */
+int32_t cannon_world_aabb_query(cannon_world* w, const float* lower, const float* upper, int32_t* bodies, int32_t cap, int32_t* n);
+
 /* ---- batches of independent worlds over the GPUs of one box ----
  * n_worlds worlds of bodies_per_world bodies each (config 4: the RL / parameter-sweep case; the reference equivalent is a
  * Dart program holding n_worlds World objects and calling World.step on each, lib/world/world_class.dart:392-431).

@@ -640,5 +640,59 @@ int32_t cannon_world_get_rows(cannon_world* cw, int32_t cap, int32_t* n_rows, in
 
 }  // extern "C"
 
+extern "C" {
+
+void cannon_ray_options_default(cannon_ray_options* o) {
+  if (!o) return;
+  o->mode = CANNON_RAY_CLOSEST; o->skip_backfaces = 1; o->collision_filter_mask = -1; o->collision_filter_group = -1; o->check_collision_response = 1;
+}
+
+int32_t cannon_world_raycast(cannon_world* cw, int32_t n_rays, const float* from, const float* to, const cannon_ray_options* opt, uint8_t* has_hit,
+                             cannon_ray_hits_soa* hits, int32_t* n_hits) {
+  if (!cw || n_rays < 0 || !opt || !hits || !n_hits || (n_rays > 0 && (!from || !to))) return CANNON_E_INVALID;
+  if (opt->mode != CANNON_RAY_CLOSEST && opt->mode != CANNON_RAY_ANY && opt->mode != CANNON_RAY_ALL) return fail(cw->ctx, CANNON_E_INVALID, "ray mode");
+  World& w = cw->w;
+  for (const Shape& s : w.shapes)
+    if (s.type == CANNON_SHAPE_HEIGHTFIELD) return fail(cw->ctx, CANNON_E_UNSUPPORTED, "heightfield rays are outside the hot-path scope (SURVEY.md 8f)");
+  const bool all = opt->mode == CANNON_RAY_ALL;
+  if (!all && hits->capacity < n_rays) { *n_hits = n_rays; return fail(cw->ctx, CANNON_E_CAPACITY, "hit arrays smaller than n_rays"); }
+  std::vector<RayHit> seq;
+  int count = 0;
+  auto put = [&](int k, const RayHit& h) {
+    if (hits->ray) hits->ray[k] = h.ray;
+    if (hits->body) hits->body[k] = h.body;
+    if (hits->hit_face_index) hits->hit_face_index[k] = h.hitFaceIndex;
+    if (hits->distance) hits->distance[k] = h.distance;
+    if (hits->hit_point_world) PUTF3(hits->hit_point_world, k, h.hitPointWorld);
+    if (hits->hit_normal_world) PUTF3(hits->hit_normal_world, k, h.hitNormalWorld);
+  };
+  for (int r = 0; r < n_rays; r++) {
+    RayHit res;
+    const bool hit = w.raycast(r, V3{from[3 * r], from[3 * r + 1], from[3 * r + 2]}, V3{to[3 * r], to[3 * r + 1], to[3 * r + 2]}, *opt, res, all ? &seq : nullptr);
+    if (has_hit) has_hit[r] = hit ? 1 : 0;
+    if (!all) { put(r, res); count += hit ? 1 : 0; }
+  }
+  if (all) {
+    *n_hits = (int)seq.size();
+    if ((int)seq.size() > hits->capacity) return fail(cw->ctx, CANNON_E_CAPACITY, "hit arrays too small");
+    for (size_t k = 0; k < seq.size(); k++) put((int)k, seq[k]);
+  } else {
+    *n_hits = count;
+  }
+  return CANNON_OK;
+}
+
+int32_t cannon_world_aabb_query(cannon_world* cw, const float* lower, const float* upper, int32_t* bodies, int32_t cap, int32_t* n) {
+  if (!cw || !lower || !upper || !n || cap < 0 || (cap > 0 && !bodies)) return CANNON_E_INVALID;
+  std::vector<int> res;
+  cw->w.aabbQuery(V3{lower[0], lower[1], lower[2]}, V3{upper[0], upper[1], upper[2]}, res);
+  *n = (int)res.size();
+  if ((int)res.size() > cap) return fail(cw->ctx, CANNON_E_CAPACITY, "body array too small");
+  for (size_t k = 0; k < res.size(); k++) bodies[k] = res[k];
+  return CANNON_OK;
+}
+
+}  // extern "C"
+
 // cannon_batch_*: host glue over the entry points above, shared by both libraries
 #include "../cannon_physics_b200/csrc/batch_impl.inc"

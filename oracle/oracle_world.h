@@ -109,6 +109,12 @@ struct Spring {  // lib/objects/spring.dart
   V3 localAnchorA{0, 0, 0}, localAnchorB{0, 0, 0};
 };
 
+struct RayHit {  // one reported intersection (RaycastResult, lib/collision/raycast_result.dart)
+  int ray, body, hitFaceIndex;
+  double distance;
+  V3 hitPointWorld, hitNormalWorld;
+};
+
 struct RowDebug {
   int bi, bj;
   double B, invC, lambda;
@@ -150,6 +156,8 @@ struct World {
   void updateInertiaWorld(Body& b, bool force) const;
   void updateBoundingRadius(Body& b) const;
 
+  void aabbQuery(const V3& lower, const V3& upper, std::vector<int>& result);  // NaiveBroadphase.aabbQuery
+  bool raycast(int rayIndex, const V3& from, const V3& to, const cannon_ray_options& opt, RayHit& out, std::vector<RayHit>* all);
   void collisionPairs();            // broadphase + constraint-pair filter
   void getContacts();               // narrowphase over p1/p2
   void makeContactConstraints();    // restitution override + wake-up flags
