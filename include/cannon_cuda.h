@@ -361,7 +361,10 @@ int32_t cannon_world_update_bodies(cannon_world* w, int32_t first, int32_t count
  * has_hit (n_rays entries, may be NULL) is intersectWorld's return value per ray.
  * Candidates are visited in body-index order for every broadphase kind (SAPBroadphase.aabbQuery would walk its axis list,
  * GridBroadphase has none: broadphase.dart:151-154) - it decides ties between equidistant hits and the sequence of ALL.
- * Worlds with a Heightfield shape are refused (CANNON_E_UNSUPPORTED; ray_class.dart:344-409 is outside the scope). */
+ * Worlds with a Heightfield shape are refused (CANNON_E_UNSUPPORTED). The reference's own _intersectHeightfield
+ * (ray_class.dart:344-409) takes its cell range from a list that Heightfield.getIndexOfPosition only ever appends to
+ * (heightfield.dart:173: `result.addAll([xi, yi])`, read back as index[0] / index[1] at ray_class.dart:367-372), i.e. from the
+ * FIRST heightfield ray a Ray object ever cast - there is no history-free behaviour to reproduce. */
 enum { CANNON_RAY_CLOSEST = 1, CANNON_RAY_ANY = 2, CANNON_RAY_ALL = 4 };  /* RayMode, ray_class.dart:9-21 */
 typedef struct cannon_ray_options {
   int32_t mode;                     /* CANNON_RAY_* */

@@ -10,7 +10,8 @@
  * Candidate order: body index order (NaiveBroadphase.aabbQuery). SAPBroadphase.aabbQuery walks its axis list instead and
  * GridBroadphase has no aabbQuery at all (Broadphase.aabbQuery returns [] with a log line, broadphase.dart:151-154): both
  * are served with Naive's order here - a documented choice shared with the CUDA library.
- * Heightfield and trimesh rays (ray_class.dart:344-409,555-653) are outside the scope.
+ * Heightfield rays are refused: the reference reads their cell range from a list getIndexOfPosition only appends to
+ * (heightfield.dart:173, ray_class.dart:367-372), so its answer depends on the first ray ever cast. Trimesh is out of scope.
  */
 #include <algorithm>
 

@@ -65,7 +65,44 @@ scale2 = ("Multi-GPU checks (`gpurun --gpus N`, one process per GPU, no collecti
           "(colouring 0.12, ring sweep 0.28 = the serial chain of one world: 10 iterations × ≈ 14 colour segments × ≈ 2 µs).") if sc else ""
 c4 = [t for t, sv in zip(tab, solvers) if sv.startswith("colored (ring")][0]
 c5 = tab[-1]
+# ---- round 2 -----------------------------------------------------------------------------------------------------------
+b2, ref2 = load("r02_bench_c3.json"), load("r02_bench_c3_reference.json")
+rf2, e2, cp2, st2, ls2 = b2["roofline"], b2["e2e"], b2["cpu_baseline"], b2["stage_ms"], b2["last_step"]
+tr2 = json.load(open(os.path.join(HERE, "r02_ncu_traffic.json")))["k_gs_exact"]
+r02 = [f"""| quantity | value |
+|---|---|
+| driver command `python bench.py --gpus 1 --steps 20 --warmup 5`, settled pile (start state `bench_data/c3_settled.npz`) | {b2['steps_per_s']:.1f} steps/s, {b2['ms_per_step']:.3f} ms per step |
+| body-steps/s (`value`, device time) / through the C ABI with host buffers (`e2e`) | {sci(b2['value'])} / {sci(e2['value'])} |
+| contact-iters/s | {sci(b2['contact_iters_per_s'])} |
+| last step: pairs / contacts / rows / colours / iterations | {ls2['pairs']} / {ls2['contacts']} / {ls2['rows']} / {ls2['levels']} / {ls2['iterations']} |
+| stage times, ms (eager pass, CUDA events): broadphase / narrowphase / solve (colouring, sweep) / integrate | {st2['broadphase']:.3f} / {st2['narrowphase']:.3f} / {st2['solve']:.3f} ({st2['schedule']:.3f}, {st2['gs']:.3f}) / {st2['integrate']:.3f} |
+| kernels launched per step | {b2['gpu_launches'] // b2['steps']} (one CUDA-graph replay; 76 before the single-pass scan) |
+| reference arm (`--impl reference`: the oracle in reference order on the SAME 100 001-body settled state, 1 core) | {ref2['ms_per_step'] / 1e3:.2f} s per step, {sci(ref2['value'])} body-steps/s |
+| `cpu_baseline` inside the product line (oracle in the colour order, {cp2['sample'].split(' oracle')[0]} steps) | {sci(cp2['value'])} body-steps/s |
+| e2e ratio product / reference arm | {e2['value'] / ref2['value']:.0f} x |
+| arithmetic of the timed sweep | f64 on f32-stored vectors, no FMA: bit-exact against the oracle (`dtype: "{b2['dtype']}"`) |""",
+       f"""Roofline of `k_gs_exact` (one launch = {ls2['iterations']} iterations x {ls2['levels']} colours): algorithmic bytes (SURVEY 8d: 408 B x contact-iterations) =
+{rf2['algorithmic_bytes_per_launch'] / 1e9:.3f} GB in {rf2['launch_ms']:.3f} ms (CUDA events, eager pass of the same run) = **{rf2['achieved'] / 1e3:.2f} TB/s = {rf2['frac']:.3f} of the measured
+{rf2['peak']:.0f} GB/s**. ncu (`r02_k_gs_exact.md`): DRAM traffic {tr2['dram_bytes'] / 1e9:.3f} GB per launch in {tr2['seconds'] * 1e3:.3f} ms = {tr2['dram_bytes'] / tr2['seconds'] / 1e12:.2f} TB/s
+({tr2['dram_bytes'] / tr2['seconds'] / 1e9 / rf2['peak']:.3f}): less than the algorithmic figure because the body deltas stay in L2; every row byte is read once per iteration."""]
+sc2 = ["| GPUs | c3 replicas: body-steps/s (ms/step) | e2e body-steps/s | c4, 4096 worlds: 1 GPU ms | sharded ms | speed-up |", "|---|---|---|---|---|---|"]
+for n in (1, 2, 4, 8):
+    j = b2 if n == 1 else load(f"r02_scale{n}.json")
+    c = j["c4"]
+    sc2.append(f"| {n} | {sci(j['value'])} ({j['ms_per_step']:.3f}) | {sci(j['e2e']['value'])} | {c['ms_per_step_1gpu']:.3f} | "
+               + (f"{c['ms_per_step_sharded']:.3f} | {c['speedup']:.2f} x |" if "speedup" in c else "- | - |"))
+sh, fu = load("r02_c4_shard512.json"), load("r02_c4_full.json")
+c4txt = (f"Config 4 on one GPU, exact COLORED solver (`bench.py --config c4 [--scale 0.125]`): 4096 worlds {fu['ms_per_step']:.2f} ms per step "
+         f"(broadphase {fu['stage_ms']['broadphase']:.2f}, narrowphase {fu['stage_ms']['narrowphase']:.2f}, solve {fu['stage_ms']['solve']:.2f} of which the per-world sweep "
+         f"{fu['stage_ms']['gs']:.2f}); one 512-world shard {sh['ms_per_step']:.2f} ms (sweep {sh['stage_ms']['gs']:.2f}). The grid-wide level sweep needed 5.06 / 1.90 ms.")
+shares2 = []
+for line in open(os.path.join(HERE, "r02_launches.md")):
+    m = re.match(r"\| `([^`]+)` \| (\d+) \| ([\d.]+) \| ([\d.]+) % \|", line)
+    if m and len(shares2) < 8:
+        shares2.append(f"`{m.group(1)}` {m.group(4)} %")
 s = open(os.path.join(HERE, "README.tmpl.md")).read()
+for k, v in (("@@R02HEAD@@", r02[0]), ("@@R02ROOF@@", r02[1]), ("@@R02SCALE@@", "\n".join(sc2)), ("@@R02C4@@", c4txt), ("@@R02SHARES@@", ", ".join(shares2) + ".")):
+    s = s.replace(k, v)
 for k, v in (("@@HEADLINE@@", head), ("@@ROOFLINE@@", roof), ("@@SHARES@@", ", ".join(shares) + "."), ("@@TABLE@@", "\n".join(rows)), ("@@SCALE2@@", scale2),
              ("@@C3MS@@", f"{b['ms_per_step']:.2f}"), ("@@C4MS@@", f"{c4['ms_per_step']:.2f}"), ("@@C5MS@@", f"{c5['ms_per_step']:.1f}")):
     s = s.replace(k, v)
