@@ -86,7 +86,6 @@ __device__ __forceinline__ void gx_wait(unsigned* bar, unsigned epoch, bool last
   while (true) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 32) : "memory");
     if (g >= epoch) break;
-    __nanosleep(20);
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }

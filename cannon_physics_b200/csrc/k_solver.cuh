@@ -273,12 +273,26 @@ __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays 
   const int nc = min(*C.nContacts, S.contactCap);
   const int nt = min(*S.nTasks, S.taskCap);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (int t = tid; t < nt; t += nth) {
-    const int m = S.taskCnt[t], c0 = S.taskOff[t];
-    if (m <= 0 || c0 + m > nc) continue;
-    const int w = B.world[C.bi[c0]];
-    atomicMin(&wk[w], c0);
-    atomicAdd(&wk[nWorlds + w], m);
+  // neighbouring tasks belong to the same world: one atomic per (warp, world) instead of one per task
+  for (int t0 = tid - (int)(threadIdx.x & 31); t0 < nt; t0 += nth) {
+    const int t = t0 + (int)(threadIdx.x & 31);
+    int w = -1, c0 = 0x7fffffff, m = 0;
+    if (t < nt) {
+      m = S.taskCnt[t];
+      const int c = S.taskOff[t];
+      if (m > 0 && c + m <= nc) { w = B.world[C.bi[c]]; c0 = c; } else m = 0;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, w);
+    int mn = c0, sum = m;
+    // reduce over the peer group with shuffles from every peer lane
+    for (int l = 0; l < 32; l++) {
+      const int oc = __shfl_sync(0xffffffffu, c0, l), om = __shfl_sync(0xffffffffu, m, l);
+      if (((peers >> l) & 1u) && l != (int)(threadIdx.x & 31)) { mn = min(mn, oc); sum += om; }
+    }
+    if (w >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      atomicMin(&wk[w], mn);
+      atomicAdd(&wk[nWorlds + w], sum);
+    }
   }
   for (int s2 = tid; s2 < J.nAccepted; s2 += nth) atomicMin(&wk[2 * nWorlds + B.world[J.bodyA[J.slotEq[s2]]]], s2);
 }

@@ -12,7 +12,7 @@ from cannon_physics_b200 import engine  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 220
 config = sys.argv[2] if len(sys.argv) > 2 else "c3"
-spec, label = bench.build_spec(config, 1.0, 0, 1)
+spec, label, _state = bench.build_spec(config, 1.0, 0, 1)
 w = engine.DeviceWorld(cp.lib, spec, device=0)
 w.step(1 / 60, steps)
 prof = w.profile()
