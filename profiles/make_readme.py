@@ -100,7 +100,13 @@ for line in open(os.path.join(HERE, "r02_launches.md")):
     m = re.match(r"\| `([^`]+)` \| (\d+) \| ([\d.]+) \| ([\d.]+) % \|", line)
     if m and len(shares2) < 8:
         shares2.append(f"`{m.group(1)}` {m.group(4)} %")
+rows2 = ["| config | solver | ms/step | steps/s | body-steps/s | contact-iters/s | contacts / colours | sweep: algorithmic bytes / time vs HBM peak |", "|---|---|---|---|---|---|---|---|"]
+for t in (json.loads(l) for l in open(os.path.join(HERE, "r02_table.jsonl")) if l.strip()):
+    wl = t["config"]["workload"]
+    rows2.append(f"| {names[wl[:2]]} | {wl.split('solver=')[1]} | {t['ms_per_step']:.2f} | {t['steps_per_s']:.0f} | {sci(t['value'])} | {sci(t['contact_iters_per_s'])} | "
+                 f"{t['last_step']['contacts']} / {t['last_step']['levels']} | {t['roofline']['frac']:.3f} (`{t['roofline']['kernel']}`) |")
 s = open(os.path.join(HERE, "README.tmpl.md")).read()
+s = s.replace("@@R02TABLE@@", "\n".join(rows2))
 for k, v in (("@@R02HEAD@@", r02[0]), ("@@R02ROOF@@", r02[1]), ("@@R02SCALE@@", "\n".join(sc2)), ("@@R02C4@@", c4txt), ("@@R02SHARES@@", ", ".join(shares2) + ".")):
     s = s.replace(k, v)
 for k, v in (("@@HEADLINE@@", head), ("@@ROOFLINE@@", roof), ("@@SHARES@@", ", ".join(shares) + "."), ("@@TABLE@@", "\n".join(rows)), ("@@SCALE2@@", scale2),
