@@ -336,7 +336,7 @@ def main():
     if kind == F.SOLVER_COLORED_F32:
         gs_kernel = "k_gs_world_ring" if spec.desc.get("n_worlds", 1) > 1 else "k_gs_fast"
     elif kind == F.SOLVER_COLORED:
-        gs_kernel = "k_gs_exact"
+        gs_kernel = "k_gs_world_exact" if spec.desc.get("n_worlds", 1) > 1 else "k_gs_exact"
     else:
         gs_kernel = "k_gs"
     step_ms_prof = pp["sum_step_ms"] / max(pp["sum_steps"], 1)

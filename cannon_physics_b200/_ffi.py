@@ -90,6 +90,7 @@ class ConstraintDesc(C.Structure):
         ("max_force", c_f64), ("collide_connected", c_i32), ("motor_enabled", c_i32),
         ("motor_target_velocity", c_f64), ("motor_max_force", c_f64),
         ("distance", c_f64), ("angle", c_f64), ("twist_angle", c_f64),
+        ("has_ctor_pose", c_i32), ("ctor_pos_a", c_f32 * 3), ("ctor_quat_a", c_f32 * 4), ("ctor_pos_b", c_f32 * 3), ("ctor_quat_b", c_f32 * 4),
     ]
 
 

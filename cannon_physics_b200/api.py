@@ -413,6 +413,14 @@ class LockConstraint(PointToPointConstraint):  # lock_constraint.dart:9
 
     def __init__(self, bodyA, bodyB, maxForce: float = 1e6):
         super().__init__(bodyA, bodyB, None, None, maxForce)
+        self._ctor_pose = None
+
+    def _desc(self, idx):
+        d = super()._desc(idx)
+        if self._ctor_pose is not None:
+            pa, qa, pb, qb = self._ctor_pose
+            d.update(has_ctor_pose=1, ctor_pos_a=pa, ctor_quat_a=qa, ctor_pos_b=pb, ctor_quat_b=qb)
+        return d
 
 
 class ConeTwistConstraint(PointToPointConstraint):  # cone_twist_constraint.dart:11
@@ -520,6 +528,11 @@ class World:  # lib/world/world_class.dart:44
     def addConstraint(self, c: Constraint):
         self._pull()
         c.world = self
+        if isinstance(c, LockConstraint) and c._ctor_pose is None:
+            # lock_constraint.dart:29-43 derives pivots and frame vectors from the poses its constructor sees: recorded now,
+            # so a later rebuild of the device world (addBody ...) reproduces the same constraint instead of re-locking the
+            # bodies in whatever pose they have drifted to
+            c._ctor_pose = (c.bodyA.position.copy(), c.bodyA.quaternion.copy(), c.bodyB.position.copy(), c.bodyB.quaternion.copy())
         if isinstance(c, DistanceConstraint) and c.distance is None:
             # Vector3.distanceTo on the f32-stored positions, evaluated in double (distance_constraint.dart:16)
             d = c.bodyA.position.astype(np.float64) - c.bodyB.position.astype(np.float64)

@@ -239,6 +239,7 @@ struct cannon_world {
   bool recordSolveEvents = false;
   bool stepPending = false;             // cannon_world_step_async enqueued work that cannon_ctx_sync has not collected yet
   std::vector<cudaEvent_t> profPool;    // cannon_world_step_profiled: PROF_EV events per step
+  bool stageEventsValid = false;        // the call's last step ran eagerly: ev[0..7,10] were recorded outside a graph and can be read
   // one World.step captured as a CUDA graph (all counts live on the device, so the launch sequence of a step is
   // fixed for a given dt and capacity; the cooperative kernels size their own barrier on the device); replayed by
   // cannon_world_step
@@ -935,8 +936,14 @@ int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_co
     }
     const bool trig = (flags[d.body_a] & BF_IS_TRIGGER) || (flags[d.body_b] & BF_IS_TRIGGER);
     const int firstEq = (int)bodyA.size();
-    const f3 xA = ld3(hpos[d.body_a]), xB = ld3(hpos[d.body_b]);
-    const q4 qA = ldq(hquat[d.body_a]), qB = ldq(hquat[d.body_b]);
+    // the poses the constraint's constructor saw: the current ones, or the recorded ones of a constraint made earlier
+    f3 xA = ld3(hpos[d.body_a]), xB = ld3(hpos[d.body_b]);
+    q4 qA = ldq(hquat[d.body_a]), qB = ldq(hquat[d.body_b]);
+    if (d.has_ctor_pose) {
+      xA.x = d.ctor_pos_a[0]; xA.y = d.ctor_pos_a[1]; xA.z = d.ctor_pos_a[2]; xB.x = d.ctor_pos_b[0]; xB.y = d.ctor_pos_b[1]; xB.z = d.ctor_pos_b[2];
+      qA.x = d.ctor_quat_a[0]; qA.y = d.ctor_quat_a[1]; qA.z = d.ctor_quat_a[2]; qA.w = d.ctor_quat_a[3];
+      qB.x = d.ctor_quat_b[0]; qB.y = d.ctor_quat_b[1]; qB.z = d.ctor_quat_b[2]; qB.w = d.ctor_quat_b[3];
+    }
     f3 pvA, pvB;
     pvA.x = d.pivot_a[0]; pvA.y = d.pivot_a[1]; pvA.z = d.pivot_a[2];
     pvB.x = d.pivot_b[0]; pvB.y = d.pivot_b[1]; pvB.z = d.pivot_b[2];
@@ -1832,6 +1839,7 @@ static int32_t step_enqueue(cannon_world* w, double dt, int32_t nsteps, bool pro
       if (rc != CANNON_OK) return rc;
       w->eagerSteps++;
     }
+    w->stageEventsValid = !done;
     w->stepnumber += 1;
     w->time += dt;  // World.step: time += dt after internalStep (world_class.dart:396-399)
   }
@@ -1872,7 +1880,7 @@ static int32_t step_finish(cannon_world* w, int32_t nsteps, bool profiled) {
       if (cudaEventElapsedTime(&ms, ev[0], ev[4]) == cudaSuccess) p.sum_step_ms += ms;
       p.sum_steps += 1;
     }
-  } else {
+  } else if (w->stageEventsValid) {  // events recorded inside a graph replay cannot be read: the previous values stay
     stage(w->ev);
   }
   if (cudaEventElapsedTime(&ms, w->ev[8], w->ev[9]) == cudaSuccess) p.step_call_ms = ms;

@@ -194,10 +194,10 @@ class DeviceWorld:
             d.axis_b[0] = 1.0
             d.distance = -1.0  # DistanceConstraint: current distance unless given
             for k, v in c.items():
-                if k in ("pivot_a", "pivot_b", "axis_a", "axis_b"):
+                if k in ("pivot_a", "pivot_b", "axis_a", "axis_b", "ctor_pos_a", "ctor_quat_a", "ctor_pos_b", "ctor_quat_b"):
                     vv = np.asarray(v, dtype=np.float32)
                     a = getattr(d, k)
-                    for j in range(3):
+                    for j in range(len(vv)):
                         a[j] = float(vv[j])
                 else:
                     setattr(d, k, v)

@@ -126,6 +126,11 @@ final class CannonConstraintDesc extends Struct {
   @Double() external double distance;
   @Double() external double angle;
   @Double() external double twistAngle;
+  @Int32() external int hasCtorPose;
+  @Array(3) external Array<Float> ctorPosA;
+  @Array(4) external Array<Float> ctorQuatA;
+  @Array(3) external Array<Float> ctorPosB;
+  @Array(4) external Array<Float> ctorQuatB;
 }
 
 final class CannonSpringDesc extends Struct {

@@ -207,6 +207,11 @@ typedef struct cannon_constraint_desc {
   double  distance;               /* distance constraint: < 0 => bodyA.position.distanceTo(bodyB.position) at set time */
   double  angle;                  /* cone-twist: ConeEquation.angle */
   double  twist_angle;            /* cone-twist: maxAngle of the twist RotationalEquation */
+  /* The poses the constraint's CONSTRUCTOR saw, for constraints that were made earlier than this upload (a world rebuilt
+   * after bodies moved): has_ctor_pose != 0 makes LockConstraint's pivots / frame vectors (lock_constraint.dart:29-43) and
+   * DistanceConstraint's default distance (distance_constraint.dart:16) come from these instead of the current poses. */
+  int32_t has_ctor_pose;
+  float   ctor_pos_a[3], ctor_quat_a[4], ctor_pos_b[3], ctor_quat_b[4];
 } cannon_constraint_desc;
 
 /* Spring, lib/objects/spring.dart:17. The reference applies springs from user code, canonically

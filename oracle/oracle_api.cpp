@@ -351,8 +351,12 @@ int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_c
       e.maxAngle = maxAngle;
       return e;
     };
-    Body& A = w.bodies[c.bodyA];
-    Body& B = w.bodies[c.bodyB];
+    Body Actor = w.bodies[c.bodyA], Bctor = w.bodies[c.bodyB];  // what the constraint's constructor saw
+    if (d.has_ctor_pose) {
+      Actor.position = V3{d.ctor_pos_a[0], d.ctor_pos_a[1], d.ctor_pos_a[2]}; Actor.quaternion = Q4{d.ctor_quat_a[0], d.ctor_quat_a[1], d.ctor_quat_a[2], d.ctor_quat_a[3]};
+      Bctor.position = V3{d.ctor_pos_b[0], d.ctor_pos_b[1], d.ctor_pos_b[2]}; Bctor.quaternion = Q4{d.ctor_quat_b[0], d.ctor_quat_b[1], d.ctor_quat_b[2], d.ctor_quat_b[3]};
+    }
+    const Body &A = Actor, &B = Bctor;
     if (d.type == CANNON_CONSTRAINT_DISTANCE) {  // distance_constraint.dart:14-23: one bidirectional ContactEquation
       c.distance = d.distance >= 0 ? d.distance : distance_to(A.position, B.position);
       Eq e;

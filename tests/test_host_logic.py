@@ -391,3 +391,31 @@ def test_bench_reference_arm_uses_the_settled_state_and_never_maps_the_cuda_libr
         "print('ok')\n" % root)
     out = subprocess.check_output([sys.executable, "-c", code], text=True)
     assert out.strip().endswith("ok")
+
+
+def test_world_api_lock_constraint_survives_a_rebuild(oracle_lib):
+    """LockConstraint derives its pivots and frame vectors from the poses its constructor sees (lock_constraint.dart:29-43).
+    A structural change later rebuilds the device world: the constraint must come back as it was made (the recorded poses
+    travel in cannon_constraint_desc.ctor_*), not re-lock the bodies in the pose they have drifted to."""
+    from cannon_physics_b200 import api
+
+    def build():
+        w = api.World(gravity=(0, -10, 0), _lib=oracle_lib)
+        a = api.Body(mass=0, shape=api.Box((0.25, 0.25, 0.25)), position=(0, 5, 0))
+        b = api.Body(mass=1, shape=api.Box((0.25, 0.25, 0.25)), position=(1, 5, 0), quaternion=(0, 0.38268343, 0, 0.92387953), angularDamping=0.0)
+        w.addBody(a)
+        w.addBody(b)
+        w.addConstraint(api.LockConstraint(a, b, maxForce=50.0))  # soft: the hanging box sags and swings
+        return w, b
+
+    ref, rb = build()
+    for _ in range(60):
+        ref.step(1 / 60)
+    w, b = build()
+    for _ in range(25):
+        w.step(1 / 60, sync=False)
+    w.addBody(api.Body(mass=1, shape=api.Sphere(0.2), position=(50, 0, 0)))  # rebuild while the box is displaced
+    for _ in range(35):
+        w.step(1 / 60, sync=False)
+    w.sync()
+    assert np.array_equal(b.position, rb.position) and np.array_equal(b.quaternion, rb.quaternion)
