@@ -18,6 +18,9 @@
 // read from global memory every iteration 3.57 / 1.50 ms (a lone warp per SM waiting for L2); this kernel 2.73 / 0.46 ms.
 // A world's solve is one warp's dependent chain (~0.4 ms for 10 iterations of 13 colours, conversion-pipe latency bound);
 // the full batch is 4096 / 592 = 7 rounds of that - shared memory per world, not arithmetic, caps the concurrency.
+// Tried and rejected: two lanes per unit (one per body, an f64 shuffle pair per row; tools/ubench/row_step.cu promises 348
+// instead of 545 clk per row for a lone warp): bit-exact, but 0.50 / 2.91 ms here - the shuffles and the second lane's
+// shared-memory reads cost more than the halved conversions save.
 #pragma once
 #include "k_gs_exact.cuh"
 
