@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(32) k_gs_world_exact(RowArrays R, BodyArrays B
   double* const s_lam = (double*)(s_dyn + (size_t)GWX_MAXR * sizeof(GxRow));  // their multipliers
   float4* const s_vw = (float4*)(s_dyn + (size_t)GWX_MAXR * GWX_ROW_BYTES);
   GwxUnit* const s_units = (GwxUnit*)(s_dyn + (size_t)GWX_MAXR * GWX_ROW_BYTES + GWX_MAXB * 32);
+  __shared__ int s_bs[GR_LV + 1];  // first unit of every colour of this world: read once, not once per colour and iteration
   const int lane = threadIdx.x, wd = blockIdx.x;
   const int nLevels = *nLevelsPtr;
-  const int* bs = binStart + (size_t)wd * GR_LV;
+  for (int i = lane; i <= GR_LV; i += 32) s_bs[i] = binStart[(size_t)wd * GR_LV + i];
+  __syncwarp();
+  const int* const bs = s_bs;
   const int a0 = bs[0], nU = bs[GR_LV] - a0;
   if (nU <= 0) { if (lane == 0) G.worldIters[wd] = 0; return; }
   const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
@@ -112,6 +115,30 @@ __global__ void __launch_bounds__(32) k_gs_world_exact(RowArrays R, BodyArrays B
         f3 vA = ld3((m.fl & 1) ? vw[ia] : z4), wA = ld3((m.fl & 1) ? vw[ia + 1] : z4);
         f3 vB = ld3((m.fl & 2) ? vw[ib] : z4), wB = ld3((m.fl & 2) ? vw[ib + 1] : z4);
         double acc = 0.0;
+        if (m.r1 - r0w <= nRs) {
+          // every row of the unit is staged (the common case): software-pipelined like k_gs_exact - the next row's record is
+          // read and widened in the shadow of this row's dependent chain; one basic block, no movable-body branches (an
+          // immovable body has invMassSolve = 0 and I^-1 r = 0: its never-stored deltas stay +0 by arithmetic)
+          const int k0 = m.r0 - r0w, nr = m.r1 - m.r0;
+          GxJ cur, nxt;
+          gwx_widen(s_rows[k0], s_lam[k0], cur);
+          for (int rr = 0; rr < nr; rr++) {
+            const int kn = k0 + min(rr + 1, nr - 1);
+            gwx_widen(s_rows[kn], s_lam[kn], nxt);
+            const double gwl = (gx_dot(vA, cur.sAx, cur.sAy, cur.sAz) + gx_dot(wA, cur.rAx, cur.rAy, cur.rAz)) +
+                               (gx_dot(vB, cur.nx, cur.ny, cur.nz) + gx_dot(wB, cur.rBx, cur.rBy, cur.rBz));
+            double dl = cur.invC * (cur.Bv - gwl - cur.eps * cur.lam);
+            double mn = cur.mn, mx = cur.mx;
+            if (cur.general) { mn = R.minF[m.r0 + rr]; mx = R.maxF[m.r0 + rr]; }
+            if (cur.lam + dl < mn) dl = mn - cur.lam;
+            else if (cur.lam + dl > mx) dl = mx - cur.lam;
+            s_lam[k0 + rr] = cur.lam + dl;
+            vA = gx_axpy(vA, m.imA * dl, cur.sAx, cur.sAy, cur.sAz); wA = gx_axpy(wA, dl, cur.iAx, cur.iAy, cur.iAz);
+            vB = gx_axpy(vB, m.imB * dl, cur.nx, cur.ny, cur.nz); wB = gx_axpy(wB, dl, cur.iBx, cur.iBy, cur.iBz);
+            acc += dl > 0.0 ? dl : -dl;
+            cur = nxt;
+          }
+        } else
         for (int r = m.r0; r < m.r1; r++) {
           const int k = r - r0w;
           GxJ j;
