@@ -137,6 +137,7 @@ struct cannon_world {
   std::vector<double> hHfData;
   std::vector<double> hLdamp, hAdamp;
   std::vector<int> hBig, hBigWorldStart, hWorldStart;
+  int maxWorldBodies = 0;  // largest world of a batch (chooses the all-pairs broadphase for small worlds)
   bool hasOversizeHull = false;  // some hull exceeds the tile kernel's scratch: run the sequential SAT kernels for those tasks
   double cell = 1.0;
   int nBig = 0, hashSize = 1024;
@@ -866,6 +867,8 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   for (int k = 0; k < nW; k++) w->hBigWorldStart[k + 1] += w->hBigWorldStart[k];
   for (int i = n - 1; i >= 0; i--) w->hWorldStart[world[i]] = i;
   for (int k = nW - 1; k >= 0; k--) if (w->hWorldStart[k] > w->hWorldStart[k + 1]) w->hWorldStart[k] = w->hWorldStart[k + 1];
+  w->maxWorldBodies = 0;
+  for (int k = 0; k < nW; k++) w->maxWorldBodies = std::max(w->maxWorldBodies, w->hWorldStart[k + 1] - w->hWorldStart[k]);
   w->hLdamp = ldamp;
   w->hAdamp = adamp;
   w->powDt = -1;
@@ -1174,6 +1177,12 @@ static int32_t st_broadphase(cannon_world* w) {
     { g_kernel_launches++; k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 0, nullptr, nullptr, 0, nullptr); }
     W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
     { g_kernel_launches++; k_sap_sweep<<<gw, 256, 0, s>>>(B, P, A, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS); }
+  } else if (P.kind == CANNON_BP_NAIVE && w->desc.n_worlds > 1 && w->maxWorldBodies <= 512 && !getenv("CANNON_BP_NO_WORLD_KERNEL")) {
+    // batches of small worlds: all pairs inside every world, no grid (k_broadphase.cuh, k_bp_world_all)
+    const int g = grid_for(w, 32LL * n, 128);
+    { g_kernel_launches++; k_bp_world_all<<<g, 128, 0, s>>>(B, P, A, n, 0, nullptr, nullptr, 0, nullptr); }
+    W_TRY(w, scan_exclusive(A.counts, A.offs, nullptr, n, n, cnt + CT_NPAIRS, w->scanTmp, s));
+    { g_kernel_launches++; k_bp_world_all<<<g, 128, 0, s>>>(B, P, A, n, 1, w->p1.p, w->p2.p, w->pairCap, cnt + CT_OVF_PAIRS); }
   } else {
     { g_kernel_launches++; k_bp_cells<<<grid_for(w, n, 256), 256, 0, s>>>(B, shape_tables(w), P, A); }
     int bits = 1;
