@@ -762,7 +762,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   }
   const int unitCap = rowCap + 2;
   w->unitCap = unitCap;
-  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(uKey, unitCap); RES(uPri, unitCap); RES(worldKeys, 3 * (size_t)std::max(1, w->desc.n_worlds) + 1); RES(eBi, unitCap); RES(eBj, unitCap);
+  RES(uBi, unitCap); RES(uBj, unitCap); RES(uFlags, unitCap); RES(uRows, unitCap); RES(uSrc, unitCap); RES(uKey, unitCap); RES(uPri, unitCap); RES(worldKeys, WK_ARRAYS * (size_t)std::max(1, w->desc.n_worlds) + 1); RES(eBi, unitCap); RES(eBj, unitCap);
   RES(eFlags, unitCap); RES(eRowBase, unitCap + 1); RES(eRows, unitCap + 1); RES(unitRow, unitCap); RES(eImA, unitCap); RES(eImB, unitCap);
   RES(lenBins, 3 * LEN_BINS); RES(eLevel, unitCap); RES(orderW, unitCap); RES(worldCount, 2 * ((size_t)w->desc.n_worlds * GR_LV + 4)); RES(worldUnitStart, (size_t)w->desc.n_worlds * GR_LV + 4);
   RES(unitLevel, unitCap); RES(order, unitCap); RES(act0, unitCap); RES(act1, unitCap); RES(levelStart, w->maxLevels + 2);
@@ -1426,7 +1426,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
   Us.fricTotal = cnt + CT_FRICTOTAL; Us.contTotal = cnt + CT_CONTTOTAL; Us.taskOff = w->taskOff.p; Us.taskCnt = w->taskCnt.p;
   Us.nTasks = cnt + CT_NTASKS; Us.taskCap = w->taskCap; Us.contactCap = w->contactCap;
   if (P.colored && nW > 1) {  // world-local keys for the colouring of a batch
-    { g_kernel_launches++; k_world_keys_init<<<grid_for(w, 3 * nW, 256), 256, 0, s>>>(w->worldKeys.p, nW); }
+    { g_kernel_launches++; k_world_keys_init<<<grid_for(w, WK_ARRAYS * nW, 256), 256, 0, s>>>(w->worldKeys.p, nW); }
     { g_kernel_launches++; k_world_keys<<<grid_for(w, w->taskCap, 256), 256, 0, s>>>(B, C, Us, J, nW, w->worldKeys.p); }
   }
   { g_kernel_launches++; k_units_build<<<grid_for(w, w->unitCap, 256), 256, 0, s>>>(B, C, Us, J, U, nW, w->worldRows.p, cnt + CT_OVF_ROWS, w->worldKeys.p); }
@@ -1439,7 +1439,14 @@ static int32_t st_solve(cannon_world* w, double dt) {
   S.unitSeq = nullptr; S.bodyCnt = nullptr;
   W_TRY(w, cudaMemsetAsync(w->claim.p, 0xff, ((size_t)w->n + 1) * sizeof(unsigned long long), s));
   if (w->recordSolveEvents) cudaEventRecord(w->ev[5], s);
-  {
+  // a COLORED batch of small worlds is coloured world by world (one warp each, no grid barrier)
+  const bool worldSched = P.colored && nW > 1 && w->maxWorldBodies <= SW_MAXB && !split && !kind_fast(w) && !w->gxOff && !getenv("CANNON_NO_WORLD_SCHEDULE");
+  if (worldSched) {
+    W_TRY(w, cudaMemsetAsync(cnt + CT_NEXEC, 0, sizeof(int), s));
+    W_TRY(w, cudaMemsetAsync(cnt + CT_NLEVELS, 0, sizeof(int), s));
+    g_kernel_launches++;
+    k_schedule_worlds<<<nW, 32, 0, s>>>(B, U, S, w->worldKeys.p, w->worldStart.p, nW, 0, cnt + CT_NTASKS, w->taskCap);
+  } else {
     int colored = P.colored;
     void* args[] = {&U, &S, &colored};
     g_kernel_launches++;

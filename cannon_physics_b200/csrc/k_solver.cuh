@@ -265,9 +265,15 @@ __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& 
 // COLORED batches: the colouring hashes a unit's key, and a world's colours must not depend on which other worlds share
 // the handle (a batch may be sharded over GPUs in any way). So the hashed key is counted inside the world:
 // contacts from the world's first ContactEquation, constraints from the world's contact count. wk[w] = first contact
-// index, wk[nW + w] = contacts, wk[2 nW + w] = first accepted joint slot of world w.
+// index, wk[nW + w] = contacts, wk[2 nW + w] = first accepted joint slot of world w. For the per-world colouring
+// (k_schedule_worlds) also the world's ranges of unit ids: wk[3 nW + w] / wk[4 nW + w] = first / last task with contacts,
+// wk[5 nW + w] = last accepted joint slot.
+#define WK_ARRAYS 6
 __global__ void __launch_bounds__(256) k_world_keys_init(int* __restrict__ wk, int nWorlds) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * nWorlds; i += gridDim.x * blockDim.x) wk[i] = (i >= nWorlds && i < 2 * nWorlds) ? 0 : 0x7fffffff;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < WK_ARRAYS * nWorlds; i += gridDim.x * blockDim.x) {
+    const int a = i / nWorlds;
+    wk[i] = (a == 0 || a == 2 || a == 3) ? 0x7fffffff : (a == 1 ? 0 : -1);
+  }
 }
 __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, int nWorlds, int* __restrict__ wk) {
   const int nc = min(*C.nContacts, S.contactCap);
@@ -283,18 +289,20 @@ __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays 
       if (m > 0 && c + m <= nc) { w = B.world[C.bi[c]]; c0 = c; } else m = 0;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, w);
-    int mn = c0, sum = m;
-    // reduce over the peer group with shuffles from every peer lane
-    for (int l = 0; l < 32; l++) {
-      const int oc = __shfl_sync(0xffffffffu, c0, l), om = __shfl_sync(0xffffffffu, m, l);
-      if (((peers >> l) & 1u) && l != (int)(threadIdx.x & 31)) { mn = min(mn, oc); sum += om; }
-    }
+    const int mn = __reduce_min_sync(peers, c0), sum = __reduce_add_sync(peers, m);
+    const int tmn = __reduce_min_sync(peers, w >= 0 ? t : 0x7fffffff), tmx = __reduce_max_sync(peers, w >= 0 ? t : -1);
     if (w >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
       atomicMin(&wk[w], mn);
       atomicAdd(&wk[nWorlds + w], sum);
+      atomicMin(&wk[3 * nWorlds + w], tmn);
+      atomicMax(&wk[4 * nWorlds + w], tmx);
     }
   }
-  for (int s2 = tid; s2 < J.nAccepted; s2 += nth) atomicMin(&wk[2 * nWorlds + B.world[J.bodyA[J.slotEq[s2]]]], s2);
+  for (int s2 = tid; s2 < J.nAccepted; s2 += nth) {
+    const int w = B.world[J.bodyA[J.slotEq[s2]]];
+    atomicMin(&wk[2 * nWorlds + w], s2);
+    atomicMax(&wk[5 * nWorlds + w], s2);
+  }
 }
 
 // unit table. Reference order: unit id == reference row index [2*fricRank | nF2 + contRank | joints].
@@ -543,6 +551,129 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
 }
 
 // rows per unit in execution order (input of the row-base scan) + per-unit execution data
+// The colouring of a COLORED batch, one warp per world (no grid barrier: worlds share no body). Same rule as k_schedule -
+// colour(u) = round in which u holds the smallest pending priority on all of its movable bodies - over the world's own
+// units: the tasks [wk[3 nW + w], wk[4 nW + w]] that produced rows and the joint units of slots [wk[2 nW + w], wk[5 nW + w]].
+// The claims live in shared memory and are cleared every round; a round visits all candidates and skips the coloured ones
+// (~100 units x ~13 rounds per world). Scheduled units are appended to `order` (k_world_count / k_world_fill regroup them
+// by world and colour anyway); nLevels is the maximum over the worlds.
+#define SW_REG 8     // units a lane keeps in registers (256 per world; larger worlds re-read theirs from global memory)
+#define SW_MAXB 512  // bodies of a world (the host picks this kernel only for batches of worlds up to this size)
+__global__ void __launch_bounds__(32) k_schedule_worlds(BodyArrays B, UnitArrays U, SchedArrays S, const int* __restrict__ wk, const int* __restrict__ worldBody,
+                                                        int nWorlds, int jointBase0 /* unused */, const int* __restrict__ nTasksPtr, int taskCap) {
+  __shared__ unsigned s_claim[SW_MAXB];
+  const int lane = threadIdx.x, wd = blockIdx.x;
+  const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
+  const int jointBase = min(*nTasksPtr, taskCap);  // unit id of joint slot 0 (k_units_build)
+  const int t0 = wk[3 * nWorlds + wd], t1 = wk[4 * nWorlds + wd];
+  const int j0 = wk[2 * nWorlds + wd], j1 = wk[5 * nWorlds + wd];
+  const int nT = t1 >= t0 ? t1 - t0 + 1 : 0, nJ = j1 >= j0 ? j1 - j0 + 1 : 0;
+  const int nCand = nT + nJ;
+  if (nCand == 0) return;
+  auto unit_of = [&](int k) { return k < nT ? t0 + k : jointBase + j0 + (k - nT); };
+  int round = 0;
+  // the candidates that own rows, compacted in candidate order (most joint slots and a third of the tasks own none)
+  __shared__ int s_u[32 * SW_REG];
+  int nAct = 0;
+  for (int kb = 0; kb < nCand; kb += 32) {
+    const int k = kb + lane;
+    const bool has = k < nCand && U.uRows[unit_of(k)] > 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, has);
+    if (has) { const int pos = nAct + __popc(bits & ((1u << lane) - 1u)); if (pos < 32 * SW_REG) s_u[pos] = unit_of(k); }
+    nAct += __popc(bits);
+  }
+  __syncwarp();
+  if (nAct <= 32 * SW_REG) {
+    // the usual case: every lane keeps its units (priority, body slots, level) in registers for all rounds
+    unsigned pri[SW_REG];
+    int ba[SW_REG], bb[SW_REG], lv[SW_REG];  // body slots (-1: not movable / no unit), level (-1 pending, -2 none)
+#pragma unroll
+    for (int i = 0; i < SW_REG; i++) {
+      const int k = lane + 32 * i;
+      pri[i] = 0u; ba[i] = bb[i] = -1; lv[i] = -2;
+      if (k < nAct) {
+        const int u = s_u[k];
+        const int fl = U.uFlags[u];
+        pri[i] = (unsigned)U.uPri[u] * 2654435761u;
+        ba[i] = (fl & 1) ? U.uBi[u] - b0 : -1;
+        bb[i] = (fl & 2) ? U.uBj[u] - b0 : -1;
+        lv[i] = -1;
+      }
+    }
+    while (true) {
+      if (round >= S.maxLevels) { if (lane == 0) *S.levelOverflow = 1; break; }
+      for (int i = lane; i < nB; i += 32) s_claim[i] = 0xffffffffu;
+      __syncwarp();
+      bool pending = false;
+#pragma unroll
+      for (int i = 0; i < SW_REG; i++)
+        if (lv[i] == -1) {
+          pending = true;
+          if (ba[i] >= 0) atomicMin(&s_claim[ba[i]], pri[i]);
+          if (bb[i] >= 0) atomicMin(&s_claim[bb[i]], pri[i]);
+        }
+      if (!__any_sync(0xffffffffu, pending)) break;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < SW_REG; i++)
+        if (lv[i] == -1 && (ba[i] < 0 || s_claim[ba[i]] == pri[i]) && (bb[i] < 0 || s_claim[bb[i]] == pri[i])) lv[i] = round;
+      round++;
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < SW_REG; i++) {
+      const int k = lane + 32 * i;
+      if (k < nAct && lv[i] >= 0) S.unitLevel[s_u[k]] = lv[i];
+    }
+  } else {
+  for (int k = lane; k < nCand; k += 32) S.unitLevel[unit_of(k)] = -1;
+  __syncwarp();
+  while (true) {
+    if (round >= S.maxLevels) { if (lane == 0) *S.levelOverflow = 1; break; }
+    for (int i = lane; i < nB; i += 32) s_claim[i] = 0xffffffffu;
+    __syncwarp();
+    int pending = 0;
+    for (int k = lane; k < nCand; k += 32) {
+      const int u = unit_of(k);
+      if (U.uRows[u] <= 0 || S.unitLevel[u] >= 0) continue;
+      pending++;
+      const unsigned pri = (unsigned)U.uPri[u] * 2654435761u;
+      const int fl = U.uFlags[u];
+      if (fl & 1) atomicMin(&s_claim[U.uBi[u] - b0], pri);
+      if (fl & 2) atomicMin(&s_claim[U.uBj[u] - b0], pri);
+    }
+    if (!__any_sync(0xffffffffu, pending > 0)) break;
+    __syncwarp();
+    for (int k = lane; k < nCand; k += 32) {
+      const int u = unit_of(k);
+      if (U.uRows[u] <= 0 || S.unitLevel[u] >= 0) continue;
+      const unsigned pri = (unsigned)U.uPri[u] * 2654435761u;
+      const int fl = U.uFlags[u];
+      bool win = true;
+      if ((fl & 1) && s_claim[U.uBi[u] - b0] != pri) win = false;
+      if ((fl & 2) && s_claim[U.uBj[u] - b0] != pri) win = false;
+      if (win) S.unitLevel[u] = round;
+    }
+    round++;
+    __syncwarp();
+  }
+  }
+  // the world's scheduled units, in candidate order, at a block of `order` reserved with one atomic
+  int mine = 0;
+  for (int k = lane; k < nCand; k += 32) mine += (U.uRows[unit_of(k)] > 0) ? 1 : 0;
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 0 && total > 0) base = atomicAdd(U.nExec, total);
+  base = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
+  for (int k = lane; k < nCand; k += 32) {
+    const int u = unit_of(k);
+    if (U.uRows[u] > 0) S.order[base++] = u;
+  }
+  if (lane == 0) atomicMax(S.nLevels, round);
+}
+
 __global__ void __launch_bounds__(256) k_exec_units(BodyArrays B, UnitArrays U, const int* __restrict__ order, const int* __restrict__ unitLevel) {
   const int nUnits = min(*U.nExec, U.unitCap);
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nUnits; a += gridDim.x * blockDim.x) {
