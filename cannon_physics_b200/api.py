@@ -26,7 +26,7 @@ from . import _ffi as F
 from .engine import Context, DeviceWorld, SceneSpec
 
 __all__ = [
-    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron",
+    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
     "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
     "World",
@@ -142,13 +142,133 @@ class Cylinder(Shape):  # cylinder.dart:15
 class ConvexPolyhedron(Shape):  # convex_polyhedron.dart:51
     type = F.SHAPE_CONVEX
 
-    def __init__(self, vertices, faces, **kw):
+    def __init__(self, vertices, faces, axes=None, **kw):
         super().__init__(**kw)
-        self.vertices = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self.vertices = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)  # Vector3 stores f32
         self.faces = [list(f) for f in faces]
+        self.uniqueAxes = None if axes is None else np.asarray(axes, dtype=np.float32).reshape(-1, 3)  # :105; only its presence is used
 
     def _desc(self):
-        return dict(super()._desc(), vertices=self.vertices, faces=self.faces)
+        return dict(super()._desc(), vertices=self.vertices, faces=self.faces, convex_has_axes=int(self.uniqueAxes is not None))
+
+
+def _ring(radius, y, theta):  # Vector3(-r sin, y, r cos) as cylinder.dart:56,60 / cone.dart:44,49 write it
+    return (-radius * math.sin(theta), y, radius * math.cos(theta))
+
+
+class Cone(ConvexPolyhedron):  # cone.dart:15-63: apex first, then the base ring; side faces + base; `axes` given
+    type = F.SHAPE_CONE
+
+    def __init__(self, radius=1.0, height=1.0, numSegments=8, **kw):
+        if radius < 0:
+            raise ValueError("The cylinder radiusBottom cannot be negative.")  # the reference's message, cone.dart:32
+        self.radius, self.height, self.numSegments = float(radius), float(height), int(numSegments)
+        N = self.numSegments
+        verts = [(0.0, self.height * 0.5, 0.0), _ring(self.radius, -self.height * 0.5, 0.0)]
+        faces, bottom = [], [1]
+        for i in range(N):
+            theta = ((2 * math.pi) / N) * (i + 1)
+            if i < N - 1:
+                verts.append(_ring(self.radius, -self.height * 0.5, theta))
+                bottom.append(i + 2)
+                faces.append([0, i + 2, i + 1])
+            else:
+                faces.append([0, 1, i + 1])
+        faces.append(bottom)
+        super().__init__(verts, faces, axes=[(0, 1, 0)], **kw)
+
+
+class Capsule(ConvexPolyhedron):  # capsule.dart:15-170: cylinder walls + two (numSegments+1) x (numHeightSegments+1) vertex grids
+    type = F.SHAPE_CAPSULE
+
+    def __init__(self, radiusTop=1.0, radiusBottom=1.0, height=1.0, numSegments=8, numHeightSegments=4, **kw):
+        if radiusTop < 0:
+            raise ValueError("The Capsule radiusTop cannot be negative.")
+        if radiusBottom < 0:
+            raise ValueError("The Capsule radiusBottom cannot be negative.")
+        self.radiusTop, self.radiusBottom, self.height = float(radiusTop), float(radiusBottom), float(height)
+        self.numSegments, self.numHeightSegments = int(numSegments), int(numHeightSegments)
+        rt, rb, h, ns, nh = self.radiusTop, self.radiusBottom, self.height, self.numSegments, self.numHeightSegments
+        verts = [_ring(rb, -h * 0.5, 0.0), _ring(rt, h * 0.5, 0.0)]
+        faces, top, bot, grid, index = [], [], [], [], 0
+        phiStart, phiLength, thetaStart, thetaLength = math.pi, 2 * math.pi, math.pi / 2, math.pi / 2
+        for iy in range(nh + 1):
+            row = []
+            v = iy / nh
+            for ix in range(ns + 1):
+                ub, ut = ix / ns, (ns - ix) / ns
+                if iy == 0 and ix < ns:  # the cylinder walls (:72-98)
+                    theta = ((2 * math.pi) / ns) * (ix + 1)
+                    if ix < ns - 1:
+                        verts.append(_ring(rb, -h * 0.5, theta))
+                        verts.append(_ring(rt, h * 0.5, theta))
+                        faces.append([2 * ix, 2 * ix + 1, 2 * ix + 3, 2 * ix + 2])
+                    else:
+                        faces.append([2 * ix, 2 * ix + 1, 1, 0])
+                # hemisphere vertices (:101-121; the `true ||` makes this the only live branch, both caps use radiusTop)
+                st, ct = math.sin(thetaStart + v * thetaLength), math.cos(thetaStart + v * thetaLength)
+                top.append((-rt * math.cos(phiStart + ut * phiLength) * st, h * 0.5 - rt * ct, rt * math.sin(phiStart + ut * phiLength) * st))
+                bot.append((-rt * math.cos(phiStart + ub * phiLength) * st, -h * 0.5 + rt * ct, rt * math.sin(phiStart + ub * phiLength) * st))
+                row.append(index)
+                index += 1
+            grid.append(row)
+        start1, start2 = len(verts), len(verts) + len(top)
+        for iy in range(nh):
+            for ix in range(ns):
+                for start in (start1, start2):  # :150-164, top cap triangle pair then bottom cap pair
+                    a, b = grid[iy][ix + 1] + start, grid[iy][ix] + start
+                    c, d = grid[iy + 1][ix] + start, grid[iy + 1][ix + 1] + start
+                    faces.append([a, b, d])
+                    faces.append([b, c, d])
+        super().__init__(verts + top + bot, faces, **kw)
+
+
+class SizedPlane(ConvexPolyhedron):  # sized_plane.dart:10-37: one quad in the y = 0 plane
+    type = F.SHAPE_SIZED_PLANE
+
+    def __init__(self, width=1.0, height=1.0, **kw):
+        self.width, self.height = float(width), float(height)
+        sx, sz = self.width / 2, self.height / 2
+        super().__init__([(-sx, 0, -sz), (sx, 0, -sz), (sx, 0, sz), (-sx, 0, sz)], [[3, 2, 1, 0]], **kw)
+
+
+class LatheShape(ConvexPolyhedron):  # lathe.dart:6-67: a Vector2 (f32) profile swept around y, two triangles per quad
+    def __init__(self, points, numSegments=8, phiStart=0.0, phiLength=math.pi * 2, **kw):
+        self.points = np.asarray(points, dtype=np.float32).reshape(-1, 2)
+        self.numSegments = int(numSegments)
+        phiLength = min(max(phiLength, 0.0), math.pi * 2)
+        inverseSegments = 1.0 / self.numSegments
+        P = self.points.astype(np.float64)
+        n = len(P)
+        verts, faces = [], []
+        for i in range(self.numSegments + 1):
+            phi = phiStart + i * inverseSegments * phiLength
+            for j in range(n - 1, -1, -1):
+                verts.append((P[j, 0] * math.sin(phi), P[j, 1], P[j, 0] * math.cos(phi)))
+        for i in range(self.numSegments):
+            for j in range(n - 2, -1, -1):
+                base = j + i * n
+                a, b, c, d = base, base + n, base + n + 1, base + 1
+                faces.append([a, b, d])
+                faces.append([c, d, b])
+        super().__init__(verts, faces, **kw)
+
+
+class CapsuleLathe(LatheShape):  # capsule_lathe.dart:14-74: the capsule profile handed to LatheShape, reported as a capsule
+    type = F.SHAPE_CAPSULE
+
+    def __init__(self, radiusTop=1.0, radiusBottom=1.0, height=1.0, numSegments=8, numHeightSegments=4, **kw):
+        self.radiusTop, self.radiusBottom, self.height = float(radiusTop), float(radiusBottom), float(height)
+        rt, rb, h = self.radiusTop, self.radiusBottom, self.height
+        ptsTop, ptsBottom = [(0.0, h * 0.5 + rt)], []
+        for i in range(numHeightSegments - 1):
+            theta = ((math.pi / 2) / numHeightSegments) * (i + 1) + (2 * math.pi + math.pi / 2)
+            ptsTop.append((-math.cos(theta) * rt, h * 0.5 + math.sin(theta) * rt))
+            ptsBottom.insert(0, (-math.cos(theta) * rb, -h * 0.5 - math.sin(theta) * rb))
+        ptsTop.append((rt, h * 0.5))
+        ptsBottom.append((0.0, -h * 0.5 - rb))
+        ptsBottom.insert(0, (rb, -h * 0.5))
+        super().__init__(ptsTop + ptsBottom, numSegments=numSegments, **kw)
 
 
 class Heightfield(Shape):  # heightfield.dart:34

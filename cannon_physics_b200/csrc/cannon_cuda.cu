@@ -544,7 +544,10 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
         w->hHulls.push_back(hull);
         break;
       }
-      case CANNON_SHAPE_CONVEX: {
+      case CANNON_SHAPE_CONVEX:
+      case CANNON_SHAPE_CAPSULE:
+      case CANNON_SHAPE_CONE:
+      case CANNON_SHAPE_SIZED_PLANE: {
         if (d.n_vertices <= 0 || d.n_faces <= 0 || !d.vertices || !d.face_offsets || !d.face_indices)
           return fail(w->ctx, CANNON_E_INVALID, "convex shape needs vertices and faces");
         HostHull hull;
@@ -555,7 +558,7 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
           for (int idx : face) if (idx < 0 || idx >= d.n_vertices) return fail(w->ctx, CANNON_E_INVALID, "convex face index out of range");
           hull.faces.push_back(face);
         }
-        hull.hasAxes = false;  // plain ConvexPolyhedron: no `axes` => no face-normal axes
+        hull.hasAxes = d.convex_has_axes != 0;  // no `axes` => no face-normal axes; Cone passes them
         hull.finish();
         h.hull = (int)w->hHulls.size();
         h.bsr = hull.bsr;
@@ -706,7 +709,10 @@ static void host_shape_aabb(const cannon_world* w, int shapeIdx, const f3& pos, 
       break;
     }
     case CANNON_SHAPE_CONVEX:
-    case CANNON_SHAPE_CYLINDER: {
+    case CANNON_SHAPE_CYLINDER:
+    case CANNON_SHAPE_CAPSULE:
+    case CANNON_SHAPE_CONE:
+    case CANNON_SHAPE_SIZED_PLANE: {
       const HostHull& h = w->hHulls[s.hull];
       for (size_t i = 0; i < h.v.size(); i++) {
         const f3 p = vadd(qrot(q, h.v[i]), pos);

@@ -58,7 +58,10 @@ __device__ inline void shape_aabb(const ShapeTables& T, int shapeIdx, const f3& 
       break;
     }
     case CANNON_SHAPE_CONVEX:
-    case CANNON_SHAPE_CYLINDER: {  // convex_polyhedron.dart:663-703
+    case CANNON_SHAPE_CYLINDER:
+    case CANNON_SHAPE_CAPSULE:
+    case CANNON_SHAPE_CONE:
+    case CANNON_SHAPE_SIZED_PLANE: {  // convex_polyhedron.dart:663-703
       const HullDev h = T.hulls[s.hull];
       for (int i = 0; i < h.nV; i++) {
         f3 w = vadd(qrot(q, ld3(T.verts[h.vOff + i])), pos);

@@ -82,7 +82,7 @@ __device__ __forceinline__ HullView hull_view(const ShapeTables& T, int hull) {
   return H;
 }
 
-__device__ __forceinline__ bool is_hull_type(int t) { return t == CANNON_SHAPE_BOX || t == CANNON_SHAPE_CONVEX || t == CANNON_SHAPE_CYLINDER; }
+__device__ __forceinline__ bool is_hull_type(int t) { return t >= CANNON_SHAPE_BOX && t <= CANNON_SHAPE_SIZED_PLANE; }  // box + the ConvexPolyhedron subclasses
 
 // heightfield index window: sphereHeightfield :1318-1362 / heightfieldConvex :2070-2113 (+ getRectMinMax, heightfield.dart:146-162)
 __device__ inline bool hf_window(const ShapeTables& T, const HfDev& hf, const f3& local, double radius, int& iMinX, int& iMaxX, int& iMinY,
@@ -298,12 +298,13 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
             if (hi == CANNON_SHAPE_SPHERE) code = NP_SS;
             else if (hi == CANNON_SHAPE_PLANE) code = NP_SP;
             else if (hi == CANNON_SHAPE_BOX) code = NP_SB;
-            else if (hi == CANNON_SHAPE_CONVEX || hi == CANNON_SHAPE_CYLINDER) code = NP_SH;
+            else if (is_hull_type(hi)) code = NP_SH;
             else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_SPIL;
           } else if (lo == CANNON_SHAPE_PLANE) {
             if (is_hull_type(hi)) code = NP_PH;
           } else if (is_hull_type(lo)) {
-            if (is_hull_type(hi)) code = NP_HH;
+            // `convexSizedPlane` is the one key of narrow_phase.dart:336-473 that can never match its lower-cased name
+            if (is_hull_type(hi)) code = (lo == CANNON_SHAPE_CONVEX && hi == CANNON_SHAPE_SIZED_PLANE) ? -1 : NP_HH;
             else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_HPIL;
           }
           if (code >= 0) nt = 1;

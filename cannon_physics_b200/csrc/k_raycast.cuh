@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, Ra
       int ord = 0;
       if (s.type == CANNON_SHAPE_SPHERE) ray_sphere(A, L, ray, s.radius, xi, b, ord);
       else if (s.type == CANNON_SHAPE_PLANE) ray_plane(A, L, ray, qi, xi, b, ord);
-      else if (s.hull >= 0) ray_convex(A, L, ray, hull_view(T, s.hull), qi, xi, b, ord);
+      else if (s.type == CANNON_SHAPE_BOX || s.type == CANNON_SHAPE_CONVEX || s.type == CANNON_SHAPE_CYLINDER)  // ray_class.dart:101-123: no other handler
+        ray_convex(A, L, ray, hull_view(T, s.hull), qi, xi, b, ord);
     }
     // the warp's answer: (distance, key) minimum for closest, key minimum for any, key maximum for all / hitFaceIndex
     double dist = L.has ? L.dist : INFINITY;

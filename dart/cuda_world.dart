@@ -32,6 +32,9 @@ int _shapeTypeCode(Shape s) {
     case ShapeType.box: return shapeBox;
     case ShapeType.convex: return shapeConvex;
     case ShapeType.cylinder: return shapeCylinder;
+    case ShapeType.capsule: return shapeCapsule;        // Capsule / CapsuleLathe: the hull their constructor built is passed as is
+    case ShapeType.cone: return shapeCone;
+    case ShapeType.sizedPlane: return shapeSizedPlane;
     case ShapeType.heightfield: return shapeHeightfield;
     default: throw 'CudaSession: shape type ${s.type} is outside the hot-path scope (SURVEY.md 8f)';
   }
@@ -144,6 +147,7 @@ class CudaSession {
           for (var f = 0; f < s.faces.length; f++) { off[f] = o; for (final vi in s.faces[f]) { idx[o++] = vi; } }
           off[s.faces.length] = o;
           r.nVertices = s.vertices.length; r.vertices = v; r.nFaces = s.faces.length; r.faceOffsets = off; r.faceIndices = idx;
+          r.convexHasAxes = s.uniqueAxes != null ? 1 : 0;  // findSeparatingAxis only asks whether axes were given
         }
       }
       check(cuda.worldSetShapes(handle, shapes.length, sd), 'cannon_world_set_shapes');

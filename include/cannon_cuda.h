@@ -51,8 +51,15 @@ extern "C" {
  * shape is passed first to a resolver (lib/world/narrow_phase.dart:706-710). */
 enum {
   CANNON_SHAPE_SPHERE = 0, CANNON_SHAPE_PLANE = 1, CANNON_SHAPE_BOX = 2, CANNON_SHAPE_CONVEX = 3,
-  CANNON_SHAPE_CYLINDER = 4, CANNON_SHAPE_HEIGHTFIELD = 8
+  CANNON_SHAPE_CYLINDER = 4, CANNON_SHAPE_CAPSULE = 5, CANNON_SHAPE_CONE = 6, CANNON_SHAPE_SIZED_PLANE = 7,
+  CANNON_SHAPE_HEIGHTFIELD = 8
 };
+/* CAPSULE / CONE / SIZED_PLANE are ConvexPolyhedron subclasses in the reference
+ * (lib/rigid_body_shapes/{capsule,capsule_lathe,cone,sized_plane}.dart): the binding passes the hull the reference's
+ * own constructor built (vertices, faces, convex_has_axes) exactly like CONVEX; the type only selects the resolver and
+ * which shape a resolver sees first. The table of narrow_phase.dart:336-473 is reproduced as written, including the
+ * pair it cannot reach: its `convexSizedPlane` key is compared with a lower-cased name and never matches, so a plain
+ * CONVEX and a SIZED_PLANE never collide. Rays ignore the three types (ray_class.dart:101-123 has no handler). */
 /* BodyTypes / BodySleepStates, lib/objects/rigid_body.dart:15-16 */
 enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 2 };
 enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };
@@ -149,6 +156,10 @@ typedef struct cannon_shape_desc {
   int32_t hf_nx, hf_ny;
   const double*  hf_data;
   int32_t hf_element_size;       /* int in the reference (heightfield.dart:46) */
+  /* CONVEX / CAPSULE / CONE / SIZED_PLANE: ConvexPolyhedron.uniqueAxes != null (convex_polyhedron.dart:105). Only its
+   * presence matters: findSeparatingAxis (:255,:290) tests the hull's face normals when axes were given and none when
+   * not (its `else if` on the same condition is dead code). Cone passes axes, Capsule / SizedPlane / Lathe do not. */
+  int32_t convex_has_axes;
 } cannon_shape_desc;
 
 /* Body state, structure of arrays. In *_set_bodies a NULL pointer means "reference default"

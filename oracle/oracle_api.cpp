@@ -136,7 +136,10 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
         make_cylinder_hull(d.radius_top, d.radius_bottom, d.height, d.num_segments, s.hull);
         s.boundingSphereRadius = s.hull.boundingSphereRadius;
         break;
-      case CANNON_SHAPE_CONVEX: {
+      case CANNON_SHAPE_CONVEX:
+      case CANNON_SHAPE_CAPSULE:      // ConvexPolyhedron subclasses (capsule.dart, capsule_lathe.dart, cone.dart, sized_plane.dart):
+      case CANNON_SHAPE_CONE:         // the hull arrives as the reference's constructor built it
+      case CANNON_SHAPE_SIZED_PLANE: {
         if (d.n_vertices <= 0 || d.n_faces <= 0 || !d.vertices || !d.face_offsets || !d.face_indices)
           return fail(cw->ctx, CANNON_E_INVALID, "convex shape needs vertices and faces");
         s.hull.vertices.resize(d.n_vertices);
@@ -144,7 +147,7 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
         s.hull.faces.resize(d.n_faces);
         for (int f = 0; f < d.n_faces; f++)
           s.hull.faces[f].assign(d.face_indices + d.face_offsets[f], d.face_indices + d.face_offsets[f + 1]);
-        s.hull.hasUniqueAxes = false;  // plain ConvexPolyhedron: no `axes` => no face-normal axes (§5.9-9)
+        s.hull.hasUniqueAxes = d.convex_has_axes != 0;  // no `axes` => no face-normal axes (§5.9-9); Cone passes them (cone.dart:58-61)
         s.hull.computeNormals();
         s.hull.updateBoundingSphereRadius();
         s.hull.computeEdges();

@@ -648,7 +648,8 @@ struct NP {
         }
   }
 
-  static bool isHullType(int t) { return t == CANNON_SHAPE_BOX || t == CANNON_SHAPE_CONVEX || t == CANNON_SHAPE_CYLINDER; }
+  // box, convex, cylinder, capsule, cone, sizedPlane: every one of them reaches the convex resolvers (narrow_phase.dart:131-184)
+  static bool isHullType(int t) { return t >= CANNON_SHAPE_BOX && t <= CANNON_SHAPE_SIZED_PLANE; }
 
   // dispatch: getCollisionType + operator[] (narrow_phase.dart:116-238,336-489) for the in-scope types.
   // (sa,xa,qa,ba) has the lower ShapeType index; equal types arrive swapped (narrow_phase.dart:706-710).
@@ -659,12 +660,15 @@ struct NP {
       if (tb == CANNON_SHAPE_SPHERE) sphereSphere(sa, sb, xa, xb, ba, bb);
       else if (tb == CANNON_SHAPE_PLANE) spherePlane(sa, sb, xa, xb, qb, ba, bb);
       else if (tb == CANNON_SHAPE_BOX) sphereBox(sa, sb, xa, xb, qb, ba, bb);
-      else if (tb == CANNON_SHAPE_CONVEX || tb == CANNON_SHAPE_CYLINDER) sphereConvex(sa, sb.hull, sb.collisionResponse, xa, xb, qb, ba, bb);
+      else if (isHullType(tb)) sphereConvex(sa, sb.hull, sb.collisionResponse, xa, xb, qb, ba, bb);
       else if (tb == CANNON_SHAPE_HEIGHTFIELD) sphereHeightfield(sa, sb, xa, xb, qb, ba, bb);
     } else if (ta == CANNON_SHAPE_PLANE) {
       if (isHullType(tb)) planeConvex(sa, sb.hull, sb.collisionResponse, xa, xb, qa, qb, ba, bb);
       // plane-plane, plane-heightfield: no resolver
     } else if (isHullType(ta)) {
+      // narrow_phase.dart:448 spells the key "convexSizedPlane"; getCollisionType (:476-479) compares lower-cased names,
+      // so a plain convex against a sized plane finds no resolver
+      if (ta == CANNON_SHAPE_CONVEX && tb == CANNON_SHAPE_SIZED_PLANE) return;
       if (isHullType(tb)) convexConvex(sa.hull, sb.hull, sa.collisionResponse, sb.collisionResponse, xa, xb, qa, qb, ba, bb, nullptr, 0);
       else if (tb == CANNON_SHAPE_HEIGHTFIELD) heightfieldConvex(sa.hull, sa.collisionResponse, sb, xa, xb, qa, qb, ba, bb);
     }

@@ -145,7 +145,10 @@ void shape_world_aabb(const Shape& s, const V3& pos, const Q4& q, V3& mn, V3& mx
       break;
     }
     case CANNON_SHAPE_CONVEX:
-    case CANNON_SHAPE_CYLINDER: {  // convex_polyhedron.dart:663-703
+    case CANNON_SHAPE_CYLINDER:
+    case CANNON_SHAPE_CAPSULE:
+    case CANNON_SHAPE_CONE:
+    case CANNON_SHAPE_SIZED_PLANE: {  // convex_polyhedron.dart:663-703
       bool first = true;
       for (const V3& v : s.hull.vertices) {
         V3 w = add(qvmult(q, v), pos);
