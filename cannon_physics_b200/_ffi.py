@@ -17,7 +17,7 @@ P = C.POINTER
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NOGPU = 0, -1, -2, -3, -4, -5
 
 SHAPE_SPHERE, SHAPE_PLANE, SHAPE_BOX, SHAPE_CONVEX, SHAPE_CYLINDER, SHAPE_HEIGHTFIELD = 0, 1, 2, 3, 4, 8
-SHAPE_CAPSULE, SHAPE_CONE, SHAPE_SIZED_PLANE = 5, 6, 7
+SHAPE_CAPSULE, SHAPE_CONE, SHAPE_SIZED_PLANE, SHAPE_PARTICLE = 5, 6, 7, 9
 BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC = 0, 1, 2
 AWAKE, SLEEPY, SLEEPING = 0, 1, 2
 BP_NAIVE, BP_SAP, BP_GRID = 0, 1, 2

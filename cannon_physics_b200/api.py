@@ -26,7 +26,7 @@ from . import _ffi as F
 from .engine import Context, DeviceWorld, SceneSpec
 
 __all__ = [
-    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe",
+    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
     "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
     "World",
@@ -269,6 +269,10 @@ class CapsuleLathe(LatheShape):  # capsule_lathe.dart:14-74: the capsule profile
         ptsBottom.append((0.0, -h * 0.5 - rb))
         ptsBottom.insert(0, (rb, -h * 0.5))
         super().__init__(ptsTop + ptsBottom, numSegments=numSegments, **kw)
+
+
+class Particle(Shape):  # particle.dart:9: a point (bounding radius 0, zero inertia, AABB = its position)
+    type = F.SHAPE_PARTICLE
 
 
 class Heightfield(Shape):  # heightfield.dart:34

@@ -153,6 +153,10 @@ struct cannon_world {
   DBuf<float4> dVerts, dFnormals, dEdges, dEdgesK;
   DBuf<int> dFacesK;
   DBuf<PillarRec> dPillars;
+  // particleConvex state of the shape table (ShapeTables.pc*): only allocated when a Particle shape exists
+  bool hasParticle = false;
+  DBuf<int> dPcFrozen, dPcFreezeTask;
+  DBuf<float4> dPcPos, dPcQuat;
   DBuf<double> dFplanec, dHfData, dMatFriction, dMatRestitution;
   DBuf<int> dFvOff, dFvIdx, dFcOff, dFcIdx, dCmTable;
   DBuf<HfDev> dHfs;
@@ -309,6 +313,8 @@ static ShapeTables shape_tables(cannon_world* w) {
   T.edgesK = w->dEdgesK.p; T.facesK = w->dFacesK.p; T.pillars = w->dPillars.p;
   T.hfs = w->dHfs.p; T.hfdata = w->dHfData.p; T.cmTable = w->dCmTable.p; T.cms = w->dCms.p;
   T.matFriction = w->dMatFriction.p; T.matRestitution = w->dMatRestitution.p; T.nMat = w->nMat;
+  T.nShapes = (int)w->hShapes.size();
+  T.pcFrozen = w->dPcFrozen.p; T.pcFreezeTask = w->dPcFreezeTask.p; T.pcPos = w->dPcPos.p; T.pcQuat = w->dPcQuat.p;
   return T;
 }
 static int grid_for(cannon_world* w, long long n, int threads) {
@@ -453,7 +459,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(lam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
-  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars);
+  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars); REL(dPcFrozen); REL(dPcFreezeTask); REL(dPcPos); REL(dPcQuat);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
   REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
@@ -523,6 +529,9 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
         break;
       case CANNON_SHAPE_PLANE:
         h.bsr = INFINITY;  // plane.dart:20
+        break;
+      case CANNON_SHAPE_PARTICLE:
+        h.bsr = 0;  // particle.dart:24-26
         break;
       case CANNON_SHAPE_BOX: {
         for (int k = 0; k < 3; k++) h.he[k] = d.half_extents[k];
@@ -667,6 +676,15 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     }
     W_TRY(w, cudaGetLastError());
   }
+  // a new shape table starts with no ConvexPolyhedron.worldVertices computed (convex_polyhedron.dart:101-103)
+  w->hasParticle = false;
+  for (const HostShape& h : w->hShapes) if (h.type == CANNON_SHAPE_PARTICLE) w->hasParticle = true;
+  if (w->hasParticle) {
+    const size_t nt = (size_t)n + (size_t)nPillars;
+    W_TRY(w, w->dPcFrozen.reserve(nt)); W_TRY(w, w->dPcFreezeTask.reserve(nt)); W_TRY(w, w->dPcPos.reserve(nt)); W_TRY(w, w->dPcQuat.reserve(nt));
+    W_TRY(w, cudaMemsetAsync(w->dPcFrozen.p, 0, nt * sizeof(int), s));
+    W_TRY(w, cudaMemsetAsync(w->dPcFreezeTask.p, 0x7f, nt * sizeof(int), s));  // 0x7f7f7f7f: above every task index
+  }
   W_TRY(w, cudaStreamSynchronize(s));
   return CANNON_OK;
 }
@@ -726,6 +744,10 @@ static void host_shape_aabb(const cannon_world* w, int shapeIdx, const f3& pos, 
       }
       break;
     }
+    case CANNON_SHAPE_PARTICLE:  // particle.dart:29-33
+      mn = pos;
+      mx = pos;
+      break;
     default:
       mn.x = mn.y = mn.z = -inf;
       mx.x = mx.y = mx.z = inf;
@@ -1286,6 +1308,12 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
+  if (w->hasParticle) {
+    { g_kernel_launches++; k_np_particle_simple<<<g, 128, 0, s>>>(B, T, A); }
+    { g_kernel_launches++; k_np_particle_hull<0><<<g, 128, 0, s>>>(B, T, A); }
+    { g_kernel_launches++; k_np_particle_hull<1><<<g, 128, 0, s>>>(B, T, A); }
+    { g_kernel_launches++; k_np_particle_hull<2><<<g, 128, 0, s>>>(B, T, A); }
+  }
   W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[0], 0));
   if (hf) {
     W_TRY(w, cudaStreamWaitEvent(s, w->npJoin[1], 0));
@@ -1912,7 +1940,7 @@ static int32_t step_finish(cannon_world* w, int32_t nsteps, bool profiled) {
   w->lastUnits = w->hCnt[CT_NUNITS]; w->lastLevels = w->hCnt[CT_NLEVELS];
   p.n_tasks = w->hCnt[CT_NTASKS];
   p.n_islands = w->hCnt[CT_NISLANDS];
-  for (int t = 0; t < NP_NTYPES; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];
+  for (int t = 0; t < 8; t++) p.n_tasks_by_type[t] = w->hCnt[CT_BUCKETCOUNT + t];  // the four Particle task types are only in n_tasks
   return CANNON_OK;
 }
 

@@ -75,6 +75,10 @@ __device__ inline void shape_aabb(const ShapeTables& T, int shapeIdx, const f3& 
       }
       break;
     }
+    case CANNON_SHAPE_PARTICLE:  // particle.dart:29-33
+      mn = pos;
+      mx = pos;
+      break;
     default:  // heightfield.dart:499-503
       mn.x = mn.y = mn.z = -inf;
       mx.x = mx.y = mx.z = inf;

@@ -11,7 +11,10 @@
 #pragma once
 #include "world.cuh"
 
-enum { NP_SS = 0, NP_SP = 1, NP_SB = 2, NP_SH = 3, NP_PH = 4, NP_HH = 5, NP_SPIL = 6, NP_HPIL = 7, NP_NTYPES = 8 };
+enum { NP_SS = 0, NP_SP = 1, NP_SB = 2, NP_SH = 3, NP_PH = 4, NP_HH = 5, NP_SPIL = 6, NP_HPIL = 7,
+       NP_SPT = 8, NP_PPT = 9, NP_HPT = 10, NP_PILPT = 11,  // sphere / plane / hull / heightfield pillar against a Particle
+       NP_NTYPES = 12 };
+__device__ __forceinline__ bool np_pillar_code(int c) { return c == NP_SPIL || c == NP_HPIL || c == NP_PILPT; }
 #define NP_MAXPOLY 40
 
 struct NpArrays {
@@ -294,7 +297,12 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           int lo = si.type, hi = sj.type;
           first = a; second = b;
           if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
-          if (lo == CANNON_SHAPE_SPHERE) {
+          if (hi == CANNON_SHAPE_PARTICLE) {  // narrow_phase.dart:196-211 (particle-particle has no key)
+            if (lo == CANNON_SHAPE_SPHERE) code = NP_SPT;
+            else if (lo == CANNON_SHAPE_PLANE) code = NP_PPT;
+            else if (is_hull_type(lo)) code = NP_HPT;
+            else if (lo == CANNON_SHAPE_HEIGHTFIELD) { code = NP_PILPT; const int t = first; first = second; second = t; }  // expansion: `first` is the small shape
+          } else if (lo == CANNON_SHAPE_SPHERE) {
             if (hi == CANNON_SHAPE_SPHERE) code = NP_SS;
             else if (hi == CANNON_SHAPE_PLANE) code = NP_SP;
             else if (hi == CANNON_SHAPE_BOX) code = NP_SB;
@@ -308,11 +316,11 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
             else if (hi == CANNON_SHAPE_HEIGHTFIELD) code = NP_HPIL;
           }
           if (code >= 0) nt = 1;
-          if (code == NP_SPIL || code == NP_HPIL) {
+          if (np_pillar_code(code)) {
             const ShapeDev s1 = T.shapes[B.shape[first]], s2 = T.shapes[B.shape[second]];
             const HfDev hf = T.hfs[s2.hf];
             const f3 local = to_local_point(ld3(B.pos[second]), ldq(B.quat[second]), ld3(B.pos[first]));
-            const double radius = code == NP_SPIL ? s1.radius : T.hulls[s1.hull].bsr;
+            const double radius = code == NP_SPIL ? s1.radius : (code == NP_PILPT ? s1.bsr : T.hulls[s1.hull].bsr);
             nt = 0;
             hfPair = hf_window(T, hf, local, radius, iMinX, iMaxX, iMinY, iMaxY) && iMaxX > iMinX && iMaxY > iMinY;
           }
@@ -343,7 +351,8 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
         } else {
           X.rFirst = s1.bsr;
           X.lc = to_local_point(X.xs, X.qs, X.xf);
-          X.margin = fmax(0.0, s1.radius - s1.bsr) + 0.01 * (double)X.hf.esize + 1e-4 * (fabs(W(X.xf.x)) + fabs(W(X.xf.y)) + fabs(W(X.xf.z)) + fabs(W(X.xs.x)) + fabs(W(X.xs.y)) +
+          if (code == NP_PILPT) X.margin = INFINITY;  // heightfieldParticle (:2421-2440) has the bounding gate only
+          else X.margin = fmax(0.0, s1.radius - s1.bsr) + 0.01 * (double)X.hf.esize + 1e-4 * (fabs(W(X.xf.x)) + fabs(W(X.xf.y)) + fabs(W(X.xf.z)) + fabs(W(X.xs.x)) + fabs(W(X.xs.y)) +
                                                          fabs(W(X.xs.z)) + fabs(W(X.lc.x)) + fabs(W(X.lc.y)) + fabs(W(X.lc.z)));
         }
       }
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
     }
     // exclusive prefix of nt inside the lane's type group (heightfield pairs carry several tasks each)
     int before = 0;
-    if (gcode == NP_SPIL || gcode == NP_HPIL) {
+    if (np_pillar_code(gcode)) {
       for (unsigned m = peers; m; m &= m - 1) {  // the same trips for every lane of the group
         const int src = __ffs(m) - 1;
         const int v = __shfl_sync(peers, nt, src);
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
     if (lane == leader) slot = A.bucketStart[gcode] + atomicAdd(&A.bucketCursor[gcode], total);
     slot = __shfl_sync(peers, slot, leader) + before;
     const int off = myOff;
-    if (gcode == NP_SPIL || gcode == NP_HPIL) {
+    if (np_pillar_code(gcode)) {
       for (int t = 0; t < nt; t++) A.bucket[slot + t] = off + t;
     } else {
       A.taskPair[off] = k;
@@ -1160,6 +1169,134 @@ __global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables
   }
 }
 
+// ---- Particle resolvers -------------------------------------------------------------------
+// load_task order: `first` = the sphere / plane / hull / heightfield (lower ShapeType), `second` = the particle.
+// sphereParticle :1258-1294 and planeParticle :1805-1846: one thread per task.
+__global__ void __launch_bounds__(128) k_np_particle_simple(BodyArrays B, ShapeTables T, NpArrays A) {
+  {
+    NP_BUCKET_LOOP(NP_SPT) {
+      TaskCtx c; load_task(B, T, A, NP_TASK(NP_SPT), c);
+      RawOut o; o.A = A; o.task = c.task;
+      f3 normal = vsub(c.xj, c.xi);  // particle - sphere
+      const double lengthSquared = vlen2(normal);
+      const bool hit = lengthSquared <= c.si.radius * c.si.radius;
+      if (!raw_alloc(o, hit ? 1 : 0)) continue;
+      vnormalize(normal);
+      f3 zero; zero.x = zero.y = zero.z = 0.f;
+      raw_put(o, zero, vscale(c.si.radius, normal), vneg(normal));  // ri = particle centre, rj on the sphere, ni = -normal
+    }
+  }
+  {
+    NP_BUCKET_LOOP(NP_PPT) {
+      TaskCtx c; load_task(B, T, A, NP_TASK(NP_PPT), c);
+      RawOut o; o.A = A; o.task = c.task;
+      f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
+      const f3 normal = qrot(ldq(B.quat[c.first]), up);
+      const f3 relpos = vsub(c.xj, ld3(B.pos[c.first]));
+      const bool hit = vdot(normal, relpos) <= 0.0;
+      if (!raw_alloc(o, hit ? 1 : 0)) continue;
+      f3 projected = vscale(vdot(normal, c.xj), normal);
+      projected = vsub(c.xj, projected);
+      f3 zero; zero.x = zero.y = zero.z = 0.f;
+      raw_put(o, zero, projected, vneg(normal));
+    }
+  }
+}
+
+// ConvexPolyhedron.pointIsInside, convex_polyhedron.dart:760-787 (getAveragePointLocal :712-720)
+__device__ inline bool hull_point_inside(const HullView& H, const f3& p) {
+  f3 pointInside; pointInside.x = pointInside.y = pointInside.z = 0.f;
+  for (int i = 0; i < H.nV; i++) pointInside = vadd(pointInside, ld3(H.v[i]));
+  pointInside = vscale(1.0 / (double)H.nV, pointInside);
+  for (int i = 0; i < H.nF; i++) {
+    const f3 n = ld3(H.n[i]);
+    const f3 v = ld3(H.v[H.fvIdx[H.fvOff[i]]]);
+    const double r1 = vdot(n, vsub(p, v));
+    const double r2 = vdot(n, vsub(pointInside, v));
+    if ((r1 < 0 && r2 > 0) || (r1 > 0 && r2 < 0)) return false;
+  }
+  return true;
+}
+
+// particleConvex :2179-2264 / boxParticle :1731 / heightfieldParticle :2343-2444 in three launches over the NP_HPT and
+// NP_PILPT buckets. The reference measures the penetration against worldVertices / worldFaceNormals that it computes
+// on the FIRST penetration a hull object ever sees and never refreshes (:2207-2212), and tasks are resolved in pair
+// order, so: PHASE 0 tests pointIsInside (stateless, local frame) and lets the lowest penetrating task of a not yet
+// frozen target claim it; PHASE 1 freezes the claimed targets at their claimant's pose; PHASE 2 emits the contacts
+// against the frozen poses and clears the claims.
+template <int PHASE>
+__global__ void __launch_bounds__(128) k_np_particle_hull(BodyArrays B, ShapeTables T, NpArrays A) {
+#pragma unroll 1
+  for (int pil = 0; pil < 2; pil++) {
+    const int TYPE = pil ? NP_PILPT : NP_HPT;
+    NP_BUCKET_LOOP(TYPE) {
+      TaskCtx c; load_task(B, T, A, NP_TASK(TYPE), c);
+      HullView H;
+      f3 xh;       // hull position: the body's, or the pillar offset in the world frame
+      int target;
+      if (pil) {
+        const HfDev hf = T.hfs[c.si.hf];
+        const int2 cell = A.taskCell[c.task];
+        const bool upper = (c.info >> 4) & 1;
+        const PillarRec* R = pillar_rec(T, hf, cell.x, cell.y, upper);
+        xh = to_world_point(c.xi, c.qi, ld3(R->off));
+        H = pillar_view_rec(R, upper);
+        target = T.nShapes + (int)(R - T.pillars);
+      } else {
+        H = hull_view(T, c.si.hull);
+        xh = c.xi;
+        target = B.shape[c.first];
+      }
+      const f3 xp = c.xj;  // the particle
+      RawOut o; o.A = A; o.task = c.task;
+      if (PHASE == 0) {
+        // the pillar bounding gate (:2421) was applied when the task was created
+        const bool inside = hull_point_inside(H, qrot(qconj(c.qi), vsub(xp, xh)));
+        A.taskCnt[c.task] = inside ? 1 : 0;  // provisional; PHASE 2 writes the final count
+        if (inside && !T.pcFrozen[target]) atomicMin(&T.pcFreezeTask[target], c.task);
+        continue;
+      }
+      if (A.taskCnt[c.task] == 0) { if (PHASE == 2) raw_alloc(o, 0); continue; }
+      if (PHASE == 1) {
+        if (!T.pcFrozen[target] && T.pcFreezeTask[target] == c.task) {
+          T.pcPos[target] = st3(xh);
+          const q4 q = c.qi;
+          T.pcQuat[target] = make_float4(q.x, q.y, q.z, q.w);
+          __threadfence();
+          T.pcFrozen[target] = 1;
+        }
+        continue;
+      }
+      // PHASE 2
+      if (T.pcFreezeTask[target] == c.task) T.pcFreezeTask[target] = 0x7f7f7f7f;  // the memset pattern of cannon_world_set_shapes
+      const f3 fpos = ld3(T.pcPos[target]);
+      const q4 fq = ldq(T.pcQuat[target]);
+      int penetratedFaceIndex = -1;
+      double minPenetration = 0.0;
+      f3 penetratedFaceNormal; penetratedFaceNormal.x = penetratedFaceNormal.y = penetratedFaceNormal.z = 0.f;
+      for (int i = 0; i < H.nF; i++) {
+        const f3 verts = vadd(fpos, qrot(fq, ld3(H.v[H.fvIdx[H.fvOff[i]]])));  // computeWorldVertices :599-600
+        const f3 normal = qrot(fq, ld3(H.n[i]));                                // computeWorldFaceNormals :642
+        const double penetration = -vdot(normal, vsub(xp, verts));
+        if (penetratedFaceIndex < 0 || fabs(penetration) < fabs(minPenetration)) {
+          minPenetration = penetration;
+          penetratedFaceIndex = i;
+          penetratedFaceNormal = normal;
+        }
+      }
+      if (!raw_alloc(o, penetratedFaceIndex >= 0 ? 1 : 0)) continue;
+      f3 wpv = vscale(minPenetration, penetratedFaceNormal);
+      wpv = vadd(wpv, xp);
+      wpv = vsub(wpv, xh);
+      f3 rj = qrot(c.qi, wpv);  // :2246 rotates the world-frame vector once more
+      f3 ri; ri.x = ri.y = ri.z = 0.f;
+      ri = rel_to_body(ri, xp, xp);
+      rj = rel_to_body(rj, xh, c.xi);
+      raw_put(o, ri, rj, vneg(penetratedFaceNormal));
+    }
+  }
+}
+
 // raw pool -> canonical order + createContactEquation / createFrictionEquationsFromContact parameters
 struct NpWorld {
   double dt;
@@ -1208,9 +1345,11 @@ __global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T
       if (reducedMass > 0) reducedMass = 1 / reducedMass;
       slip = mug * reducedMass;
     }
+    // the particle resolvers hand createContactEquation the particle's body first (narrow_phase.dart:1280,1829,2239)
+    const bool particleFirst = s2.type == CANNON_SHAPE_PARTICLE;
     for (int q = 0; q < m; q++) {
       const int o = dst + q;
-      C.bi[o] = first; C.bj[o] = second;
+      C.bi[o] = particleFirst ? second : first; C.bj[o] = particleFirst ? first : second;
       C.ri[o] = A.rawRi[src + q]; C.rj[o] = A.rawRj[src + q]; C.ni[o] = A.rawNi[src + q];
       C.rest[o] = restitution; C.mu[o] = friction; C.slip[o] = slip;
       C.ca[o] = ca; C.cb[o] = cb; C.ceps[o] = ceps; C.fb[o] = fb; C.feps[o] = feps;

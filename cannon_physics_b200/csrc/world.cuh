@@ -91,6 +91,13 @@ struct ShapeTables {
   const double* matFriction;
   const double* matRestitution;
   int nMat;
+  // particleConvex state (k_narrowphase.cuh, k_np_particle_hull): the pose a hull shape / heightfield pillar was frozen at.
+  // Target t < nShapes is shape t, nShapes + p is pillar p. nullptr unless the shape table holds a Particle.
+  int nShapes;
+  int* pcFrozen;       // 0 until the target's first penetration
+  int* pcFreezeTask;   // lowest task of this step that penetrates a not yet frozen target (0x7f7f7f7f between steps)
+  float4* pcPos;
+  float4* pcQuat;
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ int _shapeTypeCode(Shape s) {
     case ShapeType.cone: return shapeCone;
     case ShapeType.sizedPlane: return shapeSizedPlane;
     case ShapeType.heightfield: return shapeHeightfield;
+    case ShapeType.particle: return shapeParticle;
     default: throw 'CudaSession: shape type ${s.type} is outside the hot-path scope (SURVEY.md 8f)';
   }
 }

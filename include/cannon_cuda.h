@@ -52,14 +52,23 @@ extern "C" {
 enum {
   CANNON_SHAPE_SPHERE = 0, CANNON_SHAPE_PLANE = 1, CANNON_SHAPE_BOX = 2, CANNON_SHAPE_CONVEX = 3,
   CANNON_SHAPE_CYLINDER = 4, CANNON_SHAPE_CAPSULE = 5, CANNON_SHAPE_CONE = 6, CANNON_SHAPE_SIZED_PLANE = 7,
-  CANNON_SHAPE_HEIGHTFIELD = 8
+  CANNON_SHAPE_HEIGHTFIELD = 8, CANNON_SHAPE_PARTICLE = 9
 };
 /* CAPSULE / CONE / SIZED_PLANE are ConvexPolyhedron subclasses in the reference
  * (lib/rigid_body_shapes/{capsule,capsule_lathe,cone,sized_plane}.dart): the binding passes the hull the reference's
  * own constructor built (vertices, faces, convex_has_axes) exactly like CONVEX; the type only selects the resolver and
  * which shape a resolver sees first. The table of narrow_phase.dart:336-473 is reproduced as written, including the
  * pair it cannot reach: its `convexSizedPlane` key is compared with a lower-cased name and never matches, so a plain
- * CONVEX and a SIZED_PLANE never collide. Rays ignore the three types (ray_class.dart:101-123 has no handler). */
+ * CONVEX and a SIZED_PLANE never collide. Rays ignore the three types (ray_class.dart:101-123 has no handler).
+ *
+ * PARTICLE (lib/rigid_body_shapes/particle.dart): a point; sphereParticle / planeParticle / boxParticle / particleConvex /
+ * heightfieldParticle (narrow_phase.dart:1258,1805,1731,2179,2343). Its contacts list the particle's body first.
+ * particleConvex measures the penetration against ConvexPolyhedron.worldVertices / worldFaceNormals, which the reference
+ * computes when their NeedsUpdate flags are set and never invalidates (convex_polyhedron.dart:101-103,603,645;
+ * narrow_phase.dart:2207-2212): every hull Shape (and every cached heightfield pillar, heightfield.dart:285-301) keeps
+ * the pose of the first penetration it ever saw. That state lives with the shape table here as well: it is part of the
+ * world, is cleared by cannon_world_set_shapes, and makes particle-in-hull contacts history dependent exactly as in
+ * the reference. */
 /* BodyTypes / BodySleepStates, lib/objects/rigid_body.dart:15-16 */
 enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 2 };
 enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };

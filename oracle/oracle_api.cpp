@@ -126,6 +126,9 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
       case CANNON_SHAPE_PLANE:
         s.boundingSphereRadius = INFINITY;  // plane.dart:20
         break;
+      case CANNON_SHAPE_PARTICLE:
+        s.boundingSphereRadius = 0;  // particle.dart:24-26
+        break;
       case CANNON_SHAPE_BOX:
         s.halfExtents = V3{d.half_extents[0], d.half_extents[1], d.half_extents[2]};
         make_box_hull(s.halfExtents, s.hull);

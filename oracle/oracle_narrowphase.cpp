@@ -7,7 +7,9 @@
  *   planeConvex/planeBox :1847/:1786, convexConvex/boxBox/boxConvex :1981/:1693/:1713,
  *   heightfieldConvex/boxHeightfield :2044/:1749, _pointInPolygon :2584,
  *   ConvexPolyhedron.findSeparatingAxis :232, testSepAxis :360, project :843, clipAgainstHull :189,
- *   clipFaceAgainstHull :417, clipFaceAgainstPlane :545, Heightfield.getConvexTrianglePillar :330.
+ *   clipFaceAgainstHull :417, clipFaceAgainstPlane :545, Heightfield.getConvexTrianglePillar :330,
+ *   sphereParticle :1258, planeParticle :1805, boxParticle :1731, particleConvex :2179, heightfieldParticle :2343,
+ *   ConvexPolyhedron.pointIsInside :760, getAveragePointLocal :712, computeWorldVertices :590, computeWorldFaceNormals :633.
  */
 #include <algorithm>
 #include <cmath>
@@ -545,6 +547,100 @@ struct NP {
     }
   }
 
+  // sphereParticle, narrow_phase.dart:1258-1294. (sj, xj, bj) = the sphere, (xi, bi) = the particle; the contact's
+  // first body is the PARTICLE's (createContactEquation(bi, bj, ...), :1280).
+  void sphereParticle(const Shape& sj, const Shape& si, V3 xj, V3 xi, int bj, int bi) {
+    V3 normal = sub(xi, xj);
+    const double lengthSquared = length2(normal);
+    if (lengthSquared <= sj.radius * sj.radius) {
+      Eq r = createContactEquation(bi, bj, si.collisionResponse, sj.collisionResponse);
+      normalize(normal);
+      r.rj = normal;
+      r.rj = scale(sj.radius, r.rj);
+      r.ni = neg(normal);
+      r.ri = V3{0, 0, 0};
+      addContact(r);
+    }
+  }
+
+  // planeParticle, narrow_phase.dart:1805-1846
+  void planeParticle(const Shape& sj, const Shape& si, V3 xj, V3 xi, int bj, int bi) {
+    V3 normal = qvmult(w.bodies[bj].quaternion, V3{0, 0, 1});
+    V3 relpos = sub(xi, w.bodies[bj].position);
+    const double d = dot(normal, relpos);
+    if (d <= 0.0) {
+      Eq r = createContactEquation(bi, bj, si.collisionResponse, sj.collisionResponse);
+      r.ni = neg(normal);
+      r.ri = V3{0, 0, 0};
+      V3 projected = scale(dot(normal, xi), normal);
+      projected = sub(xi, projected);
+      r.rj = projected;  // the reference does not subtract the plane position here
+      addContact(r);
+    }
+  }
+
+  // ConvexPolyhedron.pointIsInside, convex_polyhedron.dart:760-787 (with getAveragePointLocal :712-720)
+  static bool pointIsInside(const Hull& h, const V3& p) {
+    V3 pointInside{0, 0, 0};
+    for (const V3& v : h.vertices) pointInside = add(pointInside, v);
+    pointInside = scale(1.0 / (double)h.vertices.size(), pointInside);
+    for (size_t i = 0; i < h.faces.size(); i++) {
+      const V3& n = h.faceNormals[i];
+      const V3& v = h.vertices[h.faces[i][0]];
+      const V3 vToP = sub(p, v);
+      const double r1 = dot(n, vToP);
+      const V3 vToPointInside = sub(pointInside, v);
+      const double r2 = dot(n, vToPointInside);
+      if ((r1 < 0 && r2 > 0) || (r1 > 0 && r2 < 0)) return false;
+    }
+    return true;
+  }
+
+  // particleConvex, narrow_phase.dart:2179-2264. (sj, xj, qj, bj) = the hull, (xi, bi) = the particle. The world
+  // vertices / normals are those frozen in `wv` / `wn` (computed on the first penetration of this hull object).
+  void particleConvex(const Hull& sj, bool crHull, bool crParticle, std::vector<V3>& wv, std::vector<V3>& wn, bool& needsUpdate, V3 xj, V3 xi, Q4 qj,
+                      int bj, int bi) {
+    V3 local = sub(xi, xj);
+    local = qvmult(qconj(qj), local);
+    if (!pointIsInside(sj, local)) return;
+    if (needsUpdate) {  // computeWorldVertices :590-604 + computeWorldFaceNormals :633-646; never invalidated afterwards
+      wv.resize(sj.vertices.size());
+      for (size_t i = 0; i < sj.vertices.size(); i++) wv[i] = add(xj, qvmult(qj, sj.vertices[i]));
+      wn.resize(sj.faceNormals.size());
+      for (size_t i = 0; i < sj.faceNormals.size(); i++) wn[i] = qvmult(qj, sj.faceNormals[i]);
+      needsUpdate = false;
+    }
+    int penetratedFaceIndex = -1;
+    V3 penetratedFaceNormal{0, 0, 0};
+    double minPenetration = 0;
+    bool have = false;
+    for (size_t i = 0; i < sj.faces.size(); i++) {
+      const V3& verts = wv[sj.faces[i][0]];
+      const V3& normal = wn[i];
+      const V3 v2p = sub(xi, verts);
+      const double penetration = -dot(normal, v2p);
+      if (!have || std::fabs(penetration) < std::fabs(minPenetration)) {
+        have = true;
+        minPenetration = penetration;
+        penetratedFaceIndex = (int)i;
+        penetratedFaceNormal = normal;
+      }
+    }
+    if (penetratedFaceIndex != -1) {
+      Eq r = createContactEquation(bi, bj, crParticle, crHull);
+      V3 worldPenetrationVec = scale(minPenetration, penetratedFaceNormal);
+      worldPenetrationVec = add(worldPenetrationVec, xi);
+      worldPenetrationVec = sub(worldPenetrationVec, xj);
+      r.rj = worldPenetrationVec;
+      r.rj = qvmult(qj, r.rj);  // :2246 rotates the world-frame vector once more
+      r.ni = neg(penetratedFaceNormal);
+      r.ri = V3{0, 0, 0};
+      r.ri = rel(r.ri, xi, w.bodies[bi].position);
+      r.rj = rel(r.rj, xj, w.bodies[bj].position);
+      addContact(r);
+    }
+  }
+
   // Heightfield.getConvexTrianglePillar, heightfield.dart:330-487
   static void pillar(const Shape& hf, int xi, int yi, bool upper, Hull& result, V3& offset) {
     const double es = hf.elementSize;
@@ -648,14 +744,47 @@ struct NP {
         }
   }
 
+  // heightfieldParticle, narrow_phase.dart:2343-2444. (si, xi, qi, bi) = the heightfield, (xj, bj) = the particle.
+  void heightfieldParticle(Shape& si, const Shape& sj, V3 xi, V3 xj, Q4 qi, int bi, int bj) {
+    const double radius = sj.boundingSphereRadius;
+    V3 local = point_to_local_frame(xi, qi, xj);
+    int iMinX, iMaxX, iMinY, iMaxY;
+    if (!hfWindow(si, local, radius, iMinX, iMaxX, iMinY, iMaxY)) return;
+    Hull pc;
+    V3 po;
+    for (int i = iMinX; i < iMaxX; i++)
+      for (int j = iMinY; j < iMaxY; j++)
+        for (int up = 0; up < 2; up++) {
+          pillar(si, i, j, up != 0, pc, po);
+          V3 worldPillarOffset = point_to_world_frame(xi, qi, po);
+          if (distance_to(xj, worldPillarOffset) < pc.boundingSphereRadius) {
+            manifold++;
+            const long long key = (((long long)i * si.ny + j) << 1) | up;
+            auto it = si.pillarWorld.find(key);
+            bool needsUpdate = it == si.pillarWorld.end();
+            Shape::PillarWorld fresh;
+            Shape::PillarWorld& pw = needsUpdate ? fresh : it->second;
+            particleConvex(pc, true, sj.collisionResponse, pw.worldVertices, pw.worldFaceNormals, needsUpdate, worldPillarOffset, xj, qi, bi, bj);
+            if (it == si.pillarWorld.end() && !needsUpdate) si.pillarWorld[key] = fresh;
+          }
+        }
+  }
+
   // box, convex, cylinder, capsule, cone, sizedPlane: every one of them reaches the convex resolvers (narrow_phase.dart:131-184)
   static bool isHullType(int t) { return t >= CANNON_SHAPE_BOX && t <= CANNON_SHAPE_SIZED_PLANE; }
 
   // dispatch: getCollisionType + operator[] (narrow_phase.dart:116-238,336-489) for the in-scope types.
   // (sa,xa,qa,ba) has the lower ShapeType index; equal types arrive swapped (narrow_phase.dart:706-710).
-  void resolve(const Shape& sa, const Shape& sb, V3 xa, V3 xb, Q4 qa, Q4 qb, int ba, int bb) {
+  void resolve(Shape& sa, Shape& sb, V3 xa, V3 xb, Q4 qa, Q4 qb, int ba, int bb) {
     const int ta = sa.type, tb = sb.type;
     manifold++;
+    if (tb == CANNON_SHAPE_PARTICLE) {  // narrow_phase.dart:196-211; particle-particle has no key
+      if (ta == CANNON_SHAPE_SPHERE) sphereParticle(sa, sb, xa, xb, ba, bb);
+      else if (ta == CANNON_SHAPE_PLANE) planeParticle(sa, sb, xa, xb, ba, bb);
+      else if (isHullType(ta)) particleConvex(sa.hull, sa.collisionResponse, sb.collisionResponse, sa.hull.worldVertices, sa.hull.worldFaceNormals, sa.hull.worldNeedsUpdate, xa, xb, qa, ba, bb);
+      else if (ta == CANNON_SHAPE_HEIGHTFIELD) heightfieldParticle(sa, sb, xa, xb, qa, ba, bb);
+      return;
+    }
     if (ta == CANNON_SHAPE_SPHERE) {
       if (tb == CANNON_SHAPE_SPHERE) sphereSphere(sa, sb, xa, xb, ba, bb);
       else if (tb == CANNON_SHAPE_PLANE) spherePlane(sa, sb, xa, xb, qb, ba, bb);
@@ -703,8 +832,8 @@ void World::getContacts() {
                           (A.type == CANNON_BODY_STATIC && B.type == CANNON_BODY_KINEMATIC) ||
                           (A.type == CANNON_BODY_KINEMATIC && B.type == CANNON_BODY_KINEMATIC);
     if (A.shape < 0 || B.shape < 0) continue;
-    const Shape& si = shapes[A.shape];
-    const Shape& sj = shapes[B.shape];
+    Shape& si = shapes[A.shape];
+    Shape& sj = shapes[B.shape];
     // shapeOrientation = identity, shapeOffset = 0: qi = bodyQ (x) identity and xi = bodyQ*0 + pos are exact
     Q4 qi = qmul(A.quaternion, Q4{0, 0, 0, 1});
     V3 xi = add(qvmult(A.quaternion, V3{0, 0, 0}), A.position);

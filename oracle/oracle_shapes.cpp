@@ -162,6 +162,10 @@ void shape_world_aabb(const Shape& s, const V3& pos, const Q4& q, V3& mn, V3& mx
       }
       break;
     }
+    case CANNON_SHAPE_PARTICLE:  // particle.dart:29-33
+      mn = pos;
+      mx = pos;
+      break;
     case CANNON_SHAPE_HEIGHTFIELD:  // heightfield.dart:499-503
     default:
       mn = V3{-inf, -inf, -inf};

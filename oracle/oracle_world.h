@@ -4,6 +4,7 @@
  * World) closely on purpose: the product uses a completely different (SoA, device) layout.
  */
 #pragma once
+#include <map>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,11 @@ struct Hull {
   void computeEdges();
   void updateBoundingSphereRadius();
   double planeConstantOfFace(int f) const;
+  // worldVertices / worldFaceNormals with their NeedsUpdate flags (convex_polyhedron.dart:55-58,101-103): only
+  // particleConvex reads them (narrow_phase.dart:2207-2218) and nothing ever sets the flags back to true, so they hold
+  // the pose of the FIRST penetration this ConvexPolyhedron object ever saw
+  bool worldNeedsUpdate = true;
+  std::vector<V3> worldVertices, worldFaceNormals;
 };
 
 struct Shape {
@@ -39,6 +45,10 @@ struct Shape {
   std::vector<double> data;
   double minValue = 0, maxValue = 0;
   double h(int i, int j) const { return data[(size_t)i * ny + j]; }
+  // Heightfield._cachedPillars (heightfield.dart:52,285-301; cacheEnabled = true): one ConvexPolyhedron object per
+  // (xi, yi, upper), kept for the life of the shape. Only the frozen world geometry of particleConvex is state.
+  struct PillarWorld { std::vector<V3> worldVertices, worldFaceNormals; };
+  std::map<long long, PillarWorld> pillarWorld;
 };
 
 struct Body {
