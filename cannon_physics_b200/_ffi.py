@@ -163,6 +163,7 @@ PROTOTYPES = {
     "cannon_world_destroy": (None, [VP]),
     "cannon_world_set_materials": (c_i32, [VP, c_i32, P(c_f64), P(c_f64), c_i32, P(ContactMaterialPOD)]),
     "cannon_world_set_shapes": (c_i32, [VP, c_i32, P(ShapeDesc)]),
+    "cannon_world_set_body_shapes": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_f32), P(c_f32)]),
     "cannon_world_set_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_get_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_set_constraints": (c_i32, [VP, c_i32, P(ConstraintDesc)]),

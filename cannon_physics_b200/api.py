@@ -306,6 +306,8 @@ class Body:  # lib/objects/rigid_body.dart:26-86
         self.fixedRotation, self.isTrigger = fixedRotation, isTrigger
         self.collisionFilterGroup, self.collisionFilterMask, self.collisionResponse = collisionFilterGroup, collisionFilterMask, collisionResponse
         self.shapes: List[Shape] = []
+        self.shapeOffsets: List[np.ndarray] = []       # rigid_body.dart:98-104
+        self.shapeOrientations: List[np.ndarray] = []
         self.world: Optional["World"] = None
         self.index = -1
         self.timeLastSleepy = 0.0      # rigid_body.dart:130; World.addBody sets it to world.time (world_class.dart:291)
@@ -314,14 +316,10 @@ class Body:  # lib/objects/rigid_body.dart:26-86
             self.addShape(shape)
 
     def addShape(self, shape: Shape, offset=None, orientation=None) -> "Body":  # rigid_body.dart:348-369
-        if self.shapes:
-            raise CannonError(F.E_UNSUPPORTED, "compound bodies are outside the hot-path scope (SURVEY.md §8f)")
-        if offset is not None and np.any(np.asarray(offset) != 0):
-            raise CannonError(F.E_UNSUPPORTED, "shape offsets are outside the hot-path scope (SURVEY.md §8f)")
-        if orientation is not None and np.any(np.asarray(orientation, dtype=np.float32) != np.array([0, 0, 0, 1], np.float32)):
-            raise CannonError(F.E_UNSUPPORTED, "shape orientations are outside the hot-path scope (SURVEY.md §8f)")
         self._before_write()
         self.shapes.append(shape)
+        self.shapeOffsets.append(np.zeros(3, np.float32) if offset is None else np.asarray(offset, dtype=np.float32).copy())
+        self.shapeOrientations.append(np.array([0, 0, 0, 1], np.float32) if orientation is None else np.asarray(orientation, dtype=np.float32).copy())
         self._invInertia = None  # addShape recomputes the mass properties (rigid_body.dart:362)
         if self.world is not None:
             self.world._structure_dirty = True
@@ -712,6 +710,7 @@ class World:  # lib/world/world_class.dart:44
             "collision_response": np.zeros(n, np.uint8), "is_trigger": np.zeros(n, np.uint8), "material": np.zeros(n, np.int32),
             "shape": np.zeros(n, np.int32), "time_last_sleepy": np.zeros(n),
         }
+        inst_first, inst_shape, inst_off, inst_ori = [0], [], [], []
         for i, body in enumerate(self.bodies):
             b["position"][i], b["quaternion"][i], b["velocity"][i] = body.position, body.quaternion, body.velocity
             b["angular_velocity"][i], b["force"][i], b["torque"][i] = body.angularVelocity, body.force, body.torque
@@ -723,14 +722,15 @@ class World:  # lib/world/world_class.dart:44
             b["collision_response"][i], b["is_trigger"][i] = body.collisionResponse, body.isTrigger
             b["material"][i] = mat_index(body.material)
             b["time_last_sleepy"][i] = body.timeLastSleepy
-            if body.shapes:
-                sh = body.shapes[0]
+            for k, sh in enumerate(body.shapes):
                 if id(sh) not in shape_ids:
                     shape_ids[id(sh)] = len(shapes)
                     shapes.append(sh._desc())
-                b["shape"][i] = shape_ids[id(sh)]
-            else:
-                b["shape"][i] = -1
+                inst_shape.append(shape_ids[id(sh)])
+                inst_off.append(body.shapeOffsets[k])
+                inst_ori.append(body.shapeOrientations[k])
+            inst_first.append(len(inst_shape))
+            b["shape"][i] = inst_shape[inst_first[i]] if body.shapes else -1
         bp = self.broadphase
         desc = dict(gravity=self.gravity, allow_sleep=int(self.allowSleep), quat_normalize_skip=self.quatNormalizeSkip,
                     quat_normalize_fast=int(self.quatNormalizeFast), solver_kind=self.solver.kind, solver_iterations=self.solver.iterations,
@@ -755,7 +755,12 @@ class World:  # lib/world/world_class.dart:44
             if id(c.bodyA) not in idx or id(c.bodyB) not in idx:
                 raise CannonError(F.E_INVALID, "a constraint or spring references a body that is not in the world (remove it first)")
         cons = [c._desc(idx) for c in self.constraints]
-        return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n,
+        # the shape table is only needed when some body is not "one shape at its origin"
+        plain = all(len(body.shapes) == 1 and not np.any(body.shapeOffsets[0] != 0) and np.array_equal(body.shapeOrientations[0], np.array([0, 0, 0, 1], np.float32))
+                    for body in self.bodies if True) if self.bodies else True
+        body_shapes = None if plain else dict(first=np.array(inst_first, np.int32), shape=np.array(inst_shape, np.int32),
+                                              offset=np.array(inst_off, np.float32).reshape(-1, 3), orientation=np.array(inst_ori, np.float32).reshape(-1, 4))
+        return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n, body_shapes=body_shapes,
                          material_friction=np.array([m.friction for m in mats], dtype=np.float64) if mats else None,
                          material_restitution=np.array([m.restitution for m in mats], dtype=np.float64) if mats else None,
                          contact_materials=cms, constraints=cons, springs=[sp._desc(idx) for sp in self.springs], name="api_world")
@@ -888,7 +893,7 @@ class World:  # lib/world/world_class.dart:44
         result.rayFromWorld[:], result.rayToWorld[:] = from_, to
         result.hasHit = True
         result.body = self.bodies[int(r["body"][k])]
-        result.shape = result.body.shapes[0]
+        result.shape = result.body.shapes[0] if len(result.body.shapes) == 1 else None  # the ABI reports the body, not which of its shapes
         result.hitFaceIndex, result.distance = int(r["hit_face_index"][k]), float(r["distance"][k])
         result.hitPointWorld[:], result.hitNormalWorld[:] = r["hit_point_world"][k], r["hit_normal_world"][k]
 

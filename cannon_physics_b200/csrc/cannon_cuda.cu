@@ -31,7 +31,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NROWS_PAD, CT_NCLIP0, CT_NCLIP1, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NROWS_PAD, CT_NCLIP0, CT_NCLIP1, CT_NPPAIRS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -137,6 +137,14 @@ struct cannon_world {
   std::vector<double> hHfData;
   std::vector<double> hLdamp, hAdamp;
   std::vector<int> hBig, hBigWorldStart, hWorldStart;
+  // compound bodies (cannon_world_set_body_shapes): the table as given, and what cannon_world_set_bodies made of it
+  std::vector<int> hInstFirst, hInstShape, hInstBody;
+  std::vector<float4> hInstOff, hInstQuat;
+  bool compound = false;  // some body has != 1 shape, or a shape away from the body origin / rotated against it
+  int nInst = 0, maxInst = 1, ppCap = 0;
+  DBuf<int> dInstFirst, dInstShape, dInstBody, pxType, pxFlags, pxMaterial, pp1, pp2, ppCnt, ppOff, ppPer;
+  DBuf<float4> dInstOff, dInstQuat, pxPos, pxQuat;
+  DBuf<double> pxInvMass;
   int maxWorldBodies = 0;  // largest world of a batch (chooses the all-pairs broadphase for small worlds)
   bool hasOversizeHull = false;  // some hull exceeds the tile kernel's scratch: run the sequential SAT kernels for those tasks
   double cell = 1.0;
@@ -304,6 +312,16 @@ static BodyArrays body_arrays(cannon_world* w) {
   B.ldpow = w->ldpow.p; B.adpow = w->adpow.p; B.sleepSpeed = w->sleepSpeed.p; B.sleepTime = w->sleepTime.p; B.tLastSleepy = w->tLastSleepy.p;
   B.type = w->type.p; B.sleep = w->sleep.p; B.shape = w->shape.p; B.material = w->material.p; B.group = w->group.p; B.mask = w->mask.p;
   B.world = w->world.p; B.flags = w->flags.p;
+  B.bpos = w->pos.p; B.bquat = w->quat.p; B.owner = nullptr;
+  return B;
+}
+// what the narrowphase kernels see: the bodies, or the shape instances of a world with compound bodies
+static BodyArrays np_body_arrays(cannon_world* w) {
+  BodyArrays B = body_arrays(w);
+  if (w->compound) {
+    B.pos = w->pxPos.p; B.quat = w->pxQuat.p; B.shape = w->dInstShape.p; B.type = w->pxType.p; B.flags = w->pxFlags.p;
+    B.material = w->pxMaterial.p; B.invMass = w->pxInvMass.p; B.owner = w->dInstBody.p;
+  }
   return B;
 }
 static ShapeTables shape_tables(cannon_world* w) {
@@ -313,6 +331,7 @@ static ShapeTables shape_tables(cannon_world* w) {
   T.edgesK = w->dEdgesK.p; T.facesK = w->dFacesK.p; T.pillars = w->dPillars.p;
   T.hfs = w->dHfs.p; T.hfdata = w->dHfData.p; T.cmTable = w->dCmTable.p; T.cms = w->dCms.p;
   T.matFriction = w->dMatFriction.p; T.matRestitution = w->dMatRestitution.p; T.nMat = w->nMat;
+  T.instFirst = w->compound ? w->dInstFirst.p : nullptr; T.instShape = w->dInstShape.p; T.instOff = w->dInstOff.p; T.instQuat = w->dInstQuat.p;
   T.nShapes = (int)w->hShapes.size();
   T.pcFrozen = w->dPcFrozen.p; T.pcFreezeTask = w->dPcFreezeTask.p; T.pcPos = w->dPcPos.p; T.pcQuat = w->dPcQuat.p;
   return T;
@@ -459,7 +478,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(lam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
-  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars); REL(dPcFrozen); REL(dPcFreezeTask); REL(dPcPos); REL(dPcQuat);
+  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars); REL(dInstFirst); REL(dInstShape); REL(dInstBody); REL(pxType); REL(pxFlags); REL(pxMaterial); REL(pp1); REL(pp2); REL(ppCnt); REL(ppOff); REL(ppPer); REL(dInstOff); REL(dInstQuat); REL(pxPos); REL(pxQuat); REL(pxInvMass); REL(dPcFrozen); REL(dPcFreezeTask); REL(dPcPos); REL(dPcQuat);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
   REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
@@ -759,13 +778,18 @@ static int32_t ensure_capacities(cannon_world* w) {
   const int n = w->n;
   const int pairCap = w->desc.max_pairs > 0 ? w->desc.max_pairs : std::max(4096, 24 * n);
   const int contactCap = w->desc.max_contacts > 0 ? w->desc.max_contacts : std::max(4096, 32 * n);
-  const int taskCap = std::max(2 * pairCap, 48 * n);
+  // compound bodies: the narrowphase pairs are shape-instance pairs
+  long long ppc = w->compound ? (long long)pairCap * w->maxInst : pairCap;
+  const int npPairCap = (int)std::min<long long>(ppc, 1 << 28);
+  w->ppCap = w->compound ? npPairCap : 0;
+  const int taskCap = std::max(2 * npPairCap, 48 * std::max(n, w->nInst));
   const int rowCap = 3 * contactCap + w->nJointAccepted + 16;
   w->pairCap = pairCap; w->contactCap = contactCap; w->taskCap = taskCap; w->rowCap = rowCap;
   w->maxLevels = std::min(rowCap, 1 << 20);
 #define RES(buf, cnt) W_TRY(w, w->buf.reserve((size_t)(cnt)))
   RES(p1, pairCap); RES(p2, pairCap); RES(q1, pairCap); RES(q2, pairCap); RES(keep, pairCap); RES(keepOff, pairCap);
-  RES(pairTasks, pairCap); RES(pairTaskOff, pairCap); RES(pairMask, pairCap);
+  RES(pairTasks, npPairCap); RES(pairTaskOff, npPairCap); RES(pairMask, npPairCap);
+  if (w->compound) { RES(pp1, npPairCap); RES(pp2, npPairCap); RES(ppPer, npPairCap); RES(ppCnt, pairCap); RES(ppOff, pairCap); }
   RES(taskPair, taskCap); RES(taskInfo, taskCap); RES(taskCell, taskCap); RES(bucket, taskCap); RES(taskCnt, taskCap); RES(taskRaw, taskCap);
   RES(taskOff, taskCap);
   RES(rawRi, contactCap); RES(rawRj, contactCap); RES(rawNi, contactCap);
@@ -803,6 +827,26 @@ static int32_t ensure_capacities(cannon_world* w) {
   return CANNON_OK;
 }
 
+int32_t cannon_world_set_body_shapes(cannon_world* w, int32_t n_bodies, const int32_t* first, const int32_t* shape, const float* offset,
+                                     const float* orientation) {
+  if (!w || n_bodies < 0) return CANNON_E_INVALID;
+  w->hInstFirst.clear(); w->hInstShape.clear(); w->hInstOff.clear(); w->hInstQuat.clear();
+  if (n_bodies == 0) return CANNON_OK;
+  if (!first || first[0] != 0) return fail(w->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: first[0] must be 0");
+  for (int b = 0; b < n_bodies; b++) if (first[b + 1] < first[b]) return fail(w->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: first[] must ascend");
+  const int ni = first[n_bodies];
+  if (ni > 0 && !shape) return fail(w->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: shape[] missing");
+  for (int k = 0; k < ni; k++) {
+    if (shape[k] < 0 || shape[k] >= (int)w->hShapes.size()) return fail(w->ctx, CANNON_E_INVALID, "body references unknown shape");
+    w->hInstShape.push_back(shape[k]);
+    w->hInstOff.push_back(offset ? make_float4(offset[3 * k], offset[3 * k + 1], offset[3 * k + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+    w->hInstQuat.push_back(orientation ? make_float4(orientation[4 * k], orientation[4 * k + 1], orientation[4 * k + 2], orientation[4 * k + 3])
+                                       : make_float4(0.f, 0.f, 0.f, 1.f));
+  }
+  w->hInstFirst.assign(first, first + n_bodies + 1);
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || !sb || sb->n < 0) return CANNON_E_INVALID;
@@ -819,6 +863,25 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   };
   double radSum = 0;
   int radCnt = 0;
+  const bool haveTable = !w->hInstFirst.empty();
+  if (haveTable && (int)w->hInstFirst.size() != n + 1) return fail(w->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes described another body count");
+  w->compound = false;
+  w->nInst = 0;
+  w->maxInst = 1;
+  if (haveTable) {
+    w->nInst = w->hInstFirst[n];
+    w->hInstBody.assign(w->nInst, 0);
+    for (int i = 0; i < n; i++) {
+      const int c = w->hInstFirst[i + 1] - w->hInstFirst[i];
+      if (c != 1) w->compound = true;
+      w->maxInst = std::max(w->maxInst, c);
+      for (int k = w->hInstFirst[i]; k < w->hInstFirst[i + 1]; k++) w->hInstBody[k] = i;
+    }
+    for (int k = 0; k < w->nInst; k++) {
+      const float4 o = w->hInstOff[k], q = w->hInstQuat[k];
+      if (o.x != 0.f || o.y != 0.f || o.z != 0.f || q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 1.f) w->compound = true;
+    }
+  }
   for (int i = 0; i < n; i++) {
     pos[i] = g3(sb->position, i, 0, 0, 0);
     quat[i] = sb->quaternion ? make_float4(sb->quaternion[4 * i], sb->quaternion[4 * i + 1], sb->quaternion[4 * i + 2], sb->quaternion[4 * i + 3])
@@ -842,6 +905,7 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
     mask[i] = sb->collision_filter_mask ? sb->collision_filter_mask[i] : -1;
     material[i] = sb->material ? sb->material[i] : -1;
     shape[i] = sb->shape ? sb->shape[i] : -1;
+    if (haveTable) shape[i] = w->hInstFirst[i + 1] > w->hInstFirst[i] ? w->hInstShape[w->hInstFirst[i]] : -1;  // shapes[0]
     world[i] = sb->world_id ? sb->world_id[i] : 0;
     if (shape[i] >= (int)w->hShapes.size()) return fail(w->ctx, CANNON_E_INVALID, "body references unknown shape");
     if (material[i] >= w->nMat) return fail(w->ctx, CANNON_E_INVALID, "body references unknown material");
@@ -858,7 +922,18 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
     f3 mn, mx;
     const f3 p = ld3(pos[i]);
     const q4 q = ldq(quat[i]);
-    host_shape_aabb(w, shape[i], p, q, mn, mx);
+    if (w->compound) {  // Body.updateAABB over the instances, rigid_body.dart:415-447
+      for (int k = w->hInstFirst[i]; k < w->hInstFirst[i + 1]; k++) {
+        const f3 offset = vadd(qrot(q, ld3(w->hInstOff[k])), p);
+        const q4 orientation = qmul(q, ldq(w->hInstQuat[k]));
+        f3 lo, hi;
+        host_shape_aabb(w, w->hInstShape[k], offset, orientation, lo, hi);
+        if (k == w->hInstFirst[i]) { mn = lo; mx = hi; continue; }
+        mn.x = fminf(mn.x, lo.x); mn.y = fminf(mn.y, lo.y); mn.z = fminf(mn.z, lo.z);
+        mx.x = fmaxf(mx.x, hi.x); mx.y = fmaxf(mx.y, hi.y); mx.z = fmaxf(mx.z, hi.z);
+      }
+      if (shape[i] < 0) { mn = p; mx = p; }
+    } else host_shape_aabb(w, shape[i], p, q, mn, mx);
     f3 he = mk3((W(mx.x) - W(mn.x)) / 2, (W(mx.y) - W(mn.y)) / 2, (W(mx.z) - W(mn.z)) / 2);
     if (shape[i] < 0) { he.x = he.y = he.z = 0.f; }
     const double m = mass[i], ex = W(he.x), ey = W(he.y), ez = W(he.z);
@@ -871,6 +946,13 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
     inertia_world(q, iI, iiw0[i], iiw1[i], iiw2[i]);  // updateInertiaWorld(true)
     // Body.updateBoundingRadius, rigid_body.dart:395-412 (zero shape offset)
     brad[i] = shape[i] >= 0 ? 0.0 + w->hShapes[shape[i]].bsr : 0.0;
+    if (w->compound) {
+      brad[i] = 0.0;
+      for (int k = w->hInstFirst[i]; k < w->hInstFirst[i + 1]; k++) {
+        const double r = vlen(ld3(w->hInstOff[k])) + w->hShapes[w->hInstShape[k]].bsr;
+        if (r > brad[i]) brad[i] = r;
+      }
+    }
     if (brad[i] < 0) brad[i] = 0;
     if (std::isfinite(brad[i])) { radSum += brad[i]; radCnt++; }
     flags[i] = fl;
@@ -918,6 +1000,13 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   W_TRY(w, upload(w->world, world, s)); W_TRY(w, upload(w->flags, flags, s));
   W_TRY(w, upload(w->bigList, w->hBig, s)); W_TRY(w, upload(w->bigWorldStart, w->hBigWorldStart, s));
   W_TRY(w, upload(w->worldStart, w->hWorldStart, s));
+  if (w->compound) {
+    W_TRY(w, upload(w->dInstFirst, w->hInstFirst, s)); W_TRY(w, upload(w->dInstShape, w->hInstShape, s)); W_TRY(w, upload(w->dInstBody, w->hInstBody, s));
+    W_TRY(w, upload(w->dInstOff, w->hInstOff, s)); W_TRY(w, upload(w->dInstQuat, w->hInstQuat, s));
+    const size_t ni = (size_t)std::max(w->nInst, 1);
+    W_TRY(w, w->pxPos.reserve(ni)); W_TRY(w, w->pxQuat.reserve(ni)); W_TRY(w, w->pxType.reserve(ni)); W_TRY(w, w->pxFlags.reserve(ni));
+    W_TRY(w, w->pxMaterial.reserve(ni)); W_TRY(w, w->pxInvMass.reserve(ni));
+  }
   const size_t nn = (size_t)std::max(n, 1);
   W_TRY(w, w->nbCache.reserve((size_t)nn * BP_CACHE + 4)); W_TRY(w, w->cellc.reserve(nn)); W_TRY(w, w->smeta.reserve(nn)); W_TRY(w, w->scell.reserve(nn)); W_TRY(w, w->binLo.reserve(nn));
   W_TRY(w, w->binHi.reserve(nn)); W_TRY(w, w->skey.reserve(nn)); W_TRY(w, w->sval.reserve(nn)); W_TRY(w, w->sapKey.reserve(nn));
@@ -1247,6 +1336,7 @@ static NpArrays np_arrays(cannon_world* w) {
   NpArrays A;
   int* cnt = w->cnt.p;
   A.p1 = w->p1.p; A.p2 = w->p2.p; A.nPairs = cnt + CT_NPAIRS;
+  if (w->compound) { A.p1 = w->pp1.p; A.p2 = w->pp2.p; A.nPairs = cnt + CT_NPPAIRS; }
   A.pairTasks = w->pairTasks.p; A.pairTaskOff = w->pairTaskOff.p; A.pairMask = w->pairMask.p; A.nTasks = cnt + CT_NTASKS;
   A.taskPair = w->taskPair.p; A.taskInfo = w->taskInfo.p; A.taskCell = w->taskCell.p;
   A.bucket = w->bucket.p; A.bucketCount = cnt + CT_BUCKETCOUNT; A.bucketStart = cnt + CT_BUCKETSTART; A.bucketCursor = cnt + CT_BUCKETCURSOR;
@@ -1270,15 +1360,27 @@ static ContactArrays contact_arrays(cannon_world* w) {
 // Narrowphase.getContacts over the device pair list
 static int32_t st_narrowphase(cannon_world* w, double dt) {
   cudaStream_t s = w->ctx->stream;
-  BodyArrays B = body_arrays(w);
+  BodyArrays B = np_body_arrays(w);
   ShapeTables T = shape_tables(w);
   NpArrays A = np_arrays(w);
   ContactArrays C = contact_arrays(w);
   int* cnt = w->cnt.p;
-  const int gp = grid_for(w, w->pairCap, 128);
+  const int npPairCap = w->compound ? w->ppCap : w->pairCap;
+  if (w->compound) {  // shape instances at their world poses, body pairs -> instance pairs (narrow_phase.dart:669-680)
+    ProxyArrays X;
+    X.instBody = w->dInstBody.p; X.pos = w->pxPos.p; X.quat = w->pxQuat.p; X.type = w->pxType.p; X.flags = w->pxFlags.p;
+    X.material = w->pxMaterial.p; X.invMass = w->pxInvMass.p; X.nInst = w->nInst;
+    { g_kernel_launches++; k_proxies<<<grid_for(w, w->nInst, 256), 256, 0, s>>>(body_arrays(w), T, X); }
+    const int gb = grid_for(w, w->pairCap, 256);
+    { g_kernel_launches++; k_pp_count<<<gb, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->dInstFirst.p, w->ppCnt.p); }
+    W_TRY(w, scan_exclusive(w->ppCnt.p, w->ppOff.p, nullptr, w->pairCap, w->pairCap, cnt + CT_NPPAIRS, w->scanTmp, s));
+    { g_kernel_launches++; k_pp_fill<<<gb, 256, 0, s>>>(w->p1.p, w->p2.p, cnt + CT_NPAIRS, w->pairCap, w->dInstFirst.p, w->ppOff.p, w->pp1.p, w->pp2.p, w->ppCap, cnt + CT_OVF_PAIRS); }
+    { g_kernel_launches++; k_clamp_count<<<1, 32, 0, s>>>(cnt + CT_NPPAIRS, w->ppCap); }
+  }
+  const int gp = grid_for(w, npPairCap, 128);
   const int hoistBytes = (int)(4 * 32 * QS_HOIST_AXES * sizeof(QsAxis));  // pass 0 only
   { g_kernel_launches++; k_np_tasks<<<gp, 128, hoistBytes, s>>>(B, T, A, 0, hoistBytes); }
-  W_TRY(w, scan_exclusive(A.pairTasks, A.pairTaskOff, cnt + CT_NPAIRS, 0, w->pairCap, cnt + CT_NTASKS, w->scanTmp, s));
+  W_TRY(w, scan_exclusive(A.pairTasks, A.pairTaskOff, A.nPairs, 0, npPairCap, cnt + CT_NTASKS, w->scanTmp, s));
   { g_kernel_launches++; k_bucket_starts<<<1, 32, 0, s>>>(cnt); }
   { g_kernel_launches++; k_np_tasks<<<gp, 128, 0, s>>>(B, T, A, 1, 0); }
   const int g = w->ctx->sms * 8;
@@ -1414,7 +1516,7 @@ static int32_t st_contact_events(cannon_world* w) {
   const size_t tabBytes = ((size_t)w->evMask + 1) * sizeof(unsigned long long);
   W_TRY(w, cudaMemsetAsync(E.tabCur, 0xff, tabBytes, s));
   { g_kernel_launches++; k_ev_begin<<<1, 32, 0, s>>>(E); }
-  { g_kernel_launches++; k_ev_collect<<<grid_for(w, w->pairCap, 256), 256, 0, s>>>(np_arrays(w), E); }
+  { g_kernel_launches++; k_ev_collect<<<grid_for(w, w->compound ? w->ppCap : w->pairCap, 256), 256, 0, s>>>(np_arrays(w), E, w->compound ? w->dInstBody.p : nullptr); }
   { g_kernel_launches++; k_ev_diff<<<grid_for(w, 2LL * w->pairCap, 256), 256, 0, s>>>(E); }
   { g_kernel_launches++; k_ev_roll<<<grid_for(w, w->pairCap, 256), 256, 0, s>>>(E); }
   W_TRY(w, cudaMemcpyAsync(E.tabPrev, E.tabCur, tabBytes, cudaMemcpyDeviceToDevice, s));
@@ -1740,7 +1842,12 @@ int32_t cannon_narrowphase_contacts(cannon_world* w, const int32_t* p1, const in
   if (w->dt < 0) w->dt = 1.0 / 60;  // World.defaultDt
   if ((rc = st_narrowphase(w, w->dt)) != CANNON_OK) return rc;
   if (per_pair_count && np > 0) {
-    { g_kernel_launches++; k_np_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(np_arrays(w), w->keep.p); }
+    if (w->compound) {
+      { g_kernel_launches++; k_np_per_pair<<<grid_for(w, w->ppCap, 256), 256, 0, s>>>(np_arrays(w), w->ppPer.p); }
+      { g_kernel_launches++; k_pp_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(w->ppPer.p, w->ppOff.p, w->ppCnt.p, np, w->keep.p); }
+    } else {
+      { g_kernel_launches++; k_np_per_pair<<<grid_for(w, np, 256), 256, 0, s>>>(np_arrays(w), w->keep.p); }
+    }
     W_TRY(w, cudaGetLastError());
   }
   if ((rc = sync_counters(w)) != CANNON_OK) return rc;

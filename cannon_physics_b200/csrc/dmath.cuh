@@ -105,6 +105,15 @@ HD f3 qrot(const q4& q, const f3& v) {                                          
 }
 HD q4 qconj(const q4& q) { q4 r; r.x = -q.x; r.y = -q.y; r.z = -q.z; r.w = q.w; return r; }
 HD q4 qnegw(const q4& q) { q4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = -q.w; return r; }  // transform.dart:65-71
+HD q4 qmul(const q4& a, const q4& b) {  // Quaternion.multiply2, quaternion.dart:65-83
+  const double ax = W(a.x), ay = W(a.y), az = W(a.z), aw = W(a.w), bx = W(b.x), by = W(b.y), bz = W(b.z), bw = W(b.w);
+  q4 t;
+  t.x = (float)(ax * bw + aw * bx + ay * bz - az * by);
+  t.y = (float)(ay * bw + aw * by + az * bx - ax * bz);
+  t.z = (float)(az * bw + aw * bz + ax * by - ay * bx);
+  t.w = (float)(aw * bw - ax * bx - ay * by - az * bz);
+  return t;
+}
 HD f3 to_local_point(const f3& pos, const q4& q, const f3& wp) { return qrot(qconj(q), vsub(wp, pos)); }     // transform.dart:43
 HD f3 to_world_point(const f3& pos, const q4& q, const f3& lp) { return vadd(qrot(q, lp), pos); }            // transform.dart:52
 

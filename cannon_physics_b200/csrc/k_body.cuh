@@ -22,7 +22,7 @@ struct StepParams {
 // Shape.calculateWorldAABB for the in-scope shapes
 __device__ inline void shape_aabb(const ShapeTables& T, int shapeIdx, const f3& pos, const q4& q, f3& mn, f3& mx) {
   const float inf = __int_as_float(0x7f800000);
-  if (shapeIdx < 0) { mn = pos; mx = pos; return; }
+  if (shapeIdx < 0) { mn = mk3(0.0, 0.0, 0.0); mx = mn; return; }  // Body.updateAABB has nothing to loop over: the AABB stays AABB() (aabb.dart:13-16)
   const ShapeDev s = T.shapes[shapeIdx];
   switch (s.type) {
     case CANNON_SHAPE_SPHERE: {  // sphere.dart:43-53
@@ -86,6 +86,25 @@ __device__ inline void shape_aabb(const ShapeTables& T, int shapeIdx, const f3& 
   }
 }
 
+// Body.updateAABB, rigid_body.dart:415-447: the union (AABB.extend, aabb.dart:121-128) of the shape AABBs at their
+// world poses; a body without a shape table entry is the single-shape case
+__device__ inline void body_aabb(const BodyArrays& B, const ShapeTables& T, int i, f3& mn, f3& mx) {
+  const f3 pos = ld3(B.pos[i]);
+  const q4 q = ldq(B.quat[i]);
+  if (!T.instFirst) { shape_aabb(T, B.shape[i], pos, q, mn, mx); return; }
+  const int k0 = T.instFirst[i], k1 = T.instFirst[i + 1];
+  if (k0 == k1) { mn = mk3(0.0, 0.0, 0.0); mx = mn; return; }
+  for (int k = k0; k < k1; k++) {
+    const f3 offset = vadd(qrot(q, ld3(T.instOff[k])), pos);
+    const q4 orientation = qmul(q, ldq(T.instQuat[k]));
+    f3 lo, hi;
+    shape_aabb(T, T.instShape[k], offset, orientation, lo, hi);
+    if (k == k0) { mn = lo; mx = hi; continue; }
+    mn.x = fminf(mn.x, lo.x); mn.y = fminf(mn.y, lo.y); mn.z = fminf(mn.z, lo.z);
+    mx.x = fmaxf(mx.x, hi.x); mx.y = fmaxf(mx.y, hi.y); mx.z = fmaxf(mx.z, hi.z);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_prestep(BodyArrays B, ShapeTables T, StepParams P, int doGravity) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
     if (doGravity && B.type[i] == CANNON_BODY_DYNAMIC) {
@@ -98,7 +117,7 @@ __global__ void __launch_bounds__(256) k_prestep(BodyArrays B, ShapeTables T, St
     }
     if (P.needAABB) {
       f3 mn, mx;
-      shape_aabb(T, B.shape[i], ld3(B.pos[i]), ldq(B.quat[i]), mn, mx);
+      body_aabb(B, T, i, mn, mx);
       B.aabbLo[i] = st3(mn);
       B.aabbHi[i] = st3(mx);
     }

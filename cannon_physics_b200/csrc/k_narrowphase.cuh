@@ -530,8 +530,9 @@ __device__ __forceinline__ void raw_put(RawOut& o, const f3& ri, const f3& rj, c
 
 struct TaskCtx {
   int task, pair, first, second, info;
-  f3 xi, xj;   // positions of first / second (== shape world positions: single shape at the body origin)
+  f3 xi, xj;   // world positions of the two shapes (narrow_phase.dart:672-680)
   q4 qi, qj;
+  f3 bxi, bxj; // positions of the bodies that own them ("make relative to bodies")
   ShapeDev si, sj;
 };
 __device__ __forceinline__ void load_task(const BodyArrays& B, const ShapeTables& T, const NpArrays& A, int task, TaskCtx& c) {
@@ -544,6 +545,7 @@ __device__ __forceinline__ void load_task(const BodyArrays& B, const ShapeTables
   else { c.first = b; c.second = a; c.si = sb; c.sj = sa; }
   c.xi = ld3(B.pos[c.first]); c.xj = ld3(B.pos[c.second]);
   c.qi = ldq(B.quat[c.first]); c.qj = ldq(B.quat[c.second]);
+  c.bxi = ld3(B.bpos[np_owner(B, c.first)]); c.bxj = ld3(B.bpos[np_owner(B, c.second)]);
 }
 
 #define NP_BUCKET_LOOP(TYPE)                                                     \
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(256) k_np_sphere_sphere(BodyArrays B, ShapeTab
     vnormalize(ni);
     f3 ri = vscale(c.si.radius, ni);
     f3 rj = vscale(-c.sj.radius, ni);
-    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+    raw_put(o, rel_to_body(ri, c.xi, c.bxi), rel_to_body(rj, c.xj, c.bxj), ni);
   }
 }
 
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(256) k_np_sphere_plane(BodyArrays B, ShapeTabl
     f3 rj = vsub(p2s, ortho);
     const bool hit = -vdot(p2s, ni) <= R;
     if (!raw_alloc(o, hit ? 1 : 0)) continue;
-    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+    raw_put(o, rel_to_body(ri, c.xi, c.bxi), rel_to_body(rj, c.xj, c.bxj), ni);
   }
 }
 
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(128) k_np_sphere_box(BodyArrays B, ShapeTables
         }
       }
     if (!raw_alloc(o, found ? 1 : 0)) continue;
-    raw_put(o, rel_to_body(outRi, xi, xi), rel_to_body(outRj, xj, xj), outNi);
+    raw_put(o, rel_to_body(outRi, xi, c.bxi), rel_to_body(outRj, xj, c.bxj), outNi);
   }
 }
 
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(128) k_np_sphere_hull(BodyArrays B, ShapeTable
     f3 ri, rj, ni;
     const bool hit = sphere_convex(H, c.si.radius, c.xi, c.xj, c.qj, ri, rj, ni);
     if (!raw_alloc(o, hit ? 1 : 0)) continue;
-    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), ni);
+    raw_put(o, rel_to_body(ri, c.xi, c.bxi), rel_to_body(rj, c.xj, c.bxj), ni);
   }
 }
 
@@ -798,7 +800,7 @@ __global__ void __launch_bounds__(128) k_np_plane_hull(BodyArrays B, ShapeTables
         projected = vsub(wv, projected);
         const f3 ri = vsub(projected, c.xi);
         const f3 rj = vsub(wv, c.xj);
-        raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, c.xj, c.xj), worldNormal);
+        raw_put(o, rel_to_body(ri, c.xi, c.bxi), rel_to_body(rj, c.xj, c.bxj), worldNormal);
       }
     }
   }
@@ -989,7 +991,7 @@ __global__ void __launch_bounds__(64) k_np_hull_hull(BodyArrays B, ShapeTables T
     RawOut o; o.A = A; o.task = c.task;
     const HullView HA = hull_view(T, c.si.hull), HB = hull_view(T, c.sj.hull);
     if (oversizeOnly && !sat_oversize(HA, HB)) continue;
-    convex_convex_emit(o, HA, HB, c.xi, c.xj, c.qi, c.qj, c.xi, c.xj, false, clipOverflow);
+    convex_convex_emit(o, HA, HB, c.xi, c.xj, c.qi, c.qj, c.bxi, c.bxj, false, clipOverflow);
   }
 }
 
@@ -1139,7 +1141,7 @@ __global__ void __launch_bounds__(64) k_np_sphere_pillar(BodyArrays B, ShapeTabl
       hit = sphere_convex(H, c.si.radius, c.xi, wpo, c.qj, ri, rj, ni);
     }
     if (!raw_alloc(o, hit ? 1 : 0)) continue;
-    raw_put(o, rel_to_body(ri, c.xi, c.xi), rel_to_body(rj, wpo, c.xj), ni);
+    raw_put(o, rel_to_body(ri, c.xi, c.bxi), rel_to_body(rj, wpo, c.bxj), ni);
   }
 }
 
@@ -1162,7 +1164,7 @@ __global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables
     const HullView HA = hull_view(T, c.si.hull);
     if (vdist(c.xi, wpo) < S.bsr + HA.bsr) {
       const HullView HB = pillar_view(S, upper);
-      convex_convex_emit(o, HA, HB, c.xi, wpo, c.qi, c.qj, c.xi, c.xj, true, clipOverflow);
+      convex_convex_emit(o, HA, HB, c.xi, wpo, c.qi, c.qj, c.bxi, c.bxj, true, clipOverflow);
     } else {
       raw_alloc(o, 0);
     }
@@ -1191,8 +1193,8 @@ __global__ void __launch_bounds__(128) k_np_particle_simple(BodyArrays B, ShapeT
       TaskCtx c; load_task(B, T, A, NP_TASK(NP_PPT), c);
       RawOut o; o.A = A; o.task = c.task;
       f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
-      const f3 normal = qrot(ldq(B.quat[c.first]), up);
-      const f3 relpos = vsub(c.xj, ld3(B.pos[c.first]));
+      const f3 normal = qrot(ldq(B.bquat[np_owner(B, c.first)]), up);  // bj.quaternion / bj.position: the BODY's pose (:1821-1823)
+      const f3 relpos = vsub(c.xj, c.bxi);
       const bool hit = vdot(normal, relpos) <= 0.0;
       if (!raw_alloc(o, hit ? 1 : 0)) continue;
       f3 projected = vscale(vdot(normal, c.xj), normal);
@@ -1290,8 +1292,8 @@ __global__ void __launch_bounds__(128) k_np_particle_hull(BodyArrays B, ShapeTab
       wpv = vsub(wpv, xh);
       f3 rj = qrot(c.qi, wpv);  // :2246 rotates the world-frame vector once more
       f3 ri; ri.x = ri.y = ri.z = 0.f;
-      ri = rel_to_body(ri, xp, xp);
-      rj = rel_to_body(rj, xh, c.xi);
+      ri = rel_to_body(ri, xp, c.bxj);
+      rj = rel_to_body(rj, xh, c.bxi);
       raw_put(o, ri, rj, vneg(penetratedFaceNormal));
     }
   }
@@ -1349,7 +1351,7 @@ __global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T
     const bool particleFirst = s2.type == CANNON_SHAPE_PARTICLE;
     for (int q = 0; q < m; q++) {
       const int o = dst + q;
-      C.bi[o] = particleFirst ? second : first; C.bj[o] = particleFirst ? first : second;
+      C.bi[o] = np_owner(B, particleFirst ? second : first); C.bj[o] = np_owner(B, particleFirst ? first : second);
       C.ri[o] = A.rawRi[src + q]; C.rj[o] = A.rawRj[src + q]; C.ni[o] = A.rawNi[src + q];
       C.rest[o] = restitution; C.mu[o] = friction; C.slip[o] = slip;
       C.ca[o] = ca; C.cb[o] = cb; C.ceps[o] = ceps; C.fb[o] = fb; C.feps[o] = feps;
@@ -1368,6 +1370,61 @@ __global__ void __launch_bounds__(256) k_np_per_pair(NpArrays A, int* __restrict
     int s = 0;
     for (int t = t0; t < t1 && t < nt; t++) s += A.taskCnt[t];
     perPair[k] = s;
+  }
+}
+
+// ---- compound bodies (cannon_world_set_body_shapes) ------------------------------------------
+// The narrowphase runs on shape instances ("proxies"): k_proxies gives every instance its world pose
+// (bi.quaternion.vmult(shapeOffsets[i]) + bi.position, bi.quaternion * shapeOrientations[i]; narrow_phase.dart:671-680) and
+// a copy of the body attributes the resolvers read; k_pp_count / k_pp_fill expand the body pairs into instance pairs in
+// the reference's loop order (pair, i over bi.shapes, j over bj.shapes; :669-676). Everything downstream is unchanged:
+// tasks, resolvers and the canonical contact order work on the instance pairs, k_np_finalize maps back to bodies.
+struct ProxyArrays {
+  const int* instBody;
+  float4 *pos, *quat;
+  int *type, *flags, *material;
+  double* invMass;
+  int nInst;
+};
+__global__ void __launch_bounds__(256) k_proxies(BodyArrays B, ShapeTables T, ProxyArrays X) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < X.nInst; k += gridDim.x * blockDim.x) {
+    const int b = X.instBody[k];
+    const q4 q = ldq(B.quat[b]);
+    X.pos[k] = st3(vadd(qrot(q, ld3(T.instOff[k])), ld3(B.pos[b])));
+    const q4 o = qmul(q, ldq(T.instQuat[k]));
+    X.quat[k] = make_float4(o.x, o.y, o.z, o.w);
+    X.type[k] = B.type[b]; X.flags[k] = B.flags[b]; X.material[k] = B.material[b]; X.invMass[k] = B.invMass[b];
+  }
+}
+__global__ void __launch_bounds__(256) k_pp_count(const int* __restrict__ p1, const int* __restrict__ p2, const int* __restrict__ nPairs, int pairCap,
+                                                  const int* __restrict__ instFirst, int* __restrict__ cnt) {
+  const int np = min(*nPairs, pairCap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < pairCap; k += gridDim.x * blockDim.x) {
+    int c = 0;
+    if (k < np) { const int a = p1[k], b = p2[k]; c = (instFirst[a + 1] - instFirst[a]) * (instFirst[b + 1] - instFirst[b]); }
+    cnt[k] = c;
+  }
+}
+__global__ void __launch_bounds__(256) k_pp_fill(const int* __restrict__ p1, const int* __restrict__ p2, const int* __restrict__ nPairs, int pairCap,
+                                                 const int* __restrict__ instFirst, const int* __restrict__ off, int* __restrict__ pp1, int* __restrict__ pp2,
+                                                 int ppCap, int* __restrict__ overflow) {
+  const int np = min(*nPairs, pairCap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const int a = p1[k], b = p2[k];
+    const int a0 = instFirst[a], a1 = instFirst[a + 1], b0 = instFirst[b], b1 = instFirst[b + 1];
+    int o = off[k];
+    if (o + (a1 - a0) * (b1 - b0) > ppCap) { atomicMax(overflow, o + (a1 - a0) * (b1 - b0)); continue; }
+    for (int i = a0; i < a1; i++)
+      for (int j = b0; j < b1; j++) { pp1[o] = i; pp2[o] = j; o++; }
+  }
+}
+// contacts per BODY pair from the per-instance-pair counts (cannon_narrowphase_contacts' per_pair_count)
+__global__ void __launch_bounds__(256) k_pp_per_pair(const int* __restrict__ perProxy, const int* __restrict__ off, const int* __restrict__ cnt, int nBodyPairs,
+                                                     int* __restrict__ out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nBodyPairs; k += gridDim.x * blockDim.x) {
+    int s = 0;
+    for (int t = off[k]; t < off[k] + cnt[k]; t++) s += perProxy[t];
+    out[k] = s;
   }
 }
 
@@ -1395,14 +1452,14 @@ __device__ __forceinline__ bool ev_find(const unsigned long long* __restrict__ t
   }
 }
 __global__ void k_ev_begin(EvArrays E) { if (threadIdx.x == 0) { E.cnt[0] = 0; E.cnt[2] = 0; E.cnt[3] = 0; } }
-__global__ void __launch_bounds__(256) k_ev_collect(NpArrays A, EvArrays E) {
+__global__ void __launch_bounds__(256) k_ev_collect(NpArrays A, EvArrays E, const int* __restrict__ owner) {
   const int np = *A.nPairs, nt = min(*A.nTasks, A.taskCap);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
     const int t0 = A.pairTaskOff[k], t1 = min(t0 + A.pairTasks[k], nt);
     bool any = false;
     for (int t = t0; t < t1 && !any; t++) any = A.taskCnt[t] > 0;
     if (!any) continue;
-    const int a = A.p1[k], b = A.p2[k];
+    const int a = owner ? owner[A.p1[k]] : A.p1[k], b = owner ? owner[A.p2[k]] : A.p2[k];  // bodyOverlapKeeper: body ids
     const unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned long long)(unsigned)max(a, b);
     for (unsigned h = ev_hash(key, E.mask);; h = (h + 1) & E.mask) {
       const unsigned long long prev = atomicCAS(&E.tabCur[h], EV_EMPTY, key);

@@ -176,7 +176,7 @@ __device__ __forceinline__ bool ray_aabb_overlaps(const f3& l1, const f3& u1, co
 __device__ __forceinline__ void ray_body_aabb(const BodyArrays& B, const ShapeTables& T, int b, f3& mn, f3& mx) {
   const int sh = B.shape[b];
   const f3 pos = ld3(B.pos[b]);
-  if (sh < 0) { mn = pos; mx = pos; } else shape_aabb(T, sh, pos, ldq(B.quat[b]), mn, mx);
+  if (sh < 0) { mn = pos; mx = pos; } else body_aabb(B, T, b, mn, mx);
 }
 
 __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, RayArgs A) {
@@ -200,26 +200,32 @@ __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, Ra
       const int fl = B.flags[b];
       if (A.checkCollisionResponse && !(fl & BF_COLLISION_RESPONSE)) continue;
       if ((A.group & B.mask[b]) == 0 || (B.group[b] & A.mask) == 0) continue;
-      const int sh = B.shape[b];
-      if (sh < 0) continue;
-      const ShapeDev s = T.shapes[sh];
-      if (A.checkCollisionResponse && !s.collisionResponse) continue;
+      if (B.shape[b] < 0) continue;
       const q4 bq = ldq(B.quat[b]);
-      q4 ident; ident.x = ident.y = ident.z = 0.f; ident.w = 1.f;
-      const q4 qi = ray_qmul(bq, ident);
-      const f3 xi = vadd(qrot(bq, mk3(0.0, 0.0, 0.0)), ld3(B.pos[b]));
-      {  // Ray.distanceFromIntersection, :709-722
-        const f3 v0 = vsub(xi, L.from);
-        const double d = vdot(v0, L.dir);
-        f3 ip = vscale(d, L.dir);
-        ip = vadd(ip, L.from);
-        if (vdist(xi, ip) > s.bsr) continue;
-      }
+      const f3 bp = ld3(B.pos[b]);
+      const int k0 = T.instFirst ? T.instFirst[b] : 0, k1 = T.instFirst ? T.instFirst[b + 1] : 1;
       int ord = 0;
-      if (s.type == CANNON_SHAPE_SPHERE) ray_sphere(A, L, ray, s.radius, xi, b, ord);
-      else if (s.type == CANNON_SHAPE_PLANE) ray_plane(A, L, ray, qi, xi, b, ord);
-      else if (s.type == CANNON_SHAPE_BOX || s.type == CANNON_SHAPE_CONVEX || s.type == CANNON_SHAPE_CYLINDER)  // ray_class.dart:101-123: no other handler
-        ray_convex(A, L, ray, hull_view(T, s.hull), qi, xi, b, ord);
+      for (int k = k0; k < k1; k++) {  // Ray.intersectBody over body.shapes, :226-243
+        if (A.mode == CANNON_RAY_ANY && L.has) break;  // result.shouldStop
+        const ShapeDev s = T.shapes[T.instFirst ? T.instShape[k] : B.shape[b]];
+        if (A.checkCollisionResponse && !s.collisionResponse) continue;
+        q4 so; so.x = so.y = so.z = 0.f; so.w = 1.f;
+        f3 off = mk3(0.0, 0.0, 0.0);
+        if (T.instFirst) { so = ldq(T.instQuat[k]); off = ld3(T.instOff[k]); }
+        const q4 qi = ray_qmul(bq, so);
+        const f3 xi = vadd(qrot(bq, off), bp);
+        {  // Ray.distanceFromIntersection, :709-722
+          const f3 v0 = vsub(xi, L.from);
+          const double d = vdot(v0, L.dir);
+          f3 ip = vscale(d, L.dir);
+          ip = vadd(ip, L.from);
+          if (vdist(xi, ip) > s.bsr) continue;
+        }
+        if (s.type == CANNON_SHAPE_SPHERE) ray_sphere(A, L, ray, s.radius, xi, b, ord);
+        else if (s.type == CANNON_SHAPE_PLANE) ray_plane(A, L, ray, qi, xi, b, ord);
+        else if (s.type == CANNON_SHAPE_BOX || s.type == CANNON_SHAPE_CONVEX || s.type == CANNON_SHAPE_CYLINDER)  // ray_class.dart:101-123: no other handler
+          ray_convex(A, L, ray, hull_view(T, s.hull), qi, xi, b, ord);
+      }
     }
     // the warp's answer: (distance, key) minimum for closest, key minimum for any, key maximum for all / hitFaceIndex
     double dist = L.has ? L.dist : INFINITY;

@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyA
       f3 rj = S.u.c.pa[j];
       ri = vsub(ri, c.xi);
       rj = vsub(rj, xB);
-      ri = vsub(vadd(ri, c.xi), c.xi);
-      rj = vsub(vadd(rj, xB), c.xj);
+      ri = vsub(vadd(ri, c.xi), c.bxi);
+      rj = vsub(vadd(rj, xB), c.bxj);
       A.rawRi[start + j] = st3(ri);
       A.rawRj[start + j] = st3(rj);
       A.rawNi[start + j] = st3(ni);

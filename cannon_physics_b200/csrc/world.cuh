@@ -29,7 +29,14 @@ struct BodyArrays {
   float4 *aabbLo, *aabbHi;
   double *mass, *invMass, *brad, *ldamp, *adamp, *ldpow, *adpow, *sleepSpeed, *sleepTime, *tLastSleepy;
   int *type, *sleep, *shape, *material, *group, *mask, *world, *flags;
+  // Narrowphase view of a world with compound bodies (cannon_world_set_body_shapes): the arrays above that the
+  // narrowphase reads (pos, quat, shape, type, flags, material, invMass) are then per SHAPE INSTANCE ("proxy"), owner[]
+  // maps a proxy to its body and bpos / bquat are the real per-body poses (indexed by body). Otherwise owner == nullptr
+  // and bpos / bquat alias pos / quat.
+  const float4 *bpos, *bquat;
+  const int* owner;
 };
+__device__ __forceinline__ int np_owner(const BodyArrays& B, int i) { return B.owner ? B.owner[i] : i; }
 
 struct ShapeDev {
   int type, collisionResponse, group, mask;
@@ -91,6 +98,11 @@ struct ShapeTables {
   const double* matFriction;
   const double* matRestitution;
   int nMat;
+  // compound bodies: body b owns the instances [instFirst[b], instFirst[b+1]); nullptr = one shape per body at its origin
+  const int* instFirst;
+  const int* instShape;
+  const float4* instOff;
+  const float4* instQuat;
   // particleConvex state (k_narrowphase.cuh, k_np_particle_hull): the pose a hull shape / heightfield pillar was frozen at.
   // Target t < nShapes is shape t, nShapes + p is pillar p. nullptr unless the shape table holds a Particle.
   int nShapes;

@@ -27,6 +27,9 @@ class SceneSpec:
     contact_materials: List[Dict] = field(default_factory=list)
     constraints: List[Dict] = field(default_factory=list)
     springs: List[Dict] = field(default_factory=list)
+    # compound bodies (cannon_world_set_body_shapes): dict(first=(n+1) int32, shape=(k) int32, offset=(k,3) f32 | None,
+    # orientation=(k,4) f32 | None); None = one shape per body (the `shape` column of `bodies`)
+    body_shapes: Optional[Dict] = None
     name: str = ""
 
 
@@ -94,6 +97,8 @@ class DeviceWorld:
         self.n = 0
         self.set_materials(spec.material_friction, spec.material_restitution, spec.contact_materials)
         self.set_shapes(spec.shapes)
+        if spec.body_shapes is not None:
+            self.set_body_shapes(**spec.body_shapes)
         self.set_bodies(spec.bodies, spec.n_bodies)
         if spec.constraints:
             self.set_constraints(spec.constraints)
@@ -162,6 +167,15 @@ class DeviceWorld:
                     setattr(d, k, v)
         self._chk(self.lib.cannon_world_set_shapes(self.handle, len(shapes), arr))
         self.n_shapes = len(shapes)
+
+    def set_body_shapes(self, first, shape, offset=None, orientation=None):
+        """Body.addShape(shape, offset, orientation) for every body: body b owns the instances [first[b], first[b+1])."""
+        first = np.ascontiguousarray(first, dtype=np.int32)
+        shape = np.ascontiguousarray(shape, dtype=np.int32)
+        off = None if offset is None else np.ascontiguousarray(offset, dtype=np.float32).reshape(-1, 3)
+        ori = None if orientation is None else np.ascontiguousarray(orientation, dtype=np.float32).reshape(-1, 4)
+        self._chk(self.lib.cannon_world_set_body_shapes(self.handle, len(first) - 1, F.ptr(first, F.c_i32), F.ptr(shape, F.c_i32),
+                                                        F.ptr(off, F.c_f32), F.ptr(ori, F.c_f32)))
 
     def _soa(self, arrays: Dict[str, np.ndarray], n: int, allocate: Sequence[str] = ()):
         soa = F.BodiesSoA()

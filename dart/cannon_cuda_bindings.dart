@@ -250,6 +250,9 @@ class CannonCuda {
       int Function(H, int, Pointer<Double>, Pointer<Double>, int, Pointer<CannonContactMaterial>)>('cannon_world_set_materials');
   late final int Function(H, int, Pointer<CannonShapeDesc>) worldSetShapes =
       lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonShapeDesc>), int Function(H, int, Pointer<CannonShapeDesc>)>('cannon_world_set_shapes');
+  late final int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>) worldSetBodyShapes = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>),
+      int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>)>('cannon_world_set_body_shapes');
   late final int Function(H, Pointer<CannonBodiesSoa>) worldSetBodies =
       lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_world_set_bodies');
   late final int Function(H, Pointer<CannonBodiesSoa>) worldGetBodies =

@@ -118,8 +118,9 @@ class CudaSession {
       _shapeIndex.clear();
       final shapes = <Shape>[];
       for (final b in world.bodies) {
-        if (b.shapes.length > 1) throw 'CudaSession: compound bodies are outside the hot-path scope (SURVEY.md 8f)';
-        if (b.shapes.isNotEmpty && _shapeIndex.putIfAbsent(b.shapes[0], () => shapes.length) == shapes.length) shapes.add(b.shapes[0]);
+        for (final sh in b.shapes) {
+          if (_shapeIndex.putIfAbsent(sh, () => shapes.length) == shapes.length) shapes.add(sh);
+        }
       }
       final sd = a<CannonShapeDesc>(shapes.length + 1);
       for (var i = 0; i < shapes.length; i++) {
@@ -182,6 +183,24 @@ class CudaSession {
         s.shape[i] = b.shapes.isEmpty ? -1 : _shapeIndex[b.shapes[0]]!;
       }
       _gather();
+      // Body.shapes / shapeOffsets / shapeOrientations (rigid_body.dart:96-104) as the instance table of the next set_bodies
+      var nInst = 0;
+      for (final b in world.bodies) { nInst += b.shapes.length; }
+      final first = a<Int32>(_n + 2), ish = a<Int32>(nInst + 1);
+      final ioff = a<Float>(3 * nInst + 3), iori = a<Float>(4 * nInst + 4);
+      var k = 0;
+      for (var i = 0; i < _n; i++) {
+        final b = world.bodies[i];
+        first[i] = k;
+        for (var j = 0; j < b.shapes.length; j++, k++) {
+          ish[k] = _shapeIndex[b.shapes[j]]!;
+          final o = b.shapeOffsets[j], q = b.shapeOrientations[j];
+          ioff[3 * k] = o.x; ioff[3 * k + 1] = o.y; ioff[3 * k + 2] = o.z;
+          iori[4 * k] = q.x; iori[4 * k + 1] = q.y; iori[4 * k + 2] = q.z; iori[4 * k + 3] = q.w;
+        }
+      }
+      first[_n] = k;
+      check(cuda.worldSetBodyShapes(handle, _n, first, ish, ioff, iori), 'cannon_world_set_body_shapes');
       check(cuda.worldSetBodies(handle, _soa), 'cannon_world_set_bodies');
 
       // constraints (lib/constraints/*.dart). LockConstraint / default-distance parameters are evaluated by the library on

@@ -299,6 +299,18 @@ int32_t cannon_world_set_materials(cannon_world* w, int32_t n_materials, const d
                                    const double* restitution, int32_t n_contact_materials,
                                    const cannon_contact_material* cms);
 int32_t cannon_world_set_shapes(cannon_world* w, int32_t n_shapes, const cannon_shape_desc* shapes);
+/* Compound bodies: Body.addShape(shape, offset, orientation), lib/objects/rigid_body.dart:348-377 (shapes, shapeOffsets,
+ * shapeOrientations). The table replaces the `shape` column of the following cannon_world_set_bodies calls (until it is
+ * replaced or dropped), which must describe the same n_bodies: body b owns the shape instances [first[b], first[b+1]) in addShape order (an empty
+ * range = a body without shapes). offset: 3 floats per instance, NULL = zeros; orientation: 4 floats (x,y,z,w),
+ * NULL = identity. n_bodies = 0 drops the table (one shape per body at the body origin again). What follows the
+ * reference: Body.updateAABB / updateBoundingRadius / updateMassProperties over all instances (rigid_body.dart:395-447,
+ * 587-609), the shape-pair loops of Narrowphase.getContacts (narrow_phase.dart:669-721: every resolver sees the shape's
+ * world pose and makes ri / rj relative to the BODY position), Ray.intersectBody (ray_class.dart:226-243);
+ * GridBroadphase bins a body by shapes[0] (grid_broadphase.dart:136), as the reference does. */
+int32_t cannon_world_set_body_shapes(cannon_world* world, int32_t n_bodies, const int32_t* first, const int32_t* shape,
+                                     const float* offset, const float* orientation);
+
 /* World.addBody for all bodies at once (upload path); derives mass properties. */
 int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* bodies);
 int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* out);

@@ -186,10 +186,31 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
 
 #define GETF3(dst, src, i) dst = V3{src[3 * (i)], src[3 * (i) + 1], src[3 * (i) + 2]}
 
+int32_t cannon_world_set_body_shapes(cannon_world* cw, int32_t n_bodies, const int32_t* first, const int32_t* shape, const float* offset,
+                                     const float* orientation) {
+  if (!cw || n_bodies < 0) return CANNON_E_INVALID;
+  World& w = cw->w;
+  w.pendFirst.clear(); w.pendShape.clear(); w.pendOffset.clear(); w.pendOrient.clear();
+  if (n_bodies == 0) return CANNON_OK;
+  if (!first || first[0] != 0) return fail(cw->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: first[0] must be 0");
+  for (int b = 0; b < n_bodies; b++) if (first[b + 1] < first[b]) return fail(cw->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: first[] must ascend");
+  const int ni = first[n_bodies];
+  if (ni > 0 && !shape) return fail(cw->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes: shape[] missing");
+  for (int k = 0; k < ni; k++) {
+    if (shape[k] < 0 || shape[k] >= (int)w.shapes.size()) return fail(cw->ctx, CANNON_E_INVALID, "body references unknown shape");
+    w.pendShape.push_back(shape[k]);
+    w.pendOffset.push_back(offset ? V3{offset[3 * k], offset[3 * k + 1], offset[3 * k + 2]} : V3{0, 0, 0});
+    w.pendOrient.push_back(orientation ? Q4{orientation[4 * k], orientation[4 * k + 1], orientation[4 * k + 2], orientation[4 * k + 3]} : Q4{0, 0, 0, 1});
+  }
+  w.pendFirst.assign(first, first + n_bodies + 1);
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_bodies(cannon_world* cw, const cannon_bodies_soa* s) {
   if (!cw || !s || s->n < 0) return CANNON_E_INVALID;
   World& w = cw->w;
   const int n = s->n;
+  if (!w.pendFirst.empty() && (int)w.pendFirst.size() != n + 1) return fail(cw->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes described another body count");
   w.bodies.clear();
   w.bodies.resize(n);
   w.sapAxisList.clear();
@@ -220,6 +241,19 @@ int32_t cannon_world_set_bodies(cannon_world* cw, const cannon_bodies_soa* s) {
     if (s->is_trigger) b.isTrigger = s->is_trigger[i] != 0;
     b.material = s->material ? s->material[i] : -1;
     b.shape = s->shape ? s->shape[i] : -1;
+    b.shapes.clear(); b.shapeOffsets.clear(); b.shapeOrientations.clear();
+    if (!w.pendFirst.empty()) {  // Body.addShape for every instance of the table (rigid_body.dart:348-377)
+      for (int k = w.pendFirst[i]; k < w.pendFirst[i + 1]; k++) {
+        b.shapes.push_back(w.pendShape[k]);
+        b.shapeOffsets.push_back(w.pendOffset[k]);
+        b.shapeOrientations.push_back(w.pendOrient[k]);
+      }
+      b.shape = b.shapes.empty() ? -1 : b.shapes[0];
+    } else if (b.shape >= 0) {
+      b.shapes.push_back(b.shape);
+      b.shapeOffsets.push_back(V3{0, 0, 0});
+      b.shapeOrientations.push_back(Q4{0, 0, 0, 1});
+    }
     b.worldId = s->world_id ? s->world_id[i] : 0;
     if (b.shape >= (int)w.shapes.size()) return fail(cw->ctx, CANNON_E_INVALID, "body references unknown shape");
     if (b.material >= (int)w.matFriction.size()) return fail(cw->ctx, CANNON_E_INVALID, "body references unknown material");

@@ -815,7 +815,7 @@ const cannon_contact_material* World::contactMaterial(int ma, int mb) const {
   return idx >= 0 ? &cms[idx] : nullptr;
 }
 
-// Narrowphase.getContacts, narrow_phase.dart:634-721 (single shape per body at the body origin)
+// Narrowphase.getContacts, narrow_phase.dart:634-721
 void World::getContacts() {
   contacts.clear();
   frictions.clear();
@@ -831,20 +831,22 @@ void World::getContacts() {
     const bool justTest = (A.type == CANNON_BODY_KINEMATIC && B.type == CANNON_BODY_STATIC) ||
                           (A.type == CANNON_BODY_STATIC && B.type == CANNON_BODY_KINEMATIC) ||
                           (A.type == CANNON_BODY_KINEMATIC && B.type == CANNON_BODY_KINEMATIC);
-    if (A.shape < 0 || B.shape < 0) continue;
-    Shape& si = shapes[A.shape];
-    Shape& sj = shapes[B.shape];
-    // shapeOrientation = identity, shapeOffset = 0: qi = bodyQ (x) identity and xi = bodyQ*0 + pos are exact
-    Q4 qi = qmul(A.quaternion, Q4{0, 0, 0, 1});
-    V3 xi = add(qvmult(A.quaternion, V3{0, 0, 0}), A.position);
-    Q4 qj = qmul(B.quaternion, Q4{0, 0, 0, 1});
-    V3 xj = add(qvmult(B.quaternion, V3{0, 0, 0}), B.position);
-    if (!((si.mask & sj.group) != 0 && (sj.mask & si.group) != 0)) continue;
-    if (distance_to(xi, xj) > si.boundingSphereRadius + sj.boundingSphereRadius) continue;
-    np.cm = bodyCm ? bodyCm : &desc.default_contact_material;
-    if (justTest) continue;  // resolvers create no equations in justTest mode (only overlap-keeper events)
-    if (si.type < sj.type) np.resolve(si, sj, xi, xj, qi, qj, bi, bj);
-    else np.resolve(sj, si, xj, xi, qj, qi, bj, bi);
+    for (size_t i = 0; i < A.shapes.size(); i++) {      // narrow_phase.dart:670-721
+      Shape& si = shapes[A.shapes[i]];
+      const Q4 qi = qmul(A.quaternion, A.shapeOrientations[i]);
+      const V3 xi = add(qvmult(A.quaternion, A.shapeOffsets[i]), A.position);
+      for (size_t j = 0; j < B.shapes.size(); j++) {
+        Shape& sj = shapes[B.shapes[j]];
+        const Q4 qj = qmul(B.quaternion, B.shapeOrientations[j]);
+        const V3 xj = add(qvmult(B.quaternion, B.shapeOffsets[j]), B.position);
+        if (!((si.mask & sj.group) != 0 && (sj.mask & si.group) != 0)) continue;
+        if (distance_to(xi, xj) > si.boundingSphereRadius + sj.boundingSphereRadius) continue;
+        np.cm = bodyCm ? bodyCm : &desc.default_contact_material;
+        if (justTest) continue;  // resolvers create no equations in justTest mode (only overlap-keeper events)
+        if (si.type < sj.type) np.resolve(si, sj, xi, xj, qi, qj, bi, bj);
+        else np.resolve(sj, si, xj, xi, qj, qi, bj, bi);
+      }
+    }
     perPairCount[k] = (int)(contacts.size() - before);
   }
 }

@@ -173,7 +173,7 @@ bool aabbOverlaps(const V3& l1, const V3& u1, const V3& l2, const V3& u2) {
 void World::aabbQuery(const V3& lower, const V3& upper, std::vector<int>& result) {
   for (int i = 0; i < (int)bodies.size(); i++) {
     Body& b = bodies[i];
-    if (b.shape < 0) { b.aabbLower = b.position; b.aabbUpper = b.position; } else updateAABB(b);
+    if (b.shapes.empty()) { b.aabbLower = b.position; b.aabbUpper = b.position; } else updateAABB(b);
     if (aabbOverlaps(b.aabbLower, b.aabbUpper, lower, upper)) result.push_back(i);
   }
 }
@@ -196,18 +196,21 @@ bool World::raycast(int rayIndex, const V3& from, const V3& to, const cannon_ray
     const Body& body = bodies[cand[k]];
     if (r.checkCollisionResponse && !body.collisionResponse) continue;
     if ((r.group & body.mask) == 0 || (body.group & r.mask) == 0) continue;
-    if (body.shape < 0) continue;
-    const Shape& shape = shapes[body.shape];
-    if (r.checkCollisionResponse && !shape.collisionResponse) continue;
-    const Q4 qi = qmul(body.quaternion, Q4{0, 0, 0, 1});
-    const V3 xi = add(qvmult(body.quaternion, V3{0, 0, 0}), body.position);
-    // _intersectShape, :270-283
-    if (distanceFromIntersection(r.from, r.direction, xi) > shape.boundingSphereRadius) continue;
-    switch (shape.type) {
-      case CANNON_SHAPE_SPHERE: intersectSphere(r, shape, xi, cand[k]); break;
-      case CANNON_SHAPE_PLANE: intersectPlane(r, qi, xi, cand[k]); break;
-      case CANNON_SHAPE_BOX: case CANNON_SHAPE_CYLINDER: case CANNON_SHAPE_CONVEX: intersectConvex(r, shape.hull, qi, xi, cand[k]); break;
-      default: break;  // heightfield rays: outside the scope (the API refuses such worlds)
+    for (size_t si = 0; si < body.shapes.size(); si++) {  // intersectBody, :226-243
+      const Shape& shape = shapes[body.shapes[si]];
+      if (r.checkCollisionResponse && !shape.collisionResponse) continue;
+      const Q4 qi = qmul(body.quaternion, body.shapeOrientations[si]);
+      const V3 xi = add(qvmult(body.quaternion, body.shapeOffsets[si]), body.position);
+      // _intersectShape, :270-283
+      if (!(distanceFromIntersection(r.from, r.direction, xi) > shape.boundingSphereRadius)) {
+        switch (shape.type) {
+          case CANNON_SHAPE_SPHERE: intersectSphere(r, shape, xi, cand[k]); break;
+          case CANNON_SHAPE_PLANE: intersectPlane(r, qi, xi, cand[k]); break;
+          case CANNON_SHAPE_BOX: case CANNON_SHAPE_CYLINDER: case CANNON_SHAPE_CONVEX: intersectConvex(r, shape.hull, qi, xi, cand[k]); break;
+          default: break;  // heightfield rays: outside the scope (the API refuses such worlds); no handler for the other types
+        }
+      }
+      if (r.shouldStop) break;
     }
   }
   out = RayHit{rayIndex, r.body, r.hitFaceIndex, r.distance, r.hitPointWorld, r.hitNormalWorld};

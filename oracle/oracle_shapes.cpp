@@ -174,10 +174,18 @@ void shape_world_aabb(const Shape& s, const V3& pos, const Q4& q, V3& mn, V3& mx
   }
 }
 
-// Body.updateAABB, rigid_body.dart:415-447 (one shape, zero offset, identity orientation)
+// Body.updateAABB, rigid_body.dart:415-447; AABB.extend, aabb.dart:121-128
 void World::updateAABB(Body& b) const {
-  if (b.shape < 0) return;
-  shape_world_aabb(shapes[b.shape], b.position, b.quaternion, b.aabbLower, b.aabbUpper);
+  for (size_t i = 0; i < b.shapes.size(); i++) {
+    V3 offset = qvmult(b.quaternion, b.shapeOffsets[i]);
+    offset = add(offset, b.position);
+    const Q4 orientation = qmul(b.quaternion, b.shapeOrientations[i]);
+    V3 lo, hi;
+    shape_world_aabb(shapes[b.shapes[i]], offset, orientation, lo, hi);
+    if (i == 0) { b.aabbLower = lo; b.aabbUpper = hi; continue; }
+    b.aabbLower = V3{std::fmin(b.aabbLower.x, lo.x), std::fmin(b.aabbLower.y, lo.y), std::fmin(b.aabbLower.z, lo.z)};
+    b.aabbUpper = V3{std::fmax(b.aabbUpper.x, hi.x), std::fmax(b.aabbUpper.y, hi.y), std::fmax(b.aabbUpper.z, hi.z)};
+  }
 }
 
 // Body.updateInertiaWorld, rigid_body.dart:450-466
@@ -208,12 +216,12 @@ void World::updateMassProperties(Body& b) const {
   updateInertiaWorld(b, true);
 }
 
-// Body.updateBoundingRadius, rigid_body.dart:395-412 (zero shape offset)
+// Body.updateBoundingRadius, rigid_body.dart:395-412
 void World::updateBoundingRadius(Body& b) const {
   double radius = 0;
-  if (b.shape >= 0) {
-    double offset = 0.0;
-    double r = shapes[b.shape].boundingSphereRadius;
+  for (size_t i = 0; i < b.shapes.size(); i++) {
+    const double offset = length(b.shapeOffsets[i]);
+    const double r = shapes[b.shapes[i]].boundingSphereRadius;
     if (offset + r > radius) radius = offset + r;
   }
   b.boundingRadius = radius;

@@ -67,7 +67,11 @@ struct Body {
   int group = 1, mask = -1;
   bool collisionResponse = true, isTrigger = false;
   int material = -1;
-  int shape = -1;
+  int shape = -1;  // shapes[0] (or -1): what GridBroadphase looks at (grid_broadphase.dart:136)
+  // Body.shapes / shapeOffsets / shapeOrientations, rigid_body.dart:96-104 (indices into World::shapes)
+  std::vector<int> shapes;
+  std::vector<V3> shapeOffsets;
+  std::vector<Q4> shapeOrientations;
   int worldId = 0;
   bool wakeUpAfterNarrowphase = false;
   V3 inertia{0, 0, 0}, invInertia{0, 0, 0};
@@ -146,6 +150,10 @@ struct World {
   std::vector<int> sapAxisList;
   // outputs of the last stages
   std::vector<int> p1, p2;
+  // cannon_world_set_body_shapes: the table the next set_bodies consumes
+  std::vector<int> pendFirst, pendShape;
+  std::vector<V3> pendOffset;
+  std::vector<Q4> pendOrient;
   std::vector<Eq> contacts;   // ContactEquations (World.contacts)
   std::vector<Eq> frictions;  // FrictionEquations (World.frictionEquations)
   std::vector<int> perPairCount;

@@ -114,8 +114,11 @@ def test_api_world_flattens_like_the_reference_objects(oracle_lib):
     ys = [float(b.position[1]) for b in boxes]
     assert 0.45 < ys[0] < 0.55 and ys[0] < ys[1] < ys[2]  # the stack stays a stack
     assert len(world.contacts["body_i"]) >= 8
-    with pytest.raises(F.CannonError):
-        boxes[0].addShape(api.Sphere(1.0))  # compound bodies are outside the hot-path scope
+    boxes[2].addShape(api.Sphere(0.4), offset=(0, 0.9, 0))  # a compound body: the world is rebuilt with a shape table
+    spec = world._spec()
+    assert spec.body_shapes is not None and spec.body_shapes["first"].tolist() == [0, 1, 2, 3, 5] and spec.body_shapes["shape"].tolist() == [0, 1, 1, 1, 2]
+    world.step(1 / 60)
+    assert world.stepnumber == 31
 
 
 def test_world_api_contact_event_listeners(oracle_lib):
