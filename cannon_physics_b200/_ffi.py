@@ -17,7 +17,7 @@ P = C.POINTER
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NOGPU = 0, -1, -2, -3, -4, -5
 
 SHAPE_SPHERE, SHAPE_PLANE, SHAPE_BOX, SHAPE_CONVEX, SHAPE_CYLINDER, SHAPE_HEIGHTFIELD = 0, 1, 2, 3, 4, 8
-SHAPE_CAPSULE, SHAPE_CONE, SHAPE_SIZED_PLANE, SHAPE_PARTICLE = 5, 6, 7, 9
+SHAPE_CAPSULE, SHAPE_CONE, SHAPE_SIZED_PLANE, SHAPE_PARTICLE, SHAPE_TRIMESH = 5, 6, 7, 9, 10
 BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC = 0, 1, 2
 AWAKE, SLEEPY, SLEEPING = 0, 1, 2
 BP_NAIVE, BP_SAP, BP_GRID = 0, 1, 2
@@ -57,6 +57,7 @@ class ShapeDesc(C.Structure):
         ("n_faces", c_i32), ("face_offsets", P(c_i32)), ("face_indices", P(c_i32)),
         ("hf_nx", c_i32), ("hf_ny", c_i32), ("hf_data", P(c_f64)), ("hf_element_size", c_i32),
         ("convex_has_axes", c_i32),
+        ("n_triangles", c_i32), ("tm_indices", P(c_i32)), ("tm_scale", c_f32 * 3),
     ]
 
 

@@ -26,7 +26,7 @@ from . import _ffi as F
 from .engine import Context, DeviceWorld, SceneSpec
 
 __all__ = [
-    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle",
+    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle", "Trimesh",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
     "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
     "World",
@@ -273,6 +273,38 @@ class CapsuleLathe(LatheShape):  # capsule_lathe.dart:14-74: the capsule profile
 
 class Particle(Shape):  # particle.dart:9: a point (bounding radius 0, zero inertia, AABB = its position)
     type = F.SHAPE_PARTICLE
+
+
+class Trimesh(Shape):  # trimesh.dart:37 (sphere and plane contacts; the reference's other trimesh resolvers are unfinished)
+    type = F.SHAPE_TRIMESH
+
+    def __init__(self, vertices, indices, **kw):
+        super().__init__(**kw)
+        self.vertices = np.asarray(vertices, dtype=np.float64).reshape(-1, 3)
+        self.indices = np.asarray(indices, dtype=np.int32).reshape(-1)
+        self.scale = np.ones(3, np.float32)
+
+    def setScale(self, scale):  # trimesh.dart:142-152
+        self.scale[:] = scale
+
+    def _desc(self):
+        return dict(super()._desc(), vertices=self.vertices.astype(np.float32), tm_indices=self.indices, tm_scale=self.scale)
+
+    @staticmethod
+    def createTorus(radius=1.0, tube=0.5, radialSegments=8, tubularSegments=6, arc=math.pi * 2):  # trimesh.dart:382-443
+        verts, idx = [], []
+        for j in range(radialSegments + 1):
+            for i in range(tubularSegments + 1):
+                u = i / tubularSegments * arc
+                v = j / radialSegments * math.pi * 2
+                verts.append(np.array([(radius + tube * math.cos(v)) * math.cos(u), (radius + tube * math.cos(v)) * math.sin(u), tube * math.sin(v)], np.float32))
+                if i != 0 and j != 0:
+                    a = (tubularSegments + 1) * j + i - 1
+                    b = (tubularSegments + 1) * (j - 1) + i - 1
+                    c = (tubularSegments + 1) * (j - 1) + i
+                    d = (tubularSegments + 1) * j + i
+                    idx += [a, b, d, b, c, d]
+        return Trimesh(np.array(verts, np.float64), idx)
 
 
 class Heightfield(Shape):  # heightfield.dart:34

@@ -31,7 +31,7 @@
 enum {
   CT_NPAIRS = 0, CT_NTASKS, CT_NCONTACTS, CT_NROWS, CT_RAWCOUNT, CT_FRICTOTAL, CT_CONTTOTAL, CT_NLEVELS, CT_ITERS,
   CT_OVF_PAIRS, CT_OVF_TASKS, CT_OVF_CONTACTS, CT_OVF_ROWS, CT_OVF_LEVELS, CT_OVF_CLIP, CT_CURSOR, CT_ACT0, CT_ACT1,
-  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NROWS_PAD, CT_NCLIP0, CT_NCLIP1, CT_NPPAIRS, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
+  CT_GS_NTASKS, CT_NPAIRS_RAW, CT_NUNITS, CT_NEXEC, CT_NUNITS1, CT_ISL_CHANGED0, CT_ISL_CHANGED1, CT_NISLANDS, CT_RING_OK, CT_GS_ABORT, CT_NROWS_PAD, CT_NCLIP0, CT_NCLIP1, CT_NPPAIRS, CT_UNSUPPORTED, CT_BUCKETCOUNT, CT_BUCKETSTART = CT_BUCKETCOUNT + NP_NTYPES,
   CT_BUCKETCURSOR = CT_BUCKETSTART + NP_NTYPES, CT_BAR = ((CT_BUCKETCURSOR + NP_NTYPES + 31) / 32) * 32, CT_COUNT = CT_BAR + 64
 };
 
@@ -44,7 +44,7 @@ __global__ void k_bucket_starts(int* cnt) {
 __global__ void k_set_int(int* p, int v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
 
 // persistent accumulators (never reset by the per-step counter memset): statistics and sticky overflow needs
-enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_GS_ABORT, AC_COUNT };
+enum { AC_CONTACT_ITERS = 0, AC_STEPS, AC_OVF_PAIRS, AC_OVF_TASKS, AC_OVF_CONTACTS, AC_OVF_ROWS, AC_OVF_LEVELS, AC_OVF_CLIP, AC_GS_ABORT, AC_UNSUPPORTED, AC_COUNT };
 __global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restrict__ acc, int taskCap, int contactCap, long long* __restrict__ clk,
                                 double dt) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -60,6 +60,7 @@ __global__ void k_step_epilogue(const int* __restrict__ cnt, long long* __restri
   mx(AC_OVF_LEVELS, cnt[CT_OVF_LEVELS]);
   mx(AC_OVF_CLIP, cnt[CT_OVF_CLIP]);
   mx(AC_GS_ABORT, cnt[CT_GS_ABORT]);
+  mx(AC_UNSUPPORTED, cnt[CT_UNSUPPORTED]);
 }
 
 // constraint-pair filter, world_class.dart:488-499: drop pairs joined by a constraint with collideConnected == false
@@ -119,7 +120,7 @@ struct HostShape {
   int type = 0, collisionResponse = 1, group = -1, mask = -1;
   double radius = 0, bsr = 0;
   float he[3] = {0, 0, 0};
-  int hull = -1, hf = -1;
+  int hull = -1, hf = -1, tm = -1;
 };
 
 struct cannon_world {
@@ -162,7 +163,13 @@ struct cannon_world {
   DBuf<int> dFacesK;
   DBuf<PillarRec> dPillars;
   // particleConvex state of the shape table (ShapeTables.pc*): only allocated when a Particle shape exists
-  bool hasParticle = false;
+  bool hasParticle = false, hasTrimesh = false;
+  std::vector<TrimeshDev> hTms;
+  std::vector<float4> hTmVerts, hTmNormals;
+  std::vector<int> hTmIdx;
+  DBuf<TrimeshDev> dTms;
+  DBuf<float4> dTmVerts, dTmNormals;
+  DBuf<int> dTmIdx;
   DBuf<int> dPcFrozen, dPcFreezeTask;
   DBuf<float4> dPcPos, dPcQuat;
   DBuf<double> dFplanec, dHfData, dMatFriction, dMatRestitution;
@@ -331,6 +338,7 @@ static ShapeTables shape_tables(cannon_world* w) {
   T.edgesK = w->dEdgesK.p; T.facesK = w->dFacesK.p; T.pillars = w->dPillars.p;
   T.hfs = w->dHfs.p; T.hfdata = w->dHfData.p; T.cmTable = w->dCmTable.p; T.cms = w->dCms.p;
   T.matFriction = w->dMatFriction.p; T.matRestitution = w->dMatRestitution.p; T.nMat = w->nMat;
+  T.tms = w->dTms.p; T.tmVerts = w->dTmVerts.p; T.tmNormals = w->dTmNormals.p; T.tmIdx = w->dTmIdx.p;
   T.instFirst = w->compound ? w->dInstFirst.p : nullptr; T.instShape = w->dInstShape.p; T.instOff = w->dInstOff.p; T.instQuat = w->dInstQuat.p;
   T.nShapes = (int)w->hShapes.size();
   T.pcFrozen = w->dPcFrozen.p; T.pcFreezeTask = w->dPcFreezeTask.p; T.pcPos = w->dPcPos.p; T.pcQuat = w->dPcQuat.p;
@@ -397,6 +405,7 @@ void cannon_shape_desc_default(cannon_shape_desc* d) {
   d->radius_top = d->radius_bottom = d->height = 1.0;
   d->num_segments = 8;
   d->hf_element_size = 1;
+  d->tm_scale[0] = d->tm_scale[1] = d->tm_scale[2] = 1.f;
 }
 
 int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out) {
@@ -478,7 +487,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(lam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
-  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars); REL(dInstFirst); REL(dInstShape); REL(dInstBody); REL(pxType); REL(pxFlags); REL(pxMaterial); REL(pp1); REL(pp2); REL(ppCnt); REL(ppOff); REL(ppPer); REL(dInstOff); REL(dInstQuat); REL(pxPos); REL(pxQuat); REL(pxInvMass); REL(dPcFrozen); REL(dPcFreezeTask); REL(dPcPos); REL(dPcQuat);
+  REL(world); REL(flags); REL(dShapes); REL(dHulls); REL(dVerts); REL(dFnormals); REL(dEdges); REL(dFplanec); REL(dHfData); REL(dEdgesK); REL(dFacesK); REL(dPillars); REL(dInstFirst); REL(dInstShape); REL(dInstBody); REL(pxType); REL(pxFlags); REL(pxMaterial); REL(pp1); REL(pp2); REL(ppCnt); REL(ppOff); REL(ppPer); REL(dInstOff); REL(dInstQuat); REL(pxPos); REL(pxQuat); REL(pxInvMass); REL(dTms); REL(dTmVerts); REL(dTmNormals); REL(dTmIdx); REL(dPcFrozen); REL(dPcFreezeTask); REL(dPcPos); REL(dPcQuat);
   REL(dMatFriction); REL(dMatRestitution); REL(dFvOff); REL(dFvIdx); REL(dFcOff); REL(dFcIdx); REL(dCmTable); REL(dHfs); REL(dCms);
   REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
@@ -532,6 +541,7 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   w->hHulls.clear();
   w->hHfs.clear();
   w->hHfData.clear();
+  w->hTms.clear(); w->hTmVerts.clear(); w->hTmNormals.clear(); w->hTmIdx.clear();
   long long nPillars = 0;
   for (int i = 0; i < n; i++) {
     const cannon_shape_desc& d = sd[i];
@@ -552,6 +562,40 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
       case CANNON_SHAPE_PARTICLE:
         h.bsr = 0;  // particle.dart:24-26
         break;
+      case CANNON_SHAPE_TRIMESH: {  // Trimesh constructor, trimesh.dart:60-73
+        if (d.n_vertices <= 0 || d.n_triangles <= 0 || !d.vertices || !d.tm_indices) return fail(w->ctx, CANNON_E_INVALID, "trimesh needs vertices and indices");
+        for (int k = 0; k < 3 * d.n_triangles; k++)
+          if (d.tm_indices[k] < 0 || d.tm_indices[k] >= d.n_vertices) return fail(w->ctx, CANNON_E_INVALID, "trimesh index out of range");
+        TrimeshDev m;
+        m.vOff = (int)w->hTmVerts.size(); m.nV = d.n_vertices; m.iOff = (int)w->hTmIdx.size(); m.nT = d.n_triangles;
+        std::vector<f3> raw(d.n_vertices), sc(d.n_vertices);
+        for (int v = 0; v < d.n_vertices; v++) {  // getVertex :260-268: setValues, then *= scale component by component
+          raw[v].x = d.vertices[3 * v]; raw[v].y = d.vertices[3 * v + 1]; raw[v].z = d.vertices[3 * v + 2];
+          sc[v] = mk3(W(raw[v].x) * W(d.tm_scale[0]), W(raw[v].y) * W(d.tm_scale[1]), W(raw[v].z) * W(d.tm_scale[2]));
+          w->hTmVerts.push_back(st3(sc[v]));
+        }
+        for (int t = 0; t < d.n_triangles; t++) {  // updateNormals :157-175 with computeNormal(vb, va, vc) :220-230, unit scale
+          const f3 &va = raw[d.tm_indices[3 * t]], &vb = raw[d.tm_indices[3 * t + 1]], &vc = raw[d.tm_indices[3 * t + 2]];
+          const f3 ab = vsub(va, vb), cb = vsub(vc, va);
+          f3 nn = vcross(cb, ab);
+          if (!(nn.x == 0 && nn.y == 0 && nn.z == 0)) vnormalize(nn);
+          w->hTmNormals.push_back(st3(nn));
+          for (int k = 0; k < 3; k++) w->hTmIdx.push_back(d.tm_indices[3 * t + k]);
+        }
+        f3 l = sc[0], u = sc[0];  // computeLocalAABB :315-343 (note the else-if), updateBoundingSphereRadius :350-363
+        double max2 = 0;
+        for (const f3& v : sc) {
+          if (v.x < l.x) l.x = v.x; else if (v.x > u.x) u.x = v.x;
+          if (v.y < l.y) l.y = v.y; else if (v.y > u.y) u.y = v.y;
+          if (v.z < l.z) l.z = v.z; else if (v.z > u.z) u.z = v.z;
+          max2 = fmax(max2, vlen2(v));
+        }
+        m.lo = st3(l); m.hi = st3(u);
+        h.bsr = sqrt(max2);
+        h.tm = (int)w->hTms.size();
+        w->hTms.push_back(m);
+        break;
+      }
       case CANNON_SHAPE_BOX: {
         for (int k = 0; k < 3; k++) h.he[k] = d.half_extents[k];
         HostHull hull;
@@ -621,7 +665,7 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     const HostShape& h = w->hShapes[i];
     ShapeDev& d = shapes[i];
     d.type = h.type; d.collisionResponse = h.collisionResponse; d.group = h.group; d.mask = h.mask;
-    d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.pad = 0;
+    d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.tm = h.tm;
   }
   std::vector<HullDev> hulls;
   w->hasOversizeHull = false;
@@ -684,6 +728,11 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   W_TRY(w, upload(w->dFacesK, facesK, s));
   W_TRY(w, upload(w->dHfs, w->hHfs, s));
   W_TRY(w, upload(w->dHfData, w->hHfData, s));
+  w->hasTrimesh = !w->hTms.empty();
+  if (w->hasTrimesh) {
+    W_TRY(w, upload(w->dTms, w->hTms, s)); W_TRY(w, upload(w->dTmVerts, w->hTmVerts, s)); W_TRY(w, upload(w->dTmNormals, w->hTmNormals, s));
+    W_TRY(w, upload(w->dTmIdx, w->hTmIdx, s));
+  }
   if (nPillars > 0) {
     W_TRY(w, w->dPillars.reserve((size_t)nPillars));
     const ShapeTables T = shape_tables(w);
@@ -767,6 +816,25 @@ static void host_shape_aabb(const cannon_world* w, int shapeIdx, const f3& pos, 
       mn = pos;
       mx = pos;
       break;
+    case CANNON_SHAPE_TRIMESH: {  // trimesh.dart:366-375 (device twin: shape_aabb)
+      const TrimeshDev& m = w->hTms[s.tm];
+      const f3 l = ld3(m.lo), u = ld3(m.hi);
+      for (int i = 0; i < 8; i++) {
+        f3 c;
+        c.x = (i == 0 || i == 3 || i == 5 || i == 6) ? l.x : u.x;
+        c.y = (i == 0 || i == 1 || i == 4 || i == 6) ? l.y : u.y;
+        c.z = (i == 0 || i == 1 || i == 2 || i == 5) ? l.z : u.z;
+        const f3 p = to_world_point(pos, q, c);
+        if (i == 0) { mn = p; mx = p; continue; }
+        if (p.x > mx.x) mx.x = p.x;
+        if (p.x < mn.x) mn.x = p.x;
+        if (p.y > mx.y) mx.y = p.y;
+        if (p.y < mn.y) mn.y = p.y;
+        if (p.z > mx.z) mx.z = p.z;
+        if (p.z < mn.z) mn.z = p.z;
+      }
+      break;
+    }
     default:
       mn.x = mn.y = mn.z = -inf;
       mx.x = mx.y = mx.z = inf;
@@ -1343,7 +1411,7 @@ static NpArrays np_arrays(cannon_world* w) {
   A.taskCnt = w->taskCnt.p; A.taskRaw = w->taskRaw.p; A.taskOff = w->taskOff.p; A.rawCount = cnt + CT_RAWCOUNT;
   A.rawRi = w->rawRi.p; A.rawRj = w->rawRj.p; A.rawNi = w->rawNi.p;
   A.taskCap = w->taskCap; A.contactCap = w->contactCap;
-  A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS;
+  A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS; A.unsupported = cnt + CT_UNSUPPORTED;
   { const char* e = getenv("CANNON_NP_DEBUG"); A.debug = e ? atoi(e) : 0; }
   A.clipList = w->clipList.p; A.nClip = cnt + CT_NCLIP0; A.taskSep = w->taskSep.p;
   return A;
@@ -1410,6 +1478,7 @@ static int32_t st_narrowphase(cannon_world* w, double dt) {
   { g_kernel_launches++; k_np_sphere_box<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_sphere_hull<<<g, 128, 0, s>>>(B, T, A); }
   { g_kernel_launches++; k_np_plane_hull<<<g, 128, 0, s>>>(B, T, A); }
+  if (w->hasTrimesh) { g_kernel_launches++; k_np_trimesh<<<g, 128, 0, s>>>(B, T, A); }
   if (w->hasParticle) {
     { g_kernel_launches++; k_np_particle_simple<<<g, 128, 0, s>>>(B, T, A); }
     { g_kernel_launches++; k_np_particle_hull<0><<<g, 128, 0, s>>>(B, T, A); }
@@ -1733,6 +1802,7 @@ static int32_t check_overflow_acc(cannon_world* w) {
   if (a[AC_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
   if (a[AC_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
   if (a[AC_GS_ABORT] > 0) return fail(w->ctx, CANNON_E_CUDA, "k_gs_exact: a dependency wait ran out (solver aborted instead of hanging)");
+  if (a[AC_UNSUPPORTED] > 0) return fail(w->ctx, CANNON_E_UNSUPPORTED, "a trimesh met a box / convex / particle / trimesh: the reference's resolvers for these pairs are unfinished (narrow_phase.dart:2265-2341)");
   return CANNON_OK;
 }
 
@@ -1746,6 +1816,7 @@ static int32_t check_overflow(cannon_world* w) {
   if (c[CT_OVF_LEVELS] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "solver dependency levels exceeded the level table");
   if (c[CT_OVF_CLIP] > 0) return fail(w->ctx, CANNON_E_CAPACITY, "clipped contact polygon exceeded NP_MAXPOLY vertices");
   if (c[CT_GS_ABORT] > 0) return fail(w->ctx, CANNON_E_CUDA, "k_gs_exact: a dependency wait ran out (solver aborted instead of hanging)");
+  if (c[CT_UNSUPPORTED] > 0) return fail(w->ctx, CANNON_E_UNSUPPORTED, "a trimesh met a box / convex / particle / trimesh: the reference's resolvers for these pairs are unfinished (narrow_phase.dart:2265-2341)");
   return CANNON_OK;
 }
 
@@ -2383,7 +2454,7 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
                              cannon_ray_hits_soa* hits, int32_t* n_hits) {
   if (!w || n_rays < 0 || !opt || !hits || !n_hits || (n_rays > 0 && (!from || !to))) return CANNON_E_INVALID;
   if (opt->mode != CANNON_RAY_CLOSEST && opt->mode != CANNON_RAY_ANY && opt->mode != CANNON_RAY_ALL) return fail(w->ctx, CANNON_E_INVALID, "ray mode");
-  if (!w->hHfs.empty()) return fail(w->ctx, CANNON_E_UNSUPPORTED, "heightfield rays are outside the hot-path scope (SURVEY.md 8f)");
+  if (!w->hHfs.empty() || w->hasTrimesh) return fail(w->ctx, CANNON_E_UNSUPPORTED, "heightfield / trimesh rays are outside the hot-path scope (SURVEY.md 8f)");
   const bool all = opt->mode == CANNON_RAY_ALL;
   if (!all && hits->capacity < n_rays) { *n_hits = n_rays; return fail(w->ctx, CANNON_E_CAPACITY, "hit arrays smaller than n_rays"); }
   *n_hits = 0;

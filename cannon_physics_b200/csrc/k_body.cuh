@@ -79,6 +79,25 @@ __device__ inline void shape_aabb(const ShapeTables& T, int shapeIdx, const f3& 
       mn = pos;
       mx = pos;
       break;
+    case CANNON_SHAPE_TRIMESH: {  // trimesh.dart:366-375: AABB.toWorldFrame of the local AABB (aabb.dart:175-187,216-237)
+      const TrimeshDev m = T.tms[s.tm];
+      const f3 l = ld3(m.lo), u = ld3(m.hi);
+      for (int i = 0; i < 8; i++) {
+        f3 c;
+        c.x = (i == 0 || i == 3 || i == 5 || i == 6) ? l.x : u.x;
+        c.y = (i == 0 || i == 1 || i == 4 || i == 6) ? l.y : u.y;
+        c.z = (i == 0 || i == 1 || i == 2 || i == 5) ? l.z : u.z;
+        const f3 w = to_world_point(pos, q, c);
+        if (i == 0) { mn = w; mx = w; continue; }
+        if (w.x > mx.x) mx.x = w.x;
+        if (w.x < mn.x) mn.x = w.x;
+        if (w.y > mx.y) mx.y = w.y;
+        if (w.y < mn.y) mn.y = w.y;
+        if (w.z > mx.z) mx.z = w.z;
+        if (w.z < mn.z) mn.z = w.z;
+      }
+      break;
+    }
     default:  // heightfield.dart:499-503
       mn.x = mn.y = mn.z = -inf;
       mx.x = mx.y = mx.z = inf;

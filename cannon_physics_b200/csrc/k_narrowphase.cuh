@@ -13,7 +13,8 @@
 
 enum { NP_SS = 0, NP_SP = 1, NP_SB = 2, NP_SH = 3, NP_PH = 4, NP_HH = 5, NP_SPIL = 6, NP_HPIL = 7,
        NP_SPT = 8, NP_PPT = 9, NP_HPT = 10, NP_PILPT = 11,  // sphere / plane / hull / heightfield pillar against a Particle
-       NP_NTYPES = 12 };
+       NP_STM = 12, NP_PTM = 13,  // sphere / plane against a Trimesh
+       NP_NTYPES = 14 };
 __device__ __forceinline__ bool np_pillar_code(int c) { return c == NP_SPIL || c == NP_HPIL || c == NP_PILPT; }
 #define NP_MAXPOLY 40
 
@@ -41,6 +42,7 @@ struct NpArrays {
   int debug;               // profiling aid (CANNON_NP_DEBUG): 1 skip clipping, 2 skip the axis loop, 3 skip after pillar build
   int* overflowTasks;
   int* overflowContacts;
+  int* unsupported;        // set when a pair only the reference's unfinished trimesh resolvers would handle passes the prologue
   // tile SAT kernel (k_sat_warp.cuh): tasks that passed the separating-axis test, queued for the clipping launch
   int* clipList;           // [2][taskCap]: hull/hull, hull/pillar
   int* nClip;              // [2]
@@ -297,7 +299,11 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
           int lo = si.type, hi = sj.type;
           first = a; second = b;
           if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
-          if (hi == CANNON_SHAPE_PARTICLE) {  // narrow_phase.dart:196-211 (particle-particle has no key)
+          if (hi == CANNON_SHAPE_TRIMESH) {  // narrow_phase.dart:212-238 (heightfield-trimesh has no key)
+            if (lo == CANNON_SHAPE_SPHERE) code = NP_STM;
+            else if (lo == CANNON_SHAPE_PLANE) code = NP_PTM;
+            else if (lo != CANNON_SHAPE_HEIGHTFIELD) atomicExch(A.unsupported, 1);  // boxTrimesh / trimeshConvex / particleTrimesh / trimeshTrimesh
+          } else if (hi == CANNON_SHAPE_PARTICLE) {  // narrow_phase.dart:196-211 (particle-particle has no key)
             if (lo == CANNON_SHAPE_SPHERE) code = NP_SPT;
             else if (lo == CANNON_SHAPE_PLANE) code = NP_PPT;
             else if (is_hull_type(lo)) code = NP_HPT;
@@ -1171,6 +1177,15 @@ __global__ void __launch_bounds__(64) k_np_hull_pillar(BodyArrays B, ShapeTables
   }
 }
 
+// Ray.pointInTriangle, ray_class.dart:697-709
+__device__ inline bool np_point_in_triangle(const f3& p, const f3& a, const f3& b, const f3& c) {
+  const f3 v0 = vsub(c, a), v1 = vsub(b, a), v2 = vsub(p, a);
+  const double dot00 = vdot(v0, v0), dot01 = vdot(v0, v1), dot02 = vdot(v0, v2), dot11 = vdot(v1, v1), dot12 = vdot(v1, v2);
+  const double u = dot11 * dot02 - dot01 * dot12;
+  const double v = dot00 * dot12 - dot01 * dot02;
+  return u >= 0 && v >= 0 && (u + v) < (dot00 * dot11 - dot01 * dot01);
+}
+
 // ---- Particle resolvers -------------------------------------------------------------------
 // load_task order: `first` = the sphere / plane / hull / heightfield (lower ShapeType), `second` = the particle.
 // sphereParticle :1258-1294 and planeParticle :1805-1846: one thread per task.
@@ -1370,6 +1385,120 @@ __global__ void __launch_bounds__(256) k_np_per_pair(NpArrays A, int* __restrict
     int s = 0;
     for (int t = t0; t < t1 && t < nt; t++) s += A.taskCnt[t];
     perPair[k] = s;
+  }
+}
+
+// ---- Trimesh -------------------------------------------------------------------------------
+// sphereTrimesh, narrow_phase.dart:1438-1691 as the Dart port runs it: every triangle in index order (the octree query of
+// :1480 is not used) and per corner j a vertex test, an edge test and the triangle-face test (:1573-1603 sits inside the
+// j loop: a face contact is reported three times). EMIT = false counts, EMIT = true writes (same walk, same order).
+template <bool EMIT>
+__device__ inline int sphere_trimesh(const ShapeTables& T, const TrimeshDev& m, const TaskCtx& c, RawOut& o) {
+  const f3 xi = c.xi, xj = c.xj;
+  const q4 qj = c.qj;
+  const double R = c.si.radius;
+  const f3 local = to_local_point(xj, qj, xi);
+  const double radiusSquared = R * R;
+  const float4* V = T.tmVerts + m.vOff;
+  const int* I = T.tmIdx + m.iOff;
+  int n = 0;
+  auto emit_local = [&](f3 tmp) {  // :1549-1566 / :1586-1601
+    if (EMIT) {
+      f3 ni = vsub(tmp, local);
+      vnormalize(ni);
+      f3 ri = vscale(R, ni);
+      ri = vadd(ri, xi);
+      ri = vsub(ri, c.bxi);
+      tmp = to_world_point(xj, qj, tmp);
+      const f3 rj = vsub(tmp, c.bxj);
+      ni = qrot(qj, ni);
+      ri = qrot(qj, ri);
+      raw_put(o, ri, rj, ni);
+    }
+    n++;
+  };
+  for (int i = 0; i < m.nT; i++) {
+    const f3 va = ld3(V[I[i * 3]]), vb = ld3(V[I[i * 3 + 1]]), vc = ld3(V[I[i * 3 + 2]]);
+    const f3 normal = ld3(T.tmNormals[m.iOff / 3 + i]);
+#pragma unroll 1
+    for (int j = 0; j < 3; j++) {
+      const f3 A = j == 0 ? va : (j == 1 ? vb : vc), Bv = j == 0 ? vb : (j == 1 ? vc : va);
+      {
+        f3 relpos = vsub(A, local);
+        if (vlen2(relpos) <= radiusSquared) {
+          if (EMIT) {
+            const f3 v = to_world_point(xj, qj, A);
+            relpos = vsub(v, xi);
+            f3 ni = relpos;
+            vnormalize(ni);
+            f3 ri = vscale(R, ni);
+            ri = vadd(ri, xi);
+            ri = vsub(ri, c.bxi);
+            raw_put(o, ri, vsub(v, c.bxj), ni);
+          }
+          n++;
+        }
+        const f3 edgeVector = vsub(Bv, A);
+        f3 tmp = vsub(local, Bv);
+        const double positionAlongEdgeB = vdot(tmp, edgeVector);
+        tmp = vsub(local, A);
+        double positionAlongEdgeA = vdot(tmp, edgeVector);
+        if (positionAlongEdgeA > 0 && positionAlongEdgeB < 0) {
+          f3 unit = edgeVector;
+          vnormalize(unit);
+          positionAlongEdgeA = vdot(tmp, unit);
+          tmp = vscale(positionAlongEdgeA, unit);
+          tmp = vadd(tmp, A);
+          if (vdist(tmp, local) < R) emit_local(tmp);
+        }
+      }
+      {
+        f3 tmp = vsub(local, va);
+        double dist = vdot(tmp, normal);
+        tmp = vscale(dist, normal);
+        tmp = vsub(local, tmp);
+        dist = vdist(tmp, local);
+        if (np_point_in_triangle(tmp, va, vb, vc) && dist < R) emit_local(tmp);
+      }
+    }
+  }
+  return n;
+}
+// sphereTrimesh / planeTrimesh (narrow_phase.dart:1438,1916): one thread per task, count then emit
+__global__ void __launch_bounds__(128) k_np_trimesh(BodyArrays B, ShapeTables T, NpArrays A) {
+  {
+    NP_BUCKET_LOOP(NP_STM) {
+      TaskCtx c; load_task(B, T, A, NP_TASK(NP_STM), c);
+      RawOut o; o.A = A; o.task = c.task;
+      const TrimeshDev m = T.tms[c.sj.tm];
+      const int n = sphere_trimesh<false>(T, m, c, o);
+      if (!raw_alloc(o, n)) continue;
+      sphere_trimesh<true>(T, m, c, o);
+    }
+  }
+  {
+    NP_BUCKET_LOOP(NP_PTM) {
+      TaskCtx c; load_task(B, T, A, NP_TASK(NP_PTM), c);
+      RawOut o; o.A = A; o.task = c.task;
+      const TrimeshDev m = T.tms[c.sj.tm];
+      f3 up; up.x = 0.f; up.y = 0.f; up.z = 1.f;
+      const f3 normal = qrot(c.qi, up);
+      int n = 0;
+      for (int i = 0; i < m.nV; i++) {
+        const f3 v = to_world_point(c.xj, c.qj, ld3(T.tmVerts[m.vOff + i]));
+        if (vdot(normal, vsub(v, c.xi)) <= 0.0) n++;
+      }
+      if (!raw_alloc(o, n)) continue;
+      for (int i = 0; i < m.nV; i++) {
+        const f3 v = to_world_point(c.xj, c.qj, ld3(T.tmVerts[m.vOff + i]));
+        const f3 relpos = vsub(v, c.xi);
+        if (vdot(normal, relpos) <= 0.0) {
+          f3 projected = vscale(vdot(relpos, normal), normal);
+          projected = vsub(v, projected);
+          raw_put(o, vsub(projected, c.bxi), vsub(v, c.bxj), normal);
+        }
+      }
+    }
   }
 }
 

@@ -44,7 +44,7 @@ struct ShapeDev {
   float hx, hy, hz;
   int hull;  // index into hull table (box / convex / cylinder), -1 otherwise
   int hf;    // index into heightfield table, -1 otherwise
-  int pad;
+  int tm;    // index into trimesh table, -1 otherwise
 };
 
 struct HullDev {
@@ -56,6 +56,12 @@ struct HullDev {
   double bsr;         // boundingSphereRadius
   int ekOff, nEk;     // unique edges that are not +-copies of an earlier one (SAT axis pruning, k_sat_warp.cuh)
   int fkOff, nFk;     // likewise for the face normals: list of face indices
+};
+
+// Trimesh (trimesh.dart): getVertex results, triangle indices, face normals, local AABB
+struct TrimeshDev {
+  int vOff, nV, iOff, nT;  // vertices in tmVerts, 3 indices per triangle in tmIdx (local to the mesh), normals at tmNormals[iOff / 3 + t]
+  float4 lo, hi;           // computeLocalAABB, trimesh.dart:315-343
 };
 
 struct HfDev {
@@ -98,6 +104,10 @@ struct ShapeTables {
   const double* matFriction;
   const double* matRestitution;
   int nMat;
+  const TrimeshDev* tms;
+  const float4* tmVerts;
+  const float4* tmNormals;
+  const int* tmIdx;
   // compound bodies: body b owns the instances [instFirst[b], instFirst[b+1]); nullptr = one shape per body at its origin
   const int* instFirst;
   const int* instShape;

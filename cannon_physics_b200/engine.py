@@ -156,6 +156,13 @@ class DeviceWorld:
                     idx = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.int32) for f in v]))
                     keep += [offs, idx]
                     d.face_offsets, d.face_indices, d.n_faces = F.ptr(offs, F.c_i32), F.ptr(idx, F.c_i32), len(v)
+                elif k == "tm_indices":
+                    idx = np.ascontiguousarray(v, dtype=np.int32).reshape(-1)
+                    keep.append(idx)
+                    d.tm_indices, d.n_triangles = F.ptr(idx, F.c_i32), len(idx) // 3
+                elif k == "tm_scale":
+                    for j in range(3):
+                        d.tm_scale[j] = float(np.float32(v[j]))
                 elif k == "hf_data":
                     a = np.ascontiguousarray(v, dtype=np.float64)
                     assert a.ndim == 2

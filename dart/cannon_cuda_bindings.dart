@@ -12,7 +12,7 @@ import 'package:ffi/ffi.dart';
 // ---- enums of the header -------------------------------------------------------------------------------------------
 const cannonOk = 0, cannonEInvalid = -1, cannonECuda = -2, cannonECapacity = -3, cannonEUnsupported = -4, cannonENoGpu = -5;
 const shapeSphere = 0, shapePlane = 1, shapeBox = 2, shapeConvex = 3, shapeCylinder = 4, shapeCapsule = 5, shapeCone = 6, shapeSizedPlane = 7,
-    shapeHeightfield = 8, shapeParticle = 9; // ShapeType.index
+    shapeHeightfield = 8, shapeParticle = 9, shapeTrimesh = 10; // ShapeType.index
 const bpNaive = 0, bpSap = 1, bpGrid = 2;
 const solverReferenceOrder = 0, solverColored = 1, solverSplit = 2, solverColoredF32 = 3;
 const constraintPointToPoint = 0, constraintHinge = 1, constraintDistance = 2, constraintLock = 3, constraintConeTwist = 4;
@@ -76,6 +76,9 @@ final class CannonShapeDesc extends Struct {
   external Pointer<Double> hfData;
   @Int32() external int hfElementSize;
   @Int32() external int convexHasAxes;
+  @Int32() external int nTriangles;
+  external Pointer<Int32> tmIndices;
+  @Array(3) external Array<Float> tmScale;
 }
 
 final class CannonBodiesSoa extends Struct {

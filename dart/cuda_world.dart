@@ -37,6 +37,7 @@ int _shapeTypeCode(Shape s) {
     case ShapeType.sizedPlane: return shapeSizedPlane;
     case ShapeType.heightfield: return shapeHeightfield;
     case ShapeType.particle: return shapeParticle;
+    case ShapeType.trimesh: return shapeTrimesh;
     default: throw 'CudaSession: shape type ${s.type} is outside the hot-path scope (SURVEY.md 8f)';
   }
 }
@@ -139,6 +140,14 @@ class CudaSession {
           final hd = a<Double>(nx * ny);
           for (var x = 0; x < nx; x++) { for (var y = 0; y < ny; y++) { hd[x * ny + y] = s.data[x][y]; } }
           r.hfNx = nx; r.hfNy = ny; r.hfData = hd; r.hfElementSize = s.elementSize.toInt();
+        } else if (s is Trimesh) {
+          final nv = s.vertices.length ~/ 3;
+          final v = a<Float>(3 * nv + 3);
+          for (var k = 0; k < 3 * nv; k++) { v[k] = s.vertices[k]; }  // getVertex rounds to float the same way (trimesh.dart:270-275)
+          final idx = a<Int32>(s.indices.length + 1);
+          for (var k = 0; k < s.indices.length; k++) { idx[k] = s.indices[k]; }
+          r.nVertices = nv; r.vertices = v; r.nTriangles = s.indices.length ~/ 3; r.tmIndices = idx;
+          _put3(r.tmScale, s.scale);
         } else if (s is ConvexPolyhedron) {
           final v = a<Float>(3 * s.vertices.length);
           for (var k = 0; k < s.vertices.length; k++) { v[3 * k] = s.vertices[k].x; v[3 * k + 1] = s.vertices[k].y; v[3 * k + 2] = s.vertices[k].z; }

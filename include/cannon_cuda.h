@@ -52,7 +52,7 @@ extern "C" {
 enum {
   CANNON_SHAPE_SPHERE = 0, CANNON_SHAPE_PLANE = 1, CANNON_SHAPE_BOX = 2, CANNON_SHAPE_CONVEX = 3,
   CANNON_SHAPE_CYLINDER = 4, CANNON_SHAPE_CAPSULE = 5, CANNON_SHAPE_CONE = 6, CANNON_SHAPE_SIZED_PLANE = 7,
-  CANNON_SHAPE_HEIGHTFIELD = 8, CANNON_SHAPE_PARTICLE = 9
+  CANNON_SHAPE_HEIGHTFIELD = 8, CANNON_SHAPE_PARTICLE = 9, CANNON_SHAPE_TRIMESH = 10
 };
 /* CAPSULE / CONE / SIZED_PLANE are ConvexPolyhedron subclasses in the reference
  * (lib/rigid_body_shapes/{capsule,capsule_lathe,cone,sized_plane}.dart): the binding passes the hull the reference's
@@ -68,7 +68,16 @@ enum {
  * narrow_phase.dart:2207-2212): every hull Shape (and every cached heightfield pillar, heightfield.dart:285-301) keeps
  * the pose of the first penetration it ever saw. That state lives with the shape table here as well: it is part of the
  * world, is cleared by cannon_world_set_shapes, and makes particle-in-hull contacts history dependent exactly as in
- * the reference. */
+ * the reference.
+ *
+ * TRIMESH (lib/rigid_body_shapes/trimesh.dart): sphereTrimesh and planeTrimesh (narrow_phase.dart:1438,1916) as the Dart
+ * port runs them - every triangle is visited in index order (the octree query result is not used, :1490), and the
+ * triangle-face test sits inside the per-corner loop, so a face contact is reported three times. The reference's other
+ * trimesh resolvers are unfinished (trimeshConvex indexes triangles by vertex index and collides a degenerate hull,
+ * :2313-2330; boxTrimesh / particleTrimesh / trimeshTrimesh build on it): a step in which such a pair passes the
+ * prologue of getContacts returns CANNON_E_UNSUPPORTED instead of inventing a result. Face normals are those of the
+ * unscaled mesh (setScale calls updateNormals before it stores the new scale, trimesh.dart:142-152). Rays refuse worlds
+ * with a trimesh like those with a heightfield. */
 /* BodyTypes / BodySleepStates, lib/objects/rigid_body.dart:15-16 */
 enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 2 };
 enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };
@@ -169,6 +178,11 @@ typedef struct cannon_shape_desc {
    * presence matters: findSeparatingAxis (:255,:290) tests the hull's face normals when axes were given and none when
    * not (its `else if` on the same condition is dead code). Cone passes axes, Capsule / SizedPlane / Lathe do not. */
   int32_t convex_has_axes;
+  /* Trimesh, lib/rigid_body_shapes/trimesh.dart:37: `vertices` / `n_vertices` above are the mesh vertices (the reference
+   * keeps doubles and rounds them to float in getVertex, :260-275); tm_indices: 3 per triangle; tm_scale: Trimesh.scale */
+  int32_t n_triangles;
+  const int32_t* tm_indices;
+  float   tm_scale[3];
 } cannon_shape_desc;
 
 /* Body state, structure of arrays. In *_set_bodies a NULL pointer means "reference default"

@@ -70,6 +70,7 @@ void cannon_shape_desc_default(cannon_shape_desc* d) {
   d->radius_top = d->radius_bottom = d->height = 1.0;
   d->num_segments = 8;
   d->hf_element_size = 1;
+  d->tm_scale[0] = d->tm_scale[1] = d->tm_scale[2] = 1.f;
 }
 
 int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out) {
@@ -129,6 +130,39 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
       case CANNON_SHAPE_PARTICLE:
         s.boundingSphereRadius = 0;  // particle.dart:24-26
         break;
+      case CANNON_SHAPE_TRIMESH: {  // Trimesh constructor, trimesh.dart:60-73
+        if (d.n_vertices <= 0 || d.n_triangles <= 0 || !d.vertices || !d.tm_indices) return fail(cw->ctx, CANNON_E_INVALID, "trimesh needs vertices and indices");
+        for (int k = 0; k < 3 * d.n_triangles; k++)
+          if (d.tm_indices[k] < 0 || d.tm_indices[k] >= d.n_vertices) return fail(cw->ctx, CANNON_E_INVALID, "trimesh index out of range");
+        s.tmIdx.assign(d.tm_indices, d.tm_indices + 3 * d.n_triangles);
+        std::vector<V3> raw(d.n_vertices);
+        s.tmVerts.resize(d.n_vertices);
+        for (int v = 0; v < d.n_vertices; v++) {  // getVertex :260-268: setValues, then *= scale component by component
+          raw[v] = V3{d.vertices[3 * v], d.vertices[3 * v + 1], d.vertices[3 * v + 2]};
+          s.tmVerts[v] = v3(D(raw[v].x) * D(d.tm_scale[0]), D(raw[v].y) * D(d.tm_scale[1]), D(raw[v].z) * D(d.tm_scale[2]));
+        }
+        s.tmNormals.resize(d.n_triangles);
+        for (int t = 0; t < d.n_triangles; t++) {  // updateNormals :157-175 with computeNormal(vb, va, vc) :220-230, unit scale
+          const V3 &va = raw[s.tmIdx[3 * t]], &vb = raw[s.tmIdx[3 * t + 1]], &vc = raw[s.tmIdx[3 * t + 2]];
+          const V3 ab = sub(va, vb), cb = sub(vc, va);
+          V3 n = cross(cb, ab);
+          if (!(n.x == 0 && n.y == 0 && n.z == 0)) normalize(n);
+          s.tmNormals[t] = n;
+        }
+        // computeLocalAABB :315-343 (note the else-if) and updateBoundingSphereRadius :350-363
+        V3 l = s.tmVerts[0], u = s.tmVerts[0];
+        double max2 = 0;
+        for (const V3& v : s.tmVerts) {
+          if (v.x < l.x) l.x = v.x; else if (v.x > u.x) u.x = v.x;
+          if (v.y < l.y) l.y = v.y; else if (v.y > u.y) u.y = v.y;
+          if (v.z < l.z) l.z = v.z; else if (v.z > u.z) u.z = v.z;
+          const double n2 = length2(v);
+          if (n2 > max2) max2 = n2;
+        }
+        s.tmLo = l; s.tmHi = u;
+        s.boundingSphereRadius = std::sqrt(max2);
+        break;
+      }
       case CANNON_SHAPE_BOX:
         s.halfExtents = V3{d.half_extents[0], d.half_extents[1], d.half_extents[2]};
         make_box_hull(s.halfExtents, s.hull);
@@ -594,6 +628,7 @@ int32_t cannon_narrowphase_contacts(cannon_world* cw, const int32_t* p1, const i
     if (p1[k] < 0 || p2[k] < 0 || p1[k] >= nb || p2[k] >= nb) return fail(cw->ctx, CANNON_E_INVALID, "pair references unknown body");
   if (w.dt < 0) w.dt = 1.0 / 60;  // World.defaultDt
   w.getContacts();
+  if (w.unsupportedPair) { w.unsupportedPair = false; return fail(cw->ctx, CANNON_E_UNSUPPORTED, "a trimesh met a box / convex / particle / trimesh: the reference's resolvers for these pairs are unfinished (narrow_phase.dart:2265-2341)"); }
   if (per_pair_count)
     for (int k = 0; k < np; k++) per_pair_count[k] = w.perPairCount[k];
   return export_contacts(cw, out, n_contacts);
@@ -619,7 +654,10 @@ int32_t cannon_integrate(cannon_world* cw, double dt) {
 
 int32_t cannon_world_step(cannon_world* cw, double dt, int32_t nsteps) {
   if (!cw || nsteps < 0) return CANNON_E_INVALID;
-  for (int s = 0; s < nsteps; s++) cw->w.internalStep(dt);
+  for (int s = 0; s < nsteps; s++) {
+    cw->w.internalStep(dt);
+    if (cw->w.unsupportedPair) { cw->w.unsupportedPair = false; return fail(cw->ctx, CANNON_E_UNSUPPORTED, "a trimesh met a box / convex / particle / trimesh: the reference's resolvers for these pairs are unfinished (narrow_phase.dart:2265-2341)"); }
+  }
   return CANNON_OK;
 }
 
@@ -697,7 +735,7 @@ int32_t cannon_world_raycast(cannon_world* cw, int32_t n_rays, const float* from
   if (opt->mode != CANNON_RAY_CLOSEST && opt->mode != CANNON_RAY_ANY && opt->mode != CANNON_RAY_ALL) return fail(cw->ctx, CANNON_E_INVALID, "ray mode");
   World& w = cw->w;
   for (const Shape& s : w.shapes)
-    if (s.type == CANNON_SHAPE_HEIGHTFIELD) return fail(cw->ctx, CANNON_E_UNSUPPORTED, "heightfield rays are outside the hot-path scope (SURVEY.md 8f)");
+    if (s.type == CANNON_SHAPE_HEIGHTFIELD || s.type == CANNON_SHAPE_TRIMESH) return fail(cw->ctx, CANNON_E_UNSUPPORTED, "heightfield / trimesh rays are outside the hot-path scope (SURVEY.md 8f)");
   const bool all = opt->mode == CANNON_RAY_ALL;
   if (!all && hits->capacity < n_rays) { *n_hits = n_rays; return fail(cw->ctx, CANNON_E_CAPACITY, "hit arrays smaller than n_rays"); }
   std::vector<RayHit> seq;

@@ -770,6 +770,100 @@ struct NP {
         }
   }
 
+  // Ray.pointInTriangle, ray_class.dart:697-709
+  static bool pointInTriangle(const V3& p, const V3& a, const V3& b, const V3& c) {
+    const V3 v0 = sub(c, a), v1 = sub(b, a), v2 = sub(p, a);
+    const double dot00 = dot(v0, v0), dot01 = dot(v0, v1), dot02 = dot(v0, v2), dot11 = dot(v1, v1), dot12 = dot(v1, v2);
+    const double u = dot11 * dot02 - dot01 * dot12;
+    const double v = dot00 * dot12 - dot01 * dot02;
+    return u >= 0 && v >= 0 && (u + v) < (dot00 * dot11 - dot01 * dot01);
+  }
+
+  // sphereTrimesh, narrow_phase.dart:1438-1691 as the Dart port runs it: every triangle in index order (the octree query
+  // of :1480 is not used), and per corner j a vertex test, an edge test and the triangle-face test (:1573-1603 sits inside
+  // the j loop, so a face contact appears three times)
+  void sphereTrimesh(const Shape& si, const Shape& sj, V3 xi, V3 xj, Q4 qj, int bi, int bj) {
+    const V3 local = point_to_local_frame(xj, qj, xi);
+    const double radiusSquared = si.radius * si.radius;
+    const int nT = (int)sj.tmIdx.size() / 3;
+    auto emitLocal = [&](V3 tmp) {  // :1549-1566 / :1586-1601
+      Eq r = createContactEquation(bi, bj, si.collisionResponse, sj.collisionResponse);
+      r.ni = sub(tmp, local);
+      normalize(r.ni);
+      r.ri = scale(si.radius, r.ni);
+      r.ri = add(r.ri, xi);
+      r.ri = sub(r.ri, w.bodies[bi].position);
+      tmp = point_to_world_frame(xj, qj, tmp);
+      r.rj = sub(tmp, w.bodies[bj].position);
+      r.ni = qvmult(qj, r.ni);
+      r.ri = qvmult(qj, r.ri);
+      addContact(r);
+    };
+    for (int i = 0; i < nT; i++)
+      for (int j = 0; j < 3; j++) {
+        {
+          V3 v = sj.tmVerts[sj.tmIdx[i * 3 + j]];
+          V3 relpos = sub(v, local);
+          if (length2(relpos) <= radiusSquared) {
+            v = point_to_world_frame(xj, qj, v);
+            relpos = sub(v, xi);
+            Eq r = createContactEquation(bi, bj, si.collisionResponse, sj.collisionResponse);
+            r.ni = relpos;
+            normalize(r.ni);
+            r.ri = scale(si.radius, r.ni);
+            r.ri = add(r.ri, xi);
+            r.ri = sub(r.ri, w.bodies[bi].position);
+            r.rj = sub(v, w.bodies[bj].position);
+            addContact(r);
+          }
+          const V3 edgeVertexA = sj.tmVerts[sj.tmIdx[i * 3 + j]], edgeVertexB = sj.tmVerts[sj.tmIdx[i * 3 + ((j + 1) % 3)]];
+          const V3 edgeVector = sub(edgeVertexB, edgeVertexA);
+          V3 tmp = sub(local, edgeVertexB);
+          const double positionAlongEdgeB = dot(tmp, edgeVector);
+          tmp = sub(local, edgeVertexA);
+          double positionAlongEdgeA = dot(tmp, edgeVector);
+          if (positionAlongEdgeA > 0 && positionAlongEdgeB < 0) {
+            tmp = sub(local, edgeVertexA);
+            V3 edgeVectorUnit = edgeVector;
+            normalize(edgeVectorUnit);
+            positionAlongEdgeA = dot(tmp, edgeVectorUnit);
+            tmp = scale(positionAlongEdgeA, edgeVectorUnit);
+            tmp = add(tmp, edgeVertexA);
+            const double dist = distance_to(tmp, local);
+            if (dist < si.radius) emitLocal(tmp);
+          }
+        }
+        {
+          const V3 &va = sj.tmVerts[sj.tmIdx[i * 3]], &vb = sj.tmVerts[sj.tmIdx[i * 3 + 1]], &vc = sj.tmVerts[sj.tmIdx[i * 3 + 2]];
+          const V3& normal = sj.tmNormals[i];
+          V3 tmp = sub(local, va);
+          double dist = dot(tmp, normal);
+          tmp = scale(dist, normal);
+          tmp = sub(local, tmp);
+          dist = distance_to(tmp, local);
+          if (pointInTriangle(tmp, va, vb, vc) && dist < si.radius) emitLocal(tmp);
+        }
+      }
+  }
+
+  // planeTrimesh, narrow_phase.dart:1916-1980
+  void planeTrimesh(const Shape& planeShape, const Shape& sj, V3 planePos, V3 xj, Q4 planeQuat, Q4 qj, int planeBody, int bj) {
+    const V3 normal = qvmult(planeQuat, V3{0, 0, 1});
+    for (size_t i = 0; i < sj.tmVerts.size(); i++) {
+      const V3 v = point_to_world_frame(xj, qj, sj.tmVerts[i]);
+      const V3 relpos = sub(v, planePos);
+      if (dot(normal, relpos) <= 0.0) {
+        Eq r = createContactEquation(planeBody, bj, planeShape.collisionResponse, sj.collisionResponse);
+        r.ni = normal;
+        V3 projected = scale(dot(relpos, normal), normal);
+        projected = sub(v, projected);
+        r.ri = sub(projected, w.bodies[planeBody].position);
+        r.rj = sub(v, w.bodies[bj].position);
+        addContact(r);
+      }
+    }
+  }
+
   // box, convex, cylinder, capsule, cone, sizedPlane: every one of them reaches the convex resolvers (narrow_phase.dart:131-184)
   static bool isHullType(int t) { return t >= CANNON_SHAPE_BOX && t <= CANNON_SHAPE_SIZED_PLANE; }
 
@@ -778,6 +872,12 @@ struct NP {
   void resolve(Shape& sa, Shape& sb, V3 xa, V3 xb, Q4 qa, Q4 qb, int ba, int bb) {
     const int ta = sa.type, tb = sb.type;
     manifold++;
+    if (tb == CANNON_SHAPE_TRIMESH) {  // narrow_phase.dart:212-238; heightfield-trimesh has no key
+      if (ta == CANNON_SHAPE_SPHERE) sphereTrimesh(sa, sb, xa, xb, qb, ba, bb);
+      else if (ta == CANNON_SHAPE_PLANE) planeTrimesh(sa, sb, xa, xb, qa, qb, ba, bb);
+      else if (ta != CANNON_SHAPE_HEIGHTFIELD) w.unsupportedPair = true;  // boxTrimesh / trimeshConvex / particleTrimesh / trimeshTrimesh: unfinished in the reference
+      return;
+    }
     if (tb == CANNON_SHAPE_PARTICLE) {  // narrow_phase.dart:196-211; particle-particle has no key
       if (ta == CANNON_SHAPE_SPHERE) sphereParticle(sa, sb, xa, xb, ba, bb);
       else if (ta == CANNON_SHAPE_PLANE) planeParticle(sa, sb, xa, xb, ba, bb);

@@ -162,6 +162,21 @@ void shape_world_aabb(const Shape& s, const V3& pos, const Q4& q, V3& mn, V3& mx
       }
       break;
     }
+    case CANNON_SHAPE_TRIMESH: {  // trimesh.dart:366-375: AABB.toWorldFrame of the local AABB (aabb.dart:175-187,216-237, setFromPoints :45-82)
+      const V3 &l = s.tmLo, &u = s.tmHi;
+      const V3 c[8] = {l, V3{u.x, l.y, l.z}, V3{u.x, u.y, l.z}, V3{l.x, u.y, u.z}, V3{u.x, l.y, u.z}, V3{l.x, u.y, l.z}, V3{l.x, l.y, u.z}, u};
+      for (int i = 0; i < 8; i++) {
+        const V3 p = point_to_world_frame(pos, q, c[i]);
+        if (i == 0) { mn = p; mx = p; continue; }
+        if (p.x > mx.x) mx.x = p.x;
+        if (p.x < mn.x) mn.x = p.x;
+        if (p.y > mx.y) mx.y = p.y;
+        if (p.y < mn.y) mn.y = p.y;
+        if (p.z > mx.z) mx.z = p.z;
+        if (p.z < mn.z) mn.z = p.z;
+      }
+      break;
+    }
     case CANNON_SHAPE_PARTICLE:  // particle.dart:29-33
       mn = pos;
       mx = pos;

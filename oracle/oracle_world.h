@@ -47,6 +47,10 @@ struct Shape {
   double h(int i, int j) const { return data[(size_t)i * ny + j]; }
   // Heightfield._cachedPillars (heightfield.dart:52,285-301; cacheEnabled = true): one ConvexPolyhedron object per
   // (xi, yi, upper), kept for the life of the shape. Only the frozen world geometry of particleConvex is state.
+  // trimesh (trimesh.dart): getVertex results (scale applied), triangle indices, face normals, local AABB
+  std::vector<V3> tmVerts, tmNormals;
+  std::vector<int> tmIdx;
+  V3 tmLo{0, 0, 0}, tmHi{0, 0, 0};
   struct PillarWorld { std::vector<V3> worldVertices, worldFaceNormals; };
   std::map<long long, PillarWorld> pillarWorld;
 };
@@ -150,6 +154,7 @@ struct World {
   std::vector<int> sapAxisList;
   // outputs of the last stages
   std::vector<int> p1, p2;
+  bool unsupportedPair = false;  // a pair only the reference's unfinished trimesh resolvers would handle reached getContacts
   // cannon_world_set_body_shapes: the table the next set_bodies consumes
   std::vector<int> pendFirst, pendShape;
   std::vector<V3> pendOffset;
