@@ -61,6 +61,11 @@ class ShapeDesc(C.Structure):
     ]
 
 
+class SphDesc(C.Structure):
+    _fields_ = [("n_particles", c_i32), ("particles", P(c_i32)), ("density", c_f64), ("smoothing_radius", c_f64), ("speed_of_sound", c_f64),
+                ("viscosity", c_f64), ("eps", c_f64)]
+
+
 # (field, ctypes element type, numpy dtype, components per body)
 BODY_FIELDS = [
     ("position", c_f32, np.float32, 3), ("quaternion", c_f32, np.float32, 4),
@@ -164,6 +169,8 @@ PROTOTYPES = {
     "cannon_world_destroy": (None, [VP]),
     "cannon_world_set_materials": (c_i32, [VP, c_i32, P(c_f64), P(c_f64), c_i32, P(ContactMaterialPOD)]),
     "cannon_world_set_shapes": (c_i32, [VP, c_i32, P(ShapeDesc)]),
+    "cannon_sph_desc_default": (None, [P(SphDesc)]),
+    "cannon_world_set_sph_systems": (c_i32, [VP, c_i32, P(SphDesc)]),
     "cannon_world_set_body_shapes": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_f32), P(c_f32)]),
     "cannon_world_set_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_get_bodies": (c_i32, [VP, P(BodiesSoA)]),

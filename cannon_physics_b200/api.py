@@ -26,7 +26,7 @@ from . import _ffi as F
 from .engine import Context, DeviceWorld, SceneSpec
 
 __all__ = [
-    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle", "Trimesh",
+    "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle", "Trimesh", "SPHSystem",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
     "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
     "World",
@@ -305,6 +305,28 @@ class Trimesh(Shape):  # trimesh.dart:37 (sphere and plane contacts; the referen
                     d = (tubularSegments + 1) * j + i
                     idx += [a, b, d, b, c, d]
         return Trimesh(np.array(verts, np.float64), idx)
+
+
+class SPHSystem:  # lib/objects/sph_system.dart:6 (append to World.subsystems)
+    def __init__(self):
+        self.particles: List["Body"] = []
+        self.density, self.smoothingRadius, self.speedOfSound, self.viscosity, self.eps = 1.0, 1.0, 1.0, 0.01, 0.00001
+        self._world: Optional["World"] = None
+
+    def add(self, particle: "Body"):
+        self.particles.append(particle)
+        if self._world is not None:
+            self._world._structure_dirty = True
+
+    def remove(self, particle: "Body"):
+        if particle in self.particles:
+            self.particles.remove(particle)
+            if self._world is not None:
+                self._world._structure_dirty = True
+
+    def _desc(self, idx):
+        return dict(particles=[idx[id(p)] for p in self.particles], density=self.density, smoothing_radius=self.smoothingRadius,
+                    speed_of_sound=self.speedOfSound, viscosity=self.viscosity, eps=self.eps)
 
 
 class Heightfield(Shape):  # heightfield.dart:34
@@ -630,6 +652,8 @@ class World:  # lib/world/world_class.dart:44
         self.bodies: List[Body] = []
         self.constraints: List[Constraint] = []
         self.springs: List[Spring] = []
+        self.subsystems: List["SPHSystem"] = []  # world_class.dart:121; a plain list in the reference, so changes are detected by signature
+        self._sub_sig = ()
         self.contactmaterials: List[ContactMaterial] = []
         self.defaultMaterial = Material(name="default")
         self.defaultContactMaterial = ContactMaterial(self.defaultMaterial, self.defaultMaterial, friction=0.3, restitution=0.0)
@@ -792,12 +816,21 @@ class World:  # lib/world/world_class.dart:44
                     for body in self.bodies if True) if self.bodies else True
         body_shapes = None if plain else dict(first=np.array(inst_first, np.int32), shape=np.array(inst_shape, np.int32),
                                               offset=np.array(inst_off, np.float32).reshape(-1, 3), orientation=np.array(inst_ori, np.float32).reshape(-1, 4))
-        return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n, body_shapes=body_shapes,
+        for sub_ in self.subsystems:
+            for p_ in sub_.particles:
+                if id(p_) not in idx:
+                    raise CannonError(F.E_INVALID, "an SPH particle is not a body of the world")
+        return SceneSpec(desc=desc, shapes=shapes, bodies=b, n_bodies=n, body_shapes=body_shapes, sph_systems=[s_._desc(idx) for s_ in self.subsystems],
                          material_friction=np.array([m.friction for m in mats], dtype=np.float64) if mats else None,
                          material_restitution=np.array([m.restitution for m in mats], dtype=np.float64) if mats else None,
                          contact_materials=cms, constraints=cons, springs=[sp._desc(idx) for sp in self.springs], name="api_world")
 
     def _ensure_uploaded(self):
+        sig = tuple((id(s_), tuple(id(p_) for p_ in s_.particles), s_.density, s_.smoothingRadius, s_.speedOfSound, s_.viscosity, s_.eps) for s_ in self.subsystems)
+        if sig != self._sub_sig:
+            if self._dev is not None:
+                self._pull()
+            self._structure_dirty, self._sub_sig = True, sig
         if self._structure_dirty or self._dev is None:
             spec = self._spec()  # may refuse (dangling constraint): the old device world stays usable
             if self._dev is not None:

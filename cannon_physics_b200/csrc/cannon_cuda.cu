@@ -25,6 +25,7 @@
 #include "k_gs_exact.cuh"
 #include "k_gs_world_exact.cuh"
 #include "k_raycast.cuh"
+#include "k_sph.cuh"
 #include "world.cuh"
 
 // ---- device counters ---------------------------------------------------------------------------------
@@ -163,6 +164,9 @@ struct cannon_world {
   DBuf<int> dFacesK;
   DBuf<PillarRec> dPillars;
   // particleConvex state of the shape table (ShapeTables.pc*): only allocated when a Particle shape exists
+  // SPHSystem subsystems (k_sph.cuh)
+  struct HostSph { int n = 0; double density = 1, h = 1, cs = 1, viscosity = 0.01, eps = 0.00001; DBuf<int> particles; DBuf<double> densities, pressures; };
+  std::vector<HostSph> sph;
   bool hasParticle = false, hasTrimesh = false;
   std::vector<TrimeshDev> hTms;
   std::vector<float4> hTmVerts, hTmNormals;
@@ -484,6 +488,7 @@ void cannon_world_destroy(cannon_world* w) {
   cudaStreamSynchronize(w->ctx->stream);
   // DBuf members are released explicitly (plain structs, no destructors)
 #define REL(x) w->x.release()
+  for (auto& hs : w->sph) { hs.particles.release(); hs.densities.release(); hs.pressures.release(); }
   REL(pos); REL(quat); REL(vel); REL(angvel); REL(force); REL(torque); REL(lam); REL(iiw0); REL(iiw1); REL(iiw2);
   REL(invI); REL(linF); REL(angF); REL(aabbLo); REL(aabbHi); REL(mass); REL(invMass); REL(brad); REL(ldamp); REL(adamp); REL(ldpow);
   REL(adpow); REL(sleepSpeed); REL(sleepTime); REL(tLastSleepy); REL(type); REL(sleep); REL(shape); REL(material); REL(group); REL(mask);
@@ -1086,6 +1091,35 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   return CANNON_OK;
 }
 
+void cannon_sph_desc_default(cannon_sph_desc* d) {
+  if (!d) return;
+  memset(d, 0, sizeof(*d));
+  d->density = 1; d->smoothing_radius = 1; d->speed_of_sound = 1; d->viscosity = 0.01; d->eps = 0.00001;  // sph_system.dart:10-17
+}
+
+int32_t cannon_world_set_sph_systems(cannon_world* w, int32_t n, const cannon_sph_desc* sd) {
+  if (w) drop_step_graph(w);
+  if (!w || n < 0 || (n > 0 && !sd)) return CANNON_E_INVALID;
+  cudaSetDevice(w->ctx->device);
+  cudaStream_t s = w->ctx->stream;
+  W_TRY(w, cudaStreamSynchronize(s));
+  for (auto& hs : w->sph) { hs.particles.release(); hs.densities.release(); hs.pressures.release(); }
+  w->sph.clear();
+  for (int k = 0; k < n; k++) {
+    if (sd[k].n_particles < 0 || (sd[k].n_particles > 0 && !sd[k].particles)) return fail(w->ctx, CANNON_E_INVALID, "SPH system needs its particle list");
+    for (int i = 0; i < sd[k].n_particles; i++)
+      if (sd[k].particles[i] < 0 || sd[k].particles[i] >= w->n) return fail(w->ctx, CANNON_E_INVALID, "SPH particle references unknown body");
+    w->sph.emplace_back();
+    auto& hs = w->sph.back();
+    hs.n = sd[k].n_particles; hs.density = sd[k].density; hs.h = sd[k].smoothing_radius; hs.cs = sd[k].speed_of_sound; hs.viscosity = sd[k].viscosity; hs.eps = sd[k].eps;
+    std::vector<int> pl(sd[k].particles, sd[k].particles + hs.n);
+    W_TRY(w, upload(hs.particles, pl, s));
+    W_TRY(w, hs.densities.reserve((size_t)std::max(hs.n, 1))); W_TRY(w, hs.pressures.reserve((size_t)std::max(hs.n, 1)));
+  }
+  W_TRY(w, cudaStreamSynchronize(s));
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs) {
   if (w) drop_step_graph(w);  // buffers may move: the captured step is rebuilt on the next cannon_world_step
   if (!w || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
@@ -1305,6 +1339,16 @@ static int32_t st_prestep(cannon_world* w, double dt, int doGravity, int forceAA
   if (forceAABB) P.needAABB = 1;
   if (!doGravity && !P.needAABB) return CANNON_OK;
   { g_kernel_launches++; k_prestep<<<grid_for(w, w->n, 256), 256, 0, w->ctx->stream>>>(body_arrays(w), shape_tables(w), P, doGravity); }
+  if (doGravity) {  // World.subsystems update between gravity and the broadphase (world_class.dart:472-475)
+    for (auto& hs : w->sph) {
+      if (hs.n == 0) continue;
+      SphDev S;
+      S.particles = hs.particles.p; S.densities = hs.densities.p; S.pressures = hs.pressures.p; S.n = hs.n;
+      S.density = hs.density; S.h = hs.h; S.h9 = pow(hs.h, 9); S.cs = hs.cs; S.viscosity = hs.viscosity; S.eps = hs.eps;
+      { g_kernel_launches++; k_sph_density<<<grid_for(w, hs.n, 128), 128, 0, w->ctx->stream>>>(body_arrays(w), S); }
+      { g_kernel_launches++; k_sph_forces<<<grid_for(w, hs.n, 128), 128, 0, w->ctx->stream>>>(body_arrays(w), S); }
+    }
+  }
   W_TRY(w, cudaGetLastError());
   return CANNON_OK;
 }

@@ -30,6 +30,8 @@ class SceneSpec:
     # compound bodies (cannon_world_set_body_shapes): dict(first=(n+1) int32, shape=(k) int32, offset=(k,3) f32 | None,
     # orientation=(k,4) f32 | None); None = one shape per body (the `shape` column of `bodies`)
     body_shapes: Optional[Dict] = None
+    # SPHSystem subsystems: dict(particles=[body indices], density=, smoothing_radius=, speed_of_sound=, viscosity=, eps=)
+    sph_systems: List[Dict] = field(default_factory=list)
     name: str = ""
 
 
@@ -104,6 +106,8 @@ class DeviceWorld:
             self.set_constraints(spec.constraints)
         if spec.springs:
             self.set_springs(spec.springs)
+        if spec.sph_systems:
+            self.set_sph_systems(spec.sph_systems)
 
     def _chk(self, code):
         _check(self.lib, self.ctx.handle, code)
@@ -174,6 +178,21 @@ class DeviceWorld:
                     setattr(d, k, v)
         self._chk(self.lib.cannon_world_set_shapes(self.handle, len(shapes), arr))
         self.n_shapes = len(shapes)
+
+    def set_sph_systems(self, systems: Sequence[Dict]):
+        """World.subsystems = [SPHSystem, ...] (sph_system.dart); particles are body indices in SPHSystem.add order."""
+        arr = (F.SphDesc * max(1, len(systems)))()
+        keep = []
+        for i, sd in enumerate(systems):
+            d = arr[i]
+            self.lib.cannon_sph_desc_default(C.byref(d))
+            pl = np.ascontiguousarray(sd["particles"], dtype=np.int32)
+            keep.append(pl)
+            d.n_particles, d.particles = len(pl), F.ptr(pl, F.c_i32)
+            for k, v in sd.items():
+                if k != "particles":
+                    setattr(d, k, float(v))
+        self._chk(self.lib.cannon_world_set_sph_systems(self.handle, len(systems), arr))
 
     def set_body_shapes(self, first, shape, offset=None, orientation=None):
         """Body.addShape(shape, offset, orientation) for every body: body b owns the instances [first[b], first[b+1])."""

@@ -148,6 +148,16 @@ final class CannonSpringDesc extends Struct {
   @Array(3) external Array<Float> localAnchorB;
 }
 
+final class CannonSphDesc extends Struct {
+  @Int32() external int nParticles;
+  external Pointer<Int32> particles;
+  @Double() external double density;
+  @Double() external double smoothingRadius;
+  @Double() external double speedOfSound;
+  @Double() external double viscosity;
+  @Double() external double eps;
+}
+
 final class CannonContactsSoa extends Struct {
   @Int32() external int capacity;
   external Pointer<Int32> bodyI;
@@ -264,6 +274,10 @@ class CannonCuda {
       Int32 Function(H, Int32, Pointer<CannonConstraintDesc>), int Function(H, int, Pointer<CannonConstraintDesc>)>('cannon_world_set_constraints');
   late final int Function(H, int, Pointer<CannonSpringDesc>) worldSetSprings =
       lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonSpringDesc>), int Function(H, int, Pointer<CannonSpringDesc>)>('cannon_world_set_springs');
+  late final void Function(Pointer<CannonSphDesc>) sphDescDefault =
+      lib.lookupFunction<Void Function(Pointer<CannonSphDesc>), void Function(Pointer<CannonSphDesc>)>('cannon_sph_desc_default');
+  late final int Function(H, int, Pointer<CannonSphDesc>) worldSetSphSystems =
+      lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonSphDesc>), int Function(H, int, Pointer<CannonSphDesc>)>('cannon_world_set_sph_systems');
   late final int Function(H, double) worldSetTime = lib.lookupFunction<Int32 Function(H, Double), int Function(H, double)>('cannon_world_set_time');
   late final int Function(H, Pointer<Double>, Pointer<Int64>) worldGetTime =
       lib.lookupFunction<Int32 Function(H, Pointer<Double>, Pointer<Int64>), int Function(H, Pointer<Double>, Pointer<Int64>)>('cannon_world_get_time');

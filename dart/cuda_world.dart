@@ -241,6 +241,19 @@ class CudaSession {
         }
       }
       check(cuda.worldSetConstraints(handle, _nConstraints, cd), 'cannon_world_set_constraints');
+      // World.subsystems (world_class.dart:121,472-475): the SPHSystem instances, particles as body indices in add() order
+      final sphs = world.subsystems.whereType<SPHSystem>().toList();
+      final sphd = a<CannonSphDesc>(sphs.length + 1);
+      for (var i = 0; i < sphs.length; i++) {
+        final sp = sphs[i];
+        cuda.sphDescDefault(sphd + i);
+        final pl = a<Int32>(sp.particles.length + 1);
+        for (var k = 0; k < sp.particles.length; k++) { pl[k] = sp.particles[k].index; }
+        sphd[i].nParticles = sp.particles.length; sphd[i].particles = pl;
+        sphd[i].density = sp.density; sphd[i].smoothingRadius = sp.smoothingRadius; sphd[i].speedOfSound = sp.speedOfSound;
+        sphd[i].viscosity = sp.viscosity; sphd[i].eps = sp.eps;
+      }
+      check(cuda.worldSetSphSystems(handle, sphs.length, sphd), 'cannon_world_set_sph_systems');
       check(cuda.worldSetTime(handle, world.time), 'cannon_world_set_time');
       check(cuda.worldSetStepnumber(handle, world.stepnumber), 'cannon_world_set_stepnumber');
     });

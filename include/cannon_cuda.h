@@ -328,6 +328,24 @@ int32_t cannon_world_set_body_shapes(cannon_world* world, int32_t n_bodies, cons
 /* World.addBody for all bodies at once (upload path); derives mass properties. */
 int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* bodies);
 int32_t cannon_world_get_bodies(cannon_world* w, cannon_bodies_soa* out);
+/* SPHSystem, lib/objects/sph_system.dart:6 (World.subsystems, updated after gravity and before the broadphase,
+ * world_class.dart:472-475). particles: body indices in SPHSystem.add order. update() (:62-163) is reproduced as written:
+ * neighbours are the particles within smoothingRadius in list order with the particle itself appended last; the
+ * pressure / viscosity sums read pressures[j] / densities[j] with j = the POSITION in that neighbour list, not the
+ * neighbour's own index (:131-133,142). math.pow(x, 2 | 3) of the kernel functions (:166-182) is evaluated correctly
+ * rounded (x*x; x*x*x through an exact product), pow(h, 9) by the host's libm. */
+typedef struct cannon_sph_desc {
+  int32_t n_particles;
+  const int32_t* particles;
+  double density;            /* 1 */
+  double smoothing_radius;   /* 1 */
+  double speed_of_sound;     /* 1 */
+  double viscosity;          /* 0.01 */
+  double eps;                /* 0.00001 */
+} cannon_sph_desc;
+void    cannon_sph_desc_default(cannon_sph_desc* d);
+int32_t cannon_world_set_sph_systems(cannon_world* world, int32_t n, const cannon_sph_desc* systems);
+
 /* World.addConstraint for all constraints at once. */
 int32_t cannon_world_set_constraints(cannon_world* w, int32_t n, const cannon_constraint_desc* cs);
 /* Springs applied in every step's postStep slot (see cannon_spring_desc); n = 0 removes them. */

@@ -396,6 +396,29 @@ int32_t cannon_world_set_hinge_motor(cannon_world* cw, int32_t constraint, int32
   return CANNON_OK;
 }
 
+void cannon_sph_desc_default(cannon_sph_desc* d) {
+  if (!d) return;
+  memset(d, 0, sizeof(*d));
+  d->density = 1; d->smoothing_radius = 1; d->speed_of_sound = 1; d->viscosity = 0.01; d->eps = 0.00001;  // sph_system.dart:10-17
+}
+
+int32_t cannon_world_set_sph_systems(cannon_world* cw, int32_t n, const cannon_sph_desc* sd) {
+  if (!cw || n < 0 || (n > 0 && !sd)) return CANNON_E_INVALID;
+  World& w = cw->w;
+  w.sphSystems.clear();
+  for (int k = 0; k < n; k++) {
+    World::Sph S;
+    if (sd[k].n_particles < 0 || (sd[k].n_particles > 0 && !sd[k].particles)) return fail(cw->ctx, CANNON_E_INVALID, "SPH system needs its particle list");
+    for (int i = 0; i < sd[k].n_particles; i++) {
+      if (sd[k].particles[i] < 0 || sd[k].particles[i] >= (int)w.bodies.size()) return fail(cw->ctx, CANNON_E_INVALID, "SPH particle references unknown body");
+      S.particles.push_back(sd[k].particles[i]);
+    }
+    S.density = sd[k].density; S.smoothingRadius = sd[k].smoothing_radius; S.speedOfSound = sd[k].speed_of_sound; S.viscosity = sd[k].viscosity; S.eps = sd[k].eps;
+    w.sphSystems.push_back(S);
+  }
+  return CANNON_OK;
+}
+
 int32_t cannon_world_set_constraints(cannon_world* cw, int32_t n, const cannon_constraint_desc* cs) {
   if (!cw || n < 0 || (n > 0 && !cs)) return CANNON_E_INVALID;
   World& w = cw->w;
@@ -580,6 +603,7 @@ int32_t cannon_apply_gravity(cannon_world* cw) {
       bi.force.y = (float)(D(bi.force.y) + bi.mass * gy);
       bi.force.z = (float)(D(bi.force.z) + bi.mass * gz);
     }
+  w.sphUpdate();  // the subsystems run between gravity and the broadphase (world_class.dart:472-475)
   return CANNON_OK;
 }
 

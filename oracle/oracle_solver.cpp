@@ -600,6 +600,73 @@ void World::applySprings() {
   }
 }
 
+// math.pow(x, 3) correctly rounded: x*x exactly as hi + lo (fma), times x in double-double, rounded once. A libm pow with
+// < 1 ulp error agrees except when the exact cube lies within its error of a rounding boundary.
+static inline double pow3_cr(double x) {
+  const double hi = x * x, lo = std::fma(x, x, -hi);
+  const double p = hi * x, e = std::fma(hi, x, -p);
+  return p + (e + lo * x);
+}
+
+// SPHSystem.update, sph_system.dart:62-163 (w :166-170, gradw :173-177, nablaw :180-184)
+void World::sphUpdate() {
+  for (const Sph& S : sphSystems) {
+    const int N = (int)S.particles.size();
+    const double h = S.smoothingRadius, r2 = h * h, cs = S.speedOfSound, eps = S.eps;
+    const double h9 = std::pow(h, 9);
+    std::vector<double> densities(N), pressures(N);
+    std::vector<std::vector<int>> neighbors(N);
+    for (int i = 0; i < N; i++) {
+      const Body& p = bodies[S.particles[i]];
+      std::vector<int>& nb = neighbors[i];
+      for (int k = 0; k < N; k++) {  // getNeighbors :50-60
+        const Body& q = bodies[S.particles[k]];
+        const V3 dist = sub(q.position, p.position);
+        if (S.particles[k] != S.particles[i] && length2(dist) < r2) nb.push_back(S.particles[k]);
+      }
+      nb.push_back(S.particles[i]);
+      double sum = 0.0;
+      for (int b : nb) {
+        const V3 dist = sub(p.position, bodies[b].position);
+        const double len = length(dist);
+        const double weight = (315.0 / (64.0 * M_PI * h9)) * pow3_cr(h * h - len * len);
+        sum += bodies[b].mass * weight;
+      }
+      densities[i] = sum;
+      pressures[i] = cs * cs * (densities[i] - S.density);
+    }
+    for (int i = 0; i < N; i++) {
+      Body& particle = bodies[S.particles[i]];
+      V3 aPressure{0, 0, 0}, aVisc{0, 0, 0};
+      const std::vector<int>& nb = neighbors[i];
+      for (int j = 0; j < (int)nb.size(); j++) {
+        const Body& neighbor = bodies[nb[j]];
+        const V3 rVec = sub(particle.position, neighbor.position);
+        const double r = length(rVec);
+        // pressures[j] / densities[j]: indexed by the position in the neighbour list (:131-133), as written
+        const double pij = -neighbor.mass * (pressures[i] / (densities[i] * densities[i] + eps) + pressures[j] / (densities[j] * densities[j] + eps));
+        V3 gradW;
+        {  // gradw: r is recomputed from rVec (:174)
+          const double rr = length(rVec);
+          const double q = h * h - rr * rr;
+          gradW = scale(945.0 / (32.0 * M_PI * h9) * (q * q), rVec);
+        }
+        gradW = scale(pij, gradW);
+        aPressure = add(aPressure, gradW);
+        V3 u = sub(neighbor.velocity, particle.velocity);
+        u = scale((1.0 / (0.0001 + densities[i] * densities[j])) * S.viscosity * neighbor.mass, u);
+        const double nabla = (945.0 / (32.0 * M_PI * h9)) * (h * h - r * r) * (7 * r * r - 3 * h * h);
+        u = scale(nabla, u);
+        aVisc = add(aVisc, u);
+      }
+      aVisc = scale(particle.mass, aVisc);
+      aPressure = scale(particle.mass, aPressure);
+      particle.force = add(particle.force, aVisc);
+      particle.force = add(particle.force, aPressure);
+    }
+  }
+}
+
 // World.internalStep + the `time += dt` of World.step, world_class.dart:392-399,433-701
 void World::internalStep(double h) {
   dt = h;
@@ -612,6 +679,7 @@ void World::internalStep(double h) {
       bi.force.z = (float)(D(bi.force.z) + m * gz);
     }
   }
+  sphUpdate();  // world_class.dart:472-475
   collisionPairs();
   getContacts();
   makeContactConstraints();

@@ -154,7 +154,11 @@ struct World {
   std::vector<int> sapAxisList;
   // outputs of the last stages
   std::vector<int> p1, p2;
-  bool unsupportedPair = false;  // a pair only the reference's unfinished trimesh resolvers would handle reached getContacts
+  bool unsupportedPair = false;
+  // SPHSystem, sph_system.dart (World.subsystems)
+  struct Sph { std::vector<int> particles; double density = 1, smoothingRadius = 1, speedOfSound = 1, viscosity = 0.01, eps = 0.00001; };
+  std::vector<Sph> sphSystems;
+  void sphUpdate();  // a pair only the reference's unfinished trimesh resolvers would handle reached getContacts
   // cannon_world_set_body_shapes: the table the next set_bodies consumes
   std::vector<int> pendFirst, pendShape;
   std::vector<V3> pendOffset;
