@@ -31,7 +31,23 @@ CASES = {
     # World(quatNormalizeFast: true, quatNormalizeSkip: 2, frictionGravity: ...) (world_class.dart:135-144,668; quaternion.dart:171-185)
     "c2_quatfast_small": (lambda: _with(scenes.mixed_pile_on_heightfield(4, 4, 3, with_heightfield=False, solver=REF, grid_cells=(8, 4, 8)),
                                         quat_normalize_fast=1, quat_normalize_skip=2, has_friction_gravity=1, friction_gravity=(0, -3, 0)), 90),
+    # SURVEY 8f rank 4 (the scene builders live next to their tests): hull subclasses, Particle, compound bodies, Trimesh, SPH
+    "hulls_small": (lambda: _t("test_hull_shapes")._mixed_spec("heightfield"), 90),
+    "particles_small": (lambda: _t("test_particle")._pile_spec("heightfield", n_part=24), 90),
+    "compound_small": (lambda: _t("test_compound")._pile_spec("heightfield", n_obj=8), 90),
+    "compound_colored_small": (lambda: _t("test_compound")._pile_spec("plane", solver=F.SOLVER_COLORED, n_obj=8), 90),
+    "trimesh_small": (lambda: _t("test_trimesh")._terrain_spec(scale=(1.25, 0.75, 1.0)), 80),
+    "sph_small": (lambda: _t("test_sph")._block_spec(4, 3, 4), 60),
 }
+RANK4_CASES = ["hulls_small", "particles_small", "compound_small", "compound_colored_small", "trimesh_small", "sph_small"]
+
+
+def _t(module):
+    import importlib
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    return importlib.import_module(module)
 
 
 def _with(spec, **desc):
@@ -86,11 +102,16 @@ def run_events(lib, make_spec, steps):
 if __name__ == "__main__":
     lib = F.bind(os.path.join(ROOT, "oracle", "libcannon_oracle.so"))
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    only = sys.argv[1:]  # optional: fixture names to (re)write; default all
     for name, (mk, steps) in CASES.items():
+        if only and name not in only:
+            continue
         res = run_case(lib, mk, steps)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **res)
         print(name, {k: v.shape for k, v in res.items() if k in ("p1", "c_bi", "row_B")})
     for name, (mk, steps) in EVENT_CASES.items():
+        if only and name not in only:
+            continue
         res = run_events(lib, mk, steps)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **res)
         print(name, {k: v.shape for k, v in res.items()})

@@ -218,7 +218,8 @@ def test_cone_equation_limits_the_swing(oracle_lib):
 
 
 GOLDEN_CASES = ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small",
-                "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small"]
+                "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small",
+                "hulls_small", "particles_small", "compound_small", "compound_colored_small", "trimesh_small", "sph_small"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)

@@ -183,7 +183,8 @@ def test_world_options_quat_normalize_and_friction_gravity(cuda_lib, oracle_lib,
 
 
 @pytest.mark.parametrize("name", ["c1_small", "c2_small", "c3_plane_small", "c3_hf_small", "c4_small", "c5_small", "joints_small",
-                                  "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small"])
+                                  "c2_colored_small", "c3_hf_colored_small", "c4_colored_small", "c2_quatfast_small",
+                                  "hulls_small", "particles_small", "compound_small", "compound_colored_small", "trimesh_small", "sph_small"])
 def test_cuda_matches_golden_fixture(cuda_lib, name):
     from make_golden import CASES, run_case
     got = run_case(cuda_lib, *CASES[name])
