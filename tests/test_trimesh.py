@@ -93,11 +93,11 @@ def _terrain_spec(solver=None, seed=2, scale=(1, 1, 1)):
     shape = np.zeros(n, np.int32)
     pos[0], mass[0], shape[0] = (0, 0.5, 0), 0, 0                       # static terrain mesh half a metre above ...
     pos[1], mass[1], shape[1], quat[1] = (0, 0, 0), 0, 1, scenes.GROUND_QUAT  # ... the ground plane
-    pos[2], shape[2] = (6, 1.0, 0), 2                                   # a dynamic torus mesh that only meets the plane and the spheres
+    pos[2], shape[2] = (12, 1.0, 0), 2                                  # a dynamic torus mesh that only meets the plane and the spheres
     q = rng.normal(size=4)
     quat[2] = (q / np.linalg.norm(q)).astype(np.float32)
     for k in range(14):
-        pos[3 + k] = (rng.uniform(-2.5, 2.5), rng.uniform(1.0, 3.5), rng.uniform(-2.5, 2.5)) if k < 11 else (6 + 0.3 * (k - 12), 2.0 + 0.8 * (k - 11), 0.1 * (k - 12))
+        pos[3 + k] = (rng.uniform(-2.5, 2.5), rng.uniform(1.0, 3.5), rng.uniform(-2.5, 2.5)) if k < 11 else (12 + 0.3 * (k - 12), 2.0 + 0.8 * (k - 11), 0.1 * (k - 12))
         shape[3 + k] = 3 + (k % 2)
     desc = dict(gravity=(0, -10, 0))
     if solver is not None:
