@@ -171,6 +171,7 @@ PROTOTYPES = {
     "cannon_world_set_shapes": (c_i32, [VP, c_i32, P(ShapeDesc)]),
     "cannon_sph_desc_default": (None, [P(SphDesc)]),
     "cannon_world_set_sph_systems": (c_i32, [VP, c_i32, P(SphDesc)]),
+    "cannon_batch_set_body_shapes": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_f32), P(c_f32)]),
     "cannon_world_set_body_shapes": (c_i32, [VP, c_i32, P(c_i32), P(c_i32), P(c_f32), P(c_f32)]),
     "cannon_world_set_bodies": (c_i32, [VP, P(BodiesSoA)]),
     "cannon_world_get_bodies": (c_i32, [VP, P(BodiesSoA)]),

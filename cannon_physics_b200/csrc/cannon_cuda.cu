@@ -942,6 +942,7 @@ int32_t cannon_world_set_bodies(cannon_world* w, const cannon_bodies_soa* sb) {
   w->nInst = 0;
   w->maxInst = 1;
   if (haveTable) {
+    for (int sh : w->hInstShape) if (sh >= (int)w->hShapes.size()) return fail(w->ctx, CANNON_E_INVALID, "the body shape table references a shape the current shape table does not have");
     w->nInst = w->hInstFirst[n];
     w->hInstBody.assign(w->nInst, 0);
     for (int i = 0; i < n; i++) {

@@ -467,7 +467,8 @@ class DeviceWorld:
 class _BatchCalls:
     """The upload / download entry points DeviceWorld's marshalling code calls, mapped onto their cannon_batch_* twins."""
     _MAP = {"cannon_world_set_materials": "cannon_batch_set_materials", "cannon_world_set_shapes": "cannon_batch_set_shapes",
-            "cannon_world_set_bodies": "cannon_batch_set_bodies", "cannon_world_set_constraints": "cannon_batch_set_constraints",
+            "cannon_world_set_bodies": "cannon_batch_set_bodies", "cannon_world_set_body_shapes": "cannon_batch_set_body_shapes",
+            "cannon_world_set_constraints": "cannon_batch_set_constraints",
             "cannon_world_get_bodies": "cannon_batch_get_bodies", "cannon_world_step": "cannon_batch_step"}
 
     def __init__(self, lib):
@@ -493,8 +494,8 @@ class DeviceBatch(DeviceWorld):
         n_worlds = int(spec.desc.get("n_worlds", 1))
         if spec.n_bodies % n_worlds:
             raise ValueError("a batch needs the same number of bodies in every world")
-        if spec.springs:
-            raise F.CannonError(F.E_UNSUPPORTED, "springs have no batch entry point")
+        if spec.springs or spec.sph_systems:
+            raise F.CannonError(F.E_UNSUPPORTED, "springs / SPH systems have no batch entry point")
         desc = make_world_desc(lib, **spec.desc)
         self.desc = desc
         self.handle = F.VP()
@@ -505,6 +506,8 @@ class DeviceBatch(DeviceWorld):
         self.n = 0
         self.set_materials(spec.material_friction, spec.material_restitution, spec.contact_materials)
         self.set_shapes(spec.shapes)
+        if spec.body_shapes is not None:
+            self.set_body_shapes(**spec.body_shapes)
         self.set_bodies({k: v for k, v in spec.bodies.items() if k != "world_id"}, spec.n_bodies)
         if spec.constraints:
             self.set_constraints(spec.constraints)

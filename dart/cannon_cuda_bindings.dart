@@ -357,6 +357,9 @@ class CannonCuda {
       lib.lookupFunction<Int32 Function(H, Int32, Pointer<CannonShapeDesc>), int Function(H, int, Pointer<CannonShapeDesc>)>('cannon_batch_set_shapes');
   late final int Function(H, Pointer<CannonBodiesSoa>) batchSetBodies =
       lib.lookupFunction<Int32 Function(H, Pointer<CannonBodiesSoa>), int Function(H, Pointer<CannonBodiesSoa>)>('cannon_batch_set_bodies');
+  late final int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>) batchSetBodyShapes = lib.lookupFunction<
+      Int32 Function(H, Int32, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>),
+      int Function(H, int, Pointer<Int32>, Pointer<Int32>, Pointer<Float>, Pointer<Float>)>('cannon_batch_set_body_shapes');
   late final int Function(H, int, Pointer<CannonConstraintDesc>) batchSetConstraints = lib.lookupFunction<
       Int32 Function(H, Int32, Pointer<CannonConstraintDesc>), int Function(H, int, Pointer<CannonConstraintDesc>)>('cannon_batch_set_constraints');
   late final int Function(H, double, int) batchStep = lib.lookupFunction<Int32 Function(H, Double, Int32), int Function(H, double, int)>('cannon_batch_step');

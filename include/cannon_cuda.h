@@ -485,6 +485,8 @@ const char* cannon_batch_last_error(const cannon_batch* b);
 int32_t     cannon_batch_set_materials(cannon_batch* b, int32_t n_materials, const double* friction, const double* restitution,
                                        int32_t n_contact_materials, const cannon_contact_material* cms);
 int32_t     cannon_batch_set_shapes(cannon_batch* b, int32_t n_shapes, const cannon_shape_desc* shapes);
+int32_t     cannon_batch_set_body_shapes(cannon_batch* b, int32_t n_bodies, const int32_t* first, const int32_t* shape,
+                                         const float* offset, const float* orientation);  /* cannon_world_set_body_shapes over the whole batch, before set_bodies */
 int32_t     cannon_batch_set_bodies(cannon_batch* b, const cannon_bodies_soa* bodies);   /* world_id is derived, not read */
 int32_t     cannon_batch_set_constraints(cannon_batch* b, int32_t n, const cannon_constraint_desc* cs);
 int32_t     cannon_batch_step(cannon_batch* b, double dt, int32_t nsteps);

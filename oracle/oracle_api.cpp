@@ -245,6 +245,7 @@ int32_t cannon_world_set_bodies(cannon_world* cw, const cannon_bodies_soa* s) {
   World& w = cw->w;
   const int n = s->n;
   if (!w.pendFirst.empty() && (int)w.pendFirst.size() != n + 1) return fail(cw->ctx, CANNON_E_INVALID, "cannon_world_set_body_shapes described another body count");
+  for (int sh : w.pendShape) if (sh >= (int)w.shapes.size()) return fail(cw->ctx, CANNON_E_INVALID, "the body shape table references a shape the current shape table does not have");
   w.bodies.clear();
   w.bodies.resize(n);
   w.sapAxisList.clear();

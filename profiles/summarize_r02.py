@@ -40,6 +40,9 @@ WHY = {
     "k_scan_onepass": "single-pass look-back scan: tiles wait for their predecessors, ~20 us fixed latency per scan whatever the size",
     "k_integrate": "the one streaming kernel of the step: 100k bodies x ~250 B; too small to reach steady state (13 us)",
     "k_prestep": "streaming, too small to reach steady state",
+    "k_bp_world_all": "all-pairs Naive broadphase of a small world, one warp per body with ballots: latency of one pass over <= 64 bodies",
+    "k_schedule_worlds": "Jones-Plassmann colouring per world (one warp, claims in shared memory, units in registers): a few dependent rounds, no grid barrier",
+    "k_world_keys": "per-world min / max of the contact keys (world-local colouring priorities): one atomic per warp and world",
     "k_gs_world_exact": "one warp per world, rows in shared memory: conversion-pipe latency of a lone warp per SM sub-partition (DRAM is only touched when the rows are staged)",
 }
 

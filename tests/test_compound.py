@@ -189,3 +189,58 @@ def test_compound_rays_and_events_parity(cuda_lib, oracle_lib):
         for k in ("has_hit", "body", "distance", "hit_point_world", "hit_normal_world", "hit_face_index"):
             assert np.array_equal(a[k], b[k]), (mode, k)
     assert a["n_hits"] > 20
+
+
+def _batch_spec(n_worlds=5, solver=None):
+    """n_worlds copies (slightly perturbed) of: ground plane, a table, a dumbbell, a plain box - world-major, with world ids."""
+    shapes = [api.Box((0.7, 0.08, 0.45)), api.Box((0.08, 0.35, 0.08)), api.Cylinder(0.1, 0.1, 1.0, 8), api.Sphere(0.3), api.Box((0.3, 0.3, 0.3)), dict(type=F.SHAPE_PLANE)]
+    shapes = [s._desc() if hasattr(s, "_desc") else s for s in shapes]
+    rng = np.random.default_rng(12)
+    bodies, wid = [], []
+    for w in range(n_worlds):
+        bodies.append(dict(pos=(0, 0, 0), mass=0, quat=scenes.GROUND_QUAT, inst=[(5, None, None)]))
+        bodies.append(dict(pos=(0.05 * w, 0.9, 0), mass=2.0, inst=_table(0)))
+        bodies.append(dict(pos=(0.1, 1.8 + 0.02 * w, 0.05), mass=1.0, inst=[(3, (-0.5, 0, 0), None), (3, (0.5, 0, 0), None)],
+                           quat=(rng.normal(size=4) / 2).astype(np.float32)))
+        bodies.append(dict(pos=(-0.2, 2.6, 0.1 * w), mass=1.0, inst=[(4, None, None)]))
+        wid += [w] * 4
+    for b in bodies:
+        if "quat" in b and b["mass"] > 0:
+            q = np.asarray(b["quat"], np.float64)
+            b["quat"] = (q / np.linalg.norm(q)).astype(np.float32)
+    desc = dict(n_worlds=n_worlds)
+    if solver is not None:
+        desc["solver_kind"] = solver
+    spec = _spec(shapes, bodies, **desc)
+    spec.bodies["world_id"] = np.array(wid, np.int32)
+    return spec
+
+
+def test_batch_of_compound_worlds_is_shard_independent(oracle_lib):
+    """cannon_batch_set_body_shapes cuts the shape table at the shard boundaries (host glue shared by both libraries)."""
+    from cannon_physics_b200 import engine
+    fields = ("position", "quaternion", "velocity", "angular_velocity")
+    for solver in (F.SOLVER_REFERENCE_ORDER, F.SOLVER_COLORED):
+        spec = _batch_spec(5, solver)
+        whole = engine.DeviceWorld(oracle_lib, spec)
+        whole.step(1 / 60, 40)
+        ref = whole.get_bodies(fields)
+        assert len(whole.get_contacts()["body_i"]) > 10
+        for devices in ((0,), (0, 0), (0, 0, 0)):
+            b = engine.DeviceBatch(oracle_lib, spec, devices=devices)
+            b.step(1 / 60, 40)
+            got = b.get_bodies(fields)
+            for k in fields:
+                assert np.array_equal(got[k], ref[k]), (devices, k)
+            b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [F.SOLVER_REFERENCE_ORDER, F.SOLVER_COLORED])
+def test_batch_of_compound_worlds_parity(cuda_lib, oracle_lib, solver):
+    spec = _batch_spec(24, solver)
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, spec)
+    for s in range(0, 120, 40):
+        dev.step(1 / 60, 40)
+        ref.step(1 / 60, 40)
+        parity.assert_same_state(dev, ref, f"compound batch step {s + 40}")
