@@ -149,7 +149,10 @@ class ConvexPolyhedron(Shape):  # convex_polyhedron.dart:51
         self.uniqueAxes = None if axes is None else np.asarray(axes, dtype=np.float32).reshape(-1, 3)  # :105; only its presence is used
 
     def _desc(self):
-        return dict(super()._desc(), vertices=self.vertices, faces=self.faces, convex_has_axes=int(self.uniqueAxes is not None))
+        d = dict(super()._desc(), vertices=self.vertices, faces=self.faces, convex_has_axes=int(self.uniqueAxes is not None))
+        if getattr(self, "_ctor", None):
+            d["_ctor"] = self._ctor  # which reference constructor built this hull (tools/reference_golden replays it)
+        return d
 
 
 def _ring(radius, y, theta):  # Vector3(-r sin, y, r cos) as cylinder.dart:56,60 / cone.dart:44,49 write it
@@ -176,6 +179,7 @@ class Cone(ConvexPolyhedron):  # cone.dart:15-63: apex first, then the base ring
                 faces.append([0, 1, i + 1])
         faces.append(bottom)
         super().__init__(verts, faces, axes=[(0, 1, 0)], **kw)
+        self._ctor = dict(kind="Cone", radius=self.radius, height=self.height, numSegments=self.numSegments)
 
 
 class Capsule(ConvexPolyhedron):  # capsule.dart:15-170: cylinder walls + two (numSegments+1) x (numHeightSegments+1) vertex grids
@@ -221,6 +225,7 @@ class Capsule(ConvexPolyhedron):  # capsule.dart:15-170: cylinder walls + two (n
                     faces.append([a, b, d])
                     faces.append([b, c, d])
         super().__init__(verts + top + bot, faces, **kw)
+        self._ctor = dict(kind="Capsule", radiusTop=rt, radiusBottom=rb, height=h, numSegments=ns, numHeightSegments=nh)
 
 
 class SizedPlane(ConvexPolyhedron):  # sized_plane.dart:10-37: one quad in the y = 0 plane
@@ -230,6 +235,7 @@ class SizedPlane(ConvexPolyhedron):  # sized_plane.dart:10-37: one quad in the y
         self.width, self.height = float(width), float(height)
         sx, sz = self.width / 2, self.height / 2
         super().__init__([(-sx, 0, -sz), (sx, 0, -sz), (sx, 0, sz), (-sx, 0, sz)], [[3, 2, 1, 0]], **kw)
+        self._ctor = dict(kind="SizedPlane", width=self.width, height=self.height)
 
 
 class LatheShape(ConvexPolyhedron):  # lathe.dart:6-67: a Vector2 (f32) profile swept around y, two triangles per quad
@@ -252,6 +258,7 @@ class LatheShape(ConvexPolyhedron):  # lathe.dart:6-67: a Vector2 (f32) profile 
                 faces.append([a, b, d])
                 faces.append([c, d, b])
         super().__init__(verts, faces, **kw)
+        self._ctor = dict(kind="LatheShape", points=self.points.tolist(), numSegments=self.numSegments, phiStart=phiStart, phiLength=phiLength)
 
 
 class CapsuleLathe(LatheShape):  # capsule_lathe.dart:14-74: the capsule profile handed to LatheShape, reported as a capsule
@@ -269,6 +276,7 @@ class CapsuleLathe(LatheShape):  # capsule_lathe.dart:14-74: the capsule profile
         ptsBottom.append((0.0, -h * 0.5 - rb))
         ptsBottom.insert(0, (rb, -h * 0.5))
         super().__init__(ptsTop + ptsBottom, numSegments=numSegments, **kw)
+        self._ctor = dict(kind="CapsuleLathe", radiusTop=rt, radiusBottom=rb, height=h, numSegments=int(numSegments), numHeightSegments=int(numHeightSegments))
 
 
 class Particle(Shape):  # particle.dart:9: a point (bounding radius 0, zero inertia, AABB = its position)

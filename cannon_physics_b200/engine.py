@@ -145,6 +145,8 @@ class DeviceWorld:
             d = arr[i]
             self.lib.cannon_shape_desc_default(C.byref(d))
             for k, v in sh.items():
+                if k.startswith("_"):
+                    continue  # annotations for tools/reference_golden (e.g. the constructor that built a hull), not ABI fields
                 if k == "half_extents":
                     vv = np.asarray(v, dtype=np.float32)
                     for j in range(3):

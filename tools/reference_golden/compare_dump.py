@@ -28,7 +28,9 @@ def spec_from_json(s):
     return engine.SceneSpec(desc=s["desc"], shapes=shapes, bodies=b, n_bodies=s["n_bodies"],
                             material_friction=None if s["material_friction"] is None else np.asarray(s["material_friction"]),
                             material_restitution=None if s["material_restitution"] is None else np.asarray(s["material_restitution"]),
-                            contact_materials=s["contact_materials"], constraints=s["constraints"], springs=s["springs"], name=s["name"])
+                            contact_materials=s["contact_materials"], constraints=s["constraints"], springs=s["springs"], name=s["name"],
+                            body_shapes=None if s.get("body_shapes") is None else {k: (None if v is None else np.asarray(v)) for k, v in s["body_shapes"].items()},
+                            sph_systems=s.get("sph_systems") or [])
 
 
 def main():

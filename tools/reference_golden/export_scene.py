@@ -30,6 +30,8 @@ def export(spec, steps, dt=1 / 60, checkpoints=None):
         "bodies": jsonable(spec.bodies), "material_friction": jsonable(spec.material_friction),
         "material_restitution": jsonable(spec.material_restitution), "contact_materials": jsonable(spec.contact_materials),
         "constraints": jsonable(spec.constraints), "springs": jsonable(spec.springs),
+        # Body.addShape table (first / shape / offset / orientation) and the SPHSystem subsystems
+        "body_shapes": jsonable(spec.body_shapes), "sph_systems": jsonable(spec.sph_systems),
     }
 
 

@@ -21,9 +21,34 @@ Shape makeShape(Map s) {
     case 1: return Plane();
     case 2: return Box(v3(s['half_extents']));
     case 3:
+    case 5:
+    case 6:
+    case 7:
+      // hull subclasses: replay the reference constructor named by the exporter, so their vertex generation is pinned too
+      final c = s['_ctor'] as Map?;
+      if (c != null) {
+        switch (c['kind'] as String) {
+          case 'Cone': return Cone(radius: d(c['radius'], 1), height: d(c['height'], 1), numSegments: (c['numSegments'] ?? 8) as int);
+          case 'Capsule': return Capsule(radiusTop: d(c['radiusTop'], 1), radiusBottom: d(c['radiusBottom'], 1), height: d(c['height'], 1),
+              numSegments: (c['numSegments'] ?? 8) as int, numHeightSegments: (c['numHeightSegments'] ?? 4) as int);
+          case 'CapsuleLathe': return CapsuleLathe(radiusTop: d(c['radiusTop'], 1), radiusBottom: d(c['radiusBottom'], 1), height: d(c['height'], 1),
+              numSegments: (c['numSegments'] ?? 8) as int, numHeightSegments: (c['numHeightSegments'] ?? 4) as int);
+          case 'SizedPlane': return SizedPlane(d(c['width'], 1), d(c['height'], 1));
+          case 'LatheShape': return LatheShape(points: [for (final p in c['points'] as List) Vector2(((p as List)[0] as num).toDouble(), (p[1] as num).toDouble())],
+              numSegments: (c['numSegments'] ?? 8) as int, phiStart: d(c['phiStart'], 0), phiLength: d(c['phiLength'], 6.283185307179586));
+        }
+      }
       final verts = <Vector3>[for (final p in s['vertices'] as List) v3(p as List)];
       final faces = <List<int>>[for (final f in s['faces'] as List) [for (final i in f as List) i as int]];
-      return ConvexPolyhedron(vertices: verts, faces: faces);
+      return ConvexPolyhedron(vertices: verts, faces: faces, axes: (s['convex_has_axes'] ?? 0) != 0 ? [Vector3(0, 1, 0)] : null,
+          type: ShapeType.values[s['type'] as int]);
+    case 9: return Particle();
+    case 10:
+      final tv = <double>[for (final p in s['vertices'] as List) for (final x in p as List) (x as num).toDouble()];
+      final ti = <int>[for (final i in s['tm_indices'] as List) i as int];
+      final tm = Trimesh(tv, ti);
+      if (s['tm_scale'] != null) tm.setScale(v3(s['tm_scale'] as List));
+      return tm;
     case 4:
       return Cylinder(radiusTop: d(s['radius_top'], 1), radiusBottom: d(s['radius_bottom'], 1), height: d(s['height'], 1),
           numSegments: (s['num_segments'] ?? 8) as int);
@@ -93,6 +118,7 @@ void main(List<String> args) {
   // shapes are shared between bodies like in the reference's demos (examples/lib/examples/container.dart:105)
   final shapes = <Shape>[for (final s in scene['shapes'] as List) makeShape(s as Map)];
   List? arr(String k) => bodies[k] as List?;
+  final bodyShapes = scene['body_shapes'] as Map?;
   for (var i = 0; i < n; i++) {
     final mass = arr('mass') == null ? 0.0 : (arr('mass')![i] as num).toDouble();
     final q = arr('quaternion')?[i] as List?;
@@ -119,8 +145,17 @@ void main(List<String> args) {
       collisionFilterMask: arr('collision_filter_mask') == null ? -1 : arr('collision_filter_mask')![i] as int,
       collisionResponse: arr('collision_response') == null ? true : (arr('collision_response')![i] as int) != 0,
       isTrigger: arr('is_trigger') == null ? false : (arr('is_trigger')![i] as int) != 0,
-      shape: shapeIdx < 0 ? null : shapes[shapeIdx],
+      shape: (shapeIdx < 0 || bodyShapes != null) ? null : shapes[shapeIdx],
     );
+    if (bodyShapes != null) {  // Body.addShape(shape, offset, orientation) in table order (rigid_body.dart:348-377)
+      final first = bodyShapes['first'] as List, ish = bodyShapes['shape'] as List;
+      final off = bodyShapes['offset'] as List?, ori = bodyShapes['orientation'] as List?;
+      for (var k = first[i] as int; k < (first[i + 1] as int); k++) {
+        final o = ori == null ? null : ori[k] as List;
+        b.addShape(shapes[ish[k] as int], off == null ? null : v3(off[k] as List),
+            o == null ? null : Quaternion((o[0] as num).toDouble(), (o[1] as num).toDouble(), (o[2] as num).toDouble(), (o[3] as num).toDouble()));
+      }
+    }
     if (arr('force') != null) b.force.setFrom(v3(arr('force')![i] as List));
     if (arr('torque') != null) b.torque.setFrom(v3(arr('torque')![i] as List));
     if (arr('sleep_state') != null) b.sleepState = BodySleepStates.values[arr('sleep_state')![i] as int];
@@ -165,6 +200,16 @@ void main(List<String> args) {
   ];
   if (springs.isNotEmpty) {
     world.addEventListener('postStep', (e) { for (final s in springs) { s.applyForce(); } });
+  }
+
+  // SPH subsystems (lib/objects/sph_system.dart; World.subsystems, world_class.dart:121,472-475)
+  for (final sj in (scene['sph_systems'] ?? const []) as List) {
+    final m = sj as Map;
+    final sph = SPHSystem();
+    sph.density = d(m['density'], 1); sph.smoothingRadius = d(m['smoothing_radius'], 1); sph.speedOfSound = d(m['speed_of_sound'], 1);
+    sph.viscosity = d(m['viscosity'], 0.01); sph.eps = d(m['eps'], 0.00001);
+    for (final p in m['particles'] as List) { sph.add(world.bodies[p as int]); }
+    world.subsystems.add(sph);
   }
 
   final dt = (scene['dt'] as num).toDouble();
