@@ -298,10 +298,16 @@ __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays 
       atomicMax(&wk[4 * nWorlds + w], tmx);
     }
   }
-  for (int s2 = tid; s2 < J.nAccepted; s2 += nth) {
-    const int w = B.world[J.bodyA[J.slotEq[s2]]];
-    atomicMin(&wk[2 * nWorlds + w], s2);
-    atomicMax(&wk[5 * nWorlds + w], s2);
+  // neighbouring joint slots belong to the same world too: one atomic pair per (warp, world)
+  for (int s0 = tid - (int)(threadIdx.x & 31); s0 < J.nAccepted; s0 += nth) {
+    const int s2 = s0 + (int)(threadIdx.x & 31);
+    const int w = s2 < J.nAccepted ? B.world[J.bodyA[J.slotEq[s2]]] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, w);
+    const int smn = __reduce_min_sync(peers, s2), smx = __reduce_max_sync(peers, s2);
+    if (w >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      atomicMin(&wk[2 * nWorlds + w], smn);
+      atomicMax(&wk[5 * nWorlds + w], smx);
+    }
   }
 }
 
