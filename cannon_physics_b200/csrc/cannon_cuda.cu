@@ -194,7 +194,7 @@ struct cannon_world {
   bool sapInit = false;
   int pairCap = 0;
   // device: narrowphase
-  DBuf<int> pairTasks, pairTaskOff, taskPair, taskInfo, bucket, taskCnt, taskRaw, taskOff;
+  DBuf<int> pairTasks, pairTaskOff, taskPair, taskInfo, bucket, taskCnt, taskRaw, taskOff, taskHit;
   DBuf<unsigned long long> pairMask;
   DBuf<int2> taskCell;
   DBuf<float4> rawRi, rawRj, rawNi;
@@ -497,7 +497,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
   REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairMask); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
-  REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
+  REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskHit); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
@@ -865,6 +865,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   if (w->compound) { RES(pp1, npPairCap); RES(pp2, npPairCap); RES(ppPer, npPairCap); RES(ppCnt, pairCap); RES(ppOff, pairCap); }
   RES(taskPair, taskCap); RES(taskInfo, taskCap); RES(taskCell, taskCap); RES(bucket, taskCap); RES(taskCnt, taskCap); RES(taskRaw, taskCap);
   RES(taskOff, taskCap);
+  if (w->evEnabled) RES(taskHit, taskCap);
   RES(rawRi, contactCap); RES(rawRj, contactCap); RES(rawNi, contactCap);
   RES(cBi, contactCap); RES(cBj, contactCap); RES(cEnabled, contactCap); RES(cRow, contactCap); RES(fricFlag, contactCap);
   RES(contFlag, contactCap); RES(fricOff, contactCap); RES(contOff, contactCap); RES(cRi, contactCap); RES(cRj, contactCap);
@@ -1457,6 +1458,7 @@ static NpArrays np_arrays(cannon_world* w) {
   A.rawRi = w->rawRi.p; A.rawRj = w->rawRj.p; A.rawNi = w->rawNi.p;
   A.taskCap = w->taskCap; A.contactCap = w->contactCap;
   A.overflowTasks = cnt + CT_OVF_TASKS; A.overflowContacts = cnt + CT_OVF_CONTACTS; A.unsupported = cnt + CT_UNSUPPORTED;
+  A.taskHit = (w->evEnabled && w->evCap > 0) ? w->taskHit.p : nullptr;
   { const char* e = getenv("CANNON_NP_DEBUG"); A.debug = e ? atoi(e) : 0; }
   A.clipList = w->clipList.p; A.nClip = cnt + CT_NCLIP0; A.taskSep = w->taskSep.p;
   return A;
@@ -1617,6 +1619,7 @@ static int32_t ensure_events(cannon_world* w) {
   while (tab < 2 * cap) tab <<= 1;
   W_TRY(w, w->evKeysCur.reserve(cap)); W_TRY(w, w->evKeysPrev.reserve(cap)); W_TRY(w, w->evBegin.reserve(cap)); W_TRY(w, w->evEnd.reserve(cap));
   W_TRY(w, w->evTabCur.reserve(tab)); W_TRY(w, w->evTabPrev.reserve(tab)); W_TRY(w, w->evCnt.reserve(8));
+  W_TRY(w, w->taskHit.reserve((size_t)std::max(w->taskCap, 1)));
   w->evCap = (int)cap; w->evMask = (unsigned)(tab - 1);
   W_TRY(w, cudaMemsetAsync(w->evTabPrev.p, 0xff, tab * sizeof(unsigned long long), s));
   W_TRY(w, cudaMemsetAsync(w->evCnt.p, 0, 8 * sizeof(int), s));

@@ -42,6 +42,7 @@ struct NpArrays {
   int debug;               // profiling aid (CANNON_NP_DEBUG): 1 skip clipping, 2 skip the axis loop, 3 skip after pillar build
   int* overflowTasks;
   int* overflowContacts;
+  int* taskHit;            // contact events on: per task, "a justTest resolver returned true" (nullptr otherwise: justTest pairs make no tasks)
   int* unsupported;        // set when a pair only the reference's unfinished trimesh resolvers would handle passes the prologue
   // tile SAT kernel (k_sat_warp.cuh): tasks that passed the separating-axis test, queued for the clipping launch
   int* clipList;           // [2][taskCap]: hull/hull, hull/pillar
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
   const int stride = gridDim.x * blockDim.x;
   for (int kb = warpStart; kb < np; kb += stride) {
     const int k = kb + lane;
-    int nt = 0, code = -1;
+    int nt = 0, code = -1, jt = 0;
     int first = 0, second = 0;
     int iMinX = 0, iMaxX = 0, iMinY = 0, iMaxY = 0;
     bool hfPair = false;
@@ -295,7 +296,10 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
                               (tya == CANNON_BODY_KINEMATIC && tyb == CANNON_BODY_KINEMATIC);
         const bool maskOk = (si.mask & sj.group) != 0 && (sj.mask & si.group) != 0;
         const f3 xi = ld3(B.pos[a]), xj = ld3(B.pos[b]);
-        if (maskOk && !justTest && !(vdist(xi, xj) > si.bsr + sj.bsr)) {
+        // kinematic / static pairs run their resolver in justTest mode (narrow_phase.dart:706-716): no equations, only the
+        // overlap keepers behind the contact events - so they become tasks only when events are on (bit 5 of taskInfo)
+        jt = justTest ? 1 : 0;
+        if (maskOk && (!justTest || A.taskHit != nullptr) && !(vdist(xi, xj) > si.bsr + sj.bsr)) {
           int lo = si.type, hi = sj.type;
           first = a; second = b;
           if (!(lo < hi)) { int t = lo; lo = hi; hi = t; first = b; second = a; }
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int pCode = __shfl_sync(0xffffffffu, code, src), pk = kb + src;
+      const int pCode = __shfl_sync(0xffffffffu, code, src) | (__shfl_sync(0xffffffffu, jt, src) << 5), pk = kb + src;
       const int x0 = __shfl_sync(0xffffffffu, iMinX, src), x1 = __shfl_sync(0xffffffffu, iMaxX, src);
       const int y0 = __shfl_sync(0xffffffffu, iMinY, src), y1 = __shfl_sync(0xffffffffu, iMaxY, src);
       const int pOff = __shfl_sync(0xffffffffu, myOff, src);
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       const HfDev hf = X.hf;
       const f3 xf = X.xf, xs = X.xs;
       const q4 qs = X.qs;
-      const bool hullTask = pCode == NP_HPIL;
+      const bool hullTask = (pCode & 15) == NP_HPIL;
       const double rFirst = X.rFirst;
       HullDev hd;
       q4 qf;
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(128) k_np_tasks(BodyArrays B, ShapeTables T, N
       for (int t = 0; t < nt; t++) A.bucket[slot + t] = off + t;
     } else {
       A.taskPair[off] = k;
-      A.taskInfo[off] = gcode;
+      A.taskInfo[off] = gcode | (jt << 5);
       A.bucket[slot] = off;
     }
   }
@@ -517,6 +521,11 @@ struct RawOut {
 __device__ __forceinline__ bool raw_alloc(RawOut& o, int m) {
   o.n = 0;
   o.start = 0;
+  if (o.A.taskHit) {  // justTest task: remember whether the resolver would have created a contact, create none
+    const int jt = (o.A.taskInfo[o.task] >> 5) & 1;
+    o.A.taskHit[o.task] = jt ? (m > 0) : 0;
+    if (jt) m = 0;
+  }
   if (m > 0) {
     o.start = atomicAdd(o.A.rawCount, m);
     if (o.start + m > o.A.contactCap) { atomicMax(o.A.overflowContacts, o.start + m); m = 0; o.start = 0; }
@@ -564,7 +573,13 @@ __global__ void __launch_bounds__(256) k_np_sphere_sphere(BodyArrays B, ShapeTab
   NP_BUCKET_LOOP(NP_SS) {
     TaskCtx c; load_task(B, T, A, NP_TASK(NP_SS), c);
     RawOut o; o.A = A; o.task = c.task;
-    if (!raw_alloc(o, 1)) continue;
+    int m = 1;
+    if ((c.info >> 5) & 1) {  // justTest has a test of its own (:735-737): Vector3.distanceSquared (vec3.dart:88-93) against (ri + rj)^2
+      const double dx = W(c.xj.x) - W(c.xi.x), dy = W(c.xj.y) - W(c.xi.y), dz = W(c.xj.z) - W(c.xi.z);
+      const double rs = c.si.radius + c.sj.radius;
+      m = dx * dx + dy * dy + dz * dz < rs * rs ? 1 : 0;
+    }
+    if (!raw_alloc(o, m)) continue;
     f3 ni = vsub(c.xj, c.xi);
     vnormalize(ni);
     f3 ri = vscale(c.si.radius, ni);
@@ -1586,7 +1601,7 @@ __global__ void __launch_bounds__(256) k_ev_collect(NpArrays A, EvArrays E, cons
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
     const int t0 = A.pairTaskOff[k], t1 = min(t0 + A.pairTasks[k], nt);
     bool any = false;
-    for (int t = t0; t < t1 && !any; t++) any = A.taskCnt[t] > 0;
+    for (int t = t0; t < t1 && !any; t++) any = A.taskCnt[t] > 0 || (A.taskHit && A.taskHit[t] != 0);
     if (!any) continue;
     const int a = owner ? owner[A.p1[k]] : A.p1[k], b = owner ? owner[A.p2[k]] : A.p2[k];  // bodyOverlapKeeper: body ids
     const unsigned long long key = ((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned long long)(unsigned)max(a, b);

@@ -21,12 +21,21 @@ namespace cg = cooperative_groups;
 
 #define SAT_GROUP 8  // lanes per task (a tile of the warp); 4 tasks share a warp
 #define SAT_TILES 8            // tiles per CTA
+#ifndef SAT_PILLAR_CTAS
+#define SAT_PILLAR_CTAS 8      // resident CTAs per SM the hull / pillar kernels are compiled for. Measured on the settled 100k
+                               // pile: 8 (96 registers) narrowphase 1.288 ms, 10 -> 1.317 ms, 12 (80 registers) -> 1.330 ms: more resident
+                               // warps only queue on the FP64 pipe, the extra register pressure costs more than the latency hiding gains
+#endif
 
-struct SatScratch {
-  f3 nA[SAT_MAXF], nB[SAT_MAXF];  // world face normals
-  f3 eA[SAT_MAXE], eB[SAT_MAXE];  // world unique edges
+// The B side of a hull / pillar task is a heightfield pillar (5 faces, <= 7 pruned edges, 6 vertices): its tables are
+// sized for that, which takes a CTA's scratch from 23 KB to 18 KB (shared memory no longer bounds the occupancy; see
+// SAT_PILLAR_CTAS for why it is not raised).
+template <int NFB, int NEB, int NVB>
+struct SatScratchT {
+  f3 nA[SAT_MAXF], nB[NFB];  // world face normals
+  f3 eA[SAT_MAXE], eB[NEB];  // world unique edges
   union {                          // three phases of a task that never overlap
-    struct { double vA[SAT_MAXV][3], vB[SAT_MAXV][3]; } v;                              // axis loop: local vertices, widened once
+    struct { double vA[SAT_MAXV][3], vB[NVB][3]; } v;                                   // axis loop: local vertices, widened once
     struct { f3 pa[NP_MAXPOLY], pb[NP_MAXPOLY]; double depth[NP_MAXPOLY]; } c;          // clipping + emission
   } u;
   int kept, overflow, closestA;
@@ -81,7 +90,7 @@ __device__ __forceinline__ void hull_project_w(const double (*v)[3], int nV, con
 // tile: the face searches are lexicographic reductions (first extremum wins, like the sequential scans), each
 // Sutherland-Hodgman pass gives one polygon edge to a lane and places its 0 / 1 / 2 output vertices with a prefix sum,
 // so the output polygon has the sequential order and every vertex is produced by the sequential expression.
-template <class Tile>
+template <class Tile, class SatScratch>
 __device__ inline int clip_hulls_tile(const Tile& tile, int lane, SatScratch& S, const HullView& HA, const f3& posA, const HullView& HB,
                                       const f3& posB, const q4& quatB, const f3& sep, bool& overflow) {
   f3* pa = S.u.c.pa;
@@ -200,7 +209,8 @@ __device__ inline int clip_hulls_tile(const Tile& tile, int lane, SatScratch& S,
 // walked by four divergent tiles per warp - far beyond the 32 KB L1.5 instruction cache (`no_instruction` was the second
 // largest stall); each phase fits, and phase 1 only sees tasks that all take the same path.
 template <bool PILLAR, int PHASE>
-__global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, 8) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+__global__ void __launch_bounds__(SAT_TILES * SAT_GROUP, PILLAR ? SAT_PILLAR_CTAS : 8) k_np_hull_warp(BodyArrays B, ShapeTables T, NpArrays A, int* clipOverflow) {
+  typedef SatScratchT<PILLAR ? 8 : SAT_MAXF, PILLAR ? 8 : SAT_MAXE, PILLAR ? 8 : SAT_MAXV> SatScratch;
   __shared__ SatScratch s_scr[SAT_TILES];
   cg::thread_block_tile<SAT_GROUP> tile = cg::tiled_partition<SAT_GROUP>(cg::this_thread_block());
   const int lane = tile.thread_rank(), tib = threadIdx.x / SAT_GROUP;

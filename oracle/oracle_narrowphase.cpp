@@ -920,6 +920,7 @@ void World::getContacts() {
   contacts.clear();
   frictions.clear();
   contactManifold.clear();
+  justTestOverlaps.clear();
   perPairCount.assign(p1.size(), 0);
   NP np(*this);
   for (size_t k = 0; k != p1.size(); k++) {
@@ -942,7 +943,26 @@ void World::getContacts() {
         if (!((si.mask & sj.group) != 0 && (sj.mask & si.group) != 0)) continue;
         if (distance_to(xi, xj) > si.boundingSphereRadius + sj.boundingSphereRadius) continue;
         np.cm = bodyCm ? bodyCm : &desc.default_contact_material;
-        if (justTest) continue;  // resolvers create no equations in justTest mode (only overlap-keeper events)
+        if (justTest) {
+          // justTest mode (:706-716): no equations; the resolver returns true where it would have created its first contact
+          // (every `if (justTest) return true` sits right before a createContactEquation), and the world only uses that to
+          // feed the overlap keepers. sphereSphere has its own test (:735-737).
+          if (!trackOverlaps) continue;
+          bool hit;
+          if (si.type == CANNON_SHAPE_SPHERE && sj.type == CANNON_SHAPE_SPHERE) {
+            const double dx = D(xj.x) - D(xi.x), dy = D(xj.y) - D(xi.y), dz = D(xj.z) - D(xi.z);  // Vector3.distanceSquared, vec3.dart:88-93
+            const double rs = si.radius + sj.radius;
+            hit = dx * dx + dy * dy + dz * dz < rs * rs;
+          } else {
+            const size_t nc = contacts.size(), nf = frictions.size(), nm = contactManifold.size();
+            if (si.type < sj.type) np.resolve(si, sj, xi, xj, qi, qj, bi, bj);
+            else np.resolve(sj, si, xj, xi, qj, qi, bj, bi);
+            hit = contacts.size() > nc;
+            contacts.resize(nc); frictions.resize(nf); contactManifold.resize(nm);
+          }
+          if (hit) { justTestOverlaps.push_back(bi); justTestOverlaps.push_back(bj); }
+          continue;
+        }
         if (si.type < sj.type) np.resolve(si, sj, xi, xj, qi, qj, bi, bj);
         else np.resolve(sj, si, xj, xi, qj, qi, bj, bi);
       }

@@ -207,6 +207,8 @@ void World::makeContactConstraints() {
   if (trackOverlaps) {  // collisionMatrixTick, world_class.dart:219 (bodyOverlapKeeper.tick, overlap_keeper.dart:40-45)
     overlapCurrent.swap(overlapPrevious);
     overlapCurrent.clear();
+    // bodyOverlapKeeper.set of the justTest pairs happened inside getContacts, after the tick (world_class.dart:500,519; narrow_phase.dart:715)
+    for (size_t k = 0; k + 1 < justTestOverlaps.size(); k += 2) overlapSet(justTestOverlaps[k], justTestOverlaps[k + 1]);
   }
   for (Eq& c : contacts) {
     Body& bi = bodies[c.bi];

