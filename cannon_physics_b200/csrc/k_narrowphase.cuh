@@ -107,6 +107,9 @@ __device__ inline bool hf_window(const ShapeTables& T, const HfDev& hf, const f3
   if (iMaxX >= hf.nx) iMaxX = hf.nx - 1;
   if (iMaxY >= hf.ny) iMaxY = hf.ny - 1;
   if (iMinY >= hf.ny) iMinY = hf.ny - 1;
+  // the window maximum below never exceeds the heightfield's maximum: a shape above that (most of a pile) is rejected
+  // by the test after the loop whatever the window holds, so the loop (up to 36 scattered loads per pair) is skipped
+  if (W(local.z) - radius > hf.maxV) return false;
   double mx = hf.minV;
   for (int i = iMinX; i <= iMaxX; i++)
     for (int j = iMinY; j <= iMaxY; j++) {
