@@ -179,7 +179,8 @@ __device__ __forceinline__ void project_verts(const float4* __restrict__ gv, con
 // evaluates each axis, its hull projection and its image in the heightfield frame ONCE per pair (one axis per lane,
 // QsAxis in shared memory) and every lane then projects only the six vertices of its own pillar.
 struct QsAxis {
-  f3 lax;            // qrot(qnegw(qP), axis): the axis in the heightfield's local frame
+  double lx, ly, lz; // qrot(qnegw(qP), axis): the axis in the heightfield's local frame, widened once (float -> double is exact):
+                     // every pillar of the pair multiplies it with its six vertices, and the conversions are the scarce pipe
   double maxA, minA; // hull projection (ConvexPolyhedron.project of the hull on the axis)
   int valid;
 };
@@ -219,14 +220,20 @@ __device__ __forceinline__ bool sphere_pillar_far(const f3& lc, double R, double
 __device__ __forceinline__ bool pillar_quick_separated_pre(const QsAxis* __restrict__ ax, int nAx, const f3* pv, const f3& xP, const q4& qP) {
   f3 zero; zero.x = zero.y = zero.z = 0.f;
   const f3 oP = to_local_point(xP, qP, zero);
+  const double ox = W(oP.x), oy = W(oP.y), oz = W(oP.z);
+  // vdot(v, localAxis) = (vx * lx + vy * ly) + vz * lz on the widened components, exactly as dmath.cuh evaluates it
+  double px[6], py[6], pz[6];  // the pillar's vertices widened once for all axes
+#pragma unroll
+  for (int i = 0; i < 6; i++) { px[i] = W(pv[i].x); py[i] = W(pv[i].y); pz[i] = W(pv[i].z); }
   for (int t = 0; t < nAx; t++) {
     if (!ax[t].valid) continue;
-    const f3 localAxis = ax[t].lax;
-    const double add = vdot(oP, localAxis);
+    const double lx = ax[t].lx, ly = ax[t].ly, lz = ax[t].lz;
+    const double add = ox * lx + oy * ly + oz * lz;
     double mn, mx;
-    mn = mx = vdot(pv[0], localAxis);
+    mn = mx = px[0] * lx + py[0] * ly + pz[0] * lz;
+#pragma unroll
     for (int i = 1; i < 6; i++) {
-      const double val = vdot(pv[i], localAxis);
+      const double val = px[i] * lx + py[i] * ly + pz[i] * lz;
       if (val > mx) mx = val;
       if (val < mn) mn = val;
     }
@@ -254,14 +261,15 @@ __device__ __forceinline__ QsAxis qs_axis(const ShapeTables& T, const HullDev& h
   QsAxis q;
   q.valid = valid ? 1 : 0;
   q.maxA = q.minA = 0.0;
-  q.lax = axis;
+  q.lx = W(axis.x); q.ly = W(axis.y); q.lz = W(axis.z);
   if (valid) {
     project_verts(T.verts + hd.vOff, nullptr, hd.nV, axis, qf, oA, q.maxA, q.minA);
-    q.lax = qrot(qnegw(qs), axis);
+    const f3 lax = qrot(qnegw(qs), axis);
+    q.lx = W(lax.x); q.ly = W(lax.y); q.lz = W(lax.z);
   }
   return q;
 }
-#define QS_HOIST_AXES 8  // pairs with at most this many quick axes (box 4, 8-segment cylinder 6) get them computed up front
+#define QS_HOIST_AXES 6  // pairs with at most this many quick axes (box 4, 8-segment cylinder 6) get them computed up front
 
 // which body plays "i" for the resolver: lower ShapeType index first, equal types swapped (narrow_phase.dart:706-710)
 __device__ __forceinline__ void np_order(int a, int b, int ta, int tb, int& first, int& second) {

@@ -74,14 +74,17 @@ struct HfDev {
 // shapes are set - the reference caches pillars too (getCachedConvexTrianglePillar, heightfield.dart:300-328); the
 // height samples are immutable through this ABI. e[] holds the unique edges minus +-copies, in their original order.
 struct PillarRec {
+  // first 128 bytes = one cache line: everything the task expansion (bounding gate, quick separation) reads per pillar
   float4 off;      // pillar offset in the heightfield frame
   float4 v[6];
+  double bsr;
+  int nE, pad;
+  // the resolvers' part
   float4 n[5];
   float4 e[9];
   double pc[5];
-  double bsr;
-  int nE, pad;
 };
+static_assert(sizeof(PillarRec) == 400 && offsetof(PillarRec, n) == 128, "PillarRec: the gate fields must fill the first cache line");
 
 struct ShapeTables {
   const ShapeDev* shapes;
