@@ -422,3 +422,37 @@ def test_world_api_lock_constraint_survives_a_rebuild(oracle_lib):
         w.step(1 / 60, sync=False)
     w.sync()
     assert np.array_equal(b.position, rb.position) and np.array_equal(b.quaternion, rb.quaternion)
+
+
+def test_dart_binding_matches_the_header():
+    """dart/cannon_cuda_bindings.dart cannot be compiled here (no SDK): check it against include/cannon_cuda.h textually -
+    every exported symbol is looked up, and every struct has the header's fields in the header's order (camelCase)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "cannon_cuda.h")).read(), flags=re.S)
+    d = open(os.path.join(root, "dart", "cannon_cuda_bindings.dart")).read()
+    syms = set(re.findall(r"\b(cannon_[a-z0-9_]+)\s*\(", h))
+    assert syms == set(re.findall(r"'(cannon_[a-z0-9_]+)'", d))
+
+    def camel(s):
+        p = s.split("_")
+        return p[0] + "".join(x.capitalize() for x in p[1:])
+
+    n_structs = 0
+    for m in re.finditer(r"typedef struct (\w+) \{(.*?)\} (\w+);", h, flags=re.S):
+        fields = []
+        for line in m.group(2).split(";"):
+            line = line.strip()
+            if not line:
+                continue
+            decl = re.sub(r"^(const\s+)?\w+\s*\**\s*", "", line)
+            for nm in decl.split(","):
+                nm = re.sub(r"\[.*\]", "", nm.strip().lstrip("*").strip())
+                if nm:
+                    fields.append(camel(nm))
+        cls = "".join(x.capitalize() for x in m.group(3).split("_"))
+        dm = re.search(r"final class " + cls + r" extends Struct \{(.*?)\n\}", d, flags=re.S)
+        assert dm, f"no Dart struct for {m.group(3)}"
+        assert re.findall(r"external (?:[\w<>]+) (\w+);", dm.group(1)) == fields, m.group(3)
+        n_structs += 1
+    assert n_structs >= 12
