@@ -27,7 +27,7 @@ raw = np.fromfile(path, dtype=np.int64)
 nsm = (len(raw)) // (4 * 64 * 2 + 64)
 t = raw[: nsm * 4 * 64 * 2].reshape(-1, 64, 2)
 raw_tail_base = None
-grid = int(os.environ.get('GS_TRACE_CTAS', '296'))
+grid = int(os.environ.get('GS_TRACE_CTAS', '148'))
 t = t[:grid]
 raw_tail_base = grid * 64 * 2
 print("CTAs", t.shape[0])
