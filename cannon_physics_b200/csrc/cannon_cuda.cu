@@ -200,7 +200,7 @@ struct cannon_world {
   DBuf<float4> rawRi, rawRj, rawNi;
   int taskCap = 0, contactCap = 0;
   // device: contacts
-  DBuf<int> cBi, cBj, cEnabled, cRow, fricFlag, contFlag, fricOff, contOff;
+  DBuf<int> cBi, cBj, cTask, cEnabled, cRow, fricFlag, contFlag, fricOff, contOff;
   DBuf<float4> cRi, cRj, cNi;
   DBuf<double> cRest, cMu, cSlip, cCa, cCb, cCeps, cFb, cFeps, cMult;
   // device: rows
@@ -497,7 +497,7 @@ void cannon_world_destroy(cannon_world* w) {
   REL(clipList); REL(taskSep); REL(nbCache); REL(cellc); REL(smeta); REL(scell); REL(binLo); REL(binHi); REL(cellStart); REL(cellEnd); REL(bigList); REL(bigWorldStart);
   REL(worldStart); REL(bpCounts); REL(bpOffs); REL(skey); REL(sval); REL(sapKey); REL(sapList); REL(spos); REL(srad); REL(p1); REL(p2);
   REL(q1); REL(q2); REL(keep); REL(keepOff); REL(filterKeys); REL(pairMask); REL(pairTasks); REL(pairTaskOff); REL(taskPair); REL(taskInfo); REL(bucket);
-  REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskHit); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cEnabled); REL(cRow);
+  REL(taskCnt); REL(taskRaw); REL(taskOff); REL(taskHit); REL(taskCell); REL(rawRi); REL(rawRj); REL(rawNi); REL(cBi); REL(cBj); REL(cTask); REL(cEnabled); REL(cRow);
   REL(fricFlag); REL(contFlag); REL(fricOff); REL(contOff); REL(cRi); REL(cRj); REL(cNi); REL(cRest); REL(cMu); REL(cSlip); REL(cCa);
   REL(cCb); REL(cCeps); REL(cFb); REL(cFeps); REL(cMult); REL(rKind); REL(rN); REL(rRA); REL(rRB);
   REL(rIA); REL(rIB); REL(rB); REL(rInvC); REL(rEps); REL(rMinF); REL(rMaxF); REL(rLambda); REL(jBodyA); REL(jBodyB);
@@ -867,7 +867,7 @@ static int32_t ensure_capacities(cannon_world* w) {
   RES(taskOff, taskCap);
   if (w->evEnabled) RES(taskHit, taskCap);
   RES(rawRi, contactCap); RES(rawRj, contactCap); RES(rawNi, contactCap);
-  RES(cBi, contactCap); RES(cBj, contactCap); RES(cEnabled, contactCap); RES(cRow, contactCap); RES(fricFlag, contactCap);
+  RES(cBi, contactCap); RES(cBj, contactCap); RES(cTask, contactCap); RES(cEnabled, contactCap); RES(cRow, contactCap); RES(fricFlag, contactCap);
   RES(contFlag, contactCap); RES(fricOff, contactCap); RES(contOff, contactCap); RES(cRi, contactCap); RES(cRj, contactCap);
   RES(cNi, contactCap); RES(cRest, contactCap); RES(cMu, contactCap); RES(cSlip, contactCap); RES(cCa, contactCap); RES(cCb, contactCap);
   RES(cCeps, contactCap); RES(cFb, contactCap); RES(cFeps, contactCap); RES(cMult, contactCap);
@@ -1468,7 +1468,7 @@ static ContactArrays contact_arrays(cannon_world* w) {
   C.nContacts = w->cnt.p + CT_NCONTACTS;
   C.bi = w->cBi.p; C.bj = w->cBj.p; C.ri = w->cRi.p; C.rj = w->cRj.p; C.ni = w->cNi.p;
   C.rest = w->cRest.p; C.mu = w->cMu.p; C.slip = w->cSlip.p; C.ca = w->cCa.p; C.cb = w->cCb.p; C.ceps = w->cCeps.p;
-  C.fb = w->cFb.p; C.feps = w->cFeps.p; C.enabled = w->cEnabled.p; C.row = w->cRow.p;
+  C.fb = w->cFb.p; C.feps = w->cFeps.p; C.enabled = w->cEnabled.p; C.row = w->cRow.p; C.task = w->cTask.p;
   return C;
 }
 
@@ -1698,7 +1698,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     W_TRY(w, cudaMemsetAsync(cnt + CT_NEXEC, 0, sizeof(int), s));
     W_TRY(w, cudaMemsetAsync(cnt + CT_NLEVELS, 0, sizeof(int), s));
     g_kernel_launches++;
-    k_schedule_worlds<<<nW, 32, 0, s>>>(B, U, S, w->worldKeys.p, w->worldStart.p, nW, 0, cnt + CT_NTASKS, w->taskCap);
+    k_schedule_worlds<<<nW, 32, 0, s>>>(B, U, S, w->worldKeys.p, w->worldStart.p, nW, 0, cnt + CT_NCONTACTS, w->contactCap);
   } else {
     int colored = P.colored;
     void* args[] = {&U, &S, &colored};

@@ -59,6 +59,7 @@ struct ContactArrays {
   double *fb, *feps;                   // friction SPOOK (a is unused: g == 0)
   int* enabled;
   int* row;                            // solver row of the contact equation, -1 if filtered
+  int* task;                           // resolver task (manifold) the contact came from
 };
 
 struct HullView {
@@ -1398,6 +1399,7 @@ __global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T
       C.ca[o] = ca; C.cb[o] = cb; C.ceps[o] = ceps; C.fb[o] = fb; C.feps[o] = feps;
       C.enabled[o] = enabled;
       C.row[o] = -1;
+      C.task[o] = t;
     }
   }
 }

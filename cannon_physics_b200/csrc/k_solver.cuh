@@ -266,8 +266,8 @@ __device__ __forceinline__ void put_unit(const UnitArrays& U, const BodyArrays& 
 // the handle (a batch may be sharded over GPUs in any way). So the hashed key is counted inside the world:
 // contacts from the world's first ContactEquation, constraints from the world's contact count. wk[w] = first contact
 // index, wk[nW + w] = contacts, wk[2 nW + w] = first accepted joint slot of world w. For the per-world colouring
-// (k_schedule_worlds) also the world's ranges of unit ids: wk[3 nW + w] / wk[4 nW + w] = first / last task with contacts,
-// wk[5 nW + w] = last accepted joint slot.
+// (k_schedule_worlds) also the world's ranges of unit ids: wk[3 nW + w] / wk[4 nW + w] = first / last contact (a contact
+// unit's id is the index of its first contact, k_units_build), wk[5 nW + w] = last accepted joint slot.
 #define WK_ARRAYS 6
 __global__ void __launch_bounds__(256) k_world_keys_init(int* __restrict__ wk, int nWorlds) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < WK_ARRAYS * nWorlds; i += gridDim.x * blockDim.x) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays 
     }
     const unsigned peers = __match_any_sync(0xffffffffu, w);
     const int mn = __reduce_min_sync(peers, c0), sum = __reduce_add_sync(peers, m);
-    const int tmn = __reduce_min_sync(peers, w >= 0 ? t : 0x7fffffff), tmx = __reduce_max_sync(peers, w >= 0 ? t : -1);
+    const int tmn = mn, tmx = __reduce_max_sync(peers, w >= 0 ? c0 + m - 1 : -1);  // the world's contacts are contiguous
     if (w >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
       atomicMin(&wk[w], mn);
       atomicAdd(&wk[nWorlds + w], sum);
@@ -312,30 +312,29 @@ __global__ void __launch_bounds__(256) k_world_keys(BodyArrays B, ContactArrays 
 }
 
 // unit table. Reference order: unit id == reference row index [2*fricRank | nF2 + contRank | joints].
-// Coloured: unit id == task id (manifold) followed by the joint rows.
+// Coloured: a manifold's contacts are cut into runs of CANNON_COLORED_UNIT_CONTACTS; unit id == index of the run's first
+// contact (the ids in between stay empty), followed by the joint rows.
 __global__ void __launch_bounds__(256) k_units_build(BodyArrays B, ContactArrays C, UnitSrc S, JointArrays J, UnitArrays U, int nWorlds,
                                                      int* __restrict__ worldRows, int* __restrict__ unitOverflow, const int* __restrict__ wk) {
   const int nc = min(*C.nContacts, S.contactCap);
   const int nF2 = 2 * (*S.fricTotal), nC = *S.contTotal;
   const int nt = min(*S.nTasks, S.taskCap);
-  const int jointBase = S.colored ? nt : nF2 + nC;
+  const int jointBase = S.colored ? nc : nF2 + nC;
   const int nUnits = jointBase + J.nAccepted;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   if (tid == 0) { *U.nUnits = nUnits; if (nUnits > U.unitCap) atomicMax(unitOverflow, nUnits); }
   if (nUnits > U.unitCap) return;
   if (S.colored) {
-    for (int t = tid; t < nt; t += nth) {
-      const int m = S.taskCnt[t];
+    for (int c0 = tid; c0 < nc; c0 += nth) {
+      const int t = C.task[c0];
+      const int first = S.taskOff[t], end = min(first + S.taskCnt[t], nc);
       int rows = 0, bi = 0, bj = 0;
-      if (m > 0) {
-        const int c0 = S.taskOff[t], c1 = c0 + m;
-        if (c1 <= nc) {
-          bi = C.bi[c0]; bj = C.bj[c0];
-          for (int c = c0; c < c1; c++) rows += S.contFlag[c] + 2 * S.fricFlag[c];
-        }
+      if ((c0 - first) % CANNON_COLORED_UNIT_CONTACTS == 0) {  // head of a run
+        const int c1 = min(c0 + CANNON_COLORED_UNIT_CONTACTS, end);
+        bi = C.bi[c0]; bj = C.bj[c0];
+        for (int c = c0; c < c1; c++) rows += S.contFlag[c] + 2 * S.fricFlag[c];
       }
-      const int key = m > 0 ? S.taskOff[t] : 0;
-      put_unit(U, B, t, bi, bj, rows, t * 8 + SRC_TASK, nWorlds, worldRows, key, (nWorlds > 1 && rows > 0) ? key - wk[B.world[bi]] : key);
+      put_unit(U, B, c0, bi, bj, rows, c0 * 8 + SRC_TASK, nWorlds, worldRows, c0, (nWorlds > 1 && rows > 0) ? c0 - wk[B.world[bi]] : c0);
     }
   } else if (S.split) {
     // unit id = position in descending creation-id order (split_solver.dart:108,167-169)
@@ -559,7 +558,7 @@ __global__ void __launch_bounds__(256) k_schedule(UnitArrays U, SchedArrays S, i
 // rows per unit in execution order (input of the row-base scan) + per-unit execution data
 // The colouring of a COLORED batch, one warp per world (no grid barrier: worlds share no body). Same rule as k_schedule -
 // colour(u) = round in which u holds the smallest pending priority on all of its movable bodies - over the world's own
-// units: the tasks [wk[3 nW + w], wk[4 nW + w]] that produced rows and the joint units of slots [wk[2 nW + w], wk[5 nW + w]].
+// units: the contact runs with ids in [wk[3 nW + w], wk[4 nW + w]] and the joint units of slots [wk[2 nW + w], wk[5 nW + w]].
 // The claims live in shared memory and are cleared every round; a round visits all candidates and skips the coloured ones
 // (~100 units x ~13 rounds per world). Scheduled units are appended to `order` (k_world_count / k_world_fill regroup them
 // by world and colour anyway); nLevels is the maximum over the worlds.
@@ -570,7 +569,7 @@ __global__ void __launch_bounds__(32) k_schedule_worlds(BodyArrays B, UnitArrays
   __shared__ unsigned s_claim[SW_MAXB];
   const int lane = threadIdx.x, wd = blockIdx.x;
   const int b0 = worldBody[wd], nB = worldBody[wd + 1] - b0;
-  const int jointBase = min(*nTasksPtr, taskCap);  // unit id of joint slot 0 (k_units_build)
+  const int jointBase = min(*nTasksPtr, taskCap);  // unit id of joint slot 0 = number of contacts (k_units_build)
   const int t0 = wk[3 * nWorlds + wd], t1 = wk[4 * nWorlds + wd];
   const int j0 = wk[2 * nWorlds + wd], j1 = wk[5 * nWorlds + wd];
   const int nT = t1 >= t0 ? t1 - t0 + 1 : 0, nJ = j1 >= j0 ? j1 - j0 + 1 : 0;
@@ -810,7 +809,8 @@ __global__ void __launch_bounds__(128) k_rows_build(BodyArrays B, ContactArrays 
     } else if (kind == SRC_JOINTS) {  // COLORED: the accepted equations of one constraint, slots idx .. idx + rows - 1
       for (int k = 0; k < U.eRows[a]; k++) build_joint_row(R, row + k * rs, B, J, J.slotEq[idx + k], A, Bd, h);
     } else if (kind == SRC_TASK) {
-      const int c0 = S.taskOff[idx], c1 = c0 + S.taskCnt[idx];
+      const int tk = C.task[idx];  // idx = first contact of the run
+      const int c0 = idx, c1 = min(c0 + CANNON_COLORED_UNIT_CONTACTS, S.taskOff[tk] + S.taskCnt[tk]);
       for (int c = c0; c < c1; c++) {
         const f3 ri = ld3(C.ri[c]), rj = ld3(C.rj[c]), ni = ld3(C.ni[c]);
         if (S.fricFlag[c]) {

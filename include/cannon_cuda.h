@@ -83,13 +83,16 @@ enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 
 enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };
 /* World.broadphase choices: NaiveBroadphase / SAPBroadphase / GridBroadphase */
 enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
+#define CANNON_COLORED_UNIT_CONTACTS 4
 /* World.solver choices.
  *   REFERENCE_ORDER: GSSolver with the reference's exact equation order
  *       (lib/world/world_class.dart:539-541,562,627-635); bit-reproducible validation mode.
  *   COLORED: graph-coloured Gauss-Seidel, the throughput mode. Same per-row arithmetic as GSSolver (f64 on
  *       f32-stored operands, no FMA, every Vector3 store rounds to float), different - but fully specified -
  *       row order: units = contact manifolds (the ContactEquations of one resolver call, rows [f1,f2,n] per
- *       contact) followed by one unit per constraint; unit key = index of its first ContactEquation in
+ *       contact), cut into runs of at most CANNON_COLORED_UNIT_CONTACTS consecutive contacts (a colour lasts as
+ *       long as its longest unit: 30-row manifolds made every colour of a pile a 30-step chain), followed by one
+ *       unit per constraint; unit key = index of its first ContactEquation in
  *       World.contacts (constraints: n_contacts + ordinal of its first accepted equation), counted inside the
  *       unit's world for a batch (n_worlds > 1: contacts from the world's first ContactEquation, constraints
  *       from the world's contact count), so a world's result does not depend on the rest of the batch; priority =

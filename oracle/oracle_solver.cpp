@@ -338,7 +338,8 @@ int World::solve(double h) {
     prof.n_islands = nIslands;
   } else if (desc.solver_kind == CANNON_SOLVER_COLORED || desc.solver_kind == CANNON_SOLVER_COLORED_F32) {
     // COLORED order (include/cannon_cuda.h): GSSolver's arithmetic over a different, fully specified equation order.
-    // Units = contact manifolds (the ContactEquations of one resolver call; rows [f1, f2, n] per contact) and one unit per
+    // Units = contact manifolds (the ContactEquations of one resolver call; rows [f1, f2, n] per contact) in runs of at most
+    // CANNON_COLORED_UNIT_CONTACTS contacts, and one unit per
     // constraint; colour(u) = round in which u holds the smallest pending priority on all of its movable bodies; colours
     // ascend, units of a colour are independent (ordered by key here). Sequential GS over that list is the coloured sweep.
     // In a batch the hashed key is counted inside the unit's world (contacts from the world's first ContactEquation,
@@ -364,7 +365,7 @@ int World::solve(double h) {
       size_t f = 0;
       for (size_t c = 0; c < contacts.size();) {
         size_t e = c;
-        while (e < contacts.size() && contactManifold[e] == contactManifold[c]) e++;
+        while (e < contacts.size() && contactManifold[e] == contactManifold[c] && e - c < (size_t)CANNON_COLORED_UNIT_CONTACTS) e++;
         CUnit u{contacts[c].bi, contacts[c].bj, (int)c, -1, 0u, {}, (int)c - (nWk > 1 ? wFirstC[worldOf(contacts[c].bi)] : 0)};
         for (size_t k = c; k < e; k++) {
           if (contacts[k].friction > 0) {
