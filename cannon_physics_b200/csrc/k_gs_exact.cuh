@@ -22,14 +22,15 @@
 // ~350 clk of conversion pipe however many lanes are active (measured: 545 clk for a lone warp, 1412 clk with four warps
 // per sub-partition; replacing the conversions by integer or add-magic forms is exact but not faster). The solve is
 // therefore conversion-bound at ~0.13 ms for this scene if perfectly packed; the rest of the time is the longest unit of
-// every colour phase (up to 30 rows on one lane) and ~3 us of barrier + prologue per phase (100 phases).
+// every colour phase and ~3 us of barrier + prologue per phase (100-120 phases). The colour order therefore cuts manifolds
+// into units of at most CANNON_COLORED_UNIT_CONTACTS = 4 contacts (12 rows on one lane instead of up to 30).
 // History on the settled 100k pile of config 3 (1.36e6 rows, 10 colours, 10 iterations; profiles/README.md):
 //   unstaged level sweep k_gs 3.43 ms -> TMA-staged per-warp row windows with per-body dataflow counters 1.74 ms (8 warps
 //   per SM, 12 of 32 lanes busy: instruction-latency bound) -> 32-unit windows, dynamic claiming, dataflow 2.32 ms (every
 //   iteration drains at the tolerance barrier; a window waits for the slowest of its 64 predecessors, i.e. dataflow
 //   degenerates to one barrier per colour plus polling traffic) -> barrier per colour, window-interleaved rows, cp.async
 //   rings 1.55 ms -> four lanes per unit (quarter of the chain, but 3x the warp instructions: 2.4 ms, rejected) -> split
-//   barrier, balanced dealing, tail colours on one CTA, pipelined row loop 1.28 ms.
+//   barrier, balanced dealing, tail colours on one CTA, pipelined row loop 1.28 ms -> units of at most 4 contacts 1.04 ms.
 #pragma once
 #include "k_solver.cuh"
 
