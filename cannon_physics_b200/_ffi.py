@@ -139,7 +139,7 @@ class RayOptions(C.Structure):
 
 class RayHitsSoA(C.Structure):
     _fields_ = [("capacity", c_i32), ("ray", P(c_i32)), ("body", P(c_i32)), ("hit_face_index", P(c_i32)), ("distance", P(c_f64)),
-                ("hit_point_world", P(c_f32)), ("hit_normal_world", P(c_f32))]
+                ("hit_point_world", P(c_f32)), ("hit_normal_world", P(c_f32)), ("shape_ordinal", P(c_i32))]
 
 
 BATCH_MAX_GPUS = 16

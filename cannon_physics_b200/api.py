@@ -966,7 +966,7 @@ class World:  # lib/world/world_class.dart:44
         result.rayFromWorld[:], result.rayToWorld[:] = from_, to
         result.hasHit = True
         result.body = self.bodies[int(r["body"][k])]
-        result.shape = result.body.shapes[0] if len(result.body.shapes) == 1 else None  # the ABI reports the body, not which of its shapes
+        result.shape = result.body.shapes[int(r["shape_ordinal"][k])]  # RaycastResult.shape (ray_class.dart:676-690)
         result.hitFaceIndex, result.distance = int(r["hit_face_index"][k]), float(r["distance"][k])
         result.hitPointWorld[:], result.hitNormalWorld[:] = r["hit_point_world"][k], r["hit_normal_world"][k]
 

@@ -2514,19 +2514,19 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
   const int allCap = all ? std::max(hits->capacity, 1) : 1;
   DBuf<float> dFrom, dTo;
   DBuf<unsigned char> dHas;
-  DBuf<int> dBody, dFace, dCount, aRay, aBody, aFace;
+  DBuf<int> dBody, dFace, dCount, aRay, aBody, aFace, dInst, aInst;
   DBuf<double> dDist, aDist;
   DBuf<float4> dPoint, dNormal, aPoint, aNormal;
   DBuf<unsigned long long> aKey;
   int32_t rc = CANNON_OK;
   auto done = [&](int32_t code) {
-    dFrom.release(); dTo.release(); dHas.release(); dBody.release(); dFace.release(); dCount.release(); aRay.release(); aBody.release(); aFace.release();
+    dFrom.release(); dTo.release(); dHas.release(); dBody.release(); dFace.release(); dCount.release(); aRay.release(); aBody.release(); aFace.release(); dInst.release(); aInst.release();
     dDist.release(); aDist.release(); dPoint.release(); dNormal.release(); aPoint.release(); aNormal.release(); aKey.release();
     return code;
   };
 #define R_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(w->ctx, CANNON_E_CUDA, cudaGetErrorString(e_)); return done(CANNON_E_CUDA); } } while (0)
   R_TRY(dFrom.reserve(3 * n)); R_TRY(dTo.reserve(3 * n)); R_TRY(dHas.reserve(n)); R_TRY(dBody.reserve(n)); R_TRY(dFace.reserve(n)); R_TRY(dCount.reserve(1));
-  R_TRY(dDist.reserve(n)); R_TRY(dPoint.reserve(n)); R_TRY(dNormal.reserve(n));
+  R_TRY(dDist.reserve(n)); R_TRY(dPoint.reserve(n)); R_TRY(dNormal.reserve(n)); R_TRY(dInst.reserve(n)); R_TRY(aInst.reserve(allCap));
   R_TRY(aRay.reserve(allCap)); R_TRY(aBody.reserve(allCap)); R_TRY(aFace.reserve(allCap)); R_TRY(aKey.reserve(allCap)); R_TRY(aDist.reserve(allCap));
   R_TRY(aPoint.reserve(allCap)); R_TRY(aNormal.reserve(allCap));
   R_TRY(cudaMemcpyAsync(dFrom.p, from, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -2538,11 +2538,11 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
   A.checkCollisionResponse = opt->check_collision_response;
   A.hasHit = dHas.p; A.body = dBody.p; A.face = dFace.p; A.dist = dDist.p; A.point = dPoint.p; A.normal = dNormal.p;
   A.allCount = dCount.p; A.allCap = all ? hits->capacity : 0; A.allRay = aRay.p; A.allBody = aBody.p; A.allFace = aFace.p; A.allKey = aKey.p; A.allDist = aDist.p;
-  A.allPoint = aPoint.p; A.allNormal = aNormal.p;
+  A.allPoint = aPoint.p; A.allNormal = aNormal.p; A.inst = dInst.p; A.allInst = aInst.p;
   { g_kernel_launches++; k_raycast<<<grid_for(w, 32LL * n_rays, 128), 128, 0, s>>>(body_arrays(w), shape_tables(w), A); }
   R_TRY(cudaGetLastError());
   std::vector<unsigned char> hHas(n);
-  std::vector<int> hBody(n), hFace(n);
+  std::vector<int> hBody(n), hFace(n), hInst(n);
   std::vector<double> hDist(n);
   std::vector<float4> hPoint(n), hNormal(n);
   int count = 0;
@@ -2551,13 +2551,15 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
   if (!all) {
     R_TRY(cudaMemcpyAsync(hBody.data(), dBody.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     R_TRY(cudaMemcpyAsync(hFace.data(), dFace.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    R_TRY(cudaMemcpyAsync(hInst.data(), dInst.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     R_TRY(cudaMemcpyAsync(hDist.data(), dDist.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     R_TRY(cudaMemcpyAsync(hPoint.data(), dPoint.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
     R_TRY(cudaMemcpyAsync(hNormal.data(), dNormal.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
   }
   R_TRY(cudaStreamSynchronize(s));
   if (has_hit) memcpy(has_hit, hHas.data(), n);
-  auto put = [&](int k, int ray, int body, int face, double dist, const float4& p, const float4& nn) {
+  auto put = [&](int k, int ray, int body, int face, double dist, const float4& p, const float4& nn, int inst) {
+    if (hits->shape_ordinal) hits->shape_ordinal[k] = inst;
     if (hits->ray) hits->ray[k] = ray;
     if (hits->body) hits->body[k] = body;
     if (hits->hit_face_index) hits->hit_face_index[k] = face;
@@ -2567,13 +2569,13 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
   };
   if (!all) {
     int nh = 0;
-    for (int r = 0; r < n_rays; r++) { put(r, r, hBody[r], hFace[r], hDist[r], hPoint[r], hNormal[r]); nh += hHas[r] ? 1 : 0; }
+    for (int r = 0; r < n_rays; r++) { put(r, r, hBody[r], hFace[r], hDist[r], hPoint[r], hNormal[r], hInst[r]); nh += hHas[r] ? 1 : 0; }
     *n_hits = nh;
   } else {
     *n_hits = count;
     if (count > hits->capacity) { fail(w->ctx, CANNON_E_CAPACITY, "hit arrays too small"); return done(CANNON_E_CAPACITY); }
     const size_t m = (size_t)count;
-    std::vector<int> r(m), bd(m), fc(m);
+    std::vector<int> r(m), bd(m), fc(m), in(m);
     std::vector<unsigned long long> key(m);
     std::vector<double> ds(m);
     std::vector<float4> pt(m), nm(m);
@@ -2582,12 +2584,13 @@ int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from,
       R_TRY(cudaMemcpy(fc.data(), aFace.p, m * sizeof(int), cudaMemcpyDeviceToHost)); R_TRY(cudaMemcpy(key.data(), aKey.p, m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
       R_TRY(cudaMemcpy(ds.data(), aDist.p, m * sizeof(double), cudaMemcpyDeviceToHost)); R_TRY(cudaMemcpy(pt.data(), aPoint.p, m * sizeof(float4), cudaMemcpyDeviceToHost));
       R_TRY(cudaMemcpy(nm.data(), aNormal.p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+      R_TRY(cudaMemcpy(in.data(), aInst.p, m * sizeof(int), cudaMemcpyDeviceToHost));
     }
     std::vector<int> ord(m);
     for (size_t k = 0; k < m; k++) ord[k] = (int)k;
     // the reference's callback sequence: ray by ray, bodies ascending, reports of a body in the order they were made
     std::sort(ord.begin(), ord.end(), [&](int a, int b) { return r[a] != r[b] ? r[a] < r[b] : key[a] < key[b]; });
-    for (size_t k = 0; k < m; k++) { const int i = ord[k]; put((int)k, r[i], bd[i], fc[i], ds[i], pt[i], nm[i]); }
+    for (size_t k = 0; k < m; k++) { const int i = ord[k]; put((int)k, r[i], bd[i], fc[i], ds[i], pt[i], nm[i], in[i]); }
   }
 #undef R_TRY
   return done(rc);

@@ -30,7 +30,8 @@ struct RayArgs {
   // RayMode.all: every report
   int* allCount;
   int allCap;
-  int *allRay, *allBody, *allFace;
+  int *allRay, *allBody, *allFace, *allInst;
+  int* inst;  // per ray: position of the hit shape in Body.shapes
   unsigned long long* allKey;
   double* allDist;
   float4 *allPoint, *allNormal;
@@ -43,6 +44,7 @@ struct RayLane {
   unsigned long long key, lastKey;
   f3 point, normal;
   int body, face, lastFace;
+  int inst, curInst;  // shape of the held report / shape being intersected (position in Body.shapes)
   bool any;  // lastKey is valid
 };
 
@@ -67,7 +69,7 @@ __device__ inline void ray_report(const RayArgs& A, RayLane& L, int ray, const f
   if (A.mode == CANNON_RAY_ALL) {
     const int k = atomicAdd(A.allCount, 1);
     if (k < A.allCap) {
-      A.allRay[k] = ray; A.allBody[k] = body; A.allFace[k] = face; A.allKey[k] = key; A.allDist[k] = distance;
+      A.allRay[k] = ray; A.allBody[k] = body; A.allFace[k] = face; A.allKey[k] = key; A.allDist[k] = distance; A.allInst[k] = L.curInst;
       A.allPoint[k] = st3(hit); A.allNormal[k] = st3(normal);
     }
   }
@@ -75,7 +77,7 @@ __device__ inline void ray_report(const RayArgs& A, RayLane& L, int ray, const f
   if (A.mode == CANNON_RAY_CLOSEST) take = !L.has || distance < L.dist;
   else if (A.mode == CANNON_RAY_ANY) take = !L.has;  // the earliest report of this lane
   else take = true;                                  // all: RaycastResult holds the latest report
-  if (take) { L.has = true; L.dist = distance; L.key = key; L.point = hit; L.normal = normal; L.body = body; L.face = face; }
+  if (take) { L.has = true; L.dist = distance; L.key = key; L.point = hit; L.normal = normal; L.body = body; L.face = face; L.inst = L.curInst; }
 }
 
 // Ray.pointInTriangle, ray_class.dart:696-708
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, Ra
     L.to = mk3(A.to[3 * ray], A.to[3 * ray + 1], A.to[3 * ray + 2]);
     L.dir = vsub(L.to, L.from);  // Ray._updateDirection, ray_class.dart:258-261
     vnormalize(L.dir);
-    L.has = false; L.any = false; L.dist = -1.0; L.key = ~0ull; L.lastKey = 0ull; L.body = -1; L.face = -1; L.lastFace = -1;
+    L.has = false; L.any = false; L.dist = -1.0; L.key = ~0ull; L.lastKey = 0ull; L.body = -1; L.face = -1; L.lastFace = -1; L.inst = -1; L.curInst = 0;
     L.point = mk3(0.0, 0.0, 0.0); L.normal = L.point;
     f3 lo, hi;  // Ray.getAABB, :329-342
     lo.x = fminf(L.to.x, L.from.x); lo.y = fminf(L.to.y, L.from.y); lo.z = fminf(L.to.z, L.from.z);
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, Ra
       int ord = 0;
       for (int k = k0; k < k1; k++) {  // Ray.intersectBody over body.shapes, :226-243
         if (A.mode == CANNON_RAY_ANY && L.has) break;  // result.shouldStop
+        L.curInst = k - k0;
         const ShapeDev s = T.shapes[T.instFirst ? T.instShape[k] : B.shape[b]];
         if (A.checkCollisionResponse && !s.collisionResponse) continue;
         q4 so; so.x = so.y = so.z = 0.f; so.w = 1.f;
@@ -252,6 +255,7 @@ __global__ void __launch_bounds__(128) k_raycast(BodyArrays B, ShapeTables T, Ra
     if (lane == src) {
       A.hasHit[ray] = anyHit ? 1 : 0;
       A.body[ray] = anyHit ? L.body : -1;
+      A.inst[ray] = anyHit ? L.inst : -1;
       A.dist[ray] = anyHit ? L.dist : -1.0;
       A.point[ray] = st3(anyHit ? L.point : mk3(0.0, 0.0, 0.0));
       A.normal[ray] = st3(anyHit ? L.normal : mk3(0.0, 0.0, 0.0));

@@ -302,10 +302,11 @@ class DeviceWorld:
         cap = max(n, 1) if mode != F.RAY_ALL else max(4 * n, 64)
         while True:
             out = dict(ray=np.zeros(cap, np.int32), body=np.zeros(cap, np.int32), hit_face_index=np.zeros(cap, np.int32), distance=np.zeros(cap),
-                       hit_point_world=np.zeros((cap, 3), np.float32), hit_normal_world=np.zeros((cap, 3), np.float32))
+                       hit_point_world=np.zeros((cap, 3), np.float32), hit_normal_world=np.zeros((cap, 3), np.float32), shape_ordinal=np.zeros(cap, np.int32))
             soa = F.RayHitsSoA(capacity=cap, ray=F.ptr(out["ray"], F.c_i32), body=F.ptr(out["body"], F.c_i32),
                                hit_face_index=F.ptr(out["hit_face_index"], F.c_i32), distance=F.ptr(out["distance"], F.c_f64),
-                               hit_point_world=F.ptr(out["hit_point_world"], F.c_f32), hit_normal_world=F.ptr(out["hit_normal_world"], F.c_f32))
+                               hit_point_world=F.ptr(out["hit_point_world"], F.c_f32), hit_normal_world=F.ptr(out["hit_normal_world"], F.c_f32),
+                               shape_ordinal=F.ptr(out["shape_ordinal"], F.c_i32))
             nh = F.c_i32()
             code = self.lib.cannon_world_raycast(self.handle, n, F.ptr(a, F.c_f32), F.ptr(b, F.c_f32), C.byref(opt), F.ptr(has, F.c_u8), C.byref(soa), C.byref(nh))
             if code == F.E_CAPACITY and nh.value > cap:

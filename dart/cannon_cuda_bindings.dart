@@ -217,6 +217,7 @@ final class CannonRayHitsSoa extends Struct {
   external Pointer<Double> distance;
   external Pointer<Float> hitPointWorld;
   external Pointer<Float> hitNormalWorld;
+  external Pointer<Int32> shapeOrdinal;
 }
 
 final class CannonBatchStatistics extends Struct {

@@ -362,7 +362,7 @@ class CudaWorld extends World {
       final hits = a<CannonRayHitsSoa>();
       hits.ref.capacity = 1;
       hits.ref.ray = a<Int32>(); hits.ref.body = a<Int32>(); hits.ref.hitFaceIndex = a<Int32>(); hits.ref.distance = a<Double>();
-      hits.ref.hitPointWorld = a<Float>(3); hits.ref.hitNormalWorld = a<Float>(3);
+      hits.ref.hitPointWorld = a<Float>(3); hits.ref.hitNormalWorld = a<Float>(3); hits.ref.shapeOrdinal = a<Int32>();
       final has = a<Uint8>(), n = a<Int32>();
       session.check(cuda.worldRaycast(session.handle, 1, pf, pt, opt, has, hits, n), 'cannon_world_raycast');
       final r = result ?? RaycastResult();
@@ -370,7 +370,7 @@ class CudaWorld extends World {
       if (has.value != 0) {
         final b = bodies[hits.ref.body.value];
         final hp = hits.ref.hitPointWorld, hn = hits.ref.hitNormalWorld;
-        r.set(f, t, Vector3(hn[0], hn[1], hn[2]), Vector3(hp[0], hp[1], hp[2]), b.shapes[0], b, hits.ref.distance.value);
+        r.set(f, t, Vector3(hn[0], hn[1], hn[2]), Vector3(hp[0], hp[1], hp[2]), b.shapes[hits.ref.shapeOrdinal.value], b, hits.ref.distance.value);
         r.hasHit = true;
         r.hitFaceIndex = hits.ref.hitFaceIndex.value;
       }

@@ -453,6 +453,7 @@ typedef struct cannon_ray_hits_soa {
   double*  distance;          /* RaycastResult.distance */
   float*   hit_point_world;   /* 3 per entry */
   float*   hit_normal_world;  /* 3 per entry */
+  int32_t* shape_ordinal;     /* RaycastResult.shape as its position in Body.shapes (0 for a single-shape body), -1 without a hit; may be NULL */
 } cannon_ray_hits_soa;
 void    cannon_ray_options_default(cannon_ray_options* o);
 int32_t cannon_world_raycast(cannon_world* w, int32_t n_rays, const float* from, const float* to, const cannon_ray_options* opt,

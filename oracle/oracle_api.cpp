@@ -772,6 +772,7 @@ int32_t cannon_world_raycast(cannon_world* cw, int32_t n_rays, const float* from
     if (hits->distance) hits->distance[k] = h.distance;
     if (hits->hit_point_world) PUTF3(hits->hit_point_world, k, h.hitPointWorld);
     if (hits->hit_normal_world) PUTF3(hits->hit_normal_world, k, h.hitNormalWorld);
+    if (hits->shape_ordinal) hits->shape_ordinal[k] = h.shapeOrdinal;
   };
   for (int r = 0; r < n_rays; r++) {
     RayHit res;

@@ -29,6 +29,7 @@ struct RayCtx {
   // RaycastResult (raycast_result.dart)
   bool hasHit = false, shouldStop = false;
   int body = -1, hitFaceIndex = -1;
+  int shapeOrdinal = -1, curShape = 0;  // result.shape (set with the result) / the shape being intersected
   double distance = -1;
   V3 hitNormalWorld{0, 0, 0}, hitPointWorld{0, 0, 0};
   std::vector<RayHit>* all = nullptr;
@@ -40,12 +41,12 @@ void report(RayCtx& r, const V3& normal, const V3& hitPointWorld, int body, int 
   const double distance = distance_to(r.from, hitPointWorld);
   if (r.skipBackfaces && dot(normal, r.direction) > 0) return;
   r.hitFaceIndex = hitFaceIndex;  // written for every reported intersection, whatever the mode does with it
-  auto set = [&]() { r.hitNormalWorld = normal; r.hitPointWorld = hitPointWorld; r.body = body; r.distance = distance; };
+  auto set = [&]() { r.hitNormalWorld = normal; r.hitPointWorld = hitPointWorld; r.body = body; r.distance = distance; r.shapeOrdinal = r.curShape; };
   switch (r.mode) {
     case CANNON_RAY_ALL:
       r.hasHit = true;
       set();
-      r.all->push_back(RayHit{r.rayIndex, body, hitFaceIndex, distance, hitPointWorld, normal});
+      r.all->push_back(RayHit{r.rayIndex, body, hitFaceIndex, distance, hitPointWorld, normal, r.curShape});
       break;
     case CANNON_RAY_CLOSEST:
       if (distance < r.distance || !r.hasHit) { r.hasHit = true; set(); }
@@ -198,6 +199,7 @@ bool World::raycast(int rayIndex, const V3& from, const V3& to, const cannon_ray
     if ((r.group & body.mask) == 0 || (body.group & r.mask) == 0) continue;
     for (size_t si = 0; si < body.shapes.size(); si++) {  // intersectBody, :226-243
       const Shape& shape = shapes[body.shapes[si]];
+      r.curShape = (int)si;
       if (r.checkCollisionResponse && !shape.collisionResponse) continue;
       const Q4 qi = qmul(body.quaternion, body.shapeOrientations[si]);
       const V3 xi = add(qvmult(body.quaternion, body.shapeOffsets[si]), body.position);
@@ -213,7 +215,7 @@ bool World::raycast(int rayIndex, const V3& from, const V3& to, const cannon_ray
       if (r.shouldStop) break;
     }
   }
-  out = RayHit{rayIndex, r.body, r.hitFaceIndex, r.distance, r.hitPointWorld, r.hitNormalWorld};
+  out = RayHit{rayIndex, r.body, r.hitFaceIndex, r.distance, r.hitPointWorld, r.hitNormalWorld, r.hasHit ? r.shapeOrdinal : -1};
   return r.hasHit;
 }
 

@@ -131,6 +131,7 @@ struct RayHit {  // one reported intersection (RaycastResult, lib/collision/rayc
   int ray, body, hitFaceIndex;
   double distance;
   V3 hitPointWorld, hitNormalWorld;
+  int shapeOrdinal = -1;  // RaycastResult.shape as its position in Body.shapes
 };
 
 struct RowDebug {

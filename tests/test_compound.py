@@ -85,7 +85,9 @@ def test_api_add_shape_builds_the_table_and_rays_see_every_shape(oracle_lib):
     world.step(1 / 60)
     res = api.RaycastResult()
     assert world.raycastClosest((-2, 5, 0), (-2, -5, 0), result=res) and abs(res.distance - 4.5) < 1e-5
+    assert res.shape is body.shapes[0]  # RaycastResult.shape: the shape that was hit, not the body's first
     assert world.raycastClosest((2, 5, 0), (2, -5, 0), result=res) and abs(res.distance - 4.5) < 1e-5
+    assert res.shape is body.shapes[1]
     assert not world.raycastClosest((0, 5, 0), (0, -5, 0), result=res)  # between the two shapes
 
 
@@ -186,9 +188,9 @@ def test_compound_rays_and_events_parity(cuda_lib, oracle_lib):
     to = frm + np.array([0.3, -8, -0.2], np.float32)
     for mode in (F.RAY_CLOSEST, F.RAY_ANY, F.RAY_ALL):
         a, b = dev.raycast(frm, to, mode=mode), ref.raycast(frm, to, mode=mode)
-        for k in ("has_hit", "body", "distance", "hit_point_world", "hit_normal_world", "hit_face_index"):
+        for k in ("has_hit", "body", "distance", "hit_point_world", "hit_normal_world", "hit_face_index", "shape_ordinal"):
             assert np.array_equal(a[k], b[k]), (mode, k)
-    assert a["n_hits"] > 20
+    assert a["n_hits"] > 20 and a["shape_ordinal"].max() > 0
 
 
 def _batch_spec(n_worlds=5, solver=None):

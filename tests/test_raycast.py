@@ -101,7 +101,7 @@ def test_cuda_raycasts_equal_the_oracle(cuda_lib, oracle_lib, name):
                 x = dev.raycast(a, b, mode=mode, skip_backfaces=skip)
                 y = ref.raycast(a, b, mode=mode, skip_backfaces=skip)
                 assert x["n_hits"] == y["n_hits"], (name, phase, mode, skip)
-                for k in ("has_hit", "ray", "body", "hit_face_index", "distance", "hit_point_world", "hit_normal_world"):
+                for k in ("has_hit", "ray", "body", "hit_face_index", "distance", "hit_point_world", "hit_normal_world", "shape_ordinal"):
                     assert np.array_equal(x[k], y[k]), (name, phase, mode, skip, k)
         assert x["n_hits"] > 10
         lo, hi = np.array([-1.5, -0.5, -1.5], np.float32), np.array([1.0, 2.5, 1.5], np.float32)
