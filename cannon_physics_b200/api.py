@@ -387,6 +387,17 @@ class Body:  # lib/objects/rigid_body.dart:26-86
             self.world._structure_dirty = True
         return self
 
+    def removeShape(self, shape: Shape) -> "Body":  # rigid_body.dart:371-391
+        for k, s in enumerate(self.shapes):
+            if s is shape:
+                self._before_write()
+                del self.shapes[k], self.shapeOffsets[k], self.shapeOrientations[k]
+                self._invInertia = None  # updateMassProperties (:383)
+                if self.world is not None:
+                    self.world._structure_dirty = True
+                return self
+        return self  # "Shape does not belong to the body": the reference logs a warning and returns
+
     def _before_write(self):
         """Every mutator starts here: after World.step(sync=False) the device holds the newer state, so it is pulled into
         the Body objects BEFORE the write - otherwise the next upload would roll the world back to stale host values."""

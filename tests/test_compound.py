@@ -89,6 +89,11 @@ def test_api_add_shape_builds_the_table_and_rays_see_every_shape(oracle_lib):
     assert world.raycastClosest((2, 5, 0), (2, -5, 0), result=res) and abs(res.distance - 4.5) < 1e-5
     assert res.shape is body.shapes[1]
     assert not world.raycastClosest((0, 5, 0), (0, -5, 0), result=res)  # between the two shapes
+    # Body.removeShape (rigid_body.dart:371-391): the sphere goes, the box stays where its offset put it
+    body.removeShape(body.shapes[0])
+    world.step(1 / 60)
+    assert not world.raycastClosest((-2, 5, 0), (-2, -5, 0), result=res)
+    assert world.raycastClosest((2, 5, 0), (2, -5, 0), result=res) and res.shape is body.shapes[0]
 
 
 def _table(k):
