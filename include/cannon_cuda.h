@@ -83,7 +83,9 @@ enum { CANNON_BODY_DYNAMIC = 0, CANNON_BODY_STATIC = 1, CANNON_BODY_KINEMATIC = 
 enum { CANNON_AWAKE = 0, CANNON_SLEEPY = 1, CANNON_SLEEPING = 2 };
 /* World.broadphase choices: NaiveBroadphase / SAPBroadphase / GridBroadphase */
 enum { CANNON_BP_NAIVE = 0, CANNON_BP_SAP = 1, CANNON_BP_GRID = 2 };
-#define CANNON_COLORED_UNIT_CONTACTS 4
+#ifndef CANNON_COLORED_UNIT_CONTACTS
+#define CANNON_COLORED_UNIT_CONTACTS 4   /* part of the COLORED order: changing it changes results (and the fixtures) */
+#endif
 /* World.solver choices.
  *   REFERENCE_ORDER: GSSolver with the reference's exact equation order
  *       (lib/world/world_class.dart:539-541,562,627-635); bit-reproducible validation mode.
