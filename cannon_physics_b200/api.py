@@ -29,7 +29,7 @@ __all__ = [
     "Vec3", "Quaternion", "Material", "ContactMaterial", "Shape", "Sphere", "Plane", "Box", "Cylinder", "ConvexPolyhedron", "Cone", "Capsule", "SizedPlane", "LatheShape", "CapsuleLathe", "Particle", "Trimesh", "SPHSystem",
     "Heightfield", "Body", "BodyTypes", "BodySleepStates", "Broadphase", "NaiveBroadphase", "SAPBroadphase", "GridBroadphase",
     "CudaBroadphase", "Solver", "GSSolver", "CudaGSSolver", "SplitSolver", "Constraint", "PointToPointConstraint", "HingeConstraint", "DistanceConstraint", "LockConstraint", "ConeTwistConstraint", "Spring",
-    "World",
+    "SpringConstraint", "RaycastResult", "World",
     "CudaWorld", "CannonError",
 ]
 
