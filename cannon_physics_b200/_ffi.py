@@ -57,7 +57,7 @@ class ShapeDesc(C.Structure):
         ("n_faces", c_i32), ("face_offsets", P(c_i32)), ("face_indices", P(c_i32)),
         ("hf_nx", c_i32), ("hf_ny", c_i32), ("hf_data", P(c_f64)), ("hf_element_size", c_i32),
         ("convex_has_axes", c_i32),
-        ("n_triangles", c_i32), ("tm_indices", P(c_i32)), ("tm_scale", c_f32 * 3),
+        ("n_triangles", c_i32), ("tm_indices", P(c_i32)), ("tm_scale", c_f32 * 3), ("material", c_i32),
     ]
 
 

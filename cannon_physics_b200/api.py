@@ -87,9 +87,10 @@ class ContactMaterial:  # lib/material/contact_material.dart:5
 class Shape:  # lib/rigid_body_shapes/shape.dart:28
     type = -1
 
-    def __init__(self, collisionResponse=True, collisionFilterGroup=-1, collisionFilterMask=-1):
+    def __init__(self, collisionResponse=True, collisionFilterGroup=-1, collisionFilterMask=-1, material: Optional["Material"] = None):
         self.collisionResponse = collisionResponse
         self.collisionFilterGroup, self.collisionFilterMask = collisionFilterGroup, collisionFilterMask
+        self.material = material  # shape.dart:48: overrides the body's material for this shape
 
     def _desc(self) -> dict:
         return dict(type=self.type, collision_response=int(self.collisionResponse), collision_filter_group=self.collisionFilterGroup,
@@ -800,7 +801,7 @@ class World:  # lib/world/world_class.dart:44
             for k, sh in enumerate(body.shapes):
                 if id(sh) not in shape_ids:
                     shape_ids[id(sh)] = len(shapes)
-                    shapes.append(sh._desc())
+                    shapes.append(dict(sh._desc(), material=mat_index(getattr(sh, "material", None))))
                 inst_shape.append(shape_ids[id(sh)])
                 inst_off.append(body.shapeOffsets[k])
                 inst_ori.append(body.shapeOrientations[k])

@@ -121,7 +121,7 @@ struct HostShape {
   int type = 0, collisionResponse = 1, group = -1, mask = -1;
   double radius = 0, bsr = 0;
   float he[3] = {0, 0, 0};
-  int hull = -1, hf = -1, tm = -1;
+  int hull = -1, hf = -1, tm = -1, material = -1;
 };
 
 struct cannon_world {
@@ -167,7 +167,7 @@ struct cannon_world {
   // SPHSystem subsystems (k_sph.cuh)
   struct HostSph { int n = 0; double density = 1, h = 1, cs = 1, viscosity = 0.01, eps = 0.00001; DBuf<int> particles; DBuf<double> densities, pressures; };
   std::vector<HostSph> sph;
-  bool hasParticle = false, hasTrimesh = false;
+  bool hasParticle = false, hasTrimesh = false, hasShapeMaterial = false;
   std::vector<TrimeshDev> hTms;
   std::vector<float4> hTmVerts, hTmNormals;
   std::vector<int> hTmIdx;
@@ -410,6 +410,7 @@ void cannon_shape_desc_default(cannon_shape_desc* d) {
   d->num_segments = 8;
   d->hf_element_size = 1;
   d->tm_scale[0] = d->tm_scale[1] = d->tm_scale[2] = 1.f;
+  d->material = -1;
 }
 
 int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out) {
@@ -555,6 +556,8 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     h.collisionResponse = d.collision_response != 0;
     h.group = d.collision_filter_group;
     h.mask = d.collision_filter_mask;
+    h.material = d.material;
+    if (h.material >= w->nMat) return fail(w->ctx, CANNON_E_INVALID, "shape references unknown material");
     switch (d.type) {
       case CANNON_SHAPE_SPHERE:
         if (d.radius < 0) return fail(w->ctx, CANNON_E_INVALID, "The sphere radius cannot be negative.");  // sphere.dart:16-18
@@ -670,7 +673,7 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
     const HostShape& h = w->hShapes[i];
     ShapeDev& d = shapes[i];
     d.type = h.type; d.collisionResponse = h.collisionResponse; d.group = h.group; d.mask = h.mask;
-    d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.tm = h.tm;
+    d.radius = h.radius; d.bsr = h.bsr; d.hx = h.he[0]; d.hy = h.he[1]; d.hz = h.he[2]; d.hull = h.hull; d.hf = h.hf; d.tm = h.tm; d.material = h.material; d.pad = 0;
   }
   std::vector<HullDev> hulls;
   w->hasOversizeHull = false;
@@ -734,6 +737,8 @@ int32_t cannon_world_set_shapes(cannon_world* w, int32_t n, const cannon_shape_d
   W_TRY(w, upload(w->dHfs, w->hHfs, s));
   W_TRY(w, upload(w->dHfData, w->hHfData, s));
   w->hasTrimesh = !w->hTms.empty();
+  w->hasShapeMaterial = false;
+  for (const HostShape& h : w->hShapes) if (h.material >= 0) w->hasShapeMaterial = true;
   if (w->hasTrimesh) {
     W_TRY(w, upload(w->dTms, w->hTms, s)); W_TRY(w, upload(w->dTmVerts, w->hTmVerts, s)); W_TRY(w, upload(w->dTmNormals, w->hTmNormals, s));
     W_TRY(w, upload(w->dTmIdx, w->hTmIdx, s));
@@ -1664,7 +1669,7 @@ static int32_t st_solve(cannon_world* w, double dt) {
     P.trace = w->gsTrace.p;
   }
   const int gc = grid_for(w, w->contactCap, 256);
-  { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p); }
+  { g_kernel_launches++; k_contact_flags<<<gc, 256, 0, s>>>(B, C, w->contactCap, w->fricFlag.p, w->contFlag.p, w->hasShapeMaterial ? w->dMatRestitution.p : nullptr); }
   W_TRY(w, scan_exclusive(w->fricFlag.p, w->fricOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_FRICTOTAL, w->scanTmp, s));
   W_TRY(w, scan_exclusive(w->contFlag.p, w->contOff.p, cnt + CT_NCONTACTS, 0, w->contactCap, cnt + CT_CONTTOTAL, w->scanTmp, s));
   { g_kernel_launches++; k_presolve<<<grid_for(w, w->n, 256), 256, 0, s>>>(B, w->n); }

@@ -1361,11 +1361,28 @@ __global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T
     int first, second;
     np_order(a, b, sa.type, sb.type, first, second);
     const ShapeDev s1 = (first == a) ? sa : sb, s2 = (first == a) ? sb : sa;
-    const int matA = B.material[first], matB = B.material[second];
+    int matA = B.material[first], matB = B.material[second];
     const cannon_contact_material* cm = &Wd.defaultCm;
     if (matA >= 0 && matB >= 0) {
       const int idx = T.cmTable[matA * T.nMat + matB];
       if (idx >= 0) cm = &T.cms[idx];
+    }
+    int fricA = matA, fricB = matB;
+    if (sa.material >= 0 || sb.material >= 0) {
+      // Shape.material (see cannon_shape_desc.material): the pair's contact material prefers the shapes' (narrow_phase.dart:
+      // 692-696); createContactEquation takes shape ?? body material in resolver order, a pillar convex has none (:517-518);
+      // the friction takes the shapes in PAIR order (c.si = rsi) with the bodies in RESOLVER order (c.bi) (:533-542)
+      if (sa.material >= 0 && sb.material >= 0) {
+        const int idx = T.cmTable[sa.material * T.nMat + sb.material];
+        if (idx >= 0) cm = &T.cms[idx];
+      }
+      const int m1 = s1.type == CANNON_SHAPE_HEIGHTFIELD ? -1 : s1.material, m2 = s2.type == CANNON_SHAPE_HEIGHTFIELD ? -1 : s2.material;
+      const bool pf = s2.type == CANNON_SHAPE_PARTICLE;              // c.bi = the particle's body
+      const int cbi = pf ? second : first, cbj = pf ? first : second;
+      fricA = sa.material >= 0 ? sa.material : B.material[cbi];
+      fricB = sb.material >= 0 ? sb.material : B.material[cbj];
+      if (m1 >= 0) matA = m1;
+      if (m2 >= 0) matB = m2;
     }
     const bool cr2 = (s2.type == CANNON_SHAPE_HEIGHTFIELD) ? true : (s2.collisionResponse != 0);  // pillar hulls default to true
     const int enabled = ((B.flags[first] & BF_COLLISION_RESPONSE) && (B.flags[second] & BF_COLLISION_RESPONSE) && s1.collisionResponse && cr2) ? 1 : 0;
@@ -1374,7 +1391,9 @@ __global__ void __launch_bounds__(256) k_np_finalize(BodyArrays B, ShapeTables T
     if (matA >= 0 && matB >= 0) {
       const double ra = T.matRestitution[matA], rb = T.matRestitution[matB];
       if (ra >= 0 && rb >= 0) restitution = ra * rb;
-      const double fa = T.matFriction[matA], fbb = T.matFriction[matB];
+    }
+    if (fricA >= 0 && fricB >= 0) {
+      const double fa = T.matFriction[fricA], fbb = T.matFriction[fricB];
       if (fa >= 0 && fbb >= 0) friction = fa * fbb;
     }
     const double h = Wd.dt;

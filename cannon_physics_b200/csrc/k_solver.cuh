@@ -216,10 +216,14 @@ __device__ inline void finish_row(const RowArrays& R, int row, int kind, const R
 
 // per contact: acceptance flags (Solver.addEquation filter, solver.dart:30-34) + wake-up flags (world_class.dart:564-590)
 __global__ void __launch_bounds__(256) k_contact_flags(BodyArrays B, ContactArrays C, int contactCap, int* __restrict__ fricFlag,
-                                                       int* __restrict__ contFlag) {
+                                                       int* __restrict__ contFlag, const double* __restrict__ matRestitution) {
   const int nc = min(*C.nContacts, contactCap);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int bi = C.bi[c], bj = C.bj[c];
+    if (matRestitution) {  // worlds with shape materials: World.internalStep overrides the restitution by the BODY materials (world_class.dart:556-560)
+      const int ma = B.material[bi], mb = B.material[bj];
+      if (ma >= 0 && mb >= 0 && matRestitution[ma] >= 0 && matRestitution[mb] >= 0) C.rest[c] = matRestitution[ma] * matRestitution[mb];
+    }
     const int fi = B.flags[bi], fj = B.flags[bj];
     const bool ok = C.enabled[c] && !(fi & BF_IS_TRIGGER) && !(fj & BF_IS_TRIGGER);
     contFlag[c] = ok ? 1 : 0;

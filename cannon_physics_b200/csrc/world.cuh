@@ -45,6 +45,7 @@ struct ShapeDev {
   int hull;  // index into hull table (box / convex / cylinder), -1 otherwise
   int hf;    // index into heightfield table, -1 otherwise
   int tm;    // index into trimesh table, -1 otherwise
+  int material, pad;  // Shape.material (index into the material table) or -1
 };
 
 struct HullDev {

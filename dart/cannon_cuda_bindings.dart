@@ -79,6 +79,7 @@ final class CannonShapeDesc extends Struct {
   @Int32() external int nTriangles;
   external Pointer<Int32> tmIndices;
   @Array(3) external Array<Float> tmScale;
+  @Int32() external int material;
 }
 
 final class CannonBodiesSoa extends Struct {

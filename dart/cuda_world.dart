@@ -104,7 +104,7 @@ class CudaSession {
       _materialIndex.clear();
       int mat(Material? m) => m == null ? -1 : _materialIndex.putIfAbsent(m, () => _materialIndex.length);
       for (final cm in world.contactmaterials) { mat(cm.materials[0]); mat(cm.materials[1]); }
-      for (final b in world.bodies) { mat(b.material); }
+      for (final b in world.bodies) { mat(b.material); for (final sh in b.shapes) { mat(sh.material); } }
       final nm = _materialIndex.length;
       final fr = a<Double>(nm + 1), re = a<Double>(nm + 1);
       _materialIndex.forEach((m, i) { fr[i] = m.friction; re[i] = m.restitution; });
@@ -132,6 +132,7 @@ class CudaSession {
         r.collisionResponse = s.collisionResponse ? 1 : 0;
         r.collisionFilterGroup = s.collisionFilterGroup;
         r.collisionFilterMask = s.collisionFilterMask;
+        r.material = mat(s.material);  // Shape.material (shape.dart:48), -1 = null
         if (s is Sphere) { r.radius = s.radius; }
         else if (s is Box) { _put3(r.halfExtents, s.halfExtents); }
         else if (s is Cylinder) { r.radiusTop = s.radiusTop; r.radiusBottom = s.radiusBottom; r.height = s.height; r.numSegments = s.numSegments; }

@@ -188,6 +188,15 @@ typedef struct cannon_shape_desc {
   int32_t n_triangles;
   const int32_t* tm_indices;
   float   tm_scale[3];
+  /* Shape.material (shape.dart:48) as an index into the material table, -1 = null (cannon_shape_desc_default sets -1).
+   * Reproduced as the reference uses it: the contact material of a shape pair is getContactMaterial(si.material,
+   * sj.material) when both shapes have one, else the bodies', else the default (narrow_phase.dart:692-696);
+   * createContactEquation takes `shape.material ?? body.material` of the shapes and bodies in resolver order (:517-521; a
+   * heightfield pillar has none), World.internalStep then overrides the restitution by the two BODY materials when both
+   * exist (world_class.dart:556-560); createFrictionEquationsFromContact pairs the shapes in PAIR order (c.si = rsi) with
+   * the bodies in RESOLVER order (c.bi), so a pair whose shapes arrive swapped mixes one body's shape material with the
+   * other body's body material (:541-542). */
+  int32_t material;
 } cannon_shape_desc;
 
 /* Body state, structure of arrays. In *_set_bodies a NULL pointer means "reference default"

@@ -71,6 +71,7 @@ void cannon_shape_desc_default(cannon_shape_desc* d) {
   d->num_segments = 8;
   d->hf_element_size = 1;
   d->tm_scale[0] = d->tm_scale[1] = d->tm_scale[2] = 1.f;
+  d->material = -1;
 }
 
 int32_t cannon_world_create(cannon_ctx* ctx, const cannon_world_desc* desc, cannon_world** out) {
@@ -118,6 +119,8 @@ int32_t cannon_world_set_shapes(cannon_world* cw, int32_t n, const cannon_shape_
     s.collisionResponse = d.collision_response != 0;
     s.group = d.collision_filter_group;
     s.mask = d.collision_filter_mask;
+    s.material = d.material;
+    if (s.material >= (int)w.matFriction.size()) return fail(cw->ctx, CANNON_E_INVALID, "shape references unknown material");
     switch (d.type) {
       case CANNON_SHAPE_SPHERE:
         if (d.radius < 0) return fail(cw->ctx, CANNON_E_INVALID, "The sphere radius cannot be negative.");

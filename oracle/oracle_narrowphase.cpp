@@ -24,6 +24,11 @@ namespace {
 struct NP {
   World& w;
   const cannon_contact_material* cm = nullptr;  // currentContactMaterial
+  // Shape.material of the shapes handed to the current resolver, by body (createContactEquation: `si.material ?? bi.material`;
+  // a heightfield pillar is a plain ConvexPolyhedron without material) and of the pair's shapes in pair order (c.si / c.sj = rsi / rsj)
+  int resBody[2] = {-1, -1}, resMat[2] = {-1, -1};
+  int rsiMat = -1, rsjMat = -1;
+  int shapeMatOf(int body) const { return body == resBody[0] ? resMat[0] : (body == resBody[1] ? resMat[1] : -1); }
   int manifold = 0;  // ordinal of the current resolver call (one sphereConvex / convexConvex call per heightfield pillar)
   explicit NP(World& w_) : w(w_) {}
 
@@ -41,7 +46,7 @@ struct NP {
     c.enabled = A.collisionResponse && B.collisionResponse && crA && crB;
     c.restitution = cm->restitution;
     c.setSpookParams(cm->contact_equation_stiffness, cm->contact_equation_relaxation, w.dt);
-    int matA = A.material, matB = B.material;  // shape materials: out of scope (always null)
+    int matA = shapeMatOf(bi) >= 0 ? shapeMatOf(bi) : A.material, matB = shapeMatOf(bj) >= 0 ? shapeMatOf(bj) : B.material;  // :517-518
     if (matA >= 0 && matB >= 0 && w.matRestitution[matA] >= 0 && w.matRestitution[matB] >= 0)
       c.restitution = w.matRestitution[matA] * w.matRestitution[matB];
     return c;
@@ -52,7 +57,7 @@ struct NP {
     const Body& A = w.bodies[c.bi];
     const Body& B = w.bodies[c.bj];
     double friction = cm->friction;
-    int matA = A.material, matB = B.material;
+    int matA = rsiMat >= 0 ? rsiMat : A.material, matB = rsjMat >= 0 ? rsjMat : B.material;  // shapeA = c.si = rsi, bodyA = c.bi (:533-542)
     if (matA >= 0 && matB >= 0 && w.matFriction[matA] >= 0 && w.matFriction[matB] >= 0)
       friction = w.matFriction[matA] * w.matFriction[matB];
     c.friction = friction;
@@ -872,6 +877,9 @@ struct NP {
   void resolve(Shape& sa, Shape& sb, V3 xa, V3 xb, Q4 qa, Q4 qb, int ba, int bb) {
     const int ta = sa.type, tb = sb.type;
     manifold++;
+    resBody[0] = ba; resBody[1] = bb;
+    resMat[0] = ta == CANNON_SHAPE_HEIGHTFIELD ? -1 : sa.material;  // the pillar convex carries no material
+    resMat[1] = tb == CANNON_SHAPE_HEIGHTFIELD ? -1 : sb.material;
     if (tb == CANNON_SHAPE_TRIMESH) {  // narrow_phase.dart:212-238; heightfield-trimesh has no key
       if (ta == CANNON_SHAPE_SPHERE) sphereTrimesh(sa, sb, xa, xb, qb, ba, bb);
       else if (ta == CANNON_SHAPE_PLANE) planeTrimesh(sa, sb, xa, xb, qa, qb, ba, bb);
@@ -942,7 +950,9 @@ void World::getContacts() {
         const V3 xj = add(qvmult(B.quaternion, B.shapeOffsets[j]), B.position);
         if (!((si.mask & sj.group) != 0 && (sj.mask & si.group) != 0)) continue;
         if (distance_to(xi, xj) > si.boundingSphereRadius + sj.boundingSphereRadius) continue;
-        np.cm = bodyCm ? bodyCm : &desc.default_contact_material;
+        const cannon_contact_material* shapeCm = (si.material >= 0 && sj.material >= 0) ? contactMaterial(si.material, sj.material) : nullptr;  // :692-696
+        np.cm = shapeCm ? shapeCm : (bodyCm ? bodyCm : &desc.default_contact_material);
+        np.rsiMat = si.material; np.rsjMat = sj.material;
         if (justTest) {
           // justTest mode (:706-716): no equations; the resolver returns true where it would have created its first contact
           // (every `if (justTest) return true` sits right before a createContactEquation), and the world only uses that to

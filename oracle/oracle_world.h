@@ -36,6 +36,7 @@ struct Shape {
   int type = CANNON_SHAPE_SPHERE;
   bool collisionResponse = true;
   int group = -1, mask = -1;
+  int material = -1;  // Shape.material (index into the material table) or -1 = null
   double boundingSphereRadius = 0;
   double radius = 1;  // sphere
   V3 halfExtents{0, 0, 0};
